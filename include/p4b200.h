@@ -1,0 +1,215 @@
+/* p4b200.h -- C ABI of the B200 Felsenstein-pruning likelihood engine.
+ *
+ * This is the drop-in boundary for ONE path of pgfoster/p4-phylogenetics: the
+ * likelihood engine behind the CPython extension `p4.pf` (Pf/pfmodule.c).  Every
+ * entry point below replaces one `pf.*` wrapper of the reference and keeps its
+ * argument order and meaning; the citation after each prototype is the
+ * reference wrapper it stands in for.  Handles are opaque pointers that the
+ * Python side stores as integers, exactly like the reference's
+ * Py_BuildValue("l", ptr) convention (Pf/pfmodule.c:1405, 1455, 1530).
+ *
+ * Plain C types only: no CUDA, PyTorch or C++ types cross this boundary.
+ *
+ * Borrowed buffers.  Like the reference (Pf/p4_model.c:339, 504-506;
+ * Pf/p4_tree.c:46-49) the engine KEEPS the raw pointers of these caller-owned
+ * arrays and re-reads them on every compute call, because p4's Python code
+ * mutates them in place without calling a setter:
+ *   comp val[dim]; gdasrv val[1], freqs[nCat], rates[nCat];
+ *   bQETneedsReset[nComps*nRMatrices] (int32); preOrder/postOrder[nNodes]
+ *   (int32); partLikes[nParts]; the model limit arrays.
+ * The caller must keep them alive until the owning object is freed.
+ *
+ * Errors.  The reference prints a message and calls exit(1) on internal errors
+ * (e.g. Pf/p4_tree.c:436, 495).  A library must not end the host process, so
+ * functions that can fail return int (0 = ok, nonzero = fatal) or a NULL
+ * handle, and the message is available from p4b_lastError().  The Python `pf`
+ * mirror turns that into an exception whose default outcome is process exit
+ * status 1.  The numerical sentinel is unchanged: a non-positive site
+ * likelihood makes the part log-likelihood -1.0e99 (Pf/p4_tree.c:1182).
+ *
+ * There is NO CPU fallback for the compute entry points: without a usable
+ * CUDA device they fail with an error.
+ */
+#ifndef P4B200_H
+#define P4B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *p4b_data;
+typedef void *p4b_part;
+typedef void *p4b_model;
+typedef void *p4b_gdasrv;
+typedef void *p4b_tree;
+typedef void *p4b_node;
+
+#define P4B_NO_ORDER (-10000)        /* Pf/defines.h:66, p4/var.py:109 */
+#define P4B_GAP_CODE (-1)            /* Pf/defines.h:33 */
+#define P4B_QMARK_CODE (-2)          /* Pf/defines.h:34 */
+#define P4B_EQUATES_BASE (-64)       /* Pf/defines.h:36 */
+#define P4B_BAD_LIKE (-1.0e99)       /* Pf/p4_tree.c:1182 */
+
+/* ---- engine ------------------------------------------------------------- */
+const char *p4b_version(void);
+const char *p4b_lastError(void);
+/* Number of usable CUDA devices (0 on a CPU-only host; never an error). */
+int p4b_deviceCount(void);
+/* Bind this process to one CUDA device.  Must precede the first p4b_newTree. */
+int p4b_setDevice(int device);
+/* Pattern sharding for one-process-per-GPU runs: this
+ * process keeps patterns [lo,hi) of every part on its device, with
+ * lo = floor(nPatterns*rank/world).  Default rank 0 of 1.  Call before
+ * p4b_newTree. */
+int p4b_setShard(int rank, int world);
+/* NCCL communicator over the shard ranks.  p4b_commGetUniqueId fills a
+ * 128-byte id on rank 0; the host program ships it to the other ranks by any
+ * means and every rank calls p4b_commInitRank.  With a communicator present
+ * p4b_partLogLike / p4b_treeLogLike return the all-reduced (global) value. */
+int p4b_commGetUniqueId(char id128[128]);
+int p4b_commInitRank(const char id128[128], int rank, int world);
+int p4b_commDestroy(void);
+/* Count of engine kernel launches since process start (bench.py gpu_launches). */
+long long p4b_kernelLaunchCount(void);
+
+/* ---- data parts --------------------------------------------- Pf/part.c -- */
+p4b_data p4b_newData(int nTax, int nParts);                              /* pf.newData, Pf/pfmodule.c:29 */
+void p4b_freeData(p4b_data d);                                           /* pf.freeData :43 */
+int p4b_pokePartInData(p4b_part p, p4b_data d, int i);                   /* pf.pokePartInData :73 */
+p4b_part p4b_newPart(int nTax, int nChar, const char *equateSymbols, int nEquates,
+                     const char *symbols, int dim);                      /* pf.newPart :112 */
+void p4b_freePart(p4b_part p);                                           /* pf.freePart :134 */
+int p4b_pokeEquatesTable(p4b_part p, const char *table);                 /* pf.pokeEquatesTable :151, Pf/part.c:279 */
+int p4b_pokeSequences(p4b_part p, const char *allSequences);             /* pf.pokeSequences :169, Pf/part.c:127 */
+int p4b_makePatterns(p4b_part p);                                        /* pf.makePatterns :186, Pf/part.c:317 */
+int p4b_setGlobalInvarSitesVec(p4b_part p);                              /* pf.setGlobalInvarSitesVec :310, Pf/part.c:716 */
+int p4b_partPatternCount(p4b_part p);                                    /* pf.partPatternCount :247 */
+/* pf.getSiteLikes :378 -- copies part->siteLikes (nChar doubles) filled by the
+ * last p4b_partLogLike(..., getSiteLikes=1).  Returns nChar, or -1 if none. */
+int p4b_getSiteLikes(p4b_part p, double *out, int nOut);
+/* Read-only views of the host arrays of struct partStruct (Pf/pftypes.h:31-53),
+ * for bit-exact parity checks.  Row-major, same shapes as the reference:
+ * sequences/patterns [nTax][nChar] (patterns valid for columns < nPatterns),
+ * patternCounts / sequencePositionPatternIndex / globalInvarSitesVec [nChar],
+ * globalInvarSitesArray [dim][nChar], equates [nEquates][dim]. */
+const int *p4b_partSequences(p4b_part p);
+const int *p4b_partPatterns(p4b_part p);
+const int *p4b_partPatternCounts(p4b_part p);
+const int *p4b_partSequencePositionPatternIndex(p4b_part p);
+const int *p4b_partGlobalInvarSitesVec(p4b_part p);
+const int *p4b_partGlobalInvarSitesArray(p4b_part p);
+const int *p4b_partEquates(p4b_part p);
+int p4b_partNChar(p4b_part p);
+int p4b_partNTax(p4b_part p);
+int p4b_partDim(p4b_part p);
+
+/* ---- model ------------------------------------------------ Pf/p4_model.c -- */
+p4b_model p4b_newModel(int nParts, int doRelRates, int relRatesAreFree, int nFreePrams, int isHet,
+                       int *rMatrixNormalizeTo1,
+                       double *PINVAR_MIN, double *PINVAR_MAX, double *KAPPA_MIN, double *KAPPA_MAX,
+                       double *GAMMA_SHAPE_MIN, double *GAMMA_SHAPE_MAX, double *PIVEC_MIN, double *PIVEC_MAX,
+                       double *RATE_MIN, double *RATE_MAX, double *RELRATE_MIN, double *RELRATE_MAX,
+                       double *BRLEN_MIN, double *BRLEN_MAX);            /* pf.p4_newModel :1484 */
+void p4b_freeModel(p4b_model m);                                         /* pf.p4_freeModel :1554 */
+int p4b_newModelPart(p4b_model m, int pNum, int dim, int nComps, int nRMatrices, int nGdasrvs,
+                     int nCat, int pInvarFree, int *bQETneedsReset);     /* pf.p4_newModelPart :1590 */
+int p4b_newComp(p4b_model m, int pNum, int mNum, int isFree, double *val);          /* pf.p4_newComp :1634 */
+int p4b_newRMatrix(p4b_model m, int pNum, int mNum, int isFree, int spec);          /* pf.p4_newRMatrix :1653 */
+p4b_gdasrv p4b_newGdasrv(p4b_model m, int pNum, int mNum, int nCat, int isFree,
+                         double *val, double *freqs, double *rates);                /* pf.p4_newGdasrv :1672 */
+int p4b_gdasrvCalcRates(p4b_gdasrv g);                                   /* pf.gdasrvCalcRates :1813 */
+int p4b_gdasrvCalcRates_np(int nCat, double alpha, double *freqs, double *rates);   /* pf.gdasrvCalcRates_np :1836 */
+int p4b_setRMatrixBigR(p4b_model m, int pNum, int rNum, int i, int j, double val);  /* pf.p4_setRMatrixBigR :1720 */
+int p4b_setKappa(p4b_model m, int pNum, int rNum, double val);           /* pf.p4_setKappa :1741 */
+int p4b_setPInvarVal(p4b_model m, int pNum, double val);                 /* pf.p4_setPInvarVal :1871 */
+int p4b_setRelRateVal(p4b_model m, int pNum, double val);                /* pf.p4_setRelRateVal :1887 */
+int p4b_resetBQET(p4b_model m, int pNum, int compNum, int rMatrixNum);   /* pf.p4_resetBQET :1613, Pf/p4_model.c:513 */
+double p4b_getRelRate(p4b_model m, int pNum);                            /* pf.p4_getRelRate :2316 */
+/* pf.getBigQ :1238 -- copy the cached, normalised Q of (comp,rMatrix): dim*dim doubles, row-major [from][to]. */
+int p4b_getBigQ(p4b_model m, int pNum, int compNum, int rMatrixNum, double *out);
+/* pf.getBigR :1271 -- the 20x20 empirical protein exchangeability table for an
+ * RMATRIX_* spec code (Pf/defines.h:9-29), row-major. */
+int p4b_getBigR(int spec, double *out400);
+/* The current bigR of one rMatrix of the model: dim*dim doubles (inspection). */
+int p4b_getModelBigR(p4b_model m, int pNum, int rMatrixNum, double *out);
+
+/* ---- tree and nodes -------------------------------- Pf/p4_tree.c, p4_node.c -- */
+p4b_tree p4b_newTree(int nNodes, int nLeaves, int *preOrder, int *postOrder,
+                     int *newtAndBrentPowellOptPassLimit, double *partLikes,
+                     p4b_data d, p4b_model m);                           /* pf.p4_newTree :1383 */
+void p4b_freeTree(p4b_tree t);                                           /* pf.p4_freeTree :1410 */
+p4b_node p4b_newNode(int nodeNum, p4b_tree t, int seqNum, int isLeaf, int inTree);  /* pf.p4_newNode :1443 */
+void p4b_freeNode(p4b_node n);                                           /* pf.p4_freeNode :1460 */
+/* relation: 0 parent, 1 leftChild, 2 sibling; relNum = nodeNum of the relative or -1 for none. */
+int p4b_setNodeRelation(p4b_node n, int relation, int relNum);           /* pf.p4_setNodeRelation :1907 */
+int p4b_setTreeRoot(p4b_tree t, p4b_node n);                             /* pf.p4_setTreeRoot :1944 */
+int p4b_setBrLen(p4b_node n, double brLen);                              /* pf.p4_setBrLen :1960 */
+int p4b_setCompNum(p4b_node n, int pNum, int val);                       /* pf.p4_setCompNum :2013 */
+int p4b_setRMatrixNum(p4b_node n, int pNum, int val);                    /* pf.p4_setRMatrixNum :2029 */
+int p4b_setGdasrvNum(p4b_node n, int pNum, int val);                     /* pf.p4_setGdasrvNum :2045 */
+double p4b_getTreeLen(p4b_tree t);                                       /* pf.p4_getTreeLen :1978 */
+
+/* ---- the hot path ------------------------------------------------------- */
+/* pf.p4_setPrams(tree, pNum|-1) :2086 -> p4_setPramsPart, Pf/p4_tree.c:218-541.
+ * Host: gamma rates of free gdasrvs, 2-parameter R, comp checks, Q + eigensystem
+ * for every (comp,rMatrix) used by a non-root node.  Device: the batched P(t)
+ * kernel for every non-root node of the part(s).  Asynchronous. */
+int p4b_setPrams(p4b_tree t, int pNum);
+/* pf.p4_calculateBigPDecks(node) :2165 -> Pf/p4_node.c:286-346 (all parts). */
+int p4b_calculateBigPDecks(p4b_node n);
+/* pf.p4_calculateAllBigPDecksAllParts(tree) :2180. */
+int p4b_calculateAllBigPDecksAllParts(p4b_tree t);
+/* pf.p4_setConditionalLikelihoodsOfInternalNodePart(node, pNum) :2195
+ * -> Pf/p4_node.c:636-857.  Enqueues the CL kernel for one node; asynchronous. */
+int p4b_setConditionalLikelihoodsOfInternalNodePart(p4b_node n, int pNum);
+/* pf.p4_partLogLike(tree, part, pNum, getSiteLikes) :2147 -> Pf/p4_tree.c:924-1197.
+ * Synchronises; writes partLikes[pNum]; returns the part lnL (or -1.0e99). */
+double p4b_partLogLike(p4b_tree t, p4b_part p, int pNum, int getSiteLikes);
+/* pf.p4_treeLogLike(tree, getSiteLikes) :2132 -> Pf/p4_tree.c:868-922.
+ * Recomputes the CL of EVERY internal node in postOrder, then all parts. */
+double p4b_treeLogLike(p4b_tree t, int getSiteLikes);
+
+/* ---- cur/prop state transfer ------------------------ Pf/p4_treeCopyVerify.c -- */
+int p4b_copyCondLikes(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyCondLikes :2445, Pf/p4_treeCopyVerify.c:7 */
+int p4b_copyBigPDecks(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyBigPDecks :2462, :33 */
+int p4b_copyModelPrams(p4b_tree a, p4b_tree b);                          /* pf.p4_copyModelPrams :2479, :63 */
+/* 0 = same, 1 = different (epsilon 1e-15, Pf/p4_node.c:1406). */
+int p4b_verifyIdentityOfTwoTrees(p4b_tree a, p4b_tree b);                /* pf.p4_verifyIdentityOfTwoTrees :2431, :187 */
+
+/* ---- inspection (parity tests, profiling) ------------------------------- */
+/* Number of patterns of part pNum resident on this process's device and the
+ * global index of the first one (the shard [lo,hi) of p4b_setShard). */
+int p4b_treeShardRange(p4b_tree t, int pNum, int *lo, int *hi);
+/* Download one node's CL of part pNum in the reference layout
+ * cl[cat][state][pattern] (Pf/pftypes.h:133), shard patterns only:
+ * nCat*dim*(hi-lo) doubles.  Synchronises. */
+int p4b_getNodeCL(p4b_node n, int pNum, double *out);
+/* Download one node's transition matrices bigPDecks[cat][from][to]:
+ * nCat*dim*dim doubles.  Synchronises. */
+int p4b_getNodeBigP(p4b_node n, int pNum, double *out);
+/* Test hook: overwrite one node's transition matrices with nCat*dim*dim given
+ * doubles (the leaf lookup table is rebuilt from them).  Lets a parity test hold
+ * P identical to the reference's and compare the CL kernels alone. */
+int p4b_setNodeBigP(p4b_node n, int pNum, const double *in);
+/* Eigen-decomposition cached for (comp,rMatrix): eigvecs, inverseEigvecs
+ * (dim*dim each, row-major) and eigvals (dim).  Any may be NULL. */
+int p4b_getEig(p4b_model m, int pNum, int compNum, int rMatrixNum,
+               double *eigvecs, double *inverseEigvecs, double *eigvals);
+/* Wait for every kernel enqueued on the tree's stream. */
+int p4b_treeSync(p4b_tree t);
+/* Device-side timing on the tree's stream (CUDA events): call Begin, enqueue
+ * work through the entry points above, call End; returns milliseconds. */
+int p4b_treeTimerBegin(p4b_tree t);
+double p4b_treeTimerEnd(p4b_tree t);
+/* Timing of the last p4b_treeLogLike on the tree: total ms of the CL kernels
+ * and their count (CUDA events around the CL section on the tree's stream). */
+int p4b_treeLastCLTiming(p4b_tree t, double *ms, int *nLaunches);
+/* Bytes of device memory held by the tree (CL arena + P decks). */
+long long p4b_treeDeviceBytes(p4b_tree t);
+/* Write a buffer larger than L2 (bench.py: L2 flush between timed steps). */
+int p4b_flushL2(p4b_tree t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P4B200_H */

@@ -1,0 +1,382 @@
+// kernels.cuh -- sm_100a FP64 kernels of the likelihood path.
+//
+//   pmatrix_kernel   batched P(t) = V exp(Lt) V^-1       (Pf/eig.c:163-191, Pf/p4_node.c:296-346)
+//   cl_dna_kernel    CL update, 4 states, pattern pairs  (Pf/p4_node.c:636-857)
+//   cl_dim_kernel    CL update, DIM states in registers
+//   cl_generic_kernel CL update, any dim <= 64
+//   like_kernel / like_final_kernel  per-part lnL        (Pf/p4_tree.c:1029-1197, 1199-1378)
+//
+// Memory layout (all in HBM, per tree and part):
+//   CL of a node      cl[k][pat], k = cat*dim + state, row stride `ps` doubles
+//                     (ps = shard pattern count padded to a multiple of 32, so
+//                     rows are 256-byte aligned).  Same index order as the
+//                     reference's cl[part][cat][state][pattern] (Pf/pftypes.h:133).
+//   P deck of a node  P[cat][from][to] row-major, as bigPDecks (Pf/pftypes.h:130).
+//   leaf table        T[k][w], w = tip code index: w < dim a state (P[s][w]),
+//                     w == dim "matches all" (1.0), w > dim an ambiguity
+//                     (sum of P[s][x] over its states, Pf/p4_node.c:705-716).
+//   tips              one byte per (taxon, pattern): the tip code index.
+#pragma once
+#include <cstdint>
+
+namespace p4b {
+
+constexpr int kMaxChildren = 6;    // children folded into one CL launch; more are chained
+
+struct PJob {
+    long long pOff;     // into the tree's P deck (doubles)
+    long long tblOff;   // into the tree's leaf tables (doubles); used when tblW > 0
+    long long eigOff;   // into the tree's eigensystem mirror: V | Vinv | lambda
+    long long eqOff;    // into the tree's equate masks
+    int dim, nCat, tblW, nRealEq;
+    long long tOff;     // into the staged doubles: t[cat] effective branch lengths
+};
+
+struct CLChild {
+    const double *cl;     // internal child: its CL
+    const double *P;      // internal child: its P deck
+    const uint8_t *tips;  // leaf child: tip code indices of its sequence
+    const double *tbl;    // leaf child: its lookup table
+};
+
+struct CLArgs {
+    double *out;
+    int nChildren;
+    int accumulate;   // multiply into the existing CL (continuation of a >kMaxChildren node)
+    int ps;           // pattern stride (multiple of 32)
+    int dim, nCat, tblW;
+    CLChild ch[kMaxChildren];
+};
+
+struct LikeArgs {
+    const double *cl;          // root CL
+    const int *counts;
+    const uint64_t *invarMask;
+    const uint8_t *rootTips;   // non-NULL when the root is a leaf
+    const uint64_t *eqMask;    // masks of the non-N-like equates
+    double *patLikes;          // optional [ps]
+    double *partials;          // [2*gridDim.x]: sum count*log(like), count of like <= 0
+    int ps, nPat, dim, nCat;
+    double pInvar;
+    double pi[64];
+};
+
+// ---------------------------------------------------------------------------
+// P(t)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged, const double *__restrict__ eig,
+               const uint64_t *__restrict__ eqMasks, double *__restrict__ Pdeck, double *__restrict__ tbl)
+{
+    extern __shared__ double sExp[];   // [nCat][dim] exp(lambda_k * t_cat)
+    const PJob job = jobs[blockIdx.x];
+    const int dim = job.dim, nCat = job.nCat;
+    const double *V = eig + job.eigOff;
+    const double *Vi = V + dim * dim;
+    const double *lam = Vi + dim * dim;
+    const double *t = staged + job.tOff;
+    for (int i = threadIdx.x; i < nCat * dim; i += blockDim.x) sExp[i] = exp(lam[i % dim] * t[i / dim]);
+    __syncthreads();
+    double *P = Pdeck + job.pOff;
+    const int n = nCat * dim * dim;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int c = idx / (dim * dim), ij = idx - c * dim * dim, i = ij / dim, j = ij - i * dim;
+        double sum = 0.0;
+        // same association as the reference: sum += (V[i][k] * Vinv[k][j]) * exp(.)
+        for (int k = 0; k < dim; k++) sum = fma(__dmul_rn(V[i * dim + k], Vi[k * dim + j]), sExp[c * dim + k], sum);
+        P[idx] = sum;
+    }
+    if (job.tblW > 0) {
+        __syncthreads();   // the block's own global writes of P are visible after the barrier
+        const int W = job.tblW;
+        double *T = tbl + job.tblOff;
+        const uint64_t *em = eqMasks + job.eqOff;
+        const int nT = nCat * dim * W;
+        for (int idx = threadIdx.x; idx < nT; idx += blockDim.x) {
+            const int k = idx / W, w = idx - k * W;   // k = cat*dim + s
+            double v;
+            if (w < dim) v = P[k * dim + w];
+            else if (w == dim) v = 1.0;
+            else {
+                const uint64_t m = em[w - dim - 1];
+                v = 0.0;
+                for (int x = 0; x < dim; x++)
+                    if ((m >> x) & 1ull) v += P[k * dim + x];
+            }
+            T[idx] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CL, 4 states.  One thread owns two adjacent patterns and all NCAT*4 entries;
+// every global access is a 16-byte vector, 512 contiguous bytes per warp.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+template <int NCAT>
+__global__ void __launch_bounds__(256)
+cl_dna_kernel(const CLArgs a)
+{
+    constexpr int K = NCAT * 4;
+    extern __shared__ double sm[];   // per child: P[NCAT][4][4] (internal) or T[K][tblW] (leaf)
+    const int W = a.tblW;
+    const int perChild = (K * W > K * 4) ? K * W : K * 4;
+    for (int c = 0; c < a.nChildren; c++) {
+        const bool leaf = a.ch[c].tips != nullptr;
+        const double *src = leaf ? a.ch[c].tbl : a.ch[c].P;
+        const int n = leaf ? K * W : K * 4;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sm[c * perChild + i] = src[i];
+    }
+    __syncthreads();
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pat = pair * 2;
+    if (pat >= a.ps) return;
+    const size_t ps = (size_t)a.ps;
+
+    double2 acc[K];
+    if (a.accumulate) {
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = ld2(a.out + k * ps + pat);
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxChildren; c++) {
+        if (c < a.nChildren) {
+            const bool first = (c == 0) && !a.accumulate;
+            const double *s = sm + c * perChild;
+            if (a.ch[c].tips == nullptr) {
+                const double *cl = a.ch[c].cl + pat;
+#pragma unroll
+                for (int cat = 0; cat < NCAT; cat++) {
+                    const double2 v0 = ld2(cl + (cat * 4 + 0) * ps);
+                    const double2 v1 = ld2(cl + (cat * 4 + 1) * ps);
+                    const double2 v2 = ld2(cl + (cat * 4 + 2) * ps);
+                    const double2 v3 = ld2(cl + (cat * 4 + 3) * ps);
+#pragma unroll
+                    for (int st = 0; st < 4; st++) {
+                        const double2 p01 = *reinterpret_cast<const double2 *>(s + cat * 16 + st * 4);
+                        const double2 p23 = *reinterpret_cast<const double2 *>(s + cat * 16 + st * 4 + 2);
+                        double2 sum;
+                        sum.x = p01.x * v0.x;
+                        sum.y = p01.x * v0.y;
+                        sum.x = fma(p01.y, v1.x, sum.x);
+                        sum.y = fma(p01.y, v1.y, sum.y);
+                        sum.x = fma(p23.x, v2.x, sum.x);
+                        sum.y = fma(p23.x, v2.y, sum.y);
+                        sum.x = fma(p23.y, v3.x, sum.x);
+                        sum.y = fma(p23.y, v3.y, sum.y);
+                        const int k = cat * 4 + st;
+                        if (first) acc[k] = sum;
+                        else { acc[k].x *= sum.x; acc[k].y *= sum.y; }
+                    }
+                }
+            } else {
+                const uchar2 code = *reinterpret_cast<const uchar2 *>(a.ch[c].tips + pat);
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const double fx = s[k * W + code.x], fy = s[k * W + code.y];
+                    if (first) { acc[k].x = fx; acc[k].y = fy; }
+                    else { acc[k].x *= fx; acc[k].y *= fy; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) st2(a.out + k * ps + pat, acc[k]);
+}
+
+// ---------------------------------------------------------------------------
+// CL, DIM states held in registers.  grid.y = rate category; one thread owns
+// one pattern of one category; P / leaf tables of that category sit in shared
+// memory and are read as warp-wide broadcasts.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128)
+cl_dim_kernel(const CLArgs a)
+{
+    extern __shared__ double sm[];   // per child: P[DIM][DIM] or T[DIM][tblW] of this category
+    const int cat = blockIdx.y;
+    const int W = a.tblW;
+    const int perChild = (DIM * W > DIM * DIM) ? DIM * W : DIM * DIM;
+    for (int c = 0; c < a.nChildren; c++) {
+        const bool leaf = a.ch[c].tips != nullptr;
+        const double *src = leaf ? a.ch[c].tbl + (size_t)cat * DIM * W : a.ch[c].P + (size_t)cat * DIM * DIM;
+        const int n = leaf ? DIM * W : DIM * DIM;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sm[c * perChild + i] = src[i];
+    }
+    __syncthreads();
+    const int pat = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pat >= a.ps) return;
+    const size_t ps = (size_t)a.ps;
+    const size_t base = (size_t)cat * DIM * ps + pat;
+
+    double acc[DIM];
+    if (a.accumulate) {
+#pragma unroll
+        for (int s = 0; s < DIM; s++) acc[s] = a.out[base + s * ps];
+    }
+    for (int c = 0; c < a.nChildren; c++) {
+        const bool first = (c == 0) && !a.accumulate;
+        const double *sp = sm + c * perChild;
+        if (a.ch[c].tips == nullptr) {
+            double v[DIM];
+            const double *cl = a.ch[c].cl + base;
+#pragma unroll
+            for (int x = 0; x < DIM; x++) v[x] = cl[x * ps];
+#pragma unroll
+            for (int s = 0; s < DIM; s++) {
+                double sum = sp[s * DIM] * v[0];
+#pragma unroll
+                for (int x = 1; x < DIM; x++) sum = fma(sp[s * DIM + x], v[x], sum);
+                acc[s] = first ? sum : acc[s] * sum;
+            }
+        } else {
+            const int code = a.ch[c].tips[pat];
+#pragma unroll
+            for (int s = 0; s < DIM; s++) {
+                const double f = sp[s * W + code];
+                acc[s] = first ? f : acc[s] * f;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < DIM; s++) a.out[base + s * ps] = acc[s];
+}
+
+// ---------------------------------------------------------------------------
+// CL, any dim.  grid.y = rate category; one thread per pattern; child values
+// are re-read per parent state (served by L1).  Correctness path for unusual
+// state counts (2, 6-state recodings, ...).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cl_generic_kernel(const CLArgs a)
+{
+    const int cat = blockIdx.y;
+    const int pat = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pat >= a.ps) return;
+    const int dim = a.dim, W = a.tblW;
+    const size_t ps = (size_t)a.ps;
+    const size_t base = (size_t)cat * dim * ps + pat;
+    for (int s = 0; s < dim; s++) {
+        double prod = a.accumulate ? a.out[base + s * ps] : 1.0;
+        for (int c = 0; c < a.nChildren; c++) {
+            double f;
+            if (a.ch[c].tips == nullptr) {
+                const double *P = a.ch[c].P + ((size_t)cat * dim + s) * dim;
+                const double *cl = a.ch[c].cl + base;
+                f = __ldg(P) * cl[0];
+                for (int x = 1; x < dim; x++) f = fma(__ldg(P + x), cl[x * ps], f);
+            } else {
+                f = __ldg(a.ch[c].tbl + ((size_t)cat * dim + s) * W + a.ch[c].tips[pat]);
+            }
+            prod = (c == 0 && !a.accumulate) ? f : prod * f;
+        }
+        a.out[base + s * ps] = prod;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Site likelihoods and the per-part log-likelihood.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+like_kernel(const LikeArgs a)
+{
+    __shared__ double sSum[8], sBad[8];
+    const int pat = blockIdx.x * blockDim.x + threadIdx.x;
+    double term = 0.0, bad = 0.0;
+    if (pat < a.nPat) {
+        const int dim = a.dim, nCat = a.nCat;
+        const size_t ps = (size_t)a.ps;
+        uint64_t mask = ~0ull;    // states the root may be in
+        if (a.rootTips) {         // the root is a leaf: only its observed state(s) (Pf/p4_tree.c:1199-1378)
+            const int w = a.rootTips[pat];
+            if (w < dim) mask = 1ull << w;
+            else if (w > dim) mask = a.eqMask[w - dim - 1];
+        }
+        double like = 0.0;
+        for (int c = 0; c < nCat; c++)
+            for (int s = 0; s < dim; s++)
+                if ((mask >> s) & 1ull) like = fma(a.pi[s], a.cl[((size_t)c * dim + s) * ps + pat], like);
+        if (a.pInvar != 0.0) {
+            like *= (1.0 - a.pInvar) / (double)nCat;           // freqsTimesOneMinusPInvar[0], Pf/p4_tree.c:992-996
+            const uint64_t im = a.invarMask ? a.invarMask[pat] : 0ull;
+            if (im) {
+                for (int s = 0; s < dim; s++)
+                    if ((im >> s) & 1ull) like += a.pi[s] * a.pInvar;
+            }
+        } else if (nCat > 1) {
+            like = like / (double)nCat;
+        }
+        if (a.patLikes) a.patLikes[pat] = like;
+        if (like <= 0.0) bad = 1.0;
+        else term = (double)a.counts[pat] * log(like);
+    }
+    term = warpSum(term);
+    bad = warpSum(bad);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sSum[w] = term; sBad[w] = bad; }
+    __syncthreads();
+    if (w == 0) {
+        term = (l < (int)(blockDim.x >> 5)) ? sSum[l] : 0.0;
+        bad = (l < (int)(blockDim.x >> 5)) ? sBad[l] : 0.0;
+        term = warpSum(term);
+        bad = warpSum(bad);
+        if (l == 0) {
+            a.partials[2 * blockIdx.x] = term;
+            a.partials[2 * blockIdx.x + 1] = bad;
+        }
+    }
+}
+
+// One block folds the per-block partials in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+like_final_kernel(const double *__restrict__ partials, int n, double *__restrict__ result)
+{
+    __shared__ double sSum[8], sBad[8];
+    double term = 0.0, bad = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        term += partials[2 * i];
+        bad += partials[2 * i + 1];
+    }
+    term = warpSum(term);
+    bad = warpSum(bad);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sSum[w] = term; sBad[w] = bad; }
+    __syncthreads();
+    if (w == 0) {
+        term = (l < 8) ? sSum[l] : 0.0;
+        bad = (l < 8) ? sBad[l] : 0.0;
+        term = warpSum(term);
+        bad = warpSum(bad);
+        if (l == 0) { result[0] = term; result[1] = bad; }
+    }
+}
+
+// max |a-b| > eps ?  (p4_verifyCondLikes / p4_verifyBigPDecks, epsilon 1e-15)
+__global__ void __launch_bounds__(256)
+diff_kernel(const double *__restrict__ x, const double *__restrict__ y, size_t n, double eps, int *__restrict__ flag)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i < n; i += stride)
+        if (fabs(x[i] - y[i]) > eps) bad = 1;
+    if (bad) atomicOr(flag, 1);
+}
+
+__global__ void flush_kernel(double *buf, size_t n, double v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = v;
+}
+
+}  // namespace p4b

@@ -1,0 +1,964 @@
+// tree.cu -- device state of trees and the launch logic of the hot path.
+//
+// Reference call sites this file answers (see include/p4b200.h):
+//   p4_setPramsPart            Pf/p4_tree.c:218-541
+//   p4_calculateBigPDecksPart  Pf/p4_node.c:296-346
+//   p4_setConditionalLikelihoodsOfInternalNodePart  Pf/p4_node.c:636-857
+//   p4_treeLogLike / p4_partLogLike                 Pf/p4_tree.c:868-1027
+//   p4_copyCondLikes / p4_copyBigPDecks / verify    Pf/p4_treeCopyVerify.c
+//
+// One CUDA stream serves the whole engine: the reference is single-threaded
+// and its callers (Tree.calcLogLike, Chain.proposeSp) issue calls in a valid
+// dependency order, so stream order is exactly the order the reference would
+// have executed them in.  Compute calls only enqueue; p4b_partLogLike and
+// p4b_treeLogLike are the synchronisation points.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/p4b200.h"
+#include "engine.h"
+#include "kernels.cuh"
+
+namespace p4b {
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            setError("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,   \
+                     cudaGetErrorString(e_));                                                  \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Engine-wide state
+// ---------------------------------------------------------------------------
+struct Engine {
+    bool ready = false;
+    int device = 0;
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    // staging ring: small host->device parameter blocks (P jobs, eigensystems)
+    char *hStage = nullptr, *dStage = nullptr;
+    size_t stageCap = 0, stageHead = 0;
+    bool stageDirtySinceSync = false;
+    long long launches = 0;
+    uint64_t stamp = 0;
+    double *flushBuf = nullptr;
+    size_t flushN = 0;
+    int numSMs = 148;
+};
+static Engine G;
+
+int deviceCount()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int setDevice(int device)
+{
+    if (G.ready && device != G.device) { setError("p4b_setDevice: engine already bound to device %d", G.device); return 1; }
+    G.device = device;
+    return 0;
+}
+
+int setShard(int rank, int world)
+{
+    if (world < 1 || rank < 0 || rank >= world) { setError("p4b_setShard: bad rank %d of %d", rank, world); return 1; }
+    G.rank = rank;
+    G.world = world;
+    return 0;
+}
+
+void shardRange(int nPatterns, int *lo, int *hi)
+{
+    *lo = (int)(((long long)nPatterns * G.rank) / G.world);
+    *hi = (int)(((long long)nPatterns * (G.rank + 1)) / G.world);
+}
+
+long long kernelLaunchCount() { return G.launches; }
+
+static int engineInit()
+{
+    if (G.ready) return 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        setError("no usable CUDA device (%s): the likelihood engine has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return 1;
+    }
+    if (G.device >= n) { setError("device %d requested but only %d present", G.device, n); return 1; }
+    CUDA_TRY(cudaSetDevice(G.device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+    G.stageCap = 32u << 20;
+    CUDA_TRY(cudaMallocHost(&G.hStage, G.stageCap));
+    CUDA_TRY(cudaMalloc(&G.dStage, G.stageCap));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, G.device));
+    G.numSMs = prop.multiProcessorCount;
+    G.ready = true;
+    return 0;
+}
+
+// Copy a small parameter block to the device through the pinned ring; returns
+// the device address it will occupy once the stream reaches the copy.
+static int stage(const void *src, size_t bytes, void **devPtr)
+{
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (need > G.stageCap) { setError("staging block of %zu bytes exceeds the ring", bytes); return 1; }
+    if (G.stageHead + need > G.stageCap) {
+        // wrap: everything staged before must have been consumed
+        if (G.stageDirtySinceSync) CUDA_TRY(cudaStreamSynchronize(G.stream));
+        G.stageDirtySinceSync = false;
+        G.stageHead = 0;
+    }
+    memcpy(G.hStage + G.stageHead, src, bytes);
+    CUDA_TRY(cudaMemcpyAsync(G.dStage + G.stageHead, G.hStage + G.stageHead, bytes, cudaMemcpyHostToDevice, G.stream));
+    *devPtr = G.dStage + G.stageHead;
+    G.stageHead += need;
+    G.stageDirtySinceSync = true;
+    return 0;
+}
+
+static int streamSync()
+{
+    CUDA_TRY(cudaStreamSynchronize(G.stream));
+    G.stageDirtySinceSync = false;
+    G.stageHead = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Part mirror: tip code indices, counts, constant-site masks
+// ---------------------------------------------------------------------------
+void partDeviceFree(Part *p)
+{
+    PartDevice &d = p->dev;
+    if (d.tips) cudaFree(d.tips);
+    if (d.counts) cudaFree(d.counts);
+    if (d.invarMask) cudaFree(d.invarMask);
+    if (d.equateMask) cudaFree(d.equateMask);
+    d = PartDevice();
+}
+
+static int partDeviceEnsure(Part *p)
+{
+    PartDevice &d = p->dev;
+    if (d.tips && d.dataVersion == p->version && d.device == G.device) return 0;
+    partDeviceFree(p);
+    if (p->nPatterns <= 0) { setError("part has no patterns (pf.makePatterns not called?)"); return 1; }
+    shardRange(p->nPatterns, &d.lo, &d.hi);
+    const int n = d.hi - d.lo;
+    d.ps = ((n > 0 ? n : 1) + 31) & ~31;
+    const size_t ps = (size_t)d.ps;
+    const int dim = p->dim;
+    std::vector<uint8_t> tips((size_t)p->nTax * ps, (uint8_t)dim);   // padding behaves like a gap
+    for (int t = 0; t < p->nTax; t++) {
+        const int *row = p->patterns.data() + (size_t)t * p->nChar + d.lo;
+        uint8_t *out = tips.data() + (size_t)t * ps;
+        for (int k = 0; k < n; k++) {
+            const int c = row[k];
+            int w;
+            if (c >= 0) w = c;
+            else if (c == P4B_GAP_CODE || c == P4B_QMARK_CODE || c == -3) w = dim;
+            else {
+                const int e = c - P4B_EQUATES_BASE;
+                if (e < 0 || e >= p->nEquates) { setError("bad character code %d in patterns", c); return 1; }
+                const int j = p->realEquateOfEquate[e];
+                w = j < 0 ? dim : dim + 1 + j;
+            }
+            out[k] = (uint8_t)w;
+        }
+    }
+    CUDA_TRY(cudaMalloc(&d.tips, tips.size()));
+    CUDA_TRY(cudaMemcpy(d.tips, tips.data(), tips.size(), cudaMemcpyHostToDevice));
+    std::vector<int> counts(ps, 0);
+    for (int k = 0; k < n; k++) counts[k] = p->patternCounts[d.lo + k];
+    CUDA_TRY(cudaMalloc(&d.counts, ps * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d.counts, counts.data(), ps * sizeof(int), cudaMemcpyHostToDevice));
+    if (!p->globalInvarSitesArray.empty()) {
+        std::vector<uint64_t> im(ps, 0);
+        for (int s = 0; s < dim; s++) {
+            const int *row = p->globalInvarSitesArray.data() + (size_t)s * p->nChar + d.lo;
+            for (int k = 0; k < n; k++)
+                if (row[k]) im[k] |= 1ull << s;
+        }
+        CUDA_TRY(cudaMalloc(&d.invarMask, ps * sizeof(uint64_t)));
+        CUDA_TRY(cudaMemcpy(d.invarMask, im.data(), ps * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    std::vector<uint64_t> em(p->nRealEquates > 0 ? p->nRealEquates : 1, 0);
+    for (int e = 0; e < p->nEquates; e++) {
+        const int j = p->realEquateOfEquate[e];
+        if (j < 0) continue;
+        for (int s = 0; s < dim; s++)
+            if (p->equates[(size_t)e * dim + s]) em[j] |= 1ull << s;
+    }
+    CUDA_TRY(cudaMalloc(&d.equateMask, em.size() * sizeof(uint64_t)));
+    CUDA_TRY(cudaMemcpy(d.equateMask, em.data(), em.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    d.dataVersion = p->version;
+    d.device = G.device;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Tree device state
+// ---------------------------------------------------------------------------
+struct PartLayout {
+    int dim = 0, nCat = 1, W = 0, ps = 0, nPat = 0;
+    size_t clNodeDoubles = 0;    // nCat*dim*ps
+    size_t pOff = 0, pDoubles = 0;       // within a node's P deck
+    size_t tblOff = 0, tblDoubles = 0;   // within a node's leaf tables
+    size_t eigOff = 0, eigStride = 0;    // within the eig mirror; stride per (comp,rMatrix)
+    size_t eqOff = 0;                    // within the equate mask mirror
+    int nPairs = 0;                      // nComps*nRMatrices
+    double *clArena = nullptr;
+    int slotsUsed = 0, nSlots = 0;
+    std::vector<uint64_t> eigUploaded;   // version of each (comp,rMatrix) mirrored on the device
+};
+
+struct TreeDevice {
+    std::vector<PartLayout> parts;
+    size_t pNodeDoubles = 0, tblNodeDoubles = 0;
+    double *P = nullptr, *tbl = nullptr, *eig = nullptr;
+    uint64_t *eqMasks = nullptr;
+    double *result = nullptr;     // [2*nParts] device
+    double *hResult = nullptr;    // pinned
+    double *partials = nullptr;   // [2*maxBlocks]
+    int maxLikeBlocks = 0;
+    double *patLikes = nullptr;
+    int patLikesCap = 0;
+    int *flag = nullptr;          // verify
+    cudaEvent_t evA = nullptr, evB = nullptr, evCLa = nullptr, evCLb = nullptr;
+    bool clTimed = false;
+    int lastCLLaunches = 0;
+    long long bytes = 0;
+};
+
+int treeDeviceCreate(Tree *t)
+{
+    if (engineInit()) return 1;
+    if (!t->data || !t->model) { setError("p4_newTree: data and model are required"); return 1; }
+    if (t->data->nParts != t->model->nParts) { setError("p4_newTree: data has %d parts, model %d", t->data->nParts, t->model->nParts); return 1; }
+    TreeDevice *d = new TreeDevice();
+    t->dev = d;
+    d->parts.resize(t->nParts);
+    size_t eigTotal = 0, eqTotal = 0;
+    const int nInternalSlots = t->nNodes - t->nLeaves + 1;   // +1: a root that is a leaf (Pf/p4_node.c:608-626)
+    for (int p = 0; p < t->nParts; p++) {
+        Part *dp = t->data->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        if (!dp || !mp) { setError("p4_newTree: part %d missing in data or model", p); return 1; }
+        if (dp->dim != mp->dim) { setError("p4_newTree: part %d dim mismatch data %d model %d", p, dp->dim, mp->dim); return 1; }
+        if (partDeviceEnsure(dp)) return 1;
+        PartLayout &L = d->parts[p];
+        L.dim = mp->dim;
+        L.nCat = mp->nCat;
+        L.W = dp->tableWidth();
+        L.ps = dp->dev.ps;
+        L.nPat = dp->dev.hi - dp->dev.lo;
+        L.clNodeDoubles = (size_t)L.nCat * L.dim * L.ps;
+        L.pOff = d->pNodeDoubles;
+        L.pDoubles = (size_t)L.nCat * L.dim * L.dim;
+        d->pNodeDoubles += L.pDoubles;
+        L.tblOff = d->tblNodeDoubles;
+        L.tblDoubles = (size_t)L.nCat * L.dim * L.W;
+        d->tblNodeDoubles += L.tblDoubles;
+        L.nPairs = mp->nComps * mp->nRMatrices;
+        L.eigStride = (size_t)2 * L.dim * L.dim + L.dim;
+        L.eigOff = eigTotal;
+        eigTotal += L.eigStride * L.nPairs;
+        L.eigUploaded.assign(L.nPairs, 0);
+        L.eqOff = eqTotal;
+        eqTotal += dp->nRealEquates > 0 ? dp->nRealEquates : 1;
+        L.nSlots = nInternalSlots;
+        const size_t arenaBytes = L.clNodeDoubles * sizeof(double) * (size_t)L.nSlots;
+        CUDA_TRY(cudaMalloc(&L.clArena, arenaBytes));
+        CUDA_TRY(cudaMemsetAsync(L.clArena, 0, arenaBytes, G.stream));
+        d->bytes += (long long)arenaBytes;
+        const int blocks = (L.ps + 255) / 256;
+        if (blocks > d->maxLikeBlocks) d->maxLikeBlocks = blocks;
+    }
+    const size_t pBytes = d->pNodeDoubles * sizeof(double) * (size_t)t->nNodes;
+    const size_t tblBytes = d->tblNodeDoubles * sizeof(double) * (size_t)t->nNodes;
+    CUDA_TRY(cudaMalloc(&d->P, pBytes));
+    CUDA_TRY(cudaMemsetAsync(d->P, 0, pBytes, G.stream));
+    CUDA_TRY(cudaMalloc(&d->tbl, tblBytes));
+    CUDA_TRY(cudaMemsetAsync(d->tbl, 0, tblBytes, G.stream));
+    CUDA_TRY(cudaMalloc(&d->eig, eigTotal * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d->eqMasks, eqTotal * sizeof(uint64_t)));
+    for (int p = 0; p < t->nParts; p++) {
+        Part *dp = t->data->parts[p];
+        const int n = dp->nRealEquates > 0 ? dp->nRealEquates : 1;
+        CUDA_TRY(cudaMemcpyAsync(d->eqMasks + d->parts[p].eqOff, dp->dev.equateMask, n * sizeof(uint64_t),
+                                 cudaMemcpyDeviceToDevice, G.stream));
+    }
+    d->bytes += (long long)(pBytes + tblBytes + eigTotal * sizeof(double));
+    CUDA_TRY(cudaMalloc(&d->result, 2 * sizeof(double) * t->nParts));
+    CUDA_TRY(cudaMallocHost(&d->hResult, 2 * sizeof(double) * t->nParts));
+    CUDA_TRY(cudaMalloc(&d->partials, 2 * sizeof(double) * (size_t)d->maxLikeBlocks * t->nParts));
+    CUDA_TRY(cudaMalloc(&d->flag, sizeof(int)));
+    CUDA_TRY(cudaEventCreate(&d->evA));
+    CUDA_TRY(cudaEventCreate(&d->evB));
+    CUDA_TRY(cudaEventCreate(&d->evCLa));
+    CUDA_TRY(cudaEventCreate(&d->evCLb));
+    return 0;
+}
+
+void treeDeviceDestroy(Tree *t)
+{
+    TreeDevice *d = t->dev;
+    if (!d) return;
+    if (G.stream) cudaStreamSynchronize(G.stream);
+    for (auto &L : d->parts)
+        if (L.clArena) cudaFree(L.clArena);
+    if (d->P) cudaFree(d->P);
+    if (d->tbl) cudaFree(d->tbl);
+    if (d->eig) cudaFree(d->eig);
+    if (d->eqMasks) cudaFree(d->eqMasks);
+    if (d->result) cudaFree(d->result);
+    if (d->hResult) cudaFreeHost(d->hResult);
+    if (d->partials) cudaFree(d->partials);
+    if (d->patLikes) cudaFree(d->patLikes);
+    if (d->flag) cudaFree(d->flag);
+    if (d->evA) cudaEventDestroy(d->evA);
+    if (d->evB) cudaEventDestroy(d->evB);
+    if (d->evCLa) cudaEventDestroy(d->evCLa);
+    if (d->evCLb) cudaEventDestroy(d->evCLb);
+    delete d;
+    t->dev = nullptr;
+}
+
+static int nodeEnsureCLSlot(Node *n, int p)
+{
+    if (n->clSlot[p] >= 0) return 0;
+    PartLayout &L = n->tree->dev->parts[p];
+    if (L.slotsUsed >= L.nSlots) { setError("node %d: no CL slot left (nNodes/nLeaves given to p4_newTree were wrong?)", n->nodeNum); return 1; }
+    n->clSlot[p] = L.slotsUsed++;
+    return 0;
+}
+
+int nodeDeviceCreate(Node *n)
+{
+    Tree *t = n->tree;
+    n->clSlot.assign(t->nParts, -1);
+    n->clStamp.assign(t->nParts, 0);
+    n->pStamp.assign(t->nParts, 0);
+    if (!n->isLeaf)
+        for (int p = 0; p < t->nParts; p++)
+            if (nodeEnsureCLSlot(n, p)) return 1;
+    return 0;
+}
+
+static inline double *nodeCL(Node *n, int p)
+{
+    PartLayout &L = n->tree->dev->parts[p];
+    return L.clArena + L.clNodeDoubles * (size_t)n->clSlot[p];
+}
+static inline double *nodeP(Node *n, int p)
+{
+    TreeDevice *d = n->tree->dev;
+    return d->P + d->pNodeDoubles * (size_t)n->nodeNum + d->parts[p].pOff;
+}
+static inline double *nodeTbl(Node *n, int p)
+{
+    TreeDevice *d = n->tree->dev;
+    return d->tbl + d->tblNodeDoubles * (size_t)n->nodeNum + d->parts[p].tblOff;
+}
+
+// ---------------------------------------------------------------------------
+// setPrams: host part (Pf/p4_tree.c:218-501) then the batched P(t) kernel
+// ---------------------------------------------------------------------------
+static int eigEnsureUploaded(Tree *t, int p, int cNum, int rNum)
+{
+    ModelPart *mp = t->model->parts[p];
+    PartLayout &L = t->dev->parts[p];
+    const int idx = cNum * mp->nRMatrices + rNum;
+    Eig &e = mp->bqe[idx];
+    if (!e.allocated) { setError("part %d comp %d rMatrix %d has no eigensystem", p, cNum, rNum); return 1; }
+    if (L.eigUploaded[idx] == e.version) return 0;
+    const int dim = L.dim;
+    std::vector<double> buf(L.eigStride);
+    memcpy(buf.data(), e.V.data(), sizeof(double) * dim * dim);
+    memcpy(buf.data() + dim * dim, e.Vinv.data(), sizeof(double) * dim * dim);
+    memcpy(buf.data() + 2 * dim * dim, e.lam.data(), sizeof(double) * dim);
+    void *dsrc = nullptr;
+    if (stage(buf.data(), buf.size() * sizeof(double), &dsrc)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(t->dev->eig + L.eigOff + L.eigStride * idx, dsrc, buf.size() * sizeof(double),
+                             cudaMemcpyDeviceToDevice, G.stream));
+    L.eigUploaded[idx] = e.version;
+    return 0;
+}
+
+static int hostSetPramsPart(Tree *t, int p)
+{
+    Model *m = t->model;
+    ModelPart *mp = m->parts[p];
+    // gamma rates of free gdasrvs (Pf/p4_tree.c:236-258)
+    if (mp->nCat > 1)
+        for (Gdasrv *g : mp->gdasrvs)
+            if (g && g->isFree) discreteGamma(g->freqs, g->rates, g->val[0], g->val[0], mp->nCat, 0);
+    // 2-parameter rate matrices (:297-322)
+    for (RMatrix &r : mp->rMatrices)
+        if (r.isFree && r.spec == 5) setKappaBigR(r);
+    // composition checks (:424-452)
+    for (int i = 0; i < mp->nComps; i++) {
+        const double *v = mp->comps[i].val;
+        if (!v) { setError("p4_setPramsPart() part %d, comp %d was never created", p, i); return 1; }
+        for (int j = 0; j < mp->dim; j++)
+            if (v[j] < m->PIVEC_MIN[0]) {
+                setError("p4_setPramsPart()  part %d, comp %d, value %d is %g   Bad.", p, i, j, v[j]);
+                return 1;
+            }
+        double sum = 0.0;
+        for (int j = 0; j < mp->dim; j++) sum += v[j];
+        if (fabs(sum - 1.0) > 1e-14) {
+            setError("**p4_setPramsPart()  part %d, comp %d, values do not sum to 1.0.  sum=%g  sum - 1.0 = %g", p, i, sum, sum - 1.0);
+            return 1;
+        }
+    }
+    // mark every (comp,rMatrix) stale, then rebuild the ones a non-root node uses (:455-501)
+    for (int i = 0; i < mp->nComps * mp->nRMatrices; i++) mp->bQETneedsReset[i] = 1;
+    for (Node *n : t->nodes) {
+        if (!n || n == t->root) continue;
+        const int c = n->compNums[p], r = n->rMatrixNums[p];
+        if (c < 0 || c >= mp->nComps || r < 0 || r >= mp->nRMatrices) { setError("node %d part %d uses comp %d rMatrix %d which do not exist", n->nodeNum, p, c, r); return 1; }
+        if (mp->bQETneedsReset[c * mp->nRMatrices + r])
+            if (resetBQET(m, p, c, r)) return 1;
+    }
+    return 0;
+}
+
+// Append the P(t) job of (node, part) to the batch.
+static int buildPJob(Node *n, int p, std::vector<PJob> &jobs, std::vector<double> &tvals)
+{
+    Tree *t = n->tree;
+    ModelPart *mp = t->model->parts[p];
+    TreeDevice *d = t->dev;
+    PartLayout &L = d->parts[p];
+    const int c = n->compNums[p], r = n->rMatrixNums[p];
+    if (c < 0 || c >= mp->nComps || r < 0 || r >= mp->nRMatrices) { setError("node %d part %d uses comp %d rMatrix %d which do not exist", n->nodeNum, p, c, r); return 1; }
+    if (mp->bQETneedsReset[c * mp->nRMatrices + r]) {   // Pf/p4_node.c:310-315: self-heal with a warning
+        printf("p4_calculateBigPDecksPart() pNum=%i, compNum=%i, rMatrixNum=%i, needsReset. Fix me.\n", p, c, r);
+        if (resetBQET(t->model, p, c, r)) return 1;
+    }
+    if (eigEnsureUploaded(t, p, c, r)) return 1;
+    const Gdasrv *g = nullptr;
+    if (mp->nGdasrvs) {
+        const int gi = n->gdasrvNums[p];
+        if (gi < 0 || gi >= mp->nGdasrvs || !mp->gdasrvs[gi]) { setError("node %d part %d uses gdasrv %d which does not exist", n->nodeNum, p, gi); return 1; }
+        g = mp->gdasrvs[gi];
+    }
+    PJob j;
+    j.pOff = (long long)(d->pNodeDoubles * (size_t)n->nodeNum + L.pOff);
+    j.tblOff = (long long)(d->tblNodeDoubles * (size_t)n->nodeNum + L.tblOff);
+    j.eigOff = (long long)(L.eigOff + L.eigStride * (size_t)(c * mp->nRMatrices + r));
+    j.eqOff = (long long)L.eqOff;
+    j.dim = L.dim;
+    j.nCat = L.nCat;
+    j.tblW = n->isLeaf ? L.W : 0;
+    j.nRealEq = L.W - L.dim - 1;
+    j.tOff = (long long)tvals.size();
+    for (int cat = 0; cat < mp->nCat; cat++) {   // Pf/p4_node.c:321-345, same expressions
+        double tt;
+        if (mp->pInvar == 0.0) tt = g ? (n->brLen * g->rates[cat] * mp->relRate) : (n->brLen * mp->relRate);
+        else tt = g ? (n->brLen * g->rates[cat] * mp->relRate) / (1.0 - mp->pInvar) : (n->brLen * mp->relRate) / (1.0 - mp->pInvar);
+        tvals.push_back(tt);
+    }
+    jobs.push_back(j);
+    n->pStamp[p] = ++G.stamp;
+    return 0;
+}
+
+static int launchPJobs(Tree *t, std::vector<PJob> &jobs, std::vector<double> &tvals)
+{
+    if (jobs.empty()) return 0;
+    // one staged block: [tvals | jobs]; job.tOff is relative to the block start
+    const size_t tBytes = ((tvals.size() * sizeof(double)) + 15) & ~(size_t)15;
+    std::vector<char> blk(tBytes + jobs.size() * sizeof(PJob));
+    memcpy(blk.data(), tvals.data(), tvals.size() * sizeof(double));
+    memcpy(blk.data() + tBytes, jobs.data(), jobs.size() * sizeof(PJob));
+    void *dblk = nullptr;
+    if (stage(blk.data(), blk.size(), &dblk)) return 1;
+    int maxSm = 0;
+    for (auto &j : jobs) maxSm = j.nCat * j.dim > maxSm ? j.nCat * j.dim : maxSm;
+    TreeDevice *d = t->dev;
+    pmatrix_kernel<<<(unsigned)jobs.size(), 128, maxSm * sizeof(double), G.stream>>>(
+        reinterpret_cast<const PJob *>((char *)dblk + tBytes), reinterpret_cast<const double *>(dblk), d->eig, d->eqMasks, d->P, d->tbl);
+    CUDA_TRY(cudaGetLastError());
+    G.launches++;
+    return 0;
+}
+
+int treeSetPrams(Tree *t, int pNum)
+{
+    if (!t->dev) { setError("tree has no device state"); return 1; }
+    if (pNum < -1 || pNum >= t->nParts) { setError("p4_setPrams: bad part %d", pNum); return 1; }
+    std::vector<PJob> jobs;
+    std::vector<double> tvals;
+    for (int p = 0; p < t->nParts; p++) {
+        if (pNum >= 0 && p != pNum) continue;
+        if (hostSetPramsPart(t, p)) return 1;
+        for (Node *n : t->nodes)
+            if (n && n != t->root)
+                if (buildPJob(n, p, jobs, tvals)) return 1;
+    }
+    return launchPJobs(t, jobs, tvals);
+}
+
+int nodeCalculateBigPDecks(Node *n)
+{
+    Tree *t = n->tree;
+    std::vector<PJob> jobs;
+    std::vector<double> tvals;
+    for (int p = 0; p < t->nParts; p++)
+        if (buildPJob(n, p, jobs, tvals)) return 1;
+    return launchPJobs(t, jobs, tvals);
+}
+
+int treeCalculateAllBigPDecks(Tree *t)   // Pf/p4_tree.c p4_calculateAllBigPDecksAllParts
+{
+    std::vector<PJob> jobs;
+    std::vector<double> tvals;
+    for (int p = 0; p < t->nParts; p++)
+        for (Node *n : t->nodes)
+            if (n && n != t->root)
+                if (buildPJob(n, p, jobs, tvals)) return 1;
+    return launchPJobs(t, jobs, tvals);
+}
+
+// ---------------------------------------------------------------------------
+// Conditional likelihoods
+// ---------------------------------------------------------------------------
+static int launchCL(const CLArgs &a)
+{
+    const int maxPer = a.dim * (a.tblW > a.dim ? a.tblW : a.dim);
+    if (a.dim == 4 && (a.nCat == 4 || a.nCat == 1)) {
+        const int K = a.nCat * 4;
+        const size_t sm = (size_t)a.nChildren * K * (a.tblW > 4 ? a.tblW : 4) * sizeof(double);
+        const int pairs = a.ps / 2;
+        const dim3 grid((pairs + 255) / 256);
+        if (a.nCat == 4) cl_dna_kernel<4><<<grid, 256, sm, G.stream>>>(a);
+        else cl_dna_kernel<1><<<grid, 256, sm, G.stream>>>(a);
+    } else if (a.dim == 20) {
+        const size_t sm = (size_t)a.nChildren * maxPer * sizeof(double);
+        const dim3 grid((a.ps + 127) / 128, a.nCat);
+        static bool attrSet = false;
+        if (!attrSet) {
+            CUDA_TRY(cudaFuncSetAttribute(cl_dim_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attrSet = true;
+        }
+        if (sm > 96 * 1024) { setError("leaf table too wide for the 20-state kernel"); return 1; }
+        cl_dim_kernel<20><<<grid, 128, sm, G.stream>>>(a);
+    } else {
+        const dim3 grid((a.ps + 127) / 128, a.nCat);
+        cl_generic_kernel<<<grid, 128, 0, G.stream>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    G.launches++;
+    return 0;
+}
+
+int nodeSetCL(Node *n, int p)
+{
+    Tree *t = n->tree;
+    TreeDevice *d = t->dev;
+    if (p < 0 || p >= t->nParts) { setError("p4_setConditionalLikelihoodsOfInternalNodePart: bad part %d", p); return 1; }
+    if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
+    if (nodeEnsureCLSlot(n, p)) return 1;   // a root that is a leaf gets its CL lazily, Pf/p4_node.c:608-626
+    PartLayout &L = d->parts[p];
+    Part *dp = t->data->parts[p];
+    CLArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out = nodeCL(n, p);
+    a.ps = L.ps;
+    a.dim = L.dim;
+    a.nCat = L.nCat;
+    a.tblW = L.W;
+    a.accumulate = 0;
+    int k = 0;
+    for (Node *c = n->leftChild; c; c = c->sibling) {
+        CLChild &ch = a.ch[k];
+        if (c->isLeaf) {
+            if (c->seqNum < 0 || c->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", c->nodeNum, c->seqNum); return 1; }
+            ch.tips = dp->dev.tips + (size_t)c->seqNum * L.ps;
+            ch.tbl = nodeTbl(c, p);
+            ch.cl = nullptr;
+            ch.P = nullptr;
+        } else {
+            if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return 1; }
+            ch.cl = nodeCL(c, p);
+            ch.P = nodeP(c, p);
+            ch.tips = nullptr;
+            ch.tbl = nullptr;
+        }
+        k++;
+        if (k == kMaxChildren && c->sibling) {   // polytomy wider than one launch: chain
+            a.nChildren = k;
+            if (launchCL(a)) return 1;
+            d->lastCLLaunches++;
+            a.accumulate = 1;
+            k = 0;
+        }
+    }
+    if (k > 0) {
+        a.nChildren = k;
+        if (launchCL(a)) return 1;
+        d->lastCLLaunches++;
+    }
+    n->clStamp[p] = ++G.stamp;
+    n->clNeedsUpdating = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Log-likelihood
+// ---------------------------------------------------------------------------
+static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
+{
+    TreeDevice *d = t->dev;
+    PartLayout &L = d->parts[p];
+    Part *dp = t->data->parts[p];
+    ModelPart *mp = t->model->parts[p];
+    Node *root = t->root;
+    if (!root) { setError("tree has no root"); return 1; }
+    if (root->clSlot[p] < 0) { setError("the root has no conditional likelihoods"); return 1; }
+    const int rc = root->compNums[p];
+    if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+    LikeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cl = nodeCL(root, p);
+    a.counts = dp->dev.counts;
+    a.invarMask = dp->dev.invarMask;
+    a.rootTips = root->isLeaf ? dp->dev.tips + (size_t)root->seqNum * L.ps : nullptr;
+    a.eqMask = d->eqMasks + L.eqOff;
+    a.ps = L.ps;
+    a.nPat = L.nPat;
+    a.dim = L.dim;
+    a.nCat = L.nCat;
+    a.pInvar = mp->pInvar;
+    if (a.pInvar != 0.0 && !a.invarMask) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+    for (int s = 0; s < L.dim; s++) a.pi[s] = mp->comps[rc].val[s];
+    if (wantPatLikes) {
+        if (d->patLikesCap < L.ps) {
+            if (d->patLikes) cudaFree(d->patLikes);
+            CUDA_TRY(cudaMalloc(&d->patLikes, sizeof(double) * L.ps));
+            d->patLikesCap = L.ps;
+        }
+        a.patLikes = d->patLikes;
+    }
+    const int blocks = (L.ps + 255) / 256;
+    a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * p;
+    like_kernel<<<blocks, 256, 0, G.stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, d->result + 2 * p);
+    CUDA_TRY(cudaGetLastError());
+    G.launches += 2;
+    return 0;
+}
+
+static int fetchResults(Tree *t, int p0, int p1)
+{
+    TreeDevice *d = t->dev;
+    const int n = 2 * (p1 - p0);
+    if (commActive())
+        if (commAllReduceSum(d->result + 2 * p0, n, (void *)G.stream)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(d->hResult + 2 * p0, d->result + 2 * p0, n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    return streamSync();
+}
+
+static int fillSiteLikes(Tree *t, int p)
+{
+    // Pf/p4_tree.c:1015-1021: expand pattern likelihoods to sites.
+    TreeDevice *d = t->dev;
+    PartLayout &L = d->parts[p];
+    Part *dp = t->data->parts[p];
+    if (G.world > 1) { setError("getSiteLikes is not available when patterns are sharded over several processes"); return 1; }
+    std::vector<double> pl(L.ps);
+    CUDA_TRY(cudaMemcpyAsync(pl.data(), d->patLikes, sizeof(double) * L.ps, cudaMemcpyDeviceToHost, G.stream));
+    if (streamSync()) return 1;
+    dp->siteLikes.assign(dp->nChar, 0.0);
+    for (int i = 0; i < dp->nChar; i++) dp->siteLikes[i] = pl[dp->sequencePositionPatternIndex[i]];
+    return 0;
+}
+
+double treePartLogLike(Tree *t, Part *dpArg, int p, int getSiteLikes)
+{
+    if (!t->dev) { setError("tree has no device state"); return NAN; }
+    if (p < 0 || p >= t->nParts) { setError("p4_partLogLike: bad part %d", p); return NAN; }
+    (void)dpArg;   // the reference passes the part explicitly; it is data->parts[pNum]
+    if (enqueuePartLike(t, p, getSiteLikes != 0)) return NAN;
+    if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
+    if (fetchResults(t, p, p + 1)) return NAN;
+    double lnL = t->dev->hResult[2 * p];
+    if (t->dev->hResult[2 * p + 1] > 0.0) lnL = P4B_BAD_LIKE;
+    t->partLikes[p] = lnL;
+    return lnL;
+}
+
+double treeLogLike(Tree *t, int getSiteLikes)
+{
+    if (!t->dev) { setError("tree has no device state"); return NAN; }
+    TreeDevice *d = t->dev;
+    d->lastCLLaunches = 0;
+    cudaEventRecord(d->evCLa, G.stream);
+    for (int j = 0; j < t->nNodes; j++) {   // Pf/p4_tree.c:875-887
+        const int i = t->postOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        if (i < 0 || i >= (int)t->nodes.size() || !t->nodes[i]) { setError("postOrder[%d] = %d is not a node", j, i); return NAN; }
+        Node *n = t->nodes[i];
+        if (!n->isLeaf || n == t->root)
+            for (int p = 0; p < t->nParts; p++)
+                if (nodeSetCL(n, p)) return NAN;
+    }
+    cudaEventRecord(d->evCLb, G.stream);
+    d->clTimed = true;
+    double lnL = 0.0;
+    if (getSiteLikes) {
+        for (int p = 0; p < t->nParts; p++) {
+            const double v = treePartLogLike(t, t->data->parts[p], p, 1);
+            if (std::isnan(v) && lastError()[0]) return NAN;
+            lnL += v;
+        }
+    } else {
+        for (int p = 0; p < t->nParts; p++)
+            if (enqueuePartLike(t, p, false)) return NAN;
+        if (fetchResults(t, 0, t->nParts)) return NAN;
+        for (int p = 0; p < t->nParts; p++) {
+            double v = d->hResult[2 * p];
+            if (d->hResult[2 * p + 1] > 0.0) v = P4B_BAD_LIKE;
+            t->partLikes[p] = v;
+            lnL += v;
+        }
+    }
+    t->logLike = lnL;
+    return lnL;
+}
+
+// ---------------------------------------------------------------------------
+// cur/prop state transfer
+// ---------------------------------------------------------------------------
+static int checkTwins(Tree *a, Tree *b)
+{
+    if (!a->dev || !b->dev) { setError("tree has no device state"); return 1; }
+    if (a->nNodes != b->nNodes || a->nParts != b->nParts) { setError("the two trees differ in node or part count"); return 1; }
+    for (int p = 0; p < a->nParts; p++) {
+        const PartLayout &A = a->dev->parts[p], &B = b->dev->parts[p];
+        if (A.clNodeDoubles != B.clNodeDoubles || A.pDoubles != B.pDoubles || A.W != B.W) { setError("the two trees differ in part %d layout", p); return 1; }
+    }
+    return 0;
+}
+
+int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
+{
+    if (checkTwins(a, b)) return 1;
+    for (int j = 0; j < a->nNodes; j++) {
+        const int i = a->preOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        Node *nA = a->nodes[i], *nB = b->nodes[i];
+        if (!nA || !nB || nA->isLeaf) continue;
+        if (!doAll && !(nA->clNeedsUpdating || nB->clNeedsUpdating)) continue;
+        for (int p = 0; p < a->nParts; p++) {
+            if (nA->clSlot[p] < 0) continue;
+            if (nodeEnsureCLSlot(nB, p)) return 1;
+            // Content that is already identical (same computation id) is not moved again.
+            if (nA->clStamp[p] != nB->clStamp[p]) {
+                CUDA_TRY(cudaMemcpyAsync(nodeCL(nB, p), nodeCL(nA, p), a->dev->parts[p].clNodeDoubles * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, G.stream));
+                nB->clStamp[p] = nA->clStamp[p];
+            }
+        }
+        if (!doAll) nA->clNeedsUpdating = nB->clNeedsUpdating = 0;
+    }
+    return 0;
+}
+
+int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
+{
+    if (!doAll) { setError("p4_copyBigPDecks() doAll is not set. Programming error?"); return 1; }
+    if (checkTwins(a, b)) return 1;
+    for (int j = 0; j < a->nNodes; j++) {
+        const int i = a->preOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        Node *nA = a->nodes[i], *nB = b->nodes[i];
+        if (!nA || !nB || nA == a->root) continue;
+        for (int p = 0; p < a->nParts; p++) {
+            if (nA->pStamp[p] == nB->pStamp[p]) continue;
+            CUDA_TRY(cudaMemcpyAsync(nodeP(nB, p), nodeP(nA, p), a->dev->parts[p].pDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
+            if (a->dev->parts[p].tblDoubles)
+                CUDA_TRY(cudaMemcpyAsync(nodeTbl(nB, p), nodeTbl(nA, p), a->dev->parts[p].tblDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
+            nB->pStamp[p] = nA->pStamp[p];
+        }
+    }
+    return 0;
+}
+
+int treeVerifyDevice(Tree *a, Tree *b)
+{
+    if (checkTwins(a, b)) return -1;
+    TreeDevice *d = a->dev;
+    if (cudaMemsetAsync(d->flag, 0, sizeof(int), G.stream) != cudaSuccess) { setError("memset failed"); return -1; }
+    int result = 0;
+    for (int pass = 0; pass < 2; pass++) {   // 0: CL, 1: P decks
+        for (int j = 0; j < a->nNodes; j++) {
+            const int i = a->preOrder[j];
+            if (i == P4B_NO_ORDER) continue;
+            Node *nA = a->nodes[i], *nB = b->nodes[i];
+            if (!nA || !nB) continue;
+            if (pass == 0 && nA->isLeaf) continue;
+            if (pass == 1 && nA == a->root) continue;
+            for (int p = 0; p < a->nParts; p++) {
+                const double *x, *y;
+                size_t n;
+                if (pass == 0) {
+                    if (nA->clSlot[p] < 0 || nB->clSlot[p] < 0) { if (nA->clSlot[p] != nB->clSlot[p]) result = 1; continue; }
+                    x = nodeCL(nA, p); y = nodeCL(nB, p); n = d->parts[p].clNodeDoubles;
+                } else {
+                    x = nodeP(nA, p); y = nodeP(nB, p); n = d->parts[p].pDoubles;
+                }
+                int blocks = (int)((n + 255) / 256);
+                if (blocks > G.numSMs * 8) blocks = G.numSMs * 8;
+                diff_kernel<<<blocks, 256, 0, G.stream>>>(x, y, n, 1.e-15, d->flag);
+                G.launches++;
+            }
+        }
+        int h = 0;
+        if (cudaMemcpyAsync(&h, d->flag, sizeof(int), cudaMemcpyDeviceToHost, G.stream) != cudaSuccess || streamSync()) { setError("verify: copy failed"); return -1; }
+        if (h) {
+            printf(pass == 0 ? "Verify: cond likes are different.  Bad.\n" : "Verify: bigPDecks are different.  Bad.\n");
+            result = 1;
+            cudaMemsetAsync(d->flag, 0, sizeof(int), G.stream);
+        }
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------
+// Inspection / timing
+// ---------------------------------------------------------------------------
+int nodeGetCL(Node *n, int p, double *out)
+{
+    Tree *t = n->tree;
+    if (!t->dev || p < 0 || p >= t->nParts) { setError("p4b_getNodeCL: bad part"); return 1; }
+    if (n->clSlot[p] < 0) { setError("node %d has no conditional likelihoods", n->nodeNum); return 1; }
+    PartLayout &L = t->dev->parts[p];
+    std::vector<double> h(L.clNodeDoubles);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), nodeCL(n, p), L.clNodeDoubles * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    if (streamSync()) return 1;
+    for (int k = 0; k < L.nCat * L.dim; k++) memcpy(out + (size_t)k * L.nPat, h.data() + (size_t)k * L.ps, sizeof(double) * L.nPat);
+    return 0;
+}
+
+int nodeGetBigP(Node *n, int p, double *out)
+{
+    Tree *t = n->tree;
+    if (!t->dev || p < 0 || p >= t->nParts) { setError("p4b_getNodeBigP: bad part"); return 1; }
+    CUDA_TRY(cudaMemcpyAsync(out, nodeP(n, p), t->dev->parts[p].pDoubles * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    return streamSync();
+}
+
+// Test hook: overwrite one node's P deck (and its leaf lookup table) with given
+// values, so that the CL kernels can be checked against the reference with the
+// transition matrices held identical.
+int nodeSetBigP(Node *n, int p, const double *in)
+{
+    Tree *t = n->tree;
+    if (!t->dev || p < 0 || p >= t->nParts) { setError("p4b_setNodeBigP: bad part"); return 1; }
+    PartLayout &L = t->dev->parts[p];
+    Part *dp = t->data->parts[p];
+    CUDA_TRY(cudaMemcpyAsync(nodeP(n, p), in, L.pDoubles * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    std::vector<double> T(L.tblDoubles);
+    const int dim = L.dim, W = L.W;
+    std::vector<uint64_t> em(dp->nRealEquates > 0 ? dp->nRealEquates : 1, 0);
+    for (int e = 0; e < dp->nEquates; e++) {
+        const int j = dp->realEquateOfEquate[e];
+        if (j < 0) continue;
+        for (int s = 0; s < dim; s++)
+            if (dp->equates[(size_t)e * dim + s]) em[j] |= 1ull << s;
+    }
+    for (int k = 0; k < L.nCat * dim; k++)
+        for (int w = 0; w < W; w++) {
+            double v;
+            if (w < dim) v = in[(size_t)k * dim + w];
+            else if (w == dim) v = 1.0;
+            else {
+                v = 0.0;
+                for (int x = 0; x < dim; x++)
+                    if ((em[w - dim - 1] >> x) & 1ull) v += in[(size_t)k * dim + x];
+            }
+            T[(size_t)k * W + w] = v;
+        }
+    CUDA_TRY(cudaMemcpyAsync(nodeTbl(n, p), T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    if (streamSync()) return 1;
+    n->pStamp[p] = ++G.stamp;
+    return 0;
+}
+
+int treeShardRangeOf(Tree *t, int p, int *lo, int *hi)
+{
+    if (!t->data || p < 0 || p >= t->nParts) { setError("bad part"); return 1; }
+    *lo = t->data->parts[p]->dev.lo;
+    *hi = t->data->parts[p]->dev.hi;
+    return 0;
+}
+
+int treeSync(Tree *t)
+{
+    (void)t;
+    if (!G.ready) return 0;
+    return streamSync();
+}
+
+int treeTimerBegin(Tree *t)
+{
+    if (!t->dev) { setError("tree has no device state"); return 1; }
+    CUDA_TRY(cudaEventRecord(t->dev->evA, G.stream));
+    return 0;
+}
+
+double treeTimerEnd(Tree *t)
+{
+    if (!t->dev) { setError("tree has no device state"); return -1.0; }
+    if (cudaEventRecord(t->dev->evB, G.stream) != cudaSuccess || cudaEventSynchronize(t->dev->evB) != cudaSuccess) { setError("timer failed"); return -1.0; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t->dev->evA, t->dev->evB) != cudaSuccess) { setError("timer failed"); return -1.0; }
+    return (double)ms;
+}
+
+int treeLastCLTiming(Tree *t, double *ms, int *nLaunches)
+{
+    if (!t->dev || !t->dev->clTimed) { setError("no p4b_treeLogLike has run on this tree"); return 1; }
+    CUDA_TRY(cudaEventSynchronize(t->dev->evCLb));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, t->dev->evCLa, t->dev->evCLb));
+    if (ms) *ms = (double)f;
+    if (nLaunches) *nLaunches = t->dev->lastCLLaunches;
+    return 0;
+}
+
+long long treeDeviceBytes(Tree *t) { return t->dev ? t->dev->bytes : 0; }
+
+int treeFlushL2(Tree *t)
+{
+    (void)t;
+    if (engineInit()) return 1;
+    if (!G.flushBuf) {
+        G.flushN = (size_t)(256u << 20) / sizeof(double);   // 256 MiB > 126 MB L2
+        CUDA_TRY(cudaMalloc(&G.flushBuf, G.flushN * sizeof(double)));
+    }
+    flush_kernel<<<G.numSMs * 4, 256, 0, G.stream>>>(G.flushBuf, G.flushN, 1.0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+void *engineStream() { return (void *)G.stream; }
+int engineInitPublic() { return engineInit(); }
+
+}  // namespace p4b

@@ -1,0 +1,533 @@
+"""pf -- drop-in mirror of the reference's ``p4.pf`` extension module for the
+likelihood path, backed by the B200 engine (libp4b200.so, include/p4b200.h).
+
+Every function has the name, argument order and meaning of the corresponding
+wrapper in the reference's method table (Pf/pfmodule.c:2873-3020).  Handles are
+plain Python ints (the reference returns C pointers as ``Py_BuildValue("l")``,
+Pf/pfmodule.c:1405).  NumPy arrays whose buffers the reference borrows
+(comp.val, gdasrv val/freqs/rates, bQETneedsReset, preOrder/postOrder,
+partLikes, the var limits) are borrowed here too and are re-read on every
+compute call; this module additionally pins a reference to each so a buffer
+cannot be freed under the engine.
+
+Only the hot-path subset exists.  Anything else raises
+AttributeError naming the missing function.
+
+There is no CPU fallback: compute calls fail loudly without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class P4bFatal(SystemExit):
+    """An engine-level fatal error.
+
+    The reference prints a message and calls exit(1) in these situations
+    (e.g. Pf/p4_tree.c:436, 495; Pf/part.c:247).  Left uncaught this ends the
+    process with status 1 as well; unlike exit() it can be caught by a test.
+    """
+
+    def __init__(self, message):
+        super().__init__(1)
+        self.message = message
+
+    def __str__(self):
+        return self.message
+
+
+def _load():
+    path = os.path.join(_HERE, "libp4b200.so")
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback for this path." % path)
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+_lib = _load()
+ACCEPTS_BYTES = True   # pokeSequences etc. take bytes as well as str (no 320 MB re-encode)
+lib_path = os.path.join(_HERE, "libp4b200.so")
+
+_vp, _i, _d, _cp = C.c_void_p, C.c_int, C.c_double, C.c_char_p
+_ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+
+def _sig(name, res, *args):
+    f = getattr(_lib, name)
+    f.restype = res
+    f.argtypes = list(args)
+    return f
+
+
+_lastError = _sig("p4b_lastError", _cp)
+_sig("p4b_version", _cp)
+_sig("p4b_deviceCount", _i)
+_sig("p4b_setDevice", _i, _i)
+_sig("p4b_setShard", _i, _i, _i)
+_sig("p4b_commGetUniqueId", _i, C.c_char_p)
+_sig("p4b_commInitRank", _i, C.c_char_p, _i, _i)
+_sig("p4b_commDestroy", _i)
+_sig("p4b_kernelLaunchCount", C.c_longlong)
+_sig("p4b_newData", _vp, _i, _i)
+_sig("p4b_freeData", None, _vp)
+_sig("p4b_pokePartInData", _i, _vp, _vp, _i)
+_sig("p4b_newPart", _vp, _i, _i, _cp, _i, _cp, _i)
+_sig("p4b_freePart", None, _vp)
+_sig("p4b_pokeEquatesTable", _i, _vp, _cp)
+_sig("p4b_pokeSequences", _i, _vp, _cp)
+_sig("p4b_makePatterns", _i, _vp)
+_sig("p4b_setGlobalInvarSitesVec", _i, _vp)
+_sig("p4b_partPatternCount", _i, _vp)
+_sig("p4b_getSiteLikes", _i, _vp, _vp, _i)
+for _n in ("Sequences", "Patterns", "PatternCounts", "SequencePositionPatternIndex", "GlobalInvarSitesVec",
+           "GlobalInvarSitesArray", "Equates"):
+    _sig("p4b_part" + _n, _vp, _vp)
+_sig("p4b_partNChar", _i, _vp)
+_sig("p4b_partNTax", _i, _vp)
+_sig("p4b_partDim", _i, _vp)
+_sig("p4b_newModel", _vp, _i, _i, _i, _i, _i, *([_vp] * 15))
+_sig("p4b_freeModel", None, _vp)
+_sig("p4b_newModelPart", _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp)
+_sig("p4b_newComp", _i, _vp, _i, _i, _i, _vp)
+_sig("p4b_newRMatrix", _i, _vp, _i, _i, _i, _i)
+_sig("p4b_newGdasrv", _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp)
+_sig("p4b_gdasrvCalcRates", _i, _vp)
+_sig("p4b_gdasrvCalcRates_np", _i, _i, _d, _vp, _vp)
+_sig("p4b_setRMatrixBigR", _i, _vp, _i, _i, _i, _i, _d)
+_sig("p4b_setKappa", _i, _vp, _i, _i, _d)
+_sig("p4b_setPInvarVal", _i, _vp, _i, _d)
+_sig("p4b_setRelRateVal", _i, _vp, _i, _d)
+_sig("p4b_resetBQET", _i, _vp, _i, _i, _i)
+_sig("p4b_getRelRate", _d, _vp, _i)
+_sig("p4b_getBigQ", _i, _vp, _i, _i, _i, _vp)
+_sig("p4b_getBigR", _i, _i, _vp)
+_sig("p4b_getModelBigR", _i, _vp, _i, _i, _vp)
+_sig("p4b_getEig", _i, _vp, _i, _i, _i, _vp, _vp, _vp)
+_sig("p4b_newTree", _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp)
+_sig("p4b_freeTree", None, _vp)
+_sig("p4b_newNode", _vp, _i, _vp, _i, _i, _i)
+_sig("p4b_freeNode", None, _vp)
+_sig("p4b_setNodeRelation", _i, _vp, _i, _i)
+_sig("p4b_setTreeRoot", _i, _vp, _vp)
+_sig("p4b_setBrLen", _i, _vp, _d)
+_sig("p4b_setCompNum", _i, _vp, _i, _i)
+_sig("p4b_setRMatrixNum", _i, _vp, _i, _i)
+_sig("p4b_setGdasrvNum", _i, _vp, _i, _i)
+_sig("p4b_getTreeLen", _d, _vp)
+_sig("p4b_setPrams", _i, _vp, _i)
+_sig("p4b_calculateBigPDecks", _i, _vp)
+_sig("p4b_calculateAllBigPDecksAllParts", _i, _vp)
+_sig("p4b_setConditionalLikelihoodsOfInternalNodePart", _i, _vp, _i)
+_sig("p4b_partLogLike", _d, _vp, _vp, _i, _i)
+_sig("p4b_treeLogLike", _d, _vp, _i)
+_sig("p4b_copyCondLikes", _i, _vp, _vp, _i)
+_sig("p4b_copyBigPDecks", _i, _vp, _vp, _i)
+_sig("p4b_copyModelPrams", _i, _vp, _vp)
+_sig("p4b_verifyIdentityOfTwoTrees", _i, _vp, _vp)
+_sig("p4b_treeShardRange", _i, _vp, _i, _ip, _ip)
+_sig("p4b_getNodeCL", _i, _vp, _i, _vp)
+_sig("p4b_getNodeBigP", _i, _vp, _i, _vp)
+_sig("p4b_setNodeBigP", _i, _vp, _i, _vp)
+_sig("p4b_treeSync", _i, _vp)
+_sig("p4b_treeTimerBegin", _i, _vp)
+_sig("p4b_treeTimerEnd", _d, _vp)
+_sig("p4b_treeLastCLTiming", _i, _vp, _dp, _ip)
+_sig("p4b_treeDeviceBytes", C.c_longlong, _vp)
+_sig("p4b_flushL2", _i, _vp)
+
+# object -> list of borrowed numpy buffers kept alive for it
+_keep = {}
+
+
+def _fatal():
+    msg = (_lastError() or b"").decode("utf-8", "replace")
+    print(msg)
+    raise P4bFatal(msg)
+
+
+def _ok(rc):
+    if rc != 0:
+        _fatal()
+
+
+def _handle(h):
+    if not h:
+        _fatal()
+    return int(h)
+
+
+def _arr(a, dtype, what):
+    """Raw pointer of a numpy array whose buffer the engine borrows."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("%s must be a C-contiguous numpy array of %s" % (what, np.dtype(dtype)))
+    return a.ctypes.data
+
+
+def _bytes(s):
+    return s if isinstance(s, (bytes, bytearray)) else s.encode("latin-1")
+
+
+# ---- engine (additions; no counterpart in the reference) ---------------------
+def version():
+    return _lib.p4b_version().decode()
+
+
+def deviceCount():
+    return _lib.p4b_deviceCount()
+
+
+def setDevice(device):
+    _ok(_lib.p4b_setDevice(device))
+
+
+def setShard(rank, world):
+    _ok(_lib.p4b_setShard(rank, world))
+
+
+def commGetUniqueId():
+    buf = C.create_string_buffer(128)
+    _ok(_lib.p4b_commGetUniqueId(buf))
+    return buf.raw
+
+
+def commInitRank(uid, rank, world):
+    assert len(uid) == 128
+    _ok(_lib.p4b_commInitRank(uid, rank, world))
+
+
+def commDestroy():
+    _ok(_lib.p4b_commDestroy())
+
+
+def kernelLaunchCount():
+    return _lib.p4b_kernelLaunchCount()
+
+
+# ---- data ---------------------------------------------------------------------
+def newData(nTax, nParts):
+    return _handle(_lib.p4b_newData(nTax, nParts))
+
+
+def freeData(cData):
+    _lib.p4b_freeData(cData)
+
+
+def pokePartInData(cPart, cData, i):
+    _ok(_lib.p4b_pokePartInData(cPart, cData, i))
+
+
+def newPart(nTax, nChar, equateSymbols, nEquates, symbols, dim):
+    return _handle(_lib.p4b_newPart(nTax, nChar, _bytes(equateSymbols), nEquates, _bytes(symbols), dim))
+
+
+def freePart(cPart):
+    _lib.p4b_freePart(cPart)
+
+
+def pokeEquatesTable(cPart, theString):
+    _ok(_lib.p4b_pokeEquatesTable(cPart, _bytes(theString)))
+
+
+def pokeSequences(cPart, theString):
+    b = _bytes(theString)
+    need = _lib.p4b_partNTax(cPart) * _lib.p4b_partNChar(cPart)
+    if len(b) < need:
+        raise P4bFatal("pokeSequences: got %d characters, need nTax*nChar = %d" % (len(b), need))
+    _ok(_lib.p4b_pokeSequences(cPart, b))
+
+
+def makePatterns(cPart):
+    _ok(_lib.p4b_makePatterns(cPart))
+
+
+def setGlobalInvarSitesVec(cPart):
+    _ok(_lib.p4b_setGlobalInvarSitesVec(cPart))
+
+
+def partPatternCount(cPart):
+    return _lib.p4b_partPatternCount(cPart)
+
+
+def getSiteLikes(cPart):
+    n = _lib.p4b_partNChar(cPart)
+    out = np.empty(n, dtype=np.float64)
+    if _lib.p4b_getSiteLikes(cPart, out.ctypes.data, n) < 0:
+        _fatal()
+    return out.tolist()
+
+
+def _part_view(cPart, name, shape):
+    ptr = getattr(_lib, "p4b_part" + name)(cPart)
+    if not ptr:
+        return None
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array(C.cast(ptr, _ip), shape=(n,)).reshape(shape).copy()
+
+
+def partArrays(cPart):
+    """Copies of the part's host arrays (struct partStruct, Pf/pftypes.h:31-53) for parity checks."""
+    nTax, nChar, dim = _lib.p4b_partNTax(cPart), _lib.p4b_partNChar(cPart), _lib.p4b_partDim(cPart)
+    return {
+        "nPatterns": _lib.p4b_partPatternCount(cPart),
+        "sequences": _part_view(cPart, "Sequences", (nTax, nChar)),
+        "patterns": _part_view(cPart, "Patterns", (nTax, nChar)),
+        "patternCounts": _part_view(cPart, "PatternCounts", (nChar,)),
+        "sequencePositionPatternIndex": _part_view(cPart, "SequencePositionPatternIndex", (nChar,)),
+        "globalInvarSitesVec": _part_view(cPart, "GlobalInvarSitesVec", (nChar,)),
+        "globalInvarSitesArray": _part_view(cPart, "GlobalInvarSitesArray", (dim, nChar)),
+    }
+
+
+# ---- model ----------------------------------------------------------------------
+def p4_newModel(nParts, doRelRates, relRatesAreFree, nFreePrams, isHet, rMatrixNormalizeTo1,
+                PINVAR_MIN, PINVAR_MAX, KAPPA_MIN, KAPPA_MAX, GAMMA_SHAPE_MIN, GAMMA_SHAPE_MAX,
+                PIVEC_MIN, PIVEC_MAX, RATE_MIN, RATE_MAX, RELRATE_MIN, RELRATE_MAX, BRLEN_MIN, BRLEN_MAX):
+    lims = [PINVAR_MIN, PINVAR_MAX, KAPPA_MIN, KAPPA_MAX, GAMMA_SHAPE_MIN, GAMMA_SHAPE_MAX, PIVEC_MIN, PIVEC_MAX,
+            RATE_MIN, RATE_MAX, RELRATE_MIN, RELRATE_MAX, BRLEN_MIN, BRLEN_MAX]
+    ptrs = [_arr(rMatrixNormalizeTo1, np.int32, "rMatrixNormalizeTo1")] + [_arr(a, np.float64, "limit") for a in lims]
+    h = _handle(_lib.p4b_newModel(int(nParts), int(doRelRates), int(relRatesAreFree), int(nFreePrams), int(isHet), *ptrs))
+    _keep[h] = [rMatrixNormalizeTo1] + lims
+    return h
+
+
+def p4_freeModel(cModel):
+    _lib.p4b_freeModel(cModel)
+    _keep.pop(cModel, None)
+
+
+def p4_newModelPart(cModel, pNum, dim, nComps, nRMatrices, nGdasrvs, nCat, pInvarFree, bQETneedsReset):
+    _ok(_lib.p4b_newModelPart(cModel, pNum, dim, nComps, nRMatrices, nGdasrvs, nCat, int(pInvarFree),
+                              _arr(bQETneedsReset, np.int32, "bQETneedsReset")))
+    _keep.setdefault(cModel, []).append(bQETneedsReset)
+
+
+def p4_resetBQET(cModel, pNum, compNum, rMatrixNum):
+    _ok(_lib.p4b_resetBQET(cModel, pNum, compNum, rMatrixNum))
+
+
+def p4_newComp(cModel, pNum, mNum, free, val):
+    _ok(_lib.p4b_newComp(cModel, pNum, mNum, int(free), _arr(val, np.float64, "comp.val")))
+    _keep.setdefault(cModel, []).append(val)
+
+
+def p4_newRMatrix(cModel, pNum, mNum, free, spec):
+    _ok(_lib.p4b_newRMatrix(cModel, pNum, mNum, int(free), int(spec)))
+
+
+def p4_newGdasrv(cModel, pNum, mNum, nCat, free, val, freqs, rates):
+    h = _handle(_lib.p4b_newGdasrv(cModel, pNum, mNum, nCat, int(free), _arr(val, np.float64, "gdasrv.val"),
+                                   _arr(freqs, np.float64, "gdasrv.freqs"), _arr(rates, np.float64, "gdasrv.rates")))
+    _keep.setdefault(cModel, []).extend([val, freqs, rates])
+    return h
+
+
+def gdasrvCalcRates(cGdasrv):
+    _ok(_lib.p4b_gdasrvCalcRates(cGdasrv))
+
+
+def gdasrvCalcRates_np(nGammaCat, val, freqs, rates):
+    _ok(_lib.p4b_gdasrvCalcRates_np(nGammaCat, float(val), _arr(freqs, np.float64, "freqs"), _arr(rates, np.float64, "rates")))
+
+
+def p4_setRMatrixBigR(cModel, pNum, rNum, i, j, val):
+    _ok(_lib.p4b_setRMatrixBigR(cModel, pNum, rNum, i, j, float(val)))
+
+
+def p4_setKappa(cModel, pNum, rNum, val):
+    _ok(_lib.p4b_setKappa(cModel, pNum, rNum, float(val)))
+
+
+def p4_setPInvarVal(cModel, pNum, val):
+    _ok(_lib.p4b_setPInvarVal(cModel, pNum, float(val)))
+
+
+def p4_setRelRateVal(cModel, pNum, val):
+    _ok(_lib.p4b_setRelRateVal(cModel, pNum, float(val)))
+
+
+def p4_getRelRate(cModel, pNum):
+    return _lib.p4b_getRelRate(cModel, pNum)
+
+
+def getBigQ(cModel, dim, pNum, compNum, rMatrixNum, numpyBigQ):
+    assert numpyBigQ.size >= dim * dim
+    _ok(_lib.p4b_getBigQ(cModel, pNum, compNum, rMatrixNum, _arr(numpyBigQ, np.float64, "bigQ")))
+
+
+def getBigR(spec, numpyBigR):
+    assert numpyBigR.size >= 400
+    _ok(_lib.p4b_getBigR(spec, _arr(numpyBigR, np.float64, "bigR")))
+
+
+def getEig(cModel, dim, pNum, compNum, rMatrixNum):
+    """(eigvecs, inverseEigvecs, eigvals) cached for one (comp, rMatrix) -- inspection only."""
+    v, vi, lam = np.empty((dim, dim)), np.empty((dim, dim)), np.empty(dim)
+    _ok(_lib.p4b_getEig(cModel, pNum, compNum, rMatrixNum, v.ctypes.data, vi.ctypes.data, lam.ctypes.data))
+    return v, vi, lam
+
+
+# ---- tree -------------------------------------------------------------------------
+def p4_newTree(nNodes, nLeaves, preOrder, postOrder, newtAndBrentPowellOptPassLimit, partLikes, cData, cModel):
+    h = _handle(_lib.p4b_newTree(nNodes, nLeaves, _arr(preOrder, np.int32, "preOrder"), _arr(postOrder, np.int32, "postOrder"),
+                                 _arr(newtAndBrentPowellOptPassLimit, np.int32, "passLimit"),
+                                 _arr(partLikes, np.float64, "partLikes"), cData, cModel))
+    _keep[h] = [preOrder, postOrder, newtAndBrentPowellOptPassLimit, partLikes]
+    return h
+
+
+def p4_freeTree(cTree):
+    _lib.p4b_freeTree(cTree)
+    _keep.pop(cTree, None)
+
+
+def p4_newNode(nodeNum, cTree, seqNum, isLeaf, inTree):
+    return _handle(_lib.p4b_newNode(nodeNum, cTree, seqNum, int(isLeaf), int(inTree)))
+
+
+def p4_freeNode(cNode):
+    _lib.p4b_freeNode(cNode)
+
+
+def p4_setNodeRelation(cNode, relation, relNum):
+    _ok(_lib.p4b_setNodeRelation(cNode, relation, relNum))
+
+
+def p4_setTreeRoot(cTree, cNode):
+    _ok(_lib.p4b_setTreeRoot(cTree, cNode))
+
+
+def p4_setBrLen(cNode, brLen):
+    _ok(_lib.p4b_setBrLen(cNode, float(brLen)))
+
+
+def p4_getTreeLen(cTree):
+    return _lib.p4b_getTreeLen(cTree)
+
+
+def p4_setCompNum(cNode, pNum, val):
+    _ok(_lib.p4b_setCompNum(cNode, pNum, val))
+
+
+def p4_setRMatrixNum(cNode, pNum, val):
+    _ok(_lib.p4b_setRMatrixNum(cNode, pNum, val))
+
+
+def p4_setGdasrvNum(cNode, pNum, val):
+    _ok(_lib.p4b_setGdasrvNum(cNode, pNum, val))
+
+
+# ---- the hot path -------------------------------------------------------------------
+def p4_setPrams(cTree, pNum):
+    _ok(_lib.p4b_setPrams(cTree, pNum))
+
+
+def p4_calculateBigPDecks(cNode):
+    _ok(_lib.p4b_calculateBigPDecks(cNode))
+
+
+def p4_calculateAllBigPDecksAllParts(cTree):
+    _ok(_lib.p4b_calculateAllBigPDecksAllParts(cTree))
+
+
+def p4_setConditionalLikelihoodsOfInternalNodePart(cNode, pNum):
+    _ok(_lib.p4b_setConditionalLikelihoodsOfInternalNodePart(cNode, pNum))
+
+
+def p4_partLogLike(cTree, cPart, pNum, getSiteLikes):
+    v = _lib.p4b_partLogLike(cTree, cPart, pNum, int(getSiteLikes))
+    if v != v:
+        _fatal()
+    return v
+
+
+def p4_treeLogLike(cTree, getSiteLikes):
+    v = _lib.p4b_treeLogLike(cTree, int(getSiteLikes))
+    if v != v and (_lastError() or b""):
+        _fatal()
+    return v
+
+
+# ---- cur/prop state transfer ------------------------------------------------------------
+def p4_copyCondLikes(cTreeA, cTreeB, doAll):
+    _ok(_lib.p4b_copyCondLikes(cTreeA, cTreeB, int(doAll)))
+
+
+def p4_copyBigPDecks(cTreeA, cTreeB, doAll):
+    _ok(_lib.p4b_copyBigPDecks(cTreeA, cTreeB, int(doAll)))
+
+
+def p4_copyModelPrams(cTreeA, cTreeB):
+    _ok(_lib.p4b_copyModelPrams(cTreeA, cTreeB))
+
+
+def p4_verifyIdentityOfTwoTrees(cTreeA, cTreeB):
+    r = _lib.p4b_verifyIdentityOfTwoTrees(cTreeA, cTreeB)
+    if r < 0:
+        _fatal()
+    return r
+
+
+# ---- inspection (additions) ----------------------------------------------------------------
+def treeShardRange(cTree, pNum):
+    lo, hi = C.c_int(), C.c_int()
+    _ok(_lib.p4b_treeShardRange(cTree, pNum, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def getNodeCL(cTree, cNode, pNum, nCat, dim):
+    """cl[cat][state][pattern] of one node for the patterns resident on this device."""
+    lo, hi = treeShardRange(cTree, pNum)
+    out = np.empty((nCat, dim, hi - lo), dtype=np.float64)
+    _ok(_lib.p4b_getNodeCL(cNode, pNum, out.ctypes.data))
+    return out
+
+
+def getNodeBigP(cNode, pNum, nCat, dim):
+    out = np.empty((nCat, dim, dim), dtype=np.float64)
+    _ok(_lib.p4b_getNodeBigP(cNode, pNum, out.ctypes.data))
+    return out
+
+
+def setNodeBigP(cNode, pNum, bigP):
+    """Test hook: overwrite one node's P deck (nCat, dim, dim)."""
+    a = np.ascontiguousarray(bigP, dtype=np.float64)
+    _ok(_lib.p4b_setNodeBigP(cNode, pNum, a.ctypes.data))
+
+
+def treeSync(cTree):
+    _ok(_lib.p4b_treeSync(cTree))
+
+
+def treeTimerBegin(cTree):
+    _ok(_lib.p4b_treeTimerBegin(cTree))
+
+
+def treeTimerEnd(cTree):
+    ms = _lib.p4b_treeTimerEnd(cTree)
+    if ms < 0:
+        _fatal()
+    return ms
+
+
+def treeLastCLTiming(cTree):
+    ms, n = C.c_double(), C.c_int()
+    _ok(_lib.p4b_treeLastCLTiming(cTree, C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
+def treeDeviceBytes(cTree):
+    return _lib.p4b_treeDeviceBytes(cTree)
+
+
+def flushL2(cTree):
+    _ok(_lib.p4b_flushL2(cTree))
+
+
+def __getattr__(name):
+    raise AttributeError("p4b200 pf mirror has no '%s': only the likelihood hot path of p4.pf is provided "
+                         "(SURVEY.md section 8b)" % name)

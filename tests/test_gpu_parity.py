@@ -1,0 +1,181 @@
+"""GPU parity: this engine, through the C ABI / pf mirror, against the reference's
+own Pf engine (oracle/_ref) on the same seeded inputs.
+
+Tolerances: log-likelihoods 1e-9 relative (BASELINE.json north_star).  P decks
+2e-14 absolute: both engines rebuild P from an eigensystem, which is accurate to
+about one ulp of 1.0 in absolute terms whatever the size of the entry.
+An entry of 1e-8 thus carries a relative error near 1e-8 in BOTH engines, and
+conditional likelihoods -- products of such entries -- inherit it: with each
+engine's own P they are compared at 1e-9 relative to the largest entry of the
+pattern.  test_cl_kernels_with_identical_P removes that effect by loading the
+reference's P decks into this engine: the CL kernels alone then agree with the
+reference to 1e-13 element by element.
+"""
+import numpy as np
+import pytest
+
+import ref_peek
+from util import build_pair, max_rel_err, rel
+
+pytestmark = pytest.mark.gpu
+
+LNL_TOL = 1e-9
+ARR_TOL = 1e-9
+
+
+def _check_arrays(pkg, mine, twin):
+    pf = pkg.pf
+    for pNum, mp in enumerate(mine.model.parts):
+        rp = ref_peek.part_arrays(twin.data.parts[pNum].cPart)
+        nPat = rp["nPatterns"]
+        for a, b in zip(mine.nodes, twin.nodes):
+            if a is not mine.root:
+                P1 = pf.getNodeBigP(a.cNode, pNum, mp.nGammaCat, mp.dim)
+                P0 = ref_peek.node_bigP(b.cNode, pNum, mp.nGammaCat, mp.dim)
+                assert np.max(np.abs(P1 - P0)) < 2e-14, "P deck of node %d" % a.nodeNum
+            if not a.isLeaf:
+                c1 = pf.getNodeCL(mine.cTree, a.cNode, pNum, mp.nGammaCat, mp.dim)
+                c0 = ref_peek.node_cl(b.cNode, pNum, mp.nGammaCat, mp.dim, rp["nChar"], nPat)
+                assert c1.shape == c0.shape
+                scale = np.max(np.abs(c0), axis=(0, 1), keepdims=True)
+                assert np.max(np.abs(c1 - c0) / scale) < ARR_TOL, "CL of node %d" % a.nodeNum
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (1, dict(nTax=12, nPatterns=500)),          # DNA GTR+I+G4
+    (2, dict(nTax=24, nPatterns=3000)),         # DNA GTR+G4
+    (3, dict(nTax=10, nPatterns=400)),          # protein LG+G4
+    (4, dict(nTax=8, nPatterns=200)),           # protein NDCH2, 4 parts
+])
+def test_tree_loglike_matches_reference(pkg, ref_pf, cfg, kw):
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
+    got = mine.calcLogLike()
+    want = twin.calcLogLike()
+    assert rel(got, want) <= LNL_TOL
+    for g, w in zip(mine.partLikes, twin.partLikes):
+        assert rel(g, w) <= LNL_TOL
+    _check_arrays(pkg, mine, twin)
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (1, dict(nTax=12, nPatterns=700)),
+    (3, dict(nTax=10, nPatterns=300)),
+    (4, dict(nTax=8, nPatterns=150)),
+])
+def test_cl_kernels_with_identical_P(pkg, ref_pf, cfg, kw):
+    """CL recursion alone: P decks copied from the reference, so the only differences
+    left are FMA contraction and summation order inside one dot product."""
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
+    want = twin.calcLogLike()
+    mine.calcLogLike()
+    for pNum, mp in enumerate(mine.model.parts):
+        for a, b in zip(mine.nodes, twin.nodes):
+            if a is not mine.root:
+                pf.setNodeBigP(a.cNode, pNum, ref_peek.node_bigP(b.cNode, pNum, mp.nGammaCat, mp.dim))
+    got = pf.p4_treeLogLike(mine.cTree, 0)
+    assert rel(got, want) <= 1e-13
+    for pNum, mp in enumerate(mine.model.parts):
+        rp = ref_peek.part_arrays(twin.data.parts[pNum].cPart)
+        for a, b in zip(mine.nodes, twin.nodes):
+            if not a.isLeaf:
+                c1 = pf.getNodeCL(mine.cTree, a.cNode, pNum, mp.nGammaCat, mp.dim)
+                c0 = ref_peek.node_cl(b.cNode, pNum, mp.nGammaCat, mp.dim, rp["nChar"], rp["nPatterns"])
+                assert max_rel_err(c1, c0) < 1e-13, "CL of node %d" % a.nodeNum
+
+
+def test_config1_full_size(pkg, ref_pf):
+    """BASELINE config 1 at full size: 32 taxa, 10k patterns, GTR+I+G4."""
+    mine, twin = build_pair(pkg, ref_pf, 1)
+    assert pkg.pf.partPatternCount(mine.data.parts[0].cPart) == 10000
+    assert rel(mine.calcLogLike(), twin.calcLogLike()) <= LNL_TOL
+
+
+def test_site_likes(pkg, ref_pf):
+    mine, twin = build_pair(pkg, ref_pf, 1, nTax=9, nPatterns=300)
+    a = np.array(mine.getSiteLikes())
+    b = np.array(twin.getSiteLikes())
+    assert a.shape == b.shape
+    assert max_rel_err(a, b) < 1e-11
+    assert rel(mine.logLike, twin.logLike) <= LNL_TOL
+
+
+def test_dirty_path_matches_full_recompute(pkg, ref_pf):
+    """Chain.proposeSp's node-level path (p4/chain.py:668-688) against a full
+    recompute (the reference's own self-check, p4/chain.py:265-286) and the reference."""
+    mine, twin = build_pair(pkg, ref_pf, 2, nTax=20, nPatterns=1500)
+    mine.calcLogLike()
+    twin.calcLogLike()
+    rng = np.random.default_rng(5)
+    for _ in range(5):
+        i = int(rng.integers(1, len(mine.nodes)))
+        new = float(rng.uniform(0.001, 0.4))
+        for t in (mine, twin):
+            t.nodes[i].br.len = new
+            t.nodes[i].br.lenChanged = True
+        got = mine.recalcAfterBranchChange()
+        want = twin.recalcAfterBranchChange()
+        assert rel(got, want) <= LNL_TOL
+        assert abs(got - mine.calcLogLike()) <= 1e-9 * abs(got)
+
+
+def test_root_is_leaf(pkg, ref_pf):
+    """A root that is itself a leaf (Pf/p4_tree.c:1199-1378)."""
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(77))
+    tree = P.synth.random_tree(P.pf, 9, rng, root_is_leaf=True)
+    assert tree.root.isLeaf
+    mp = P.synth.dna_model_part(0, rng, 4, pInvar=0.1)
+    sim_tree = P.synth.random_tree(P.pf, 9, np.random.Generator(np.random.PCG64(78)))
+    aln = P.synth.make_alignment(P.pf, sim_tree, mp, 300, rng, "dna", gap_frac=0.05, ambig_frac=0.05)
+    tree.attach(P.host.Data(P.pf, [aln]), P.host.Model(P.pf, [mp]))
+    twin = P.host.clone_tree(tree, ref_pf)
+    assert rel(tree.calcLogLike(), twin.calcLogLike()) <= LNL_TOL
+
+
+def test_nonpositive_site_like_gives_sentinel(pkg, ref_pf):
+    """like <= 0 -> the part returns -1.0e99 (Pf/p4_tree.c:1182).  1200 taxa of DNA
+    underflow double precision (the reference has no scalers)."""
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(3))
+    tree = P.synth.random_tree(P.pf, 1200, rng)
+    mp = P.synth.dna_model_part(0, rng, 4)
+    for n in tree.nodes:
+        n.br.len = 0.5
+    aln = P.synth.make_alignment(P.pf, tree, mp, 64, rng, "dna", gap_frac=0.0, ambig_frac=0.0, repeat=False)
+    tree.attach(P.host.Data(P.pf, [aln]), P.host.Model(P.pf, [mp]))
+    twin = P.host.clone_tree(tree, ref_pf)
+    want = twin.calcLogLike()
+    got = tree.calcLogLike()
+    assert want == -1.0e99
+    assert got == -1.0e99
+
+
+def test_cur_prop_copy_and_verify(pkg):
+    """p4_copyCondLikes / p4_copyBigPDecks / p4_copyModelPrams / p4_verifyIdentityOfTwoTrees
+    as Chain.__init__ uses them (p4/chain.py:24-71)."""
+    P = pkg
+    cur = P.synth.build_config(P.pf, 2, nTax=14, nPatterns=800)
+    prop = P.host.clone_tree(cur, P.pf, data=cur.data)
+    cur.calcLogLike()
+    prop.calcLogLike()
+    pf = P.pf
+    pf.p4_copyCondLikes(cur.cTree, prop.cTree, 1)
+    pf.p4_copyBigPDecks(cur.cTree, prop.cTree, 1)
+    pf.p4_copyModelPrams(cur.cTree, prop.cTree)
+    prop.calcLogLike()
+    assert pf.p4_verifyIdentityOfTwoTrees(cur.cTree, prop.cTree) == 0
+    # a proposal on prop makes them differ; copying prop -> cur restores identity
+    prop.nodes[3].br.len *= 1.7
+    prop.nodes[3].br.lenChanged = True
+    l1 = prop.recalcAfterBranchChange()
+    assert pf.p4_verifyIdentityOfTwoTrees(cur.cTree, prop.cTree) == 1
+    cur.nodes[3].br.len = prop.nodes[3].br.len
+    cur.setCStuff()
+    pf.p4_copyCondLikes(prop.cTree, cur.cTree, 1)
+    pf.p4_copyBigPDecks(prop.cTree, cur.cTree, 1)
+    pf.p4_copyModelPrams(prop.cTree, cur.cTree)
+    assert pf.p4_verifyIdentityOfTwoTrees(cur.cTree, prop.cTree) == 0
+    for pNum in range(cur.model.nParts):
+        pf.p4_partLogLike(cur.cTree, cur.data.parts[pNum].cPart, pNum, 0)
+    assert abs(float(sum(cur.partLikes)) - l1) <= 1e-12 * abs(l1)
