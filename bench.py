@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- full-tree log-likelihood evaluations per second on BASELINE config 2.
+
+Workload (BASELINE.json configs[1]): 200-taxon synthetic DNA alignment with
+1,000,000 distinct site patterns, GTR+G4, one tree.  A *step* is one
+``pf.p4_treeLogLike(cTree, 0)``: the conditional-likelihood recursion over all
+198 internal nodes plus the per-part reduction (Pf/p4_tree.c:868-922) -- the
+T_like timer of BASELINE.md section 3, the figure the ">= 50x" bar is stated
+against.  Patterns are sharded across ranks (one process per GPU, strong
+scaling: the alignment is fixed); the only collective is the NCCL all-reduce of
+the partial lnL.
+
+  value     evals/s with everything resident in HBM (device-timed, max over ranks)
+  e2e       evals/s of ``Tree.calcLogLike()`` through the pf mirror: Python glue,
+            host Q/eigen/gamma, host->device parameter blocks, P(t) kernel, CL
+            recursion, reduction, device->host result
+  roofline  the CL kernels: algorithmic bytes / CUDA-event time
+  cpu_baseline / --impl reference
+            the reference's own Pf engine (oracle/_ref, built from its unmodified
+            sources) on the host cores, on a bounded sample of the same alignment,
+            scaled linearly in patterns (every hot loop is linear in patterns)
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CFG = 2
+N_TAX = 200
+N_PATTERNS = 1000000
+METRIC = "full-tree lnL evals/sec"
+UNIT = "evals/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--patterns", type=int, default=N_PATTERNS, help="override the pattern count (testing only)")
+    ap.add_argument("--taxa", type=int, default=N_TAX)
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="patterns in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-node", action="store_true", help="one CL launch per node instead of the whole-tree kernel")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "cfg2: %d-taxon synthetic DNA, %d patterns, GTR+G4, full-tree lnL (p4_treeLogLike)" % (a.taxa, a.patterns)
+
+
+# ------------------------------------------------------------------------------
+# algorithmic bytes
+# ------------------------------------------------------------------------------
+def algorithmic_bytes_per_pattern(tree):
+    """Per pattern and per full-tree evaluation: for every internal node,
+    8*dim*nCat*(1 + k_internal_children) + k_leaf_children bytes."""
+    total = 0
+    for pNum, mp in enumerate(tree.model.parts):
+        unit = 8 * mp.dim * mp.nGammaCat
+        for n in tree.iterInternalsPostOrder():
+            kids = list(n.iterChildren())
+            k_int = sum(1 for c in kids if not c.isLeaf)
+            total += unit * (1 + k_int) + (len(kids) - k_int)
+    return total
+
+
+# ------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------
+# reference engine on the host cores
+# ------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process: the reference Pf engine on a slice of the sample alignment."""
+    taxa, sample, lo, hi, reps = args
+    import numpy as np
+    import ref_loader
+    import p4_phylogenetics_b200 as P
+    rpf = ref_loader.load_ref_pf()
+    tree = build_tree(P, rpf, taxa, sample, site_slice=(lo, hi), repeat=False)
+    tree._commonCStuff()
+    nPat = rpf.partPatternCount(tree.data.parts[0].cPart)
+    lnL = rpf.p4_treeLogLike(tree.cTree, 0)   # warm-up
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lnL = rpf.p4_treeLogLike(tree.cTree, 0)
+        times.append(time.perf_counter() - t0)
+    return nPat, times, lnL
+
+
+def build_tree(P, pf, taxa, patterns, site_slice=None, repeat=True):
+    """Config-2 tree/model/alignment; ``site_slice`` keeps a contiguous range of
+    alignment columns (used to split the CPU sample over host processes)."""
+    import numpy as np
+    host, synth = P.host, P.synth
+    rng = np.random.Generator(np.random.PCG64(20240 + CFG))
+    tree = synth.random_tree(pf, taxa, rng)
+    mp = synth.dna_model_part(0, rng, 4, pInvar=0.0)
+    aln = synth.make_alignment(pf, tree, mp, patterns, rng, "dna", repeat=repeat)
+    if site_slice is not None:
+        lo, hi = site_slice
+        aln = host.Alignment(pf, [s[lo:hi] for s in aln.sequences], aln.symbols, aln.equates)
+    tree.attach(host.Data(pf, [aln]), host.Model(pf, [mp]))
+    return tree
+
+
+def time_reference(taxa, full_patterns, sample, nproc, reps):
+    """Reference Pf evals/s extrapolated to ``full_patterns``: the sample alignment
+    is cut into ``nproc`` column ranges, one process each (Pf itself is
+    single-threaded); a whole-sample evaluation takes as long as
+    the slowest slice."""
+    import multiprocessing as mp
+    import numpy as np
+    import p4_phylogenetics_b200 as P
+    # length of the sample alignment (sites, not patterns), to cut it into ranges
+    rng = np.random.Generator(np.random.PCG64(20240 + CFG))
+    tree = P.synth.random_tree(None, taxa, rng)
+    mpart = P.synth.dna_model_part(0, rng, 4, pInvar=0.0)
+    aln = P.synth.make_alignment(None, tree, mpart, sample, rng, "dna", repeat=False)
+    nSites = aln.length
+    cuts = [(nSites * i) // nproc for i in range(nproc + 1)]
+    jobs = [(taxa, sample, cuts[i], cuts[i + 1], reps) for i in range(nproc)]
+    if nproc == 1:
+        res = [_ref_worker(jobs[0])]
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(nproc) as pool:
+            res = pool.map(_ref_worker, jobs)
+    nPat = sum(r[0] for r in res)                      # patterns actually evaluated (slices compress separately)
+    per_rep = [max(r[1][k] for r in res) for k in range(reps)]
+    t = min(per_rep)
+    evals_per_s_sample = 1.0 / t
+    return evals_per_s_sample * (nPat / float(full_patterns)), nPat, t
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import ref_loader
+    if not ref_loader.have_ref_pf():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pf.so was not built (needs /root/reference at build time)"}))
+        return 0
+    nproc = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nproc = max(1, min(nproc, 64))
+    sample = a.cpu_sample * nproc
+    sample = min(sample, a.patterns)
+    reps = max(1, min(a.steps, 3))
+    t0 = time.perf_counter()
+    value, nPat, t = time_reference(a.taxa, a.patterns, sample, nproc, reps)
+    wall = time.perf_counter() - t0
+    sample_desc = ("%d patterns of the %d (%d column ranges, one process each); %.3f s per evaluation of the sample; "
+                   "scaled by patterns" % (nPat, a.patterns, nproc, t))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": reps, "warmup": 1,
+        "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "engine": "reference Pf (Pf/*.c, gcc -O2) on host cores", "wall_s": round(wall, 1)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------
+# the B200 engine
+# ------------------------------------------------------------------------------
+def run_b200(a):
+    import numpy as np
+    import torch
+    import p4_phylogenetics_b200 as P
+    pf = P.pf
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        log("warning: WORLD_SIZE=%d but --gpus %d" % (world, a.gpus))
+    if not torch.cuda.is_available() or pf.deviceCount() < 1:
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    pf.setDevice(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = [pf.commGetUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pf.commInitRank(uid[0], rank, world)     # also sets the pattern shard of this rank
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if a.per_node:
+        pf.setFusedTreeKernel(0)
+    t0 = time.perf_counter()
+    tree = build_tree(P, pf, a.taxa, a.patterns)
+    nPat = pf.partPatternCount(tree.data.parts[0].cPart)
+    t_setup = time.perf_counter() - t0
+    lnL0 = tree.calcLogLike()     # allocates device state, uploads the shard, first evaluation
+    lo, hi = pf.treeShardRange(tree.cTree, 0)
+    if rank == 0:
+        log("setup %.1fs: %d taxa, %d sites, %d patterns (shard %d..%d), lnL %.6f, device bytes %.2f GB"
+            % (t_setup, a.taxa, tree.data.parts[0].nChar, nPat, lo, hi, lnL0, pf.treeDeviceBytes(tree.cTree) / 1e9))
+    bpp = algorithmic_bytes_per_pattern(tree)
+    n_internal = sum(1 for _ in tree.iterInternalsPostOrder())
+
+    # ---- value: resident, device-timed ------------------------------------------
+    for _ in range(a.warmup):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = pf.kernelLaunchCount()
+    cl_ms, cl_launches = [], 0
+    pf.treeTimerBegin(tree.cTree)
+    w0 = time.perf_counter()
+    for _ in range(a.steps):
+        lnL = pf.p4_treeLogLike(tree.cTree, 0)
+        ms, cl_launches = pf.treeLastCLTiming(tree.cTree)
+        cl_ms.append(ms)
+    dev_ms = pf.treeTimerEnd(tree.cTree)
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    launches = pf.kernelLaunchCount() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = [float(x) for x in tmax.tolist()]
+    ms_per_step = dev_ms_max / a.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- e2e: Tree.calcLogLike() through the pf mirror ----------------------------
+    rng = np.random.default_rng(1)
+    for _ in range(2):
+        tree.calcLogLike()
+    barrier()
+    e0 = time.perf_counter()
+    for k in range(a.steps):
+        # new branch lengths every step, so that the host really re-sends parameters
+        n = tree.nodes[1 + (k % (len(tree.nodes) - 1))]
+        n.br.len = float(np.clip(n.br.len * (1.0 + 0.01 * rng.standard_normal()), 1e-4, 0.5))
+        lnL_e2e = tree.calcLogLike()
+    barrier()
+    e2e_ms = (time.perf_counter() - e0) * 1e3
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = 1000.0 * a.steps / float(te.item())
+    n_nonroot = len(tree.nodes) - 1
+    h2d = n_nonroot * (56 + 8 * 4) + (2 * 16 + 4) * 8      # P jobs + effective branch lengths + one eigensystem
+    d2h = 16
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the CL kernels ------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    shard = hi - lo
+    cl_bytes = float(bpp) * shard                         # algorithmic bytes of one evaluation on this rank
+    cl_ms_avg = sum(cl_ms) / len(cl_ms)
+    achieved = cl_bytes / (cl_ms_avg * 1e-3) / 1e9
+    kernel = "cl_tree_dna_kernel<4,128> (whole-tree CL recursion + site likelihoods, one launch)" if cl_launches == 1 \
+        else "cl_dna_kernel<4> (all %d CL launches of one evaluation)" % cl_launches
+    roofline = {"bound": "hbm", "kernel": kernel,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_pattern": bpp, "launches_per_eval": cl_launches,
+                "avg_launch_us": 1e3 * cl_ms_avg / max(cl_launches, 1), "cl_ms_per_eval": cl_ms_avg}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        import ref_loader
+        if ref_loader.have_ref_pf():
+            sample = min(a.cpu_sample, a.patterns)
+            v, nP, t = time_reference(a.taxa, a.patterns, sample, 1, 3)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": "%d patterns of the %d; %.3f s per evaluation of the sample; scaled by patterns" % (nP, a.patterns, t)}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "patterns_per_gpu": shard, "internal_nodes": n_internal,
+                   "l2": "inputs larger than L2 (CL working set %.1f GB per GPU)" % (pf.treeDeviceBytes(tree.cTree) / 1e9),
+                   "timing": "CUDA events on the engine stream, max over ranks"},
+        "pattern_updates_per_s": value * n_internal * nPat,
+        "lnL": lnL, "wall_ms_per_step": wall_ms_max / a.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "Tree.calcLogLike(): model.setCStuff + tree.setCStuff + pf.p4_setPrams + pf.p4_treeLogLike", "lnL": lnL_e2e},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_b200(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

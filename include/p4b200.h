@@ -69,6 +69,10 @@ int p4b_setShard(int rank, int world);
 int p4b_commGetUniqueId(char id128[128]);
 int p4b_commInitRank(const char id128[128], int rank, int world);
 int p4b_commDestroy(void);
+/* p4b_treeLogLike evaluates 4-state parts with ONE whole-tree kernel launch by
+ * default; 0 selects the one-launch-per-node kernels instead (same results;
+ * kept for comparison and profiling). */
+void p4b_setFusedTreeKernel(int on);
 /* Count of engine kernel launches since process start (bench.py gpu_launches). */
 long long p4b_kernelLaunchCount(void);
 

@@ -29,6 +29,7 @@ int p4b_commGetUniqueId(char id128[128]) { return commGetUniqueId(id128); }
 int p4b_commInitRank(const char id128[128], int rank, int world) { return commInitRank(id128, rank, world); }
 int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
+void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
 
 // ---- data ------------------------------------------------------------------
 p4b_data p4b_newData(int nTax, int nParts)

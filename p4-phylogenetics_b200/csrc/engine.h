@@ -167,6 +167,7 @@ long long treeDeviceBytes(Tree *t);
 int treeFlushL2(Tree *t);
 int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
+void setFusedEnabled(int on);
 
 // comm.cpp -- NCCL, loaded at run time
 int commGetUniqueId(char id128[128]);

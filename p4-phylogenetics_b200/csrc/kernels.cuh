@@ -112,11 +112,18 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged,
 // CL, 4 states.  One thread owns two adjacent patterns and all NCAT*4 entries;
 // every global access is a 16-byte vector, 512 contiguous bytes per warp.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
 template <int NCAT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cl_dna_kernel(const CLArgs a)
 {
     constexpr int K = NCAT * 4;
@@ -135,20 +142,27 @@ cl_dna_kernel(const CLArgs a)
     if (pat >= a.ps) return;
     const size_t ps = (size_t)a.ps;
 
-    double2 acc[K];
-    if (a.accumulate) {
+    // tip codes of the leaf children, two patterns per thread
+    uchar2 code[kMaxChildren];
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = ld2(a.out + k * ps + pat);
-    }
+    for (int c = 0; c < kMaxChildren; c++)
+        if (c < a.nChildren && a.ch[c].tips != nullptr) code[c] = *reinterpret_cast<const uchar2 *>(a.ch[c].tips + pat);
+
+    // rate category outermost: 4 accumulators live at a time, stored as soon as done
 #pragma unroll
-    for (int c = 0; c < kMaxChildren; c++) {
-        if (c < a.nChildren) {
-            const bool first = (c == 0) && !a.accumulate;
-            const double *s = sm + c * perChild;
-            if (a.ch[c].tips == nullptr) {
-                const double *cl = a.ch[c].cl + pat;
+    for (int cat = 0; cat < NCAT; cat++) {
+        double2 acc[4];
+        if (a.accumulate) {
 #pragma unroll
-                for (int cat = 0; cat < NCAT; cat++) {
+            for (int st = 0; st < 4; st++) acc[st] = ld2(a.out + (cat * 4 + st) * ps + pat);
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxChildren; c++) {
+            if (c < a.nChildren) {
+                const bool first = (c == 0) && !a.accumulate;
+                const double *s = sm + c * perChild;
+                if (a.ch[c].tips == nullptr) {
+                    const double *cl = a.ch[c].cl + pat;
                     const double2 v0 = ld2(cl + (cat * 4 + 0) * ps);
                     const double2 v1 = ld2(cl + (cat * 4 + 1) * ps);
                     const double2 v2 = ld2(cl + (cat * 4 + 2) * ps);
@@ -166,24 +180,262 @@ cl_dna_kernel(const CLArgs a)
                         sum.y = fma(p23.x, v2.y, sum.y);
                         sum.x = fma(p23.y, v3.x, sum.x);
                         sum.y = fma(p23.y, v3.y, sum.y);
+                        if (first) acc[st] = sum;
+                        else { acc[st].x *= sum.x; acc[st].y *= sum.y; }
+                    }
+                } else {
+#pragma unroll
+                    for (int st = 0; st < 4; st++) {
                         const int k = cat * 4 + st;
-                        if (first) acc[k] = sum;
-                        else { acc[k].x *= sum.x; acc[k].y *= sum.y; }
+                        const double fx = s[k * W + code[c].x], fy = s[k * W + code[c].y];
+                        if (first) { acc[st].x = fx; acc[st].y = fy; }
+                        else { acc[st].x *= fx; acc[st].y *= fy; }
                     }
                 }
-            } else {
-                const uchar2 code = *reinterpret_cast<const uchar2 *>(a.ch[c].tips + pat);
+            }
+        }
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const double fx = s[k * W + code.x], fy = s[k * W + code.y];
-                    if (first) { acc[k].x = fx; acc[k].y = fy; }
-                    else { acc[k].x *= fx; acc[k].y *= fy; }
+        for (int st = 0; st < 4; st++) st2(a.out + (cat * 4 + st) * ps + pat, acc[st]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Whole-tree CL recursion, 4 states, ONE launch.
+//
+// Patterns are independent, so a thread that owns two patterns can walk the
+// whole list of internal nodes (in the caller's post-order) by itself: every
+// child CL it needs was written earlier by the same thread.  A CTA owns a tile
+// of 2*blockDim.x patterns and executes the step list; per step it
+//   - stages the children's P decks / leaf tables into shared memory
+//     (double-buffered, one __syncthreads per step),
+//   - takes the CL of the child computed in the previous step straight from
+//     registers (in post-order a node follows its last internal child),
+//   - loads any other internal child from global memory -- recently written by
+//     this CTA, so mostly served by the 126 MB L2 rather than HBM,
+//   - writes the node's CL to HBM (every node's CL stays resident, exactly the
+//     state the reference leaves behind), and
+//   - after the last step optionally folds the root CL into the site
+//     likelihoods and the block's partial lnL (Pf/p4_tree.c:1029-1197).
+// The same kernel serves any ordered subset of nodes (a dirty path).
+// ---------------------------------------------------------------------------
+// One step = one node (or one chunk of a node with more than kMaxChildren
+// children).  Compact, because the whole step list travels in kernel-parameter
+// (constant) memory: no descriptor ever has to be fetched from global memory.
+struct StepC {
+    int outSlot;                 // CL arena slot of the node
+    short nChildren;
+    signed char first;           // 1: the running product starts at 1; 0: continues from the previous chunk
+    signed char store;           // 1: write the CL at the end of the step
+    struct { int a, b; } ch[kMaxChildren];
+    // a = kind << 30 | index; kind 0: internal child, load CL slot `index`
+    //                         kind 1: internal child, CL in registers (computed by the previous step)
+    //                         kind 2: leaf child, tip row `index` (its seqNum)
+    // b = node number, addressing its P deck / leaf table
+};
+constexpr int kMaxSteps = 512;   // 56 B each: 28 KB of the 32 KB parameter space
+
+struct TreeArgs {
+    int nSteps;
+    int ps, nPat, tblW;
+    double *arena;            // CL arena of the part
+    long long clNodeDoubles;  // arena slot size
+    const double *Pdeck;      // tree's P decks, already offset to this part
+    long long pNodeDoubles;   // stride between nodes
+    const double *tbl;        // tree's leaf tables, already offset to this part
+    long long tblNodeDoubles;
+    const uint8_t *tips;      // part's tip rows [nTax][ps]
+    // fused root reduction (doLike != 0)
+    int doLike;
+    const int *counts;
+    const uint64_t *invarMask;
+    const uint8_t *rootTips;
+    const uint64_t *eqMask;
+    double *patLikes;
+    double *partials;
+    double pInvar;
+    double pi[4];
+    StepC steps[kMaxSteps];
+};
+
+__device__ __forceinline__ void cp_async8(double *smemDst, const double *gmemSrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmemSrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int NCAT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
+{
+    constexpr int K = NCAT * 4;
+    extern __shared__ double sm[];            // 2 buffers x kMaxChildren x perChild
+    __shared__ double sSum[THREADS / 32], sBad[THREADS / 32];
+    const int W = a.tblW;
+    const int perChild = K * (W > 4 ? W : 4);
+    const int bufSize = kMaxChildren * perChild;
+    const int pat = (blockIdx.x * THREADS + threadIdx.x) * 2;
+    const bool active = pat < a.ps;
+    const unsigned ps = (unsigned)a.ps;
+
+    // children's P decks / leaf tables of one step -> shared memory, asynchronously
+    auto stage = [&](int stepIdx, double *buf) {
+        const StepC &st = a.steps[stepIdx];
+        const int nc = st.nChildren;
+        for (int c = 0; c < nc; c++) {
+            const bool leaf = ((unsigned)st.ch[c].a >> 30) == 2u;
+            const double *src = leaf ? a.tbl + a.tblNodeDoubles * st.ch[c].b : a.Pdeck + a.pNodeDoubles * st.ch[c].b;
+            const int n = leaf ? K * W : K * 4;
+            for (int i = threadIdx.x; i < n; i += THREADS) cp_async8(buf + c * perChild + i, src + i);
+        }
+        cp_async_commit();
+    };
+    // tip codes of a step's leaf children, 16 bits (two patterns) per child, packed
+    auto loadCodes = [&](int stepIdx, unsigned long long &lo, unsigned &hi) {
+        lo = 0ull;
+        hi = 0u;
+        if (!active || stepIdx >= a.nSteps) return;
+        const StepC &st = a.steps[stepIdx];
+        const int nc = st.nChildren;
+        for (int c = 0; c < nc; c++) {
+            const unsigned av = (unsigned)st.ch[c].a;
+            if ((av >> 30) == 2u) {
+                const unsigned short v = *reinterpret_cast<const unsigned short *>(a.tips + (size_t)(av & 0x3fffffffu) * ps + pat);
+                if (c < 4) lo |= (unsigned long long)v << (16 * c);
+                else hi |= (unsigned)v << (16 * (c - 4));
+            }
+        }
+    };
+
+    double2 cur[K];   // CL of the node computed by the previous step (this thread's two patterns)
+#pragma unroll
+    for (int k = 0; k < K; k++) cur[k] = make_double2(1.0, 1.0);
+
+    unsigned long long codeLo, nextLo;
+    unsigned codeHi, nextHi;
+    stage(0, sm);
+    loadCodes(0, nextLo, nextHi);
+    for (int si = 0; si < a.nSteps; si++) {
+        cp_async_wait_all();
+        __syncthreads();   // buffer si&1 is complete; every thread is done with step si-1
+        const double *buf = sm + (si & 1) * bufSize;
+        if (si + 1 < a.nSteps) stage(si + 1, sm + ((si + 1) & 1) * bufSize);
+        codeLo = nextLo;
+        codeHi = nextHi;
+        loadCodes(si + 1, nextLo, nextHi);   // in flight while this step computes
+        if (active) {
+            const StepC &st = a.steps[si];
+            const int nc = st.nChildren;
+            const bool first = st.first != 0, store = st.store != 0;
+            double *out = a.arena + a.clNodeDoubles * st.outSlot + pat;
+#pragma unroll
+            for (int cat = 0; cat < NCAT; cat++) {
+                double2 acc[4];
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) acc[s4] = first ? make_double2(1.0, 1.0) : cur[cat * 4 + s4];
+                for (int c = 0; c < nc; c++) {            // runtime loop: kinds are uniform across the CTA
+                    const unsigned av = (unsigned)st.ch[c].a;
+                    const unsigned kind = av >> 30;
+                    const double *s = buf + c * perChild;
+                    if (kind == 2u) {
+                        const unsigned cc = (c < 4) ? (unsigned)(codeLo >> (16 * c)) : (codeHi >> (16 * (c - 4)));
+                        const unsigned cx = cc & 0xffu, cy = (cc >> 8) & 0xffu;
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const int k = cat * 4 + s4;
+                            acc[s4].x *= s[k * W + cx];
+                            acc[s4].y *= s[k * W + cy];
+                        }
+                    } else {
+                        double2 v0, v1, v2, v3;
+                        if (kind == 1u) {
+                            v0 = cur[cat * 4 + 0]; v1 = cur[cat * 4 + 1]; v2 = cur[cat * 4 + 2]; v3 = cur[cat * 4 + 3];
+                        } else {
+                            const double *cl = a.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat;
+                            v0 = ld2(cl + (cat * 4 + 0) * ps);
+                            v1 = ld2(cl + (cat * 4 + 1) * ps);
+                            v2 = ld2(cl + (cat * 4 + 2) * ps);
+                            v3 = ld2(cl + (cat * 4 + 3) * ps);
+                        }
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const double2 p01 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4);
+                            const double2 p23 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4 + 2);
+                            double2 sum;
+                            sum.x = p01.x * v0.x;
+                            sum.y = p01.x * v0.y;
+                            sum.x = fma(p01.y, v1.x, sum.x);
+                            sum.y = fma(p01.y, v1.y, sum.y);
+                            sum.x = fma(p23.x, v2.x, sum.x);
+                            sum.y = fma(p23.x, v2.y, sum.y);
+                            sum.x = fma(p23.y, v3.x, sum.x);
+                            sum.y = fma(p23.y, v3.y, sum.y);
+                            acc[s4].x *= sum.x;
+                            acc[s4].y *= sum.y;
+                        }
+                    }
+                }
+                // this category of `cur` is dead now: replace it with the new values
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) {
+                    cur[cat * 4 + s4] = acc[s4];
+                    if (store) st2(out + (cat * 4 + s4) * ps, acc[s4]);
                 }
             }
         }
     }
+
+    if (!a.doLike) return;
+    // ---- root reduction from registers ----------------------------------------
+    double term = 0.0, bad = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; k++) st2(a.out + k * ps + pat, acc[k]);
+    for (int h = 0; h < 2; h++) {
+        const int p1 = pat + h;
+        if (active && p1 < a.nPat) {
+            uint64_t mask = ~0ull;
+            if (a.rootTips) {
+                const int w = a.rootTips[p1];
+                if (w < 4) mask = 1ull << w;
+                else if (w > 4) mask = a.eqMask[w - 5];
+            }
+            double like = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const double v = h ? cur[k].y : cur[k].x;
+                if ((mask >> (k & 3)) & 1ull) like = fma(a.pi[k & 3], v, like);
+            }
+            if (a.pInvar != 0.0) {
+                like *= (1.0 - a.pInvar) / (double)NCAT;
+                const uint64_t im = a.invarMask ? a.invarMask[p1] : 0ull;
+                if (im) {
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++)
+                        if ((im >> s4) & 1ull) like += a.pi[s4] * a.pInvar;
+                }
+            } else if (NCAT > 1) {
+                like = like / (double)NCAT;
+            }
+            if (a.patLikes) a.patLikes[p1] = like;
+            if (like <= 0.0) bad += 1.0;
+            else term += (double)a.counts[p1] * log(like);
+        }
+    }
+    term = warpSum(term);
+    bad = warpSum(bad);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sSum[w] = term; sBad[w] = bad; }
+    __syncthreads();
+    if (w == 0) {
+        term = (l < THREADS / 32) ? sSum[l] : 0.0;
+        bad = (l < THREADS / 32) ? sBad[l] : 0.0;
+        term = warpSum(term);
+        bad = warpSum(bad);
+        if (l == 0) {
+            a.partials[2 * blockIdx.x] = term;
+            a.partials[2 * blockIdx.x + 1] = bad;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -279,12 +531,6 @@ cl_generic_kernel(const CLArgs a)
 // ---------------------------------------------------------------------------
 // Site likelihoods and the per-part log-likelihood.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double warpSum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 __global__ void __launch_bounds__(256)
 like_kernel(const LikeArgs a)

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -619,6 +620,146 @@ int nodeSetCL(Node *n, int p)
 }
 
 // ---------------------------------------------------------------------------
+// Whole-tree recursion in one launch (4-state parts)
+// ---------------------------------------------------------------------------
+static bool g_fusedEnabled = true;
+
+static bool fusedEligible(const PartLayout &L)
+{
+    return g_fusedEnabled && L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
+}
+
+// Build the step list for `order` (nodes to compute, already in dependency
+// order) and launch cl_tree_dna_kernel.  With withLike the root reduction is
+// fused into the same launch and only like_final_kernel follows.
+static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes)
+{
+    TreeDevice *d = t->dev;
+    PartLayout &L = d->parts[p];
+    Part *dp = t->data->parts[p];
+    ModelPart *mp = t->model->parts[p];
+    static TreeArgs a;   // ~29 KB: too big for the stack of a small thread; the engine is single-threaded
+    memset(&a, 0, offsetof(TreeArgs, steps));
+    a.ps = L.ps;
+    a.nPat = L.nPat;
+    a.tblW = L.W;
+    a.arena = L.clArena;
+    a.clNodeDoubles = (long long)L.clNodeDoubles;
+    a.Pdeck = d->P + L.pOff;
+    a.pNodeDoubles = (long long)d->pNodeDoubles;
+    a.tbl = d->tbl + L.tblOff;
+    a.tblNodeDoubles = (long long)d->tblNodeDoubles;
+    a.tips = dp->dev.tips;
+    constexpr int THREADS = 128;
+    const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
+    if (withLike) {
+        Node *root = t->root;
+        if (!root || order.empty() || order.back() != root) { setError("fused evaluation: the last node must be the root"); return 1; }
+        const int rc = root->compNums[p];
+        if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+        a.counts = dp->dev.counts;
+        a.invarMask = dp->dev.invarMask;
+        a.rootTips = root->isLeaf ? dp->dev.tips + (size_t)root->seqNum * L.ps : nullptr;
+        a.eqMask = d->eqMasks + L.eqOff;
+        a.pInvar = mp->pInvar;
+        if (a.pInvar != 0.0 && !a.invarMask) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+        for (int s = 0; s < 4; s++) a.pi[s] = mp->comps[rc].val[s];
+        if (wantPatLikes) {
+            if (d->patLikesCap < L.ps) {
+                if (d->patLikes) cudaFree(d->patLikes);
+                CUDA_TRY(cudaMalloc(&d->patLikes, sizeof(double) * L.ps));
+                d->patLikesCap = L.ps;
+            }
+            a.patLikes = d->patLikes;
+        }
+        if (blocks > d->maxLikeBlocks) { setError("internal: partial buffer too small"); return 1; }
+        a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * p;
+    }
+    const int K = L.nCat * 4;
+    const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double);
+    static bool attrSet = false;
+    if (!attrSet) {
+        CUDA_TRY(cudaFuncSetAttribute(cl_tree_dna_kernel<4, THREADS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(cl_tree_dna_kernel<1, THREADS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attrSet = true;
+    }
+    if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
+
+    auto flush = [&](int nSteps, bool last) -> int {
+        a.nSteps = nSteps;
+        a.doLike = (withLike && last) ? 1 : 0;
+        if (L.nCat == 4) cl_tree_dna_kernel<4, THREADS, 4><<<blocks, THREADS, smem, G.stream>>>(a);
+        else cl_tree_dna_kernel<1, THREADS, 4><<<blocks, THREADS, smem, G.stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        G.launches++;
+        d->lastCLLaunches++;
+        return 0;
+    };
+
+    int ns = 0;
+    Node *prev = nullptr;   // node whose CL the previous step of THIS launch left in registers
+    for (size_t oi = 0; oi < order.size(); oi++) {
+        Node *n = order[oi];
+        if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
+        if (nodeEnsureCLSlot(n, p)) return 1;
+        int nKids = 0;
+        for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
+        const int chunks = (nKids + kMaxChildren - 1) / kMaxChildren;
+        if (ns + chunks > kMaxSteps) {   // parameter space full: launch what we have, continue in a new launch
+            if (flush(ns, false)) return 1;
+            ns = 0;
+            prev = nullptr;
+        }
+        StepC *st = &a.steps[ns];
+        st->outSlot = n->clSlot[p];
+        st->first = 1;
+        int k = 0;
+        bool prevUsed = false;
+        for (Node *c = n->leftChild; c; c = c->sibling) {
+            unsigned kind, index;
+            if (c->isLeaf) {
+                if (c->seqNum < 0 || c->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", c->nodeNum, c->seqNum); return 1; }
+                kind = 2u;
+                index = (unsigned)c->seqNum;
+            } else {
+                if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return 1; }
+                kind = (c == prev && !prevUsed && st->first) ? 1u : 0u;
+                if (kind == 1u) prevUsed = true;
+                index = (unsigned)c->clSlot[p];
+            }
+            st->ch[k].a = (int)((kind << 30) | index);
+            st->ch[k].b = c->nodeNum;
+            k++;
+            if (k == kMaxChildren && c->sibling) {   // polytomy wider than one step: continue in the next
+                st->nChildren = (short)k;
+                st->store = 0;
+                ns++;
+                st = &a.steps[ns];
+                st->outSlot = n->clSlot[p];
+                st->first = 0;
+                k = 0;
+            }
+        }
+        st->nChildren = (short)k;
+        st->store = 1;
+        ns++;
+        prev = n;
+        n->clStamp[p] = ++G.stamp;
+        n->clNeedsUpdating = 0;
+    }
+    if (ns > 0 || withLike)
+        if (flush(ns, true)) return 1;
+    if (withLike) {
+        like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, d->result + 2 * p);
+        CUDA_TRY(cudaGetLastError());
+        G.launches++;
+    }
+    return 0;
+}
+
+void setFusedEnabled(int on) { g_fusedEnabled = on != 0; }
+
+// ---------------------------------------------------------------------------
 // Log-likelihood
 // ---------------------------------------------------------------------------
 static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
@@ -708,35 +849,42 @@ double treeLogLike(Tree *t, int getSiteLikes)
     if (!t->dev) { setError("tree has no device state"); return NAN; }
     TreeDevice *d = t->dev;
     d->lastCLLaunches = 0;
-    cudaEventRecord(d->evCLa, G.stream);
-    for (int j = 0; j < t->nNodes; j++) {   // Pf/p4_tree.c:875-887
+    // nodes whose CL is recomputed, in the caller's post-order (Pf/p4_tree.c:875-887)
+    std::vector<Node *> order;
+    for (int j = 0; j < t->nNodes; j++) {
         const int i = t->postOrder[j];
         if (i == P4B_NO_ORDER) continue;
         if (i < 0 || i >= (int)t->nodes.size() || !t->nodes[i]) { setError("postOrder[%d] = %d is not a node", j, i); return NAN; }
         Node *n = t->nodes[i];
-        if (!n->isLeaf || n == t->root)
-            for (int p = 0; p < t->nParts; p++)
+        if (!n->isLeaf || n == t->root) order.push_back(n);
+    }
+    if (order.empty() || order.back() != t->root) { setError("p4_treeLogLike: postOrder does not end at the root"); return NAN; }
+    cudaEventRecord(d->evCLa, G.stream);
+    std::vector<char> likeDone(t->nParts, 0);
+    for (int p = 0; p < t->nParts; p++) {
+        if (fusedEligible(d->parts[p])) {
+            if (launchFusedTree(t, p, order, true, getSiteLikes != 0)) return NAN;
+            likeDone[p] = 1;
+            if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
+        } else {
+            for (Node *n : order)
                 if (nodeSetCL(n, p)) return NAN;
+        }
     }
     cudaEventRecord(d->evCLb, G.stream);
     d->clTimed = true;
+    for (int p = 0; p < t->nParts; p++) {
+        if (likeDone[p]) continue;
+        if (enqueuePartLike(t, p, getSiteLikes != 0)) return NAN;
+        if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
+    }
+    if (fetchResults(t, 0, t->nParts)) return NAN;
     double lnL = 0.0;
-    if (getSiteLikes) {
-        for (int p = 0; p < t->nParts; p++) {
-            const double v = treePartLogLike(t, t->data->parts[p], p, 1);
-            if (std::isnan(v) && lastError()[0]) return NAN;
-            lnL += v;
-        }
-    } else {
-        for (int p = 0; p < t->nParts; p++)
-            if (enqueuePartLike(t, p, false)) return NAN;
-        if (fetchResults(t, 0, t->nParts)) return NAN;
-        for (int p = 0; p < t->nParts; p++) {
-            double v = d->hResult[2 * p];
-            if (d->hResult[2 * p + 1] > 0.0) v = P4B_BAD_LIKE;
-            t->partLikes[p] = v;
-            lnL += v;
-        }
+    for (int p = 0; p < t->nParts; p++) {
+        double v = d->hResult[2 * p];
+        if (d->hResult[2 * p + 1] > 0.0) v = P4B_BAD_LIKE;
+        t->partLikes[p] = v;
+        lnL += v;
     }
     t->logLike = lnL;
     return lnL;

@@ -73,6 +73,7 @@ _sig("p4b_commGetUniqueId", _i, C.c_char_p)
 _sig("p4b_commInitRank", _i, C.c_char_p, _i, _i)
 _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
+_sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_newData", _vp, _i, _i)
 _sig("p4b_freeData", None, _vp)
 _sig("p4b_pokePartInData", _i, _vp, _vp, _i)
@@ -202,6 +203,10 @@ def commInitRank(uid, rank, world):
 
 def commDestroy():
     _ok(_lib.p4b_commDestroy())
+
+
+def setFusedTreeKernel(on):
+    _lib.p4b_setFusedTreeKernel(int(on))
 
 
 def kernelLaunchCount():

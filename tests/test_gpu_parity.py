@@ -179,3 +179,58 @@ def test_cur_prop_copy_and_verify(pkg):
     for pNum in range(cur.model.nParts):
         pf.p4_partLogLike(cur.cTree, cur.data.parts[pNum].cPart, pNum, 0)
     assert abs(float(sum(cur.partLikes)) - l1) <= 1e-12 * abs(l1)
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (1, dict(nTax=13, nPatterns=900)),
+    (2, dict(nTax=40, nPatterns=5000)),
+])
+def test_fused_tree_kernel_equals_per_node_kernels(pkg, cfg, kw):
+    """The one-launch whole-tree kernel does the same arithmetic in the same order
+    as the per-node kernels: every CL must be bit-identical."""
+    pf = pkg.pf
+    tree = pkg.synth.build_config(pf, cfg, **kw)
+    mp = tree.model.parts[0]
+    try:
+        pf.setFusedTreeKernel(0)
+        a = tree.calcLogLike()
+        cl_a = {n.nodeNum: pf.getNodeCL(tree.cTree, n.cNode, 0, mp.nGammaCat, mp.dim) for n in tree.nodes if not n.isLeaf}
+        la = pf.kernelLaunchCount()
+        pf.setFusedTreeKernel(1)
+        b = tree.calcLogLike()
+        lb = pf.kernelLaunchCount() - la
+        cl_b = {n.nodeNum: pf.getNodeCL(tree.cTree, n.cNode, 0, mp.nGammaCat, mp.dim) for n in tree.nodes if not n.isLeaf}
+    finally:
+        pf.setFusedTreeKernel(1)
+    assert lb == 3      # P(t) batch, whole-tree CL + site likelihoods, final fold
+    assert rel(b, a) <= 1e-13
+    for k in cl_a:
+        assert np.array_equal(cl_a[k], cl_b[k]), "CL of node %d" % k
+
+
+def test_star_tree_wide_polytomy(pkg, ref_pf):
+    """A root with more children than one kernel step folds (chained steps)."""
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(11))
+    nTax = 15
+    nodes = [P.host.Node(i) for i in range(nTax + 1)]
+    root = nodes[0]
+    for i in range(1, nTax + 1):
+        nodes[i].isLeaf, nodes[i].seqNum, nodes[i].parent = 1, i - 1, root
+        nodes[i].br.len = float(rng.uniform(0.01, 0.3))
+        if i < nTax:
+            nodes[i].sibling = nodes[i + 1]
+    root.leftChild = nodes[1]
+    tree = P.host.Tree(P.pf, nodes, root)
+    tree.setPreAndPostOrder()
+    mp = P.synth.dna_model_part(0, rng, 4, pInvar=0.1)
+    aln = P.synth.make_alignment(P.pf, tree, mp, 400, rng, "dna", gap_frac=0.03, ambig_frac=0.03)
+    tree.attach(P.host.Data(P.pf, [aln]), P.host.Model(P.pf, [mp]))
+    twin = P.host.clone_tree(tree, ref_pf)
+    want = twin.calcLogLike()
+    assert rel(tree.calcLogLike(), want) <= LNL_TOL
+    P.pf.setFusedTreeKernel(0)
+    try:
+        assert rel(tree.calcLogLike(), want) <= LNL_TOL
+    finally:
+        P.pf.setFusedTreeKernel(1)
