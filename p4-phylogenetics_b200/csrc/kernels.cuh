@@ -265,6 +265,71 @@ __device__ __forceinline__ void cp_async8(double *smemDst, const double *gmemSrc
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Factor contributed by one child to the 4 states of one rate category, for the
+// thread's two patterns.  KIND is a compile-time constant: 0 internal child read
+// from global memory, 1 internal child whose CL is in `cur`, 2 leaf child.
+template <int KIND>
+__device__ __forceinline__ void child_factor(int cat, const double *__restrict__ s, int W, unsigned cx, unsigned cy,
+                                             const double2 *cur, const double *__restrict__ cl, unsigned ps, double2 f[4])
+{
+    if (KIND == 2) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const int k = cat * 4 + s4;
+            f[s4].x = s[k * W + cx];
+            f[s4].y = s[k * W + cy];
+        }
+    } else {
+        double2 v0, v1, v2, v3;
+        if (KIND == 1) {
+            v0 = cur[cat * 4 + 0]; v1 = cur[cat * 4 + 1]; v2 = cur[cat * 4 + 2]; v3 = cur[cat * 4 + 3];
+        } else {
+            v0 = ld2(cl + (cat * 4 + 0) * ps);
+            v1 = ld2(cl + (cat * 4 + 1) * ps);
+            v2 = ld2(cl + (cat * 4 + 2) * ps);
+            v3 = ld2(cl + (cat * 4 + 3) * ps);
+        }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const double2 p01 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4);
+            const double2 p23 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4 + 2);
+            double2 sum;
+            sum.x = p01.x * v0.x;
+            sum.y = p01.x * v0.y;
+            sum.x = fma(p01.y, v1.x, sum.x);
+            sum.y = fma(p01.y, v1.y, sum.y);
+            sum.x = fma(p23.x, v2.x, sum.x);
+            sum.y = fma(p23.x, v2.y, sum.y);
+            sum.x = fma(p23.y, v3.x, sum.x);
+            sum.y = fma(p23.y, v3.y, sum.y);
+            f[s4] = sum;
+        }
+    }
+}
+
+// A node with exactly two children -- nearly every node of a binary tree --
+// as straight-line code for one combination of child kinds.
+template <int NCAT, int K0, int K1>
+__device__ __forceinline__ void step_two_children(double2 *cur, const double *__restrict__ s0, const double *__restrict__ s1, int W,
+                                                  unsigned c0, unsigned c1, const double *__restrict__ cl0,
+                                                  const double *__restrict__ cl1, unsigned ps, double *__restrict__ out)
+{
+#pragma unroll
+    for (int cat = 0; cat < NCAT; cat++) {
+        double2 f0[4], f1[4];
+        child_factor<K0>(cat, s0, W, c0 & 0xffu, (c0 >> 8) & 0xffu, cur, cl0, ps, f0);
+        child_factor<K1>(cat, s1, W, c1 & 0xffu, (c1 >> 8) & 0xffu, cur, cl1, ps, f1);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            double2 r;
+            r.x = f0[s4].x * f1[s4].x;     // (left child) * (sibling), the reference's order
+            r.y = f0[s4].y * f1[s4].y;
+            cur[cat * 4 + s4] = r;
+            st2(out + (cat * 4 + s4) * ps, r);
+        }
+    }
+}
+
 template <int NCAT, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
@@ -291,96 +356,78 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         }
         cp_async_commit();
     };
-    // tip codes of a step's leaf children, 16 bits (two patterns) per child, packed
-    auto loadCodes = [&](int stepIdx, unsigned long long &lo, unsigned &hi) {
-        lo = 0ull;
-        hi = 0u;
-        if (!active || stepIdx >= a.nSteps) return;
+    // tip codes (two patterns = 16 bits) of child c of a step, if it is a leaf
+    auto tipCode = [&](int stepIdx, int c) -> unsigned {
+        if (!active || stepIdx >= a.nSteps) return 0u;
         const StepC &st = a.steps[stepIdx];
-        const int nc = st.nChildren;
-        for (int c = 0; c < nc; c++) {
-            const unsigned av = (unsigned)st.ch[c].a;
-            if ((av >> 30) == 2u) {
-                const unsigned short v = *reinterpret_cast<const unsigned short *>(a.tips + (size_t)(av & 0x3fffffffu) * ps + pat);
-                if (c < 4) lo |= (unsigned long long)v << (16 * c);
-                else hi |= (unsigned)v << (16 * (c - 4));
-            }
-        }
+        const unsigned av = (unsigned)st.ch[c].a;
+        if (c >= st.nChildren || (av >> 30) != 2u) return 0u;
+        return *reinterpret_cast<const unsigned short *>(a.tips + (size_t)(av & 0x3fffffffu) * ps + pat);
     };
 
     double2 cur[K];   // CL of the node computed by the previous step (this thread's two patterns)
 #pragma unroll
     for (int k = 0; k < K; k++) cur[k] = make_double2(1.0, 1.0);
 
-    unsigned long long codeLo, nextLo;
-    unsigned codeHi, nextHi;
     stage(0, sm);
-    loadCodes(0, nextLo, nextHi);
+    unsigned next0 = tipCode(0, 0), next1 = tipCode(0, 1);   // children 0 and 1 are prefetched one step ahead
     for (int si = 0; si < a.nSteps; si++) {
         cp_async_wait_all();
         __syncthreads();   // buffer si&1 is complete; every thread is done with step si-1
         const double *buf = sm + (si & 1) * bufSize;
         if (si + 1 < a.nSteps) stage(si + 1, sm + ((si + 1) & 1) * bufSize);
-        codeLo = nextLo;
-        codeHi = nextHi;
-        loadCodes(si + 1, nextLo, nextHi);   // in flight while this step computes
+        const unsigned code0 = next0, code1 = next1;
+        next0 = tipCode(si + 1, 0);          // in flight while this step computes
+        next1 = tipCode(si + 1, 1);
         if (active) {
             const StepC &st = a.steps[si];
             const int nc = st.nChildren;
-            const bool first = st.first != 0, store = st.store != 0;
             double *out = a.arena + a.clNodeDoubles * st.outSlot + pat;
-#pragma unroll
-            for (int cat = 0; cat < NCAT; cat++) {
-                double2 acc[4];
-#pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) acc[s4] = first ? make_double2(1.0, 1.0) : cur[cat * 4 + s4];
-                for (int c = 0; c < nc; c++) {            // runtime loop: kinds are uniform across the CTA
-                    const unsigned av = (unsigned)st.ch[c].a;
-                    const unsigned kind = av >> 30;
-                    const double *s = buf + c * perChild;
-                    if (kind == 2u) {
-                        const unsigned cc = (c < 4) ? (unsigned)(codeLo >> (16 * c)) : (codeHi >> (16 * (c - 4)));
-                        const unsigned cx = cc & 0xffu, cy = (cc >> 8) & 0xffu;
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const int k = cat * 4 + s4;
-                            acc[s4].x *= s[k * W + cx];
-                            acc[s4].y *= s[k * W + cy];
-                        }
-                    } else {
-                        double2 v0, v1, v2, v3;
-                        if (kind == 1u) {
-                            v0 = cur[cat * 4 + 0]; v1 = cur[cat * 4 + 1]; v2 = cur[cat * 4 + 2]; v3 = cur[cat * 4 + 3];
-                        } else {
-                            const double *cl = a.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat;
-                            v0 = ld2(cl + (cat * 4 + 0) * ps);
-                            v1 = ld2(cl + (cat * 4 + 1) * ps);
-                            v2 = ld2(cl + (cat * 4 + 2) * ps);
-                            v3 = ld2(cl + (cat * 4 + 3) * ps);
-                        }
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const double2 p01 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4);
-                            const double2 p23 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4 + 2);
-                            double2 sum;
-                            sum.x = p01.x * v0.x;
-                            sum.y = p01.x * v0.y;
-                            sum.x = fma(p01.y, v1.x, sum.x);
-                            sum.y = fma(p01.y, v1.y, sum.y);
-                            sum.x = fma(p23.x, v2.x, sum.x);
-                            sum.y = fma(p23.x, v2.y, sum.y);
-                            sum.x = fma(p23.y, v3.x, sum.x);
-                            sum.y = fma(p23.y, v3.y, sum.y);
-                            acc[s4].x *= sum.x;
-                            acc[s4].y *= sum.y;
-                        }
-                    }
+            const unsigned a0 = (unsigned)st.ch[0].a, a1 = (unsigned)st.ch[1].a;
+            const unsigned k0 = a0 >> 30, k1 = a1 >> 30;
+            if (nc == 2 && st.first && st.store) {
+                const double *cl0 = a.arena + a.clNodeDoubles * (a0 & 0x3fffffffu) + pat;
+                const double *cl1 = a.arena + a.clNodeDoubles * (a1 & 0x3fffffffu) + pat;
+                const double *s0 = buf, *s1 = buf + perChild;
+                switch (k0 * 3 + k1) {   // uniform across the CTA
+                case 0: step_two_children<NCAT, 0, 0>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                case 1: step_two_children<NCAT, 0, 1>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                case 2: step_two_children<NCAT, 0, 2>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                case 3: step_two_children<NCAT, 1, 0>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                case 5: step_two_children<NCAT, 1, 2>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                case 6: step_two_children<NCAT, 2, 0>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                case 7: step_two_children<NCAT, 2, 1>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                default: step_two_children<NCAT, 2, 2>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
                 }
-                // this category of `cur` is dead now: replace it with the new values
+            } else {
+                // any other shape (1 child, 3+ children, chunks of a wide polytomy): generic loop
+                const bool first = st.first != 0, store = st.store != 0;
 #pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) {
-                    cur[cat * 4 + s4] = acc[s4];
-                    if (store) st2(out + (cat * 4 + s4) * ps, acc[s4]);
+                for (int cat = 0; cat < NCAT; cat++) {
+                    double2 acc[4];
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) acc[s4] = first ? make_double2(1.0, 1.0) : cur[cat * 4 + s4];
+                    for (int c = 0; c < nc; c++) {
+                        const unsigned av = (unsigned)st.ch[c].a;
+                        const unsigned kind = av >> 30;
+                        const double *s = buf + c * perChild;
+                        double2 f[4];
+                        if (kind == 2u) {
+                            const unsigned cc = c == 0 ? code0 : (c == 1 ? code1 : tipCode(si, c));
+                            child_factor<2>(cat, s, W, cc & 0xffu, (cc >> 8) & 0xffu, cur, nullptr, ps, f);
+                        } else if (kind == 1u) {
+                            child_factor<1>(cat, s, W, 0u, 0u, cur, nullptr, ps, f);
+                        } else {
+                            child_factor<0>(cat, s, W, 0u, 0u, cur, a.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat, ps, f);
+                        }
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) { acc[s4].x *= f[s4].x; acc[s4].y *= f[s4].y; }
+                    }
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        cur[cat * 4 + s4] = acc[s4];
+                        if (store) st2(out + (cat * 4 + s4) * ps, acc[s4]);
+                    }
                 }
             }
         }

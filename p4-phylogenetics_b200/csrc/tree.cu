@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -304,7 +305,7 @@ int treeDeviceCreate(Tree *t)
     d->bytes += (long long)(pBytes + tblBytes + eigTotal * sizeof(double));
     CUDA_TRY(cudaMalloc(&d->result, 2 * sizeof(double) * t->nParts));
     CUDA_TRY(cudaMallocHost(&d->hResult, 2 * sizeof(double) * t->nParts));
-    CUDA_TRY(cudaMalloc(&d->partials, 2 * sizeof(double) * (size_t)d->maxLikeBlocks * t->nParts));
+    CUDA_TRY(cudaMalloc(&d->partials, 2 * sizeof(double) * (size_t)d->maxLikeBlocks * 4 * t->nParts));
     CUDA_TRY(cudaMalloc(&d->flag, sizeof(int)));
     CUDA_TRY(cudaEventCreate(&d->evA));
     CUDA_TRY(cudaEventCreate(&d->evB));
@@ -650,7 +651,15 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
     a.tbl = d->tbl + L.tblOff;
     a.tblNodeDoubles = (long long)d->tblNodeDoubles;
     a.tips = dp->dev.tips;
-    constexpr int THREADS = 128;
+    // launch shape: threads per CTA / minimum CTAs per SM (P4B_FUSED_VARIANT picks another for tuning)
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("P4B_FUSED_VARIANT");
+        variant = e ? atoi(e) : 0;
+        if (variant < 0 || variant > 4) variant = 0;
+    }
+    static const int kThreads[5] = {128, 128, 256, 64, 128};
+    const int THREADS = kThreads[variant];
     const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
     if (withLike) {
         Node *root = t->root;
@@ -672,24 +681,29 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
             }
             a.patLikes = d->patLikes;
         }
-        if (blocks > d->maxLikeBlocks) { setError("internal: partial buffer too small"); return 1; }
-        a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * p;
+        if (blocks > d->maxLikeBlocks * 4) { setError("internal: partial buffer too small"); return 1; }
+        a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 4 * p;
     }
     const int K = L.nCat * 4;
     const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double);
+    if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
+    typedef void (*KernelFn)(const TreeArgs);
+    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 4>, cl_tree_dna_kernel<4, 128, 3>, cl_tree_dna_kernel<4, 256, 2>,
+                                     cl_tree_dna_kernel<4, 64, 8>, cl_tree_dna_kernel<4, 128, 5>};
+    static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4>, cl_tree_dna_kernel<1, 128, 4>, cl_tree_dna_kernel<1, 256, 2>,
+                                     cl_tree_dna_kernel<1, 64, 8>, cl_tree_dna_kernel<1, 128, 4>};
+    const KernelFn fn = L.nCat == 4 ? kFn4[variant] : kFn1[variant];
     static bool attrSet = false;
     if (!attrSet) {
-        CUDA_TRY(cudaFuncSetAttribute(cl_tree_dna_kernel<4, THREADS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(cl_tree_dna_kernel<1, THREADS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(kFn4[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(kFn1[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attrSet = true;
     }
-    if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
 
     auto flush = [&](int nSteps, bool last) -> int {
         a.nSteps = nSteps;
         a.doLike = (withLike && last) ? 1 : 0;
-        if (L.nCat == 4) cl_tree_dna_kernel<4, THREADS, 4><<<blocks, THREADS, smem, G.stream>>>(a);
-        else cl_tree_dna_kernel<1, THREADS, 4><<<blocks, THREADS, smem, G.stream>>>(a);
+        fn<<<blocks, THREADS, smem, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         G.launches++;
         d->lastCLLaunches++;
@@ -796,7 +810,7 @@ static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
         a.patLikes = d->patLikes;
     }
     const int blocks = (L.ps + 255) / 256;
-    a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * p;
+    a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 4 * p;
     like_kernel<<<blocks, 256, 0, G.stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, d->result + 2 * p);
