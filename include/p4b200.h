@@ -62,6 +62,8 @@ int p4b_setDevice(int device);
  * lo = floor(nPatterns*rank/world).  Default rank 0 of 1.  Call before
  * p4b_newTree. */
 int p4b_setShard(int rank, int world);
+/* The rule p4b_setShard applies: patterns [lo,hi) of nPatterns belong to `rank` of `world`. */
+int p4b_shardRangeFor(int nPatterns, int rank, int world, int *lo, int *hi);
 /* NCCL communicator over the shard ranks.  p4b_commGetUniqueId fills a
  * 128-byte id on rank 0; the host program ships it to the other ranks by any
  * means and every rank calls p4b_commInitRank.  With a communicator present

@@ -25,6 +25,13 @@ const char *p4b_lastError(void) { return lastError(); }
 int p4b_deviceCount(void) { return deviceCount(); }
 int p4b_setDevice(int device) { return setDevice(device); }
 int p4b_setShard(int rank, int world) { return setShard(rank, world); }
+int p4b_shardRangeFor(int nPatterns, int rank, int world, int *lo, int *hi)
+{
+    if (world < 1 || rank < 0 || rank >= world || nPatterns < 0 || !lo || !hi) { setError("p4b_shardRangeFor: bad arguments"); return 1; }
+    *lo = (int)(((long long)nPatterns * rank) / world);
+    *hi = (int)(((long long)nPatterns * (rank + 1)) / world);
+    return 0;
+}
 int p4b_commGetUniqueId(char id128[128]) { return commGetUniqueId(id128); }
 int p4b_commInitRank(const char id128[128], int rank, int world) { return commInitRank(id128, rank, world); }
 int p4b_commDestroy(void) { return commDestroy(); }

@@ -110,11 +110,11 @@ class Data:
         self.alignments = alignments
         self.parts = []
         for a in alignments:
-            if not a.parts:
+            if pf is not None and not a.parts:      # pf None: inputs only (the oracle port reads the strings itself)
                 a._initParts()
             self.parts.extend(a.parts)
-        self.nParts = len(self.parts)
-        self.nTax = self.parts[0].nTax
+        self.nParts = len(alignments)
+        self.nTax = len(alignments[0].sequences)
         self.cData = None
 
     def _setCStuff(self):
@@ -402,7 +402,7 @@ class Tree:
         self.siteLikes = []
         for p in self.data.parts:
             self.siteLikes += self.pf.getSiteLikes(p.cPart)
-        return self.siteLikes
+        return self.siteLikes     # (the reference returns None and leaves the list in self.siteLikes)
 
     # -- the dirty path of Chain.proposeSp (p4/chain.py:668-688) -------------------
     def recalcAfterBranchChange(self):

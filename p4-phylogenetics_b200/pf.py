@@ -69,6 +69,7 @@ _sig("p4b_version", _cp)
 _sig("p4b_deviceCount", _i)
 _sig("p4b_setDevice", _i, _i)
 _sig("p4b_setShard", _i, _i, _i)
+_sig("p4b_shardRangeFor", _i, _i, _i, _i, _ip, _ip)
 _sig("p4b_commGetUniqueId", _i, C.c_char_p)
 _sig("p4b_commInitRank", _i, C.c_char_p, _i, _i)
 _sig("p4b_commDestroy", _i)
@@ -188,6 +189,12 @@ def setDevice(device):
 
 def setShard(rank, world):
     _ok(_lib.p4b_setShard(rank, world))
+
+
+def shardRangeFor(nPatterns, rank, world):
+    lo, hi = C.c_int(), C.c_int()
+    _ok(_lib.p4b_shardRangeFor(nPatterns, rank, world, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
 
 
 def commGetUniqueId():

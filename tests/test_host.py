@@ -1,0 +1,144 @@
+"""CPU tests of the product's host side (no GPU, no compute calls): the C-ABI library
+loads and exports every declared symbol; character coding, pattern compression,
+constant-site masks, gamma rates, Q and the eigensystem match the golden fixtures
+and the reference engine bit for bit where they are integer work."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_io
+import ref_peek
+from util import rel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "p4b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(p4b_\w+)\s*\(", hdr)))
+    assert len(names) > 70
+    lib = ctypes.CDLL(pkg.pf.lib_path)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the compute path must fail loudly, not fall back."""
+    pf = pkg.pf
+    if pf.deviceCount() > 0:
+        pytest.skip("a CUDA device is present")
+    tree = pkg.synth.build_config(pf, 1, nTax=6, nPatterns=40)
+    with pytest.raises(pf.P4bFatal) as e:
+        tree.calcLogLike()
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_bad_character_is_fatal(pkg):
+    pf = pkg.pf
+    p = pf.newPart(2, 4, "ry", 2, "acgt", 4)
+    pf.pokeEquatesTable(p, "10100101")
+    with pytest.raises(pf.P4bFatal):
+        pf.pokeSequences(p, "acgtacgz")
+    pf.freePart(p)
+
+
+@pytest.mark.parametrize("name", golden_io.case_names())
+def test_data_path_matches_golden(pkg, name):
+    meta, arr = golden_io.load(name)
+    tree = golden_io.build_tree(pkg, pkg.pf, meta)
+    for pNum, part in enumerate(tree.data.parts):
+        A = pkg.pf.partArrays(part.cPart)
+        n = int(arr["p%d_nPatterns" % pNum])
+        assert A["nPatterns"] == n
+        assert np.array_equal(A["patterns"][:, :n], arr["p%d_patterns" % pNum])
+        assert np.array_equal(A["patternCounts"][:n], arr["p%d_patternCounts" % pNum])
+        assert np.array_equal(A["sequencePositionPatternIndex"], arr["p%d_sequencePositionPatternIndex" % pNum])
+        assert np.array_equal(A["globalInvarSitesVec"][:n], arr["p%d_globalInvarSitesVec" % pNum])
+        assert np.array_equal(A["globalInvarSitesArray"][:, :n], arr["p%d_globalInvarSitesArray" % pNum])
+    tree.data.free()
+
+
+@pytest.mark.parametrize("seed,nTax,nPat,kind", [(0, 12, 300, "dna"), (1, 7, 50, "dna"), (2, 20, 2000, "protein"), (3, 5, 3, "dna"),
+                                                 (4, 40, 20000, "dna")])
+def test_pattern_compression_bit_exact_vs_reference(pkg, ref_pf, seed, nTax, nPat, kind):
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = P.synth.random_tree(P.pf, nTax, rng)
+    mp = P.synth.dna_model_part(0, rng, 4, pInvar=0.2) if kind == "dna" else P.synth.protein_model_part(0, rng)
+    aln = P.synth.make_alignment(P.pf, t, mp, nPat, rng, kind, gap_frac=0.05, ambig_frac=0.05)
+    mine = aln._initParts()
+    theirs = P.host.Alignment(ref_pf, aln.sequences, aln.symbols, aln.equates)._initParts()
+    A, B = P.pf.partArrays(mine.cPart), ref_peek.part_arrays(theirs.cPart)
+    n = A["nPatterns"]
+    assert n == B["nPatterns"] == nPat
+    for k in ("sequences", "patternCounts", "sequencePositionPatternIndex"):
+        assert np.array_equal(A[k], B[k]), k
+    assert np.array_equal(A["patterns"][:, :n], B["patterns"][:, :n])
+    assert np.array_equal(A["globalInvarSitesVec"][:n], B["globalInvarSitesVec"][:n])
+    assert np.array_equal(A["globalInvarSitesArray"][:, :n], B["globalInvarSitesArray"][:, :n])
+    P.pf.freePart(mine.cPart)
+    ref_pf.freePart(theirs.cPart)
+
+
+def test_gamma_rates_bit_identical_to_reference(pkg, ref_pf):
+    for alpha in (0.1, 0.2, 0.5, 0.73, 1.0, 2.7, 10.0, 100.0, 299.0):
+        for K in (2, 3, 4, 5, 8, 16):
+            f1, r1, f2, r2 = np.zeros(K), np.zeros(K), np.zeros(K), np.zeros(K)
+            pkg.pf.gdasrvCalcRates_np(K, alpha, f1, r1)
+            ref_pf.gdasrvCalcRates_np(K, alpha, f2, r2)
+            assert np.array_equal(r1, r2) and np.array_equal(f1, f2), (alpha, K)
+
+
+def _expm_longdouble(Q, t):
+    A = Q.astype(np.longdouble) * np.longdouble(t)
+    n = A.shape[0]
+    s = max(0, int(np.ceil(np.log2(max(1e-30, float(np.abs(A).sum(1).max()))))) + 8)
+    A = A / np.longdouble(2.0) ** s
+    E = np.eye(n, dtype=np.longdouble)
+    term = np.eye(n, dtype=np.longdouble)
+    for k in range(1, 30):
+        term = term @ A / np.longdouble(k)
+        E = E + term
+    for _ in range(s):
+        E = E @ E
+    return E
+
+
+@pytest.mark.parametrize("name", ["navidi_gtr_g4", "protein_lg_i_g4", "navidi_hetero_ndch2", "grouped_aas_dayhoff6"])
+def test_q_and_eigensystem(pkg, name):
+    """Q is bit-identical to the reference's; V diag(exp(lambda t)) V^-1 reproduces
+    exp(Qt) (80-bit Taylor reference) to 5e-15, at least as well as the reference's P decks do."""
+    pf = pkg.pf
+    meta, arr = golden_io.load(name)
+    tree = golden_io.build_tree(pkg, pf, meta)
+    tree.model.allocCStuff()
+    tree.model.setCStuff()
+    mp = tree.model.parts[0]
+    n1 = tree.nodes[1]
+    c, r = n1.parts[0].compNum, n1.br.parts[0].rMatrixNum
+    pf.p4_resetBQET(tree.model.cModel, 0, c, r)
+    Q = np.zeros((mp.dim, mp.dim))
+    pf.getBigQ(tree.model.cModel, mp.dim, 0, c, r, Q)
+    assert np.array_equal(Q, arr["p0_bigQ_%d_%d" % (c, r)])
+    V, Vi, lam = pf.getEig(tree.model.cModel, mp.dim, 0, c, r)
+    assert np.max(np.abs(V @ Vi - np.eye(mp.dim))) < 5e-15
+    assert np.max(np.abs(V @ np.diag(lam) @ Vi - Q)) < 5e-14
+    worst_mine = worst_ref = 0.0
+    for n in tree.nodes:
+        if n is tree.root or n.parts[0].compNum != c or n.br.parts[0].rMatrixNum != r:
+            continue
+        g = mp.gdasrvs[n.br.parts[0].gdasrvNum] if mp.gdasrvs else None
+        rates = meta["parts"][0]["gdasrvs"][n.br.parts[0].gdasrvNum]["rates"] if g else [1.0]
+        for cat, rate in enumerate(rates):
+            t = n.br.len * rate * mp.relRate / (1.0 - mp.pInvar.val)
+            truth = _expm_longdouble(Q, t)
+            mine = (V * np.exp(lam * t)[None, :]) @ Vi
+            worst_mine = max(worst_mine, float(np.max(np.abs(mine - truth))))
+            worst_ref = max(worst_ref, float(np.max(np.abs(arr["p0_bigP_%d" % n.nodeNum][cat] - truth))))
+    assert worst_mine < 5e-15, (worst_mine, worst_ref)
+    tree.model.free()
+    tree.data.free()
