@@ -49,7 +49,7 @@ def log(*a):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--patterns", type=int, default=N_PATTERNS, help="override the pattern count (testing only)")
@@ -340,7 +340,7 @@ def run_b200(a):
     cl_bytes = float(bpp) * shard                         # algorithmic bytes of one evaluation on this rank
     cl_ms_avg = sum(cl_ms) / len(cl_ms)
     achieved = cl_bytes / (cl_ms_avg * 1e-3) / 1e9
-    kernel = "cl_tree_dna_kernel<4,128> (whole-tree CL recursion + site likelihoods, one launch)" if cl_launches == 1 \
+    kernel = "cl_tree_dna_kernel<4,128,3> (whole-tree CL recursion + site likelihoods, one launch)" if cl_launches == 1 \
         else "cl_dna_kernel<4> (all %d CL launches of one evaluation)" % cl_launches
     roofline = {"bound": "hbm", "kernel": kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,

@@ -75,6 +75,9 @@ int p4b_commDestroy(void);
  * default; 0 selects the one-launch-per-node kernels instead (same results;
  * kept for comparison and profiling). */
 void p4b_setFusedTreeKernel(int on);
+/* 20-state parts use the FP64 tensor-core (mma.sync m8n8k4) CL kernel by default;
+ * 0 selects the FMA kernel instead (same results to rounding; for comparison). */
+void p4b_setTensorCoreKernel(int on);
 /* Count of engine kernel launches since process start (bench.py gpu_launches). */
 long long p4b_kernelLaunchCount(void);
 

@@ -168,6 +168,7 @@ int treeFlushL2(Tree *t);
 int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
 void setFusedEnabled(int on);
+void setDmmaEnabled(int on);
 
 // comm.cpp -- NCCL, loaded at run time
 int commGetUniqueId(char id128[128]);

@@ -544,6 +544,156 @@ cl_dim_kernel(const CLArgs a)
 }
 
 // ---------------------------------------------------------------------------
+// CL, 20 states, FP64 tensor cores (mma.sync m8n8k4 -- tcgen05 has no f64 kind).
+//
+// out[s][pat] = prod_children  sum_x P[s][x] * cl_child[x][pat]  is a (24 x 20) x
+// (20 x 8) product per child, rate category and tile of 8 patterns:
+//   A = P of the child, rows padded 20 -> 24 (3 m-tiles), 5 k-steps of 4 states;
+//       its 15 fragments stay in registers for every pattern tile of the CTA
+//   B = child CL tile, read straight from global memory in fragment order
+//       (4 rows x 64 contiguous bytes per load)
+//   C = the factor; factors of all children are multiplied element-wise in the
+//       accumulator layout and stored (2 adjacent patterns per lane).
+// Warp w handles rate categories w, w+4, ...; CTAs are persistent (3 per SM) and take
+// groups of 32 patterns round-robin.
+// At most two internal children per launch (their A fragments live in
+// registers); wider nodes are chained by the host like in the other kernels.
+// ---------------------------------------------------------------------------
+constexpr int kDmmaGroup = 32;    // patterns a warp handles per iteration (4 n-tiles of 8)
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// Pattern <-> fragment mapping inside a group of 32 patterns starting at pat0:
+// n-tile j (0..3), tile column n (0..7)  <->  pattern pat0 + 4*n + j.
+//   B fragment of tile j: lane (g,q) holds row x0+q, column g -> pattern pat0 + 4g + j:
+//       the 4 tiles of a lane are 4 CONSECUTIVE patterns (two 16-byte loads per row).
+//   C fragment of tile j: lane (g,q) holds row s0+g, columns 2q+i -> patterns pat0 + 8q + 4i + j:
+//       over j and i a lane owns the 8 consecutive patterns pat0 + 8q .. +7 (64-byte stores).
+__global__ void __launch_bounds__(128, 3)
+cl_dmma20_kernel(const __grid_constant__ CLArgs a)
+{
+    constexpr int DIM = 20;
+    extern __shared__ double sm[];   // A fragments [intIdx][cat][15][32], then leaf tables [leafIdx][cat][DIM][W]
+    const int W = a.tblW, nCat = a.nCat;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const size_t ps = (size_t)a.ps;
+    int nLeaf = 0, nInt = 0;
+    for (int c = 0; c < a.nChildren; c++) (a.ch[c].tips != nullptr ? nLeaf : nInt)++;
+    const int fragSize = nCat * 15 * 32, tblSize = nCat * DIM * W;
+    double *sT = sm + nInt * fragSize;
+    {
+        int ii = 0, li = 0;
+        for (int c = 0; c < a.nChildren; c++) {
+            if (a.ch[c].tips == nullptr) {
+                const double *P = a.ch[c].P;
+                for (int i = threadIdx.x; i < fragSize; i += blockDim.x) {
+                    const int l = i & 31, f = (i >> 5) % 15, cat = i / (15 * 32);
+                    const int mt = f / 5, ks = f - mt * 5, srow = mt * 8 + (l >> 2), x = ks * 4 + (l & 3);
+                    sm[ii * fragSize + i] = srow < DIM ? __ldg(P + ((size_t)cat * DIM + srow) * DIM + x) : 0.0;
+                }
+                ii++;
+            } else {
+                for (int i = threadIdx.x; i < tblSize; i += blockDim.x) sT[li * tblSize + i] = __ldg(a.ch[c].tbl + i);
+                li++;
+            }
+        }
+    }
+    __syncthreads();
+
+    // persistent CTAs: groups of 32 patterns are dealt round-robin, so the staging above is
+    // paid once per CTA and every SM ends within one group of the others
+    const int nGroups = a.ps / kDmmaGroup;
+    for (int cat = warp; cat < nCat; cat += 4) {
+        for (int tg = blockIdx.x; tg < nGroups; tg += gridDim.x) {
+            const int pat0 = tg * kDmmaGroup;
+            double acc[24];   // [mt][j][i] -> mt*8 + j*2 + i
+            if (a.accumulate) {
+#pragma unroll
+                for (int mt = 0; mt < 3; mt++) {
+                    const int srow = mt * 8 + g;
+                    const double *o = a.out + ((size_t)cat * DIM + (srow < DIM ? srow : 0)) * ps + pat0 + 8 * q;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const double2 v = ld2(o + 2 * h);   // patterns 8q + 2h, 8q + 2h + 1
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int off = 2 * h + e, i = off >> 2, j = off & 3;
+                            acc[mt * 8 + j * 2 + i] = e ? v.y : v.x;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 24; k++) acc[k] = 1.0;
+            }
+            int ii = 0, li = 0;
+            for (int c = 0; c < a.nChildren; c++) {      // uniform runtime loop
+                double f[24];
+                if (a.ch[c].tips == nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 24; k++) f[k] = 0.0;
+                    const double *cl = a.ch[c].cl + (size_t)cat * DIM * ps + pat0 + 4 * g;
+                    const double *As = sm + ii * fragSize + (size_t)cat * 15 * 32 + lane;
+                    double2 b01[5], b23[5];   // all ten 16-byte loads of the tile group in flight together
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++) {
+                        const double *row = cl + (size_t)(ks * 4 + q) * ps;
+                        b01[ks] = ld2(row);
+                        b23[ks] = ld2(row + 2);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++) {
+                        const double b[4] = {b01[ks].x, b01[ks].y, b23[ks].x, b23[ks].y};
+#pragma unroll
+                        for (int mt = 0; mt < 3; mt++) {
+                            const double aF = As[(mt * 5 + ks) * 32];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) dmma884(f[mt * 8 + j * 2], f[mt * 8 + j * 2 + 1], aF, b[j]);
+                        }
+                    }
+                    ii++;
+                } else {
+                    const uint2 cw = *reinterpret_cast<const uint2 *>(a.ch[c].tips + pat0 + 8 * q);   // 8 tip codes
+                    const double *T = sT + li * tblSize + (size_t)cat * DIM * W;
+#pragma unroll
+                    for (int mt = 0; mt < 3; mt++) {
+                        const int srow = mt * 8 + g;
+                        const double *Tr = T + (srow < DIM ? srow : 0) * W;
+#pragma unroll
+                        for (int off = 0; off < 8; off++) {
+                            const unsigned code = ((off < 4 ? cw.x : cw.y) >> (8 * (off & 3))) & 0xffu;
+                            const int i = off >> 2, j = off & 3;
+                            f[mt * 8 + j * 2 + i] = Tr[code];
+                        }
+                    }
+                    li++;
+                }
+#pragma unroll
+                for (int k = 0; k < 24; k++) acc[k] *= f[k];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) {
+                const int srow = mt * 8 + g;
+                if (srow < DIM) {
+                    double *o = a.out + ((size_t)cat * DIM + srow) * ps + pat0 + 8 * q;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const int o0 = 2 * h, o1 = 2 * h + 1;
+                        st2(o + 2 * h, make_double2(acc[mt * 8 + (o0 & 3) * 2 + (o0 >> 2)], acc[mt * 8 + (o1 & 3) * 2 + (o1 >> 2)]));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // CL, any dim.  grid.y = rate category; one thread per pattern; child values
 // are re-read per parent state (served by L1).  Correctness path for unusual
 // state counts (2, 6-state recodings, ...).

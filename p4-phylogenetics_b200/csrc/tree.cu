@@ -539,6 +539,18 @@ int treeCalculateAllBigPDecks(Tree *t)   // Pf/p4_tree.c p4_calculateAllBigPDeck
 // ---------------------------------------------------------------------------
 // Conditional likelihoods
 // ---------------------------------------------------------------------------
+static bool g_dmmaEnabled = true;
+void setDmmaEnabled(int on) { g_dmmaEnabled = on != 0; }
+
+// Shared memory of the tensor-core kernel: A fragments of the internal children
+// (15 fragments x 32 lanes per category) and the leaf children's lookup tables.
+static size_t dmmaSmemBytes(const CLArgs &a)
+{
+    int nInt = 0, nLeaf = 0;
+    for (int c = 0; c < a.nChildren; c++) (a.ch[c].tips ? nLeaf : nInt)++;
+    return ((size_t)nInt * a.nCat * 15 * 32 + (size_t)nLeaf * a.nCat * 20 * a.tblW) * sizeof(double);
+}
+
 static int launchCL(const CLArgs &a)
 {
     const int maxPer = a.dim * (a.tblW > a.dim ? a.tblW : a.dim);
@@ -549,6 +561,15 @@ static int launchCL(const CLArgs &a)
         const dim3 grid((pairs + 255) / 256);
         if (a.nCat == 4) cl_dna_kernel<4><<<grid, 256, sm, G.stream>>>(a);
         else cl_dna_kernel<1><<<grid, 256, sm, G.stream>>>(a);
+    } else if (a.dim == 20 && g_dmmaEnabled && dmmaSmemBytes(a) <= 200 * 1024) {
+        static bool attrSet = false;
+        if (!attrSet) {
+            CUDA_TRY(cudaFuncSetAttribute(cl_dmma20_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attrSet = true;
+        }
+        int nGrid = a.ps / kDmmaGroup;
+        if (nGrid > G.numSMs * 3) nGrid = G.numSMs * 3;
+        cl_dmma20_kernel<<<nGrid, 128, dmmaSmemBytes(a), G.stream>>>(a);
     } else if (a.dim == 20) {
         const size_t sm = (size_t)a.nChildren * maxPer * sizeof(double);
         const dim3 grid((a.ps + 127) / 128, a.nCat);
@@ -658,6 +679,7 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
         variant = e ? atoi(e) : 0;
         if (variant < 0 || variant > 4) variant = 0;
     }
+    // 0: 128 threads x 3 CTAs/SM (166 registers, no spills) -- measured best on B200
     static const int kThreads[5] = {128, 128, 256, 64, 128};
     const int THREADS = kThreads[variant];
     const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
@@ -688,7 +710,7 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
     const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double);
     if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
     typedef void (*KernelFn)(const TreeArgs);
-    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 4>, cl_tree_dna_kernel<4, 128, 3>, cl_tree_dna_kernel<4, 256, 2>,
+    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3>, cl_tree_dna_kernel<4, 128, 4>, cl_tree_dna_kernel<4, 256, 2>,
                                      cl_tree_dna_kernel<4, 64, 8>, cl_tree_dna_kernel<4, 128, 5>};
     static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4>, cl_tree_dna_kernel<1, 128, 4>, cl_tree_dna_kernel<1, 256, 2>,
                                      cl_tree_dna_kernel<1, 64, 8>, cl_tree_dna_kernel<1, 128, 4>};

@@ -75,6 +75,7 @@ _sig("p4b_commInitRank", _i, C.c_char_p, _i, _i)
 _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
+_sig("p4b_setTensorCoreKernel", None, _i)
 _sig("p4b_newData", _vp, _i, _i)
 _sig("p4b_freeData", None, _vp)
 _sig("p4b_pokePartInData", _i, _vp, _vp, _i)
@@ -214,6 +215,10 @@ def commDestroy():
 
 def setFusedTreeKernel(on):
     _lib.p4b_setFusedTreeKernel(int(on))
+
+
+def setTensorCoreKernel(on):
+    _lib.p4b_setTensorCoreKernel(int(on))
 
 
 def kernelLaunchCount():

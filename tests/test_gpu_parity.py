@@ -234,3 +234,29 @@ def test_star_tree_wide_polytomy(pkg, ref_pf):
         assert rel(tree.calcLogLike(), want) <= LNL_TOL
     finally:
         P.pf.setFusedTreeKernel(1)
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (3, dict(nTax=14, nPatterns=700)),
+    (4, dict(nTax=9, nPatterns=260)),
+])
+def test_tensor_core_kernel_equals_fma_kernel(pkg, ref_pf, cfg, kw):
+    """20-state CL through FP64 mma.sync tiles against the plain FMA kernel and the reference."""
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
+    want = twin.calcLogLike()
+    try:
+        pf.setTensorCoreKernel(0)
+        a = mine.calcLogLike()
+        cl_a = {(p, n.nodeNum): pf.getNodeCL(mine.cTree, n.cNode, p, mp.nGammaCat, mp.dim)
+                for p, mp in enumerate(mine.model.parts) for n in mine.nodes if not n.isLeaf}
+        pf.setTensorCoreKernel(1)
+        b = mine.calcLogLike()
+        cl_b = {(p, n.nodeNum): pf.getNodeCL(mine.cTree, n.cNode, p, mp.nGammaCat, mp.dim)
+                for p, mp in enumerate(mine.model.parts) for n in mine.nodes if not n.isLeaf}
+    finally:
+        pf.setTensorCoreKernel(1)
+    assert rel(a, want) <= LNL_TOL and rel(b, want) <= LNL_TOL
+    assert rel(a, b) <= 1e-13
+    for k in cl_a:
+        assert max_rel_err(cl_b[k], cl_a[k]) < 1e-12, k

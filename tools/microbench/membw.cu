@@ -39,6 +39,22 @@ __global__ void fma64(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+__global__ void dmma64(double *out, int iters)
+{
+    double c0[8], c1[8];
+    for (int i = 0; i < 8; i++) { c0[i] = threadIdx.x + i; c1[i] = i; }
+    const double a = 1.0000001, b = 0.9999999;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+    for (int i = 0; i < 8; i++) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F> float timeit(F f, int reps)
 {
     cudaEvent_t a, b;
@@ -80,6 +96,12 @@ int main()
         float t = timeit([&] { fma64<<<blocks, threads>>>(o, iters); }, 5);
         double flops = 2.0 * 8 * iters * (double)blocks * threads;
         printf("FP64 FMA: %.1f TFLOP/s (%.1f FMA lanes/clk/SM at 1.965 GHz)\n", flops / t / 1e9, flops / 2 / (t * 1e-3) / sm / 1.965e9);
+    }
+    {
+        const int iters = 4096, blocks = sm * 8, threads = 256;
+        float t = timeit([&] { dmma64<<<blocks, threads>>>(o, iters); }, 5);
+        double flops = 2.0 * 256 * 8 * iters * (double)blocks * threads / 32;
+        printf("FP64 mma.sync m8n8k4: %.1f TFLOP/s\n", flops / t / 1e9);
     }
     return 0;
 }
