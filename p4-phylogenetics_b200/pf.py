@@ -545,6 +545,19 @@ def flushL2(cTree):
     _ok(_lib.p4b_flushL2(cTree))
 
 
+_passthrough = None
+
+
+def set_passthrough(module):
+    """Delegate every name this module does not define (GSL wrappers, statistics, simulation, ...
+    -- everything outside the likelihood path) to ``module``, normally the stock ``p4.pf``.
+    Objects created by one engine must not be handed to the other."""
+    global _passthrough
+    _passthrough = module
+
+
 def __getattr__(name):
+    if _passthrough is not None and hasattr(_passthrough, name):
+        return getattr(_passthrough, name)
     raise AttributeError("p4b200 pf mirror has no '%s': only the likelihood hot path of p4.pf is provided "
                          "(SURVEY.md section 8b)" % name)
