@@ -304,6 +304,22 @@ def run_b200(a):
     ms_per_step = dev_ms_max / a.steps
     value = 1000.0 / ms_per_step
 
+    # ---- lnL-only evaluations (opt-in mode, reported beside the headline) -----------
+    pf.setTreeStoresCL(tree.cTree, 0)
+    for _ in range(a.warmup):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    barrier()
+    pf.treeTimerBegin(tree.cTree)
+    for _ in range(a.steps):
+        lnL_lean = pf.p4_treeLogLike(tree.cTree, 0)
+    lean_ms = pf.treeTimerEnd(tree.cTree)
+    barrier()
+    pf.setTreeStoresCL(tree.cTree, 1)
+    tl = torch.tensor([lean_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    lean_value = 1000.0 * a.steps / float(tl.item())
+
     # ---- e2e: Tree.calcLogLike() through the pf mirror ----------------------------
     rng = np.random.default_rng(1)
     for _ in range(2):
@@ -367,6 +383,8 @@ def run_b200(a):
                    "timing": "CUDA events on the engine stream, max over ranks"},
         "pattern_updates_per_s": value * n_internal * nPat,
         "lnL": lnL, "wall_ms_per_step": wall_ms_max / a.steps,
+        "lnl_only": {"value": lean_value, "unit": UNIT, "lnL": lnL_lean,
+                     "note": "opt-in p4b_setTreeStoresCL(0): only the CLs the evaluation re-reads are written; not the headline"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "Tree.calcLogLike(): model.setCStuff + tree.setCStuff + pf.p4_setPrams + pf.p4_treeLogLike", "lnL": lnL_e2e},
         "gpu_launches": launches,

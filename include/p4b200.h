@@ -204,6 +204,12 @@ int p4b_setNodeBigP(p4b_node n, int pNum, const double *in);
  * (dim*dim each, row-major) and eigvals (dim).  Any may be NULL. */
 int p4b_getEig(p4b_model m, int pNum, int compNum, int rMatrixNum,
                double *eigvecs, double *inverseEigvecs, double *eigvals);
+/* lnL-only evaluations.  By default (1) p4b_treeLogLike leaves every node's CL in memory, as the
+ * reference does.  With 0, a whole-tree evaluation of a 4-state part writes only the CLs it must
+ * re-read itself (about a third of them); the rest are recomputed by one storing pass the first time
+ * anything needs them (a node-level update, p4b_partLogLike, p4b_getNodeCL, copy, verify).  Results
+ * are identical; it suits callers that evaluate the whole tree repeatedly (optimisers). */
+int p4b_setTreeStoresCL(p4b_tree t, int on);
 /* Wait for every kernel enqueued on the tree's stream. */
 int p4b_treeSync(p4b_tree t);
 /* Device-side timing on the tree's stream (CUDA events): call Begin, enqueue

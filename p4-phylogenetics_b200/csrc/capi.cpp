@@ -608,6 +608,12 @@ int p4b_treeShardRange(p4b_tree t, int pNum, int *lo, int *hi) { CHECK_PTR(t, "p
 int p4b_getNodeCL(p4b_node n, int pNum, double *out) { CHECK_PTR(n, "p4b_getNodeCL", 1); return nodeGetCL((Node *)n, pNum, out); }
 int p4b_getNodeBigP(p4b_node n, int pNum, double *out) { CHECK_PTR(n, "p4b_getNodeBigP", 1); return nodeGetBigP((Node *)n, pNum, out); }
 int p4b_setNodeBigP(p4b_node n, int pNum, const double *in) { CHECK_PTR(n, "p4b_setNodeBigP", 1); return nodeSetBigP((Node *)n, pNum, in); }
+int p4b_setTreeStoresCL(p4b_tree t, int on)
+{
+    CHECK_PTR(t, "p4b_setTreeStoresCL", 1);
+    ((Tree *)t)->storeCL = on ? 1 : 0;
+    return 0;
+}
 int p4b_treeSync(p4b_tree t) { return treeSync((Tree *)t); }
 int p4b_treeTimerBegin(p4b_tree t) { CHECK_PTR(t, "p4b_treeTimerBegin", 1); return treeTimerBegin((Tree *)t); }
 double p4b_treeTimerEnd(p4b_tree t) { CHECK_PTR(t, "p4b_treeTimerEnd", -1.0); return treeTimerEnd((Tree *)t); }

@@ -120,6 +120,7 @@ struct Node {
     std::vector<int> clSlot;                  // per part: CL arena slot, -1 if none
     std::vector<uint64_t> clStamp;            // per part: id of the computation that filled the CL
     std::vector<uint64_t> pStamp;             // per part: id of the computation that filled the P deck
+    std::vector<char> clResident;             // per part: the CL in the arena is the current one (see Tree::storeCL)
 };
 
 struct TreeDevice;   // tree.cu
@@ -132,6 +133,10 @@ struct Tree {
     int *preOrder = nullptr, *postOrder = nullptr, *passLimit = nullptr;  // borrowed numpy int32
     double *partLikes = nullptr;                                           // borrowed numpy float64
     double logLike = 0.0;
+    // 1 (default, the reference's behaviour): p4_treeLogLike leaves every node's CL in memory.
+    // 0: a whole-tree evaluation writes only the CLs it must re-read itself; the others are
+    // recomputed (one storing pass) the first time anything asks for them.
+    int storeCL = 1;
     TreeDevice *dev = nullptr;
 };
 
@@ -169,6 +174,7 @@ int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
 void setFusedEnabled(int on);
 void setDmmaEnabled(int on);
+int treeEnsureResident(Tree *t, int p);
 
 // comm.cpp -- NCCL, loaded at run time
 int commGetUniqueId(char id128[128]);

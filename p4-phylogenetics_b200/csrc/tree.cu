@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <unordered_map>
+#include <unordered_set>
 
 #include "../../include/p4b200.h"
 #include "engine.h"
@@ -352,6 +354,7 @@ int nodeDeviceCreate(Node *n)
     Tree *t = n->tree;
     n->clSlot.assign(t->nParts, -1);
     n->clStamp.assign(t->nParts, 0);
+    n->clResident.assign(t->nParts, 1);
     n->pStamp.assign(t->nParts, 0);
     if (!n->isLeaf)
         for (int p = 0; p < t->nParts; p++)
@@ -596,6 +599,7 @@ int nodeSetCL(Node *n, int p)
     if (p < 0 || p >= t->nParts) { setError("p4_setConditionalLikelihoodsOfInternalNodePart: bad part %d", p); return 1; }
     if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
     if (nodeEnsureCLSlot(n, p)) return 1;   // a root that is a leaf gets its CL lazily, Pf/p4_node.c:608-626
+    if (treeEnsureResident(t, p)) return 1;
     PartLayout &L = d->parts[p];
     Part *dp = t->data->parts[p];
     CLArgs a;
@@ -637,6 +641,7 @@ int nodeSetCL(Node *n, int p)
         d->lastCLLaunches++;
     }
     n->clStamp[p] = ++G.stamp;
+    n->clResident[p] = 1;
     n->clNeedsUpdating = 0;
     return 0;
 }
@@ -654,7 +659,7 @@ static bool fusedEligible(const PartLayout &L)
 // Build the step list for `order` (nodes to compute, already in dependency
 // order) and launch cl_tree_dna_kernel.  With withLike the root reduction is
 // fused into the same launch and only like_final_kernel follows.
-static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes)
+static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes, bool storeAll = true)
 {
     TreeDevice *d = t->dev;
     PartLayout &L = d->parts[p];
@@ -734,6 +739,8 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
 
     int ns = 0;
     Node *prev = nullptr;   // node whose CL the previous step of THIS launch left in registers
+    std::unordered_map<Node *, int> lastStepOf;   // node -> index of the step that finishes it (this launch)
+    std::unordered_set<Node *> needsMemory;       // nodes some step loads from the arena
     for (size_t oi = 0; oi < order.size(); oi++) {
         Node *n = order[oi];
         if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
@@ -742,6 +749,7 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
         for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
         const int chunks = (nKids + kMaxChildren - 1) / kMaxChildren;
         if (ns + chunks > kMaxSteps) {   // parameter space full: launch what we have, continue in a new launch
+            if (!storeAll) { setError("internal: lnL-only evaluation needs the whole tree in one launch"); return 1; }
             if (flush(ns, false)) return 1;
             ns = 0;
             prev = nullptr;
@@ -761,6 +769,7 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
                 if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return 1; }
                 kind = (c == prev && !prevUsed && st->first) ? 1u : 0u;
                 if (kind == 1u) prevUsed = true;
+                else needsMemory.insert(c);
                 index = (unsigned)c->clSlot[p];
             }
             st->ch[k].a = (int)((kind << 30) | index);
@@ -778,10 +787,22 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
         }
         st->nChildren = (short)k;
         st->store = 1;
+        lastStepOf[n] = ns;
         ns++;
         prev = n;
         n->clStamp[p] = ++G.stamp;
+        n->clResident[p] = storeAll ? 1 : 0;
         n->clNeedsUpdating = 0;
+    }
+    if (!storeAll) {
+        // lnL-only evaluation: keep the store only for nodes that a later step of this launch
+        // re-reads from memory (kind 0); everything else lives and dies in registers.
+        for (int i = 0; i < ns; i++) a.steps[i].store = 0;
+        for (auto &kv : lastStepOf)
+            if (needsMemory.count(kv.first)) {
+                a.steps[kv.second].store = 1;
+                kv.first->clResident[p] = 1;
+            }
     }
     if (ns > 0 || withLike)
         if (flush(ns, true)) return 1;
@@ -795,6 +816,30 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
 
 void setFusedEnabled(int on) { g_fusedEnabled = on != 0; }
 
+// Make every CL of part p current in memory (after an lnL-only evaluation some are not):
+// one storing whole-tree pass over the nodes of the last evaluation order.
+int treeEnsureResident(Tree *t, int p)
+{
+    bool all = true;
+    for (Node *n : t->nodes)
+        if (n && n->clSlot[p] >= 0 && !n->clResident[p]) { all = false; break; }
+    if (all) return 0;
+    std::vector<Node *> order;
+    for (int j = 0; j < t->nNodes; j++) {
+        const int i = t->postOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        Node *n = t->nodes[i];
+        if (n && (!n->isLeaf || n == t->root)) order.push_back(n);
+    }
+    if (!fusedEligible(t->dev->parts[p])) { setError("internal: non-resident CLs on a part without the whole-tree kernel"); return 1; }
+    const int keep = t->dev->lastCLLaunches;
+    if (launchFusedTree(t, p, order, false, false, true)) return 1;
+    t->dev->lastCLLaunches = keep;
+    for (Node *n : t->nodes)
+        if (n && n->clSlot[p] >= 0) n->clResident[p] = 1;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // Log-likelihood
 // ---------------------------------------------------------------------------
@@ -807,6 +852,7 @@ static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
     Node *root = t->root;
     if (!root) { setError("tree has no root"); return 1; }
     if (root->clSlot[p] < 0) { setError("the root has no conditional likelihoods"); return 1; }
+    if (treeEnsureResident(t, p)) return 1;
     const int rc = root->compNums[p];
     if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
     LikeArgs a;
@@ -899,7 +945,8 @@ double treeLogLike(Tree *t, int getSiteLikes)
     std::vector<char> likeDone(t->nParts, 0);
     for (int p = 0; p < t->nParts; p++) {
         if (fusedEligible(d->parts[p])) {
-            if (launchFusedTree(t, p, order, true, getSiteLikes != 0)) return NAN;
+            const bool storeAll = t->storeCL != 0 || order.size() + 8 > (size_t)kMaxSteps;
+            if (launchFusedTree(t, p, order, true, getSiteLikes != 0, storeAll)) return NAN;
             likeDone[p] = 1;
             if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
         } else {
@@ -943,6 +990,8 @@ static int checkTwins(Tree *a, Tree *b)
 int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
 {
     if (checkTwins(a, b)) return 1;
+    for (int p = 0; p < a->nParts; p++)
+        if (treeEnsureResident(a, p)) return 1;
     for (int j = 0; j < a->nNodes; j++) {
         const int i = a->preOrder[j];
         if (i == P4B_NO_ORDER) continue;
@@ -953,10 +1002,11 @@ int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
             if (nA->clSlot[p] < 0) continue;
             if (nodeEnsureCLSlot(nB, p)) return 1;
             // Content that is already identical (same computation id) is not moved again.
-            if (nA->clStamp[p] != nB->clStamp[p]) {
+            if (nA->clStamp[p] != nB->clStamp[p] || !nB->clResident[p]) {
                 CUDA_TRY(cudaMemcpyAsync(nodeCL(nB, p), nodeCL(nA, p), a->dev->parts[p].clNodeDoubles * sizeof(double),
                                          cudaMemcpyDeviceToDevice, G.stream));
                 nB->clStamp[p] = nA->clStamp[p];
+                nB->clResident[p] = 1;
             }
         }
         if (!doAll) nA->clNeedsUpdating = nB->clNeedsUpdating = 0;
@@ -987,6 +1037,8 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
 int treeVerifyDevice(Tree *a, Tree *b)
 {
     if (checkTwins(a, b)) return -1;
+    for (int p = 0; p < a->nParts; p++)
+        if (treeEnsureResident(a, p) || treeEnsureResident(b, p)) return -1;
     TreeDevice *d = a->dev;
     if (cudaMemsetAsync(d->flag, 0, sizeof(int), G.stream) != cudaSuccess) { setError("memset failed"); return -1; }
     int result = 0;
@@ -1032,6 +1084,7 @@ int nodeGetCL(Node *n, int p, double *out)
     Tree *t = n->tree;
     if (!t->dev || p < 0 || p >= t->nParts) { setError("p4b_getNodeCL: bad part"); return 1; }
     if (n->clSlot[p] < 0) { setError("node %d has no conditional likelihoods", n->nodeNum); return 1; }
+    if (treeEnsureResident(t, p)) return 1;
     PartLayout &L = t->dev->parts[p];
     std::vector<double> h(L.clNodeDoubles);
     CUDA_TRY(cudaMemcpyAsync(h.data(), nodeCL(n, p), L.clNodeDoubles * sizeof(double), cudaMemcpyDeviceToHost, G.stream));

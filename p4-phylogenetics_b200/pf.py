@@ -136,6 +136,7 @@ _sig("p4b_treeShardRange", _i, _vp, _i, _ip, _ip)
 _sig("p4b_getNodeCL", _i, _vp, _i, _vp)
 _sig("p4b_getNodeBigP", _i, _vp, _i, _vp)
 _sig("p4b_setNodeBigP", _i, _vp, _i, _vp)
+_sig("p4b_setTreeStoresCL", _i, _vp, _i)
 _sig("p4b_treeSync", _i, _vp)
 _sig("p4b_treeTimerBegin", _i, _vp)
 _sig("p4b_treeTimerEnd", _d, _vp)
@@ -514,6 +515,11 @@ def setNodeBigP(cNode, pNum, bigP):
     """Test hook: overwrite one node's P deck (nCat, dim, dim)."""
     a = np.ascontiguousarray(bigP, dtype=np.float64)
     _ok(_lib.p4b_setNodeBigP(cNode, pNum, a.ctypes.data))
+
+
+def setTreeStoresCL(cTree, on):
+    """0: whole-tree evaluations keep only the CLs they re-read (lnL-only mode); see include/p4b200.h."""
+    _ok(_lib.p4b_setTreeStoresCL(cTree, int(on)))
 
 
 def treeSync(cTree):

@@ -260,3 +260,36 @@ def test_tensor_core_kernel_equals_fma_kernel(pkg, ref_pf, cfg, kw):
     assert rel(a, b) <= 1e-13
     for k in cl_a:
         assert max_rel_err(cl_b[k], cl_a[k]) < 1e-12, k
+
+
+def test_lnl_only_mode_is_transparent(pkg, ref_pf):
+    """p4b_setTreeStoresCL(0): whole-tree evaluations keep only the CLs they re-read; anything that
+    later needs a CL gets it recomputed.  lnL, CLs and the dirty path must be unaffected."""
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, 2, nTax=30, nPatterns=2500)
+    want = twin.calcLogLike()
+    full = mine.calcLogLike()
+    mp = mine.model.parts[0]
+    cl_full = {n.nodeNum: pf.getNodeCL(mine.cTree, n.cNode, 0, mp.nGammaCat, mp.dim) for n in mine.nodes if not n.isLeaf}
+    pf.setTreeStoresCL(mine.cTree, 0)
+    lean = pf.p4_treeLogLike(mine.cTree, 0)
+    assert lean == full and rel(lean, want) <= LNL_TOL
+    # reading a CL after an lnL-only evaluation triggers the storing pass
+    for n in mine.nodes:
+        if not n.isLeaf:
+            assert np.array_equal(pf.getNodeCL(mine.cTree, n.cNode, 0, mp.nGammaCat, mp.dim), cl_full[n.nodeNum])
+    # lnL-only evaluation, then the node-level dirty path
+    rng = np.random.default_rng(9)
+    for _ in range(3):
+        assert pf.p4_treeLogLike(mine.cTree, 0) == full
+        i = int(rng.integers(1, len(mine.nodes)))
+        old = mine.nodes[i].br.len
+        for t in (mine, twin):
+            t.nodes[i].br.len = old * 1.3
+            t.nodes[i].br.lenChanged = True
+        assert rel(mine.recalcAfterBranchChange(), twin.recalcAfterBranchChange()) <= LNL_TOL
+        for t in (mine, twin):
+            t.nodes[i].br.len = old
+            t.nodes[i].br.lenChanged = True
+        assert rel(mine.recalcAfterBranchChange(), want) <= LNL_TOL
+        mine.calcLogLike()
