@@ -78,6 +78,13 @@ void p4b_setFusedTreeKernel(int on);
 /* 20-state parts use the FP64 tensor-core (mma.sync m8n8k4) CL kernel by default;
  * 0 selects the FMA kernel instead (same results to rounding; for comparison). */
 void p4b_setTensorCoreKernel(int on);
+/* Per-pattern log-scalers against underflow (default 0 = off, the reference's behaviour: a site
+ * likelihood that underflows makes the part -1.0e99, Pf/p4_tree.c:1182).  With 1, trees created
+ * AFTERWARDS rescale a pattern's CL by 2^256 whenever its largest entry falls below 2^-256 and
+ * carry the exponent to the root (+4 bytes per pattern and node).  Likelihoods of patterns that
+ * never rescale are bit-identical either way; trees with hundreds of taxa get a finite lnL instead
+ * of the sentinel.  p4b_getNodeCL then returns the rescaled values. */
+void p4b_setScalers(int on);
 /* Count of engine kernel launches since process start (bench.py gpu_launches). */
 long long p4b_kernelLaunchCount(void);
 

@@ -314,118 +314,20 @@ static void matrix_exp(const double *V, const double *Vi, const double *lam, int
         }
 }
 
-/* ---- one part of one tree: Pf/p4_tree.c, Pf/p4_node.c ------------------------------ */
-double pfport_part_loglike(const pfport_tree *T, const pfport_part *D, const pfport_model *M, double *clOut, double *pOut,
-                           double *patLikes)
-{
-    const int dim = M->dim, nCat = M->nCat, nPat = D->nPatterns, nN = T->nNodes;
-    const long clSize = (long)nCat * dim * nPat, pSize = (long)nCat * dim * dim;
-    double *cl = clOut ? clOut : malloc(sizeof(double) * clSize * nN);
-    double *P = pOut ? pOut : malloc(sizeof(double) * pSize * nN);
-    const int nPairs = M->nComps * M->nRMatrices;
-    double *V = malloc(sizeof(double) * dim * dim * nPairs), *Vi = malloc(sizeof(double) * dim * dim * nPairs),
-           *lam = malloc(sizeof(double) * dim * nPairs), *Q = malloc(sizeof(double) * dim * dim);
-    char *have = calloc(nPairs, 1);
-    double lnL = 0.0;
-
-    /* p4_setPramsPart, Pf/p4_tree.c:455-528: Q + eigensystem per used (comp,rMatrix), then P for every non-root node;
-     * p4_calculateBigPDecksPart, Pf/p4_node.c:296-346 for the effective branch lengths. */
-    for (int n = 0; n < nN; n++) {
-        if (n == T->root || T->parent[n] < 0) continue;
-        const int c = T->compNum[n], r = T->rMatrixNum[n], pr = c * M->nRMatrices + r;
-        if (!have[pr]) {
-            pfport_big_q(M->bigR + (long)r * dim * dim, M->comps + (long)c * dim, dim, Q);
-            eigen_reversible(Q, M->comps + (long)c * dim, dim, V + (long)pr * dim * dim, Vi + (long)pr * dim * dim, lam + (long)pr * dim);
-            have[pr] = 1;
-        }
-        for (int cat = 0; cat < nCat; cat++) {
-            double t;
-            const double *rates = M->nGdasrvs ? M->rates + (long)T->gdasrvNum[n] * nCat : NULL;
-            if (M->pInvar == 0.0) t = rates ? (T->brLen[n] * rates[cat] * M->relRate) : (T->brLen[n] * M->relRate);
-            else t = rates ? (T->brLen[n] * rates[cat] * M->relRate) / (1.0 - M->pInvar) : (T->brLen[n] * M->relRate) / (1.0 - M->pInvar);
-            matrix_exp(V + (long)pr * dim * dim, Vi + (long)pr * dim * dim, lam + (long)pr * dim, dim, t,
-                       P + (long)n * pSize + (long)cat * dim * dim);
-        }
-    }
-
-    /* p4_treeLogLike, Pf/p4_tree.c:875-887 with p4_setConditionalLikelihoodsOfInternalNodePart, Pf/p4_node.c:636-857:
-     * loop order pattern -> category -> parent state -> child -> child state; the left child initialises. */
-    for (int j = 0; j < T->nPost; j++) {
-        const int n = T->postOrder[j];
-        if (n < 0) continue;
-        if (T->isLeaf[n] && n != T->root) continue;
-        double *out = cl + (long)n * clSize;
-        for (int pat = 0; pat < nPat; pat++)
-            for (int cat = 0; cat < nCat; cat++)
-                for (int s = 0; s < dim; s++) {
-                    double v = 0.0;
-                    int firstChild = 1;
-                    for (int ch = T->leftChild[n]; ch >= 0; ch = T->sibling[ch]) {
-                        const double *Pc = P + (long)ch * pSize + (long)cat * dim * dim + (long)s * dim;
-                        double f;
-                        if (T->isLeaf[ch]) {
-                            const int code = D->patterns[(long)T->seqNum[ch] * D->stride + pat];
-                            if (code >= 0) f = Pc[code];
-                            else if (code == GAP_CODE || code == QMARK_CODE) f = 1.0;
-                            else {
-                                const int *eq = D->equates + (code - EQUATES_BASE) * dim;
-                                int isN = 1;
-                                for (int x = 0; x < dim; x++)
-                                    if (!eq[x]) { isN = 0; break; }
-                                if (isN) f = 1.0;
-                                else {
-                                    f = 0.0;
-                                    for (int x = 0; x < dim; x++)
-                                        if (eq[x]) f += Pc[x];
-                                }
-                            }
-                        } else {
-                            const double *cc = cl + (long)ch * clSize + (long)cat * dim * nPat + pat;
-                            f = 0.0;
-                            for (int x = 0; x < dim; x++) f = f + (Pc[x] * cc[(long)x * nPat]);
-                        }
-                        v = firstChild ? f : v * f;
-                        firstChild = 0;
-                    }
-                    out[((long)cat * dim + s) * nPat + pat] = v;
-                }
-    }
-
-    /* p4_partLogLike + p4_partLogLikeLoop / ...RootLeaf, Pf/p4_tree.c:924-1378 */
-    {
-        const double *rcl = cl + (long)T->root * clSize;
-        const double *pi = M->comps + (long)T->compNum[T->root] * dim;
-        const double f0 = (1.0 - M->pInvar) / (double)nCat;
-        int bad = 0;
-        for (int pat = 0; pat < nPat && !bad; pat++) {
-            double like = 0.0;
-            for (int cat = 0; cat < nCat; cat++)
-                for (int s = 0; s < dim; s++) {
-                    int use = 1;
-                    if (T->isLeaf[T->root]) {   /* only the root's observed state(s) */
-                        const int code = D->patterns[(long)T->seqNum[T->root] * D->stride + pat];
-                        if (code >= 0) use = (s == code);
-                        else if (code == GAP_CODE || code == QMARK_CODE) use = 1;
-                        else use = D->equates[(code - EQUATES_BASE) * dim + s] != 0;
-                    }
-                    if (use) like += pi[s] * rcl[((long)cat * dim + s) * nPat + pat];
-                }
-            if (M->pInvar != 0.0) {
-                like *= f0;
-                if (D->invarVec[pat] > 0)
-                    for (int s = 0; s < dim; s++)
-                        if (D->invarArray[(long)s * D->stride + pat]) like += pi[s] * M->pInvar;
-            } else if (nCat > 1) {
-                like = like / (double)nCat;
-            }
-            if (patLikes) patLikes[pat] = like;
-            if (like <= 0.0) { bad = 1; break; }
-            lnL = lnL + (D->patternCounts[pat] * log(like));
-        }
-        if (bad) lnL = -1.0e99;
-    }
-    if (!clOut) free(cl);
-    if (!pOut) free(P);
-    free(V); free(Vi); free(lam); free(Q); free(have);
-    return lnL;
-}
+/* The CL recursion and the log-likelihood are instantiated twice: in double, like the reference, and in
+ * long double (x87 80-bit, exponent range 1e-4932), which does not underflow for thousands of taxa and
+ * serves as the independent check of the engine's optional scalers. */
+#define REAL double
+#define FN pfport_part_loglike
+#define LOGF log
+#include "pf_port_cl.inc"
+#undef REAL
+#undef FN
+#undef LOGF
+#define REAL long double
+#define FN pfport_part_loglike_ld
+#define LOGF logl
+#include "pf_port_cl.inc"
+#undef REAL
+#undef FN
+#undef LOGF

@@ -39,4 +39,7 @@ void pfport_big_q(const double *R, const double *pi, int dim, double *Q);
  * patLikes ([nPatterns]) are optional outputs. */
 double pfport_part_loglike(const pfport_tree *T, const pfport_part *D, const pfport_model *M, double *clOut, double *pOut,
                            double *patLikes);
+/* Same, with the CL recursion carried in long double (no underflow for thousands of taxa). */
+double pfport_part_loglike_ld(const pfport_tree *T, const pfport_part *D, const pfport_model *M, double *clOut, double *pOut,
+                              double *patLikes);
 #endif

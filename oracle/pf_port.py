@@ -44,6 +44,8 @@ def lib():
         _lib = C.CDLL(path)
         _lib.pfport_part_loglike.restype = C.c_double
         _lib.pfport_part_loglike.argtypes = [C.POINTER(_Tree), C.POINTER(_Part), C.POINTER(_Model), _dp, _dp, _dp]
+        _lib.pfport_part_loglike_ld.restype = C.c_double
+        _lib.pfport_part_loglike_ld.argtypes = _lib.pfport_part_loglike.argtypes
         _lib.pfport_make_patterns.restype = C.c_int
     return _lib
 
@@ -137,10 +139,11 @@ def protein_big_r(spec):
     return _protein_cache[spec]
 
 
-def tree_loglike(tree, want_arrays=False):
+def tree_loglike(tree, want_arrays=False, long_double=False):
     """lnL of a ``host.Tree`` (data and model attached) computed by the oracle port alone.
 
-    Returns lnL, or (lnL, partLikes, per-part dict of arrays) with ``want_arrays``."""
+    Returns lnL, or (lnL, partLikes, per-part dict of arrays) with ``want_arrays``.
+    ``long_double`` carries the CL recursion in 80-bit floats (no underflow; checks the scalers)."""
     L = lib()
     nodes = tree.nodes
     nN = len(nodes)
@@ -178,7 +181,8 @@ def tree_loglike(tree, want_arrays=False):
             cl = np.zeros((nN, nCat, dim, nPat))
             P = np.zeros((nN, nCat, dim, dim))
             pl = np.zeros(nPat)
-        v = L.pfport_part_loglike(C.byref(T), C.byref(D), C.byref(M), _d(cl) if want_arrays else None,
+        fn = L.pfport_part_loglike_ld if long_double else L.pfport_part_loglike
+        v = fn(C.byref(T), C.byref(D), C.byref(M), _d(cl) if want_arrays else None,
                                   _d(P) if want_arrays else None, _d(pl) if want_arrays else None)
         partLikes.append(v)
         total += v

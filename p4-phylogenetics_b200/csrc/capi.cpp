@@ -38,6 +38,7 @@ int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
 void p4b_setTensorCoreKernel(int on) { setDmmaEnabled(on); }
+void p4b_setScalers(int on) { setScalersEnabled(on); }
 
 // ---- data ------------------------------------------------------------------
 p4b_data p4b_newData(int nTax, int nParts)

@@ -174,6 +174,7 @@ int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
 void setFusedEnabled(int on);
 void setDmmaEnabled(int on);
+void setScalersEnabled(int on);
 int treeEnsureResident(Tree *t, int p);
 
 // comm.cpp -- NCCL, loaded at run time

@@ -56,10 +56,77 @@ struct LikeArgs {
     const uint64_t *eqMask;    // masks of the non-N-like equates
     double *patLikes;          // optional [ps]
     double *partials;          // [2*gridDim.x]: sum count*log(like), count of like <= 0
+    const int *rootScale;      // optional [ps]: the root CL of pattern p carries a factor 2^(256*rootScale[p])
     int ps, nPat, dim, nCat;
     double pInvar;
     double pi[64];
 };
+
+// ---------------------------------------------------------------------------
+// Per-pattern scalers (opt-in, p4b_setScalers).  The reference has none and
+// returns -1e99 once a site likelihood underflows (Pf/p4_tree.c:1182).  When
+// enabled, a node whose largest CL entry for a pattern falls below 2^-256 has
+// that pattern's entries multiplied by 2^256 (exact in binary floating point)
+// and the pattern's exponent count e incremented; e is summed up the tree and
+// the root turns it back into  log(like) - e*256*ln2.  Patterns that never
+// trigger a rescale produce bit-identical likelihoods with scalers on or off.
+// ---------------------------------------------------------------------------
+#define P4B_SCALE_THRESHOLD 8.636168555094445e-78    /* 2^-256 */
+#define P4B_SCALE_FACTOR 1.157920892373162e+77       /* 2^256  */
+#define P4B_SCALE_LOG 177.445678223345993            /* 256*ln(2) */
+
+// count * log-likelihood of one pattern from its (possibly scaled) mixture sum A.
+// Returns false when the site likelihood is not positive.
+__device__ __forceinline__ bool like_term(double A, int e, double pInvar, int nCat, uint64_t invarBits, const double *pi, int dim,
+                                          int count, double *term, double *likeOut)
+{
+    double like;
+    if (pInvar != 0.0) {
+        A *= (1.0 - pInvar) / (double)nCat;          // freqsTimesOneMinusPInvar[0], Pf/p4_tree.c:992-996
+        if (invarBits) {
+            // the constant-site term is unscaled: bring A back down first, then add the terms one
+            // by one in state order like the reference (Pf/p4_tree.c:1073-1091)
+            like = e ? scalbn(A, -256 * e) : A;
+            for (int s = 0; s < dim; s++)
+                if ((invarBits >> s) & 1ull) like += pi[s] * pInvar;
+            *likeOut = like;
+            if (like <= 0.0) return false;
+            *term = (double)count * log(like);
+            return true;
+        }
+        like = A;
+    } else {
+        like = nCat > 1 ? A / (double)nCat : A;
+    }
+    *likeOut = e ? scalbn(like, -256 * e) : like;
+    if (like <= 0.0) return false;
+    *term = (double)count * (e ? log(like) - (double)e * P4B_SCALE_LOG : log(like));
+    return true;
+}
+
+struct RescaleArgs {
+    double *cl;            // the node's CL, rescaled in place
+    int *scOut;            // its exponent counts [ps]
+    const int *scChild[16];
+    int nScChild, nRows, ps;
+};
+
+// Node-level paths with scalers on: one extra pass over the node's CL.
+__global__ void __launch_bounds__(256)
+rescale_kernel(const RescaleArgs a)
+{
+    const int pat = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pat >= a.ps) return;
+    int e = 0;
+    for (int c = 0; c < a.nScChild; c++) e += a.scChild[c][pat];
+    double m = 0.0;
+    for (int k = 0; k < a.nRows; k++) m = fmax(m, a.cl[(size_t)k * a.ps + pat]);
+    if (m < P4B_SCALE_THRESHOLD && m > 0.0) {
+        for (int k = 0; k < a.nRows; k++) a.cl[(size_t)k * a.ps + pat] *= P4B_SCALE_FACTOR;
+        e += 1;
+    }
+    a.scOut[pat] = e;
+}
 
 // ---------------------------------------------------------------------------
 // P(t)
@@ -244,6 +311,7 @@ struct TreeArgs {
     const double *tbl;        // tree's leaf tables, already offset to this part
     long long tblNodeDoubles;
     const uint8_t *tips;      // part's tip rows [nTax][ps]
+    int *scArena;             // per-pattern scaler exponents, [slot][ps] (SCALE kernels only)
     // fused root reduction (doLike != 0)
     int doLike;
     const int *counts;
@@ -262,12 +330,18 @@ __device__ __forceinline__ void cp_async8(double *smemDst, const double *gmemSrc
     const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmemSrc));
 }
+__device__ __forceinline__ void cp_async16(void *smemDst, const void *gmemSrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmemSrc));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Factor contributed by one child to the 4 states of one rate category, for the
 // thread's two patterns.  KIND is a compile-time constant: 0 internal child read
-// from global memory, 1 internal child whose CL is in `cur`, 2 leaf child.
+// from global memory, 1 internal child whose CL is in `cur`, 2 leaf child,
+// 3 internal child prefetched into this thread's shared-memory slots.
 template <int KIND>
 __device__ __forceinline__ void child_factor(int cat, const double *__restrict__ s, int W, unsigned cx, unsigned cy,
                                              const double2 *cur, const double *__restrict__ cl, unsigned ps, double2 f[4])
@@ -283,6 +357,9 @@ __device__ __forceinline__ void child_factor(int cat, const double *__restrict__
         double2 v0, v1, v2, v3;
         if (KIND == 1) {
             v0 = cur[cat * 4 + 0]; v1 = cur[cat * 4 + 1]; v2 = cur[cat * 4 + 2]; v3 = cur[cat * 4 + 3];
+        } else if (KIND == 3) {   // `cl` points at this thread's slot of the prefetch buffer, row stride `ps` double2
+            const double2 *pre = reinterpret_cast<const double2 *>(cl);
+            v0 = pre[(cat * 4 + 0) * ps]; v1 = pre[(cat * 4 + 1) * ps]; v2 = pre[(cat * 4 + 2) * ps]; v3 = pre[(cat * 4 + 3) * ps];
         } else {
             v0 = ld2(cl + (cat * 4 + 0) * ps);
             v1 = ld2(cl + (cat * 4 + 1) * ps);
@@ -309,7 +386,7 @@ __device__ __forceinline__ void child_factor(int cat, const double *__restrict__
 
 // A node with exactly two children -- nearly every node of a binary tree --
 // as straight-line code for one combination of child kinds.
-template <int NCAT, int K0, int K1>
+template <int NCAT, int K0, int K1, int THREADS, bool STORE>
 __device__ __forceinline__ void step_two_children(double2 *cur, const double *__restrict__ s0, const double *__restrict__ s1, int W,
                                                   unsigned c0, unsigned c1, const double *__restrict__ cl0,
                                                   const double *__restrict__ cl1, unsigned ps, double *__restrict__ out)
@@ -317,20 +394,20 @@ __device__ __forceinline__ void step_two_children(double2 *cur, const double *__
 #pragma unroll
     for (int cat = 0; cat < NCAT; cat++) {
         double2 f0[4], f1[4];
-        child_factor<K0>(cat, s0, W, c0 & 0xffu, (c0 >> 8) & 0xffu, cur, cl0, ps, f0);
-        child_factor<K1>(cat, s1, W, c1 & 0xffu, (c1 >> 8) & 0xffu, cur, cl1, ps, f1);
+        child_factor<K0>(cat, s0, W, c0 & 0xffu, (c0 >> 8) & 0xffu, cur, cl0, K0 == 3 ? (unsigned)THREADS : ps, f0);
+        child_factor<K1>(cat, s1, W, c1 & 0xffu, (c1 >> 8) & 0xffu, cur, cl1, K1 == 3 ? (unsigned)THREADS : ps, f1);
 #pragma unroll
         for (int s4 = 0; s4 < 4; s4++) {
             double2 r;
             r.x = f0[s4].x * f1[s4].x;     // (left child) * (sibling), the reference's order
             r.y = f0[s4].y * f1[s4].y;
             cur[cat * 4 + s4] = r;
-            st2(out + (cat * 4 + s4) * ps, r);
+            if (STORE) st2(out + (cat * 4 + s4) * ps, r);
         }
     }
 }
 
-template <int NCAT, int THREADS, int MINB>
+template <int NCAT, int THREADS, int MINB, bool SCALE>
 __global__ void __launch_bounds__(THREADS, MINB)
 cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
 {
@@ -365,17 +442,39 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         return *reinterpret_cast<const unsigned short *>(a.tips + (size_t)(av & 0x3fffffffu) * ps + pat);
     };
 
+    // Prefetch buffer: the one internal child of a two-children step that is not in registers
+    // (kind 3) is copied by cp.async into slots private to each thread, one step ahead, so its
+    // L2 / HBM latency is paid while the previous step computes.  [K][THREADS] double2.
+    double2 *pre = reinterpret_cast<double2 *>(sm + 2 * bufSize) + threadIdx.x;
+    auto usesPre = [&](int stepIdx) -> bool {
+        const StepC &st = a.steps[stepIdx];
+        return st.nChildren == 2 && ((((unsigned)st.ch[0].a >> 30) == 3u) || (((unsigned)st.ch[1].a >> 30) == 3u));
+    };
+    auto prefetch = [&](int stepIdx) {
+        if (!active) return;
+        const StepC &st = a.steps[stepIdx];
+        const unsigned av = (((unsigned)st.ch[0].a >> 30) == 3u) ? (unsigned)st.ch[0].a : (unsigned)st.ch[1].a;
+        const double *cl = a.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat;
+#pragma unroll
+        for (int k = 0; k < K; k++) cp_async16(pre + k * THREADS, cl + (size_t)k * ps);
+    };
+
     double2 cur[K];   // CL of the node computed by the previous step (this thread's two patterns)
 #pragma unroll
     for (int k = 0; k < K; k++) cur[k] = make_double2(1.0, 1.0);
+    int2 ecur = make_int2(0, 0);   // its scaler exponents (SCALE only)
 
+    if (usesPre(0)) prefetch(0);
     stage(0, sm);
     unsigned next0 = tipCode(0, 0), next1 = tipCode(0, 1);   // children 0 and 1 are prefetched one step ahead
     for (int si = 0; si < a.nSteps; si++) {
         cp_async_wait_all();
         __syncthreads();   // buffer si&1 is complete; every thread is done with step si-1
         const double *buf = sm + (si & 1) * bufSize;
+        const bool nextWantsPre = si + 1 < a.nSteps && usesPre(si + 1), curUsesPre = usesPre(si);
+        if (nextWantsPre && !curUsesPre) prefetch(si + 1);    // joins the commit group of stage() below
         if (si + 1 < a.nSteps) stage(si + 1, sm + ((si + 1) & 1) * bufSize);
+        else cp_async_commit();
         const unsigned code0 = next0, code1 = next1;
         next0 = tipCode(si + 1, 0);          // in flight while this step computes
         next1 = tipCode(si + 1, 1);
@@ -385,19 +484,30 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
             double *out = a.arena + a.clNodeDoubles * st.outSlot + pat;
             const unsigned a0 = (unsigned)st.ch[0].a, a1 = (unsigned)st.ch[1].a;
             const unsigned k0 = a0 >> 30, k1 = a1 >> 30;
-            if (nc == 2 && st.first && st.store) {
-                const double *cl0 = a.arena + a.clNodeDoubles * (a0 & 0x3fffffffu) + pat;
-                const double *cl1 = a.arena + a.clNodeDoubles * (a1 & 0x3fffffffu) + pat;
+            int2 esum = make_int2(0, 0);
+            if (SCALE) {     // exponents of the internal children add up
+                if (!st.first) esum = ecur;
+                for (int c = 0; c < nc; c++) {
+                    const unsigned av = (unsigned)st.ch[c].a, kind = av >> 30;
+                    if (kind == 1u) { esum.x += ecur.x; esum.y += ecur.y; }
+                    else if (kind != 2u) {
+                        const int2 ec = *reinterpret_cast<const int2 *>(a.scArena + (size_t)ps * (av & 0x3fffffffu) + pat);
+                        esum.x += ec.x;
+                        esum.y += ec.y;
+                    }
+                }
+            }
+            if (nc == 2 && st.first && st.store && k0 != 0u && k1 != 0u) {
+                const double *pre0 = reinterpret_cast<const double *>(pre);
                 const double *s0 = buf, *s1 = buf + perChild;
-                switch (k0 * 3 + k1) {   // uniform across the CTA
-                case 0: step_two_children<NCAT, 0, 0>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                case 1: step_two_children<NCAT, 0, 1>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                case 2: step_two_children<NCAT, 0, 2>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                case 3: step_two_children<NCAT, 1, 0>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                case 5: step_two_children<NCAT, 1, 2>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                case 6: step_two_children<NCAT, 2, 0>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                case 7: step_two_children<NCAT, 2, 1>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
-                default: step_two_children<NCAT, 2, 2>(cur, s0, s1, W, code0, code1, cl0, cl1, ps, out); break;
+                switch (k0 * 4 + k1) {   // uniform across the CTA; kinds 1 (registers), 2 (leaf), 3 (prefetched)
+                case 1 * 4 + 2: step_two_children<NCAT, 1, 2, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, nullptr, nullptr, ps, out); break;
+                case 2 * 4 + 1: step_two_children<NCAT, 2, 1, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, nullptr, nullptr, ps, out); break;
+                case 1 * 4 + 3: step_two_children<NCAT, 1, 3, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, nullptr, pre0, ps, out); break;
+                case 3 * 4 + 1: step_two_children<NCAT, 3, 1, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, pre0, nullptr, ps, out); break;
+                case 2 * 4 + 3: step_two_children<NCAT, 2, 3, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, nullptr, pre0, ps, out); break;
+                case 3 * 4 + 2: step_two_children<NCAT, 3, 2, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, pre0, nullptr, ps, out); break;
+                default: step_two_children<NCAT, 2, 2, THREADS, !SCALE>(cur, s0, s1, W, code0, code1, nullptr, nullptr, ps, out); break;
                 }
             } else {
                 // any other shape (1 child, 3+ children, chunks of a wide polytomy): generic loop
@@ -426,10 +536,35 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
 #pragma unroll
                     for (int s4 = 0; s4 < 4; s4++) {
                         cur[cat * 4 + s4] = acc[s4];
-                        if (store) st2(out + (cat * 4 + s4) * ps, acc[s4]);
+                        if (!SCALE && store) st2(out + (cat * 4 + s4) * ps, acc[s4]);
                     }
                 }
             }
+            if (SCALE) {
+                double mx = 0.0, my = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; k++) { mx = fmax(mx, cur[k].x); my = fmax(my, cur[k].y); }
+                if (mx < P4B_SCALE_THRESHOLD && mx > 0.0) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) cur[k].x *= P4B_SCALE_FACTOR;
+                    esum.x += 1;
+                }
+                if (my < P4B_SCALE_THRESHOLD && my > 0.0) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) cur[k].y *= P4B_SCALE_FACTOR;
+                    esum.y += 1;
+                }
+                ecur = esum;
+                if (st.store) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) st2(out + k * ps, cur[k]);
+                    *reinterpret_cast<int2 *>(a.scArena + (size_t)ps * st.outSlot + pat) = ecur;
+                }
+            }
+        }
+        if (nextWantsPre && curUsesPre) {   // the buffer was in use by this step: refill it now
+            prefetch(si + 1);
+            cp_async_commit();
         }
     }
 
@@ -446,26 +581,18 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                 if (w < 4) mask = 1ull << w;
                 else if (w > 4) mask = a.eqMask[w - 5];
             }
-            double like = 0.0;
+            double A = 0.0;
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const double v = h ? cur[k].y : cur[k].x;
-                if ((mask >> (k & 3)) & 1ull) like = fma(a.pi[k & 3], v, like);
+                if ((mask >> (k & 3)) & 1ull) A = fma(a.pi[k & 3], v, A);
             }
-            if (a.pInvar != 0.0) {
-                like *= (1.0 - a.pInvar) / (double)NCAT;
-                const uint64_t im = a.invarMask ? a.invarMask[p1] : 0ull;
-                if (im) {
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++)
-                        if ((im >> s4) & 1ull) like += a.pi[s4] * a.pInvar;
-                }
-            } else if (NCAT > 1) {
-                like = like / (double)NCAT;
-            }
+            const int e = SCALE ? (h ? ecur.y : ecur.x) : 0;
+            const uint64_t im = (a.pInvar != 0.0 && a.invarMask) ? a.invarMask[p1] : 0ull;
+            double t1 = 0.0, like = 0.0;
+            if (like_term(A, e, a.pInvar, NCAT, im, a.pi, 4, a.counts[p1], &t1, &like)) term += t1;
+            else bad += 1.0;
             if (a.patLikes) a.patLikes[p1] = like;
-            if (like <= 0.0) bad += 1.0;
-            else term += (double)a.counts[p1] * log(like);
         }
     }
     term = warpSum(term);
@@ -744,23 +871,16 @@ like_kernel(const LikeArgs a)
             if (w < dim) mask = 1ull << w;
             else if (w > dim) mask = a.eqMask[w - dim - 1];
         }
-        double like = 0.0;
+        double A = 0.0;
         for (int c = 0; c < nCat; c++)
             for (int s = 0; s < dim; s++)
-                if ((mask >> s) & 1ull) like = fma(a.pi[s], a.cl[((size_t)c * dim + s) * ps + pat], like);
-        if (a.pInvar != 0.0) {
-            like *= (1.0 - a.pInvar) / (double)nCat;           // freqsTimesOneMinusPInvar[0], Pf/p4_tree.c:992-996
-            const uint64_t im = a.invarMask ? a.invarMask[pat] : 0ull;
-            if (im) {
-                for (int s = 0; s < dim; s++)
-                    if ((im >> s) & 1ull) like += a.pi[s] * a.pInvar;
-            }
-        } else if (nCat > 1) {
-            like = like / (double)nCat;
-        }
+                if ((mask >> s) & 1ull) A = fma(a.pi[s], a.cl[((size_t)c * dim + s) * ps + pat], A);
+        const int e = a.rootScale ? a.rootScale[pat] : 0;
+        const uint64_t im = (a.pInvar != 0.0 && a.invarMask) ? a.invarMask[pat] : 0ull;
+        double t1 = 0.0, like = 0.0;
+        if (like_term(A, e, a.pInvar, nCat, im, a.pi, dim, a.counts[pat], &t1, &like)) term = t1;
+        else bad = 1.0;
         if (a.patLikes) a.patLikes[pat] = like;
-        if (like <= 0.0) bad = 1.0;
-        else term = (double)a.counts[pat] * log(like);
     }
     term = warpSum(term);
     bad = warpSum(bad);

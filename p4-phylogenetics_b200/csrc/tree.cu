@@ -57,6 +57,8 @@ struct Engine {
     int numSMs = 148;
 };
 static Engine G;
+static bool g_useScalers = false;
+void setScalersEnabled(int on) { g_useScalers = on != 0; }
 
 int deviceCount()
 {
@@ -224,12 +226,14 @@ struct PartLayout {
     size_t eqOff = 0;                    // within the equate mask mirror
     int nPairs = 0;                      // nComps*nRMatrices
     double *clArena = nullptr;
+    int *scArena = nullptr;              // per-pattern scaler exponents [slot][ps]; NULL when scalers are off
     int slotsUsed = 0, nSlots = 0;
     std::vector<uint64_t> eigUploaded;   // version of each (comp,rMatrix) mirrored on the device
 };
 
 struct TreeDevice {
     std::vector<PartLayout> parts;
+    bool scalers = false;
     size_t pNodeDoubles = 0, tblNodeDoubles = 0;
     double *P = nullptr, *tbl = nullptr, *eig = nullptr;
     uint64_t *eqMasks = nullptr;
@@ -253,6 +257,7 @@ int treeDeviceCreate(Tree *t)
     if (t->data->nParts != t->model->nParts) { setError("p4_newTree: data has %d parts, model %d", t->data->nParts, t->model->nParts); return 1; }
     TreeDevice *d = new TreeDevice();
     t->dev = d;
+    d->scalers = g_useScalers;
     d->parts.resize(t->nParts);
     size_t eigTotal = 0, eqTotal = 0;
     const int nInternalSlots = t->nNodes - t->nLeaves + 1;   // +1: a root that is a leaf (Pf/p4_node.c:608-626)
@@ -287,6 +292,12 @@ int treeDeviceCreate(Tree *t)
         CUDA_TRY(cudaMalloc(&L.clArena, arenaBytes));
         CUDA_TRY(cudaMemsetAsync(L.clArena, 0, arenaBytes, G.stream));
         d->bytes += (long long)arenaBytes;
+        if (g_useScalers) {
+            const size_t scBytes = sizeof(int) * (size_t)L.ps * (size_t)L.nSlots;
+            CUDA_TRY(cudaMalloc(&L.scArena, scBytes));
+            CUDA_TRY(cudaMemsetAsync(L.scArena, 0, scBytes, G.stream));
+            d->bytes += (long long)scBytes;
+        }
         const int blocks = (L.ps + 255) / 256;
         if (blocks > d->maxLikeBlocks) d->maxLikeBlocks = blocks;
     }
@@ -321,8 +332,10 @@ void treeDeviceDestroy(Tree *t)
     TreeDevice *d = t->dev;
     if (!d) return;
     if (G.stream) cudaStreamSynchronize(G.stream);
-    for (auto &L : d->parts)
+    for (auto &L : d->parts) {
         if (L.clArena) cudaFree(L.clArena);
+        if (L.scArena) cudaFree(L.scArena);
+    }
     if (d->P) cudaFree(d->P);
     if (d->tbl) cudaFree(d->tbl);
     if (d->eig) cudaFree(d->eig);
@@ -366,6 +379,11 @@ static inline double *nodeCL(Node *n, int p)
 {
     PartLayout &L = n->tree->dev->parts[p];
     return L.clArena + L.clNodeDoubles * (size_t)n->clSlot[p];
+}
+static inline int *nodeSC(Node *n, int p)
+{
+    PartLayout &L = n->tree->dev->parts[p];
+    return L.scArena ? L.scArena + (size_t)L.ps * (size_t)n->clSlot[p] : nullptr;
 }
 static inline double *nodeP(Node *n, int p)
 {
@@ -640,6 +658,22 @@ int nodeSetCL(Node *n, int p)
         if (launchCL(a)) return 1;
         d->lastCLLaunches++;
     }
+    if (L.scArena) {   // scalers on: one extra pass rescales the node and sums the children's exponents
+        RescaleArgs r;
+        memset(&r, 0, sizeof(r));
+        r.cl = nodeCL(n, p);
+        r.scOut = nodeSC(n, p);
+        r.nRows = L.nCat * L.dim;
+        r.ps = L.ps;
+        for (Node *c = n->leftChild; c; c = c->sibling)
+            if (!c->isLeaf) {
+                if (r.nScChild == 16) { setError("scalers: node %d has more than 16 internal children", n->nodeNum); return 1; }
+                r.scChild[r.nScChild++] = nodeSC(c, p);
+            }
+        rescale_kernel<<<(L.ps + 255) / 256, 256, 0, G.stream>>>(r);
+        CUDA_TRY(cudaGetLastError());
+        G.launches++;
+    }
     n->clStamp[p] = ++G.stamp;
     n->clResident[p] = 1;
     n->clNeedsUpdating = 0;
@@ -677,6 +711,7 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
     a.tbl = d->tbl + L.tblOff;
     a.tblNodeDoubles = (long long)d->tblNodeDoubles;
     a.tips = dp->dev.tips;
+    a.scArena = L.scArena;
     // launch shape: threads per CTA / minimum CTAs per SM (P4B_FUSED_VARIANT picks another for tuning)
     static int variant = -1;
     if (variant < 0) {
@@ -712,18 +747,27 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
         a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 4 * p;
     }
     const int K = L.nCat * 4;
-    const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double);
+    const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
     if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
     typedef void (*KernelFn)(const TreeArgs);
-    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3>, cl_tree_dna_kernel<4, 128, 4>, cl_tree_dna_kernel<4, 256, 2>,
-                                     cl_tree_dna_kernel<4, 64, 8>, cl_tree_dna_kernel<4, 128, 5>};
-    static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4>, cl_tree_dna_kernel<1, 128, 4>, cl_tree_dna_kernel<1, 256, 2>,
-                                     cl_tree_dna_kernel<1, 64, 8>, cl_tree_dna_kernel<1, 128, 4>};
-    const KernelFn fn = L.nCat == 4 ? kFn4[variant] : kFn1[variant];
+    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 128, 4, false>,
+                                     cl_tree_dna_kernel<4, 256, 2, false>, cl_tree_dna_kernel<4, 64, 8, false>,
+                                     cl_tree_dna_kernel<4, 128, 5, false>};
+    static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 128, 4, false>,
+                                     cl_tree_dna_kernel<1, 256, 2, false>, cl_tree_dna_kernel<1, 64, 8, false>,
+                                     cl_tree_dna_kernel<1, 128, 4, false>};
+    static const KernelFn kFn4s = cl_tree_dna_kernel<4, 128, 3, true>, kFn1s = cl_tree_dna_kernel<1, 128, 4, true>;
+    KernelFn fn = L.nCat == 4 ? kFn4[variant] : kFn1[variant];
+    if (L.scArena) {
+        if (THREADS != 128) { setError("scalers need the default launch shape"); return 1; }
+        fn = L.nCat == 4 ? kFn4s : kFn1s;
+    }
     static bool attrSet = false;
     if (!attrSet) {
         CUDA_TRY(cudaFuncSetAttribute(kFn4[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(kFn1[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(kFn4s, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(kFn1s, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attrSet = true;
     }
 
@@ -787,6 +831,12 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
         }
         st->nChildren = (short)k;
         st->store = 1;
+        if (k == 2 && st->first) {
+            // two-children step: its one re-loaded internal child (if any) goes through the prefetch buffer
+            const unsigned k0 = (unsigned)st->ch[0].a >> 30, k1 = (unsigned)st->ch[1].a >> 30;
+            if (k0 == 0u && k1 != 0u) st->ch[0].a = (int)((3u << 30) | ((unsigned)st->ch[0].a & 0x3fffffffu));
+            else if (k1 == 0u && k0 != 0u) st->ch[1].a = (int)((3u << 30) | ((unsigned)st->ch[1].a & 0x3fffffffu));
+        }
         lastStepOf[n] = ns;
         ns++;
         prev = n;
@@ -862,6 +912,7 @@ static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
     a.invarMask = dp->dev.invarMask;
     a.rootTips = root->isLeaf ? dp->dev.tips + (size_t)root->seqNum * L.ps : nullptr;
     a.eqMask = d->eqMasks + L.eqOff;
+    a.rootScale = nodeSC(root, p);
     a.ps = L.ps;
     a.nPat = L.nPat;
     a.dim = L.dim;
@@ -982,7 +1033,7 @@ static int checkTwins(Tree *a, Tree *b)
     if (a->nNodes != b->nNodes || a->nParts != b->nParts) { setError("the two trees differ in node or part count"); return 1; }
     for (int p = 0; p < a->nParts; p++) {
         const PartLayout &A = a->dev->parts[p], &B = b->dev->parts[p];
-        if (A.clNodeDoubles != B.clNodeDoubles || A.pDoubles != B.pDoubles || A.W != B.W) { setError("the two trees differ in part %d layout", p); return 1; }
+        if (A.clNodeDoubles != B.clNodeDoubles || A.pDoubles != B.pDoubles || A.W != B.W || (A.scArena != nullptr) != (B.scArena != nullptr)) { setError("the two trees differ in part %d layout", p); return 1; }
     }
     return 0;
 }
@@ -1005,6 +1056,8 @@ int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
             if (nA->clStamp[p] != nB->clStamp[p] || !nB->clResident[p]) {
                 CUDA_TRY(cudaMemcpyAsync(nodeCL(nB, p), nodeCL(nA, p), a->dev->parts[p].clNodeDoubles * sizeof(double),
                                          cudaMemcpyDeviceToDevice, G.stream));
+                if (nodeSC(nA, p) && nodeSC(nB, p))
+                    CUDA_TRY(cudaMemcpyAsync(nodeSC(nB, p), nodeSC(nA, p), a->dev->parts[p].ps * sizeof(int), cudaMemcpyDeviceToDevice, G.stream));
                 nB->clStamp[p] = nA->clStamp[p];
                 nB->clResident[p] = 1;
             }

@@ -76,6 +76,7 @@ _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setTensorCoreKernel", None, _i)
+_sig("p4b_setScalers", None, _i)
 _sig("p4b_newData", _vp, _i, _i)
 _sig("p4b_freeData", None, _vp)
 _sig("p4b_pokePartInData", _i, _vp, _vp, _i)
@@ -220,6 +221,11 @@ def setFusedTreeKernel(on):
 
 def setTensorCoreKernel(on):
     _lib.p4b_setTensorCoreKernel(int(on))
+
+
+def setScalers(on):
+    """Per-pattern log-scalers for trees created afterwards (off by default; see include/p4b200.h)."""
+    _lib.p4b_setScalers(int(on))
 
 
 def kernelLaunchCount():

@@ -73,3 +73,11 @@ def test_port_root_leaf_and_sentinel(pkg, ref_pf):
     aln = P.synth.make_alignment(ref_pf, sim_tree, mp, 200, rng, "dna", gap_frac=0.05, ambig_frac=0.05)
     tree.attach(P.host.Data(ref_pf, [aln]), P.host.Model(ref_pf, [mp]))
     assert rel(pf_port.tree_loglike(tree), tree.calcLogLike()) <= 1e-12
+
+
+def test_long_double_port_agrees_with_double_port(pkg):
+    """The 80-bit variant of the port (used to check the engine's scalers) equals the double one in range."""
+    tree = pkg.synth.build_config(None, 1, nTax=12, nPatterns=200)
+    a = pf_port.tree_loglike(tree)
+    b = pf_port.tree_loglike(tree, long_double=True)
+    assert rel(a, b) <= 1e-13
