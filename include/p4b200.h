@@ -185,6 +185,17 @@ double p4b_partLogLike(p4b_tree t, p4b_part p, int pNum, int getSiteLikes);
  * Recomputes the CL of EVERY internal node in postOrder, then all parts. */
 double p4b_treeLogLike(p4b_tree t, int getSiteLikes);
 
+/* ---- the optimisers' seam --------------- Pf/p4_treeOpt.c -- */
+/* The reference's optimisers pack the free model parameters (and optionally all branch lengths)
+ * into one vector and evaluate  p4_unWindParameters -> p4_setPrams -> p4_treeLogLike  per trial
+ * (Pf/p4_treeOpt.c:17-120, 186-565, 579-615).  Same packing order, bounds and unpacking here. */
+int p4b_countParameters(p4b_tree t, int doBrLens);
+int p4b_windUpParameters(p4b_tree t, int doBrLens, double *x, double *lowerBounds, double *upperBounds);
+int p4b_unWindParameters(p4b_tree t, int doBrLens, const double *x);
+double p4b_logLikeForParameters(p4b_tree t, int doBrLens, const double *x);   /* p4_logLikeForNLOpt :579 */
+int p4b_treeNNodes(p4b_tree t);
+int p4b_getBrLens(p4b_tree t, double *outNNodes);                            /* pf.p4_getBrLens :2279; root slot = -1 */
+
 /* ---- cur/prop state transfer ------------------------ Pf/p4_treeCopyVerify.c -- */
 int p4b_copyCondLikes(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyCondLikes :2445, Pf/p4_treeCopyVerify.c:7 */
 int p4b_copyBigPDecks(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyBigPDecks :2462, :33 */

@@ -11,6 +11,7 @@ Python layer issues around the hot path, with the same method names:
     Tree.setCStuff             p4/tree.py:9322-9377
     Tree._commonCStuff         p4/tree.py:9379-9404
     Tree.calcLogLike           p4/tree.py:9406-9415
+    Tree.optLogLike            p4/tree.py:9417-9499
     Tree.getSiteLikes          p4/tree.py:9679-9700
     Chain.proposeSp dirty path p4/chain.py:668-688
     Chain.__init__ / gen state transfer   p4/chain.py:43-46, 1497-1531
@@ -244,6 +245,40 @@ class Model:
             if partNum is None or pNum == partNum:
                 mp.setCStuff(self)
 
+    def restoreFreePrams(self, prams):
+        """After an optimisation: copy the optimised values back (p4/model.py:835-960).  Comps and
+        gdasrv shapes are shared arrays the engine already updated in place."""
+        pos = 0
+        for mp in self.parts:
+            for mt in mp.comps:
+                if mt.free:
+                    pos += mp.dim - 1
+            for mt in mp.rMatrices:
+                if mt.free:
+                    if mt.spec == "2p":
+                        mt.val[0] = prams[pos]
+                        pos += 1
+                    else:
+                        mt.spec = "optimized"
+                        n = mp.dim * (mp.dim - 1) // 2
+                        if mt.val is None or len(mt.val) != n:
+                            mt.val = np.zeros(n)
+                        for k in range(n - 1):
+                            mt.val[k] = prams[pos]
+                            pos += 1
+                        mt.val[-1] = 1.0 - float(np.sum(mt.val[:-1])) if var._rMatrixNormalizeTo1[0] else 1.0
+            for mt in mp.gdasrvs:
+                if mt.free:
+                    mt.val[0] = prams[pos]
+                    pos += 1
+            if mp.pInvar.free:
+                mp.pInvar.val = prams[pos]
+                pos += 1
+        if self.relRatesAreFree:
+            for mp in self.parts[:-1]:
+                mp.relRate = prams[pos]
+                pos += 1
+
     def free(self):
         if self.cModel:
             self.pf.p4_freeModel(self.cModel)
@@ -394,6 +429,25 @@ class Tree:
         self.logLike = self.pf.p4_treeLogLike(self.cTree, 0)
         if verbose:
             print("Tree.calcLogLike(). %f" % self.logLike)
+        return self.logLike
+
+    def optLogLike(self, verbose=0, method="BOBYQA", optBrLens=True):
+        """Maximise the likelihood over the free parameters (p4/tree.py:9417-9499)."""
+        pf = self.pf
+        self._commonCStuff()
+        if method == "BOBYQA":
+            pf.p4_allBOBYQAOptimize(self.cTree, 1 if optBrLens else 0)
+        elif method == "allBrentPowell":
+            pf.p4_allBrentPowellOptimize(self.cTree)
+        else:
+            raise ValueError('method should be "BOBYQA" or "allBrentPowell"')
+        self.logLike = pf.p4_treeLogLike(self.cTree, 0)
+        brLens = pf.p4_getBrLens(self.cTree)
+        for n in self.iterNodesNoRoot():
+            n.br.len = brLens[n.nodeNum]
+        self.model.restoreFreePrams(pf.p4_getFreePrams(self.cTree))
+        if verbose:
+            print("optLogLike = %f" % self.logLike)
         return self.logLike
 
     def getSiteLikes(self):

@@ -129,6 +129,12 @@ _sig("p4b_calculateAllBigPDecksAllParts", _i, _vp)
 _sig("p4b_setConditionalLikelihoodsOfInternalNodePart", _i, _vp, _i)
 _sig("p4b_partLogLike", _d, _vp, _vp, _i, _i)
 _sig("p4b_treeLogLike", _d, _vp, _i)
+_sig("p4b_countParameters", _i, _vp, _i)
+_sig("p4b_windUpParameters", _i, _vp, _i, _vp, _vp, _vp)
+_sig("p4b_unWindParameters", _i, _vp, _i, _vp)
+_sig("p4b_logLikeForParameters", _d, _vp, _i, _vp)
+_sig("p4b_getBrLens", _i, _vp, _vp)
+_sig("p4b_treeNNodes", _i, _vp)
 _sig("p4b_copyCondLikes", _i, _vp, _vp, _i)
 _sig("p4b_copyBigPDecks", _i, _vp, _vp, _i)
 _sig("p4b_copyModelPrams", _i, _vp, _vp)
@@ -474,6 +480,74 @@ def p4_treeLogLike(cTree, getSiteLikes):
     if v != v and (_lastError() or b""):
         _fatal()
     return v
+
+
+# ---- optimisers (callers of the hot path) ----------------------------
+def windUpParameters(cTree, doBrLens=1):
+    """(x, lower, upper): the reference's parameter vector and bounds (Pf/p4_treeOpt.c:17-120)."""
+    n = _lib.p4b_countParameters(cTree, int(doBrLens))
+    if n < 0:
+        _fatal()
+    x, lo, hi = np.zeros(n), np.zeros(n), np.zeros(n)
+    if _lib.p4b_windUpParameters(cTree, int(doBrLens), x.ctypes.data, lo.ctypes.data, hi.ctypes.data) != n:
+        _fatal()
+    return x, lo, hi
+
+
+def logLikeForParameters(cTree, doBrLens, x):
+    """The optimisers' objective: unwind, p4_setPrams, p4_treeLogLike (Pf/p4_treeOpt.c:579-615)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    v = _lib.p4b_logLikeForParameters(cTree, int(doBrLens), x.ctypes.data)
+    if v != v:
+        _fatal()
+    return v
+
+
+def p4_getBrLens(cTree):
+    """pf.p4_getBrLens(cTree) -> list of branch lengths by node number (-1.0 for the root)."""
+    out = np.zeros(_lib.p4b_treeNNodes(cTree))
+    _ok(_lib.p4b_getBrLens(cTree, out.ctypes.data))
+    return [float(v) for v in out]
+
+
+def p4_getFreePrams(cTree):
+    """pf.p4_getFreePrams(cTree) -> list: the model part of the parameter vector."""
+    return [float(v) for v in windUpParameters(cTree, 0)[0]]
+
+
+def p4_allBOBYQAOptimize(cTree, doBrLens=1, verbose=0, maxEvals=None, ftol=1e-8):
+    """pf.p4_allBOBYQAOptimize(cTree, doBrLens): maximise lnL over the free model parameters and,
+    with doBrLens, all branch lengths (Pf/p4_treeOpt.c:617-753).
+
+    The reference hands its objective to nlopt's BOBYQA.  nlopt is a third-party dependency that this
+    engine does not link; the same objective -- evaluated on the GPU in lnL-only mode -- is driven here
+    by SciPy's bounded Powell method, also derivative-free.  The contract is the optimum, not the
+    trajectory.  Returns the number of likelihood evaluations."""
+    from scipy.optimize import minimize
+    x0, lo, hi = windUpParameters(cTree, doBrLens)
+    if len(x0) == 0:
+        return 0
+    _ok(_lib.p4b_setTreeStoresCL(cTree, 0))
+    nEvals = [0]
+
+    def neg(x):
+        nEvals[0] += 1
+        v = logLikeForParameters(cTree, doBrLens, x)
+        return 1.0e99 if v <= -1.0e98 else -v
+
+    try:
+        x0 = np.clip(x0, lo, hi)
+        res = minimize(neg, x0, method="Powell", bounds=list(zip(lo, hi)),
+                       options={"xtol": 1e-6, "ftol": ftol, "maxfev": maxEvals or 200 * len(x0) + 2000})
+        logLikeForParameters(cTree, doBrLens, res.x)
+    finally:
+        _ok(_lib.p4b_setTreeStoresCL(cTree, 1))
+    if verbose:
+        print("p4_allBOBYQAOptimize (Powell on the B200 objective): %d evaluations, lnL %.6f" % (nEvals[0], -res.fun))
+    return nEvals[0]
+
+
+p4_allBrentPowellOptimize = p4_allBOBYQAOptimize
 
 
 # ---- cur/prop state transfer ------------------------------------------------------------
