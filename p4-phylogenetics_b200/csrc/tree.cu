@@ -318,7 +318,7 @@ int treeDeviceCreate(Tree *t)
     d->bytes += (long long)(pBytes + tblBytes + eigTotal * sizeof(double));
     CUDA_TRY(cudaMalloc(&d->result, 2 * sizeof(double) * t->nParts));
     CUDA_TRY(cudaMallocHost(&d->hResult, 2 * sizeof(double) * t->nParts));
-    CUDA_TRY(cudaMalloc(&d->partials, 2 * sizeof(double) * (size_t)d->maxLikeBlocks * 4 * t->nParts));
+    CUDA_TRY(cudaMalloc(&d->partials, 2 * sizeof(double) * (size_t)d->maxLikeBlocks * 8 * t->nParts));
     CUDA_TRY(cudaMalloc(&d->flag, sizeof(int)));
     CUDA_TRY(cudaEventCreate(&d->evA));
     CUDA_TRY(cudaEventCreate(&d->evB));
@@ -712,15 +712,25 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
     a.tblNodeDoubles = (long long)d->tblNodeDoubles;
     a.tips = dp->dev.tips;
     a.scArena = L.scArena;
-    // launch shape: threads per CTA / minimum CTAs per SM (P4B_FUSED_VARIANT picks another for tuning)
-    static int variant = -1;
-    if (variant < 0) {
+    // launch shape: threads per CTA x CTAs per SM.  0: 128x3, 1: 64x6, 2: 32x12 (all 166-168 registers, no
+    // spills); 3: 128x4 and 4: 256x2 are kept for comparison.  Small shards want small CTAs: with 256
+    // patterns per CTA a 125k-pattern shard is 1.1 waves of 444 CTAs, i.e. half the machine idles
+    // through the second wave.  P4B_FUSED_VARIANT overrides the choice (tuning).
+    static int forced = -2;
+    if (forced == -2) {
         const char *e = getenv("P4B_FUSED_VARIANT");
-        variant = e ? atoi(e) : 0;
-        if (variant < 0 || variant > 4) variant = 0;
+        forced = e ? atoi(e) : -1;
+        if (forced < -1 || forced > 4) forced = -1;
     }
-    // 0: 128 threads x 3 CTAs/SM (166 registers, no spills) -- measured best on B200
-    static const int kThreads[5] = {128, 128, 256, 64, 128};
+    static const int kThreads[5] = {128, 64, 32, 128, 256};
+    int variant = forced;
+    if (variant < 0) {
+        // Measured on B200 (tools/sweep_shapes.sh, 200 taxa): 1 M patterns 5.14 / 5.24 / 6.33 ms for shapes 0 / 1 / 2,
+        // 500 k 2.70 / 2.82 / 3.21, 250 k 1.56 / 1.42 / 1.65, 125 k 0.99 / 0.90 / 0.86.  What decides is how many
+        // waves of 128-thread CTAs the shard makes: the last, partial wave leaves SMs idle unless the CTAs are small.
+        const double waves = (double)(L.ps / 2) / (128.0 * 3.0 * G.numSMs);
+        variant = waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
+    }
     const int THREADS = kThreads[variant];
     const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
     if (withLike) {
@@ -743,31 +753,38 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
             }
             a.patLikes = d->patLikes;
         }
-        if (blocks > d->maxLikeBlocks * 4) { setError("internal: partial buffer too small"); return 1; }
-        a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 4 * p;
+        if (blocks > d->maxLikeBlocks * 8) { setError("internal: partial buffer too small"); return 1; }
+        a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
     }
     const int K = L.nCat * 4;
     const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
     if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
     typedef void (*KernelFn)(const TreeArgs);
-    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 128, 4, false>,
-                                     cl_tree_dna_kernel<4, 256, 2, false>, cl_tree_dna_kernel<4, 64, 8, false>,
-                                     cl_tree_dna_kernel<4, 128, 5, false>};
-    static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 128, 4, false>,
-                                     cl_tree_dna_kernel<1, 256, 2, false>, cl_tree_dna_kernel<1, 64, 8, false>,
-                                     cl_tree_dna_kernel<1, 128, 4, false>};
-    static const KernelFn kFn4s = cl_tree_dna_kernel<4, 128, 3, true>, kFn1s = cl_tree_dna_kernel<1, 128, 4, true>;
+    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
+                                     cl_tree_dna_kernel<4, 32, 12, false>, cl_tree_dna_kernel<4, 128, 4, false>,
+                                     cl_tree_dna_kernel<4, 256, 2, false>};
+    static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 64, 8, false>,
+                                     cl_tree_dna_kernel<1, 32, 16, false>, cl_tree_dna_kernel<1, 128, 4, false>,
+                                     cl_tree_dna_kernel<1, 256, 2, false>};
+    static const KernelFn kFn4s[3] = {cl_tree_dna_kernel<4, 128, 3, true>, cl_tree_dna_kernel<4, 64, 6, true>,
+                                      cl_tree_dna_kernel<4, 32, 12, true>};
+    static const KernelFn kFn1s[3] = {cl_tree_dna_kernel<1, 128, 4, true>, cl_tree_dna_kernel<1, 64, 8, true>,
+                                      cl_tree_dna_kernel<1, 32, 16, true>};
     KernelFn fn = L.nCat == 4 ? kFn4[variant] : kFn1[variant];
     if (L.scArena) {
-        if (THREADS != 128) { setError("scalers need the default launch shape"); return 1; }
-        fn = L.nCat == 4 ? kFn4s : kFn1s;
+        if (variant > 2) { setError("scalers need one of the default launch shapes"); return 1; }
+        fn = L.nCat == 4 ? kFn4s[variant] : kFn1s[variant];
     }
     static bool attrSet = false;
     if (!attrSet) {
-        CUDA_TRY(cudaFuncSetAttribute(kFn4[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(kFn1[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(kFn4s, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(kFn1s, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        for (int v = 0; v < 5; v++) {
+            CUDA_TRY(cudaFuncSetAttribute(kFn4[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(kFn1[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        }
+        for (int v = 0; v < 3; v++) {
+            CUDA_TRY(cudaFuncSetAttribute(kFn4s[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(kFn1s[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        }
         attrSet = true;
     }
 
@@ -929,7 +946,7 @@ static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
         a.patLikes = d->patLikes;
     }
     const int blocks = (L.ps + 255) / 256;
-    a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 4 * p;
+    a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
     like_kernel<<<blocks, 256, 0, G.stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, d->result + 2 * p);
