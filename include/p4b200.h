@@ -75,6 +75,14 @@ int p4b_commDestroy(void);
  * default; 0 selects the one-launch-per-node kernels instead (same results;
  * kept for comparison and profiling). */
 void p4b_setFusedTreeKernel(int on);
+/* Node-level calls (p4b_calculateBigPDecks, p4b_setConditionalLikelihoodsOfInternalNodePart) only
+ * QUEUE work by default (1): the reference's callers issue them in dependency order along the dirty
+ * path of a proposal (p4/chain.py:668-688), and the engine runs a tree's whole queue as one P(t)
+ * launch plus one step-list CL launch when the result is needed -- at p4b_partLogLike (which then
+ * fuses the root reduction into the same launch), or before anything else reads or changes the state
+ * the queue depends on (copy, verify, inspection, a topology or parameter change).  Results are
+ * those of immediate execution.  0 launches every call at once (for comparison). */
+void p4b_setDeferredNodeCalls(int on);
 /* 20-state parts use the FP64 tensor-core (mma.sync m8n8k4) CL kernel by default;
  * 0 selects the FMA kernel instead (same results to rounding; for comparison). */
 void p4b_setTensorCoreKernel(int on);
@@ -158,6 +166,11 @@ p4b_node p4b_newNode(int nodeNum, p4b_tree t, int seqNum, int isLeaf, int inTree
 void p4b_freeNode(p4b_node n);                                           /* pf.p4_freeNode :1460 */
 /* relation: 0 parent, 1 leftChild, 2 sibling; relNum = nodeNum of the relative or -1 for none. */
 int p4b_setNodeRelation(p4b_node n, int relation, int relNum);           /* pf.p4_setNodeRelation :1907 */
+/* Addition: everything Tree.setCStuff (p4/tree.py:9338-9355) sends per node -- parent, leftChild,
+ * sibling (node numbers, -1 = none), branch length -- and the root, as arrays indexed by node number:
+ * one call instead of 4*nNodes.  Optional; the per-node calls above remain. */
+int p4b_setTreeCStuff(p4b_tree t, int nNodes, const int *parent, const int *leftChild, const int *sibling,
+                      const double *brLen, int rootNum);
 int p4b_setTreeRoot(p4b_tree t, p4b_node n);                             /* pf.p4_setTreeRoot :1944 */
 int p4b_setBrLen(p4b_node n, double brLen);                              /* pf.p4_setBrLen :1960 */
 int p4b_setCompNum(p4b_node n, int pNum, int val);                       /* pf.p4_setCompNum :2013 */
@@ -195,6 +208,14 @@ int p4b_unWindParameters(p4b_tree t, int doBrLens, const double *x);
 double p4b_logLikeForParameters(p4b_tree t, int doBrLens, const double *x);   /* p4_logLikeForNLOpt :579 */
 int p4b_treeNNodes(p4b_tree t);
 int p4b_getBrLens(p4b_tree t, double *outNNodes);                            /* pf.p4_getBrLens :2279; root slot = -1 */
+
+/* pf.p4_partLogLike for nTrees trees in one go -- the prop trees of Metropolis-coupled chains after
+ * each has had its proposal's node-level calls issued (p4/mcmc.py:2830-2835 runs the chains of a
+ * generation one after the other; they are independent until the swap).  When all trees share the
+ * data part and every tree's queued calls end at its root, all dirty paths and root reductions run as
+ * ONE kernel launch (grid.y = tree), one fold, one all-reduce, one device->host copy.  Otherwise it
+ * is a loop over p4b_partLogLike.  out[i] and each tree's partLikes[pNum] receive the values. */
+int p4b_treesPartLogLike(int nTrees, const p4b_tree *trees, int pNum, double *out);
 
 /* ---- cur/prop state transfer ------------------------ Pf/p4_treeCopyVerify.c -- */
 int p4b_copyCondLikes(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyCondLikes :2445, Pf/p4_treeCopyVerify.c:7 */

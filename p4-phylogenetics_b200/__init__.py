@@ -8,6 +8,7 @@ behind the reference's own ``pf`` extension-module interface.
           (ctypes over libp4b200.so, C ABI in include/p4b200.h)
   host    the callers of that path, mirroring p4's Tree / Model / Data glue
   synth   seeded synthetic inputs for the BASELINE configs
+  mcmc    the pf call protocol of p4's Mcmc / Chain (proposals, dirty path, cur/prop transfer)
   _build  nvcc recipe for libp4b200.so
 
 The directory name is not a Python identifier; import it through the
@@ -17,7 +18,7 @@ ImportError when libp4b200.so is missing -- there is no CPU fallback.
 """
 import importlib
 
-__all__ = ["pf", "host", "synth", "_build"]
+__all__ = ["pf", "host", "synth", "mcmc", "_build"]
 
 
 def __getattr__(name):

@@ -37,6 +37,7 @@ int p4b_commInitRank(const char id128[128], int rank, int world) { return commIn
 int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
+void p4b_setDeferredNodeCalls(int on) { setDeferEnabled(on); }
 void p4b_setTensorCoreKernel(int on) { setDmmaEnabled(on); }
 void p4b_setScalers(int on) { setScalersEnabled(on); }
 
@@ -371,6 +372,7 @@ void p4b_freeNode(p4b_node n)
 {
     Node *N = (Node *)n;
     if (!N) return;
+    if (N->tree && treeHasPending(N->tree)) treeFlushPending(N->tree);   // queued CL calls may name this node
     if (N->tree && N->nodeNum >= 0 && N->nodeNum < (int)N->tree->nodes.size() && N->tree->nodes[N->nodeNum] == N) N->tree->nodes[N->nodeNum] = nullptr;
     delete N;
 }
@@ -379,6 +381,8 @@ int p4b_setNodeRelation(p4b_node n, int relation, int relNum)
 {
     Node *N = (Node *)n;
     CHECK_PTR(N, "p4_setNodeRelation", 1);
+    // queued node-level CL calls were issued against the current topology: run them before it changes
+    if (treeHasPending(N->tree) && treeFlushPending(N->tree)) return 1;
     Node *rel = nullptr;
     if (relNum >= 0) {
         if (relNum >= N->tree->nNodes || !N->tree->nodes[relNum]) { setError("p4_setNodeRelation: node %d does not exist", relNum); return 1; }
@@ -400,6 +404,30 @@ int p4b_setBrLen(p4b_node n, double brLen)
 {
     CHECK_PTR(n, "p4_setBrLen", 1);
     ((Node *)n)->brLen = brLen;
+    return 0;
+}
+// Tree.setCStuff in one call: what 3*nNodes p4_setNodeRelation, p4_setTreeRoot and nNodes-1 p4_setBrLen
+// calls say (p4/tree.py:9338-9355), as arrays indexed by node number.
+int p4b_setTreeCStuff(p4b_tree t, int nNodes, const int *parent, const int *leftChild, const int *sibling, const double *brLen, int rootNum)
+{
+    Tree *T = (Tree *)t;
+    CHECK_PTR(T, "p4b_setTreeCStuff", 1);
+    if (nNodes != T->nNodes || !parent || !leftChild || !sibling || !brLen) { setError("p4b_setTreeCStuff: bad arguments"); return 1; }
+    if (rootNum < 0 || rootNum >= nNodes || !T->nodes[rootNum]) { setError("p4b_setTreeCStuff: bad root %d", rootNum); return 1; }
+    if (treeHasPending(T) && treeFlushPending(T)) return 1;
+    auto at = [&](int i, Node **out) -> int {
+        if (i < 0) { *out = nullptr; return 0; }
+        if (i >= nNodes || !T->nodes[i]) { setError("p4b_setTreeCStuff: node %d does not exist", i); return 1; }
+        *out = T->nodes[i];
+        return 0;
+    };
+    for (int i = 0; i < nNodes; i++) {
+        Node *n = T->nodes[i];
+        if (!n) continue;
+        if (at(parent[i], &n->parent) || at(leftChild[i], &n->leftChild) || at(sibling[i], &n->sibling)) return 1;
+        if (i != rootNum) n->brLen = brLen[i];
+    }
+    T->root = T->nodes[rootNum];
     return 0;
 }
 static int setNum(p4b_node n, int pNum, int val, int which)
@@ -447,6 +475,12 @@ double p4b_treeLogLike(p4b_tree t, int getSiteLikes)
     return treeLogLike((Tree *)t, getSiteLikes);
 }
 
+int p4b_treesPartLogLike(int nTrees, const p4b_tree *trees, int pNum, double *out)
+{
+    if (nTrees < 0 || (nTrees > 0 && (!trees || !out))) { setError("p4b_treesPartLogLike: bad arguments"); return 1; }
+    return treesPartLogLike((Tree **)trees, nTrees, pNum, out);
+}
+
 // ---- state transfer -----------------------------------------------------------
 int p4b_copyCondLikes(p4b_tree a, p4b_tree b, int doAll)
 {
@@ -489,11 +523,15 @@ int p4b_copyModelPrams(p4b_tree ta, p4b_tree tb)   // Pf/p4_treeCopyVerify.c:63-
             }
         for (size_t i = 0; i < a->bqe.size(); i++) {
             Eig &ea = a->bqe[i], &eb = b->bqe[i];
-            if (ea.allocated && eb.allocated) {
+            if (ea.allocated && eb.allocated && (ea.content != eb.content || ea.content == 0)) {
+                // same solve on both sides (content id) -> nothing to move, nothing to re-upload
                 eb.Q = ea.Q;
                 eb.V = ea.V;
                 eb.Vinv = ea.Vinv;
                 eb.lam = ea.lam;
+                eb.inPi = ea.inPi;
+                eb.inR = ea.inR;
+                eb.content = ea.content;
                 eb.version++;
             }
         }

@@ -69,7 +69,9 @@ int setGlobalInvarSitesVec(Part *p);
 struct Eig {                      // cf. p4_bigQAndEigStruct + eigStruct, Pf/pftypes.h:56-72, 219-224
     bool allocated = false;       // reference: aQE->bigQ != NULL
     std::vector<double> Q, V, Vinv, lam;   // dim*dim, dim*dim, dim*dim, dim
+    std::vector<double> inPi, inR;         // the (pi, R) this eigensystem was solved for; empty = none
     uint64_t version = 0;         // bumped on every recompute
+    uint64_t content = 0;         // id of the solve that produced it (equal ids = identical numbers)
 };
 struct Comp { int isFree = 0; double *val = nullptr; };
 struct RMatrix {
@@ -176,6 +178,10 @@ void setFusedEnabled(int on);
 void setDmmaEnabled(int on);
 void setScalersEnabled(int on);
 int treeEnsureResident(Tree *t, int p);
+int treeFlushPending(Tree *t);
+bool treeHasPending(Tree *t);
+void setDeferEnabled(int on);
+int treesPartLogLike(Tree **trees, int n, int p, double *out);
 
 // comm.cpp -- NCCL, loaded at run time
 int commGetUniqueId(char id128[128]);

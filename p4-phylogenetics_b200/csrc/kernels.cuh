@@ -24,12 +24,12 @@ namespace p4b {
 constexpr int kMaxChildren = 6;    // children folded into one CL launch; more are chained
 
 struct PJob {
-    long long pOff;     // into the tree's P deck (doubles)
-    long long tblOff;   // into the tree's leaf tables (doubles); used when tblW > 0
-    long long eigOff;   // into the tree's eigensystem mirror: V | Vinv | lambda
-    long long eqOff;    // into the tree's equate masks
+    double *P;             // the node's P deck for this part: [cat][from][to]
+    double *tbl;           // the node's leaf lookup table; used when tblW > 0
+    const double *eig;     // device mirror of the eigensystem: V | Vinv | lambda
+    const uint64_t *eq;    // masks of the part's non-N-like equates
     int dim, nCat, tblW, nRealEq;
-    long long tOff;     // into the staged doubles: t[cat] effective branch lengths
+    long long tOff;        // into the staged doubles: t[cat] effective branch lengths
 };
 
 struct CLChild {
@@ -132,19 +132,18 @@ rescale_kernel(const RescaleArgs a)
 // P(t)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged, const double *__restrict__ eig,
-               const uint64_t *__restrict__ eqMasks, double *__restrict__ Pdeck, double *__restrict__ tbl)
+pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
 {
     extern __shared__ double sExp[];   // [nCat][dim] exp(lambda_k * t_cat)
     const PJob job = jobs[blockIdx.x];
     const int dim = job.dim, nCat = job.nCat;
-    const double *V = eig + job.eigOff;
+    const double *V = job.eig;
     const double *Vi = V + dim * dim;
     const double *lam = Vi + dim * dim;
     const double *t = staged + job.tOff;
     for (int i = threadIdx.x; i < nCat * dim; i += blockDim.x) sExp[i] = exp(lam[i % dim] * t[i / dim]);
     __syncthreads();
-    double *P = Pdeck + job.pOff;
+    double *P = job.P;
     const int n = nCat * dim * dim;
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const int c = idx / (dim * dim), ij = idx - c * dim * dim, i = ij / dim, j = ij - i * dim;
@@ -156,8 +155,8 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged,
     if (job.tblW > 0) {
         __syncthreads();   // the block's own global writes of P are visible after the barrier
         const int W = job.tblW;
-        double *T = tbl + job.tblOff;
-        const uint64_t *em = eqMasks + job.eqOff;
+        double *T = job.tbl;
+        const uint64_t *em = job.eq;
         const int nT = nCat * dim * W;
         for (int idx = threadIdx.x; idx < nT; idx += blockDim.x) {
             const int k = idx / W, w = idx - k * W;   // k = cat*dim + s
@@ -299,31 +298,38 @@ struct StepC {
     //                         kind 2: leaf child, tip row `index` (its seqNum)
     // b = node number, addressing its P deck / leaf table
 };
-constexpr int kMaxSteps = 512;   // 56 B each: 28 KB of the 32 KB parameter space
 
-struct TreeArgs {
-    int nSteps;
-    int ps, nPat, tblW;
-    double *arena;            // CL arena of the part
-    long long clNodeDoubles;  // arena slot size
+// Several trees that share a data part (the cur/prop trees of Metropolis-coupled chains) can be
+// evaluated by ONE launch: blockIdx.y selects the tree, i.e. its header and its range of the step list.
+struct TreeHdr {
+    double *arena;            // CL arena of the part in this tree
     const double *Pdeck;      // tree's P decks, already offset to this part
-    long long pNodeDoubles;   // stride between nodes
     const double *tbl;        // tree's leaf tables, already offset to this part
-    long long tblNodeDoubles;
-    const uint8_t *tips;      // part's tip rows [nTax][ps]
     int *scArena;             // per-pattern scaler exponents, [slot][ps] (SCALE kernels only)
-    // fused root reduction (doLike != 0)
-    int doLike;
-    const int *counts;
-    const uint64_t *invarMask;
-    const uint8_t *rootTips;
-    const uint64_t *eqMask;
-    double *patLikes;
-    double *partials;
+    double *patLikes;         // optional
+    double *partials;         // [2*gridDim.x]
+    const uint8_t *rootTips;  // non-NULL when the root is a leaf
     double pInvar;
     double pi[4];
+    int stepBase, nSteps;     // this tree's steps are steps[stepBase .. stepBase+nSteps)
+    int doLike, pad;          // fused root reduction
+};
+constexpr int kMaxBatchTrees = 16;
+constexpr int kMaxSteps = 500;   // 56 B each; with the headers the argument block stays under the 32 KB limit
+
+struct TreeArgs {
+    int ps, nPat, tblW, nTrees;
+    long long clNodeDoubles;  // arena slot size
+    long long pNodeDoubles;   // stride between nodes in a P deck
+    long long tblNodeDoubles;
+    const uint8_t *tips;      // part's tip rows [nTax][ps]
+    const int *counts;
+    const uint64_t *invarMask;
+    const uint64_t *eqMask;
+    TreeHdr hdr[kMaxBatchTrees];
     StepC steps[kMaxSteps];
 };
+static_assert(sizeof(TreeArgs) <= 32764, "kernel argument block too large");
 
 __device__ __forceinline__ void cp_async8(double *smemDst, const double *gmemSrc)
 {
@@ -412,6 +418,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
 {
     constexpr int K = NCAT * 4;
+    const TreeHdr &hd = a.hdr[blockIdx.y];     // uniform across the CTA: stays in parameter (constant) memory
     extern __shared__ double sm[];            // 2 buffers x kMaxChildren x perChild
     __shared__ double sSum[THREADS / 32], sBad[THREADS / 32];
     const int W = a.tblW;
@@ -423,11 +430,11 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
 
     // children's P decks / leaf tables of one step -> shared memory, asynchronously
     auto stage = [&](int stepIdx, double *buf) {
-        const StepC &st = a.steps[stepIdx];
+        const StepC &st = a.steps[hd.stepBase + stepIdx];
         const int nc = st.nChildren;
         for (int c = 0; c < nc; c++) {
             const bool leaf = ((unsigned)st.ch[c].a >> 30) == 2u;
-            const double *src = leaf ? a.tbl + a.tblNodeDoubles * st.ch[c].b : a.Pdeck + a.pNodeDoubles * st.ch[c].b;
+            const double *src = leaf ? hd.tbl + a.tblNodeDoubles * st.ch[c].b : hd.Pdeck + a.pNodeDoubles * st.ch[c].b;
             const int n = leaf ? K * W : K * 4;
             for (int i = threadIdx.x; i < n; i += THREADS) cp_async8(buf + c * perChild + i, src + i);
         }
@@ -435,8 +442,8 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
     };
     // tip codes (two patterns = 16 bits) of child c of a step, if it is a leaf
     auto tipCode = [&](int stepIdx, int c) -> unsigned {
-        if (!active || stepIdx >= a.nSteps) return 0u;
-        const StepC &st = a.steps[stepIdx];
+        if (!active || stepIdx >= hd.nSteps) return 0u;
+        const StepC &st = a.steps[hd.stepBase + stepIdx];
         const unsigned av = (unsigned)st.ch[c].a;
         if (c >= st.nChildren || (av >> 30) != 2u) return 0u;
         return *reinterpret_cast<const unsigned short *>(a.tips + (size_t)(av & 0x3fffffffu) * ps + pat);
@@ -447,14 +454,14 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
     // L2 / HBM latency is paid while the previous step computes.  [K][THREADS] double2.
     double2 *pre = reinterpret_cast<double2 *>(sm + 2 * bufSize) + threadIdx.x;
     auto usesPre = [&](int stepIdx) -> bool {
-        const StepC &st = a.steps[stepIdx];
+        const StepC &st = a.steps[hd.stepBase + stepIdx];
         return st.nChildren == 2 && ((((unsigned)st.ch[0].a >> 30) == 3u) || (((unsigned)st.ch[1].a >> 30) == 3u));
     };
     auto prefetch = [&](int stepIdx) {
         if (!active) return;
-        const StepC &st = a.steps[stepIdx];
+        const StepC &st = a.steps[hd.stepBase + stepIdx];
         const unsigned av = (((unsigned)st.ch[0].a >> 30) == 3u) ? (unsigned)st.ch[0].a : (unsigned)st.ch[1].a;
-        const double *cl = a.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat;
+        const double *cl = hd.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat;
 #pragma unroll
         for (int k = 0; k < K; k++) cp_async16(pre + k * THREADS, cl + (size_t)k * ps);
     };
@@ -467,21 +474,21 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
     if (usesPre(0)) prefetch(0);
     stage(0, sm);
     unsigned next0 = tipCode(0, 0), next1 = tipCode(0, 1);   // children 0 and 1 are prefetched one step ahead
-    for (int si = 0; si < a.nSteps; si++) {
+    for (int si = 0; si < hd.nSteps; si++) {
         cp_async_wait_all();
         __syncthreads();   // buffer si&1 is complete; every thread is done with step si-1
         const double *buf = sm + (si & 1) * bufSize;
-        const bool nextWantsPre = si + 1 < a.nSteps && usesPre(si + 1), curUsesPre = usesPre(si);
+        const bool nextWantsPre = si + 1 < hd.nSteps && usesPre(si + 1), curUsesPre = usesPre(si);
         if (nextWantsPre && !curUsesPre) prefetch(si + 1);    // joins the commit group of stage() below
-        if (si + 1 < a.nSteps) stage(si + 1, sm + ((si + 1) & 1) * bufSize);
+        if (si + 1 < hd.nSteps) stage(si + 1, sm + ((si + 1) & 1) * bufSize);
         else cp_async_commit();
         const unsigned code0 = next0, code1 = next1;
         next0 = tipCode(si + 1, 0);          // in flight while this step computes
         next1 = tipCode(si + 1, 1);
         if (active) {
-            const StepC &st = a.steps[si];
+            const StepC &st = a.steps[hd.stepBase + si];
             const int nc = st.nChildren;
-            double *out = a.arena + a.clNodeDoubles * st.outSlot + pat;
+            double *out = hd.arena + a.clNodeDoubles * st.outSlot + pat;
             const unsigned a0 = (unsigned)st.ch[0].a, a1 = (unsigned)st.ch[1].a;
             const unsigned k0 = a0 >> 30, k1 = a1 >> 30;
             int2 esum = make_int2(0, 0);
@@ -491,7 +498,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                     const unsigned av = (unsigned)st.ch[c].a, kind = av >> 30;
                     if (kind == 1u) { esum.x += ecur.x; esum.y += ecur.y; }
                     else if (kind != 2u) {
-                        const int2 ec = *reinterpret_cast<const int2 *>(a.scArena + (size_t)ps * (av & 0x3fffffffu) + pat);
+                        const int2 ec = *reinterpret_cast<const int2 *>(hd.scArena + (size_t)ps * (av & 0x3fffffffu) + pat);
                         esum.x += ec.x;
                         esum.y += ec.y;
                     }
@@ -528,7 +535,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                         } else if (kind == 1u) {
                             child_factor<1>(cat, s, W, 0u, 0u, cur, nullptr, ps, f);
                         } else {
-                            child_factor<0>(cat, s, W, 0u, 0u, cur, a.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat, ps, f);
+                            child_factor<0>(cat, s, W, 0u, 0u, cur, hd.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat, ps, f);
                         }
 #pragma unroll
                         for (int s4 = 0; s4 < 4; s4++) { acc[s4].x *= f[s4].x; acc[s4].y *= f[s4].y; }
@@ -558,7 +565,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                 if (st.store) {
 #pragma unroll
                     for (int k = 0; k < K; k++) st2(out + k * ps, cur[k]);
-                    *reinterpret_cast<int2 *>(a.scArena + (size_t)ps * st.outSlot + pat) = ecur;
+                    *reinterpret_cast<int2 *>(hd.scArena + (size_t)ps * st.outSlot + pat) = ecur;
                 }
             }
         }
@@ -568,7 +575,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         }
     }
 
-    if (!a.doLike) return;
+    if (!hd.doLike) return;
     // ---- root reduction from registers ----------------------------------------
     double term = 0.0, bad = 0.0;
 #pragma unroll
@@ -576,8 +583,8 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         const int p1 = pat + h;
         if (active && p1 < a.nPat) {
             uint64_t mask = ~0ull;
-            if (a.rootTips) {
-                const int w = a.rootTips[p1];
+            if (hd.rootTips) {
+                const int w = hd.rootTips[p1];
                 if (w < 4) mask = 1ull << w;
                 else if (w > 4) mask = a.eqMask[w - 5];
             }
@@ -585,14 +592,14 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const double v = h ? cur[k].y : cur[k].x;
-                if ((mask >> (k & 3)) & 1ull) A = fma(a.pi[k & 3], v, A);
+                if ((mask >> (k & 3)) & 1ull) A = fma(hd.pi[k & 3], v, A);
             }
             const int e = SCALE ? (h ? ecur.y : ecur.x) : 0;
-            const uint64_t im = (a.pInvar != 0.0 && a.invarMask) ? a.invarMask[p1] : 0ull;
+            const uint64_t im = (hd.pInvar != 0.0 && a.invarMask) ? a.invarMask[p1] : 0ull;
             double t1 = 0.0, like = 0.0;
-            if (like_term(A, e, a.pInvar, NCAT, im, a.pi, 4, a.counts[p1], &t1, &like)) term += t1;
+            if (like_term(A, e, hd.pInvar, NCAT, im, hd.pi, 4, a.counts[p1], &t1, &like)) term += t1;
             else bad += 1.0;
-            if (a.patLikes) a.patLikes[p1] = like;
+            if (hd.patLikes) hd.patLikes[p1] = like;
         }
     }
     term = warpSum(term);
@@ -606,8 +613,8 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         term = warpSum(term);
         bad = warpSum(bad);
         if (l == 0) {
-            a.partials[2 * blockIdx.x] = term;
-            a.partials[2 * blockIdx.x + 1] = bad;
+            hd.partials[2 * blockIdx.x] = term;
+            hd.partials[2 * blockIdx.x + 1] = bad;
         }
     }
 }
@@ -920,6 +927,36 @@ like_final_kernel(const double *__restrict__ partials, int n, double *__restrict
         term = warpSum(term);
         bad = warpSum(bad);
         if (l == 0) { result[0] = term; result[1] = bad; }
+    }
+}
+
+// The same fold for several trees evaluated by one batched launch: block b folds tree b.
+struct FinalBatchArgs {
+    const double *partials[kMaxBatchTrees];
+    double *result;     // [2*nTrees]
+    int nBlocks;
+};
+__global__ void __launch_bounds__(256)
+like_final_batch_kernel(const FinalBatchArgs a)
+{
+    __shared__ double sSum[8], sBad[8];
+    const double *partials = a.partials[blockIdx.x];
+    double term = 0.0, bad = 0.0;
+    for (int i = threadIdx.x; i < a.nBlocks; i += blockDim.x) {
+        term += partials[2 * i];
+        bad += partials[2 * i + 1];
+    }
+    term = warpSum(term);
+    bad = warpSum(bad);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sSum[w] = term; sBad[w] = bad; }
+    __syncthreads();
+    if (w == 0) {
+        term = (l < 8) ? sSum[l] : 0.0;
+        bad = (l < 8) ? sBad[l] : 0.0;
+        term = warpSum(term);
+        bad = warpSum(bad);
+        if (l == 0) { a.result[2 * blockIdx.x] = term; a.result[2 * blockIdx.x + 1] = bad; }
     }
 }
 

@@ -331,6 +331,15 @@ int resetBQET(Model *m, int pNum, int cNum, int rNum)
     }
     const double *pi = mp->comps[cNum].val;
     const double *R = mp->rMatrices[rNum].bigR.data();
+    // The reference recomputes every pair a non-root node uses on each p4_setPrams (Pf/p4_tree.c:455-501) --
+    // 118 eigensystems of 20x20 per part for a composition-per-node model.  The eigensystem is a pure function
+    // of (pi, R): when neither changed since it was last solved, the cached one IS the answer.
+    if (e.inPi.size() == (size_t)dim && memcmp(e.inPi.data(), pi, sizeof(double) * dim) == 0 &&
+        memcmp(e.inR.data(), R, sizeof(double) * dim * dim) == 0) {
+        if (mp->bQETneedsReset) mp->bQETneedsReset[cNum * mp->nRMatrices + rNum] = 0;
+        return 0;
+    }
+    e.inPi.clear();   // invalid until the solve below succeeds
     if (buildNormalisedQ(e.Q.data(), R, pi, dim)) return 1;
 
     std::vector<double> S((size_t)dim * dim), U((size_t)dim * dim), sp(dim);
@@ -365,6 +374,10 @@ int resetBQET(Model *m, int pNum, int cNum, int rNum)
             e.Vinv[k * dim + i] = U[i * dim + k] * sp[i];
         }
     e.version++;
+    static uint64_t solveCounter = 0;
+    e.content = ++solveCounter;
+    e.inPi.assign(pi, pi + dim);
+    e.inR.assign(R, R + (size_t)dim * dim);
     if (mp->bQETneedsReset) mp->bQETneedsReset[cNum * mp->nRMatrices + rNum] = 0;
     return 0;
 }

@@ -55,8 +55,15 @@ struct Engine {
     double *flushBuf = nullptr;
     size_t flushN = 0;
     int numSMs = 148;
+    // P(t) jobs are collected engine-wide and launched together right before anything reads a P deck
+    // (a CL launch, a copy, an inspection): the jobs of every chain of a generation share one launch.
+    std::vector<PJob> pJobs;
+    std::vector<double> pT;
+    // results of a batched evaluation of several trees: [2*kMaxBatchTrees] device + pinned host
+    double *dBatch = nullptr, *hBatch = nullptr;
 };
 static Engine G;
+static int flushPJobs();
 static bool g_useScalers = false;
 void setScalersEnabled(int on) { g_useScalers = on != 0; }
 
@@ -110,6 +117,8 @@ static int engineInit()
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, G.device));
     G.numSMs = prop.multiProcessorCount;
+    CUDA_TRY(cudaMalloc(&G.dBatch, 2 * sizeof(double) * kMaxBatchTrees));
+    CUDA_TRY(cudaMallocHost(&G.hBatch, 2 * sizeof(double) * kMaxBatchTrees));
     G.ready = true;
     return 0;
 }
@@ -233,6 +242,10 @@ struct PartLayout {
 
 struct TreeDevice {
     std::vector<PartLayout> parts;
+    // Node-level CL calls on parts the whole-tree kernel serves are not launched one by one: they queue
+    // here (per part, in call order) and run as ONE step-list launch when something needs their result --
+    // normally p4_partLogLike, which then also gets the root reduction fused in.
+    std::vector<std::vector<Node *>> pending;
     bool scalers = false;
     size_t pNodeDoubles = 0, tblNodeDoubles = 0;
     double *P = nullptr, *tbl = nullptr, *eig = nullptr;
@@ -259,6 +272,7 @@ int treeDeviceCreate(Tree *t)
     t->dev = d;
     d->scalers = g_useScalers;
     d->parts.resize(t->nParts);
+    d->pending.resize(t->nParts);
     size_t eigTotal = 0, eqTotal = 0;
     const int nInternalSlots = t->nNodes - t->nLeaves + 1;   // +1: a root that is a leaf (Pf/p4_node.c:608-626)
     for (int p = 0; p < t->nParts; p++) {
@@ -331,6 +345,7 @@ void treeDeviceDestroy(Tree *t)
 {
     TreeDevice *d = t->dev;
     if (!d) return;
+    flushPJobs();   // queued jobs may write into this tree's decks
     if (G.stream) cudaStreamSynchronize(G.stream);
     for (auto &L : d->parts) {
         if (L.clArena) cudaFree(L.clArena);
@@ -407,6 +422,7 @@ static int eigEnsureUploaded(Tree *t, int p, int cNum, int rNum)
     Eig &e = mp->bqe[idx];
     if (!e.allocated) { setError("part %d comp %d rMatrix %d has no eigensystem", p, cNum, rNum); return 1; }
     if (L.eigUploaded[idx] == e.version) return 0;
+    if (flushPJobs()) return 1;   // queued jobs must still see the eigensystem they were issued with
     const int dim = L.dim;
     std::vector<double> buf(L.eigStride);
     memcpy(buf.data(), e.V.data(), sizeof(double) * dim * dim);
@@ -460,8 +476,10 @@ static int hostSetPramsPart(Tree *t, int p)
 }
 
 // Append the P(t) job of (node, part) to the batch.
-static int buildPJob(Node *n, int p, std::vector<PJob> &jobs, std::vector<double> &tvals)
+static int buildPJob(Node *n, int p)
 {
+    std::vector<PJob> &jobs = G.pJobs;
+    std::vector<double> &tvals = G.pT;
     Tree *t = n->tree;
     ModelPart *mp = t->model->parts[p];
     TreeDevice *d = t->dev;
@@ -480,10 +498,10 @@ static int buildPJob(Node *n, int p, std::vector<PJob> &jobs, std::vector<double
         g = mp->gdasrvs[gi];
     }
     PJob j;
-    j.pOff = (long long)(d->pNodeDoubles * (size_t)n->nodeNum + L.pOff);
-    j.tblOff = (long long)(d->tblNodeDoubles * (size_t)n->nodeNum + L.tblOff);
-    j.eigOff = (long long)(L.eigOff + L.eigStride * (size_t)(c * mp->nRMatrices + r));
-    j.eqOff = (long long)L.eqOff;
+    j.P = d->P + d->pNodeDoubles * (size_t)n->nodeNum + L.pOff;
+    j.tbl = d->tbl + d->tblNodeDoubles * (size_t)n->nodeNum + L.tblOff;
+    j.eig = d->eig + L.eigOff + L.eigStride * (size_t)(c * mp->nRMatrices + r);
+    j.eq = d->eqMasks + L.eqOff;
     j.dim = L.dim;
     j.nCat = L.nCat;
     j.tblW = n->isLeaf ? L.W : 0;
@@ -500,61 +518,69 @@ static int buildPJob(Node *n, int p, std::vector<PJob> &jobs, std::vector<double
     return 0;
 }
 
-static int launchPJobs(Tree *t, std::vector<PJob> &jobs, std::vector<double> &tvals)
+static int flushPJobs()
 {
+    std::vector<PJob> &jobs = G.pJobs;
+    std::vector<double> &tvals = G.pT;
     if (jobs.empty()) return 0;
     // one staged block: [tvals | jobs]; job.tOff is relative to the block start
     const size_t tBytes = ((tvals.size() * sizeof(double)) + 15) & ~(size_t)15;
     std::vector<char> blk(tBytes + jobs.size() * sizeof(PJob));
     memcpy(blk.data(), tvals.data(), tvals.size() * sizeof(double));
     memcpy(blk.data() + tBytes, jobs.data(), jobs.size() * sizeof(PJob));
-    void *dblk = nullptr;
-    if (stage(blk.data(), blk.size(), &dblk)) return 1;
     int maxSm = 0;
     for (auto &j : jobs) maxSm = j.nCat * j.dim > maxSm ? j.nCat * j.dim : maxSm;
-    TreeDevice *d = t->dev;
-    pmatrix_kernel<<<(unsigned)jobs.size(), 128, maxSm * sizeof(double), G.stream>>>(
-        reinterpret_cast<const PJob *>((char *)dblk + tBytes), reinterpret_cast<const double *>(dblk), d->eig, d->eqMasks, d->P, d->tbl);
+    const unsigned nJobs = (unsigned)jobs.size();
+    jobs.clear();
+    tvals.clear();
+    void *dblk = nullptr;
+    if (stage(blk.data(), blk.size(), &dblk)) return 1;
+    pmatrix_kernel<<<nJobs, 128, maxSm * sizeof(double), G.stream>>>(
+        reinterpret_cast<const PJob *>((char *)dblk + tBytes), reinterpret_cast<const double *>(dblk));
     CUDA_TRY(cudaGetLastError());
     G.launches++;
     return 0;
 }
 
+static int treeFlushAllPending(Tree *t);
+
 int treeSetPrams(Tree *t, int pNum)
 {
     if (!t->dev) { setError("tree has no device state"); return 1; }
     if (pNum < -1 || pNum >= t->nParts) { setError("p4_setPrams: bad part %d", pNum); return 1; }
-    std::vector<PJob> jobs;
-    std::vector<double> tvals;
+    if (treeFlushAllPending(t)) return 1;   // queued CLs were issued against the old P decks
     for (int p = 0; p < t->nParts; p++) {
         if (pNum >= 0 && p != pNum) continue;
         if (hostSetPramsPart(t, p)) return 1;
+        // mirror every changed eigensystem first (an upload flushes the job queue), then queue all jobs
+        ModelPart *mp = t->model->parts[p];
+        for (Node *n : t->nodes)
+            if (n && n != t->root && !mp->bQETneedsReset[n->compNums[p] * mp->nRMatrices + n->rMatrixNums[p]])
+                if (eigEnsureUploaded(t, p, n->compNums[p], n->rMatrixNums[p])) return 1;
         for (Node *n : t->nodes)
             if (n && n != t->root)
-                if (buildPJob(n, p, jobs, tvals)) return 1;
+                if (buildPJob(n, p)) return 1;
     }
-    return launchPJobs(t, jobs, tvals);
+    return 0;
 }
 
 int nodeCalculateBigPDecks(Node *n)
 {
     Tree *t = n->tree;
-    std::vector<PJob> jobs;
-    std::vector<double> tvals;
+    if (treeFlushAllPending(t)) return 1;
     for (int p = 0; p < t->nParts; p++)
-        if (buildPJob(n, p, jobs, tvals)) return 1;
-    return launchPJobs(t, jobs, tvals);
+        if (buildPJob(n, p)) return 1;
+    return 0;
 }
 
 int treeCalculateAllBigPDecks(Tree *t)   // Pf/p4_tree.c p4_calculateAllBigPDecksAllParts
 {
-    std::vector<PJob> jobs;
-    std::vector<double> tvals;
+    if (treeFlushAllPending(t)) return 1;
     for (int p = 0; p < t->nParts; p++)
         for (Node *n : t->nodes)
             if (n && n != t->root)
-                if (buildPJob(n, p, jobs, tvals)) return 1;
-    return launchPJobs(t, jobs, tvals);
+                if (buildPJob(n, p)) return 1;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -562,6 +588,14 @@ int treeCalculateAllBigPDecks(Tree *t)   // Pf/p4_tree.c p4_calculateAllBigPDeck
 // ---------------------------------------------------------------------------
 static bool g_dmmaEnabled = true;
 void setDmmaEnabled(int on) { g_dmmaEnabled = on != 0; }
+static bool g_fusedEnabled = true;
+static bool g_deferCL = true;
+void setDeferEnabled(int on) { g_deferCL = on != 0; }
+
+static bool fusedEligible(const PartLayout &L)
+{
+    return g_fusedEnabled && L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
+}
 
 // Shared memory of the tensor-core kernel: A fragments of the internal children
 // (15 fragments x 32 lanes per category) and the leaf children's lookup tables.
@@ -574,6 +608,7 @@ static size_t dmmaSmemBytes(const CLArgs &a)
 
 static int launchCL(const CLArgs &a)
 {
+    if (flushPJobs()) return 1;
     const int maxPer = a.dim * (a.tblW > a.dim ? a.tblW : a.dim);
     if (a.dim == 4 && (a.nCat == 4 || a.nCat == 1)) {
         const int K = a.nCat * 4;
@@ -617,8 +652,15 @@ int nodeSetCL(Node *n, int p)
     if (p < 0 || p >= t->nParts) { setError("p4_setConditionalLikelihoodsOfInternalNodePart: bad part %d", p); return 1; }
     if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
     if (nodeEnsureCLSlot(n, p)) return 1;   // a root that is a leaf gets its CL lazily, Pf/p4_node.c:608-626
-    if (treeEnsureResident(t, p)) return 1;
     PartLayout &L = d->parts[p];
+    if (g_deferCL && fusedEligible(L)) {
+        // The callers issue node-level calls in dependency order (the dirty set is decided in
+        // Python): queue, and run the whole queue as one step-list launch when its result is needed.
+        d->pending[p].push_back(n);
+        n->clNeedsUpdating = 0;
+        return 0;
+    }
+    if (treeEnsureResident(t, p)) return 1;
     Part *dp = t->data->parts[p];
     CLArgs a;
     memset(&a, 0, sizeof(a));
@@ -683,78 +725,183 @@ int nodeSetCL(Node *n, int p)
 // ---------------------------------------------------------------------------
 // Whole-tree recursion in one launch (4-state parts)
 // ---------------------------------------------------------------------------
-static bool g_fusedEnabled = true;
 
-static bool fusedEligible(const PartLayout &L)
-{
-    return g_fusedEnabled && L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
-}
+// One job of a batched whole-tree launch: the nodes of one tree to compute, in dependency order.
+struct FusedJob {
+    Tree *t;
+    const std::vector<Node *> *order;
+    bool withLike;       // fuse the root reduction (order must end at the root)
+    bool wantPatLikes;
+    bool storeAll;       // false: lnL-only evaluation, keep only the CLs the launch itself re-reads
+};
 
-// Build the step list for `order` (nodes to compute, already in dependency
-// order) and launch cl_tree_dna_kernel.  With withLike the root reduction is
-// fused into the same launch and only like_final_kernel follows.
-static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes, bool storeAll = true)
+// Launch shape of the whole-tree kernel: threads per CTA x CTAs per SM.  0: 128x3, 1: 64x6, 2: 32x12 (all
+// 166-168 registers, no spills); 3: 128x4 and 4: 256x2 are kept for comparison.  Measured on B200
+// (tools/sweep_shapes.sh, 200 taxa): 1 M patterns 5.14 / 5.24 / 6.33 ms for shapes 0 / 1 / 2, 500 k
+// 2.70 / 2.82 / 3.21, 250 k 1.56 / 1.42 / 1.65, 125 k 0.99 / 0.90 / 0.86.  What decides is how many waves
+// of 128-thread CTAs the launch makes: the last, partial wave leaves SMs idle unless the CTAs are small.
+// P4B_FUSED_VARIANT overrides the choice (tuning).
+static int fusedVariant(int ps, int nTrees)
 {
-    TreeDevice *d = t->dev;
-    PartLayout &L = d->parts[p];
-    Part *dp = t->data->parts[p];
-    ModelPart *mp = t->model->parts[p];
-    static TreeArgs a;   // ~29 KB: too big for the stack of a small thread; the engine is single-threaded
-    memset(&a, 0, offsetof(TreeArgs, steps));
-    a.ps = L.ps;
-    a.nPat = L.nPat;
-    a.tblW = L.W;
-    a.arena = L.clArena;
-    a.clNodeDoubles = (long long)L.clNodeDoubles;
-    a.Pdeck = d->P + L.pOff;
-    a.pNodeDoubles = (long long)d->pNodeDoubles;
-    a.tbl = d->tbl + L.tblOff;
-    a.tblNodeDoubles = (long long)d->tblNodeDoubles;
-    a.tips = dp->dev.tips;
-    a.scArena = L.scArena;
-    // launch shape: threads per CTA x CTAs per SM.  0: 128x3, 1: 64x6, 2: 32x12 (all 166-168 registers, no
-    // spills); 3: 128x4 and 4: 256x2 are kept for comparison.  Small shards want small CTAs: with 256
-    // patterns per CTA a 125k-pattern shard is 1.1 waves of 444 CTAs, i.e. half the machine idles
-    // through the second wave.  P4B_FUSED_VARIANT overrides the choice (tuning).
     static int forced = -2;
     if (forced == -2) {
         const char *e = getenv("P4B_FUSED_VARIANT");
         forced = e ? atoi(e) : -1;
         if (forced < -1 || forced > 4) forced = -1;
     }
-    static const int kThreads[5] = {128, 64, 32, 128, 256};
-    int variant = forced;
-    if (variant < 0) {
-        // Measured on B200 (tools/sweep_shapes.sh, 200 taxa): 1 M patterns 5.14 / 5.24 / 6.33 ms for shapes 0 / 1 / 2,
-        // 500 k 2.70 / 2.82 / 3.21, 250 k 1.56 / 1.42 / 1.65, 125 k 0.99 / 0.90 / 0.86.  What decides is how many
-        // waves of 128-thread CTAs the shard makes: the last, partial wave leaves SMs idle unless the CTAs are small.
-        const double waves = (double)(L.ps / 2) / (128.0 * 3.0 * G.numSMs);
-        variant = waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
+    if (forced >= 0) return forced;
+    const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
+    return waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
+}
+
+// Append the steps of one job to the argument block.  Returns the number of steps written, or -1 on
+// error, or -2 when they do not fit into `room` steps (nothing is modified in that case beyond a.steps).
+static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int p, bool *overflowOk, size_t *resumeAt)
+{
+    Tree *t = job.t;
+    Part *dp = t->data->parts[p];
+    const std::vector<Node *> &order = *job.order;
+    int ns = 0;
+    Node *prev = nullptr;   // node whose CL the previous step of THIS launch left in registers
+    std::unordered_map<Node *, int> lastStepOf;   // node -> index of the step that finishes it (this launch)
+    std::unordered_set<Node *> needsMemory;       // nodes some step loads from the arena
+    size_t oi = resumeAt ? *resumeAt : 0;
+    for (; oi < order.size(); oi++) {
+        Node *n = order[oi];
+        if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return -1; }
+        if (nodeEnsureCLSlot(n, p)) return -1;
+        int nKids = 0;
+        for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
+        const int chunks = (nKids + kMaxChildren - 1) / kMaxChildren;
+        if (ns + chunks > room) {
+            if (!overflowOk || !*overflowOk) return -2;
+            break;   // the caller launches what we have and calls again from *resumeAt
+        }
+        StepC *st = &a.steps[base + ns];
+        st->outSlot = n->clSlot[p];
+        st->first = 1;
+        int k = 0;
+        bool prevUsed = false;
+        for (Node *c = n->leftChild; c; c = c->sibling) {
+            unsigned kind, index;
+            if (c->isLeaf) {
+                if (c->seqNum < 0 || c->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", c->nodeNum, c->seqNum); return -1; }
+                kind = 2u;
+                index = (unsigned)c->seqNum;
+            } else {
+                if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return -1; }
+                kind = (c == prev && !prevUsed && st->first) ? 1u : 0u;
+                if (kind == 1u) prevUsed = true;
+                else needsMemory.insert(c);
+                index = (unsigned)c->clSlot[p];
+            }
+            st->ch[k].a = (int)((kind << 30) | index);
+            st->ch[k].b = c->nodeNum;
+            k++;
+            if (k == kMaxChildren && c->sibling) {   // polytomy wider than one step: continue in the next
+                st->nChildren = (short)k;
+                st->store = 0;
+                ns++;
+                st = &a.steps[base + ns];
+                st->outSlot = n->clSlot[p];
+                st->first = 0;
+                k = 0;
+            }
+        }
+        st->nChildren = (short)k;
+        st->store = 1;
+        if (k == 2 && st->first) {
+            // two-children step: its one re-loaded internal child (if any) goes through the prefetch buffer
+            const unsigned k0 = (unsigned)st->ch[0].a >> 30, k1 = (unsigned)st->ch[1].a >> 30;
+            if (k0 == 0u && k1 != 0u) st->ch[0].a = (int)((3u << 30) | ((unsigned)st->ch[0].a & 0x3fffffffu));
+            else if (k1 == 0u && k0 != 0u) st->ch[1].a = (int)((3u << 30) | ((unsigned)st->ch[1].a & 0x3fffffffu));
+        }
+        lastStepOf[n] = ns;
+        ns++;
+        prev = n;
+        n->clStamp[p] = ++G.stamp;
+        n->clResident[p] = job.storeAll ? 1 : 0;
+        n->clNeedsUpdating = 0;
     }
+    if (resumeAt) *resumeAt = oi;
+    if (overflowOk) *overflowOk = oi < order.size();
+    if (!job.storeAll) {
+        // lnL-only evaluation: keep the store only for nodes that a later step of this launch
+        // re-reads from memory (kind 0); everything else lives and dies in registers.
+        for (int i = 0; i < ns; i++) a.steps[base + i].store = 0;
+        for (auto &kv : lastStepOf)
+            if (needsMemory.count(kv.first)) {
+                a.steps[base + kv.second].store = 1;
+                kv.first->clResident[p] = 1;
+            }
+    }
+    return ns;
+}
+
+// Whole-tree kernel over one or several trees that share data part p (same shard, same model shape).
+// With withLike jobs the per-tree results land in resultDev[2*i] (sum of count*log like) and
+// resultDev[2*i+1] (count of non-positive likelihoods) for job i.
+static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
+{
+    if (nJobs < 1 || nJobs > kMaxBatchTrees) { setError("internal: bad batch size %d", nJobs); return 1; }
+    if (flushPJobs()) return 1;
+    Tree *t0 = jobs[0].t;
+    TreeDevice *d0 = t0->dev;
+    PartLayout &L = d0->parts[p];
+    Part *dp = t0->data->parts[p];
+    static TreeArgs a;   // ~30 KB: too big for the stack of a small thread; the engine is single-threaded
+    memset(&a, 0, offsetof(TreeArgs, steps));
+    a.ps = L.ps;
+    a.nPat = L.nPat;
+    a.tblW = L.W;
+    a.clNodeDoubles = (long long)L.clNodeDoubles;
+    a.pNodeDoubles = (long long)d0->pNodeDoubles;
+    a.tblNodeDoubles = (long long)d0->tblNodeDoubles;
+    a.tips = dp->dev.tips;
+    a.counts = dp->dev.counts;
+    a.invarMask = dp->dev.invarMask;
+    a.eqMask = dp->dev.equateMask;
+    const int variant = fusedVariant(L.ps, nJobs);
+    static const int kThreads[5] = {128, 64, 32, 128, 256};
     const int THREADS = kThreads[variant];
     const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
-    if (withLike) {
-        Node *root = t->root;
-        if (!root || order.empty() || order.back() != root) { setError("fused evaluation: the last node must be the root"); return 1; }
-        const int rc = root->compNums[p];
-        if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
-        a.counts = dp->dev.counts;
-        a.invarMask = dp->dev.invarMask;
-        a.rootTips = root->isLeaf ? dp->dev.tips + (size_t)root->seqNum * L.ps : nullptr;
-        a.eqMask = d->eqMasks + L.eqOff;
-        a.pInvar = mp->pInvar;
-        if (a.pInvar != 0.0 && !a.invarMask) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
-        for (int s = 0; s < 4; s++) a.pi[s] = mp->comps[rc].val[s];
-        if (wantPatLikes) {
-            if (d->patLikesCap < L.ps) {
-                if (d->patLikes) cudaFree(d->patLikes);
-                CUDA_TRY(cudaMalloc(&d->patLikes, sizeof(double) * L.ps));
-                d->patLikesCap = L.ps;
-            }
-            a.patLikes = d->patLikes;
+    bool anyLike = false;
+    for (int i = 0; i < nJobs; i++) {
+        Tree *t = jobs[i].t;
+        TreeDevice *d = t->dev;
+        PartLayout &Li = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != 4 || Li.W != L.W || d->pNodeDoubles != d0->pNodeDoubles ||
+            d->tblNodeDoubles != d0->tblNodeDoubles || (Li.scArena != nullptr) != (L.scArena != nullptr)) {
+            setError("batched evaluation: the trees do not share the data part and model shape");
+            return 1;
         }
-        if (blocks > d->maxLikeBlocks * 8) { setError("internal: partial buffer too small"); return 1; }
-        a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
+        TreeHdr &h = a.hdr[i];
+        h.arena = Li.clArena;
+        h.Pdeck = d->P + Li.pOff;
+        h.tbl = d->tbl + Li.tblOff;
+        h.scArena = Li.scArena;
+        if (jobs[i].withLike) {
+            anyLike = true;
+            Node *root = t->root;
+            if (!root || jobs[i].order->empty() || jobs[i].order->back() != root) { setError("fused evaluation: the last node must be the root"); return 1; }
+            const int rc = root->compNums[p];
+            if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+            h.rootTips = root->isLeaf ? dp->dev.tips + (size_t)root->seqNum * L.ps : nullptr;
+            h.pInvar = mp->pInvar;
+            if (h.pInvar != 0.0 && !a.invarMask) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+            for (int s = 0; s < 4; s++) h.pi[s] = mp->comps[rc].val[s];
+            if (jobs[i].wantPatLikes) {
+                if (d->patLikesCap < L.ps) {
+                    if (d->patLikes) cudaFree(d->patLikes);
+                    CUDA_TRY(cudaMalloc(&d->patLikes, sizeof(double) * L.ps));
+                    d->patLikesCap = L.ps;
+                }
+                h.patLikes = d->patLikes;
+            }
+            if (blocks > d->maxLikeBlocks * 8) { setError("internal: partial buffer too small"); return 1; }
+            h.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
+        }
     }
     const int K = L.nCat * 4;
     const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
@@ -787,105 +934,71 @@ static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, boo
         }
         attrSet = true;
     }
-
-    auto flush = [&](int nSteps, bool last) -> int {
-        a.nSteps = nSteps;
-        a.doLike = (withLike && last) ? 1 : 0;
-        fn<<<blocks, THREADS, smem, G.stream>>>(a);
+    auto launch = [&](int nTrees) -> int {
+        a.nTrees = nTrees;
+        fn<<<dim3(blocks, nTrees), THREADS, smem, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         G.launches++;
-        d->lastCLLaunches++;
+        for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
         return 0;
     };
 
-    int ns = 0;
-    Node *prev = nullptr;   // node whose CL the previous step of THIS launch left in registers
-    std::unordered_map<Node *, int> lastStepOf;   // node -> index of the step that finishes it (this launch)
-    std::unordered_set<Node *> needsMemory;       // nodes some step loads from the arena
-    for (size_t oi = 0; oi < order.size(); oi++) {
-        Node *n = order[oi];
-        if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
-        if (nodeEnsureCLSlot(n, p)) return 1;
-        int nKids = 0;
-        for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
-        const int chunks = (nKids + kMaxChildren - 1) / kMaxChildren;
-        if (ns + chunks > kMaxSteps) {   // parameter space full: launch what we have, continue in a new launch
-            if (!storeAll) { setError("internal: lnL-only evaluation needs the whole tree in one launch"); return 1; }
-            if (flush(ns, false)) return 1;
-            ns = 0;
-            prev = nullptr;
+    if (nJobs == 1) {
+        // one tree: a step list longer than the argument block is cut into several launches
+        size_t at = 0;
+        for (;;) {
+            bool more = jobs[0].storeAll;   // in: cutting allowed (not for lnL-only evaluations); out: steps remain
+            const int ns = buildSteps(a, 0, kMaxSteps, jobs[0], p, &more, &at);
+            if (ns == -2) { setError("internal: lnL-only evaluation needs the whole tree in one launch"); return 1; }
+            if (ns < 0) return 1;
+            a.hdr[0].stepBase = 0;
+            a.hdr[0].nSteps = ns;
+            a.hdr[0].doLike = (jobs[0].withLike && !more) ? 1 : 0;
+            if (ns > 0 || a.hdr[0].doLike)
+                if (launch(1)) return 1;
+            if (!more) break;
         }
-        StepC *st = &a.steps[ns];
-        st->outSlot = n->clSlot[p];
-        st->first = 1;
-        int k = 0;
-        bool prevUsed = false;
-        for (Node *c = n->leftChild; c; c = c->sibling) {
-            unsigned kind, index;
-            if (c->isLeaf) {
-                if (c->seqNum < 0 || c->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", c->nodeNum, c->seqNum); return 1; }
-                kind = 2u;
-                index = (unsigned)c->seqNum;
-            } else {
-                if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return 1; }
-                kind = (c == prev && !prevUsed && st->first) ? 1u : 0u;
-                if (kind == 1u) prevUsed = true;
-                else needsMemory.insert(c);
-                index = (unsigned)c->clSlot[p];
-            }
-            st->ch[k].a = (int)((kind << 30) | index);
-            st->ch[k].b = c->nodeNum;
-            k++;
-            if (k == kMaxChildren && c->sibling) {   // polytomy wider than one step: continue in the next
-                st->nChildren = (short)k;
-                st->store = 0;
-                ns++;
-                st = &a.steps[ns];
-                st->outSlot = n->clSlot[p];
-                st->first = 0;
-                k = 0;
-            }
+    } else {
+        int base = 0;
+        for (int i = 0; i < nJobs; i++) {
+            const int ns = buildSteps(a, base, kMaxSteps - base, jobs[i], p, nullptr, nullptr);
+            if (ns == -2) { setError("batched evaluation: the step lists of the trees do not fit one launch"); return 1; }
+            if (ns < 0) return 1;
+            a.hdr[i].stepBase = base;
+            a.hdr[i].nSteps = ns;
+            a.hdr[i].doLike = jobs[i].withLike ? 1 : 0;
+            base += ns;
         }
-        st->nChildren = (short)k;
-        st->store = 1;
-        if (k == 2 && st->first) {
-            // two-children step: its one re-loaded internal child (if any) goes through the prefetch buffer
-            const unsigned k0 = (unsigned)st->ch[0].a >> 30, k1 = (unsigned)st->ch[1].a >> 30;
-            if (k0 == 0u && k1 != 0u) st->ch[0].a = (int)((3u << 30) | ((unsigned)st->ch[0].a & 0x3fffffffu));
-            else if (k1 == 0u && k0 != 0u) st->ch[1].a = (int)((3u << 30) | ((unsigned)st->ch[1].a & 0x3fffffffu));
-        }
-        lastStepOf[n] = ns;
-        ns++;
-        prev = n;
-        n->clStamp[p] = ++G.stamp;
-        n->clResident[p] = storeAll ? 1 : 0;
-        n->clNeedsUpdating = 0;
+        if (launch(nJobs)) return 1;
     }
-    if (!storeAll) {
-        // lnL-only evaluation: keep the store only for nodes that a later step of this launch
-        // re-reads from memory (kind 0); everything else lives and dies in registers.
-        for (int i = 0; i < ns; i++) a.steps[i].store = 0;
-        for (auto &kv : lastStepOf)
-            if (needsMemory.count(kv.first)) {
-                a.steps[kv.second].store = 1;
-                kv.first->clResident[p] = 1;
-            }
-    }
-    if (ns > 0 || withLike)
-        if (flush(ns, true)) return 1;
-    if (withLike) {
-        like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, d->result + 2 * p);
+    if (anyLike) {
+        if (nJobs == 1) {
+            like_final_kernel<<<1, 256, 0, G.stream>>>(a.hdr[0].partials, blocks, resultDev);
+        } else {
+            FinalBatchArgs f;
+            memset(&f, 0, sizeof(f));
+            for (int i = 0; i < nJobs; i++) f.partials[i] = jobs[i].withLike ? a.hdr[i].partials : a.hdr[0].partials;
+            f.result = resultDev;
+            f.nBlocks = blocks;
+            like_final_batch_kernel<<<nJobs, 256, 0, G.stream>>>(f);
+        }
         CUDA_TRY(cudaGetLastError());
         G.launches++;
     }
     return 0;
 }
 
+static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes, bool storeAll = true)
+{
+    FusedJob job = {t, &order, withLike, wantPatLikes, storeAll};
+    return launchFusedBatch(&job, 1, p, t->dev->result + 2 * p);
+}
+
 void setFusedEnabled(int on) { g_fusedEnabled = on != 0; }
 
-// Make every CL of part p current in memory (after an lnL-only evaluation some are not):
-// one storing whole-tree pass over the nodes of the last evaluation order.
-int treeEnsureResident(Tree *t, int p)
+// After an lnL-only evaluation some CLs of part p are not in memory: one storing whole-tree pass
+// over the nodes of the evaluation order makes them current again.
+static int residentPass(Tree *t, int p)
 {
     bool all = true;
     for (Node *n : t->nodes)
@@ -905,6 +1018,35 @@ int treeEnsureResident(Tree *t, int p)
     for (Node *n : t->nodes)
         if (n && n->clSlot[p] >= 0) n->clResident[p] = 1;
     return 0;
+}
+
+// Bring part p of the tree to the state the reference would be in now: every CL in memory and every
+// queued node-level CL call executed.
+int treeEnsureResident(Tree *t, int p)
+{
+    if (residentPass(t, p)) return 1;
+    std::vector<Node *> &q = t->dev->pending[p];
+    if (q.empty()) return 0;
+    std::vector<Node *> order;
+    order.swap(q);
+    return launchFusedTree(t, p, order, false, false, true);
+}
+
+static int treeFlushAllPending(Tree *t)
+{
+    if (!t->dev) return 0;
+    for (int p = 0; p < t->nParts; p++)
+        if (!t->dev->pending[p].empty())
+            if (treeEnsureResident(t, p)) return 1;
+    return 0;
+}
+int treeFlushPending(Tree *t) { return treeFlushAllPending(t); }
+bool treeHasPending(Tree *t)
+{
+    if (!t || !t->dev) return false;
+    for (auto &q : t->dev->pending)
+        if (!q.empty()) return true;
+    return false;
 }
 
 // ---------------------------------------------------------------------------
@@ -985,7 +1127,15 @@ double treePartLogLike(Tree *t, Part *dpArg, int p, int getSiteLikes)
     if (!t->dev) { setError("tree has no device state"); return NAN; }
     if (p < 0 || p >= t->nParts) { setError("p4_partLogLike: bad part %d", p); return NAN; }
     (void)dpArg;   // the reference passes the part explicitly; it is data->parts[pNum]
-    if (enqueuePartLike(t, p, getSiteLikes != 0)) return NAN;
+    std::vector<Node *> &q = t->dev->pending[p];
+    if (!q.empty() && q.back() == t->root && fusedEligible(t->dev->parts[p])) {
+        // the usual end of a proposal: the queued dirty path ends at the root, so the path and the
+        // root reduction are one launch
+        if (residentPass(t, p)) return NAN;
+        std::vector<Node *> order;
+        order.swap(q);
+        if (launchFusedTree(t, p, order, true, getSiteLikes != 0, true)) return NAN;
+    } else if (enqueuePartLike(t, p, getSiteLikes != 0)) return NAN;
     if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
     if (fetchResults(t, p, p + 1)) return NAN;
     double lnL = t->dev->hResult[2 * p];
@@ -998,6 +1148,7 @@ double treeLogLike(Tree *t, int getSiteLikes)
 {
     if (!t->dev) { setError("tree has no device state"); return NAN; }
     TreeDevice *d = t->dev;
+    if (treeFlushAllPending(t)) return NAN;
     d->lastCLLaunches = 0;
     // nodes whose CL is recomputed, in the caller's post-order (Pf/p4_tree.c:875-887)
     std::vector<Node *> order;
@@ -1041,6 +1192,74 @@ double treeLogLike(Tree *t, int getSiteLikes)
     return lnL;
 }
 
+// p4_partLogLike for several trees at once (the prop trees of Metropolis-coupled chains after their
+// proposals): when every tree's queued node-level calls end at its root, all dirty paths and all root
+// reductions run as one launch, followed by one fold, one all-reduce and one device->host copy.
+int treesPartLogLike(Tree **trees, int n, int p, double *out)
+{
+    if (n <= 0) return 0;
+    bool batchable = true;
+    for (int i = 0; i < n && batchable; i++) {
+        Tree *t = trees[i];
+        if (!t || !t->dev || p < 0 || p >= t->nParts) { setError("p4b_treesPartLogLike: bad tree or part"); return 1; }
+        const std::vector<Node *> &q = t->dev->pending[p];
+        if (q.empty() || q.back() != t->root || !fusedEligible(t->dev->parts[p]) || t->data->parts[p] != trees[0]->data->parts[p]) batchable = false;
+        for (int j = 0; j < i && batchable; j++)
+            if (trees[j] == t) batchable = false;
+    }
+    if (!batchable) {
+        for (int i = 0; i < n; i++) {
+            out[i] = treePartLogLike(trees[i], nullptr, p, 0);
+            if (out[i] != out[i]) return 1;
+        }
+        return 0;
+    }
+    int i0 = 0;
+    while (i0 < n) {
+        // greedy group: at most kMaxBatchTrees trees and kMaxSteps steps
+        int i1 = i0, steps = 0;
+        while (i1 < n && i1 - i0 < kMaxBatchTrees) {
+            int need = 0;
+            for (Node *nd : trees[i1]->dev->pending[p]) {
+                int kids = 0;
+                for (Node *c = nd->leftChild; c; c = c->sibling) kids++;
+                need += (kids + kMaxChildren - 1) / kMaxChildren;
+            }
+            if (i1 > i0 && steps + need > kMaxSteps) break;
+            steps += need;
+            i1++;
+        }
+        const int m = i1 - i0;
+        if (m == 1) {
+            out[i0] = treePartLogLike(trees[i0], nullptr, p, 0);
+            if (out[i0] != out[i0]) return 1;
+            i0 = i1;
+            continue;
+        }
+        std::vector<std::vector<Node *>> orders(m);
+        std::vector<FusedJob> jobs(m);
+        for (int k = 0; k < m; k++) {
+            Tree *t = trees[i0 + k];
+            if (residentPass(t, p)) return 1;
+            orders[k].swap(t->dev->pending[p]);
+            jobs[k] = FusedJob{t, &orders[k], true, false, true};
+        }
+        if (launchFusedBatch(jobs.data(), m, p, G.dBatch)) return 1;
+        if (commActive())
+            if (commAllReduceSum(G.dBatch, 2 * m, (void *)G.stream)) return 1;
+        CUDA_TRY(cudaMemcpyAsync(G.hBatch, G.dBatch, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+        if (streamSync()) return 1;
+        for (int k = 0; k < m; k++) {
+            double v = G.hBatch[2 * k];
+            if (G.hBatch[2 * k + 1] > 0.0) v = P4B_BAD_LIKE;
+            trees[i0 + k]->partLikes[p] = v;
+            out[i0 + k] = v;
+        }
+        i0 = i1;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // cur/prop state transfer
 // ---------------------------------------------------------------------------
@@ -1058,6 +1277,7 @@ static int checkTwins(Tree *a, Tree *b)
 int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
 {
     if (checkTwins(a, b)) return 1;
+    if (treeFlushAllPending(b)) return 1;   // b's queued calls were issued before this copy
     for (int p = 0; p < a->nParts; p++)
         if (treeEnsureResident(a, p)) return 1;
     for (int j = 0; j < a->nNodes; j++) {
@@ -1088,6 +1308,7 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
 {
     if (!doAll) { setError("p4_copyBigPDecks() doAll is not set. Programming error?"); return 1; }
     if (checkTwins(a, b)) return 1;
+    if (treeFlushAllPending(a) || treeFlushAllPending(b) || flushPJobs()) return 1;
     for (int j = 0; j < a->nNodes; j++) {
         const int i = a->preOrder[j];
         if (i == P4B_NO_ORDER) continue;
@@ -1107,6 +1328,7 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
 int treeVerifyDevice(Tree *a, Tree *b)
 {
     if (checkTwins(a, b)) return -1;
+    if (flushPJobs()) return -1;
     for (int p = 0; p < a->nParts; p++)
         if (treeEnsureResident(a, p) || treeEnsureResident(b, p)) return -1;
     TreeDevice *d = a->dev;
@@ -1167,6 +1389,7 @@ int nodeGetBigP(Node *n, int p, double *out)
 {
     Tree *t = n->tree;
     if (!t->dev || p < 0 || p >= t->nParts) { setError("p4b_getNodeBigP: bad part"); return 1; }
+    if (flushPJobs()) return 1;
     CUDA_TRY(cudaMemcpyAsync(out, nodeP(n, p), t->dev->parts[p].pDoubles * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
     return streamSync();
 }
@@ -1178,6 +1401,7 @@ int nodeSetBigP(Node *n, int p, const double *in)
 {
     Tree *t = n->tree;
     if (!t->dev || p < 0 || p >= t->nParts) { setError("p4b_setNodeBigP: bad part"); return 1; }
+    if (treeFlushAllPending(t) || flushPJobs()) return 1;
     PartLayout &L = t->dev->parts[p];
     Part *dp = t->data->parts[p];
     CUDA_TRY(cudaMemcpyAsync(nodeP(n, p), in, L.pDoubles * sizeof(double), cudaMemcpyHostToDevice, G.stream));
@@ -1218,8 +1442,9 @@ int treeShardRangeOf(Tree *t, int p, int *lo, int *hi)
 
 int treeSync(Tree *t)
 {
-    (void)t;
     if (!G.ready) return 0;
+    if (t && treeFlushAllPending(t)) return 1;
+    if (flushPJobs()) return 1;
     return streamSync();
 }
 

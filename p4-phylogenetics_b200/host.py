@@ -337,6 +337,7 @@ class Tree:
         self.preOrder = np.full(len(nodes), NO_ORDER, dtype=np.int32)
         self.postOrder = np.full(len(nodes), NO_ORDER, dtype=np.int32)
         self.preAndPostOrderAreValid = False
+        self.bulkSetCStuff = False     # True: setCStuff uses pf.setTreeCStuff where the engine offers it
 
     # -- traversal (p4/tree.py setPreAndPostOrder writes the arrays in place) --
     def setPreAndPostOrder(self):
@@ -399,13 +400,29 @@ class Tree:
 
     def setCStuff(self):
         pf = self.pf
-        for n in self.iterNodes():
-            pf.p4_setNodeRelation(n.cNode, 0, n.parent.nodeNum if n.parent else -1)
-            pf.p4_setNodeRelation(n.cNode, 1, n.leftChild.nodeNum if n.leftChild else -1)
-            pf.p4_setNodeRelation(n.cNode, 2, n.sibling.nodeNum if n.sibling else -1)
-        pf.p4_setTreeRoot(self.cTree, self.root.cNode)
-        for n in self.iterNodesNoRoot():
-            pf.p4_setBrLen(n.cNode, n.br.len)
+        if self.bulkSetCStuff and hasattr(pf, "setTreeCStuff") and all(n.nodeNum != NO_ORDER for n in self.nodes):
+            # the engine's one-call form of the loops below (include/p4b200.h p4b_setTreeCStuff)
+            nn = len(self.nodes)
+            rel = np.full((3, nn), -1, dtype=np.int32)
+            brl = np.zeros(nn, dtype=np.float64)
+            for n in self.nodes:
+                i = n.nodeNum
+                if n.parent:
+                    rel[0, i] = n.parent.nodeNum
+                    brl[i] = n.br.len
+                if n.leftChild:
+                    rel[1, i] = n.leftChild.nodeNum
+                if n.sibling:
+                    rel[2, i] = n.sibling.nodeNum
+            pf.setTreeCStuff(self.cTree, rel[0], rel[1], rel[2], brl, self.root.nodeNum)
+        else:
+            for n in self.iterNodes():
+                pf.p4_setNodeRelation(n.cNode, 0, n.parent.nodeNum if n.parent else -1)
+                pf.p4_setNodeRelation(n.cNode, 1, n.leftChild.nodeNum if n.leftChild else -1)
+                pf.p4_setNodeRelation(n.cNode, 2, n.sibling.nodeNum if n.sibling else -1)
+            pf.p4_setTreeRoot(self.cTree, self.root.cNode)
+            for n in self.iterNodesNoRoot():
+                pf.p4_setBrLen(n.cNode, n.br.len)
         if self.model.isHet:
             for pNum in range(self.model.nParts):
                 if self.model.parts[pNum].isHet:
@@ -502,6 +519,7 @@ class Tree:
             b.leftChild = nn[a.leftChild.nodeNum] if a.leftChild else None
             b.sibling = nn[a.sibling.nodeNum] if a.sibling else None
         t = Tree(self.pf, nn, nn[self.root.nodeNum])
+        t.bulkSetCStuff = self.bulkSetCStuff
         if self.model is not None:
             for a, b in zip(self.nodes, nn):
                 b.parts = [NodePart() for _ in a.parts]

@@ -76,6 +76,8 @@ _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setTensorCoreKernel", None, _i)
+_sig("p4b_setDeferredNodeCalls", None, _i)
+_sig("p4b_treesPartLogLike", _i, _i, _vp, _i, _vp)
 _sig("p4b_setScalers", None, _i)
 _sig("p4b_newData", _vp, _i, _i)
 _sig("p4b_freeData", None, _vp)
@@ -118,6 +120,7 @@ _sig("p4b_newNode", _vp, _i, _vp, _i, _i, _i)
 _sig("p4b_freeNode", None, _vp)
 _sig("p4b_setNodeRelation", _i, _vp, _i, _i)
 _sig("p4b_setTreeRoot", _i, _vp, _vp)
+_sig("p4b_setTreeCStuff", _i, _vp, _i, _vp, _vp, _vp, _vp, _i)
 _sig("p4b_setBrLen", _i, _vp, _d)
 _sig("p4b_setCompNum", _i, _vp, _i, _i)
 _sig("p4b_setRMatrixNum", _i, _vp, _i, _i)
@@ -223,6 +226,20 @@ def commDestroy():
 
 def setFusedTreeKernel(on):
     _lib.p4b_setFusedTreeKernel(int(on))
+
+
+def setDeferredNodeCalls(on):
+    """0: node-level calls launch at once instead of queueing (see include/p4b200.h)."""
+    _lib.p4b_setDeferredNodeCalls(int(on))
+
+
+def treesPartLogLike(cTrees, pNum):
+    """p4_partLogLike of several trees (sharing the data part) as one batched launch -> list of floats."""
+    n = len(cTrees)
+    arr = (C.c_void_p * n)(*cTrees)
+    out = np.empty(n, dtype=np.float64)
+    _ok(_lib.p4b_treesPartLogLike(n, arr, int(pNum), out.ctypes.data))
+    return out.tolist()
 
 
 def setTensorCoreKernel(on):
@@ -425,6 +442,12 @@ def p4_freeNode(cNode):
 
 def p4_setNodeRelation(cNode, relation, relNum):
     _ok(_lib.p4b_setNodeRelation(cNode, relation, relNum))
+
+
+def setTreeCStuff(cTree, parent, leftChild, sibling, brLen, rootNum):
+    """Addition: the relations and branch lengths of every node in one call (int32 / float64 arrays by node number)."""
+    _ok(_lib.p4b_setTreeCStuff(cTree, len(parent), _arr(parent, np.int32, "parent"), _arr(leftChild, np.int32, "leftChild"),
+                               _arr(sibling, np.int32, "sibling"), _arr(brLen, np.float64, "brLen"), int(rootNum)))
 
 
 def p4_setTreeRoot(cTree, cNode):

@@ -281,7 +281,7 @@ def make_alignment(pf, tree, mp, nPatterns, rng, datatype, gap_frac=0.01, ambig_
 # the BASELINE configs
 # ------------------------------------------------------------------------------
 def build_config(pf, cfg, nTax=None, nPatterns=None, seed=None):
-    """Tree + data + model for BASELINE.json config ``cfg`` (1..4), optionally scaled down."""
+    """Tree + data + model for BASELINE.json config ``cfg`` (1..5), optionally scaled down."""
     seed = 20240 + cfg if seed is None else seed
     rng = np.random.Generator(np.random.PCG64(seed))
     if cfg == 1:
@@ -306,6 +306,11 @@ def build_config(pf, cfg, nTax=None, nPatterns=None, seed=None):
         mps = [protein_model_part(p, rng, "lg", 4, nComps=nNodes) for p in range(4)]
         sim = protein_model_part(0, rng, "lg", 4)
         alns = [make_alignment(pf, tree, sim, nPatterns, rng, "protein") for _ in range(4)]
+    elif cfg == 5:   # the MCMC config: every model parameter free
+        nTax, nPatterns = nTax or 100, nPatterns or 500000
+        tree = random_tree(pf, nTax, rng)
+        mps = [dna_model_part(0, rng, 4, pInvar=0.0, free=1)]
+        alns = [make_alignment(pf, tree, mps[0], nPatterns, rng, "dna")]
     else:
         raise ValueError("config %r" % cfg)
     data = host.Data(pf, alns)

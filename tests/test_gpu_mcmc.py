@@ -1,0 +1,137 @@
+"""MCMC protocol on the GPU engine: queued node-level calls, batched chains, cur/prop transfer --
+against the reference's own Pf engine running the same chain (same seed, same proposals)."""
+import numpy as np
+import pytest
+
+from util import rel
+
+pytestmark = pytest.mark.gpu
+
+LNL_TOL = 1e-9
+
+
+def _mcmc(pkg, pf, nChains, seed, nTax=14, nPatterns=700, bulk=False):
+    tree = pkg.synth.build_config(pf, 5, nTax=nTax, nPatterns=nPatterns)
+    tree.bulkSetCStuff = bulk
+    return pkg.mcmc.Mcmc(tree, nChains=nChains, seed=seed)
+
+
+def _same_trace(a, b, tol):
+    assert len(a) == len(b)
+    for (ga, la), (gb, lb) in zip(a, b):
+        assert ga == gb
+        for x, y in zip(la, lb):
+            assert rel(x, y) <= tol, "generation %d: %r vs %r" % (ga, x, y)
+
+
+def test_chain_matches_reference_engine(pkg, ref_pf):
+    """The same 3-chain MCMCMC, 120 generations, on both engines: every chain's lnL after every generation
+    agrees to 1e-9 relative, hence the same accept / reject / swap decisions throughout."""
+    mine = _mcmc(pkg, pkg.pf, 3, 42)
+    ref = _mcmc(pkg, ref_pf, 3, 42)
+    ta = mine.run(120)
+    tb = ref.run(120)
+    _same_trace(ta, tb, LNL_TOL)
+    for p, q in zip(mine.proposals, ref.proposals):
+        assert (p.name, p.nProposals, p.nAcceptances) == (q.name, q.nProposals, q.nAcceptances)
+    assert (mine.nSwapAttempts, mine.nSwaps) == (ref.nSwapAttempts, ref.nSwaps)
+    for c in mine.chains:
+        assert pkg.pf.p4_verifyIdentityOfTwoTrees(c.curTree.cTree, c.propTree.cTree) == 0
+        was = c.curTree.logLike
+        assert rel(c.curTree.calcLogLike(), was) <= 1e-12
+
+
+def test_queued_calls_equal_immediate_calls(pkg):
+    """p4b_setDeferredNodeCalls(0) launches every node-level call at once (one kernel per node); the default
+    queues them into one step-list launch.  Same chain either way."""
+    pf = pkg.pf
+    a = _mcmc(pkg, pf, 2, 7).run(60, batched=False)
+    n0 = pf.kernelLaunchCount()
+    _mcmc(pkg, pf, 2, 7).run(10, batched=False)
+    queued = pf.kernelLaunchCount() - n0
+    pf.setDeferredNodeCalls(0)
+    try:
+        b = _mcmc(pkg, pf, 2, 7).run(60, batched=False)
+        n0 = pf.kernelLaunchCount()
+        _mcmc(pkg, pf, 2, 7).run(10, batched=False)
+        immediate = pf.kernelLaunchCount() - n0
+    finally:
+        pf.setDeferredNodeCalls(1)
+    _same_trace(a, b, 1e-12)
+    assert queued < immediate
+
+
+def test_batched_chains_equal_sequential_chains(pkg):
+    """Mcmc.run(batched=True): one pf.treesPartLogLike per part and generation for all chains."""
+    pf = pkg.pf
+    a = _mcmc(pkg, pf, 4, 9).run(50, batched=True)
+    b = _mcmc(pkg, pf, 4, 9).run(50, batched=False)
+    _same_trace(a, b, 1e-12)
+
+
+def test_trees_part_loglike_mixed_batch(pkg):
+    """pf.treesPartLogLike with trees whose queues do not all end at the root falls back per tree."""
+    pf = pkg.pf
+    m = _mcmc(pkg, pf, 3, 1)
+    trees = [c.propTree for c in m.chains]
+    want = [t.calcLogLike() for t in trees]
+    # tree 0: a dirty path to the root queued; tree 1: nothing queued; tree 2: the whole tree queued
+    n = [x for x in trees[0].iterInternalsPostOrder()][0]
+    q = n
+    path = [n]
+    while q.parent:
+        q = q.parent
+        path.append(q)
+    for x in path:
+        pf.p4_setConditionalLikelihoodsOfInternalNodePart(x.cNode, 0)
+    for x in trees[2].iterInternalsPostOrder():
+        pf.p4_setConditionalLikelihoodsOfInternalNodePart(x.cNode, 0)
+    got = pf.treesPartLogLike([t.cTree for t in trees], 0)
+    for g, w in zip(got, want):
+        assert rel(g, w) <= 1e-12
+    # all three with a queue ending at the root: the batched launch proper
+    for t in trees:
+        for x in t.iterInternalsPostOrder():
+            pf.p4_setConditionalLikelihoodsOfInternalNodePart(x.cNode, 0)
+    n0 = pf.kernelLaunchCount()
+    got = pf.treesPartLogLike([t.cTree for t in trees], 0)
+    assert pf.kernelLaunchCount() - n0 == 2          # one CL launch for the three trees + one fold
+    for g, w, t in zip(got, want, trees):
+        assert rel(g, w) <= 1e-12
+        assert t.partLikes[0] == g
+
+
+def test_queue_is_flushed_before_state_is_read_or_changed(pkg, ref_pf):
+    pf = pkg.pf
+    mine = pkg.synth.build_config(pf, 2, nTax=12, nPatterns=500)
+    twin = pkg.host.clone_tree(mine, ref_pf)
+    mine.calcLogLike()
+    twin.calcLogLike()
+    import ref_peek
+    # change a branch, queue the path, then READ a CL on the path before any partLogLike
+    for t in (mine, twin):
+        n = t.nodes[5]
+        n.br.len *= 2.5
+        t.setCStuff()
+        t.pf.p4_calculateBigPDecks(n.cNode)
+        q = n
+        while q.parent:
+            q = q.parent
+            if not q.isLeaf:
+                t.pf.p4_setConditionalLikelihoodsOfInternalNodePart(q.cNode, 0)
+    root = mine.root
+    c1 = pf.getNodeCL(mine.cTree, root.cNode, 0, 4, 4)
+    rp = ref_peek.part_arrays(twin.data.parts[0].cPart)
+    c0 = ref_peek.node_cl(twin.root.cNode, 0, 4, 4, rp["nChar"], rp["nPatterns"])
+    scale = np.max(np.abs(c0), axis=(0, 1), keepdims=True)
+    assert np.max(np.abs(c1 - c0) / scale) < 1e-9
+    got = pf.p4_partLogLike(mine.cTree, mine.data.parts[0].cPart, 0, 0)
+    want = ref_pf.p4_partLogLike(twin.cTree, twin.data.parts[0].cPart, 0, 0)
+    assert rel(got, want) <= LNL_TOL
+
+
+def test_bulk_setcstuff_equals_per_node_calls(pkg):
+    pf = pkg.pf
+    a = _mcmc(pkg, pf, 2, 13, bulk=True).run(40)
+    b = _mcmc(pkg, pf, 2, 13, bulk=False).run(40)
+    assert a == b
