@@ -83,6 +83,13 @@ void p4b_setFusedTreeKernel(int on);
  * the queue depends on (copy, verify, inspection, a topology or parameter change).  Results are
  * those of immediate execution.  0 launches every call at once (for comparison). */
 void p4b_setDeferredNodeCalls(int on);
+/* p4_copyCondLikes between the cur and prop tree of a chain moves no data by default (1): the CL
+ * arenas of the two trees pair up, a copied node simply references the source node's buffer, and a
+ * node whose buffer is shared is given a fresh slot when it is next computed (copy on write; the pair
+ * holds 2 x nInternal slots, exactly as two private arenas do).  The observable state is that of a
+ * real copy.  A tree can pair with one other tree; copies to or from any further tree, and all copies
+ * with 0 here, are device-to-device memcpys. */
+void p4b_setSharedCondLikes(int on);
 /* 20-state parts use the FP64 tensor-core (mma.sync m8n8k4) CL kernel by default;
  * 0 selects the FMA kernel instead (same results to rounding; for comparison). */
 void p4b_setTensorCoreKernel(int on);

@@ -38,6 +38,7 @@ int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
 void p4b_setDeferredNodeCalls(int on) { setDeferEnabled(on); }
+void p4b_setSharedCondLikes(int on) { setShareEnabled(on); }
 void p4b_setTensorCoreKernel(int on) { setDmmaEnabled(on); }
 void p4b_setScalers(int on) { setScalersEnabled(on); }
 
@@ -373,6 +374,7 @@ void p4b_freeNode(p4b_node n)
     Node *N = (Node *)n;
     if (!N) return;
     if (N->tree && treeHasPending(N->tree)) treeFlushPending(N->tree);   // queued CL calls may name this node
+    nodeDeviceRelease(N);
     if (N->tree && N->nodeNum >= 0 && N->nodeNum < (int)N->tree->nodes.size() && N->tree->nodes[N->nodeNum] == N) N->tree->nodes[N->nodeNum] = nullptr;
     delete N;
 }

@@ -120,6 +120,7 @@ struct Node {
     std::vector<int> compNums, rMatrixNums, gdasrvNums;
     int clNeedsUpdating = 0;
     std::vector<int> clSlot;                  // per part: CL arena slot, -1 if none
+    std::vector<char> clSel;                  // per part: 0 the slot is in the tree's own arena, 1 in its twin's
     std::vector<uint64_t> clStamp;            // per part: id of the computation that filled the CL
     std::vector<uint64_t> pStamp;             // per part: id of the computation that filled the P deck
     std::vector<char> clResident;             // per part: the CL in the arena is the current one (see Tree::storeCL)
@@ -152,6 +153,7 @@ long long kernelLaunchCount();
 int treeDeviceCreate(Tree *t);
 void treeDeviceDestroy(Tree *t);
 int nodeDeviceCreate(Node *n);
+void nodeDeviceRelease(Node *n);
 void partDeviceFree(Part *p);
 
 int treeSetPrams(Tree *t, int pNum);
@@ -181,6 +183,7 @@ int treeEnsureResident(Tree *t, int p);
 int treeFlushPending(Tree *t);
 bool treeHasPending(Tree *t);
 void setDeferEnabled(int on);
+void setShareEnabled(int on);
 int treesPartLogLike(Tree **trees, int n, int p, double *out);
 
 // comm.cpp -- NCCL, loaded at run time

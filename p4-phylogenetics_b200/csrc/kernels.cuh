@@ -293,6 +293,9 @@ struct StepC {
     signed char first;           // 1: the running product starts at 1; 0: continues from the previous chunk
     signed char store;           // 1: write the CL at the end of the step
     struct { int a, b; } ch[kMaxChildren];
+    // outSlot and an internal child's index address a CL buffer as (buffer - hdr.arena) / 256 bytes: buffers are
+    // 256-byte aligned, and 30 bits of such units span 274 GB -- more than the device has.  With scalers on, the
+    // buffer's per-pattern exponents (int32[ps]) sit right behind its K*ps doubles.
     // a = kind << 30 | index; kind 0: internal child, load CL slot `index`
     //                         kind 1: internal child, CL in registers (computed by the previous step)
     //                         kind 2: leaf child, tip row `index` (its seqNum)
@@ -302,10 +305,9 @@ struct StepC {
 // Several trees that share a data part (the cur/prop trees of Metropolis-coupled chains) can be
 // evaluated by ONE launch: blockIdx.y selects the tree, i.e. its header and its range of the step list.
 struct TreeHdr {
-    double *arena;            // CL arena of the part in this tree
+    double *arena;            // base address the tree's CL buffers are addressed from (covers its own arena and its twin's)
     const double *Pdeck;      // tree's P decks, already offset to this part
     const double *tbl;        // tree's leaf tables, already offset to this part
-    int *scArena;             // per-pattern scaler exponents, [slot][ps] (SCALE kernels only)
     double *patLikes;         // optional
     double *partials;         // [2*gridDim.x]
     const uint8_t *rootTips;  // non-NULL when the root is a leaf
@@ -319,7 +321,6 @@ constexpr int kMaxSteps = 500;   // 56 B each; with the headers the argument blo
 
 struct TreeArgs {
     int ps, nPat, tblW, nTrees;
-    long long clNodeDoubles;  // arena slot size
     long long pNodeDoubles;   // stride between nodes in a P deck
     long long tblNodeDoubles;
     const uint8_t *tips;      // part's tip rows [nTax][ps]
@@ -461,7 +462,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         if (!active) return;
         const StepC &st = a.steps[hd.stepBase + stepIdx];
         const unsigned av = (((unsigned)st.ch[0].a >> 30) == 3u) ? (unsigned)st.ch[0].a : (unsigned)st.ch[1].a;
-        const double *cl = hd.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat;
+        const double *cl = hd.arena + (size_t)(av & 0x3fffffffu) * 32 + pat;
 #pragma unroll
         for (int k = 0; k < K; k++) cp_async16(pre + k * THREADS, cl + (size_t)k * ps);
     };
@@ -488,7 +489,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
         if (active) {
             const StepC &st = a.steps[hd.stepBase + si];
             const int nc = st.nChildren;
-            double *out = hd.arena + a.clNodeDoubles * st.outSlot + pat;
+            double *out = hd.arena + (size_t)(unsigned)st.outSlot * 32 + pat;
             const unsigned a0 = (unsigned)st.ch[0].a, a1 = (unsigned)st.ch[1].a;
             const unsigned k0 = a0 >> 30, k1 = a1 >> 30;
             int2 esum = make_int2(0, 0);
@@ -498,7 +499,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                     const unsigned av = (unsigned)st.ch[c].a, kind = av >> 30;
                     if (kind == 1u) { esum.x += ecur.x; esum.y += ecur.y; }
                     else if (kind != 2u) {
-                        const int2 ec = *reinterpret_cast<const int2 *>(hd.scArena + (size_t)ps * (av & 0x3fffffffu) + pat);
+                        const int2 ec = *reinterpret_cast<const int2 *>(reinterpret_cast<const int *>(hd.arena + (size_t)(av & 0x3fffffffu) * 32 + (size_t)K * ps) + pat);
                         esum.x += ec.x;
                         esum.y += ec.y;
                     }
@@ -535,7 +536,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                         } else if (kind == 1u) {
                             child_factor<1>(cat, s, W, 0u, 0u, cur, nullptr, ps, f);
                         } else {
-                            child_factor<0>(cat, s, W, 0u, 0u, cur, hd.arena + a.clNodeDoubles * (av & 0x3fffffffu) + pat, ps, f);
+                            child_factor<0>(cat, s, W, 0u, 0u, cur, hd.arena + (size_t)(av & 0x3fffffffu) * 32 + pat, ps, f);
                         }
 #pragma unroll
                         for (int s4 = 0; s4 < 4; s4++) { acc[s4].x *= f[s4].x; acc[s4].y *= f[s4].y; }
@@ -565,7 +566,7 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
                 if (st.store) {
 #pragma unroll
                     for (int k = 0; k < K; k++) st2(out + k * ps, cur[k]);
-                    *reinterpret_cast<int2 *>(hd.scArena + (size_t)ps * st.outSlot + pat) = ecur;
+                    *reinterpret_cast<int2 *>(reinterpret_cast<int *>(out - pat + (size_t)K * ps) + pat) = ecur;
                 }
             }
         }

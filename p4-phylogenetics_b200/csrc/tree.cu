@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -64,6 +65,7 @@ struct Engine {
 };
 static Engine G;
 static int flushPJobs();
+void nodeDeviceRelease(Node *n);
 static bool g_useScalers = false;
 void setScalersEnabled(int on) { g_useScalers = on != 0; }
 
@@ -226,6 +228,27 @@ static int partDeviceEnsure(Part *p)
 // ---------------------------------------------------------------------------
 // Tree device state
 // ---------------------------------------------------------------------------
+// One allocation of CL buffers ("slots") for one (tree, part).  The cur and prop tree of a chain hold
+// the same numbers for every node a proposal did not touch, and p4 re-synchronises them after every
+// generation by copying all CLs (p4_copyCondLikes, p4/chain.py:1529).  Here the two trees' arenas form a
+// pair: a "copy" makes the destination node REFERENCE the source node's buffer (reference count per
+// slot), and a node whose buffer is shared gets a fresh slot the next time it is computed.  No CL is
+// ever moved between twins.
+struct Arena {
+    double *base = nullptr;
+    size_t slotDoubles = 0;              // K*ps doubles of CL, then (scalers on) ps int32 exponents, padded to 256 B
+    size_t clDoubles = 0;                // K*ps
+    bool scalers = false;
+    int ps = 0, nSlots = 0;
+    std::vector<int> refs;               // per slot: nodes (of either twin) whose CL lives there
+    std::vector<int> freeSlots;
+    Arena *partner = nullptr;            // the one other arena this one shares buffers with
+    ~Arena()
+    {
+        if (base) cudaFree(base);
+    }
+};
+
 struct PartLayout {
     int dim = 0, nCat = 1, W = 0, ps = 0, nPat = 0;
     size_t clNodeDoubles = 0;    // nCat*dim*ps
@@ -234,9 +257,9 @@ struct PartLayout {
     size_t eigOff = 0, eigStride = 0;    // within the eig mirror; stride per (comp,rMatrix)
     size_t eqOff = 0;                    // within the equate mask mirror
     int nPairs = 0;                      // nComps*nRMatrices
-    double *clArena = nullptr;
-    int *scArena = nullptr;              // per-pattern scaler exponents [slot][ps]; NULL when scalers are off
-    int slotsUsed = 0, nSlots = 0;
+    std::shared_ptr<Arena> own, twin;    // CL buffers: this tree's arena, and the arena of the tree it shares buffers with
+    bool scalers = false;
+    Arena *arena(int sel) const { return sel ? twin.get() : own.get(); }
     std::vector<uint64_t> eigUploaded;   // version of each (comp,rMatrix) mirrored on the device
 };
 
@@ -301,17 +324,20 @@ int treeDeviceCreate(Tree *t)
         L.eigUploaded.assign(L.nPairs, 0);
         L.eqOff = eqTotal;
         eqTotal += dp->nRealEquates > 0 ? dp->nRealEquates : 1;
-        L.nSlots = nInternalSlots;
-        const size_t arenaBytes = L.clNodeDoubles * sizeof(double) * (size_t)L.nSlots;
-        CUDA_TRY(cudaMalloc(&L.clArena, arenaBytes));
-        CUDA_TRY(cudaMemsetAsync(L.clArena, 0, arenaBytes, G.stream));
+        L.own = std::make_shared<Arena>();
+        Arena &A = *L.own;
+        A.nSlots = nInternalSlots;
+        A.ps = L.ps;
+        A.clDoubles = L.clNodeDoubles;
+        A.scalers = g_useScalers;
+        A.slotDoubles = L.clNodeDoubles + (g_useScalers ? (((size_t)L.ps / 2 + 31) & ~(size_t)31) : 0);
+        A.refs.assign(A.nSlots, 0);
+        for (int s = A.nSlots - 1; s >= 0; s--) A.freeSlots.push_back(s);   // slot 0 is handed out first
+        const size_t arenaBytes = A.slotDoubles * sizeof(double) * (size_t)A.nSlots;
+        CUDA_TRY(cudaMalloc(&A.base, arenaBytes));
+        CUDA_TRY(cudaMemsetAsync(A.base, 0, arenaBytes, G.stream));
         d->bytes += (long long)arenaBytes;
-        if (g_useScalers) {
-            const size_t scBytes = sizeof(int) * (size_t)L.ps * (size_t)L.nSlots;
-            CUDA_TRY(cudaMalloc(&L.scArena, scBytes));
-            CUDA_TRY(cudaMemsetAsync(L.scArena, 0, scBytes, G.stream));
-            d->bytes += (long long)scBytes;
-        }
+        L.scalers = g_useScalers;
         const int blocks = (L.ps + 255) / 256;
         if (blocks > d->maxLikeBlocks) d->maxLikeBlocks = blocks;
     }
@@ -347,9 +373,12 @@ void treeDeviceDestroy(Tree *t)
     if (!d) return;
     flushPJobs();   // queued jobs may write into this tree's decks
     if (G.stream) cudaStreamSynchronize(G.stream);
+    for (Node *n : t->nodes)
+        if (n) nodeDeviceRelease(n);
     for (auto &L : d->parts) {
-        if (L.clArena) cudaFree(L.clArena);
-        if (L.scArena) cudaFree(L.scArena);
+        // the arena's memory lives on while a twin still references buffers in it
+        L.own.reset();
+        L.twin.reset();
     }
     if (d->P) cudaFree(d->P);
     if (d->tbl) cudaFree(d->tbl);
@@ -368,19 +397,72 @@ void treeDeviceDestroy(Tree *t)
     t->dev = nullptr;
 }
 
+static void slotRelease(Arena *A, int slot)
+{
+    if (!A || slot < 0) return;
+    if (--A->refs[slot] == 0) A->freeSlots.push_back(slot);
+}
+
+// A free slot for a node of tree t: from the tree's own arena, else from its twin's.
+static int slotAcquire(Tree *t, int p, int *sel, int *slot, int nodeNum)
+{
+    PartLayout &L = t->dev->parts[p];
+    for (int s = 0; s < 2; s++) {
+        Arena *A = L.arena(s);
+        if (A && !A->freeSlots.empty()) {
+            *sel = s;
+            *slot = A->freeSlots.back();
+            A->freeSlots.pop_back();
+            A->refs[*slot] = 1;
+            return 0;
+        }
+    }
+    setError("node %d: no CL slot left (nNodes/nLeaves given to p4_newTree were wrong?)", nodeNum);
+    return 1;
+}
+
 static int nodeEnsureCLSlot(Node *n, int p)
 {
     if (n->clSlot[p] >= 0) return 0;
-    PartLayout &L = n->tree->dev->parts[p];
-    if (L.slotsUsed >= L.nSlots) { setError("node %d: no CL slot left (nNodes/nLeaves given to p4_newTree were wrong?)", n->nodeNum); return 1; }
-    n->clSlot[p] = L.slotsUsed++;
+    int sel = 0, slot = -1;
+    if (slotAcquire(n->tree, p, &sel, &slot, n->nodeNum)) return 1;
+    n->clSel[p] = (char)sel;
+    n->clSlot[p] = slot;
     return 0;
+}
+
+// Before a node's CL is (re)computed: if its buffer is shared with the twin tree, move the node to a
+// fresh slot; the twin keeps the old numbers.
+static int nodeMakeWritable(Node *n, int p)
+{
+    if (nodeEnsureCLSlot(n, p)) return 1;
+    PartLayout &L = n->tree->dev->parts[p];
+    Arena *A = L.arena(n->clSel[p]);
+    if (A->refs[n->clSlot[p]] <= 1) return 0;
+    int sel = 0, slot = -1;
+    if (slotAcquire(n->tree, p, &sel, &slot, n->nodeNum)) return 1;
+    A->refs[n->clSlot[p]]--;
+    n->clSel[p] = (char)sel;
+    n->clSlot[p] = slot;
+    return 0;
+}
+
+void nodeDeviceRelease(Node *n)
+{
+    Tree *t = n->tree;
+    if (!t || !t->dev) return;
+    for (int p = 0; p < t->nParts && p < (int)n->clSlot.size(); p++) {
+        if (n->clSlot[p] < 0) continue;
+        slotRelease(t->dev->parts[p].arena(n->clSel[p]), n->clSlot[p]);
+        n->clSlot[p] = -1;
+    }
 }
 
 int nodeDeviceCreate(Node *n)
 {
     Tree *t = n->tree;
     n->clSlot.assign(t->nParts, -1);
+    n->clSel.assign(t->nParts, 0);
     n->clStamp.assign(t->nParts, 0);
     n->clResident.assign(t->nParts, 1);
     n->pStamp.assign(t->nParts, 0);
@@ -393,12 +475,24 @@ int nodeDeviceCreate(Node *n)
 static inline double *nodeCL(Node *n, int p)
 {
     PartLayout &L = n->tree->dev->parts[p];
-    return L.clArena + L.clNodeDoubles * (size_t)n->clSlot[p];
+    Arena *A = L.arena(n->clSel[p]);
+    return A->base + A->slotDoubles * (size_t)n->clSlot[p];
 }
-static inline int *nodeSC(Node *n, int p)
+static inline int *nodeSC(Node *n, int p)   // the buffer's exponents sit right behind its CL
 {
     PartLayout &L = n->tree->dev->parts[p];
-    return L.scArena ? L.scArena + (size_t)L.ps * (size_t)n->clSlot[p] : nullptr;
+    return L.scalers ? reinterpret_cast<int *>(nodeCL(n, p) + L.clNodeDoubles) : nullptr;
+}
+// Base address the whole-tree kernel addresses this tree's CL buffers from: the lower of its own
+// arena and its twin's.
+static inline double *arenaBase(const PartLayout &L)
+{
+    return (L.twin && L.twin->base < L.own->base) ? L.twin->base : L.own->base;
+}
+// (buffer - base) / 256 bytes: the form the whole-tree kernel addresses a CL buffer by (30 bits)
+static inline unsigned nodeSlotCode(Node *n, int p)
+{
+    return (unsigned)((nodeCL(n, p) - arenaBase(n->tree->dev->parts[p])) / 32);
 }
 static inline double *nodeP(Node *n, int p)
 {
@@ -651,15 +745,16 @@ int nodeSetCL(Node *n, int p)
     TreeDevice *d = t->dev;
     if (p < 0 || p >= t->nParts) { setError("p4_setConditionalLikelihoodsOfInternalNodePart: bad part %d", p); return 1; }
     if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
-    if (nodeEnsureCLSlot(n, p)) return 1;   // a root that is a leaf gets its CL lazily, Pf/p4_node.c:608-626
     PartLayout &L = d->parts[p];
     if (g_deferCL && fusedEligible(L)) {
+        if (nodeEnsureCLSlot(n, p)) return 1;   // a root that is a leaf gets its CL lazily, Pf/p4_node.c:608-626
         // The callers issue node-level calls in dependency order (the dirty set is decided in
         // Python): queue, and run the whole queue as one step-list launch when its result is needed.
         d->pending[p].push_back(n);
         n->clNeedsUpdating = 0;
         return 0;
     }
+    if (nodeMakeWritable(n, p)) return 1;
     if (treeEnsureResident(t, p)) return 1;
     Part *dp = t->data->parts[p];
     CLArgs a;
@@ -700,7 +795,7 @@ int nodeSetCL(Node *n, int p)
         if (launchCL(a)) return 1;
         d->lastCLLaunches++;
     }
-    if (L.scArena) {   // scalers on: one extra pass rescales the node and sums the children's exponents
+    if (L.scalers) {   // scalers on: one extra pass rescales the node and sums the children's exponents
         RescaleArgs r;
         memset(&r, 0, sizeof(r));
         r.cl = nodeCL(n, p);
@@ -769,7 +864,6 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
     for (; oi < order.size(); oi++) {
         Node *n = order[oi];
         if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return -1; }
-        if (nodeEnsureCLSlot(n, p)) return -1;
         int nKids = 0;
         for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
         const int chunks = (nKids + kMaxChildren - 1) / kMaxChildren;
@@ -777,8 +871,9 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
             if (!overflowOk || !*overflowOk) return -2;
             break;   // the caller launches what we have and calls again from *resumeAt
         }
+        if (nodeMakeWritable(n, p)) return -1;   // a buffer shared with the twin tree is left to the twin
         StepC *st = &a.steps[base + ns];
-        st->outSlot = n->clSlot[p];
+        st->outSlot = (int)nodeSlotCode(n, p);
         st->first = 1;
         int k = 0;
         bool prevUsed = false;
@@ -793,7 +888,7 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
                 kind = (c == prev && !prevUsed && st->first) ? 1u : 0u;
                 if (kind == 1u) prevUsed = true;
                 else needsMemory.insert(c);
-                index = (unsigned)c->clSlot[p];
+                index = nodeSlotCode(c, p);
             }
             st->ch[k].a = (int)((kind << 30) | index);
             st->ch[k].b = c->nodeNum;
@@ -803,7 +898,7 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
                 st->store = 0;
                 ns++;
                 st = &a.steps[base + ns];
-                st->outSlot = n->clSlot[p];
+                st->outSlot = (int)nodeSlotCode(n, p);
                 st->first = 0;
                 k = 0;
             }
@@ -854,7 +949,6 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.ps = L.ps;
     a.nPat = L.nPat;
     a.tblW = L.W;
-    a.clNodeDoubles = (long long)L.clNodeDoubles;
     a.pNodeDoubles = (long long)d0->pNodeDoubles;
     a.tblNodeDoubles = (long long)d0->tblNodeDoubles;
     a.tips = dp->dev.tips;
@@ -872,15 +966,14 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         PartLayout &Li = d->parts[p];
         ModelPart *mp = t->model->parts[p];
         if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != 4 || Li.W != L.W || d->pNodeDoubles != d0->pNodeDoubles ||
-            d->tblNodeDoubles != d0->tblNodeDoubles || (Li.scArena != nullptr) != (L.scArena != nullptr)) {
+            d->tblNodeDoubles != d0->tblNodeDoubles || Li.scalers != L.scalers) {
             setError("batched evaluation: the trees do not share the data part and model shape");
             return 1;
         }
         TreeHdr &h = a.hdr[i];
-        h.arena = Li.clArena;
+        h.arena = arenaBase(Li);
         h.Pdeck = d->P + Li.pOff;
         h.tbl = d->tbl + Li.tblOff;
-        h.scArena = Li.scArena;
         if (jobs[i].withLike) {
             anyLike = true;
             Node *root = t->root;
@@ -918,7 +1011,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     static const KernelFn kFn1s[3] = {cl_tree_dna_kernel<1, 128, 4, true>, cl_tree_dna_kernel<1, 64, 8, true>,
                                       cl_tree_dna_kernel<1, 32, 16, true>};
     KernelFn fn = L.nCat == 4 ? kFn4[variant] : kFn1[variant];
-    if (L.scArena) {
+    if (L.scalers) {
         if (variant > 2) { setError("scalers need one of the default launch shapes"); return 1; }
         fn = L.nCat == 4 ? kFn4s[variant] : kFn1s[variant];
     }
@@ -1269,9 +1362,35 @@ static int checkTwins(Tree *a, Tree *b)
     if (a->nNodes != b->nNodes || a->nParts != b->nParts) { setError("the two trees differ in node or part count"); return 1; }
     for (int p = 0; p < a->nParts; p++) {
         const PartLayout &A = a->dev->parts[p], &B = b->dev->parts[p];
-        if (A.clNodeDoubles != B.clNodeDoubles || A.pDoubles != B.pDoubles || A.W != B.W || (A.scArena != nullptr) != (B.scArena != nullptr)) { setError("the two trees differ in part %d layout", p); return 1; }
+        if (A.clNodeDoubles != B.clNodeDoubles || A.pDoubles != B.pDoubles || A.W != B.W || A.scalers != B.scalers || A.ps != B.ps) { setError("the two trees differ in part %d layout", p); return 1; }
     }
     return 0;
+}
+
+static bool g_shareCL = true;
+void setShareEnabled(int on) { g_shareCL = on != 0; }
+
+// Can nodes of b reference CL buffers that nodes of a hold (part p)?  Arenas pair up exclusively.
+static bool canShare(Tree *a, Tree *b, int p)
+{
+    if (!g_shareCL || a == b) return false;
+    PartLayout &LA = a->dev->parts[p], &LB = b->dev->parts[p];
+    Arena *A = LA.own.get(), *B = LB.own.get();
+    if (A->slotDoubles != B->slotDoubles || A->ps != B->ps || A->scalers != B->scalers) return false;
+    if ((A->partner && A->partner != B) || (B->partner && B->partner != A)) return false;
+    {   // both arenas must be addressable from one base with 30 bits of 256-byte units
+        const char *lo = (const char *)(A->base < B->base ? A->base : B->base);
+        const char *hiA = (const char *)(A->base + A->slotDoubles * A->nSlots), *hiB = (const char *)(B->base + B->slotDoubles * B->nSlots);
+        const char *hi = hiA > hiB ? hiA : hiB;
+        if ((size_t)(hi - lo) >= ((size_t)1 << 30) * 256) return false;
+    }
+    if (!A->partner) {
+        A->partner = B;
+        B->partner = A;
+        LA.twin = LB.own;
+        LB.twin = LA.own;
+    }
+    return LA.twin.get() == B && LB.twin.get() == A;
 }
 
 int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
@@ -1280,6 +1399,8 @@ int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
     if (treeFlushAllPending(b)) return 1;   // b's queued calls were issued before this copy
     for (int p = 0; p < a->nParts; p++)
         if (treeEnsureResident(a, p)) return 1;
+    std::vector<char> share(a->nParts);
+    for (int p = 0; p < a->nParts; p++) share[p] = canShare(a, b, p) ? 1 : 0;
     for (int j = 0; j < a->nNodes; j++) {
         const int i = a->preOrder[j];
         if (i == P4B_NO_ORDER) continue;
@@ -1288,16 +1409,24 @@ int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
         if (!doAll && !(nA->clNeedsUpdating || nB->clNeedsUpdating)) continue;
         for (int p = 0; p < a->nParts; p++) {
             if (nA->clSlot[p] < 0) continue;
-            if (nodeEnsureCLSlot(nB, p)) return 1;
             // Content that is already identical (same computation id) is not moved again.
-            if (nA->clStamp[p] != nB->clStamp[p] || !nB->clResident[p]) {
-                CUDA_TRY(cudaMemcpyAsync(nodeCL(nB, p), nodeCL(nA, p), a->dev->parts[p].clNodeDoubles * sizeof(double),
-                                         cudaMemcpyDeviceToDevice, G.stream));
-                if (nodeSC(nA, p) && nodeSC(nB, p))
-                    CUDA_TRY(cudaMemcpyAsync(nodeSC(nB, p), nodeSC(nA, p), a->dev->parts[p].ps * sizeof(int), cudaMemcpyDeviceToDevice, G.stream));
-                nB->clStamp[p] = nA->clStamp[p];
-                nB->clResident[p] = 1;
+            if (nA->clStamp[p] == nB->clStamp[p] && nB->clResident[p] && nB->clSlot[p] >= 0) continue;
+            if (share[p]) {
+                // b's node now references a's buffer; b's old slot goes back to its arena
+                PartLayout &LA = a->dev->parts[p], &LB = b->dev->parts[p];
+                Arena *src = LA.arena(nA->clSel[p]);
+                const int slot = nA->clSlot[p];
+                if (nB->clSlot[p] >= 0) slotRelease(LB.arena(nB->clSel[p]), nB->clSlot[p]);
+                src->refs[slot]++;
+                nB->clSel[p] = (char)(src == LB.own.get() ? 0 : 1);
+                nB->clSlot[p] = slot;
+            } else {
+                if (nodeMakeWritable(nB, p)) return 1;
+                CUDA_TRY(cudaMemcpyAsync(nodeCL(nB, p), nodeCL(nA, p), a->dev->parts[p].own->slotDoubles * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, G.stream));   // CL and, behind it, the exponents
             }
+            nB->clStamp[p] = nA->clStamp[p];
+            nB->clResident[p] = 1;
         }
         if (!doAll) nA->clNeedsUpdating = nB->clNeedsUpdating = 0;
     }
@@ -1309,11 +1438,30 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
     if (!doAll) { setError("p4_copyBigPDecks() doAll is not set. Programming error?"); return 1; }
     if (checkTwins(a, b)) return 1;
     if (treeFlushAllPending(a) || treeFlushAllPending(b) || flushPJobs()) return 1;
+    std::vector<std::pair<Node *, Node *>> todo;
     for (int j = 0; j < a->nNodes; j++) {
         const int i = a->preOrder[j];
         if (i == P4B_NO_ORDER) continue;
         Node *nA = a->nodes[i], *nB = b->nodes[i];
         if (!nA || !nB || nA == a->root) continue;
+        for (int p = 0; p < a->nParts; p++)
+            if (nA->pStamp[p] != nB->pStamp[p]) { todo.emplace_back(nA, nB); break; }
+    }
+    TreeDevice *da = a->dev, *db = b->dev;
+    const bool sameShape = da->pNodeDoubles == db->pNodeDoubles && da->tblNodeDoubles == db->tblNodeDoubles && a->nNodes == b->nNodes;
+    if (todo.size() > 4 && sameShape) {
+        // the decks are small (cfg 2: 100 KB of P, 380 KB of leaf tables per tree): two copies of
+        // everything beat hundreds of per-node copies on launch overhead alone
+        CUDA_TRY(cudaMemcpyAsync(db->P, da->P, da->pNodeDoubles * sizeof(double) * (size_t)a->nNodes, cudaMemcpyDeviceToDevice, G.stream));
+        if (da->tblNodeDoubles)
+            CUDA_TRY(cudaMemcpyAsync(db->tbl, da->tbl, da->tblNodeDoubles * sizeof(double) * (size_t)a->nNodes, cudaMemcpyDeviceToDevice, G.stream));
+        for (int i = 0; i < a->nNodes; i++)
+            if (a->nodes[i] && b->nodes[i])
+                for (int p = 0; p < a->nParts; p++) b->nodes[i]->pStamp[p] = a->nodes[i]->pStamp[p];
+        return 0;
+    }
+    for (auto &ab : todo) {
+        Node *nA = ab.first, *nB = ab.second;
         for (int p = 0; p < a->nParts; p++) {
             if (nA->pStamp[p] == nB->pStamp[p]) continue;
             CUDA_TRY(cudaMemcpyAsync(nodeP(nB, p), nodeP(nA, p), a->dev->parts[p].pDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
@@ -1348,6 +1496,7 @@ int treeVerifyDevice(Tree *a, Tree *b)
                 if (pass == 0) {
                     if (nA->clSlot[p] < 0 || nB->clSlot[p] < 0) { if (nA->clSlot[p] != nB->clSlot[p]) result = 1; continue; }
                     x = nodeCL(nA, p); y = nodeCL(nB, p); n = d->parts[p].clNodeDoubles;
+                    if (x == y) continue;   // one buffer referenced by both trees
                 } else {
                     x = nodeP(nA, p); y = nodeP(nB, p); n = d->parts[p].pDoubles;
                 }

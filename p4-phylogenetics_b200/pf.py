@@ -77,6 +77,7 @@ _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setTensorCoreKernel", None, _i)
 _sig("p4b_setDeferredNodeCalls", None, _i)
+_sig("p4b_setSharedCondLikes", None, _i)
 _sig("p4b_treesPartLogLike", _i, _i, _vp, _i, _vp)
 _sig("p4b_setScalers", None, _i)
 _sig("p4b_newData", _vp, _i, _i)
@@ -231,6 +232,11 @@ def setFusedTreeKernel(on):
 def setDeferredNodeCalls(on):
     """0: node-level calls launch at once instead of queueing (see include/p4b200.h)."""
     _lib.p4b_setDeferredNodeCalls(int(on))
+
+
+def setSharedCondLikes(on):
+    """0: p4_copyCondLikes really copies instead of sharing buffers between twin trees (see include/p4b200.h)."""
+    _lib.p4b_setSharedCondLikes(int(on))
 
 
 def treesPartLogLike(cTrees, pNum):

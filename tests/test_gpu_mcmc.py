@@ -135,3 +135,60 @@ def test_bulk_setcstuff_equals_per_node_calls(pkg):
     a = _mcmc(pkg, pf, 2, 13, bulk=True).run(40)
     b = _mcmc(pkg, pf, 2, 13, bulk=False).run(40)
     assert a == b
+
+
+def test_shared_buffers_equal_real_copies(pkg):
+    """p4b_setSharedCondLikes(0): p4_copyCondLikes memcpys; default: twins reference one buffer."""
+    pf = pkg.pf
+    a = _mcmc(pkg, pf, 3, 21).run(60)
+    pf.setSharedCondLikes(0)
+    try:
+        b = _mcmc(pkg, pf, 3, 21).run(60)
+    finally:
+        pf.setSharedCondLikes(1)
+    assert a == b
+
+
+def test_copy_on_write_keeps_the_twin_intact(pkg, ref_pf):
+    """After p4_copyCondLikes(cur, prop) the two trees reference the same buffers; recomputing a path in
+    prop must leave every CL of cur as it was, and vice versa."""
+    pf = pkg.pf
+    cur = pkg.synth.build_config(pf, 2, nTax=12, nPatterns=600)
+    prop = pkg.host.clone_tree(cur, pf, data=cur.data)
+    cur.calcLogLike()
+    prop.calcLogLike()
+    pf.p4_copyCondLikes(cur.cTree, prop.cTree, 1)
+    pf.p4_copyBigPDecks(cur.cTree, prop.cTree, 1)
+    pf.p4_copyModelPrams(cur.cTree, prop.cTree)
+    internals = [n.nodeNum for n in cur.iterInternalsPostOrder()]
+    before = {i: pf.getNodeCL(cur.cTree, cur.nodes[i].cNode, 0, 4, 4) for i in internals}
+    l0 = cur.logLike
+    for k, t, other in ((3, prop, cur), (7, cur, prop), (5, prop, cur)):
+        t.nodes[k].br.len *= 1.9
+        t.nodes[k].br.lenChanged = True
+        lnew = t.recalcAfterBranchChange()
+        assert lnew != l0
+        # the other tree still evaluates to its own value from its own (partly shared) buffers
+        for pNum in range(other.model.nParts):
+            pf.p4_partLogLike(other.cTree, other.data.parts[pNum].cPart, pNum, 0)
+        twin = pkg.host.clone_tree(other, ref_pf)
+        assert rel(float(sum(other.partLikes)), twin.calcLogLike()) <= LNL_TOL
+        if other is cur and k == 3:
+            for i in internals:
+                assert np.array_equal(pf.getNodeCL(cur.cTree, cur.nodes[i].cNode, 0, 4, 4), before[i])
+    # many rounds of copy / recompute never run out of slots
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        src, dst = (cur, prop) if rng.random() < 0.5 else (prop, cur)
+        k = int(rng.integers(1, len(src.nodes)))
+        src.nodes[k].br.len = float(rng.uniform(0.01, 0.3))
+        src.nodes[k].br.lenChanged = True
+        src.recalcAfterBranchChange()
+        for x, y in zip(src.nodes, dst.nodes):
+            y.br.len = x.br.len
+        dst.setCStuff()
+        pf.p4_copyCondLikes(src.cTree, dst.cTree, 1)
+        pf.p4_copyBigPDecks(src.cTree, dst.cTree, 1)
+        pf.p4_copyModelPrams(src.cTree, dst.cTree)
+        assert pf.p4_verifyIdentityOfTwoTrees(src.cTree, dst.cTree) == 0
+    assert rel(cur.calcLogLike(), pkg.host.clone_tree(cur, ref_pf).calcLogLike()) <= LNL_TOL
