@@ -75,6 +75,10 @@ int p4b_commDestroy(void);
  * default; 0 selects the one-launch-per-node kernels instead (same results;
  * kept for comparison and profiling). */
 void p4b_setFusedTreeKernel(int on);
+/* 20-state parts with 4 rate categories have a whole-tree kernel of their own (FP64 tensor cores, the
+ * running CL stays in the accumulator registers from one node to the next); 0 keeps the one-launch-
+ * per-node kernels for them. */
+void p4b_setFusedTreeKernel20(int on);
 /* Node-level calls (p4b_calculateBigPDecks, p4b_setConditionalLikelihoodsOfInternalNodePart) only
  * QUEUE work by default (1): the reference's callers issue them in dependency order along the dirty
  * path of a proposal (p4/chain.py:668-688), and the engine runs a tree's whole queue as one P(t)

@@ -37,6 +37,7 @@ int p4b_commInitRank(const char id128[128], int rank, int world) { return commIn
 int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
+void p4b_setFusedTreeKernel20(int on) { setFusedAAEnabled(on); }
 void p4b_setDeferredNodeCalls(int on) { setDeferEnabled(on); }
 void p4b_setSharedCondLikes(int on) { setShareEnabled(on); }
 void p4b_setTensorCoreKernel(int on) { setDmmaEnabled(on); }

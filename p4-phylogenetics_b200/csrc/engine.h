@@ -184,6 +184,7 @@ int treeFlushPending(Tree *t);
 bool treeHasPending(Tree *t);
 void setDeferEnabled(int on);
 void setShareEnabled(int on);
+void setFusedAAEnabled(int on);
 int treesPartLogLike(Tree **trees, int n, int p, double *out);
 
 // comm.cpp -- NCCL, loaded at run time

@@ -28,6 +28,7 @@ struct PJob {
     double *tbl;           // the node's leaf lookup table; used when tblW > 0
     const double *eig;     // device mirror of the eigensystem: V | Vinv | lambda
     const uint64_t *eq;    // masks of the part's non-N-like equates
+    double *aux;           // 20-state parts served by the whole-tree kernel: P^T in fragment order + transposed leaf table
     int dim, nCat, tblW, nRealEq;
     long long tOff;        // into the staged doubles: t[cat] effective branch lengths
 };
@@ -172,6 +173,30 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
             T[idx] = v;
         }
     }
+    if (job.aux) {
+        // Operand decks of cl_tree_aa_kernel, so that its per-step staging is a straight copy:
+        //   aux[0 .. nCat*576)            P^T in mma fragment order [cat][kk = 2t+i][nt][lane]: lane (g,q) holds
+        //                                 P[cat][8nt+g][8t+2q+i], zero where either state is >= 20
+        //   aux[nCat*576 .. +nCat*W*20)   leaf table transposed, [cat][w][state]
+        __syncthreads();
+        double *A = job.aux;
+        const int nF = nCat * 576;
+        for (int i = threadIdx.x; i < nF; i += blockDim.x) {
+            const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 6, ct = i / 576;
+            const int s = 8 * nt + (l >> 2), x = 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1);
+            A[i] = (s < dim && x < dim) ? P[(ct * dim + s) * dim + x] : 0.0;
+        }
+        if (job.tblW > 0) {
+            const int W = job.tblW;
+            const double *T = job.tbl;
+            double *TT = A + nF;
+            const int nT = nCat * W * dim;
+            for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+                const int st = i % dim, w = (i / dim) % W, ct = i / (dim * W);
+                TT[i] = T[(ct * dim + st) * W + w];
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -308,6 +333,7 @@ struct TreeHdr {
     double *arena;            // base address the tree's CL buffers are addressed from (covers its own arena and its twin's)
     const double *Pdeck;      // tree's P decks, already offset to this part
     const double *tbl;        // tree's leaf tables, already offset to this part
+    const double *aux;        // 20-state kernel: tree's fragment-order decks, already offset to this part
     double *patLikes;         // optional
     double *partials;         // [2*gridDim.x]
     const uint8_t *rootTips;  // non-NULL when the root is a leaf
@@ -323,6 +349,7 @@ struct TreeArgs {
     int ps, nPat, tblW, nTrees;
     long long pNodeDoubles;   // stride between nodes in a P deck
     long long tblNodeDoubles;
+    long long auxNodeDoubles;
     const uint8_t *tips;      // part's tip rows [nTax][ps]
     const int *counts;
     const uint64_t *invarMask;
@@ -825,6 +852,254 @@ cl_dmma20_kernel(const __grid_constant__ CLArgs a)
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Whole-tree CL recursion, 20 states, FP64 tensor cores, ONE launch.
+//
+// The per-node kernel above computes out = P x cl_child with P as the A operand, so its result
+// comes out of the tensor core in the C layout and would have to be transposed (shared memory or
+// shuffles) before it could be the B operand of the parent's product.  Here the product is taken
+// the other way round,  out^T = cl_child^T x P^T :
+//   A (8 x 4)  = child CL, rows = patterns, columns = child states
+//   B (4 x 8)  = P^T,      rows = child states, columns = parent states   (pre-arranged in shared memory)
+//   C (8 x 8)  = parent CL, rows = patterns, columns = parent states
+// and the summation index is dealt to the k-steps so that k-step (t, i), t = 0..2, i = 0..1, covers the
+// child states {8t + 2q + i : q = 0..3}.  Lane (g, q) then needs, as its A element of k-step (t, i), the
+// value (pattern g, state 8t + 2q + i) -- exactly what it holds as C element i of n-tile t after the child
+// was computed.  A node's result is therefore the next node's operand with no data movement at all: a warp
+// walks the whole step list with the running CL in registers, like the 4-state kernel does with FMAs.
+// States are padded 20 -> 24 in both directions (zeros in B), 18 DMMAs per child and 8 patterns.
+//
+// A warp owns one rate category of one group of 8*MT patterns (categories never mix below the root);
+// m-tile j, row g  <->  pattern pat0 + MT*g + j, so a lane's MT m-tiles are MT consecutive patterns of a
+// row (16-byte accesses), and the eight g-lanes cover 64*MT contiguous bytes.  A CTA is NCAT x GROUPS
+// warps; P^T fragments and leaf tables of a step are staged into shared memory one step ahead (cp.async,
+// double-buffered) as straight copies: the P(t) kernel leaves P^T in fragment order and the leaf table
+// transposed ([code][state]) in an operand deck of its own.  Steps have at most two children (wider nodes
+// are chained by the host).  The root reduction is a separate kernel (like_kernel).
+// ---------------------------------------------------------------------------
+constexpr int kAAKids = 2;
+constexpr int kAAFrag = 18 * 32;     // doubles of P^T fragments per child and category
+
+__device__ __forceinline__ void named_barrier(int id, int nThreads)
+{
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nThreads) : "memory");
+}
+// mbarrier + bulk (TMA) copy: one thread arms the barrier with the byte count and issues the copies;
+// everybody waits on the barrier's phase parity.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smemDst, const void *gmemSrc, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smemDst)),
+                 "l"(gmemSrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    int spins = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (!done && ++spins > (1 << 22)) __trap();   // a lost copy must be an error, never a hang
+    } while (!done);
+}
+
+template <int NCAT, int GROUPS, int MINB, int MT>
+__global__ void __launch_bounds__(NCAT * GROUPS * 32, MINB)
+cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
+{
+    constexpr int DIM = 20, GT = GROUPS * 32;   // threads of one category group
+    constexpr int WP = 8 * MT;                  // patterns per warp: MT m-tiles of 8; a lane owns MT consecutive patterns of a row
+    const int treeIdx = blockIdx.y;
+    const TreeHdr &hd = a.hdr[treeIdx];
+    extern __shared__ double sm[];              // [cat][2 buffers][kAAKids][slot], then [cat][2] mbarriers
+    const int W = a.tblW;
+    const int tblSize = DIM * W;                // per category
+    const int slot = kAAFrag > tblSize ? kAAFrag : tblSize;
+    const int bufSize = kAAKids * slot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    // The warps of one rate category (one per pattern group) form a group of their own: one of its threads
+    // stages that category's operands (bulk copies signalling an mbarrier) and the group synchronises on a
+    // named barrier, so the categories of a CTA drift apart and one category's tensor-core phase overlaps
+    // another's loads and stores.  Consecutive warps belong to one category, so every SM sub-partition
+    // (warp % 4) hosts warps of different groups.
+    const int cat = warp / GROUPS, grp = warp % GROUPS;
+    const int gtid = grp * 32 + lane;
+    double *smc = sm + (size_t)cat * 2 * bufSize;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + (size_t)NCAT * 2 * bufSize) + cat * 2;
+    const int pat0 = (blockIdx.x * GROUPS + grp) * WP;
+    const bool active = pat0 < a.ps;
+    const size_t ps = (size_t)a.ps;
+    const size_t rowBase = (size_t)cat * DIM * ps + pat0 + MT * g;   // + state * ps: this lane's MT patterns of a row
+    const size_t auxLeafOff = (size_t)NCAT * kAAFrag + (size_t)cat * tblSize;
+    const int nSteps = hd.nSteps, stepBase = hd.stepBase;
+    // Lanes q >= 2 hold, in n-tile 2, the padding states 16+2q+i >= 20.  Their operand values only ever meet
+    // zeros of P^T, so any FINITE number will do: they re-read the rows 8 states lower instead of branching.
+    const bool tail = q >= 2;
+    const size_t hiRow = (size_t)(tail ? 8 : 16) * ps;
+
+    auto stage = [&](int stepIdx, int b) {      // one thread per category
+        const StepC &st = a.steps[stepBase + stepIdx];
+        const int nc = st.nChildren;
+        unsigned total = 0;
+        for (int c = 0; c < nc; c++) total += (((unsigned)st.ch[c].a >> 30) == 2u ? tblSize : kAAFrag) * 8;
+        mbar_expect_tx(bars + b, total);
+        for (int c = 0; c < nc; c++) {
+            const bool leaf = ((unsigned)st.ch[c].a >> 30) == 2u;
+            const double *src = hd.aux + a.auxNodeDoubles * st.ch[c].b + (leaf ? auxLeafOff : (size_t)cat * kAAFrag);
+            bulk_g2s(smc + b * bufSize + c * slot, src, (leaf ? tblSize : kAAFrag) * 8, bars + b);
+        }
+    };
+    // tip codes (MT patterns, one byte each) of child c of a step, if it is a leaf; fetched one step ahead
+    auto tipCode = [&](int stepIdx, int c) -> unsigned {
+        if (!active || stepIdx >= nSteps) return 0u;
+        const StepC &st = a.steps[stepBase + stepIdx];
+        const unsigned av = (unsigned)st.ch[c].a;
+        if (c >= st.nChildren || (av >> 30) != 2u) return 0u;
+        const uint8_t *tp = a.tips + (size_t)(av & 0x3fffffffu) * ps + pat0 + MT * g;
+        return MT == 4 ? *reinterpret_cast<const unsigned *>(tp) : (unsigned)*reinterpret_cast<const unsigned short *>(tp);
+    };
+
+    // out (=|*=) A x B for one child: A in registers (C layout of the child), B fragments of this category.
+    // The three n-tiles advance together: 3*MT independent accumulator chains keep the tensor pipe fed.
+    auto contract = [&](const double (&A)[MT][3][2], const double *__restrict__ Bc, double (&out)[MT][3][2], bool assign) {
+        double acc[MT][3][2];
+#pragma unroll
+        for (int j = 0; j < MT; j++)
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) acc[j][nt][0] = acc[j][nt][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) {
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) {
+                const double b = Bc[(kk * 3 + nt) * 32];
+#pragma unroll
+                for (int j = 0; j < MT; j++) dmma884(acc[j][nt][0], acc[j][nt][1], A[j][kk >> 1][kk & 1], b);
+            }
+        }
+        if (assign) {
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) { out[j][nt][0] = acc[j][nt][0]; out[j][nt][1] = acc[j][nt][1]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) { out[j][nt][0] *= acc[j][nt][0]; out[j][nt][1] *= acc[j][nt][1]; }
+        }
+    };
+
+    unsigned next0 = 0u, next1 = 0u;   // tip codes of the next step's children
+
+    // One step: `in` holds the CL of the node computed by the previous step, `out` receives this node's.
+    // The caller alternates two register arrays, so no step ends with a copy.
+    auto step = [&](int si, const double (&in)[MT][3][2], double (&out)[MT][3][2]) {
+        named_barrier(1 + cat, GT);   // every warp of the category is done with step si-1: its buffer is free
+        if (gtid == 0 && si + 1 < nSteps) stage(si + 1, (si + 1) & 1);
+        const unsigned code0 = next0, code1 = next1;
+        next0 = tipCode(si + 1, 0);          // in flight while this step computes
+        next1 = tipCode(si + 1, 1);
+        mbar_wait(bars + (si & 1), (unsigned)(si >> 1) & 1u);   // this step's operands have landed
+        if (!active) return;
+        const double *buf = smc + (si & 1) * bufSize;
+        const StepC &st = a.steps[stepBase + si];
+        const int nc = st.nChildren;
+        int regChild = -1;
+        for (int c = 0; c < nc; c++)
+            if (((unsigned)st.ch[c].a >> 30) == 1u) regChild = c;
+        if (regChild >= 0) {                 // the child computed by the previous step: straight from registers
+            contract(in, buf + regChild * slot + lane, out, true);
+        } else if (!st.first) {              // continuation of a node with more than two children
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int t = 0; t < 3; t++) { out[j][t][0] = in[j][t][0]; out[j][t][1] = in[j][t][1]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int t = 0; t < 3; t++) out[j][t][0] = out[j][t][1] = 1.0;
+        }
+        for (int c = 0; c < nc; c++) {
+            if (c == regChild) continue;
+            const unsigned av = (unsigned)st.ch[c].a, kind = av >> 30;
+            if (kind == 2u) {
+                // leaf: out *= T[state][code]; the table is [code][state], so the lane's states 8t+2q, 8t+2q+1 are one 16-byte load
+                const unsigned cw = c == 0 ? code0 : code1;
+                const double *T = buf + c * slot + 2 * q;
+#pragma unroll
+                for (int j = 0; j < MT; j++) {
+                    const double *Tj = T + ((cw >> (8 * j)) & 0xffu) * DIM;
+                    const double2 v0 = *reinterpret_cast<const double2 *>(Tj);
+                    const double2 v1 = *reinterpret_cast<const double2 *>(Tj + 8);
+                    const double2 v2 = *reinterpret_cast<const double2 *>(Tj + (tail ? 8 : 16));
+                    out[j][0][0] *= v0.x; out[j][0][1] *= v0.y;
+                    out[j][1][0] *= v1.x; out[j][1][1] *= v1.y;
+                    out[j][2][0] *= tail ? 0.0 : v2.x;    // padding entries must stay finite: keep them at zero
+                    out[j][2][1] *= tail ? 0.0 : v2.y;
+                }
+            } else {                         // internal child in memory (written earlier by this same lane)
+                const double *cl = hd.arena + (size_t)(av & 0x3fffffffu) * 32 + rowBase + (size_t)(2 * q) * ps;
+                double sib[MT][3][2];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    const double *row = cl + (r < 4 ? (size_t)(8 * (r >> 1)) * ps : hiRow) + (size_t)(r & 1) * ps;
+#pragma unroll
+                    for (int h = 0; h < MT / 2; h++) {
+                        const double2 v = ld2(row + 2 * h);
+                        sib[2 * h][r >> 1][r & 1] = v.x;
+                        sib[2 * h + 1][r >> 1][r & 1] = v.y;
+                    }
+                }
+                contract(sib, buf + c * slot + lane, out, false);
+            }
+        }
+        if (st.store) {
+            double *o = hd.arena + (size_t)(unsigned)st.outSlot * 32 + rowBase + (size_t)(2 * q) * ps;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                if (r < 4 || !tail) {
+                    double *orow = o + (size_t)(8 * (r >> 1) + (r & 1)) * ps;
+#pragma unroll
+                    for (int h = 0; h < MT / 2; h++) st2(orow + 2 * h, make_double2(out[2 * h][r >> 1][r & 1], out[2 * h + 1][r >> 1][r & 1]));
+                }
+            }
+        }
+    };
+
+    double cA[MT][3][2], cB[MT][3][2];
+#pragma unroll
+    for (int j = 0; j < MT; j++)
+#pragma unroll
+        for (int t = 0; t < 3; t++) cA[j][t][0] = cA[j][t][1] = cB[j][t][0] = cB[j][t][1] = 0.0;
+
+    if (gtid == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    named_barrier(1 + cat, GT);
+    if (gtid == 0 && nSteps > 0) stage(0, 0);
+    next0 = tipCode(0, 0);
+    next1 = tipCode(0, 1);
+    for (int si = 0; si < nSteps; si += 2) {
+        step(si, cA, cB);
+        if (si + 1 < nSteps) step(si + 1, cB, cA);
     }
 }
 

@@ -254,6 +254,7 @@ struct PartLayout {
     size_t clNodeDoubles = 0;    // nCat*dim*ps
     size_t pOff = 0, pDoubles = 0;       // within a node's P deck
     size_t tblOff = 0, tblDoubles = 0;   // within a node's leaf tables
+    size_t auxOff = 0, auxDoubles = 0;   // within a node's operand decks of the 20-state whole-tree kernel (0: none)
     size_t eigOff = 0, eigStride = 0;    // within the eig mirror; stride per (comp,rMatrix)
     size_t eqOff = 0;                    // within the equate mask mirror
     int nPairs = 0;                      // nComps*nRMatrices
@@ -270,8 +271,8 @@ struct TreeDevice {
     // normally p4_partLogLike, which then also gets the root reduction fused in.
     std::vector<std::vector<Node *>> pending;
     bool scalers = false;
-    size_t pNodeDoubles = 0, tblNodeDoubles = 0;
-    double *P = nullptr, *tbl = nullptr, *eig = nullptr;
+    size_t pNodeDoubles = 0, tblNodeDoubles = 0, auxNodeDoubles = 0;
+    double *P = nullptr, *tbl = nullptr, *eig = nullptr, *aux = nullptr;
     uint64_t *eqMasks = nullptr;
     double *result = nullptr;     // [2*nParts] device
     double *hResult = nullptr;    // pinned
@@ -317,6 +318,11 @@ int treeDeviceCreate(Tree *t)
         L.tblOff = d->tblNodeDoubles;
         L.tblDoubles = (size_t)L.nCat * L.dim * L.W;
         d->tblNodeDoubles += L.tblDoubles;
+        if (L.dim == 20 && L.nCat == 4) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
+            L.auxOff = d->auxNodeDoubles;
+            L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * L.dim * L.W;
+            d->auxNodeDoubles += L.auxDoubles;
+        }
         L.nPairs = mp->nComps * mp->nRMatrices;
         L.eigStride = (size_t)2 * L.dim * L.dim + L.dim;
         L.eigOff = eigTotal;
@@ -347,6 +353,12 @@ int treeDeviceCreate(Tree *t)
     CUDA_TRY(cudaMemsetAsync(d->P, 0, pBytes, G.stream));
     CUDA_TRY(cudaMalloc(&d->tbl, tblBytes));
     CUDA_TRY(cudaMemsetAsync(d->tbl, 0, tblBytes, G.stream));
+    if (d->auxNodeDoubles) {
+        const size_t auxBytes = d->auxNodeDoubles * sizeof(double) * (size_t)t->nNodes;
+        CUDA_TRY(cudaMalloc(&d->aux, auxBytes));
+        CUDA_TRY(cudaMemsetAsync(d->aux, 0, auxBytes, G.stream));
+        d->bytes += (long long)auxBytes;
+    }
     CUDA_TRY(cudaMalloc(&d->eig, eigTotal * sizeof(double)));
     CUDA_TRY(cudaMalloc(&d->eqMasks, eqTotal * sizeof(uint64_t)));
     for (int p = 0; p < t->nParts; p++) {
@@ -382,6 +394,7 @@ void treeDeviceDestroy(Tree *t)
     }
     if (d->P) cudaFree(d->P);
     if (d->tbl) cudaFree(d->tbl);
+    if (d->aux) cudaFree(d->aux);
     if (d->eig) cudaFree(d->eig);
     if (d->eqMasks) cudaFree(d->eqMasks);
     if (d->result) cudaFree(d->result);
@@ -499,6 +512,11 @@ static inline double *nodeP(Node *n, int p)
     TreeDevice *d = n->tree->dev;
     return d->P + d->pNodeDoubles * (size_t)n->nodeNum + d->parts[p].pOff;
 }
+static inline double *nodeAux(Node *n, int p)
+{
+    TreeDevice *d = n->tree->dev;
+    return d->aux + d->auxNodeDoubles * (size_t)n->nodeNum + d->parts[p].auxOff;
+}
 static inline double *nodeTbl(Node *n, int p)
 {
     TreeDevice *d = n->tree->dev;
@@ -596,6 +614,7 @@ static int buildPJob(Node *n, int p)
     j.tbl = d->tbl + d->tblNodeDoubles * (size_t)n->nodeNum + L.tblOff;
     j.eig = d->eig + L.eigOff + L.eigStride * (size_t)(c * mp->nRMatrices + r);
     j.eq = d->eqMasks + L.eqOff;
+    j.aux = L.auxDoubles ? d->aux + d->auxNodeDoubles * (size_t)n->nodeNum + L.auxOff : nullptr;
     j.dim = L.dim;
     j.nCat = L.nCat;
     j.tblW = n->isLeaf ? L.W : 0;
@@ -686,9 +705,16 @@ static bool g_fusedEnabled = true;
 static bool g_deferCL = true;
 void setDeferEnabled(int on) { g_deferCL = on != 0; }
 
+static bool g_fusedAAEnabled = true;
+void setFusedAAEnabled(int on) { g_fusedAAEnabled = on != 0; }
+
+// Parts the whole-tree kernels serve: 4 states (FMA kernel), 20 states with 4 categories (tensor-core kernel).
 static bool fusedEligible(const PartLayout &L)
 {
-    return g_fusedEnabled && L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
+    if (!g_fusedEnabled) return false;
+    if (L.dim == 4) return L.nCat == 4 || L.nCat == 1;
+    if (L.dim == 20) return g_fusedAAEnabled && g_dmmaEnabled && L.nCat == 4 && !L.scalers && L.W <= 64;
+    return false;
 }
 
 // Shared memory of the tensor-core kernel: A fragments of the internal children
@@ -821,6 +847,8 @@ int nodeSetCL(Node *n, int p)
 // Whole-tree recursion in one launch (4-state parts)
 // ---------------------------------------------------------------------------
 
+static int enqueueRootLike(Tree *t, int p, bool wantPatLikes, double *resultDev);
+
 // One job of a batched whole-tree launch: the nodes of one tree to compute, in dependency order.
 struct FusedJob {
     Tree *t;
@@ -851,7 +879,7 @@ static int fusedVariant(int ps, int nTrees)
 
 // Append the steps of one job to the argument block.  Returns the number of steps written, or -1 on
 // error, or -2 when they do not fit into `room` steps (nothing is modified in that case beyond a.steps).
-static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int p, bool *overflowOk, size_t *resumeAt)
+static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int p, bool *overflowOk, size_t *resumeAt, int maxKids)
 {
     Tree *t = job.t;
     Part *dp = t->data->parts[p];
@@ -866,7 +894,7 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
         if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return -1; }
         int nKids = 0;
         for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
-        const int chunks = (nKids + kMaxChildren - 1) / kMaxChildren;
+        const int chunks = (nKids + maxKids - 1) / maxKids;
         if (ns + chunks > room) {
             if (!overflowOk || !*overflowOk) return -2;
             break;   // the caller launches what we have and calls again from *resumeAt
@@ -893,7 +921,7 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
             st->ch[k].a = (int)((kind << 30) | index);
             st->ch[k].b = c->nodeNum;
             k++;
-            if (k == kMaxChildren && c->sibling) {   // polytomy wider than one step: continue in the next
+            if (k == maxKids && c->sibling) {   // node wider than one step: continue in the next
                 st->nChildren = (short)k;
                 st->store = 0;
                 ns++;
@@ -905,8 +933,8 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
         }
         st->nChildren = (short)k;
         st->store = 1;
-        if (k == 2 && st->first) {
-            // two-children step: its one re-loaded internal child (if any) goes through the prefetch buffer
+        if (k == 2 && st->first && maxKids > 2) {
+            // two-children step (4-state kernel): its one re-loaded internal child (if any) goes through the prefetch buffer
             const unsigned k0 = (unsigned)st->ch[0].a >> 30, k1 = (unsigned)st->ch[1].a >> 30;
             if (k0 == 0u && k1 != 0u) st->ch[0].a = (int)((3u << 30) | ((unsigned)st->ch[0].a & 0x3fffffffu));
             else if (k1 == 0u && k0 != 0u) st->ch[1].a = (int)((3u << 30) | ((unsigned)st->ch[1].a & 0x3fffffffu));
@@ -951,22 +979,39 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.tblW = L.W;
     a.pNodeDoubles = (long long)d0->pNodeDoubles;
     a.tblNodeDoubles = (long long)d0->tblNodeDoubles;
+    a.auxNodeDoubles = (long long)d0->auxNodeDoubles;
     a.tips = dp->dev.tips;
     a.counts = dp->dev.counts;
     a.invarMask = dp->dev.invarMask;
     a.eqMask = dp->dev.equateMask;
-    const int variant = fusedVariant(L.ps, nJobs);
+    const bool aa = L.dim == 20;      // tensor-core kernel: root reduction is a separate kernel
+    const int variant = aa ? 0 : fusedVariant(L.ps, nJobs);
     static const int kThreads[5] = {128, 64, 32, 128, 256};
-    const int THREADS = kThreads[variant];
-    const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
+    static int aaGroups = -1, aaMinB = 1, aaMT = 2;   // 20-state kernel: pattern groups per CTA, CTAs per SM, m-tiles per warp
+    if (aaGroups < 0) {
+        const char *e = getenv("P4B_AA_GROUPS");
+        // measured on B200, cfg 3 (100 taxa x 200 k patterns): groups x CTAs/SM = 2x2 5.63 ms, 1x3 5.76, 3x1 5.98,
+        // 4x1 6.32 (all with 2 m-tiles per warp); 2x1 with 4 m-tiles 6.02; the per-node kernels 7.70
+        aaGroups = e ? atoi(e) : 2;
+        if (aaGroups < 1 || aaGroups > 4) aaGroups = 2;
+        e = getenv("P4B_AA_MINB");
+        aaMinB = e ? atoi(e) : (aaGroups == 2 ? 2 : 1);
+        if (aaMinB < 1 || aaMinB > 3 || aaMinB * aaGroups > 4) aaMinB = 1;
+        e = getenv("P4B_AA_MT");
+        aaMT = e ? atoi(e) : 2;
+        if (aaMT != 2 && aaMT != 4) aaMT = 2;
+    }
+    const int THREADS = aa ? 128 * aaGroups : kThreads[variant];
+    const int blocks = aa ? (L.ps / (8 * aaMT) + aaGroups - 1) / aaGroups : (L.ps / 2 + THREADS - 1) / THREADS;
+    const int maxKids = aa ? kAAKids : kMaxChildren;
     bool anyLike = false;
     for (int i = 0; i < nJobs; i++) {
         Tree *t = jobs[i].t;
         TreeDevice *d = t->dev;
         PartLayout &Li = d->parts[p];
         ModelPart *mp = t->model->parts[p];
-        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != 4 || Li.W != L.W || d->pNodeDoubles != d0->pNodeDoubles ||
-            d->tblNodeDoubles != d0->tblNodeDoubles || Li.scalers != L.scalers) {
+        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != L.dim || Li.W != L.W || d->pNodeDoubles != d0->pNodeDoubles ||
+            d->tblNodeDoubles != d0->tblNodeDoubles || d->auxNodeDoubles != d0->auxNodeDoubles || Li.scalers != L.scalers) {
             setError("batched evaluation: the trees do not share the data part and model shape");
             return 1;
         }
@@ -974,7 +1019,10 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         h.arena = arenaBase(Li);
         h.Pdeck = d->P + Li.pOff;
         h.tbl = d->tbl + Li.tblOff;
-        if (jobs[i].withLike) {
+        h.aux = d->aux ? d->aux + Li.auxOff : nullptr;
+        if (jobs[i].withLike && aa) {
+            if (!t->root || jobs[i].order->empty() || jobs[i].order->back() != t->root) { setError("fused evaluation: the last node must be the root"); return 1; }
+        } else if (jobs[i].withLike) {
             anyLike = true;
             Node *root = t->root;
             if (!root || jobs[i].order->empty() || jobs[i].order->back() != root) { setError("fused evaluation: the last node must be the root"); return 1; }
@@ -997,9 +1045,23 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         }
     }
     const int K = L.nCat * 4;
-    const size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
-    if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
+    size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
+    if (aa) {
+        const size_t frag = kAAFrag, tblSize = (size_t)20 * L.W;   // per category
+        smem = (size_t)L.nCat * 2 * kAAKids * (frag > tblSize ? frag : tblSize) * sizeof(double) + 64;   // + the mbarriers
+        if (!d0->aux) { setError("internal: 20-state whole-tree kernel without operand decks"); return 1; }
+    }
+    if (smem > (aa ? 200 : 100) * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
     typedef void (*KernelFn)(const TreeArgs);
+    static const KernelFn kFnAA[2][4][3] = {
+        {{cl_tree_aa_kernel<4, 1, 1, 2>, cl_tree_aa_kernel<4, 1, 2, 2>, cl_tree_aa_kernel<4, 1, 3, 2>},
+         {cl_tree_aa_kernel<4, 2, 1, 2>, cl_tree_aa_kernel<4, 2, 2, 2>, nullptr},
+         {cl_tree_aa_kernel<4, 3, 1, 2>, nullptr, nullptr},
+         {cl_tree_aa_kernel<4, 4, 1, 2>, nullptr, nullptr}},
+        {{cl_tree_aa_kernel<4, 1, 1, 4>, cl_tree_aa_kernel<4, 1, 2, 4>, cl_tree_aa_kernel<4, 1, 3, 4>},
+         {cl_tree_aa_kernel<4, 2, 1, 4>, cl_tree_aa_kernel<4, 2, 2, 4>, nullptr},
+         {cl_tree_aa_kernel<4, 3, 1, 4>, nullptr, nullptr},
+         {cl_tree_aa_kernel<4, 4, 1, 4>, nullptr, nullptr}}};
     static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
                                      cl_tree_dna_kernel<4, 32, 12, false>, cl_tree_dna_kernel<4, 128, 4, false>,
                                      cl_tree_dna_kernel<4, 256, 2, false>};
@@ -1015,8 +1077,13 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         if (variant > 2) { setError("scalers need one of the default launch shapes"); return 1; }
         fn = L.nCat == 4 ? kFn4s[variant] : kFn1s[variant];
     }
+    if (aa) fn = kFnAA[aaMT / 2 - 1][aaGroups - 1][aaMinB - 1];
     static bool attrSet = false;
     if (!attrSet) {
+        for (int t = 0; t < 2; t++)
+            for (int v = 0; v < 4; v++)
+                for (int m = 0; m < 3; m++)
+                    if (kFnAA[t][v][m]) CUDA_TRY(cudaFuncSetAttribute(kFnAA[t][v][m], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         for (int v = 0; v < 5; v++) {
             CUDA_TRY(cudaFuncSetAttribute(kFn4[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(kFn1[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1041,12 +1108,12 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         size_t at = 0;
         for (;;) {
             bool more = jobs[0].storeAll;   // in: cutting allowed (not for lnL-only evaluations); out: steps remain
-            const int ns = buildSteps(a, 0, kMaxSteps, jobs[0], p, &more, &at);
+            const int ns = buildSteps(a, 0, kMaxSteps, jobs[0], p, &more, &at, maxKids);
             if (ns == -2) { setError("internal: lnL-only evaluation needs the whole tree in one launch"); return 1; }
             if (ns < 0) return 1;
             a.hdr[0].stepBase = 0;
             a.hdr[0].nSteps = ns;
-            a.hdr[0].doLike = (jobs[0].withLike && !more) ? 1 : 0;
+            a.hdr[0].doLike = (jobs[0].withLike && !more && !aa) ? 1 : 0;
             if (ns > 0 || a.hdr[0].doLike)
                 if (launch(1)) return 1;
             if (!more) break;
@@ -1054,12 +1121,12 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     } else {
         int base = 0;
         for (int i = 0; i < nJobs; i++) {
-            const int ns = buildSteps(a, base, kMaxSteps - base, jobs[i], p, nullptr, nullptr);
+            const int ns = buildSteps(a, base, kMaxSteps - base, jobs[i], p, nullptr, nullptr, maxKids);
             if (ns == -2) { setError("batched evaluation: the step lists of the trees do not fit one launch"); return 1; }
             if (ns < 0) return 1;
             a.hdr[i].stepBase = base;
             a.hdr[i].nSteps = ns;
-            a.hdr[i].doLike = jobs[i].withLike ? 1 : 0;
+            a.hdr[i].doLike = (jobs[i].withLike && !aa) ? 1 : 0;
             base += ns;
         }
         if (launch(nJobs)) return 1;
@@ -1078,6 +1145,10 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         CUDA_TRY(cudaGetLastError());
         G.launches++;
     }
+    if (aa)
+        for (int i = 0; i < nJobs; i++)
+            if (jobs[i].withLike)
+                if (enqueueRootLike(jobs[i].t, p, jobs[i].wantPatLikes, resultDev + 2 * i)) return 1;
     return 0;
 }
 
@@ -1145,7 +1216,8 @@ bool treeHasPending(Tree *t)
 // ---------------------------------------------------------------------------
 // Log-likelihood
 // ---------------------------------------------------------------------------
-static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
+// like_kernel + fold on the root CL as it is in memory now (stream order).
+static int enqueueRootLike(Tree *t, int p, bool wantPatLikes, double *resultDev)
 {
     TreeDevice *d = t->dev;
     PartLayout &L = d->parts[p];
@@ -1154,7 +1226,6 @@ static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
     Node *root = t->root;
     if (!root) { setError("tree has no root"); return 1; }
     if (root->clSlot[p] < 0) { setError("the root has no conditional likelihoods"); return 1; }
-    if (treeEnsureResident(t, p)) return 1;
     const int rc = root->compNums[p];
     if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
     LikeArgs a;
@@ -1184,10 +1255,18 @@ static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
     a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
     like_kernel<<<blocks, 256, 0, G.stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, d->result + 2 * p);
+    like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, resultDev);
     CUDA_TRY(cudaGetLastError());
     G.launches += 2;
     return 0;
+}
+
+static int enqueuePartLike(Tree *t, int p, bool wantPatLikes)
+{
+    if (!t->root) { setError("tree has no root"); return 1; }
+    if (t->root->clSlot[p] < 0) { setError("the root has no conditional likelihoods"); return 1; }
+    if (treeEnsureResident(t, p)) return 1;
+    return enqueueRootLike(t, p, wantPatLikes, t->dev->result + 2 * p);
 }
 
 static int fetchResults(Tree *t, int p0, int p1)
@@ -1257,7 +1336,7 @@ double treeLogLike(Tree *t, int getSiteLikes)
     std::vector<char> likeDone(t->nParts, 0);
     for (int p = 0; p < t->nParts; p++) {
         if (fusedEligible(d->parts[p])) {
-            const bool storeAll = t->storeCL != 0 || order.size() + 8 > (size_t)kMaxSteps;
+            const bool storeAll = t->storeCL != 0 || d->parts[p].dim != 4 || order.size() + 8 > (size_t)kMaxSteps;
             if (launchFusedTree(t, p, order, true, getSiteLikes != 0, storeAll)) return NAN;
             likeDone[p] = 1;
             if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
@@ -1448,13 +1527,16 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
             if (nA->pStamp[p] != nB->pStamp[p]) { todo.emplace_back(nA, nB); break; }
     }
     TreeDevice *da = a->dev, *db = b->dev;
-    const bool sameShape = da->pNodeDoubles == db->pNodeDoubles && da->tblNodeDoubles == db->tblNodeDoubles && a->nNodes == b->nNodes;
+    const bool sameShape = da->pNodeDoubles == db->pNodeDoubles && da->tblNodeDoubles == db->tblNodeDoubles &&
+                           da->auxNodeDoubles == db->auxNodeDoubles && a->nNodes == b->nNodes;
     if (todo.size() > 4 && sameShape) {
         // the decks are small (cfg 2: 100 KB of P, 380 KB of leaf tables per tree): two copies of
         // everything beat hundreds of per-node copies on launch overhead alone
         CUDA_TRY(cudaMemcpyAsync(db->P, da->P, da->pNodeDoubles * sizeof(double) * (size_t)a->nNodes, cudaMemcpyDeviceToDevice, G.stream));
         if (da->tblNodeDoubles)
             CUDA_TRY(cudaMemcpyAsync(db->tbl, da->tbl, da->tblNodeDoubles * sizeof(double) * (size_t)a->nNodes, cudaMemcpyDeviceToDevice, G.stream));
+        if (da->auxNodeDoubles)
+            CUDA_TRY(cudaMemcpyAsync(db->aux, da->aux, da->auxNodeDoubles * sizeof(double) * (size_t)a->nNodes, cudaMemcpyDeviceToDevice, G.stream));
         for (int i = 0; i < a->nNodes; i++)
             if (a->nodes[i] && b->nodes[i])
                 for (int p = 0; p < a->nParts; p++) b->nodes[i]->pStamp[p] = a->nodes[i]->pStamp[p];
@@ -1467,6 +1549,8 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
             CUDA_TRY(cudaMemcpyAsync(nodeP(nB, p), nodeP(nA, p), a->dev->parts[p].pDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
             if (a->dev->parts[p].tblDoubles)
                 CUDA_TRY(cudaMemcpyAsync(nodeTbl(nB, p), nodeTbl(nA, p), a->dev->parts[p].tblDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
+            if (a->dev->parts[p].auxDoubles && sameShape)
+                CUDA_TRY(cudaMemcpyAsync(nodeAux(nB, p), nodeAux(nA, p), a->dev->parts[p].auxDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
             nB->pStamp[p] = nA->pStamp[p];
         }
     }
@@ -1576,6 +1660,20 @@ int nodeSetBigP(Node *n, int p, const double *in)
             T[(size_t)k * W + w] = v;
         }
     CUDA_TRY(cudaMemcpyAsync(nodeTbl(n, p), T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    std::vector<double> A(L.auxDoubles);
+    if (L.auxDoubles) {   // the same two decks pmatrix_kernel derives from P
+        const int nF = L.nCat * kAAFrag;
+        for (int i = 0; i < nF; i++) {
+            const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 6, ct = i / 576;
+            const int s = 8 * nt + (l >> 2), x = 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1);
+            A[i] = (s < dim && x < dim) ? in[((size_t)ct * dim + s) * dim + x] : 0.0;
+        }
+        for (int i = 0; i < L.nCat * W * dim; i++) {
+            const int st = i % dim, w = (i / dim) % W, ct = i / (dim * W);
+            A[nF + i] = T[((size_t)ct * dim + st) * W + w];
+        }
+        CUDA_TRY(cudaMemcpyAsync(nodeAux(n, p), A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    }
     if (streamSync()) return 1;
     n->pStamp[p] = ++G.stamp;
     return 0;

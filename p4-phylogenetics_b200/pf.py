@@ -76,6 +76,7 @@ _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setTensorCoreKernel", None, _i)
+_sig("p4b_setFusedTreeKernel20", None, _i)
 _sig("p4b_setDeferredNodeCalls", None, _i)
 _sig("p4b_setSharedCondLikes", None, _i)
 _sig("p4b_treesPartLogLike", _i, _i, _vp, _i, _vp)
@@ -246,6 +247,10 @@ def treesPartLogLike(cTrees, pNum):
     out = np.empty(n, dtype=np.float64)
     _ok(_lib.p4b_treesPartLogLike(n, arr, int(pNum), out.ctypes.data))
     return out.tolist()
+
+
+def setFusedTreeKernel20(on):
+    _lib.p4b_setFusedTreeKernel20(int(on))
 
 
 def setTensorCoreKernel(on):

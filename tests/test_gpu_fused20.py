@@ -1,0 +1,113 @@
+"""The whole-tree 20-state kernel (cl_tree_aa_kernel: FP64 tensor cores, running CL in accumulator
+registers) against the one-launch-per-node kernels and the reference engine."""
+import numpy as np
+import pytest
+
+import ref_peek
+from util import build_pair, rel
+
+pytestmark = pytest.mark.gpu
+LNL_TOL = 1e-9
+
+
+def _cls(pf, tree, pNum=0):
+    mp = tree.model.parts[pNum]
+    return {n.nodeNum: pf.getNodeCL(tree.cTree, n.cNode, pNum, mp.nGammaCat, mp.dim) for n in tree.iterInternalsPostOrder()}
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (3, dict(nTax=17, nPatterns=1000)),      # 1000 patterns: 32 groups of 32, the last one partly padding
+    (3, dict(nTax=6, nPatterns=33)),
+    (4, dict(nTax=9, nPatterns=300)),
+])
+def test_whole_tree_kernel_equals_per_node_kernels(pkg, ref_pf, cfg, kw):
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
+    want = twin.calcLogLike()
+    n0 = pf.kernelLaunchCount()
+    got = mine.calcLogLike()
+    fusedLaunches = pf.kernelLaunchCount() - n0
+    a = [_cls(pf, mine, p) for p in range(mine.model.nParts)]
+    pf.setFusedTreeKernel20(0)
+    try:
+        n0 = pf.kernelLaunchCount()
+        got2 = mine.calcLogLike()
+        nodeLaunches = pf.kernelLaunchCount() - n0
+        b = [_cls(pf, mine, p) for p in range(mine.model.nParts)]
+    finally:
+        pf.setFusedTreeKernel20(1)
+    assert rel(got, want) <= LNL_TOL
+    assert rel(got, got2) <= 1e-12
+    assert fusedLaunches < nodeLaunches
+    for x, y in zip(a, b):
+        for k in x:
+            scale = np.max(np.abs(y[k]), axis=(0, 1), keepdims=True)
+            assert np.max(np.abs(x[k] - y[k]) / scale) < 1e-13, "CL of node %d" % k
+
+
+def test_cl_arrays_match_reference(pkg, ref_pf):
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, 3, nTax=11, nPatterns=400)
+    mine.calcLogLike()
+    twin.calcLogLike()
+    rp = ref_peek.part_arrays(twin.data.parts[0].cPart)
+    for a, b in zip(mine.nodes, twin.nodes):
+        if a.isLeaf:
+            continue
+        c1 = pf.getNodeCL(mine.cTree, a.cNode, 0, 4, 20)
+        c0 = ref_peek.node_cl(b.cNode, 0, 4, 20, rp["nChar"], rp["nPatterns"])
+        scale = np.max(np.abs(c0), axis=(0, 1), keepdims=True)
+        assert np.max(np.abs(c1 - c0) / scale) < 1e-9, "CL of node %d" % a.nodeNum
+
+
+def test_dirty_path_protein(pkg, ref_pf):
+    mine, twin = build_pair(pkg, ref_pf, 3, nTax=15, nPatterns=500)
+    mine.calcLogLike()
+    twin.calcLogLike()
+    rng = np.random.default_rng(8)
+    for _ in range(6):
+        i = int(rng.integers(1, len(mine.nodes)))
+        new = float(rng.uniform(0.001, 0.4))
+        for t in (mine, twin):
+            t.nodes[i].br.len = new
+            t.nodes[i].br.lenChanged = True
+        got = mine.recalcAfterBranchChange()
+        want = twin.recalcAfterBranchChange()
+        assert rel(got, want) <= LNL_TOL
+        assert rel(got, mine.calcLogLike()) <= 1e-12
+
+
+def test_polytomy_protein(pkg, ref_pf):
+    """A 7-way star: the root's children go through the kernel two at a time (chained steps)."""
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(5))
+    base = P.synth.random_tree(P.pf, 7, rng)
+    mp = P.synth.protein_model_part(0, rng, "lg", 4)
+    aln = P.synth.make_alignment(P.pf, base, mp, 200, rng, "protein", gap_frac=0.03, ambig_frac=0.03)
+    H = P.host
+    nodes = [H.Node(i) for i in range(8)]
+    root = nodes[0]
+    for k in range(7):
+        leaf = nodes[1 + k]
+        leaf.isLeaf, leaf.seqNum, leaf.parent = 1, k, root
+        leaf.br.len = 0.02 + 0.03 * k
+        if k:
+            nodes[k].sibling = leaf
+    root.leftChild = nodes[1]
+    tree = H.Tree(P.pf, nodes, root)
+    tree.attach(H.Data(P.pf, [aln]), H.Model(P.pf, [mp]))
+    twin = H.clone_tree(tree, ref_pf)
+    assert rel(tree.calcLogLike(), twin.calcLogLike()) <= LNL_TOL
+
+
+def test_ndch2_chain_matches_reference(pkg, ref_pf):
+    """A short MCMC on the tree-heterogeneous protein config: allCompsDir proposals re-solve the changed
+    eigensystems, topology moves shuffle which node uses which composition."""
+    def make(pf):
+        tree = pkg.synth.build_config(pf, 4, nTax=8, nPatterns=120)
+        return pkg.mcmc.Mcmc(tree, nChains=2, seed=3)
+    a = make(pkg.pf).run(40)
+    b = make(ref_pf).run(40)
+    for (ga, la), (gb, lb) in zip(a, b):
+        for x, y in zip(la, lb):
+            assert rel(x, y) <= LNL_TOL
