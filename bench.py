@@ -49,7 +49,7 @@ def log(*a):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--patterns", type=int, default=N_PATTERNS, help="override the pattern count (testing only)")
@@ -356,11 +356,25 @@ def run_b200(a):
     cl_bytes = float(bpp) * shard                         # algorithmic bytes of one evaluation on this rank
     cl_ms_avg = sum(cl_ms) / len(cl_ms)
     achieved = cl_bytes / (cl_ms_avg * 1e-3) / 1e9
-    kernel = "cl_tree_dna_kernel<4,128,3> (whole-tree CL recursion + site likelihoods, one launch)" if cl_launches == 1 \
+    ps_pad = (shard + 31) // 32 * 32
+    waves = (ps_pad / 2) / (128.0 * 3.0 * 148)      # the engine's launch-shape rule (csrc/tree.cu fusedVariant)
+    shape = "128,3" if waves >= 3.0 else ("64,6" if waves >= 1.6 else "32,12")
+    kernel = "cl_tree_dna_kernel<4,%s> (whole-tree CL recursion + site likelihoods, one launch)" % shape if cl_launches == 1 \
         else "cl_dna_kernel<4> (all %d CL launches of one evaluation)" % cl_launches
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and cl_launches == 1:
+        for e in json.load(open(tpath))["entries"]:
+            if e["taxa"] == a.taxa and e["patterns_per_gpu"] == shard:
+                traffic = e["dram_bytes_read"] + e["dram_bytes_write"]
+                traffic_src = e["source"]
     roofline = {"bound": "hbm", "kernel": kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": None, "algorithmic_bytes_per_pattern": bpp, "launches_per_eval": cl_launches,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_GBps": (traffic / (cl_ms_avg * 1e-3) / 1e9) if traffic else None,
+                "note": "achieved counts ALGORITHMIC bytes (SURVEY.md 8d); the kernel keeps a third of the child reads in registers "
+                        "and most of the rest in L2, so DRAM traffic is about 0.55x the algorithmic bytes and frac exceeds 1",
+                "algorithmic_bytes_per_pattern": bpp, "launches_per_eval": cl_launches,
                 "avg_launch_us": 1e3 * cl_ms_avg / max(cl_launches, 1), "cl_ms_per_eval": cl_ms_avg}
 
     cpu = None
