@@ -37,13 +37,33 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+def hot_path():
+    import sysconfig
+    return os.path.join(HERE, "_pfhot" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_hot(force=False, verbose=False):
+    """_pfhot: CPython METH_FASTCALL bindings of the per-node calls (csrc/pfhot.c), linked against libp4b200.so."""
+    import sysconfig
+    out, src = hot_path(), os.path.join(CSRC, "pfhot.c")
+    deps = [src, LIB, os.path.join(HERE, "..", "include", "p4b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-Wall", "-I" + sysconfig.get_paths()["include"],
+           "-o", out, src, "-L" + HERE, "-l:libp4b200.so", "-Wl,-rpath,$ORIGIN"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
+    return out
+
+
+def build(force=False, verbose=False, extra=()):
+    if force or needs_build():
+        cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    build_hot(force=force, verbose=verbose)
     return LIB
 
 
