@@ -84,21 +84,79 @@ def algorithmic_bytes_per_pattern(tree):
 # clocks
 # ------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML thread every 5 ms (the timed region of a
+    sharded run is well under the 100 ms floor of an `nvidia-smi -lms` loop); nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.stopFlag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                pass
+        return index
+
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self.stopFlag:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stopFlag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 5 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -122,7 +180,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------------------

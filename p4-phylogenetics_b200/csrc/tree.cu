@@ -870,7 +870,7 @@ static int fusedVariant(int ps, int nTrees)
     if (forced == -2) {
         const char *e = getenv("P4B_FUSED_VARIANT");
         forced = e ? atoi(e) : -1;
-        if (forced < -1 || forced > 4) forced = -1;
+        if (forced < -1 || forced > 6) forced = -1;
     }
     if (forced >= 0) return forced;
     const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
@@ -986,7 +986,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.eqMask = dp->dev.equateMask;
     const bool aa = L.dim == 20;      // tensor-core kernel: root reduction is a separate kernel
     const int variant = aa ? 0 : fusedVariant(L.ps, nJobs);
-    static const int kThreads[5] = {128, 64, 32, 128, 256};
+    static const int kThreads[7] = {128, 64, 32, 128, 256, 64, 32};
     static int aaGroups = -1, aaMinB = 1, aaMT = 2;   // 20-state kernel: pattern groups per CTA, CTAs per SM, m-tiles per warp
     if (aaGroups < 0) {
         const char *e = getenv("P4B_AA_GROUPS");
@@ -1062,12 +1062,14 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
          {cl_tree_aa_kernel<4, 2, 1, 4>, cl_tree_aa_kernel<4, 2, 2, 4>, nullptr},
          {cl_tree_aa_kernel<4, 3, 1, 4>, nullptr, nullptr},
          {cl_tree_aa_kernel<4, 4, 1, 4>, nullptr, nullptr}}};
-    static const KernelFn kFn4[5] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
+    static const KernelFn kFn4[7] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
                                      cl_tree_dna_kernel<4, 32, 12, false>, cl_tree_dna_kernel<4, 128, 4, false>,
-                                     cl_tree_dna_kernel<4, 256, 2, false>};
-    static const KernelFn kFn1[5] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 64, 8, false>,
+                                     cl_tree_dna_kernel<4, 256, 2, false>, cl_tree_dna_kernel<4, 64, 8, false>,
+                                     cl_tree_dna_kernel<4, 32, 16, false>};
+    static const KernelFn kFn1[7] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 64, 8, false>,
                                      cl_tree_dna_kernel<1, 32, 16, false>, cl_tree_dna_kernel<1, 128, 4, false>,
-                                     cl_tree_dna_kernel<1, 256, 2, false>};
+                                     cl_tree_dna_kernel<1, 256, 2, false>, cl_tree_dna_kernel<1, 64, 8, false>,
+                                     cl_tree_dna_kernel<1, 32, 16, false>};
     static const KernelFn kFn4s[3] = {cl_tree_dna_kernel<4, 128, 3, true>, cl_tree_dna_kernel<4, 64, 6, true>,
                                       cl_tree_dna_kernel<4, 32, 12, true>};
     static const KernelFn kFn1s[3] = {cl_tree_dna_kernel<1, 128, 4, true>, cl_tree_dna_kernel<1, 64, 8, true>,
@@ -1084,7 +1086,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
             for (int v = 0; v < 4; v++)
                 for (int m = 0; m < 3; m++)
                     if (kFnAA[t][v][m]) CUDA_TRY(cudaFuncSetAttribute(kFnAA[t][v][m], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        for (int v = 0; v < 5; v++) {
+        for (int v = 0; v < 7; v++) {
             CUDA_TRY(cudaFuncSetAttribute(kFn4[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(kFn1[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         }
