@@ -395,6 +395,18 @@ def run_b200(a):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 1000.0 * a.steps / float(te.item())
+    # ---- host-side pieces of one Tree.calcLogLike(), timed separately (SURVEY.md 8d timers i-iii) --------
+    def avg_ms(fn, n=20):
+        pf.treeSync(tree.cTree)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        pf.treeSync(tree.cTree)
+        return (time.perf_counter() - t0) * 1e3 / n
+    host_ms = {"Tree.setCStuff (4 pf calls per node)": avg_ms(tree.setCStuff),
+               "Model.setCStuff": avg_ms(tree.model.setCStuff),
+               "pf.p4_setPrams (host Q/eigen/gamma + P(t) kernel)": avg_ms(lambda: pf.p4_setPrams(tree.cTree, -1)),
+               "fast_bindings": bool(getattr(pf, "_hot", None))}
     n_nonroot = len(tree.nodes) - 1
     h2d = n_nonroot * (56 + 8 * 4) + (2 * 16 + 4) * 8      # P jobs + effective branch lengths + one eigensystem
     d2h = 16
@@ -450,7 +462,7 @@ def run_b200(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "patterns_per_gpu": shard, "internal_nodes": n_internal,
+        "config": {"workload": workload_name(a), "patterns_per_gpu": shard, "internal_nodes": n_internal, "setup_s": round(t_setup, 1),
                    "l2": "inputs larger than L2 (CL working set %.1f GB per GPU)" % (pf.treeDeviceBytes(tree.cTree) / 1e9),
                    "timing": "CUDA events on the engine stream, max over ranks"},
         "pattern_updates_per_s": value * n_internal * nPat,
@@ -458,7 +470,8 @@ def run_b200(a):
         "lnl_only": {"value": lean_value, "unit": UNIT, "lnL": lnL_lean,
                      "note": "opt-in p4b_setTreeStoresCL(0): only the CLs the evaluation re-reads are written; not the headline"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "Tree.calcLogLike(): model.setCStuff + tree.setCStuff + pf.p4_setPrams + pf.p4_treeLogLike", "lnL": lnL_e2e},
+                "call": "Tree.calcLogLike(): model.setCStuff + tree.setCStuff + pf.p4_setPrams + pf.p4_treeLogLike", "lnL": lnL_e2e,
+                "host_ms": host_ms},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

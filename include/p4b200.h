@@ -217,6 +217,13 @@ int p4b_countParameters(p4b_tree t, int doBrLens);
 int p4b_windUpParameters(p4b_tree t, int doBrLens, double *x, double *lowerBounds, double *upperBounds);
 int p4b_unWindParameters(p4b_tree t, int doBrLens, const double *x);
 double p4b_logLikeForParameters(p4b_tree t, int doBrLens, const double *x);   /* p4_logLikeForNLOpt :579 */
+/* Branch lengths one at a time through the dirty path (the role of Newton-Raphson in the reference's
+ * p4_newtAndBrentPowellOpt / p4_newtAndBOBYQAOpt, Pf/p4_treeOpt.c:755-945): each branch is maximised by
+ * Brent's bounded method, every evaluation being one P(t) launch + one step-list launch from the branch's
+ * parent to the root.  maxPasses passes over all branches or until a pass gains less than tol.  Returns
+ * the final log-likelihood (NaN on error); *nEvals receives the number of likelihood evaluations. */
+double p4b_optimizeBrLens(p4b_tree t, int maxPasses, double tol, long *nEvals);
+int p4b_treePassLimit(p4b_tree t);   /* var.newtAndBrentPowellOptPassLimit as given to p4_newTree */
 int p4b_treeNNodes(p4b_tree t);
 int p4b_getBrLens(p4b_tree t, double *outNNodes);                            /* pf.p4_getBrLens :2279; root slot = -1 */
 

@@ -346,7 +346,11 @@ void p4b_freeTree(p4b_tree t)
     Tree *T = (Tree *)t;
     if (!T) return;
     treeDeviceDestroy(T);
-    delete T;   // nodes are freed one by one through p4_freeNode, before the tree (p4/tree.py:9202-9253)
+    // nodes are freed one by one through p4_freeNode, before the tree (p4/tree.py:9202-9253); one freed
+    // later must not reach back into this tree
+    for (Node *n : T->nodes)
+        if (n) n->tree = nullptr;
+    delete T;
 }
 
 p4b_node p4b_newNode(int nodeNum, p4b_tree t, int seqNum, int isLeaf, int inTree)

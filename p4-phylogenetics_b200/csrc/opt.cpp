@@ -14,6 +14,7 @@
 // value is clamped, so the objective is a deterministic function of the vector.
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "../../include/p4b200.h"
 #include "engine.h"
@@ -149,6 +150,120 @@ int unWindParameters(Tree *t, int doBrLens, const double *x)
     return pos;
 }
 
+// ---------------------------------------------------------------------------
+// Branch lengths, one at a time, through the dirty path.
+//
+// The reference's newtAnd* optimisers (Pf/p4_treeOpt.c:755-945, Pf/p4_treeNewt.c) go around the tree
+// optimising one branch length at a time (Newton-Raphson on partials kept for both directions of every
+// branch) and hand the model parameters to Brent-Powell or BOBYQA.  Here each one-branch objective is
+// what Chain.proposeSp evaluates after a branch-length proposal: the branch's P(t), the conditional
+// likelihoods from its parent to the root, the part log-likelihoods -- one P(t) launch and one
+// step-list launch per evaluation (tree.cu, queued calls), maximised by Brent's bounded method.
+// ---------------------------------------------------------------------------
+static double evalBranch(Tree *t, Node *n, double len, long *nEvals)
+{
+    n->brLen = len;
+    if (nodeCalculateBigPDecks(n)) return NAN;
+    for (Node *q = n->parent; q; q = q->parent)
+        for (int p = 0; p < t->nParts; p++)
+            if (nodeSetCL(q, p)) return NAN;
+    double sum = 0.0;
+    for (int p = 0; p < t->nParts; p++) {
+        const double v = treePartLogLike(t, nullptr, p, 0);
+        if (v != v) return NAN;
+        sum += v;
+    }
+    if (nEvals) (*nEvals)++;
+    return sum;
+}
+
+// Brent's bounded minimiser (golden section + successive parabolic interpolation) of f on [a, b],
+// written for maximising the log-likelihood in u = log(branch length).
+template <class F>
+static double brentMax(F f, double a, double b, double x0, double f0, double tolU, int maxIter, double *fBest, bool *failed)
+{
+    const double golden = 0.3819660112501051;
+    double x = x0, w = x0, v = x0;
+    double fx = -f0, fw = fx, fv = fx;     // minimise -lnL
+    double d = 0.0, e = 0.0;
+    for (int it = 0; it < maxIter; it++) {
+        const double xm = 0.5 * (a + b);
+        const double tol1 = tolU * fabs(x) + 1e-10, tol2 = 2.0 * tol1;
+        if (fabs(x - xm) <= tol2 - 0.5 * (b - a)) break;
+        bool useGolden = true;
+        if (fabs(e) > tol1) {
+            double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), p = (x - v) * q - (x - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) p = -p;
+            q = fabs(q);
+            const double eOld = e;
+            e = d;
+            if (!(fabs(p) >= fabs(0.5 * q * eOld) || p <= q * (a - x) || p >= q * (b - x))) {
+                d = p / q;
+                const double u = x + d;
+                if (u - a < tol2 || b - u < tol2) d = xm >= x ? tol1 : -tol1;
+                useGolden = false;
+            }
+        }
+        if (useGolden) {
+            e = (x >= xm) ? a - x : b - x;
+            d = golden * e;
+        }
+        const double u = fabs(d) >= tol1 ? x + d : x + (d >= 0 ? tol1 : -tol1);
+        const double fuRaw = f(u);
+        if (fuRaw != fuRaw) { *failed = true; break; }
+        const double fu = -fuRaw;
+        if (fu <= fx) {
+            if (u >= x) a = x; else b = x;
+            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+        } else {
+            if (u < x) a = u; else b = u;
+            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+        }
+    }
+    *fBest = -fx;
+    return x;
+}
+
+// One or more passes over all branches.  Returns the final log-likelihood (NAN on error).
+double optimizeBrLens(Tree *t, int maxPasses, double tol, long *nEvals)
+{
+    Model *m = t->model;
+    const double lo = m->BRLEN_MIN[0], hi = m->BRLEN_MAX[0];
+    if (treeSetPrams(t, -1)) return NAN;
+    double cur = treeLogLike(t, 0);
+    if (cur != cur) return NAN;
+    if (nEvals) (*nEvals)++;
+    std::vector<Node *> order;       // leaves first, root-most branches last: post-order
+    for (int j = 0; j < t->nNodes; j++) {
+        const int i = t->postOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        Node *n = t->nodes[i];
+        if (n && n != t->root) order.push_back(n);
+    }
+    for (int pass = 0; pass < maxPasses; pass++) {
+        const double atStart = cur;
+        for (Node *n : order) {
+            const double t0 = n->brLen < lo ? lo : (n->brLen > hi ? hi : n->brLen);
+            // search a decade either side of the current length (the next pass moves the window)
+            const double a = log(t0 / 10.0 > lo ? t0 / 10.0 : lo), b = log(t0 * 10.0 < hi ? t0 * 10.0 : hi);
+            double fBest = cur;
+            bool failed = false;
+            const double u = brentMax([&](double uu) { return evalBranch(t, n, exp(uu), nEvals); }, a, b, log(t0), cur, 1e-4, 40, &fBest, &failed);
+            if (failed) return NAN;
+            // leave the tree in the best state found (the last point evaluated need not be it)
+            const double best = fBest >= cur ? exp(u) : t0;
+            const double v = evalBranch(t, n, best, nEvals);
+            if (v != v) return NAN;
+            cur = v;
+        }
+        if (cur - atStart < tol) break;
+    }
+    t->logLike = cur;
+    return cur;
+}
+
 }  // namespace p4b
 
 using namespace p4b;
@@ -177,6 +292,17 @@ double p4b_logLikeForParameters(p4b_tree t, int doBrLens, const double *x)
     unWindParameters(T, doBrLens, x);
     if (treeSetPrams(T, -1)) return NAN;
     return treeLogLike(T, 0);
+}
+double p4b_optimizeBrLens(p4b_tree t, int maxPasses, double tol, long *nEvals)
+{
+    if (!t) { setError("p4b_optimizeBrLens: NULL handle"); return NAN; }
+    if (nEvals) *nEvals = 0;
+    return optimizeBrLens((Tree *)t, maxPasses < 1 ? 1 : maxPasses, tol, nEvals);
+}
+int p4b_treePassLimit(p4b_tree t)
+{
+    Tree *T = (Tree *)t;
+    return (T && T->passLimit) ? T->passLimit[0] : 50;
 }
 int p4b_treeNNodes(p4b_tree t) { return t ? ((Tree *)t)->nNodes : -1; }
 int p4b_getBrLens(p4b_tree t, double *out)

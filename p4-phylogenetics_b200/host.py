@@ -456,8 +456,14 @@ class Tree:
             pf.p4_allBOBYQAOptimize(self.cTree, 1 if optBrLens else 0)
         elif method == "allBrentPowell":
             pf.p4_allBrentPowellOptimize(self.cTree)
+        elif method == "newtAndBrentPowell":
+            pf.p4_newtSetup(self.cTree)
+            pf.p4_newtAndBrentPowellOpt(self.cTree)
+        elif method == "newtAndBOBYQA":
+            pf.p4_newtSetup(self.cTree)
+            pf.p4_newtAndBOBYQAOpt(self.cTree)
         else:
-            raise ValueError('method should be "BOBYQA" or "allBrentPowell"')
+            raise ValueError('method should be one of "newtAndBrentPowell", "allBrentPowell", "newtAndBOBYQA", or "BOBYQA"')
         self.logLike = pf.p4_treeLogLike(self.cTree, 0)
         brLens = pf.p4_getBrLens(self.cTree)
         for n in self.iterNodesNoRoot():

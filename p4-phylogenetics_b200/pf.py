@@ -139,6 +139,8 @@ _sig("p4b_windUpParameters", _i, _vp, _i, _vp, _vp, _vp)
 _sig("p4b_unWindParameters", _i, _vp, _i, _vp)
 _sig("p4b_logLikeForParameters", _d, _vp, _i, _vp)
 _sig("p4b_getBrLens", _i, _vp, _vp)
+_sig("p4b_optimizeBrLens", _d, _vp, _i, _d, C.POINTER(C.c_long))
+_sig("p4b_treePassLimit", _i, _vp)
 _sig("p4b_treeNNodes", _i, _vp)
 _sig("p4b_copyCondLikes", _i, _vp, _vp, _i)
 _sig("p4b_copyBigPDecks", _i, _vp, _vp, _i)
@@ -582,6 +584,48 @@ def p4_allBOBYQAOptimize(cTree, doBrLens=1, verbose=0, maxEvals=None, ftol=1e-8)
 
 
 p4_allBrentPowellOptimize = p4_allBOBYQAOptimize
+
+
+def optimizeBrLens(cTree, maxPasses=1, tol=1e-6):
+    """All branch lengths, one at a time, each through the dirty path (include/p4b200.h p4b_optimizeBrLens).
+    Returns (lnL, number of likelihood evaluations)."""
+    n = C.c_long(0)
+    v = _lib.p4b_optimizeBrLens(cTree, int(maxPasses), float(tol), C.byref(n))
+    if v != v:
+        _fatal()
+    return v, n.value
+
+
+def p4_newtSetup(cTree):
+    """pf.p4_newtSetup(cTree): the reference allocates the work arrays of its Newton-Raphson branch-length
+    step here (Pf/p4_treeNewt.c:11-77); this engine's one-branch objective needs none."""
+    if not cTree:
+        _fatal()
+
+
+def p4_newtAndBrentPowellOpt(cTree, verbose=0):
+    """pf.p4_newtAndBrentPowellOpt(cTree) (Pf/p4_treeOpt.c:755-836): alternate between the branch lengths --
+    one at a time, the reference by Newton-Raphson, here by Brent's method on the dirty-path objective --
+    and the free model parameters (the reference's parameter vector, bounded Powell), until a round gains
+    less than 1e-6 or var.newtAndBrentPowellOptPassLimit rounds have run."""
+    limit = max(1, _lib.p4b_treePassLimit(cTree))
+    last = None
+    nEvals = 0
+    for rnd in range(limit):
+        lnL, n = optimizeBrLens(cTree, maxPasses=2, tol=1e-6)
+        nEvals += n
+        if len(windUpParameters(cTree, 0)[0]):
+            nEvals += p4_allBOBYQAOptimize(cTree, 0, ftol=1e-9)
+            lnL = p4_treeLogLike(cTree, 0)
+        if verbose:
+            print("p4_newtAndBrentPowellOpt round %d: lnL %.6f (%d evaluations so far)" % (rnd, lnL, nEvals))
+        if last is not None and lnL - last < 1.0e-6:
+            break
+        last = lnL
+    return nEvals
+
+
+p4_newtAndBOBYQAOpt = p4_newtAndBrentPowellOpt
 
 
 # ---- cur/prop state transfer ------------------------------------------------------------

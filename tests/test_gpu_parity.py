@@ -293,3 +293,74 @@ def test_lnl_only_mode_is_transparent(pkg, ref_pf):
             t.nodes[i].br.lenChanged = True
         assert rel(mine.recalcAfterBranchChange(), want) <= LNL_TOL
         mine.calcLogLike()
+
+
+def test_tree_heterogeneous_dna_ndch_ndrh(pkg, ref_pf):
+    """Composition, rate matrix AND gamma shape vary over the tree (NDCH + NDRH, p4/model.py isHet): every node
+    draws its own (comp, rMatrix, gdasrv) numbers; two data parts with different relative rates."""
+    P, H = pkg, pkg.host
+    rng = np.random.Generator(np.random.PCG64(99))
+    tree = P.synth.random_tree(P.pf, 13, rng)
+    mps, alns = [], []
+    for pNum in range(2):
+        mp = H.ModelPart(pNum, 4, 4)
+        for _ in range(3):
+            mp.comps.append(H.Comp(P.synth.normalise_comp(rng.dirichlet(8.0 * np.ones(4))), free=1))
+        for _ in range(2):
+            r = rng.dirichlet(4.0 * np.ones(6))
+            mp.rMatrices.append(H.RMatrix("specified", r / r.sum(), free=1))
+        for a in (0.3, 1.7):
+            mp.gdasrvs.append(H.Gdasrv(4, a, free=1))
+        mp.pInvar = H.PInvar(0.1 if pNum == 0 else 0.0)
+        mp.relRate = 0.7 if pNum == 0 else 1.4
+        mp.isHet = 1
+        mps.append(mp)
+        sim = P.synth.dna_model_part(0, rng, 4)
+        alns.append(P.synth.make_alignment(P.pf, tree, sim, 300 + 100 * pNum, rng, "dna", gap_frac=0.02, ambig_frac=0.02))
+    model = H.Model(P.pf, mps)
+    model.doRelRates = 1
+    tree.attach(H.Data(P.pf, alns), model)
+    for n in tree.nodes:
+        for pNum in range(2):
+            n.parts[pNum].compNum = int(rng.integers(3))
+            n.br.parts[pNum].rMatrixNum = int(rng.integers(2))
+            n.br.parts[pNum].gdasrvNum = int(rng.integers(2))
+    twin = H.clone_tree(tree, ref_pf)
+    got, want = tree.calcLogLike(), twin.calcLogLike()
+    assert rel(got, want) <= LNL_TOL
+    for g, w in zip(tree.partLikes, twin.partLikes):
+        assert rel(g, w) <= LNL_TOL
+    _check_arrays(pkg, tree, twin)
+    # a dirty path through the heterogeneous model
+    for t in (tree, twin):
+        t.nodes[4].br.len *= 3.0
+        t.nodes[4].br.lenChanged = True
+    assert rel(tree.recalcAfterBranchChange(), twin.recalcAfterBranchChange()) <= LNL_TOL
+
+
+def test_61_state_data_generic_kernel(pkg, ref_pf):
+    """north_star names 61-state codon data; the reference has no codon model, so such data are a 'standard'
+    datatype with 61 symbols: the any-dim path (SURVEY.md section 2 note)."""
+    P, H = pkg, pkg.host
+    rng = np.random.Generator(np.random.PCG64(61))
+    symbols = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ012345678"
+    assert len(symbols) == 61
+    tree = P.synth.random_tree(P.pf, 7, rng)
+    lut = np.frombuffer(symbols.encode(), dtype=np.uint8)
+    base = rng.integers(61, size=150)
+    seqs = []
+    for _ in range(7):
+        s = base.copy()
+        m = rng.random(150) < 0.4
+        s[m] = rng.integers(61, size=int(m.sum()))
+        chars = lut[s].copy()
+        chars[rng.random(150) < 0.03] = ord("-")
+        seqs.append(chars.tobytes())
+    aln = H.Alignment(P.pf, seqs, symbols, {})
+    mp = H.ModelPart(0, 61, 2)
+    mp.comps.append(H.Comp(P.synth.normalise_comp(rng.dirichlet(20.0 * np.ones(61)))))
+    mp.rMatrices.append(H.RMatrix("ones"))
+    mp.gdasrvs.append(H.Gdasrv(2, 0.8))
+    tree.attach(H.Data(P.pf, [aln]), H.Model(P.pf, [mp]))
+    twin = H.clone_tree(tree, ref_pf)
+    assert rel(tree.calcLogLike(), twin.calcLogLike()) <= LNL_TOL
