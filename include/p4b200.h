@@ -234,6 +234,11 @@ int p4b_getBrLens(p4b_tree t, double *outNNodes);                            /* 
  * ONE kernel launch (grid.y = tree), one fold, one all-reduce, one device->host copy.  Otherwise it
  * is a loop over p4b_partLogLike.  out[i] and each tree's partLikes[pNum] receive the values. */
 int p4b_treesPartLogLike(int nTrees, const p4b_tree *trees, int pNum, double *out);
+/* Start the evaluation p4b_partLogLike(t, pNum) would do -- queued P(t) jobs, queued CL calls, root
+ * reduction -- and return without waiting.  The value is collected by the next p4b_partLogLike(t, pNum) or
+ * p4b_treesPartLogLike including t (one copy and one synchronisation for all trees).  The host can prepare
+ * the next chain's proposal while the GPU evaluates this one. */
+int p4b_partLogLikeBegin(p4b_tree t, int pNum);
 
 /* ---- cur/prop state transfer ------------------------ Pf/p4_treeCopyVerify.c -- */
 int p4b_copyCondLikes(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyCondLikes :2445, Pf/p4_treeCopyVerify.c:7 */

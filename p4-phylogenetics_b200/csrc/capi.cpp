@@ -482,6 +482,11 @@ double p4b_treeLogLike(p4b_tree t, int getSiteLikes)
     return treeLogLike((Tree *)t, getSiteLikes);
 }
 
+int p4b_partLogLikeBegin(p4b_tree t, int pNum)
+{
+    CHECK_PTR(t, "p4b_partLogLikeBegin", 1);
+    return treePartLogLikeBegin((Tree *)t, pNum);
+}
 int p4b_treesPartLogLike(int nTrees, const p4b_tree *trees, int pNum, double *out)
 {
     if (nTrees < 0 || (nTrees > 0 && (!trees || !out))) { setError("p4b_treesPartLogLike: bad arguments"); return 1; }

@@ -186,6 +186,7 @@ void setDeferEnabled(int on);
 void setShareEnabled(int on);
 void setFusedAAEnabled(int on);
 int treesPartLogLike(Tree **trees, int n, int p, double *out);
+int treePartLogLikeBegin(Tree *t, int p);
 
 // comm.cpp -- NCCL, loaded at run time
 int commGetUniqueId(char id128[128]);

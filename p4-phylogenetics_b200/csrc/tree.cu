@@ -270,6 +270,8 @@ struct TreeDevice {
     // here (per part, in call order) and run as ONE step-list launch when something needs their result --
     // normally p4_partLogLike, which then also gets the root reduction fused in.
     std::vector<std::vector<Node *>> pending;
+    std::vector<char> likeBegun;   // per part: p4b_partLogLikeBegin has launched the evaluation; result not fetched yet
+    std::vector<cudaEvent_t> evLike;   // per part: recorded after the begun evaluation's device->host copy
     bool scalers = false;
     size_t pNodeDoubles = 0, tblNodeDoubles = 0, auxNodeDoubles = 0;
     double *P = nullptr, *tbl = nullptr, *eig = nullptr, *aux = nullptr;
@@ -297,6 +299,8 @@ int treeDeviceCreate(Tree *t)
     d->scalers = g_useScalers;
     d->parts.resize(t->nParts);
     d->pending.resize(t->nParts);
+    d->likeBegun.assign(t->nParts, 0);
+    d->evLike.assign(t->nParts, nullptr);
     size_t eigTotal = 0, eqTotal = 0;
     const int nInternalSlots = t->nNodes - t->nLeaves + 1;   // +1: a root that is a leaf (Pf/p4_node.c:608-626)
     for (int p = 0; p < t->nParts; p++) {
@@ -406,6 +410,8 @@ void treeDeviceDestroy(Tree *t)
     if (d->evB) cudaEventDestroy(d->evB);
     if (d->evCLa) cudaEventDestroy(d->evCLa);
     if (d->evCLb) cudaEventDestroy(d->evCLb);
+    for (cudaEvent_t e : d->evLike)
+        if (e) cudaEventDestroy(e);
     delete d;
     t->dev = nullptr;
 }
@@ -1296,26 +1302,72 @@ static int fillSiteLikes(Tree *t, int p)
     return 0;
 }
 
+// Launch everything the log-likelihood of part p needs, results into d->result[2p..2p+1]; no synchronisation.
+static int launchPartLike(Tree *t, int p, int getSiteLikes)
+{
+    std::vector<Node *> &q = t->dev->pending[p];
+    if (!q.empty() && q.back() == t->root && fusedEligible(t->dev->parts[p])) {
+        // the usual end of a proposal: the queued dirty path ends at the root, so the path and the
+        // root reduction are one launch
+        if (residentPass(t, p)) return 1;
+        std::vector<Node *> order;
+        order.swap(q);
+        return launchFusedTree(t, p, order, true, getSiteLikes != 0, true);
+    }
+    return enqueuePartLike(t, p, getSiteLikes != 0);
+}
+
+// Wait for an evaluation started by p4b_partLogLikeBegin (its result is already on its way to the pinned
+// host buffer) -- on its own event, not on the stream, so work queued behind it keeps running.
+static int collectBegun(Tree *t, int p, double *lnL)
+{
+    TreeDevice *d = t->dev;
+    CUDA_TRY(cudaEventSynchronize(d->evLike[p]));
+    d->likeBegun[p] = 0;
+    double v = d->hResult[2 * p];
+    if (d->hResult[2 * p + 1] > 0.0) v = P4B_BAD_LIKE;
+    t->partLikes[p] = v;
+    *lnL = v;
+    return 0;
+}
+
 double treePartLogLike(Tree *t, Part *dpArg, int p, int getSiteLikes)
 {
     if (!t->dev) { setError("tree has no device state"); return NAN; }
     if (p < 0 || p >= t->nParts) { setError("p4_partLogLike: bad part %d", p); return NAN; }
     (void)dpArg;   // the reference passes the part explicitly; it is data->parts[pNum]
-    std::vector<Node *> &q = t->dev->pending[p];
-    if (!q.empty() && q.back() == t->root && fusedEligible(t->dev->parts[p])) {
-        // the usual end of a proposal: the queued dirty path ends at the root, so the path and the
-        // root reduction are one launch
-        if (residentPass(t, p)) return NAN;
-        std::vector<Node *> order;
-        order.swap(q);
-        if (launchFusedTree(t, p, order, true, getSiteLikes != 0, true)) return NAN;
-    } else if (enqueuePartLike(t, p, getSiteLikes != 0)) return NAN;
+    if (t->dev->likeBegun[p] && !getSiteLikes && t->dev->pending[p].empty()) {
+        double v = NAN;
+        if (collectBegun(t, p, &v)) return NAN;
+        return v;
+    }
+    t->dev->likeBegun[p] = 0;
+    if (launchPartLike(t, p, getSiteLikes)) return NAN;
     if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
     if (fetchResults(t, p, p + 1)) return NAN;
     double lnL = t->dev->hResult[2 * p];
     if (t->dev->hResult[2 * p + 1] > 0.0) lnL = P4B_BAD_LIKE;
     t->partLikes[p] = lnL;
     return lnL;
+}
+
+// p4b_partLogLikeBegin: start the evaluation of part p (queued P(t) jobs, queued CL calls, root reduction,
+// all-reduce, device->host copy) and return at once; the value is collected by p4b_partLogLike /
+// p4b_treesPartLogLike, which wait on this evaluation's own event.  Lets the host prepare the next chain's
+// proposal, and finish the previous chain's generation, while the GPU evaluates this one.
+int treePartLogLikeBegin(Tree *t, int p)
+{
+    if (!t->dev) { setError("tree has no device state"); return 1; }
+    if (p < 0 || p >= t->nParts) { setError("p4b_partLogLikeBegin: bad part %d", p); return 1; }
+    TreeDevice *d = t->dev;
+    if (launchPartLike(t, p, 0)) return 1;
+    if (commActive())
+        if (commAllReduceSum(d->result + 2 * p, 2, (void *)G.stream)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(d->hResult + 2 * p, d->result + 2 * p, 2 * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    if (!d->evLike[p]) CUDA_TRY(cudaEventCreateWithFlags(&d->evLike[p], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(d->evLike[p], G.stream));
+    d->likeBegun[p] = 1;
+    return 0;
 }
 
 double treeLogLike(Tree *t, int getSiteLikes)
@@ -1372,12 +1424,25 @@ double treeLogLike(Tree *t, int getSiteLikes)
 int treesPartLogLike(Tree **trees, int n, int p, double *out)
 {
     if (n <= 0) return 0;
+    {   // evaluations already started by p4b_partLogLikeBegin: their results are on the way, wait for each
+        bool allBegun = n <= kMaxBatchTrees;
+        for (int i = 0; i < n && allBegun; i++) {
+            Tree *t = trees[i];
+            if (!t || !t->dev || p < 0 || p >= t->nParts) { setError("p4b_treesPartLogLike: bad tree or part"); return 1; }
+            if (!t->dev->likeBegun[p] || !t->dev->pending[p].empty()) allBegun = false;
+        }
+        if (allBegun) {
+            for (int i = 0; i < n; i++)
+                if (collectBegun(trees[i], p, &out[i])) return 1;
+            return 0;
+        }
+    }
     bool batchable = true;
     for (int i = 0; i < n && batchable; i++) {
         Tree *t = trees[i];
         if (!t || !t->dev || p < 0 || p >= t->nParts) { setError("p4b_treesPartLogLike: bad tree or part"); return 1; }
         const std::vector<Node *> &q = t->dev->pending[p];
-        if (q.empty() || q.back() != t->root || !fusedEligible(t->dev->parts[p]) || t->data->parts[p] != trees[0]->data->parts[p]) batchable = false;
+        if (q.empty() || q.back() != t->root || !fusedEligible(t->dev->parts[p]) || t->data->parts[p] != trees[0]->data->parts[p] || t->dev->likeBegun[p]) batchable = false;
         for (int j = 0; j < i && batchable; j++)
             if (trees[j] == t) batchable = false;
     }

@@ -471,22 +471,37 @@ class Mcmc:
 
     def run(self, nGens, batched=None):
         """``batched``: issue all chains' proposals, then read every prop-tree log-likelihood with one
-        ``pf.treesPartLogLike`` per part.  Default: on when the engine offers it and nChains > 1.  The
-        random stream is consumed in the same order either way, so both modes give the same chain."""
+        ``pf.treesPartLogLike`` per part (one launch for all chains).  ``batched="pipelined"``: as soon as a
+        chain's proposal is issued its evaluation is started with ``pf.partLogLikeBegin`` -- the GPU works on it
+        while the host prepares the next chain -- and the values are collected chain by chain, each wait on that
+        evaluation's own event.  Default: pipelined when
+        the engine offers it.  The random stream is consumed in the same order in every mode, so
+        all modes give the same chain."""
         pf = self.pf
         if batched is None:
-            batched = self.nChains > 1 and hasattr(pf, "treesPartLogLike")
+            batched = "pipelined" if hasattr(pf, "partLogLikeBegin") else hasattr(pf, "treesPartLogLike")
+        pipelined = batched == "pipelined"     # each chain's evaluation starts as soon as its proposal is issued
         for _ in range(nGens):
             chosen = [self._choose() for _ in self.chains]
             if batched:
                 for ch, p in zip(self.chains, chosen):
                     ch.proposeSp(p)
-                parts = sorted(set(q for ch in self.chains for q in ch.parts_to_read))
-                for pNum in parts:
-                    who = [ch for ch in self.chains if pNum in ch.parts_to_read]
-                    pf.treesPartLogLike([ch.propTree.cTree for ch in who], pNum)
-                for ch, p in zip(self.chains, chosen):
-                    ch.finish(p)
+                    if pipelined:
+                        for pNum in ch.parts_to_read:
+                            pf.partLogLikeBegin(ch.propTree.cTree, pNum)
+                if pipelined:
+                    # collect chain by chain: each wait is on that chain's own event, so a chain's accept / reject
+                    # and cur/prop transfer run on the host while the GPU is still evaluating the later chains
+                    for ch, p in zip(self.chains, chosen):
+                        ch.readLikes()
+                        ch.finish(p)
+                else:
+                    parts = sorted(set(q for ch in self.chains for q in ch.parts_to_read))
+                    for pNum in parts:
+                        who = [ch for ch in self.chains if pNum in ch.parts_to_read]
+                        pf.treesPartLogLike([ch.propTree.cTree for ch in who], pNum)
+                    for ch, p in zip(self.chains, chosen):
+                        ch.finish(p)
             else:
                 # the reference's order: a chain finishes its generation before the next one starts;
                 # the accept draws are taken after all proposals in batched mode, so draw them in the

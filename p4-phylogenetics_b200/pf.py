@@ -80,6 +80,7 @@ _sig("p4b_setFusedTreeKernel20", None, _i)
 _sig("p4b_setDeferredNodeCalls", None, _i)
 _sig("p4b_setSharedCondLikes", None, _i)
 _sig("p4b_treesPartLogLike", _i, _i, _vp, _i, _vp)
+_sig("p4b_partLogLikeBegin", _i, _vp, _i)
 _sig("p4b_setScalers", None, _i)
 _sig("p4b_newData", _vp, _i, _i)
 _sig("p4b_freeData", None, _vp)
@@ -240,6 +241,11 @@ def setDeferredNodeCalls(on):
 def setSharedCondLikes(on):
     """0: p4_copyCondLikes really copies instead of sharing buffers between twin trees (see include/p4b200.h)."""
     _lib.p4b_setSharedCondLikes(int(on))
+
+
+def partLogLikeBegin(cTree, pNum):
+    """Start p4_partLogLike(cTree, ., pNum, 0) on the GPU and return at once; collect with p4_partLogLike or treesPartLogLike."""
+    _ok(_lib.p4b_partLogLikeBegin(cTree, int(pNum)))
 
 
 def treesPartLogLike(cTrees, pNum):

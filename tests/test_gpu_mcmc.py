@@ -192,3 +192,31 @@ def test_copy_on_write_keeps_the_twin_intact(pkg, ref_pf):
         pf.p4_copyModelPrams(src.cTree, dst.cTree)
         assert pf.p4_verifyIdentityOfTwoTrees(src.cTree, dst.cTree) == 0
     assert rel(cur.calcLogLike(), pkg.host.clone_tree(cur, ref_pf).calcLogLike()) <= LNL_TOL
+
+
+def test_pipelined_chains_equal_batched_chains(pkg):
+    """Mcmc.run(batched="pipelined"): pf.partLogLikeBegin per chain, one pf.treesPartLogLike to collect."""
+    pf = pkg.pf
+    a = _mcmc(pkg, pf, 4, 9).run(50, batched="pipelined")
+    b = _mcmc(pkg, pf, 4, 9).run(50, batched=False)
+    _same_trace(a, b, 1e-12)
+
+
+def test_begin_then_plain_part_loglike(pkg):
+    pf = pkg.pf
+    t = pkg.synth.build_config(pf, 2, nTax=10, nPatterns=300)
+    want = t.calcLogLike()
+    t.nodes[3].br.len *= 1.3
+    t.nodes[3].br.lenChanged = True
+    new = t.recalcAfterBranchChange()
+    # the same proposal again, this time started asynchronously and collected by the ordinary call
+    t.nodes[3].br.len /= 1.3
+    t.setCStuff()
+    pf.p4_calculateBigPDecks(t.nodes[3].cNode)
+    q = t.nodes[3]
+    while q.parent:
+        q = q.parent
+        pf.p4_setConditionalLikelihoodsOfInternalNodePart(q.cNode, 0)
+    pf.partLogLikeBegin(t.cTree, 0)
+    got = pf.p4_partLogLike(t.cTree, t.data.parts[0].cPart, 0, 0)
+    assert rel(got, want) <= 1e-12 and new != want

@@ -34,7 +34,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--engine", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-patterns", type=int, default=2048)
-    ap.add_argument("--no-batch", action="store_true", help="chains read their likelihoods one after the other")
+    ap.add_argument("--mode", default="pipelined", choices=["pipelined", "batched", "sequential"],
+                    help="pipelined: each chain's evaluation starts when its proposal is issued and is collected on its own event; "
+                         "batched: one launch for all chains; sequential: the reference's order, one chain after the other")
     ap.add_argument("--no-defer", action="store_true", help="node-level calls launch at once")
     ap.add_argument("--no-bulk", action="store_true", help="Tree.setCStuff through the per-node calls")
     ap.add_argument("--seed", type=int, default=1)
@@ -53,7 +55,9 @@ def main():
     tree.bulkSetCStuff = not a.no_bulk
     m = P.mcmc.Mcmc(tree, nChains=a.chains, seed=a.seed)
     setup = time.perf_counter() - t0
-    batched = (a.engine == "b200") and not a.no_batch
+    batched = False
+    if a.engine == "b200":
+        batched = {"pipelined": "pipelined", "batched": True, "sequential": False}[a.mode]
     m.run(a.warmup, batched=batched)
     n0 = pf.kernelLaunchCount() if a.engine == "b200" else 0
     t0 = time.perf_counter()
@@ -63,7 +67,7 @@ def main():
     dt = time.perf_counter() - t0
     out = {"cfg": 5, "engine": a.engine, "taxa": a.taxa, "patterns": nPat, "chains": a.chains, "gens": a.gens,
            "gens_per_s": a.gens / dt, "ms_per_gen": 1e3 * dt / a.gens, "setup_s": setup,
-           "batched": batched, "deferred": not a.no_defer, "bulk_setCStuff": not a.no_bulk,
+           "mode": "sequential" if batched is False else ("batched" if batched is True else batched), "deferred": not a.no_defer, "bulk_setCStuff": not a.no_bulk,
            "proposals": {p.name: [p.nProposals, p.nAcceptances] for p in m.proposals},
            "swaps": [m.nSwapAttempts, m.nSwaps], "lnL_cold_chain": m.trace[-1][1][0]}
     if a.engine == "b200":
