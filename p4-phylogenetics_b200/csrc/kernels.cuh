@@ -347,6 +347,7 @@ constexpr int kMaxSteps = 500;   // 56 B each; with the headers the argument blo
 
 struct TreeArgs {
     int ps, nPat, tblW, nTrees;
+    int maxKids, pad0;        // most children any step of this launch has: sizes the staging buffers
     long long pNodeDoubles;   // stride between nodes in a P deck
     long long tblNodeDoubles;
     long long auxNodeDoubles;
@@ -441,17 +442,16 @@ __device__ __forceinline__ void step_two_children(double2 *cur, const double *__
     }
 }
 
-template <int NCAT, int THREADS, int MINB, bool SCALE>
-__global__ void __launch_bounds__(THREADS, MINB)
-cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
+template <int NCAT, int THREADS, bool SCALE>
+__device__ __forceinline__ void cl_tree_dna_body(const TreeArgs &a)
 {
     constexpr int K = NCAT * 4;
     const TreeHdr &hd = a.hdr[blockIdx.y];     // uniform across the CTA: stays in parameter (constant) memory
-    extern __shared__ double sm[];            // 2 buffers x kMaxChildren x perChild
+    extern __shared__ double sm[];            // 2 buffers x maxKids x perChild, then the prefetch slots
     __shared__ double sSum[THREADS / 32], sBad[THREADS / 32];
     const int W = a.tblW;
     const int perChild = K * (W > 4 ? W : 4);
-    const int bufSize = kMaxChildren * perChild;
+    const int bufSize = a.maxKids * perChild;
     const int pat = (blockIdx.x * THREADS + threadIdx.x) * 2;
     const bool active = pat < a.ps;
     const unsigned ps = (unsigned)a.ps;
@@ -645,6 +645,21 @@ cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
             hd.partials[2 * blockIdx.x + 1] = bad;
         }
     }
+}
+
+// Two ways of fixing the residency of the same body: MINB CTAs per SM (the compiler derives the register
+// budget), or an explicit register budget MAXREG (144 registers = 14 warps per SM: one wave for a 125 k-pattern shard).
+template <int NCAT, int THREADS, int MINB, bool SCALE>
+__global__ void __launch_bounds__(THREADS, MINB)
+cl_tree_dna_kernel(const __grid_constant__ TreeArgs a)
+{
+    cl_tree_dna_body<NCAT, THREADS, SCALE>(a);
+}
+template <int NCAT, int THREADS, int MAXREG>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG)
+cl_tree_dna_kernel_r(const __grid_constant__ TreeArgs a)
+{
+    cl_tree_dna_body<NCAT, THREADS, false>(a);
 }
 
 // ---------------------------------------------------------------------------

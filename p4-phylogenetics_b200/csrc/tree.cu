@@ -876,7 +876,7 @@ static int fusedVariant(int ps, int nTrees)
     if (forced == -2) {
         const char *e = getenv("P4B_FUSED_VARIANT");
         forced = e ? atoi(e) : -1;
-        if (forced < -1 || forced > 6) forced = -1;
+        if (forced < -1 || forced > 8) forced = -1;
     }
     if (forced >= 0) return forced;
     const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
@@ -992,7 +992,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.eqMask = dp->dev.equateMask;
     const bool aa = L.dim == 20;      // tensor-core kernel: root reduction is a separate kernel
     const int variant = aa ? 0 : fusedVariant(L.ps, nJobs);
-    static const int kThreads[7] = {128, 64, 32, 128, 256, 64, 32};
+    static const int kThreads[9] = {128, 64, 32, 128, 256, 64, 32, 64, 32};
     static int aaGroups = -1, aaMinB = 1, aaMT = 2;   // 20-state kernel: pattern groups per CTA, CTAs per SM, m-tiles per warp
     if (aaGroups < 0) {
         const char *e = getenv("P4B_AA_GROUPS");
@@ -1068,13 +1068,15 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
          {cl_tree_aa_kernel<4, 2, 1, 4>, cl_tree_aa_kernel<4, 2, 2, 4>, nullptr},
          {cl_tree_aa_kernel<4, 3, 1, 4>, nullptr, nullptr},
          {cl_tree_aa_kernel<4, 4, 1, 4>, nullptr, nullptr}}};
-    static const KernelFn kFn4[7] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
+    static const KernelFn kFn4[9] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
                                      cl_tree_dna_kernel<4, 32, 12, false>, cl_tree_dna_kernel<4, 128, 4, false>,
                                      cl_tree_dna_kernel<4, 256, 2, false>, cl_tree_dna_kernel<4, 64, 8, false>,
-                                     cl_tree_dna_kernel<4, 32, 16, false>};
-    static const KernelFn kFn1[7] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 64, 8, false>,
+                                     cl_tree_dna_kernel<4, 32, 16, false>, cl_tree_dna_kernel_r<4, 64, 144>,
+                                     cl_tree_dna_kernel_r<4, 32, 144>};
+    static const KernelFn kFn1[9] = {cl_tree_dna_kernel<1, 128, 4, false>, cl_tree_dna_kernel<1, 64, 8, false>,
                                      cl_tree_dna_kernel<1, 32, 16, false>, cl_tree_dna_kernel<1, 128, 4, false>,
                                      cl_tree_dna_kernel<1, 256, 2, false>, cl_tree_dna_kernel<1, 64, 8, false>,
+                                     cl_tree_dna_kernel<1, 32, 16, false>, cl_tree_dna_kernel<1, 64, 8, false>,
                                      cl_tree_dna_kernel<1, 32, 16, false>};
     static const KernelFn kFn4s[3] = {cl_tree_dna_kernel<4, 128, 3, true>, cl_tree_dna_kernel<4, 64, 6, true>,
                                       cl_tree_dna_kernel<4, 32, 12, true>};
@@ -1092,7 +1094,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
             for (int v = 0; v < 4; v++)
                 for (int m = 0; m < 3; m++)
                     if (kFnAA[t][v][m]) CUDA_TRY(cudaFuncSetAttribute(kFnAA[t][v][m], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        for (int v = 0; v < 7; v++) {
+        for (int v = 0; v < 9; v++) {
             CUDA_TRY(cudaFuncSetAttribute(kFn4[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(kFn1[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         }
@@ -1104,7 +1106,24 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     }
     auto launch = [&](int nTrees) -> int {
         a.nTrees = nTrees;
-        fn<<<dim3(blocks, nTrees), THREADS, smem, G.stream>>>(a);
+        size_t smemNow = smem;
+        if (!aa) {   // staging buffers sized by the widest step actually present (2 or 3 in a binary tree), not by kMaxChildren
+            int mk = 1;
+            for (int i = 0; i < nTrees; i++)
+                for (int k = 0; k < a.hdr[i].nSteps; k++) mk = a.steps[a.hdr[i].stepBase + k].nChildren > mk ? a.steps[a.hdr[i].stepBase + k].nChildren : mk;
+            a.maxKids = mk;
+            smemNow = (size_t)2 * mk * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
+            // Residency of the small-CTA shapes is set on purpose, through the shared-memory request: 5 CTAs of 64
+            // threads, 7 of 32.  A step costs a fixed latency whatever the occupancy, so what matters for a shard of
+            // one to three waves is that the LAST wave is nearly full: 125 k patterns are 1.9 waves of 7 x 32 threads
+            // per SM (0.86 ms) but 1.2 waves of 11 x 32 (0.93 ms); 250 k: 64 x 5 1.39 ms, 64 x 6 1.49 ms.
+            static const int kResident[3] = {0, 5, 7};
+            if (variant >= 1 && variant <= 2 && !getenv("P4B_FUSED_NOCAP")) {
+                const size_t need = (size_t)233472 / (kResident[variant] + 1) - 1024 + 256;
+                if (smemNow < need) smemNow = need;
+            }
+        }
+        fn<<<dim3(blocks, nTrees), THREADS, smemNow, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         G.launches++;
         for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
