@@ -94,6 +94,15 @@ void p4b_setDeferredNodeCalls(int on);
  * real copy.  A tree can pair with one other tree; copies to or from any further tree, and all copies
  * with 0 here, are device-to-device memcpys. */
 void p4b_setSharedCondLikes(int on);
+/* Node-level calls whose inputs are exactly those of the result already in memory are skipped by default
+ * (1).  p4_calculateBigPDecks / p4_setPrams: a node's P(t) is a pure function of its eigensystem and its
+ * effective branch length per category; p4_setConditionalLikelihoodsOfInternalNodePart: a node's CL is a pure
+ * function of its children (in order), their CLs and their P decks.  Every computation carries an id, so
+ * "same inputs" is an exact comparison of ids, not of numbers.  The reference's callers recompute a whole part
+ * after changing one composition or one node's model assignment (p4/chain.py:305-380, 560-608); with this the
+ * engine recomputes only what the change reaches: the dirty path.  p4b_treeLogLike always recomputes everything,
+ * as the reference does.  0 makes every call do its full work. */
+void p4b_setMemoize(int on);
 /* 20-state parts use the FP64 tensor-core (mma.sync m8n8k4) CL kernel by default;
  * 0 selects the FMA kernel instead (same results to rounding; for comparison). */
 void p4b_setTensorCoreKernel(int on);

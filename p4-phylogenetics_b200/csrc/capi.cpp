@@ -40,6 +40,7 @@ void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
 void p4b_setFusedTreeKernel20(int on) { setFusedAAEnabled(on); }
 void p4b_setDeferredNodeCalls(int on) { setDeferEnabled(on); }
 void p4b_setSharedCondLikes(int on) { setShareEnabled(on); }
+void p4b_setMemoize(int on) { setMemoizeEnabled(on); }
 void p4b_setTensorCoreKernel(int on) { setDmmaEnabled(on); }
 void p4b_setScalers(int on) { setScalersEnabled(on); }
 

@@ -124,6 +124,10 @@ struct Node {
     std::vector<uint64_t> clStamp;            // per part: id of the computation that filled the CL
     std::vector<uint64_t> pStamp;             // per part: id of the computation that filled the P deck
     std::vector<char> clResident;             // per part: the CL in the arena is the current one (see Tree::storeCL)
+    // what the node's current P deck / CL was computed FROM (p4b_setMemoize): a node-level call whose inputs are
+    // exactly these again would reproduce the same numbers and is skipped
+    std::vector<std::vector<double>> pKey;    // per part: eigensystem content id, effective branch length per category
+    std::vector<std::vector<uint64_t>> clKey; // per part: children in order: node number, CL stamp (or sequence), P stamp
 };
 
 struct TreeDevice;   // tree.cu
@@ -185,6 +189,7 @@ bool treeHasPending(Tree *t);
 void setDeferEnabled(int on);
 void setShareEnabled(int on);
 void setFusedAAEnabled(int on);
+void setMemoizeEnabled(int on);
 int treesPartLogLike(Tree **trees, int n, int p, double *out);
 int treePartLogLikeBegin(Tree *t, int p);
 

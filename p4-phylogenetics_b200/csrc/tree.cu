@@ -67,6 +67,7 @@ static Engine G;
 static int flushPJobs();
 void nodeDeviceRelease(Node *n);
 static bool g_useScalers = false;
+static bool g_memoize = true;    // p4b_setMemoize
 void setScalersEnabled(int on) { g_useScalers = on != 0; }
 
 int deviceCount()
@@ -485,6 +486,8 @@ int nodeDeviceCreate(Node *n)
     n->clStamp.assign(t->nParts, 0);
     n->clResident.assign(t->nParts, 1);
     n->pStamp.assign(t->nParts, 0);
+    n->pKey.assign(t->nParts, std::vector<double>());
+    n->clKey.assign(t->nParts, std::vector<uint64_t>());
     if (!n->isLeaf)
         for (int p = 0; p < t->nParts; p++)
             if (nodeEnsureCLSlot(n, p)) return 1;
@@ -594,7 +597,7 @@ static int hostSetPramsPart(Tree *t, int p)
 }
 
 // Append the P(t) job of (node, part) to the batch.
-static int buildPJob(Node *n, int p)
+static int buildPJob(Node *n, int p, bool allowSkip)
 {
     std::vector<PJob> &jobs = G.pJobs;
     std::vector<double> &tvals = G.pT;
@@ -626,13 +629,19 @@ static int buildPJob(Node *n, int p)
     j.tblW = n->isLeaf ? L.W : 0;
     j.nRealEq = L.W - L.dim - 1;
     j.tOff = (long long)tvals.size();
+    std::vector<double> key(1 + mp->nCat);
+    key[0] = (double)mp->bqe[c * mp->nRMatrices + r].content;     // which solve of which (pi, R)
     for (int cat = 0; cat < mp->nCat; cat++) {   // Pf/p4_node.c:321-345, same expressions
         double tt;
         if (mp->pInvar == 0.0) tt = g ? (n->brLen * g->rates[cat] * mp->relRate) : (n->brLen * mp->relRate);
         else tt = g ? (n->brLen * g->rates[cat] * mp->relRate) / (1.0 - mp->pInvar) : (n->brLen * mp->relRate) / (1.0 - mp->pInvar);
-        tvals.push_back(tt);
+        key[1 + cat] = tt;
     }
+    // P(t) is a pure function of (eigensystem, t per category): the same inputs again give the deck already there
+    if (g_memoize && allowSkip && n->pStamp[p] != 0 && key[0] != 0.0 && n->pKey[p] == key) return 0;
+    for (int cat = 0; cat < mp->nCat; cat++) tvals.push_back(key[1 + cat]);
     jobs.push_back(j);
+    n->pKey[p].swap(key);
     n->pStamp[p] = ++G.stamp;
     return 0;
 }
@@ -678,7 +687,7 @@ int treeSetPrams(Tree *t, int pNum)
                 if (eigEnsureUploaded(t, p, n->compNums[p], n->rMatrixNums[p])) return 1;
         for (Node *n : t->nodes)
             if (n && n != t->root)
-                if (buildPJob(n, p)) return 1;
+                if (buildPJob(n, p, true)) return 1;
     }
     return 0;
 }
@@ -688,7 +697,7 @@ int nodeCalculateBigPDecks(Node *n)
     Tree *t = n->tree;
     if (treeFlushAllPending(t)) return 1;
     for (int p = 0; p < t->nParts; p++)
-        if (buildPJob(n, p)) return 1;
+        if (buildPJob(n, p, true)) return 1;
     return 0;
 }
 
@@ -698,7 +707,7 @@ int treeCalculateAllBigPDecks(Tree *t)   // Pf/p4_tree.c p4_calculateAllBigPDeck
     for (int p = 0; p < t->nParts; p++)
         for (Node *n : t->nodes)
             if (n && n != t->root)
-                if (buildPJob(n, p)) return 1;
+                if (buildPJob(n, p, true)) return 1;
     return 0;
 }
 
@@ -709,6 +718,7 @@ static bool g_dmmaEnabled = true;
 void setDmmaEnabled(int on) { g_dmmaEnabled = on != 0; }
 static bool g_fusedEnabled = true;
 static bool g_deferCL = true;
+void setMemoizeEnabled(int on) { g_memoize = on != 0; }
 void setDeferEnabled(int on) { g_deferCL = on != 0; }
 
 static bool g_fusedAAEnabled = true;
@@ -771,14 +781,34 @@ static int launchCL(const CLArgs &a)
     return 0;
 }
 
-int nodeSetCL(Node *n, int p)
+// What a node's CL is a pure function of: its children in order, each child's CL (by computation id) or tip
+// row, each child's P deck (by computation id), and the data.
+static void makeClKey(Node *n, int p, std::vector<uint64_t> &key)
+{
+    key.clear();
+    key.push_back(n->tree->data->parts[p]->version);
+    for (Node *c = n->leftChild; c; c = c->sibling) {
+        key.push_back((uint64_t)c->nodeNum);
+        key.push_back(c->isLeaf ? (uint64_t)c->seqNum : c->clStamp[p]);
+        key.push_back(c->pStamp[p]);
+    }
+}
+static bool clIsCurrent(Node *n, int p, const std::vector<uint64_t> &key)
+{
+    return g_memoize && n->clSlot[p] >= 0 && n->clResident[p] && n->clStamp[p] != 0 && n->clKey[p] == key;
+}
+
+static int nodeSetCLImpl(Node *n, int p, bool memo);
+int nodeSetCL(Node *n, int p) { return nodeSetCLImpl(n, p, true); }
+
+static int nodeSetCLImpl(Node *n, int p, bool memo)
 {
     Tree *t = n->tree;
     TreeDevice *d = t->dev;
     if (p < 0 || p >= t->nParts) { setError("p4_setConditionalLikelihoodsOfInternalNodePart: bad part %d", p); return 1; }
     if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
     PartLayout &L = d->parts[p];
-    if (g_deferCL && fusedEligible(L)) {
+    if (memo && g_deferCL && fusedEligible(L)) {
         if (nodeEnsureCLSlot(n, p)) return 1;   // a root that is a leaf gets its CL lazily, Pf/p4_node.c:608-626
         // The callers issue node-level calls in dependency order (the dirty set is decided in
         // Python): queue, and run the whole queue as one step-list launch when its result is needed.
@@ -786,8 +816,11 @@ int nodeSetCL(Node *n, int p)
         n->clNeedsUpdating = 0;
         return 0;
     }
-    if (nodeMakeWritable(n, p)) return 1;
     if (treeEnsureResident(t, p)) return 1;
+    std::vector<uint64_t> key;
+    makeClKey(n, p, key);
+    if (memo && clIsCurrent(n, p, key)) { n->clNeedsUpdating = 0; return 0; }   // same inputs as last time: the CL in memory is the answer
+    if (nodeMakeWritable(n, p)) return 1;
     Part *dp = t->data->parts[p];
     CLArgs a;
     memset(&a, 0, sizeof(a));
@@ -844,6 +877,7 @@ int nodeSetCL(Node *n, int p)
         G.launches++;
     }
     n->clStamp[p] = ++G.stamp;
+    n->clKey[p].swap(key);
     n->clResident[p] = 1;
     n->clNeedsUpdating = 0;
     return 0;
@@ -862,6 +896,7 @@ struct FusedJob {
     bool withLike;       // fuse the root reduction (order must end at the root)
     bool wantPatLikes;
     bool storeAll;       // false: lnL-only evaluation, keep only the CLs the launch itself re-reads
+    bool memo;           // queued node-level calls: a node whose inputs are those of its current CL is skipped
 };
 
 // Launch shape of the whole-tree kernel: threads per CTA x CTAs per SM.  0: 128x3, 1: 64x6, 2: 32x12 (all
@@ -898,6 +933,10 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
     for (; oi < order.size(); oi++) {
         Node *n = order[oi];
         if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return -1; }
+        std::vector<uint64_t> key;
+        makeClKey(n, p, key);
+        // never skip the node the fused root reduction reads from registers
+        if (job.memo && !(job.withLike && oi + 1 == order.size()) && clIsCurrent(n, p, key)) { n->clNeedsUpdating = 0; continue; }
         int nKids = 0;
         for (Node *c = n->leftChild; c; c = c->sibling) nKids++;
         const int chunks = (nKids + maxKids - 1) / maxKids;
@@ -949,6 +988,7 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
         ns++;
         prev = n;
         n->clStamp[p] = ++G.stamp;
+        n->clKey[p].swap(key);
         n->clResident[p] = job.storeAll ? 1 : 0;
         n->clNeedsUpdating = 0;
     }
@@ -1179,9 +1219,9 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     return 0;
 }
 
-static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes, bool storeAll = true)
+static int launchFusedTree(Tree *t, int p, const std::vector<Node *> &order, bool withLike, bool wantPatLikes, bool storeAll = true, bool memo = false)
 {
-    FusedJob job = {t, &order, withLike, wantPatLikes, storeAll};
+    FusedJob job = {t, &order, withLike, wantPatLikes, storeAll, memo};
     return launchFusedBatch(&job, 1, p, t->dev->result + 2 * p);
 }
 
@@ -1220,7 +1260,7 @@ int treeEnsureResident(Tree *t, int p)
     if (q.empty()) return 0;
     std::vector<Node *> order;
     order.swap(q);
-    return launchFusedTree(t, p, order, false, false, true);
+    return launchFusedTree(t, p, order, false, false, true, true);
 }
 
 static int treeFlushAllPending(Tree *t)
@@ -1331,7 +1371,7 @@ static int launchPartLike(Tree *t, int p, int getSiteLikes)
         if (residentPass(t, p)) return 1;
         std::vector<Node *> order;
         order.swap(q);
-        return launchFusedTree(t, p, order, true, getSiteLikes != 0, true);
+        return launchFusedTree(t, p, order, true, getSiteLikes != 0, true, true);
     }
     return enqueuePartLike(t, p, getSiteLikes != 0);
 }
@@ -1415,7 +1455,7 @@ double treeLogLike(Tree *t, int getSiteLikes)
             if (getSiteLikes && fillSiteLikes(t, p)) return NAN;
         } else {
             for (Node *n : order)
-                if (nodeSetCL(n, p)) return NAN;
+                if (nodeSetCLImpl(n, p, false)) return NAN;   // a whole-tree evaluation recomputes every node, as the reference does
         }
     }
     cudaEventRecord(d->evCLb, G.stream);
@@ -1500,7 +1540,7 @@ int treesPartLogLike(Tree **trees, int n, int p, double *out)
             Tree *t = trees[i0 + k];
             if (residentPass(t, p)) return 1;
             orders[k].swap(t->dev->pending[p]);
-            jobs[k] = FusedJob{t, &orders[k], true, false, true};
+            jobs[k] = FusedJob{t, &orders[k], true, false, true, true};
         }
         if (launchFusedBatch(jobs.data(), m, p, G.dBatch)) return 1;
         if (commActive())
@@ -1591,6 +1631,7 @@ int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
                                          cudaMemcpyDeviceToDevice, G.stream));   // CL and, behind it, the exponents
             }
             nB->clStamp[p] = nA->clStamp[p];
+            nB->clKey[p] = nA->clKey[p];
             nB->clResident[p] = 1;
         }
         if (!doAll) nA->clNeedsUpdating = nB->clNeedsUpdating = 0;
@@ -1625,7 +1666,10 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
             CUDA_TRY(cudaMemcpyAsync(db->aux, da->aux, da->auxNodeDoubles * sizeof(double) * (size_t)a->nNodes, cudaMemcpyDeviceToDevice, G.stream));
         for (int i = 0; i < a->nNodes; i++)
             if (a->nodes[i] && b->nodes[i])
-                for (int p = 0; p < a->nParts; p++) b->nodes[i]->pStamp[p] = a->nodes[i]->pStamp[p];
+                for (int p = 0; p < a->nParts; p++) {
+                    b->nodes[i]->pStamp[p] = a->nodes[i]->pStamp[p];
+                    b->nodes[i]->pKey[p] = a->nodes[i]->pKey[p];
+                }
         return 0;
     }
     for (auto &ab : todo) {
@@ -1638,6 +1682,7 @@ int treeCopyBigPDecks(Tree *a, Tree *b, int doAll)
             if (a->dev->parts[p].auxDoubles && sameShape)
                 CUDA_TRY(cudaMemcpyAsync(nodeAux(nB, p), nodeAux(nA, p), a->dev->parts[p].auxDoubles * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
             nB->pStamp[p] = nA->pStamp[p];
+            nB->pKey[p] = nA->pKey[p];
         }
     }
     return 0;
@@ -1762,6 +1807,7 @@ int nodeSetBigP(Node *n, int p, const double *in)
     }
     if (streamSync()) return 1;
     n->pStamp[p] = ++G.stamp;
+    n->pKey[p].clear();
     return 0;
 }
 

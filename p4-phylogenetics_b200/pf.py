@@ -79,6 +79,7 @@ _sig("p4b_setTensorCoreKernel", None, _i)
 _sig("p4b_setFusedTreeKernel20", None, _i)
 _sig("p4b_setDeferredNodeCalls", None, _i)
 _sig("p4b_setSharedCondLikes", None, _i)
+_sig("p4b_setMemoize", None, _i)
 _sig("p4b_treesPartLogLike", _i, _i, _vp, _i, _vp)
 _sig("p4b_partLogLikeBegin", _i, _vp, _i)
 _sig("p4b_setScalers", None, _i)
@@ -246,6 +247,11 @@ def setSharedCondLikes(on):
 def partLogLikeBegin(cTree, pNum):
     """Start p4_partLogLike(cTree, ., pNum, 0) on the GPU and return at once; collect with p4_partLogLike or treesPartLogLike."""
     _ok(_lib.p4b_partLogLikeBegin(cTree, int(pNum)))
+
+
+def setMemoize(on):
+    """0: node-level calls always do their full work (see include/p4b200.h p4b_setMemoize)."""
+    _lib.p4b_setMemoize(int(on))
 
 
 def treesPartLogLike(cTrees, pNum):

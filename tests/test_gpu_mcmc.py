@@ -220,3 +220,49 @@ def test_begin_then_plain_part_loglike(pkg):
     pf.partLogLikeBegin(t.cTree, 0)
     got = pf.p4_partLogLike(t.cTree, t.data.parts[0].cPart, 0, 0)
     assert rel(got, want) <= 1e-12 and new != want
+
+
+def test_memoized_calls_equal_full_work(pkg, ref_pf):
+    """p4b_setMemoize: after ONE composition of a composition-per-node model changes, p4's protocol recomputes the
+    whole part (p4_setPrams + every node, p4/chain.py:305-380); the engine recognises which P decks and CLs have the
+    inputs they were computed from and redoes only the others.  Same numbers, fewer steps."""
+    pf, H = pkg.pf, pkg.host
+    mine, twin = pkg.synth.build_config(pf, 4, nTax=10, nPatterns=200), None
+    twin = H.clone_tree(mine, ref_pf)
+    mine.calcLogLike()
+    twin.calcLogLike()
+    rng = np.random.default_rng(4)
+
+    def whole_part(t, pNum):
+        p = t.pf
+        p.p4_setPrams(t.cTree, pNum)
+        for n in t.iterInternalsPostOrder():
+            p.p4_setConditionalLikelihoodsOfInternalNodePart(n.cNode, pNum)
+        return p.p4_partLogLike(t.cTree, t.data.parts[pNum].cPart, pNum, 0)
+
+    leaf = [n for n in mine.nodes if n.isLeaf][3]
+    for trial, pNum in enumerate((0, 2, 0)):
+        old = mine.model.parts[pNum].comps[leaf.nodeNum].val
+        new = pkg.synth.normalise_comp(old * np.exp(rng.normal(0.0, 0.2, size=old.shape)))
+        for t in (mine, twin):
+            t.model.parts[pNum].comps[leaf.nodeNum].val[:] = new
+        pf.treeSync(mine.cTree)
+        n0 = pf.kernelLaunchCount()
+        got = whole_part(mine, pNum)
+        want = whole_part(twin, pNum)
+        assert rel(got, want) <= LNL_TOL
+        # and against this engine doing its full work on a fresh copy of the state
+        pf.setMemoize(0)
+        try:
+            full = whole_part(mine, pNum)
+        finally:
+            pf.setMemoize(1)
+        assert full == got
+    # nothing changed at all: the calls are answered without recomputing any node but the root
+    before = [pf.getNodeCL(mine.cTree, n.cNode, 0, 4, 20) for n in mine.iterInternalsPostOrder()]
+    again = whole_part(mine, 0)
+    assert again == got
+    for b, n in zip(before, mine.iterInternalsPostOrder()):
+        assert np.array_equal(b, pf.getNodeCL(mine.cTree, n.cNode, 0, 4, 20))
+    # the whole-tree evaluation still recomputes everything and agrees
+    assert rel(pf.p4_treeLogLike(mine.cTree, 0), float(sum(mine.partLikes))) <= 1e-12

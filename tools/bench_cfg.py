@@ -22,8 +22,12 @@ def main():
     ap.add_argument("--patterns", type=int, default=None)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", action="store_true", help="compare lnL with the reference engine on the same inputs (slow)")
+    ap.add_argument("--dirty", action="store_true",
+                    help="config 4's scenario (SURVEY.md 8d): evaluate after changing one leaf composition, one internal "
+                         "composition, one branch length, with p4's call protocol; with and without p4b_setMemoize")
     a = ap.parse_args()
     pf = P.pf
+    pf.setMemoize(0)      # every call does its full work
     t0 = time.perf_counter()
     tree = P.synth.build_config(pf, a.cfg, nTax=a.taxa, nPatterns=a.patterns)
     setup = time.perf_counter() - t0
@@ -55,6 +59,45 @@ def main():
            "algorithmic_GB_per_eval": bpp / 1e9, "algorithmic_GBps": bpp / ms / 1e6,
            "GFLOP_per_eval": flops / 1e9, "TFLOPs": flops / ms / 1e9, "setup_s": setup,
            "device_GB": pf.treeDeviceBytes(tree.cTree) / 1e9}
+    if a.dirty:
+        import numpy as np
+        rng = np.random.default_rng(0)
+
+        def whole_part(pNum):     # what Chain.proposeSp issues after a composition proposal (p4/chain.py:305-380)
+            pf.p4_setPrams(tree.cTree, pNum)
+            for n in tree.iterInternalsPostOrder():
+                pf.p4_setConditionalLikelihoodsOfInternalNodePart(n.cNode, pNum)
+            return pf.p4_partLogLike(tree.cTree, tree.data.parts[pNum].cPart, pNum, 0)
+
+        def comp_change(node, pNum):
+            c = tree.model.parts[pNum].comps[node.parts[pNum].compNum]
+            c.val[:] = P.synth.normalise_comp(c.val * np.exp(rng.normal(0.0, 0.05, size=c.val.shape)))
+
+        leaves = [n for n in tree.nodes if n.isLeaf]
+        internals = [n for n in tree.nodes if not n.isLeaf and n is not tree.root]
+        res = {}
+        for memo in (1, 0):
+            pf.setMemoize(memo)
+            tree.calcLogLike()
+            for name, pool in (("one_leaf_comp", leaves), ("one_internal_comp", internals)):
+                ts = []
+                for k in range(a.steps):
+                    comp_change(pool[k % len(pool)], k % tree.model.nParts)
+                    t1 = time.perf_counter()
+                    whole_part(k % tree.model.nParts)
+                    ts.append((time.perf_counter() - t1) * 1e3)
+                res["%s_ms_memo%d" % (name, memo)] = sum(ts) / len(ts)
+            ts = []
+            for k in range(a.steps):
+                n = tree.nodes[1 + k % (len(tree.nodes) - 1)]
+                n.br.len *= 1.05
+                n.br.lenChanged = True
+                t1 = time.perf_counter()
+                tree.recalcAfterBranchChange()
+                ts.append((time.perf_counter() - t1) * 1e3)
+            res["one_brlen_ms_memo%d" % memo] = sum(ts) / len(ts)
+        pf.setMemoize(0)
+        out["dirty"] = res
     if a.check:
         import ref_loader
         twin = P.host.clone_tree(tree, ref_loader.load_ref_pf())
