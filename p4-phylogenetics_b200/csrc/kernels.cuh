@@ -175,15 +175,15 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
     }
     if (job.aux) {
         // Operand decks of cl_tree_aa_kernel, so that its per-step staging is a straight copy:
-        //   aux[0 .. nCat*576)            P^T in mma fragment order [cat][kk = 2t+i][nt][lane]: lane (g,q) holds
-        //                                 P[cat][8nt+g][8t+2q+i], zero where either state is >= 20
-        //   aux[nCat*576 .. +nCat*W*20)   leaf table transposed, [cat][w][state]
+        //   aux[0 .. nCat*480)            P^T in mma fragment order [cat][kk][nt][lane]: lane (g,q) holds P[cat][8nt+g][x],
+        //                                 x = 8t+2q+i for kk = 2t+i < 4, x = 16+q for kk = 4; zero where the parent state is >= 20
+        //   aux[nCat*480 .. +nCat*W*20)   leaf table transposed, [cat][w][state]
         __syncthreads();
         double *A = job.aux;
-        const int nF = nCat * 576;
+        const int nF = nCat * 480;
         for (int i = threadIdx.x; i < nF; i += blockDim.x) {
-            const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 6, ct = i / 576;
-            const int s = 8 * nt + (l >> 2), x = 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1);
+            const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 5, ct = i / 480;
+            const int s = 8 * nt + (l >> 2), x = kk < 4 ? 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1) : 16 + (l & 3);
             A[i] = (s < dim && x < dim) ? P[(ct * dim + s) * dim + x] : 0.0;
         }
         if (job.tblW > 0) {
@@ -880,12 +880,14 @@ cl_dmma20_kernel(const __grid_constant__ CLArgs a)
 //   A (8 x 4)  = child CL, rows = patterns, columns = child states
 //   B (4 x 8)  = P^T,      rows = child states, columns = parent states   (pre-arranged in shared memory)
 //   C (8 x 8)  = parent CL, rows = patterns, columns = parent states
-// and the summation index is dealt to the k-steps so that k-step (t, i), t = 0..2, i = 0..1, covers the
+// and the summation index is dealt to the k-steps so that k-step (t, i), t = 0..1, i = 0..1, covers the
 // child states {8t + 2q + i : q = 0..3}.  Lane (g, q) then needs, as its A element of k-step (t, i), the
 // value (pattern g, state 8t + 2q + i) -- exactly what it holds as C element i of n-tile t after the child
-// was computed.  A node's result is therefore the next node's operand with no data movement at all: a warp
-// walks the whole step list with the running CL in registers, like the 4-state kernel does with FMAs.
-// States are padded 20 -> 24 in both directions (zeros in B), 18 DMMAs per child and 8 patterns.
+// was computed.  A node's result is therefore the next node's operand with no data movement: a warp walks
+// the whole step list with the running CL in registers, like the 4-state kernel does with FMAs.  The last
+// four states (16..19, held two per lane by the lanes q = 0, 1 of n-tile 2) form a fifth k-step of their
+// own, lane q <-> state 16 + q, gathered inside each quad by one shuffle.  Parent states are padded
+// 20 -> 24 (zero columns in B): 15 DMMAs per child and 8 patterns, the same as an unpadded 24 x 20 product.
 //
 // A warp owns one rate category of one group of 8*MT patterns (categories never mix below the root);
 // m-tile j, row g  <->  pattern pat0 + MT*g + j, so a lane's MT m-tiles are MT consecutive patterns of a
@@ -896,7 +898,7 @@ cl_dmma20_kernel(const __grid_constant__ CLArgs a)
 // are chained by the host).  The root reduction is a separate kernel (like_kernel).
 // ---------------------------------------------------------------------------
 constexpr int kAAKids = 2;
-constexpr int kAAFrag = 18 * 32;     // doubles of P^T fragments per child and category
+constexpr int kAAFrag = 15 * 32;     // doubles of P^T fragments per child and category: 5 k-steps x 3 n-tiles x 32 lanes
 
 __device__ __forceinline__ void named_barrier(int id, int nThreads)
 {
@@ -962,10 +964,9 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
     const size_t rowBase = (size_t)cat * DIM * ps + pat0 + MT * g;   // + state * ps: this lane's MT patterns of a row
     const size_t auxLeafOff = (size_t)NCAT * kAAFrag + (size_t)cat * tblSize;
     const int nSteps = hd.nSteps, stepBase = hd.stepBase;
-    // Lanes q >= 2 hold, in n-tile 2, the padding states 16+2q+i >= 20.  Their operand values only ever meet
-    // zeros of P^T, so any FINITE number will do: they re-read the rows 8 states lower instead of branching.
+    // Lanes q >= 2 hold, in n-tile 2, the padding states 16+2q+i >= 20: computed as zeros (zero columns of P^T),
+    // kept at zero through leaf lookups, never stored.
     const bool tail = q >= 2;
-    const size_t hiRow = (size_t)(tail ? 8 : 16) * ps;
 
     auto stage = [&](int stepIdx, int b) {      // one thread per category
         const StepC &st = a.steps[stepBase + stepIdx];
@@ -989,21 +990,22 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
         return MT == 4 ? *reinterpret_cast<const unsigned *>(tp) : (unsigned)*reinterpret_cast<const unsigned short *>(tp);
     };
 
-    // out (=|*=) A x B for one child: A in registers (C layout of the child), B fragments of this category.
-    // The three n-tiles advance together: 3*MT independent accumulator chains keep the tensor pipe fed.
-    auto contract = [&](const double (&A)[MT][3][2], const double *__restrict__ Bc, double (&out)[MT][3][2], bool assign) {
+    // out (=|*=) A x B for one child: A in registers (C layout of the child for the states 0..15, a4 = the fifth
+    // k-step's operand: state 16 + q), B fragments of this category.  The three n-tiles advance together:
+    // 3*MT independent accumulator chains keep the tensor pipe fed.
+    auto contract = [&](const double (&A)[MT][3][2], const double (&a4)[MT], const double *__restrict__ Bc, double (&out)[MT][3][2], bool assign) {
         double acc[MT][3][2];
 #pragma unroll
         for (int j = 0; j < MT; j++)
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) acc[j][nt][0] = acc[j][nt][1] = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) {
+        for (int kk = 0; kk < 5; kk++) {
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) {
                 const double b = Bc[(kk * 3 + nt) * 32];
 #pragma unroll
-                for (int j = 0; j < MT; j++) dmma884(acc[j][nt][0], acc[j][nt][1], A[j][kk >> 1][kk & 1], b);
+                for (int j = 0; j < MT; j++) dmma884(acc[j][nt][0], acc[j][nt][1], kk < 4 ? A[j][kk >> 1][kk & 1] : a4[j], b);
             }
         }
         if (assign) {
@@ -1018,6 +1020,7 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
                 for (int nt = 0; nt < 3; nt++) { out[j][nt][0] *= acc[j][nt][0]; out[j][nt][1] *= acc[j][nt][1]; }
         }
     };
+    const int quadSrc = (lane & ~3) | (q >> 1);   // the lane of this quad that holds state 16 + q (as its element q & 1 of n-tile 2)
 
     unsigned next0 = 0u, next1 = 0u;   // tip codes of the next step's children
 
@@ -1038,7 +1041,13 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
         for (int c = 0; c < nc; c++)
             if (((unsigned)st.ch[c].a >> 30) == 1u) regChild = c;
         if (regChild >= 0) {                 // the child computed by the previous step: straight from registers
-            contract(in, buf + regChild * slot + lane, out, true);
+            double a4[MT];
+#pragma unroll
+            for (int j = 0; j < MT; j++) {
+                const double v0 = __shfl_sync(0xffffffffu, in[j][2][0], quadSrc), v1 = __shfl_sync(0xffffffffu, in[j][2][1], quadSrc);
+                a4[j] = (q & 1) ? v1 : v0;
+            }
+            contract(in, a4, buf + regChild * slot + lane, out, true);
         } else if (!st.first) {              // continuation of a node with more than two children
 #pragma unroll
             for (int j = 0; j < MT; j++)
@@ -1069,11 +1078,11 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
                     out[j][2][1] *= tail ? 0.0 : v2.y;
                 }
             } else {                         // internal child in memory (written earlier by this same lane)
-                const double *cl = hd.arena + (size_t)(av & 0x3fffffffu) * 32 + rowBase + (size_t)(2 * q) * ps;
-                double sib[MT][3][2];
+                const double *cl = hd.arena + (size_t)(av & 0x3fffffffu) * 32 + rowBase;
+                double sib[MT][3][2], a4[MT];
 #pragma unroll
-                for (int r = 0; r < 6; r++) {
-                    const double *row = cl + (r < 4 ? (size_t)(8 * (r >> 1)) * ps : hiRow) + (size_t)(r & 1) * ps;
+                for (int r = 0; r < 4; r++) {            // states 8t + 2q + i, t = r >> 1, i = r & 1
+                    const double *row = cl + (size_t)(8 * (r >> 1) + 2 * q + (r & 1)) * ps;
 #pragma unroll
                     for (int h = 0; h < MT / 2; h++) {
                         const double2 v = ld2(row + 2 * h);
@@ -1081,7 +1090,15 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
                         sib[2 * h + 1][r >> 1][r & 1] = v.y;
                     }
                 }
-                contract(sib, buf + c * slot + lane, out, false);
+#pragma unroll
+                for (int h = 0; h < MT / 2; h++) {       // state 16 + q: the fifth k-step's operand, straight from its row
+                    const double2 v = ld2(cl + (size_t)(16 + q) * ps + 2 * h);
+                    a4[2 * h] = v.x;
+                    a4[2 * h + 1] = v.y;
+                }
+#pragma unroll
+                for (int j = 0; j < MT; j++) sib[j][2][0] = sib[j][2][1] = 0.0;   // not read
+                contract(sib, a4, buf + c * slot + lane, out, false);
             }
         }
         if (st.store) {

@@ -1795,8 +1795,8 @@ int nodeSetBigP(Node *n, int p, const double *in)
     if (L.auxDoubles) {   // the same two decks pmatrix_kernel derives from P
         const int nF = L.nCat * kAAFrag;
         for (int i = 0; i < nF; i++) {
-            const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 6, ct = i / 576;
-            const int s = 8 * nt + (l >> 2), x = 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1);
+            const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 5, ct = i / kAAFrag;
+            const int s = 8 * nt + (l >> 2), x = kk < 4 ? 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1) : 16 + (l & 3);
             A[i] = (s < dim && x < dim) ? in[((size_t)ct * dim + s) * dim + x] : 0.0;
         }
         for (int i = 0; i < L.nCat * W * dim; i++) {
