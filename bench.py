@@ -429,8 +429,8 @@ def run_b200(a):
     achieved = cl_bytes / (cl_ms_avg * 1e-3) / 1e9
     ps_pad = (shard + 31) // 32 * 32
     waves = (ps_pad / 2) / (128.0 * 3.0 * 148)      # the engine's launch-shape rule (csrc/tree.cu fusedVariant)
-    shape = "128,3" if waves >= 3.0 else ("64,6" if waves >= 1.6 else "32,12")
-    kernel = "cl_tree_dna_kernel<4,%s> (whole-tree CL recursion + site likelihoods, one launch)" % shape if cl_launches == 1 \
+    shape = "128 threads x 3 CTAs/SM" if waves >= 3.0 else ("64 x 5" if waves >= 1.6 else "32 x 7")
+    kernel = "cl_tree_dna_kernel<4>, %s (whole-tree CL recursion + site likelihoods, one launch)" % shape if cl_launches == 1 \
         else "cl_dna_kernel<4> (all %d CL launches of one evaluation)" % cl_launches
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
