@@ -100,13 +100,15 @@ def test_polytomy_protein(pkg, ref_pf):
     assert rel(tree.calcLogLike(), twin.calcLogLike()) <= LNL_TOL
 
 
-def test_ndch2_chain_matches_reference(pkg, ref_pf):
+@pytest.mark.parametrize("mode", ["pipelined", True, False])
+def test_ndch2_chain_matches_reference(pkg, ref_pf, mode):
     """A short MCMC on the tree-heterogeneous protein config: allCompsDir proposals re-solve the changed
-    eigensystems, topology moves shuffle which node uses which composition."""
+    eigensystems, topology moves shuffle which node uses which composition.  All three ways of reading the chains'
+    likelihoods (pipelined, one batched launch per part, one chain after the other)."""
     def make(pf):
         tree = pkg.synth.build_config(pf, 4, nTax=8, nPatterns=120)
-        return pkg.mcmc.Mcmc(tree, nChains=2, seed=3)
-    a = make(pkg.pf).run(40)
+        return pkg.mcmc.Mcmc(tree, nChains=3, seed=3)
+    a = make(pkg.pf).run(40, batched=mode)
     b = make(ref_pf).run(40)
     for (ga, la), (gb, lb) in zip(a, b):
         for x, y in zip(la, lb):

@@ -142,3 +142,28 @@ def test_q_and_eigensystem(pkg, name):
     assert worst_mine < 5e-15, (worst_mine, worst_ref)
     tree.model.free()
     tree.data.free()
+
+
+def test_fast_bindings_mirror_the_ctypes_wrappers(pkg):
+    """csrc/pfhot.c: the METH_FASTCALL bindings of the per-node calls are installed over the ctypes wrappers and keep
+    their contract: same names, arity checked, engine errors raise P4bFatal (no GPU needed: NULL handles)."""
+    pf = pkg.pf
+    assert pf.use_fast_bindings(True), "_pfhot was not built (g.build())"
+    for name in pf._HOT_NAMES:
+        assert getattr(pf, name) is getattr(pf._hot, name)
+    with pytest.raises(pf.P4bFatal) as e:
+        pf.p4_setBrLen(0, 0.1)
+    assert "NULL handle" in str(e.value)
+    with pytest.raises(TypeError):
+        pf.p4_setBrLen(0)
+    with pytest.raises(pf.P4bFatal):
+        pf.p4_setNodeRelation(0, 0, np.int32(3))        # numpy integers are accepted as integers
+    with pytest.raises(TypeError):
+        pf.p4_setNodeRelation(0, 0, "x")
+    try:
+        assert not pf.use_fast_bindings(False)
+        assert pf.p4_setBrLen is pf._ctypes_versions["p4_setBrLen"]
+        with pytest.raises(pf.P4bFatal):
+            pf.p4_setBrLen(0, 0.1)
+    finally:
+        pf.use_fast_bindings(True)
