@@ -70,6 +70,127 @@ def mcmc_simple(nChains, nGens, seed, name):
     print(out, os.path.getsize(out), "bytes;", sum(counts.values()), "calls;", props)
 
 
+def _begin(seed):
+    fresh()
+    rec.events = []
+    rec._handles.clear()
+    rec._arrays.clear()
+    rec._nHandles = rec._nArrays = 0
+    rec.recording = True
+    random.seed(seed)
+
+
+def _finish(m, what, seed, name):
+    rec.recording = False
+    counts = {}
+    for ev in rec.events:
+        if ev[0] == "call":
+            counts[ev[1]] = counts.get(ev[1], 0) + 1
+    props = {p.name: [int(sum(p.nProposals)), int(sum(p.nAcceptances))] for p in m.props.proposals}
+    meta = {"what": what, "seed": seed, "calls": counts, "proposals [made, accepted]": props,
+            "final_cur_lnL": [float(c.curTree.logLike) for c in m.chains]}
+    out = os.path.join(HERE, name)
+    rec.save(out, meta)
+    print(out, os.path.getsize(out), "bytes;", sum(counts.values()), "calls;", props)
+
+
+def mcmc_two_parts(nChains, nGens, seed, name):
+    """Two character partitions with different models and free relative rates (share/Examples/H_calcLike/
+    C_3_data_partitions pattern): per-part proposals, the relRate proposal, p4_calculateAllBigPDecksAllParts."""
+    _begin(seed)
+    read(os.path.join(EX, "d.nex"))
+    a = var.alignments[0]
+    half = a.length // 2
+    read("#nexus\nbegin sets;\n charset c1 = 1-%d;\n charset c2 = %d-.;\n charpartition cp1 = c1:c1, c2:c2;\nend;\n" % (half, half + 1))
+    a.setCharPartition("cp1")
+    d = Data()
+    t = func.randomTree(taxNames=d.taxNames)
+    t.data = d
+    t.newComp(partNum=0, free=1, spec="empirical")
+    t.newRMatrix(partNum=0, free=1, spec="ones")
+    t.setPInvar(partNum=0, free=1, val=0.1)
+    t.setNGammaCat(partNum=0, nGammaCat=1)
+    t.setRelRate(partNum=0, val=0.6)
+    t.newComp(partNum=1, free=1, spec="empirical")
+    t.newRMatrix(partNum=1, free=0, spec="2p", val=2.5)     # a FIXED 2-parameter matrix (kappa through p4_setKappa)
+    t.setPInvar(partNum=1, free=0, val=0.0)
+    t.setNGammaCat(partNum=1, nGammaCat=4)
+    t.newGdasrv(partNum=1, free=1, val=2.0)
+    t.setRelRate(partNum=1, val=1.4)
+    t.model.relRatesAreFree = 1
+    m = Mcmc(t, nChains=nChains, runNum=2, sampleInterval=10, checkPointInterval=None)
+    m.run(nGens)
+    _finish(m, "reference p4 Mcmc.run(%d), %d chains, 2 partitions (GTR+I / fixed 2-parameter matrix +G4), free relRates, on L_mcmc/d.nex" % (nGens, nChains), seed, name)
+
+
+def mcmc_locations_polytomy(nGens, seed, name):
+    """Two compositions and two rate matrices placed on the tree (NDCH + NDRH) with the location proposals, root3 and the
+    brLen proposals switched on: model assignments move over the tree, the root changes.  (The reference's polytomy proposal does not
+    run under Python 3.12 -- random.randrange(float), p4/chain.py:6393 -- so it is not in the trace.)"""
+    _begin(seed)
+    read(os.path.join(EX, "d.nex"))
+    d = Data()
+    t = func.randomTree(taxNames=d.taxNames)
+    t.data = d
+    c0 = t.newComp(free=1, spec="empirical")
+    c1 = t.newComp(free=1, spec="empirical")
+    r0 = t.newRMatrix(free=1, spec="ones")
+    r1 = t.newRMatrix(free=1, spec="ones")
+    t.setModelComponentsOnNodesRandomly()
+    t.setNGammaCat(nGammaCat=4)
+    t.newGdasrv(free=1, val=0.7)
+    t.setPInvar(free=0, val=0.0)
+    m = Mcmc(t, nChains=1, runNum=3, sampleInterval=10, checkPointInterval=None)
+    m.prob.compLocation = 1.0
+    m.prob.rMatrixLocation = 1.0
+    m.prob.root3 = 1.0
+    m.prob.brLen = 1.0
+    m.run(nGens)
+    _finish(m, "reference p4 Mcmc.run(%d), 1 chain, 2 comps + 2 rMatrices on the tree, compLocation / rMatrixLocation / root3 / "
+            "brLen proposals on, GTR+G4 on L_mcmc/d.nex" % nGens, seed, name)
+
+
+def mcmc_grouped_aa(nChains, nGens, seed, name):
+    """share/Examples/L_mcmc/B_grouped_aa: protein recoded to the 6 Dayhoff groups (a 6-state 'standard' datatype)."""
+    _begin(seed)
+    read(os.path.join(EX, "B_grouped_aa", "protein.nex"))
+    a = var.alignments[0]
+    a.recodeDayhoff()
+    d = Data()
+    t = func.randomTree(taxNames=d.taxNames)
+    t.data = d
+    t.newComp(free=1, spec="empirical")
+    t.newRMatrix(free=1, spec="ones")
+    t.setNGammaCat(nGammaCat=4)
+    t.newGdasrv(free=1, val=0.5)
+    t.setPInvar(free=1, val=0.2)
+    m = Mcmc(t, nChains=nChains, runNum=4, sampleInterval=10, checkPointInterval=None)
+    m.run(nGens)
+    _finish(m, "reference p4 Mcmc.run(%d), %d chains, Dayhoff-6 recoded protein (L_mcmc/B_grouped_aa), 6-state GTR+I+G4" % (nGens, nChains), seed, name)
+
+
+def mcmc_protein(nChains, nGens, seed, name, nGammaCat):
+    """Protein, LG exchangeabilities, free composition, gamma rates: with 4 categories the 20-state whole-tree
+    tensor-core kernel serves both the whole-part recomputations and the dirty paths of the reference's proposals;
+    with 1 category the per-node kernels do.  Ends with Tree.getSiteLikes on the cold chain's tree."""
+    _begin(seed)
+    read(os.path.join(EX, "B_grouped_aa", "protein.nex"))
+    d = Data()
+    t = func.randomTree(taxNames=d.taxNames)
+    t.data = d
+    t.newComp(free=1, spec="empirical")
+    t.newRMatrix(free=0, spec="lg")
+    t.setNGammaCat(nGammaCat=nGammaCat)
+    if nGammaCat > 1:
+        t.newGdasrv(free=1, val=0.5)
+    t.setPInvar(free=1, val=0.1)
+    m = Mcmc(t, nChains=nChains, runNum=5 + nGammaCat, sampleInterval=10, checkPointInterval=None)
+    m.run(nGens)
+    m.chains[0].curTree.getSiteLikes()
+    _finish(m, "reference p4 Mcmc.run(%d), %d chains, protein LG+F+I%s (L_mcmc/B_grouped_aa/protein.nex), then Tree.getSiteLikes"
+            % (nGens, nChains, "+G4" if nGammaCat > 1 else ""), seed, name)
+
+
 def mcmc_ndch2(nChains, nGens, seed, name):
     """The composition-per-node model of share/Examples/W_recipes/sMcmcNDCH2.py on the same alignment: one free
     composition on every node (NDCH2 proposals change all leaf or all internal compositions; topology moves carry the
@@ -118,3 +239,8 @@ if __name__ == "__main__":
     os.chdir(tempfile.mkdtemp())
     mcmc_simple(2, 120, 11, "trace_mcmc_gtr_i_g4.json.gz")
     mcmc_ndch2(2, 100, 12, "trace_mcmc_ndch2.json.gz")
+    mcmc_two_parts(2, 100, 13, "trace_mcmc_two_parts_relrate.json.gz")
+    mcmc_locations_polytomy(150, 14, "trace_mcmc_locations_root3.json.gz")
+    mcmc_grouped_aa(2, 80, 15, "trace_mcmc_grouped_aa.json.gz")
+    mcmc_protein(2, 80, 16, "trace_mcmc_protein_lg_i_g4.json.gz", 4)
+    mcmc_protein(1, 60, 17, "trace_mcmc_protein_lg_i.json.gz", 1)
