@@ -232,6 +232,25 @@ double p4b_logLikeForParameters(p4b_tree t, int doBrLens, const double *x);   /*
  * parent to the root.  maxPasses passes over all branches or until a pass gains less than tol.  Returns
  * the final log-likelihood (NaN on error); *nEvals receives the number of likelihood evaluations. */
 double p4b_optimizeBrLens(p4b_tree t, int maxPasses, double tol, long *nEvals);
+/* ---- Newton-Raphson on the branch lengths --- Pf/p4_treeNewt.c -- */
+/* pf.p4_newtSetup(tree) Pf/pfmodule.c:2298 -> p4_newtSetup Pf/p4_treeNewt.c:11-75: allocates cl2 (per node,
+ * the conditional likelihoods of everything on the far side of the node's branch) and the work space of the
+ * first- and second-derivative P decks.  Idempotent.  Fails on a tree whose root is a leaf (the reference's
+ * p4_setCL2Up exits there, Pf/p4_node.c:905-908) and on trees created with scalers. */
+int p4b_newtSetup(p4b_tree t);
+/* p4_newtAround(tree, epsilon, likeDelta) Pf/p4_treeNewt.c:78-205, called by p4_newtAndBrentPowellOpt /
+ * p4_newtAndBOBYQAOpt (Pf/p4_treeOpt.c:755-945, 1182-1330): rounds over all branches in postOrder; per branch
+ * p4_newtNode (:210-600) iterates v <- v - lnL'/lnL'' (guards: lnL'' >= 0 -> v/5, BRLEN_MIN, 5 x the old length,
+ * BRLEN_MAX, 20 iterations, |lnL'| < epsilon) on derivatives computed from cl2 and the node's CL in one pass;
+ * a round ends with p4_treeLogLike and the rounds stop when it moves by less than likeDelta (20 at most).
+ * P decks must be current (p4_setPrams) as in the reference.  Returns the final log-likelihood (NaN on error). */
+double p4b_newtAround(p4b_tree t, double epsilon, double likeDelta);
+/* Inspection: {lnL, d lnL/dv, d2 lnL/dv2} in the length v of the node's branch at its current value
+ * (the quantities p4_newtNode forms, Pf/p4_treeNewt.c:508-517), cl2 recomputed from the root's child down;
+ * the node's cl2 [nCat*dim][nPatterns of this shard]; the number of derivative evaluations so far. */
+int p4b_newtDerivs(p4b_node n, double out3[3]);
+int p4b_getNodeCL2(p4b_node n, int pNum, double *out);
+long long p4b_newtIterations(p4b_tree t);
 int p4b_treePassLimit(p4b_tree t);   /* var.newtAndBrentPowellOptPassLimit as given to p4_newTree */
 int p4b_treeNNodes(p4b_tree t);
 int p4b_getBrLens(p4b_tree t, double *outNNodes);                            /* pf.p4_getBrLens :2279; root slot = -1 */

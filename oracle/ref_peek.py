@@ -73,3 +73,37 @@ def node_bigP(cNode, pNum, nCat, dim):
     for c in range(nCat):
         out[c] = np.ctypeslib.as_array(nd.bigPDecks[pNum][c][0], shape=(dim * dim,)).reshape(dim, dim)
     return out
+
+
+def node_cl2(cNode, pNum, nCat, dim, nChar, nPatterns):
+    """cl2[cat][state][pattern] of one reference node (after p4_newtSetup; Pf/pftypes.h:134)."""
+    nd = NodeStruct.from_address(cNode)
+    out = np.empty((nCat, dim, nPatterns))
+    for c in range(nCat):
+        m = nd.cl2[pNum][c]
+        out[c] = np.ctypeslib.as_array(m[0], shape=(dim * nChar,)).reshape(dim, nChar)[:, :nPatterns]
+    return out
+
+
+def node_brlen(cNode):
+    return float(NodeStruct.from_address(cNode).brLen[0])
+
+
+_newt_lib = None
+
+
+def newt_lib():
+    """The reference engine's Newton-Raphson entry points, which its pf module does not wrap one by one
+    (Pf/p4_tree.h:50-51, Pf/p4_treeNewt.c): p4_newtAround, p4_newtNode, p4_setNodeCL2."""
+    global _newt_lib
+    if _newt_lib is None:
+        import ref_loader
+        lib = C.CDLL(ref_loader.ref_pf_path())
+        lib.p4_newtAround.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        lib.p4_newtAround.restype = None
+        lib.p4_newtNode.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        lib.p4_newtNode.restype = None
+        lib.p4_setNodeCL2.argtypes = [C.c_void_p, C.c_void_p]
+        lib.p4_setNodeCL2.restype = None
+        _newt_lib = lib
+    return _newt_lib

@@ -192,6 +192,11 @@ void setFusedAAEnabled(int on);
 void setMemoizeEnabled(int on);
 int treesPartLogLike(Tree **trees, int n, int p, double *out);
 int treePartLogLikeBegin(Tree *t, int p);
+int treeNewtSetup(Tree *t);
+double treeNewtAround(Tree *t, double epsilon, double likeDelta);
+int nodeNewtDerivs(Node *n, double out[3]);
+int nodeGetCL2(Node *n, int pNum, double *out);
+long long treeNewtIterations(Tree *t);
 
 // comm.cpp -- NCCL, loaded at run time
 int commGetUniqueId(char id128[128]);

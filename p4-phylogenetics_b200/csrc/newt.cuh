@@ -1,0 +1,254 @@
+// newt.cuh -- sm_100a FP64 kernels of the Newton-Raphson branch-length step.
+//
+//   newt_deck_kernel   P(t), dP/dv, d2P/dv2 of ONE branch at a trial length, plus the three leaf lookup
+//                      tables when the node is a leaf   (Pf/eig.c:163-191, 294-318, 346-371;
+//                                                        Pf/p4_node.c:296-346, 442-540)
+//   transpose_deck_kernel   P^T of a node's deck: the "up" term of a child's cl2 is a CL-kernel child
+//                      whose matrix is the parent's P transposed (Pf/p4_node.c:883-928 p4_setCL2Up)
+//   newt_kernel        per pattern: like, d like, d2 like through the branch from cl2 (everything on the
+//                      far side of the branch) and the node's own CL or tip; folds
+//                      sum count*log(like), sum count*(f/l), sum count*((s*l - f*f)/(l*l))
+//                                                       (Pf/p4_treeNewt.c:210-533 p4_newtNode)
+//   newt_final_kernel  fixed-order fold of the per-block partials
+//
+// cl2 arrays have the layout of CL arrays ([cat*dim + state][pattern], row stride ps) and are computed by
+// the per-node CL kernels of kernels.cuh: cl2(n) = up(parent) * prod over siblings (P_s x cl_s), where
+// up(parent) is pi_root when the parent is the root (a "leaf" child whose table holds pi in every column,
+// Pf/p4_node.c:860-881) and P_parent^T x cl2(parent) otherwise.
+#pragma once
+#include <cstdint>
+
+namespace p4b {
+
+struct NewtDeckJob {
+    const double *eig;     // V | Vinv | lambda
+    const uint64_t *eq;    // masks of the part's non-N-like equates
+    double *decks;         // out: [3][nCat][dim][dim], then (tblW > 0) [3][nCat][dim][tblW]
+    int dim, nCat, tblW;
+    double t0[16];         // effective branch length per category as P(t) forms it (Pf/p4_node.c:321-345)
+    double t1[16];         // ... as the derivative decks form it (:456-485): the same number up to association
+    double r1[16];         // factor of the first derivative per category (Pf/p4_node.c:456-485)
+    double r2[16];         // factor of the second derivative per category, squared by the kernel (:505-534)
+};
+
+__global__ void __launch_bounds__(256)
+newt_deck_kernel(const NewtDeckJob job)
+{
+    extern __shared__ double sExp[];   // [nCat][dim] for P, then [nCat][dim] for the derivatives
+    const int dim = job.dim, nCat = job.nCat;
+    double *sExpD = sExp + nCat * dim;
+    const double *V = job.eig;
+    const double *Vi = V + dim * dim;
+    const double *lam = Vi + dim * dim;
+    for (int i = threadIdx.x; i < nCat * dim; i += blockDim.x) {
+        sExp[i] = exp(lam[i % dim] * job.t0[i / dim]);
+        sExpD[i] = exp(lam[i % dim] * job.t1[i / dim]);
+    }
+    __syncthreads();
+    const int n = nCat * dim * dim;
+    double *D0 = job.decks, *D1 = D0 + n, *D2 = D1 + n;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int c = idx / (dim * dim), ij = idx - c * dim * dim, i = ij / dim, j = ij - i * dim;
+        const double r1 = job.r1[c], r2 = job.r2[c];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < dim; k++) {
+            // the reference's association: V[i][k] * Vinv[k][j] * lambda * rate * exp(lambda t)
+            const double vv = __dmul_rn(V[i * dim + k], Vi[k * dim + j]);
+            const double e = sExpD[c * dim + k], l = lam[k];
+            s0 = fma(vv, sExp[c * dim + k], s0);                   // identical to pmatrix_kernel
+            s1 += __dmul_rn(__dmul_rn(__dmul_rn(vv, l), r1), e);
+            s2 += __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(vv, l), l), r2), r2), e);
+        }
+        D0[idx] = s0;
+        D1[idx] = s1;
+        D2[idx] = s2;
+    }
+    if (job.tblW > 0) {
+        __syncthreads();   // the block's own global writes are visible after the barrier
+        const int W = job.tblW;
+        const int nT = nCat * dim * W;
+        double *T = D2 + n;
+        for (int idx = threadIdx.x; idx < 3 * nT; idx += blockDim.x) {
+            const int d = idx / nT, r = idx - d * nT, k = r / W, w = r - k * W;   // k = cat*dim + from
+            const double *D = job.decks + (size_t)d * n + (size_t)k * dim;
+            double v = 0.0;
+            if (w < dim) v = D[w];
+            else if (w == dim) {
+                // gap, '?', N-like equates: the likelihood term is 1 (Pf/p4_treeNewt.c:292-306), the
+                // derivative terms are the row sums of the derivative decks
+                if (d == 0) v = 1.0;
+                else
+                    for (int x = 0; x < dim; x++) v += D[x];
+            } else {
+                const uint64_t m = job.eq[w - dim - 1];
+                for (int x = 0; x < dim; x++)
+                    if ((m >> x) & 1ull) v += D[x];
+            }
+            T[idx] = v;
+        }
+    }
+}
+
+// PT[cat][to][from] = P[cat][from][to]
+__global__ void __launch_bounds__(256)
+transpose_deck_kernel(const double *__restrict__ P, double *__restrict__ PT, int dim, int nCat)
+{
+    const int n = nCat * dim * dim;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int c = idx / (dim * dim), ij = idx - c * dim * dim, i = ij / dim, j = ij - i * dim;
+        PT[((size_t)c * dim + j) * dim + i] = P[idx];
+    }
+}
+
+struct NewtArgs {
+    const double *cl2;         // [nCat*dim][ps] of the node
+    const double *cl;          // internal node: its CL; NULL for a leaf
+    const uint8_t *tips;       // leaf: its tip code indices
+    const double *decks;       // newt_deck_kernel's output
+    const int *counts;
+    const uint64_t *invarMask;
+    double *partials;          // [3*gridDim.x]
+    int ps, nPat, dim, nCat, tblW, useSmem;
+    double pInvar;
+    double pi[64];             // the root's composition (constant-site term, Pf/p4_treeNewt.c:385-391)
+};
+
+// DIM > 0: the node's CL of one category is held in registers; DIM == 0: any dim, re-read through L1.
+template <int DIM>
+__global__ void __launch_bounds__(128)
+newt_kernel(const NewtArgs a)
+{
+    extern __shared__ double sD[];
+    __shared__ double sRed[3][4];
+    const int dim = DIM ? DIM : a.dim, nCat = a.nCat, W = a.tblW;
+    const bool leaf = a.cl == nullptr;
+    // a leaf needs the three tables only, an internal node the three decks only
+    const int per = leaf ? nCat * dim * W : nCat * dim * dim;
+    const double *src = leaf ? a.decks + (size_t)3 * nCat * dim * dim : a.decks;
+    const double *D = src;
+    if (a.useSmem) {
+        for (int i = threadIdx.x; i < 3 * per; i += blockDim.x) sD[i] = src[i];
+        __syncthreads();
+        D = sD;
+    }
+    const int pat = blockIdx.x * blockDim.x + threadIdx.x;
+    double tL = 0.0, tF = 0.0, tS = 0.0;
+    if (pat < a.nPat) {
+        const size_t ps = (size_t)a.ps;
+        double likeS = 0.0, firstS = 0.0, secondS = 0.0;
+        const int code = leaf ? a.tips[pat] : 0;
+        for (int c = 0; c < nCat; c++) {
+            double like = 0.0, first = 0.0, second = 0.0;
+            const double *z = a.cl2 + (size_t)c * dim * ps + pat;
+            if (leaf) {
+                const double *T0 = D + (size_t)c * dim * W + code, *T1 = T0 + per, *T2 = T1 + per;
+                for (int f = 0; f < dim; f++) {
+                    const double zz = z[f * ps];
+                    like = fma(zz, T0[f * W], like);
+                    first = fma(zz, T1[f * W], first);
+                    second = fma(zz, T2[f * W], second);
+                }
+            } else {
+                const double *x = a.cl + (size_t)c * dim * ps + pat;
+                const double *D0 = D + (size_t)c * dim * dim, *D1 = D0 + per, *D2 = D1 + per;
+                if (DIM) {
+                    double xr[DIM ? DIM : 1];
+#pragma unroll
+                    for (int t = 0; t < DIM; t++) xr[t] = x[t * ps];
+                    for (int f = 0; f < DIM; f++) {
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                        for (int t = 0; t < DIM; t++) {
+                            a0 = fma(D0[f * DIM + t], xr[t], a0);
+                            a1 = fma(D1[f * DIM + t], xr[t], a1);
+                            a2 = fma(D2[f * DIM + t], xr[t], a2);
+                        }
+                        const double zz = z[f * ps];
+                        like = fma(zz, a0, like);
+                        first = fma(zz, a1, first);
+                        second = fma(zz, a2, second);
+                    }
+                } else {
+                    for (int f = 0; f < dim; f++) {
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                        for (int t = 0; t < dim; t++) {
+                            const double xt = x[t * ps];
+                            a0 = fma(D0[f * dim + t], xt, a0);
+                            a1 = fma(D1[f * dim + t], xt, a1);
+                            a2 = fma(D2[f * dim + t], xt, a2);
+                        }
+                        const double zz = z[f * ps];
+                        like = fma(zz, a0, like);
+                        first = fma(zz, a1, first);
+                        second = fma(zz, a2, second);
+                    }
+                }
+            }
+            likeS += like;
+            firstS += first;
+            secondS += second;
+        }
+        if (a.pInvar != 0.0) {                      // Pf/p4_treeNewt.c:380-391
+            const double f = (1.0 - a.pInvar) / (double)nCat;
+            likeS *= f;
+            firstS *= f;
+            secondS *= f;
+            const uint64_t im = a.invarMask ? a.invarMask[pat] : 0ull;
+            if (im)
+                for (int s = 0; s < dim; s++)
+                    if ((im >> s) & 1ull) likeS += a.pi[s] * a.pInvar;
+        } else if (nCat > 1) {                       // :501-505
+            likeS /= (double)nCat;
+            firstS /= (double)nCat;
+            secondS /= (double)nCat;
+        }
+        const double cnt = (double)a.counts[pat];
+        if (likeS < 1.0e-300) {                      // :508-512
+            tL = cnt * -100000.0;
+            tF = cnt * 1000000.0;
+            tS = cnt * 10000000.0;
+        } else {                                     // :513-517
+            tL = cnt * log(likeS);
+            tF = cnt * (firstS / likeS);
+            tS = cnt * ((secondS * likeS - firstS * firstS) / (likeS * likeS));
+        }
+    }
+    tL = warpSum(tL);
+    tF = warpSum(tF);
+    tS = warpSum(tS);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sRed[0][w] = tL; sRed[1][w] = tF; sRed[2][w] = tS; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) v += sRed[threadIdx.x][i];
+        a.partials[3 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+// One block folds the per-block partials in a fixed order (deterministic): result[0..2].
+__global__ void __launch_bounds__(256)
+newt_final_kernel(const double *__restrict__ partials, int n, double *__restrict__ result)
+{
+    __shared__ double sRed[3][8];
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        v[0] += partials[3 * i];
+        v[1] += partials[3 * i + 1];
+        v[2] += partials[3 * i + 2];
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        v[k] = warpSum(v[k]);
+        if (l == 0) sRed[k][w] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int i = 0; i < 8; i++) s += sRed[threadIdx.x][i];
+        result[threadIdx.x] = s;
+    }
+}
+
+}  // namespace p4b

@@ -299,6 +299,27 @@ double p4b_optimizeBrLens(p4b_tree t, int maxPasses, double tol, long *nEvals)
     if (nEvals) *nEvals = 0;
     return optimizeBrLens((Tree *)t, maxPasses < 1 ? 1 : maxPasses, tol, nEvals);
 }
+int p4b_newtSetup(p4b_tree t)
+{
+    if (!t) { setError("p4b_newtSetup: NULL handle"); return 1; }
+    return treeNewtSetup((Tree *)t);
+}
+double p4b_newtAround(p4b_tree t, double epsilon, double likeDelta)
+{
+    if (!t) { setError("p4b_newtAround: NULL handle"); return NAN; }
+    return treeNewtAround((Tree *)t, epsilon, likeDelta);
+}
+int p4b_newtDerivs(p4b_node n, double out3[3])
+{
+    if (!n || !out3) { setError("p4b_newtDerivs: NULL argument"); return 1; }
+    return nodeNewtDerivs((Node *)n, out3);
+}
+int p4b_getNodeCL2(p4b_node n, int pNum, double *out)
+{
+    if (!n || !out) { setError("p4b_getNodeCL2: NULL argument"); return 1; }
+    return nodeGetCL2((Node *)n, pNum, out);
+}
+long long p4b_newtIterations(p4b_tree t) { return t ? treeNewtIterations((Tree *)t) : 0; }
 int p4b_treePassLimit(p4b_tree t)
 {
     Tree *T = (Tree *)t;

@@ -26,6 +26,7 @@
 #include "../../include/p4b200.h"
 #include "engine.h"
 #include "kernels.cuh"
+#include "newt.cuh"
 
 namespace p4b {
 
@@ -288,7 +289,9 @@ struct TreeDevice {
     bool clTimed = false;
     int lastCLLaunches = 0;
     long long bytes = 0;
+    struct NewtState *newt = nullptr;   // work arrays of the Newton-Raphson branch-length step (p4b_newtSetup)
 };
+static void newtStateFree(TreeDevice *d);
 
 int treeDeviceCreate(Tree *t)
 {
@@ -397,6 +400,7 @@ void treeDeviceDestroy(Tree *t)
         L.own.reset();
         L.twin.reset();
     }
+    newtStateFree(d);
     if (d->P) cudaFree(d->P);
     if (d->tbl) cudaFree(d->tbl);
     if (d->aux) cudaFree(d->aux);
@@ -1868,6 +1872,415 @@ int treeFlushL2(Tree *t)
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------
+// Newton-Raphson on the branch lengths (Pf/p4_treeNewt.c)
+//
+// The reference keeps, beside every node's CL (everything below the node), a second array cl2
+// (everything on the other side of the node's branch), so that the likelihood and its first two
+// derivatives in ONE branch length are a single pass over two arrays -- no walk to the root.  It goes
+// round the tree in post-order; thanks to that order every cl2 and every CL is computed once per round
+// (Pf/p4_treeNewt.c:81-172).  Here cl2 arrays live in an arena of their own, are computed by the per-node
+// CL kernels (the parent's contribution is a child with a transposed deck, or a table of pi at the root),
+// and each Newton iteration is newt_deck_kernel + newt_kernel + fold + one 24-byte read-back per part.
+// ---------------------------------------------------------------------------
+struct NewtState {
+    int nSlots = 0;                         // one per non-leaf node; the leaves share the root's (the root has no cl2)
+    std::vector<int> slotOf;                // per node number
+    std::vector<double *> cl2;              // per part: [nSlots][clNodeDoubles]
+    double *PT = nullptr;                   // [pNodeDoubles]: transposed deck of the parent whose child's cl2 is being set
+    double *rootTbl = nullptr;              // [tblNodeDoubles]: per part T[k][w] = pi_root[state of k] in every column
+    double *decks = nullptr;                // per part, at deckOff[p]: newt_deck_kernel's output
+    std::vector<size_t> deckOff;
+    double *partials = nullptr;             // per part, at 3*maxBlocks*p
+    int maxBlocks = 0;
+    double *result = nullptr, *hResult = nullptr;   // [3*nParts]
+    std::vector<char> cl2NeedsUpdating;
+    long long iters = 0;                    // derivative evaluations so far
+};
+
+static void newtStateFree(TreeDevice *d)
+{
+    NewtState *s = d->newt;
+    if (!s) return;
+    for (double *b : s->cl2)
+        if (b) cudaFree(b);
+    if (s->PT) cudaFree(s->PT);
+    if (s->rootTbl) cudaFree(s->rootTbl);
+    if (s->decks) cudaFree(s->decks);
+    if (s->partials) cudaFree(s->partials);
+    if (s->result) cudaFree(s->result);
+    if (s->hResult) cudaFreeHost(s->hResult);
+    delete s;
+    d->newt = nullptr;
+}
+
+// pf.p4_newtSetup (Pf/p4_treeNewt.c:11-75): allocate cl2 and the derivative decks, once per tree.
+int treeNewtSetup(Tree *t)
+{
+    if (!t->dev) { setError("tree has no device state"); return 1; }
+    TreeDevice *d = t->dev;
+    if (d->newt) return 0;
+    if (!t->root) { setError("p4_newtSetup: the tree has no root"); return 1; }
+    if (t->root->isLeaf) { setError("p4_newtSetup: the root is a leaf; the reference's cl2 recursion does not handle that either (Pf/p4_node.c:905-908)"); return 1; }
+    if (d->scalers) { setError("p4_newtSetup: not available on trees created with per-pattern scalers"); return 1; }
+    std::unique_ptr<NewtState> s(new NewtState());
+    s->slotOf.assign(t->nNodes, -1);
+    int next = 0;
+    for (Node *n : t->nodes)
+        if (n && !n->isLeaf) s->slotOf[n->nodeNum] = next++;
+    if (next == 0) { setError("p4_newtSetup: the tree has no internal node"); return 1; }
+    s->nSlots = next;
+    const int shared = s->slotOf[t->root->nodeNum];
+    for (Node *n : t->nodes)
+        if (n && n->isLeaf) s->slotOf[n->nodeNum] = shared;
+    s->cl2.assign(t->nParts, nullptr);
+    s->deckOff.assign(t->nParts, 0);
+    size_t deckTotal = 0;
+    long long bytes = 0;
+    d->newt = s.release();
+    NewtState *S = d->newt;
+    for (int p = 0; p < t->nParts; p++) {
+        PartLayout &L = d->parts[p];
+        if (L.nCat > 16) { setError("p4_newtSetup: more than 16 rate categories"); newtStateFree(d); return 1; }
+        const size_t b = L.clNodeDoubles * sizeof(double) * (size_t)S->nSlots;
+        if (cudaMalloc(&S->cl2[p], b) != cudaSuccess) {
+            cudaGetLastError();
+            setError("p4_newtSetup: cannot allocate %zu bytes for cl2 of part %d", b, p);
+            newtStateFree(d);
+            return 1;
+        }
+        bytes += (long long)b;
+        S->deckOff[p] = deckTotal;
+        deckTotal += (size_t)3 * L.nCat * L.dim * (L.dim + L.W);
+        const int blocks = (L.ps + 127) / 128;
+        if (blocks > S->maxBlocks) S->maxBlocks = blocks;
+    }
+    bool ok = cudaMalloc(&S->PT, d->pNodeDoubles * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&S->rootTbl, d->tblNodeDoubles * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&S->decks, deckTotal * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&S->partials, sizeof(double) * 3 * (size_t)S->maxBlocks * t->nParts) == cudaSuccess &&
+              cudaMalloc(&S->result, sizeof(double) * 3 * t->nParts) == cudaSuccess &&
+              cudaMallocHost(&S->hResult, sizeof(double) * 3 * t->nParts) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        setError("p4_newtSetup: cannot allocate the derivative decks");
+        newtStateFree(d);
+        return 1;
+    }
+    S->cl2NeedsUpdating.assign(t->nNodes, 0);
+    d->bytes += bytes;
+    return 0;
+}
+
+static inline double *nodeCL2(Node *n, int p)
+{
+    TreeDevice *d = n->tree->dev;
+    return d->newt->cl2[p] + d->parts[p].clNodeDoubles * (size_t)d->newt->slotOf[n->nodeNum];
+}
+
+// The root's composition as a leaf lookup table (every column the same), refreshed at the start of every
+// round: the compositions are borrowed buffers and may have changed since.
+static int newtUploadRootTables(Tree *t)
+{
+    TreeDevice *d = t->dev;
+    for (int p = 0; p < t->nParts; p++) {
+        PartLayout &L = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        const int rc = t->root->compNums[p];
+        if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+        std::vector<double> T(L.tblDoubles);
+        for (int k = 0; k < L.nCat * L.dim; k++)
+            for (int w = 0; w < L.W; w++) T[(size_t)k * L.W + w] = mp->comps[rc].val[k % L.dim];
+        void *src = nullptr;
+        if (stage(T.data(), T.size() * sizeof(double), &src)) return 1;
+        CUDA_TRY(cudaMemcpyAsync(d->newt->rootTbl + L.tblOff, src, T.size() * sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
+    }
+    return 0;
+}
+
+// p4_setNodeCL2 (Pf/p4_treeNewt.c:603-624): cl2 of n = what arrives at n's parent from everywhere but n.
+static int newtSetCL2(Tree *t, Node *n)
+{
+    TreeDevice *d = t->dev;
+    NewtState *S = d->newt;
+    Node *par = n->parent;
+    if (!par) { setError("p4_setNodeCL2: node %d has no parent", n->nodeNum); return 1; }
+    if (flushPJobs()) return 1;
+    for (int p = 0; p < t->nParts; p++) {
+        if (treeEnsureResident(t, p)) return 1;
+        PartLayout &L = d->parts[p];
+        Part *dp = t->data->parts[p];
+        CLArgs a;
+        memset(&a, 0, sizeof(a));
+        a.out = nodeCL2(n, p);
+        a.ps = L.ps;
+        a.dim = L.dim;
+        a.nCat = L.nCat;
+        a.tblW = L.W;
+        int k = 0;
+        if (par == t->root) {        // p4_initializeCL2ToRootComp, Pf/p4_node.c:860-881
+            a.ch[k].tips = dp->dev.tips;
+            a.ch[k].tbl = S->rootTbl + L.tblOff;
+        } else {                     // p4_setCL2Up, Pf/p4_node.c:883-928: sum_from P_par[from][s] * cl2_par[from]
+            double *PT = S->PT + L.pOff;
+            transpose_deck_kernel<<<(L.nCat * L.dim * L.dim + 255) / 256, 256, 0, G.stream>>>(nodeP(par, p), PT, L.dim, L.nCat);
+            CUDA_TRY(cudaGetLastError());
+            G.launches++;
+            a.ch[k].cl = nodeCL2(par, p);
+            a.ch[k].P = PT;
+        }
+        k++;
+        for (Node *c = par->leftChild; c; c = c->sibling) {   // p4_setCL2Down for every sibling, :614-620
+            if (c == n) continue;
+            if (k == kMaxChildren) {
+                a.nChildren = k;
+                if (launchCL(a)) return 1;
+                a.accumulate = 1;
+                k = 0;
+            }
+            CLChild &ch = a.ch[k];
+            memset(&ch, 0, sizeof(ch));
+            if (c->isLeaf) {
+                if (c->seqNum < 0 || c->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", c->nodeNum, c->seqNum); return 1; }
+                ch.tips = dp->dev.tips + (size_t)c->seqNum * L.ps;
+                ch.tbl = nodeTbl(c, p);
+            } else {
+                if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return 1; }
+                ch.cl = nodeCL(c, p);
+                ch.P = nodeP(c, p);
+            }
+            k++;
+        }
+        if (k > 0) {
+            a.nChildren = k;
+            if (launchCL(a)) return 1;
+        }
+    }
+    S->cl2NeedsUpdating[n->nodeNum] = 0;
+    return 0;
+}
+
+// lnL, d lnL / dv, d2 lnL / dv2 in the length v of n's branch, everything else fixed (the body of the
+// loop of p4_newtNode, Pf/p4_treeNewt.c:238-520).  cl2 of n and the CL of n must be current.
+static int newtDerivs(Tree *t, Node *n, double out[3])
+{
+    TreeDevice *d = t->dev;
+    NewtState *S = d->newt;
+    if (flushPJobs()) return 1;
+    for (int p = 0; p < t->nParts; p++) {
+        if (treeEnsureResident(t, p)) return 1;
+        PartLayout &L = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        Part *dp = t->data->parts[p];
+        const int c = n->compNums[p], r = n->rMatrixNums[p];
+        if (c < 0 || c >= mp->nComps || r < 0 || r >= mp->nRMatrices) { setError("node %d part %d uses comp %d rMatrix %d which do not exist", n->nodeNum, p, c, r); return 1; }
+        if (mp->bQETneedsReset[c * mp->nRMatrices + r])
+            if (resetBQET(t->model, p, c, r)) return 1;
+        if (eigEnsureUploaded(t, p, c, r)) return 1;
+        const Gdasrv *g = nullptr;
+        if (mp->nGdasrvs) {
+            const int gi = n->gdasrvNums[p];
+            if (gi < 0 || gi >= mp->nGdasrvs || !mp->gdasrvs[gi]) { setError("node %d part %d uses gdasrv %d which does not exist", n->nodeNum, p, gi); return 1; }
+            g = mp->gdasrvs[gi];
+        }
+        NewtDeckJob j;
+        memset(&j, 0, sizeof(j));
+        j.eig = d->eig + L.eigOff + L.eigStride * (size_t)(c * mp->nRMatrices + r);
+        j.eq = d->eqMasks + L.eqOff;
+        j.decks = S->decks + S->deckOff[p];
+        j.dim = L.dim;
+        j.nCat = L.nCat;
+        j.tblW = n->isLeaf ? L.W : 0;
+        for (int cat = 0; cat < mp->nCat; cat++) {
+            // P itself as p4_calculateBigPDecksPart forms its argument (Pf/p4_node.c:321-345); the derivative
+            // decks as p4_calculateBigPDecks_1stD / _2ndD form theirs (:456-485, :505-534) -- including the
+            // second derivative's extra relRate factor in the gamma, no-pInvar branch (:510-514)
+            if (mp->pInvar == 0.0) {
+                if (g) {
+                    const double temp = g->rates[cat] * mp->relRate;
+                    j.t0[cat] = n->brLen * g->rates[cat] * mp->relRate;
+                    j.t1[cat] = n->brLen * temp;
+                    j.r1[cat] = temp;
+                    j.r2[cat] = temp * mp->relRate;
+                } else {
+                    j.t0[cat] = j.t1[cat] = n->brLen * mp->relRate;
+                    j.r1[cat] = j.r2[cat] = mp->relRate;
+                }
+            } else {
+                if (g) {
+                    const double temp = g->rates[cat] * mp->relRate;
+                    j.t0[cat] = (n->brLen * g->rates[cat] * mp->relRate) / (1.0 - mp->pInvar);
+                    j.t1[cat] = (n->brLen * temp) / (1.0 - mp->pInvar);
+                    j.r1[cat] = j.r2[cat] = temp / (1.0 - mp->pInvar);
+                } else {
+                    j.t0[cat] = j.t1[cat] = (n->brLen * mp->relRate) / (1.0 - mp->pInvar);
+                    j.r1[cat] = j.r2[cat] = mp->relRate / (1.0 - mp->pInvar);
+                }
+            }
+        }
+        newt_deck_kernel<<<1, 256, 2 * L.nCat * L.dim * sizeof(double), G.stream>>>(j);
+        CUDA_TRY(cudaGetLastError());
+        NewtArgs a;
+        memset(&a, 0, sizeof(a));
+        a.cl2 = nodeCL2(n, p);
+        if (n->isLeaf) {
+            if (n->seqNum < 0 || n->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", n->nodeNum, n->seqNum); return 1; }
+            a.tips = dp->dev.tips + (size_t)n->seqNum * L.ps;
+        } else {
+            if (n->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", n->nodeNum); return 1; }
+            a.cl = nodeCL(n, p);
+        }
+        a.decks = j.decks;
+        a.counts = dp->dev.counts;
+        a.invarMask = dp->dev.invarMask;
+        a.ps = L.ps;
+        a.nPat = L.nPat;
+        a.dim = L.dim;
+        a.nCat = L.nCat;
+        a.tblW = L.W;
+        a.pInvar = mp->pInvar;
+        if (a.pInvar != 0.0 && !a.invarMask) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+        const int rc = t->root->compNums[p];
+        if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+        for (int s = 0; s < L.dim; s++) a.pi[s] = mp->comps[rc].val[s];
+        const size_t sm = (size_t)3 * L.nCat * L.dim * (n->isLeaf ? L.W : L.dim) * sizeof(double);
+        a.useSmem = sm <= 96 * 1024 ? 1 : 0;
+        const size_t smBytes = a.useSmem ? sm : 0;
+        a.partials = S->partials + (size_t)3 * S->maxBlocks * p;
+        const int blocks = (L.ps + 127) / 128;
+        static bool attrSet = false;
+        if (!attrSet) {
+            CUDA_TRY(cudaFuncSetAttribute(newt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(newt_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(newt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attrSet = true;
+        }
+        if (L.dim == 4) newt_kernel<4><<<blocks, 128, smBytes, G.stream>>>(a);
+        else if (L.dim == 20) newt_kernel<20><<<blocks, 128, smBytes, G.stream>>>(a);
+        else newt_kernel<0><<<blocks, 128, smBytes, G.stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        newt_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, S->result + 3 * p);
+        CUDA_TRY(cudaGetLastError());
+        G.launches += 3;
+    }
+    const int nRes = 3 * t->nParts;
+    if (commActive())
+        if (commAllReduceSum(S->result, nRes, (void *)G.stream)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(S->hResult, S->result, nRes * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    if (streamSync()) return 1;
+    out[0] = out[1] = out[2] = 0.0;
+    for (int p = 0; p < t->nParts; p++)
+        for (int k = 0; k < 3; k++) out[k] += S->hResult[3 * p + k];
+    S->iters++;
+    return 0;
+}
+
+// p4_newtNode (Pf/p4_treeNewt.c:210-600): Newton-Raphson on one branch length, the reference's guards.
+static int newtNode(Tree *t, Node *n, double epsilon)
+{
+    const double BRLEN_MIN = t->model->BRLEN_MIN[0], BRLEN_MAX = t->model->BRLEN_MAX[0];
+    const double oldBrLen = n->brLen;
+    double currentGuess = oldBrLen, nextGuess = 0.0;
+    int iter = 0;
+    while (true) {
+        double r[3];
+        if (newtDerivs(t, n, r)) return 1;
+        const double firstD = r[1], secondD = r[2];
+        nextGuess = currentGuess - (firstD / secondD);
+        if (secondD >= 0.0) nextGuess = currentGuess / 5.0;
+        if (nextGuess < BRLEN_MIN) { n->brLen = BRLEN_MIN; break; }
+        if (nextGuess >= 5.0 * oldBrLen) { n->brLen = 5.0 * oldBrLen; break; }
+        if (nextGuess > BRLEN_MAX) { n->brLen = BRLEN_MAX; break; }
+        if (iter > 20) { n->brLen = currentGuess; break; }
+        iter++;
+        if (fabs(firstD) < epsilon) { n->brLen = currentGuess; break; }
+        currentGuess = nextGuess;
+        n->brLen = nextGuess;
+    }
+    return nodeCalculateBigPDecks(n);
+}
+
+// p4_newtAround (Pf/p4_treeNewt.c:78-205): rounds over all branches in post-order until the
+// log-likelihood moves by less than likeDelta (at most 20 rounds).  Returns the last log-likelihood.
+double treeNewtAround(Tree *t, double epsilon, double likeDelta)
+{
+    if (!t->dev) { setError("tree has no device state"); return NAN; }
+    if (!t->dev->newt) { setError("p4_newtAround: call p4_newtSetup first"); return NAN; }
+    NewtState *S = t->dev->newt;
+    if (t->root && t->root->isLeaf) { setError("p4_newtAround: the root is a leaf"); return NAN; }
+    double previous = treeLogLike(t, 0);
+    if (previous != previous) return NAN;
+    for (Node *n : t->nodes)
+        if (n) n->clNeedsUpdating = 0;
+    std::vector<Node *> order;
+    for (int j = 0; j < t->nNodes; j++) {
+        const int i = t->postOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        Node *n = t->nodes[i];
+        if (n && n != t->root) order.push_back(n);
+    }
+    std::vector<Node *> path;
+    double thisLike = previous;
+    for (int round = 0; round < 20; round++) {
+        if (newtUploadRootTables(t)) return NAN;
+        for (Node *n : order) S->cl2NeedsUpdating[n->nodeNum] = 1;
+        for (Node *n : order) {
+            if (n->clNeedsUpdating && n->leftChild) {       // at most the one node below the branches just changed
+                for (int p = 0; p < t->nParts; p++)
+                    if (nodeSetCLImpl(n, p, false)) return NAN;
+            }
+            if (S->cl2NeedsUpdating[n->nodeNum]) {          // from the highest stale ancestor down to n
+                path.clear();
+                for (Node *q = n; q->parent && S->cl2NeedsUpdating[q->nodeNum]; q = q->parent) path.push_back(q);
+                for (size_t k = path.size(); k-- > 0;)
+                    if (newtSetCL2(t, path[k])) return NAN;
+            }
+            if (newtNode(t, n, epsilon)) return NAN;
+            for (Node *q = n->parent; q; q = q->parent) q->clNeedsUpdating = 1;
+        }
+        thisLike = treeLogLike(t, 0);
+        if (thisLike != thisLike) return NAN;
+        for (Node *n : t->nodes)
+            if (n) n->clNeedsUpdating = 0;
+        const double diff = thisLike - previous;
+        if (fabs(diff) < likeDelta) break;
+        previous = thisLike;
+    }
+    return thisLike;
+}
+
+// Test / inspection hooks: the derivatives at the node's current branch length, and its cl2.
+int nodeNewtDerivs(Node *n, double out[3])
+{
+    Tree *t = n->tree;
+    if (!t->dev || !t->dev->newt) { setError("p4b_newtDerivs: call p4_newtSetup first"); return 1; }
+    if (n == t->root || !n->parent) { setError("p4b_newtDerivs: the root has no branch"); return 1; }
+    if (treeFlushAllPending(t)) return 1;
+    if (newtUploadRootTables(t)) return 1;
+    // cl2 of every node from the root's child down to n (nothing is assumed current)
+    std::vector<Node *> path;
+    for (Node *q = n; q->parent; q = q->parent) path.push_back(q);
+    for (size_t k = path.size(); k-- > 0;)
+        if (newtSetCL2(t, path[k])) return 1;
+    return newtDerivs(t, n, out);
+}
+
+int nodeGetCL2(Node *n, int p, double *out)
+{
+    Tree *t = n->tree;
+    if (!t->dev || !t->dev->newt || p < 0 || p >= t->nParts) { setError("p4b_getNodeCL2: no Newton state or bad part"); return 1; }
+    if (n == t->root) { setError("p4b_getNodeCL2: the root has no cl2"); return 1; }
+    PartLayout &L = t->dev->parts[p];
+    std::vector<double> h(L.clNodeDoubles);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), nodeCL2(n, p), L.clNodeDoubles * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    if (streamSync()) return 1;
+    for (int k = 0; k < L.nCat * L.dim; k++) memcpy(out + (size_t)k * L.nPat, h.data() + (size_t)k * L.ps, sizeof(double) * L.nPat);
+    return 0;
+}
+
+long long treeNewtIterations(Tree *t) { return (t->dev && t->dev->newt) ? t->dev->newt->iters : 0; }
 
 void *engineStream() { return (void *)G.stream; }
 int engineInitPublic() { return engineInit(); }

@@ -143,6 +143,11 @@ _sig("p4b_logLikeForParameters", _d, _vp, _i, _vp)
 _sig("p4b_getBrLens", _i, _vp, _vp)
 _sig("p4b_optimizeBrLens", _d, _vp, _i, _d, C.POINTER(C.c_long))
 _sig("p4b_treePassLimit", _i, _vp)
+_sig("p4b_newtSetup", _i, _vp)
+_sig("p4b_newtAround", _d, _vp, _d, _d)
+_sig("p4b_newtDerivs", _i, _vp, _vp)
+_sig("p4b_getNodeCL2", _i, _vp, _i, _vp)
+_sig("p4b_newtIterations", C.c_longlong, _vp)
 _sig("p4b_treeNNodes", _i, _vp)
 _sig("p4b_copyCondLikes", _i, _vp, _vp, _i)
 _sig("p4b_copyBigPDecks", _i, _vp, _vp, _i)
@@ -609,31 +614,74 @@ def optimizeBrLens(cTree, maxPasses=1, tol=1e-6):
 
 
 def p4_newtSetup(cTree):
-    """pf.p4_newtSetup(cTree): the reference allocates the work arrays of its Newton-Raphson branch-length
-    step here (Pf/p4_treeNewt.c:11-77); this engine's one-branch objective needs none."""
+    """pf.p4_newtSetup(cTree) (Pf/pfmodule.c p4_newtSetup -> Pf/p4_treeNewt.c:11-75): allocate cl2 -- per node,
+    the conditional likelihoods of everything on the far side of its branch -- and the work space of the
+    derivative P decks on the device.  Idempotent."""
     if not cTree:
         _fatal()
+    _ok(_lib.p4b_newtSetup(cTree))
+
+
+def newtAround(cTree, epsilon, likeDelta):
+    """p4_newtAround(aTree, epsilon, likeDelta) (Pf/p4_treeNewt.c:78-205): Newton-Raphson on every branch
+    length in post-order, round after round until lnL moves by less than likeDelta.  Returns lnL."""
+    v = _lib.p4b_newtAround(cTree, float(epsilon), float(likeDelta))
+    if v != v:
+        _fatal()
+    return v
+
+
+def newtDerivs(cNode):
+    """(lnL, d lnL/dv, d2 lnL/dv2) in the length v of the node's branch, as p4_newtNode forms them."""
+    out = np.empty(3, dtype=np.float64)
+    _ok(_lib.p4b_newtDerivs(cNode, out.ctypes.data))
+    return float(out[0]), float(out[1]), float(out[2])
+
+
+def getNodeCL2(cTree, cNode, pNum, nCat, dim):
+    """cl2[cat][state][pattern] of one node for the patterns resident on this device."""
+    lo, hi = treeShardRange(cTree, pNum)
+    out = np.empty((nCat, dim, hi - lo), dtype=np.float64)
+    _ok(_lib.p4b_getNodeCL2(cNode, pNum, out.ctypes.data))
+    return out
+
+
+def newtIterations(cTree):
+    return int(_lib.p4b_newtIterations(cTree))
+
+
+def _newtSchedule(cTree, steps):
+    for eps, delta in steps:
+        lnL = newtAround(cTree, eps, delta)
+    return lnL
 
 
 def p4_newtAndBrentPowellOpt(cTree, verbose=0):
-    """pf.p4_newtAndBrentPowellOpt(cTree) (Pf/p4_treeOpt.c:755-836): alternate between the branch lengths --
-    one at a time, the reference by Newton-Raphson, here by Brent's method on the dirty-path objective --
-    and the free model parameters (the reference's parameter vector, bounded Powell), until a round gains
-    less than 1e-6 or var.newtAndBrentPowellOptPassLimit rounds have run."""
+    """pf.p4_newtAndBrentPowellOpt(cTree) (Pf/p4_treeOpt.c:1182-1330): branch lengths by Newton-Raphson
+    (p4_newtAround on the device, the reference's schedule of tolerances), free model parameters by a
+    derivative-free method on the reference's parameter vector (the reference: Brent-Powell praxis; here
+    SciPy's bounded Powell on the GPU objective), alternating until a round gains less than 1e-6 or
+    var.newtAndBrentPowellOptPassLimit rounds have run.  With no free parameter it is exactly the reference's
+    four p4_newtAround calls (:1214-1226).  Returns the number of objective evaluations of the model step."""
+    p4_newtSetup(cTree)
+    nPrams = len(windUpParameters(cTree, 0)[0])
+    if nPrams == 0:
+        _newtSchedule(cTree, ((1.0, 10.0), (1.0e-1, 1.0), (1.0e-2, 0.1), (1.0e-5, 1.0e-7)))
+        return 0
     limit = max(1, _lib.p4b_treePassLimit(cTree))
-    last = None
+    _newtSchedule(cTree, ((1.0, 10.0), (1.0e-1, 1.0), (1.0e-5, 1.0e-7)))      # :1242-1244
+    previous = p4_treeLogLike(cTree, 0)
     nEvals = 0
-    for rnd in range(limit):
-        lnL, n = optimizeBrLens(cTree, maxPasses=2, tol=1e-6)
-        nEvals += n
-        if len(windUpParameters(cTree, 0)[0]):
-            nEvals += p4_allBOBYQAOptimize(cTree, 0, ftol=1e-9)
-            lnL = p4_treeLogLike(cTree, 0)
+    for rnd in range(limit + 1):
+        newtAround(cTree, 1.0e-5, 1.0e-7)                                      # :1266
+        nEvals += p4_allBOBYQAOptimize(cTree, 0, ftol=1e-9)
+        lnL = p4_treeLogLike(cTree, 0)
         if verbose:
             print("p4_newtAndBrentPowellOpt round %d: lnL %.6f (%d evaluations so far)" % (rnd, lnL, nEvals))
-        if last is not None and lnL - last < 1.0e-6:
+        diff = lnL - previous
+        previous = lnL
+        if abs(diff) < 1.0e-6:
             break
-        last = lnL
     return nEvals
 
 
