@@ -111,7 +111,7 @@ def test_derivatives_match_finite_differences(pkg, cfg, kw):
     for n in picks:
         v = n.br.len
         l0, d1, d2 = pf.newtDerivs(n.cNode)
-        h = 1e-3 * v
+        h = max(1e-3 * v, min(1e-5, 0.1 * v))
         n.br.len = v + h
         lp = tree.calcLogLike()
         n.br.len = v - h
