@@ -253,6 +253,9 @@ int p4b_getNodeCL2(p4b_node n, int pNum, double *out);
 long long p4b_newtIterations(p4b_tree t);
 int p4b_treePassLimit(p4b_tree t);   /* var.newtAndBrentPowellOptPassLimit as given to p4_newTree */
 int p4b_treeNNodes(p4b_tree t);
+int p4b_treeNLeaves(p4b_tree t);
+int p4b_treeNParts(p4b_tree t);
+int p4b_treePartDim(p4b_tree t, int pNum);
 int p4b_getBrLens(p4b_tree t, double *outNNodes);                            /* pf.p4_getBrLens :2279; root slot = -1 */
 
 /* pf.p4_partLogLike for nTrees trees in one go -- the prop trees of Metropolis-coupled chains after
@@ -267,6 +270,15 @@ int p4b_treesPartLogLike(int nTrees, const p4b_tree *trees, int pNum, double *ou
  * p4b_treesPartLogLike including t (one copy and one synchronisation for all trees).  The host can prepare
  * the next chain's proposal while the GPU evaluates this one. */
 int p4b_partLogLikeBegin(p4b_tree t, int pNum);
+
+/* ---- consumers of the P decks beside the likelihood --- Pf/p4_treeSim.c -- */
+/* pf.p4_expectedComposition(tree) Pf/pfmodule.c:2404 -> Pf/p4_treeSim.c:951-1045, one part per call here:
+ * the root's composition pushed down every branch's P decks (p4_calculateExpectedComp, Pf/p4_node.c:1038-1250,
+ * pInvar share included), averaged over the rate categories; out[seqNum][state] for every leaf.
+ * pf.p4_expectedCompositionCounts(tree, partNum) :2384 -> :859-949: the same times the number of
+ * non-gap, non-'?' sites of the sequence.  P decks must be current (p4_setPrams). */
+int p4b_expectedComposition(p4b_tree t, int pNum, double *outNTaxTimesDim);
+int p4b_expectedCompositionCounts(p4b_tree t, int pNum, double *outNTaxTimesDim);
 
 /* ---- cur/prop state transfer ------------------------ Pf/p4_treeCopyVerify.c -- */
 int p4b_copyCondLikes(p4b_tree a, p4b_tree b, int doAll);                /* pf.p4_copyCondLikes :2445, Pf/p4_treeCopyVerify.c:7 */

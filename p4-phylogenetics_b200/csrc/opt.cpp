@@ -326,6 +326,13 @@ int p4b_treePassLimit(p4b_tree t)
     return (T && T->passLimit) ? T->passLimit[0] : 50;
 }
 int p4b_treeNNodes(p4b_tree t) { return t ? ((Tree *)t)->nNodes : -1; }
+int p4b_treeNLeaves(p4b_tree t) { return t ? ((Tree *)t)->nLeaves : -1; }
+int p4b_treeNParts(p4b_tree t) { return t ? ((Tree *)t)->nParts : -1; }
+int p4b_treePartDim(p4b_tree t, int pNum)
+{
+    Tree *T = (Tree *)t;
+    return (T && T->model && pNum >= 0 && pNum < T->nParts) ? T->model->parts[pNum]->dim : -1;
+}
 int p4b_getBrLens(p4b_tree t, double *out)
 {
     if (!t || !out) { setError("p4b_getBrLens: NULL argument"); return 1; }

@@ -143,12 +143,17 @@ _sig("p4b_logLikeForParameters", _d, _vp, _i, _vp)
 _sig("p4b_getBrLens", _i, _vp, _vp)
 _sig("p4b_optimizeBrLens", _d, _vp, _i, _d, C.POINTER(C.c_long))
 _sig("p4b_treePassLimit", _i, _vp)
+_sig("p4b_expectedComposition", _i, _vp, _i, _vp)
+_sig("p4b_expectedCompositionCounts", _i, _vp, _i, _vp)
 _sig("p4b_newtSetup", _i, _vp)
 _sig("p4b_newtAround", _d, _vp, _d, _d)
 _sig("p4b_newtDerivs", _i, _vp, _vp)
 _sig("p4b_getNodeCL2", _i, _vp, _i, _vp)
 _sig("p4b_newtIterations", C.c_longlong, _vp)
 _sig("p4b_treeNNodes", _i, _vp)
+_sig("p4b_treeNLeaves", _i, _vp)
+_sig("p4b_treeNParts", _i, _vp)
+_sig("p4b_treePartDim", _i, _vp, _i)
 _sig("p4b_copyCondLikes", _i, _vp, _vp, _i)
 _sig("p4b_copyBigPDecks", _i, _vp, _vp, _i)
 _sig("p4b_copyModelPrams", _i, _vp, _vp)
@@ -686,6 +691,27 @@ def p4_newtAndBrentPowellOpt(cTree, verbose=0):
 
 
 p4_newtAndBOBYQAOpt = p4_newtAndBrentPowellOpt
+
+
+# ---- consumers of the P decks beside the likelihood -----------------------------------------
+def _expected(cTree, pNum, fn):
+    nTax, dim = _lib.p4b_treeNLeaves(cTree), _lib.p4b_treePartDim(cTree, pNum)
+    if nTax < 0 or dim < 0:
+        _fatal()
+    out = np.zeros((nTax, dim), dtype=np.float64)
+    _ok(fn(cTree, int(pNum), out.ctypes.data))
+    return tuple(tuple(float(v) for v in row) for row in out)
+
+
+def p4_expectedComposition(cTree):
+    """pf.p4_expectedComposition(cTree) -> tuple over parts of tuple over sequences of tuple over states
+    (Pf/pfmodule.c:2404, Pf/p4_treeSim.c:951-1045): the composition the model expects at every tip."""
+    return tuple(_expected(cTree, p, _lib.p4b_expectedComposition) for p in range(_lib.p4b_treeNParts(cTree)))
+
+
+def p4_expectedCompositionCounts(cTree, partNum):
+    """pf.p4_expectedCompositionCounts(cTree, partNum) (Pf/pfmodule.c:2384, Pf/p4_treeSim.c:859-949)."""
+    return _expected(cTree, partNum, _lib.p4b_expectedCompositionCounts)
 
 
 # ---- cur/prop state transfer ------------------------------------------------------------
