@@ -128,6 +128,11 @@ int p4b_pokeSequences(p4b_part p, const char *allSequences);             /* pf.p
 int p4b_makePatterns(p4b_part p);                                        /* pf.makePatterns :186, Pf/part.c:317 */
 int p4b_setGlobalInvarSitesVec(p4b_part p);                              /* pf.setGlobalInvarSitesVec :310, Pf/part.c:716 */
 int p4b_partPatternCount(p4b_part p);                                    /* pf.partPatternCount :247 */
+/* pf.getUnconstrainedLogLike(part) :432 -> unconstrainedLogLike Pf/part.c:682-714: sum over patterns of
+ * count*log(count) - nChar*log(nChar) (the multinomial ceiling Tree.modelFitTests / Data compare lnL with,
+ * p4/data.py:223-258, p4/tree.py:8182).  Needs patterns; any gap, '?' or ambiguity is an error.
+ * Returns non-zero and leaves *out untouched on error. */
+int p4b_getUnconstrainedLogLike(p4b_part p, double *out);
 /* pf.getSiteLikes :378 -- copies part->siteLikes (nChar doubles) filled by the
  * last p4b_partLogLike(..., getSiteLikes=1).  Returns nChar, or -1 if none. */
 int p4b_getSiteLikes(p4b_part p, double *out, int nOut);

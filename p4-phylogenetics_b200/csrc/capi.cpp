@@ -74,6 +74,20 @@ int p4b_pokeSequences(p4b_part p, const char *s) { CHECK_PTR(p, "pokeSequences",
 int p4b_makePatterns(p4b_part p) { CHECK_PTR(p, "makePatterns", 1); return makePatterns((Part *)p); }
 int p4b_setGlobalInvarSitesVec(p4b_part p) { CHECK_PTR(p, "setGlobalInvarSitesVec", 1); return setGlobalInvarSitesVec((Part *)p); }
 int p4b_partPatternCount(p4b_part p) { CHECK_PTR(p, "partPatternCount", -1); return ((Part *)p)->nPatterns; }
+int p4b_getUnconstrainedLogLike(p4b_part p, double *out)
+{
+    CHECK_PTR(p, "getUnconstrainedLogLike", 1);
+    CHECK_PTR(out, "getUnconstrainedLogLike", 1);
+    Part *P = (Part *)p;
+    if (!P->nPatterns) { setError("part.c: unconstrainedLogLike: no patterns.  Needs both sequences and patterns."); return 1; }
+    for (int v : P->sequences)
+        if (v < 0) { setError("part.c: unconstrainedLogLike: bad character.  Can't do this calculation if there are any gaps, unknowns, ambiguities, or equates"); return 1; }
+    double dsum = 0.0;
+    for (int i = 0; i < P->nPatterns; i++) dsum = dsum + (P->patternCounts[i] * log((double)(P->patternCounts[i])));
+    dsum = dsum - (P->nChar * log((double)(P->nChar)));
+    *out = dsum;
+    return 0;
+}
 int p4b_getSiteLikes(p4b_part p, double *out, int nOut)
 {
     CHECK_PTR(p, "getSiteLikes", -1);

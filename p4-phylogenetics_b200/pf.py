@@ -93,6 +93,7 @@ _sig("p4b_pokeSequences", _i, _vp, _cp)
 _sig("p4b_makePatterns", _i, _vp)
 _sig("p4b_setGlobalInvarSitesVec", _i, _vp)
 _sig("p4b_partPatternCount", _i, _vp)
+_sig("p4b_getUnconstrainedLogLike", _i, _vp, _dp)
 _sig("p4b_getSiteLikes", _i, _vp, _vp, _i)
 for _n in ("Sequences", "Patterns", "PatternCounts", "SequencePositionPatternIndex", "GlobalInvarSitesVec",
            "GlobalInvarSitesArray", "Equates"):
@@ -333,6 +334,13 @@ def setGlobalInvarSitesVec(cPart):
 
 def partPatternCount(cPart):
     return _lib.p4b_partPatternCount(cPart)
+
+
+def getUnconstrainedLogLike(cPart):
+    """pf.getUnconstrainedLogLike(cPart) (Pf/pfmodule.c:432, Pf/part.c:682-714)."""
+    out = C.c_double(0.0)
+    _ok(_lib.p4b_getUnconstrainedLogLike(cPart, C.byref(out)))
+    return out.value
 
 
 def getSiteLikes(cPart):

@@ -84,6 +84,24 @@ def test_pattern_compression_bit_exact_vs_reference(pkg, ref_pf, seed, nTax, nPa
     ref_pf.freePart(theirs.cPart)
 
 
+def test_unconstrained_loglike_vs_reference(pkg, ref_pf):
+    """pf.getUnconstrainedLogLike (Pf/part.c:682-714): same number on clean data, fatal with any gap or ambiguity."""
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(8))
+    t = P.synth.random_tree(P.pf, 9, rng)
+    mp = P.synth.dna_model_part(0, rng, 4)
+    aln = P.synth.make_alignment(P.pf, t, mp, 400, rng, "dna", gap_frac=0.0, ambig_frac=0.0)
+    mine = aln._initParts()
+    theirs = P.host.Alignment(ref_pf, aln.sequences, aln.symbols, aln.equates)._initParts()
+    assert P.pf.getUnconstrainedLogLike(mine.cPart) == ref_pf.getUnconstrainedLogLike(theirs.cPart)
+    P.pf.freePart(mine.cPart)
+    ref_pf.freePart(theirs.cPart)
+    gappy = P.synth.make_alignment(P.pf, t, mp, 50, rng, "dna", gap_frac=0.1, ambig_frac=0.0)._initParts()
+    with pytest.raises(SystemExit):
+        P.pf.getUnconstrainedLogLike(gappy.cPart)
+    P.pf.freePart(gappy.cPart)
+
+
 def test_gamma_rates_bit_identical_to_reference(pkg, ref_pf):
     for alpha in (0.1, 0.2, 0.5, 0.73, 1.0, 2.7, 10.0, 100.0, 299.0):
         for K in (2, 3, 4, 5, 8, 16):
