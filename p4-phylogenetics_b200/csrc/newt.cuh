@@ -131,9 +131,8 @@ newt_kernel(const NewtArgs a)
         __syncthreads();
         D = sD;
     }
-    const int pat = blockIdx.x * blockDim.x + threadIdx.x;
     double tL = 0.0, tF = 0.0, tS = 0.0;
-    if (pat < a.nPat) {
+    for (int pat = blockIdx.x * blockDim.x + threadIdx.x; pat < a.nPat; pat += gridDim.x * blockDim.x) {
         const size_t ps = (size_t)a.ps;
         double likeS = 0.0, firstS = 0.0, secondS = 0.0;
         const int code = leaf ? a.tips[pat] : 0;
@@ -204,13 +203,13 @@ newt_kernel(const NewtArgs a)
         }
         const double cnt = (double)a.counts[pat];
         if (likeS < 1.0e-300) {                      // :508-512
-            tL = cnt * -100000.0;
-            tF = cnt * 1000000.0;
-            tS = cnt * 10000000.0;
+            tL += cnt * -100000.0;
+            tF += cnt * 1000000.0;
+            tS += cnt * 10000000.0;
         } else {                                     // :513-517
-            tL = cnt * log(likeS);
-            tF = cnt * (firstS / likeS);
-            tS = cnt * ((secondS * likeS - firstS * firstS) / (likeS * likeS));
+            tL += cnt * log(likeS);
+            tF += cnt * (firstS / likeS);
+            tS += cnt * ((secondS * likeS - firstS * firstS) / (likeS * likeS));
         }
     }
     tL = warpSum(tL);
@@ -223,6 +222,201 @@ newt_kernel(const NewtArgs a)
         double v = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); i++) v += sRed[threadIdx.x][i];
         a.partials[3 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 4 states: ONE launch per derivative evaluation.
+//   prologue  every CTA forms the three decks (and, for a leaf, the three lookup tables) of the branch in
+//             shared memory itself -- 3 x NCAT x 16 entries, the expressions of newt_deck_kernel;
+//   body      a thread owns two adjacent patterns (16-byte loads, all 8 rows of a category in flight),
+//             persistent CTAs stride over the pattern pairs;
+//   epilogue  per-CTA partials, then the LAST CTA to finish (atomic ticket) folds them in a fixed order,
+//             so the result is deterministic and no second launch is needed.
+// ---------------------------------------------------------------------------
+template <int NCAT>
+__global__ void __launch_bounds__(256)
+newt_dna_kernel(const NewtArgs a, const NewtDeckJob job, unsigned *__restrict__ ticket, double *__restrict__ result)
+{
+    extern __shared__ double sD[];          // decks [3][NCAT][4][4], then (leaf) tables [3][NCAT*4][W]
+    __shared__ double sExp[2][NCAT * 4];
+    __shared__ double sRed[3][8];
+    __shared__ bool sLast;
+    constexpr int ND = NCAT * 16;
+    const bool leaf = a.cl == nullptr;
+    const int W = a.tblW;
+    {
+        const double *V = job.eig, *Vi = V + 16, *lam = Vi + 16;
+        if (threadIdx.x < NCAT * 4) {
+            sExp[0][threadIdx.x] = exp(lam[threadIdx.x & 3] * job.t0[threadIdx.x >> 2]);
+            sExp[1][threadIdx.x] = exp(lam[threadIdx.x & 3] * job.t1[threadIdx.x >> 2]);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ND; idx += blockDim.x) {
+            const int c = idx >> 4, i = (idx >> 2) & 3, j = idx & 3;
+            const double r1 = job.r1[c], r2 = job.r2[c];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double vv = __dmul_rn(V[i * 4 + k], Vi[k * 4 + j]);
+                const double e = sExp[1][c * 4 + k], l = lam[k];
+                s0 = fma(vv, sExp[0][c * 4 + k], s0);
+                s1 += __dmul_rn(__dmul_rn(__dmul_rn(vv, l), r1), e);
+                s2 += __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(vv, l), l), r2), r2), e);
+            }
+            sD[idx] = s0;
+            sD[ND + idx] = s1;
+            sD[2 * ND + idx] = s2;
+        }
+        __syncthreads();
+        if (leaf) {
+            const int nT = NCAT * 4 * W;
+            double *T = sD + 3 * ND;
+            for (int idx = threadIdx.x; idx < 3 * nT; idx += blockDim.x) {
+                const int d = idx / nT, r = idx - d * nT, k = r / W, w = r - k * W;
+                const double *D = sD + d * ND + k * 4;
+                double v = 0.0;
+                if (w < 4) v = D[w];
+                else if (w == 4) {
+                    if (d == 0) v = 1.0;
+                    else
+                        for (int x = 0; x < 4; x++) v += D[x];
+                } else {
+                    const uint64_t m = job.eq[w - 5];
+                    for (int x = 0; x < 4; x++)
+                        if ((m >> x) & 1ull) v += D[x];
+                }
+                T[idx] = v;
+            }
+            __syncthreads();
+        }
+    }
+    const size_t ps = (size_t)a.ps;
+    const int nPairs = a.ps >> 1;
+    double tL = 0.0, tF = 0.0, tS = 0.0;
+    for (int pair = blockIdx.x * blockDim.x + threadIdx.x; pair < nPairs; pair += gridDim.x * blockDim.x) {
+        const int pat = pair * 2;
+        double2 likeS = make_double2(0.0, 0.0), firstS = likeS, secondS = likeS;
+        uchar2 code = make_uchar2(0, 0);
+        if (leaf) code = *reinterpret_cast<const uchar2 *>(a.tips + pat);
+#pragma unroll
+        for (int c = 0; c < NCAT; c++) {
+            double2 z[4];
+#pragma unroll
+            for (int f = 0; f < 4; f++) z[f] = ld2(a.cl2 + (size_t)(c * 4 + f) * ps + pat);
+            double2 like = make_double2(0.0, 0.0), first = like, second = like;
+            if (leaf) {
+                const int nT = NCAT * 4 * W;
+                const double *T0 = sD + 3 * ND + c * 4 * W, *T1 = T0 + nT, *T2 = T1 + nT;
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                    like.x = fma(z[f].x, T0[f * W + code.x], like.x);
+                    like.y = fma(z[f].y, T0[f * W + code.y], like.y);
+                    first.x = fma(z[f].x, T1[f * W + code.x], first.x);
+                    first.y = fma(z[f].y, T1[f * W + code.y], first.y);
+                    second.x = fma(z[f].x, T2[f * W + code.x], second.x);
+                    second.y = fma(z[f].y, T2[f * W + code.y], second.y);
+                }
+            } else {
+                double2 x[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) x[t] = ld2(a.cl + (size_t)(c * 4 + t) * ps + pat);
+                const double *D0 = sD + c * 16, *D1 = D0 + ND, *D2 = D1 + ND;
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const double d0 = D0[f * 4 + t], d1 = D1[f * 4 + t], d2 = D2[f * 4 + t];
+                        a0.x = fma(d0, x[t].x, a0.x);
+                        a0.y = fma(d0, x[t].y, a0.y);
+                        a1.x = fma(d1, x[t].x, a1.x);
+                        a1.y = fma(d1, x[t].y, a1.y);
+                        a2.x = fma(d2, x[t].x, a2.x);
+                        a2.y = fma(d2, x[t].y, a2.y);
+                    }
+                    like.x = fma(z[f].x, a0.x, like.x);
+                    like.y = fma(z[f].y, a0.y, like.y);
+                    first.x = fma(z[f].x, a1.x, first.x);
+                    first.y = fma(z[f].y, a1.y, first.y);
+                    second.x = fma(z[f].x, a2.x, second.x);
+                    second.y = fma(z[f].y, a2.y, second.y);
+                }
+            }
+            likeS.x += like.x;
+            likeS.y += like.y;
+            firstS.x += first.x;
+            firstS.y += first.y;
+            secondS.x += second.x;
+            secondS.y += second.y;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int pp = pat + h;
+            if (pp >= a.nPat) continue;
+            double l = h ? likeS.y : likeS.x, f1 = h ? firstS.y : firstS.x, f2 = h ? secondS.y : secondS.x;
+            if (a.pInvar != 0.0) {                      // Pf/p4_treeNewt.c:380-391
+                const double f = (1.0 - a.pInvar) / (double)NCAT;
+                l *= f;
+                f1 *= f;
+                f2 *= f;
+                const uint64_t im = a.invarMask ? a.invarMask[pp] : 0ull;
+                if (im)
+                    for (int s = 0; s < 4; s++)
+                        if ((im >> s) & 1ull) l += a.pi[s] * a.pInvar;
+            } else if (NCAT > 1) {                       // :501-505
+                l /= (double)NCAT;
+                f1 /= (double)NCAT;
+                f2 /= (double)NCAT;
+            }
+            const double cnt = (double)a.counts[pp];
+            if (l < 1.0e-300) {                          // :508-512
+                tL += cnt * -100000.0;
+                tF += cnt * 1000000.0;
+                tS += cnt * 10000000.0;
+            } else {                                     // :513-517
+                tL += cnt * log(l);
+                tF += cnt * (f1 / l);
+                tS += cnt * ((f2 * l - f1 * f1) / (l * l));
+            }
+        }
+    }
+    tL = warpSum(tL);
+    tF = warpSum(tF);
+    tS = warpSum(tS);
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (ln == 0) { sRed[0][w] = tL; sRed[1][w] = tF; sRed[2][w] = tS; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = 0; i < 8; i++) { v[0] += sRed[0][i]; v[1] += sRed[1][i]; v[2] += sRed[2][i]; }
+        a.partials[3 * blockIdx.x] = v[0];
+        a.partials[3 * blockIdx.x + 1] = v[1];
+        a.partials[3 * blockIdx.x + 2] = v[2];
+        __threadfence();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);   // wraps to 0 with the last CTA: ready for the next launch
+        sLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLast) {
+        __threadfence();
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            v[0] += __ldcg(a.partials + 3 * i);
+            v[1] += __ldcg(a.partials + 3 * i + 1);
+            v[2] += __ldcg(a.partials + 3 * i + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = warpSum(v[k]);
+            if (ln == 0) sRed[k][w] = v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double s2 = 0.0;
+            for (int i = 0; i < 8; i++) s2 += sRed[threadIdx.x][i];
+            result[threadIdx.x] = s2;
+        }
     }
 }
 

@@ -1896,6 +1896,7 @@ struct NewtState {
     double *partials = nullptr;             // per part, at 3*maxBlocks*p
     int maxBlocks = 0;
     double *result = nullptr, *hResult = nullptr;   // [3*nParts]
+    unsigned *ticket = nullptr;             // newt_dna_kernel: which CTA finished last (returns to 0 after every launch)
     std::vector<char> cl2NeedsUpdating;
     long long iters = 0;                    // derivative evaluations so far
 };
@@ -1911,6 +1912,7 @@ static void newtStateFree(TreeDevice *d)
     if (s->decks) cudaFree(s->decks);
     if (s->partials) cudaFree(s->partials);
     if (s->result) cudaFree(s->result);
+    if (s->ticket) cudaFree(s->ticket);
     if (s->hResult) cudaFreeHost(s->hResult);
     delete s;
     d->newt = nullptr;
@@ -1954,10 +1956,11 @@ int treeNewtSetup(Tree *t)
         bytes += (long long)b;
         S->deckOff[p] = deckTotal;
         deckTotal += (size_t)3 * L.nCat * L.dim * (L.dim + L.W);
-        const int blocks = (L.ps + 127) / 128;
-        if (blocks > S->maxBlocks) S->maxBlocks = blocks;
     }
-    bool ok = cudaMalloc(&S->PT, d->pNodeDoubles * sizeof(double)) == cudaSuccess &&
+    S->maxBlocks = G.numSMs * 16;           // the derivative kernels run persistent CTAs
+    bool ok = cudaMalloc(&S->ticket, sizeof(unsigned)) == cudaSuccess &&
+              cudaMemsetAsync(S->ticket, 0, sizeof(unsigned), G.stream) == cudaSuccess &&
+              cudaMalloc(&S->PT, d->pNodeDoubles * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&S->rootTbl, d->tblNodeDoubles * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&S->decks, deckTotal * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&S->partials, sizeof(double) * 3 * (size_t)S->maxBlocks * t->nParts) == cudaSuccess &&
@@ -2120,8 +2123,12 @@ static int newtDerivs(Tree *t, Node *n, double out[3])
                 }
             }
         }
-        newt_deck_kernel<<<1, 256, 2 * L.nCat * L.dim * sizeof(double), G.stream>>>(j);
-        CUDA_TRY(cudaGetLastError());
+        const bool dna = L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
+        if (!dna) {
+            newt_deck_kernel<<<1, 256, 2 * L.nCat * L.dim * sizeof(double), G.stream>>>(j);
+            CUDA_TRY(cudaGetLastError());
+            G.launches++;
+        }
         NewtArgs a;
         memset(&a, 0, sizeof(a));
         a.cl2 = nodeCL2(n, p);
@@ -2145,25 +2152,50 @@ static int newtDerivs(Tree *t, Node *n, double out[3])
         const int rc = t->root->compNums[p];
         if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
         for (int s = 0; s < L.dim; s++) a.pi[s] = mp->comps[rc].val[s];
+        a.partials = S->partials + (size_t)3 * S->maxBlocks * p;
+        if (dna) {
+            // one launch: decks in the prologue, two patterns per thread, the last CTA folds
+            const size_t smBytes = ((size_t)3 * L.nCat * 16 + (n->isLeaf ? (size_t)3 * L.nCat * 4 * L.W : 0)) * sizeof(double);
+            static int resident4 = 0, resident1 = 0;
+            int &resident = L.nCat == 4 ? resident4 : resident1;
+            if (!resident) {
+                const size_t worst = ((size_t)3 * L.nCat * 16 + (size_t)3 * L.nCat * 4 * 64) * sizeof(double);
+                if (L.nCat == 4) {
+                    CUDA_TRY(cudaFuncSetAttribute(newt_dna_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst));
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, newt_dna_kernel<4>, 256, smBytes));
+                } else {
+                    CUDA_TRY(cudaFuncSetAttribute(newt_dna_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst));
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, newt_dna_kernel<1>, 256, smBytes));
+                }
+                if (resident < 1) resident = 1;
+                if (resident > 8) resident = 8;
+            }
+            if (L.W > 64) { setError("leaf table too wide for the 4-state derivative kernel"); return 1; }
+            int grid = (L.ps / 2 + 255) / 256;
+            if (grid > G.numSMs * resident) grid = G.numSMs * resident;
+            if (L.nCat == 4) newt_dna_kernel<4><<<grid, 256, smBytes, G.stream>>>(a, j, S->ticket, S->result + 3 * p);
+            else newt_dna_kernel<1><<<grid, 256, smBytes, G.stream>>>(a, j, S->ticket, S->result + 3 * p);
+            CUDA_TRY(cudaGetLastError());
+            G.launches++;
+            continue;
+        }
         const size_t sm = (size_t)3 * L.nCat * L.dim * (n->isLeaf ? L.W : L.dim) * sizeof(double);
         a.useSmem = sm <= 96 * 1024 ? 1 : 0;
         const size_t smBytes = a.useSmem ? sm : 0;
-        a.partials = S->partials + (size_t)3 * S->maxBlocks * p;
-        const int blocks = (L.ps + 127) / 128;
+        int blocks = (L.ps + 127) / 128;
+        if (blocks > S->maxBlocks) blocks = S->maxBlocks;
         static bool attrSet = false;
         if (!attrSet) {
-            CUDA_TRY(cudaFuncSetAttribute(newt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(newt_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(newt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attrSet = true;
         }
-        if (L.dim == 4) newt_kernel<4><<<blocks, 128, smBytes, G.stream>>>(a);
-        else if (L.dim == 20) newt_kernel<20><<<blocks, 128, smBytes, G.stream>>>(a);
+        if (L.dim == 20) newt_kernel<20><<<blocks, 128, smBytes, G.stream>>>(a);
         else newt_kernel<0><<<blocks, 128, smBytes, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         newt_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, S->result + 3 * p);
         CUDA_TRY(cudaGetLastError());
-        G.launches += 3;
+        G.launches += 2;
     }
     const int nRes = 3 * t->nParts;
     if (commActive())

@@ -21,8 +21,8 @@ import numpy as np  # noqa: E402
 import p4_phylogenetics_b200 as P  # noqa: E402
 
 
-def build(pf, taxa, patterns, sd):
-    tree = P.synth.build_config(pf, 2, nTax=taxa, nPatterns=patterns)
+def build(pf, taxa, patterns, sd, cfg=2):
+    tree = P.synth.build_config(pf, cfg, nTax=taxa, nPatterns=patterns)
     rng = np.random.default_rng(7)
     start = {}
     for n in tree.iterNodesNoRoot():
@@ -39,8 +39,9 @@ def reset(tree, start):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--taxa", type=int, default=200)
-    ap.add_argument("--patterns", type=int, default=1000000)
+    ap.add_argument("--cfg", type=int, default=2, help="2: DNA GTR+G4 (200 taxa x 1M patterns); 3: protein LG+G4 (100 x 200k)")
+    ap.add_argument("--taxa", type=int, default=None)
+    ap.add_argument("--patterns", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--sd", type=float, default=0.3, help="log-normal perturbation of the starting branch lengths")
     ap.add_argument("--epsilon", type=float, default=1.0e-5)
@@ -49,13 +50,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     pf = P.pf
+    a.taxa = a.taxa or (200 if a.cfg == 2 else 100)
+    a.patterns = a.patterns or (1000000 if a.cfg == 2 else 200000)
     t0 = time.perf_counter()
-    tree, start = build(pf, a.taxa, a.patterns, a.sd)
+    tree, start = build(pf, a.taxa, a.patterns, a.sd, a.cfg)
     lnL0 = tree.calcLogLike()
     setup = time.perf_counter() - t0
     nBranches = len(start)
     nPat = pf.partPatternCount(tree.data.parts[0].cPart)
-    out = {"workload": "cfg2 shape: %d taxa, %d patterns, GTR+G4; branch lengths perturbed by exp(N(0, %.2f))" % (a.taxa, nPat, a.sd),
+    out = {"workload": "cfg%d shape: %d taxa, %d patterns, %s; branch lengths perturbed by exp(N(0, %.2f))" % (a.cfg, a.taxa, nPat, "GTR+G4" if a.cfg == 2 else "LG+G4", a.sd),
            "branches": nBranches, "lnL_start": lnL0, "setup_s": setup}
 
     pf.p4_newtSetup(tree.cTree)
@@ -85,7 +88,7 @@ def main():
         import ref_peek
         if ref_loader.have_ref_pf():
             rpf = ref_loader.load_ref_pf()
-            small, startS = build(rpf, a.taxa, min(a.cpu_sample, a.patterns), a.sd)
+            small, startS = build(rpf, a.taxa, min(a.cpu_sample, a.patterns), a.sd, a.cfg)
             small.calcLogLike()
             rpf.p4_newtSetup(small.cTree)
             w0 = time.perf_counter()
