@@ -293,34 +293,65 @@ newt_dna_kernel(const NewtArgs a, const NewtDeckJob job, unsigned *__restrict__ 
     }
     const size_t ps = (size_t)a.ps;
     const int nPairs = a.ps >> 1;
+    const int stride = gridDim.x * blockDim.x;
     double tL = 0.0, tF = 0.0, tS = 0.0;
-    for (int pair = blockIdx.x * blockDim.x + threadIdx.x; pair < nPairs; pair += gridDim.x * blockDim.x) {
+    // The rows of the NEXT rate category (or of the thread's next pattern pair) are requested before the
+    // current category is worked on: 8 (leaf: 4) 16-byte loads are always in flight behind the arithmetic.
+    int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    double2 zc[4], xc[4];
+    uchar2 codeC = make_uchar2(0, 0);
+#pragma unroll
+    for (int f = 0; f < 4; f++) zc[f] = xc[f] = make_double2(0.0, 0.0);
+    if (pair < nPairs) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) zc[f] = ld2(a.cl2 + (size_t)f * ps + 2 * pair);
+        if (leaf) codeC = *reinterpret_cast<const uchar2 *>(a.tips + 2 * pair);
+        else {
+#pragma unroll
+            for (int f = 0; f < 4; f++) xc[f] = ld2(a.cl + (size_t)f * ps + 2 * pair);
+        }
+    }
+    for (; pair < nPairs; pair += stride) {
         const int pat = pair * 2;
+        const int nextPat = (pair + stride) * 2;
+        const bool more = pair + stride < nPairs;
         double2 likeS = make_double2(0.0, 0.0), firstS = likeS, secondS = likeS;
-        uchar2 code = make_uchar2(0, 0);
-        if (leaf) code = *reinterpret_cast<const uchar2 *>(a.tips + pat);
+        uchar2 codeN = codeC;
 #pragma unroll
         for (int c = 0; c < NCAT; c++) {
-            double2 z[4];
+            double2 zn[4], xn[4];
 #pragma unroll
-            for (int f = 0; f < 4; f++) z[f] = ld2(a.cl2 + (size_t)(c * 4 + f) * ps + pat);
+            for (int f = 0; f < 4; f++) { zn[f] = zc[f]; xn[f] = xc[f]; }
+            if (c + 1 < NCAT) {
+#pragma unroll
+                for (int f = 0; f < 4; f++) zn[f] = ld2(a.cl2 + (size_t)((c + 1) * 4 + f) * ps + pat);
+                if (!leaf) {
+#pragma unroll
+                    for (int f = 0; f < 4; f++) xn[f] = ld2(a.cl + (size_t)((c + 1) * 4 + f) * ps + pat);
+                }
+            } else if (more) {
+#pragma unroll
+                for (int f = 0; f < 4; f++) zn[f] = ld2(a.cl2 + (size_t)f * ps + nextPat);
+                if (leaf) codeN = *reinterpret_cast<const uchar2 *>(a.tips + nextPat);
+                else {
+#pragma unroll
+                    for (int f = 0; f < 4; f++) xn[f] = ld2(a.cl + (size_t)f * ps + nextPat);
+                }
+            }
             double2 like = make_double2(0.0, 0.0), first = like, second = like;
             if (leaf) {
                 const int nT = NCAT * 4 * W;
                 const double *T0 = sD + 3 * ND + c * 4 * W, *T1 = T0 + nT, *T2 = T1 + nT;
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
-                    like.x = fma(z[f].x, T0[f * W + code.x], like.x);
-                    like.y = fma(z[f].y, T0[f * W + code.y], like.y);
-                    first.x = fma(z[f].x, T1[f * W + code.x], first.x);
-                    first.y = fma(z[f].y, T1[f * W + code.y], first.y);
-                    second.x = fma(z[f].x, T2[f * W + code.x], second.x);
-                    second.y = fma(z[f].y, T2[f * W + code.y], second.y);
+                    like.x = fma(zc[f].x, T0[f * W + codeC.x], like.x);
+                    like.y = fma(zc[f].y, T0[f * W + codeC.y], like.y);
+                    first.x = fma(zc[f].x, T1[f * W + codeC.x], first.x);
+                    first.y = fma(zc[f].y, T1[f * W + codeC.y], first.y);
+                    second.x = fma(zc[f].x, T2[f * W + codeC.x], second.x);
+                    second.y = fma(zc[f].y, T2[f * W + codeC.y], second.y);
                 }
             } else {
-                double2 x[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) x[t] = ld2(a.cl + (size_t)(c * 4 + t) * ps + pat);
                 const double *D0 = sD + c * 16, *D1 = D0 + ND, *D2 = D1 + ND;
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
@@ -328,19 +359,19 @@ newt_dna_kernel(const NewtArgs a, const NewtDeckJob job, unsigned *__restrict__ 
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         const double d0 = D0[f * 4 + t], d1 = D1[f * 4 + t], d2 = D2[f * 4 + t];
-                        a0.x = fma(d0, x[t].x, a0.x);
-                        a0.y = fma(d0, x[t].y, a0.y);
-                        a1.x = fma(d1, x[t].x, a1.x);
-                        a1.y = fma(d1, x[t].y, a1.y);
-                        a2.x = fma(d2, x[t].x, a2.x);
-                        a2.y = fma(d2, x[t].y, a2.y);
+                        a0.x = fma(d0, xc[t].x, a0.x);
+                        a0.y = fma(d0, xc[t].y, a0.y);
+                        a1.x = fma(d1, xc[t].x, a1.x);
+                        a1.y = fma(d1, xc[t].y, a1.y);
+                        a2.x = fma(d2, xc[t].x, a2.x);
+                        a2.y = fma(d2, xc[t].y, a2.y);
                     }
-                    like.x = fma(z[f].x, a0.x, like.x);
-                    like.y = fma(z[f].y, a0.y, like.y);
-                    first.x = fma(z[f].x, a1.x, first.x);
-                    first.y = fma(z[f].y, a1.y, first.y);
-                    second.x = fma(z[f].x, a2.x, second.x);
-                    second.y = fma(z[f].y, a2.y, second.y);
+                    like.x = fma(zc[f].x, a0.x, like.x);
+                    like.y = fma(zc[f].y, a0.y, like.y);
+                    first.x = fma(zc[f].x, a1.x, first.x);
+                    first.y = fma(zc[f].y, a1.y, first.y);
+                    second.x = fma(zc[f].x, a2.x, second.x);
+                    second.y = fma(zc[f].y, a2.y, second.y);
                 }
             }
             likeS.x += like.x;
@@ -349,7 +380,10 @@ newt_dna_kernel(const NewtArgs a, const NewtDeckJob job, unsigned *__restrict__ 
             firstS.y += first.y;
             secondS.x += second.x;
             secondS.y += second.y;
+#pragma unroll
+            for (int f = 0; f < 4; f++) { zc[f] = zn[f]; xc[f] = xn[f]; }
         }
+        codeC = codeN;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int pp = pat + h;
@@ -415,6 +449,166 @@ newt_dna_kernel(const NewtArgs a, const NewtDeckJob job, unsigned *__restrict__ 
         if (threadIdx.x < 3) {
             double s2 = 0.0;
             for (int i = 0; i < 8; i++) s2 += sRed[threadIdx.x][i];
+            result[threadIdx.x] = s2;
+        }
+    }
+}
+
+// Mixing over categories, constant-site term and the three per-pattern terms (Pf/p4_treeNewt.c:380-391, 501-517).
+__device__ __forceinline__ void newt_finish(const NewtArgs &a, int pp, int dim, int nCat, double l, double f1, double f2,
+                                            double &tL, double &tF, double &tS)
+{
+    if (a.pInvar != 0.0) {
+        const double f = (1.0 - a.pInvar) / (double)nCat;
+        l *= f;
+        f1 *= f;
+        f2 *= f;
+        const uint64_t im = a.invarMask ? a.invarMask[pp] : 0ull;
+        if (im)
+            for (int s = 0; s < dim; s++)
+                if ((im >> s) & 1ull) l += a.pi[s] * a.pInvar;
+    } else if (nCat > 1) {
+        l /= (double)nCat;
+        f1 /= (double)nCat;
+        f2 /= (double)nCat;
+    }
+    const double cnt = (double)a.counts[pp];
+    if (l < 1.0e-300) {
+        tL += cnt * -100000.0;
+        tF += cnt * 1000000.0;
+        tS += cnt * 10000000.0;
+    } else {
+        tL += cnt * log(l);
+        tF += cnt * (f1 / l);
+        tS += cnt * ((f2 * l - f1 * f1) / (l * l));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 20 states.  1260 FMAs per pattern and category against 320 bytes: the arithmetic and the shared-memory
+// operand reads bound this kernel, not HBM.  A thread owns TWO adjacent patterns, so every deck entry read
+// from shared memory (16-byte reads, two entries each) feeds two FMAs per deck; the node's CL of the current
+// category sits in registers.  Persistent CTAs; the last CTA to finish folds the partials (fixed order).
+// The decks come from newt_deck_kernel (one small launch before this one).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+newt_aa_kernel(const NewtArgs a, unsigned *__restrict__ ticket, double *__restrict__ result)
+{
+    constexpr int DIM = 20;
+    extern __shared__ double sD[];
+    __shared__ double sRed[3][4];
+    __shared__ bool sLast;
+    const int nCat = a.nCat, W = a.tblW;
+    const bool leaf = a.cl == nullptr;
+    const int per = leaf ? nCat * DIM * W : nCat * DIM * DIM;
+    {
+        const double *src = leaf ? a.decks + (size_t)3 * nCat * DIM * DIM : a.decks;
+        for (int i = threadIdx.x; i < 3 * per; i += blockDim.x) sD[i] = src[i];
+        __syncthreads();
+    }
+    const size_t ps = (size_t)a.ps;
+    const int nPairs = a.ps >> 1;
+    double tL = 0.0, tF = 0.0, tS = 0.0;
+    for (int pair = blockIdx.x * blockDim.x + threadIdx.x; pair < nPairs; pair += gridDim.x * blockDim.x) {
+        const int pat = pair * 2;
+        double2 likeS = make_double2(0.0, 0.0), firstS = likeS, secondS = likeS;
+        uchar2 code = make_uchar2(0, 0);
+        if (leaf) code = *reinterpret_cast<const uchar2 *>(a.tips + pat);
+        for (int c = 0; c < nCat; c++) {
+            const double *z = a.cl2 + (size_t)c * DIM * ps + pat;
+            double2 like = make_double2(0.0, 0.0), first = like, second = like;
+            if (leaf) {
+                const double *T0 = sD + (size_t)c * DIM * W, *T1 = T0 + per, *T2 = T1 + per;
+#pragma unroll 4
+                for (int f = 0; f < DIM; f++) {
+                    const double2 zz = ld2(z + (size_t)f * ps);
+                    like.x = fma(zz.x, T0[f * W + code.x], like.x);
+                    like.y = fma(zz.y, T0[f * W + code.y], like.y);
+                    first.x = fma(zz.x, T1[f * W + code.x], first.x);
+                    first.y = fma(zz.y, T1[f * W + code.y], first.y);
+                    second.x = fma(zz.x, T2[f * W + code.x], second.x);
+                    second.y = fma(zz.y, T2[f * W + code.y], second.y);
+                }
+            } else {
+                const double *x = a.cl + (size_t)c * DIM * ps + pat;
+                double2 xr[DIM];
+#pragma unroll
+                for (int t = 0; t < DIM; t++) xr[t] = ld2(x + (size_t)t * ps);
+                const double *D0 = sD + (size_t)c * DIM * DIM, *D1 = D0 + per, *D2 = D1 + per;
+#pragma unroll 2
+                for (int f = 0; f < DIM; f++) {
+                    const double2 zz = ld2(z + (size_t)f * ps);
+                    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0;
+#pragma unroll
+                    for (int t = 0; t < DIM; t += 2) {
+                        const double2 d0 = *reinterpret_cast<const double2 *>(D0 + f * DIM + t);
+                        const double2 d1 = *reinterpret_cast<const double2 *>(D1 + f * DIM + t);
+                        const double2 d2 = *reinterpret_cast<const double2 *>(D2 + f * DIM + t);
+                        a0.x = fma(d0.x, xr[t].x, a0.x);
+                        a0.y = fma(d0.x, xr[t].y, a0.y);
+                        a1.x = fma(d1.x, xr[t].x, a1.x);
+                        a1.y = fma(d1.x, xr[t].y, a1.y);
+                        a2.x = fma(d2.x, xr[t].x, a2.x);
+                        a2.y = fma(d2.x, xr[t].y, a2.y);
+                        a0.x = fma(d0.y, xr[t + 1].x, a0.x);
+                        a0.y = fma(d0.y, xr[t + 1].y, a0.y);
+                        a1.x = fma(d1.y, xr[t + 1].x, a1.x);
+                        a1.y = fma(d1.y, xr[t + 1].y, a1.y);
+                        a2.x = fma(d2.y, xr[t + 1].x, a2.x);
+                        a2.y = fma(d2.y, xr[t + 1].y, a2.y);
+                    }
+                    like.x = fma(zz.x, a0.x, like.x);
+                    like.y = fma(zz.y, a0.y, like.y);
+                    first.x = fma(zz.x, a1.x, first.x);
+                    first.y = fma(zz.y, a1.y, first.y);
+                    second.x = fma(zz.x, a2.x, second.x);
+                    second.y = fma(zz.y, a2.y, second.y);
+                }
+            }
+            likeS.x += like.x;
+            likeS.y += like.y;
+            firstS.x += first.x;
+            firstS.y += first.y;
+            secondS.x += second.x;
+            secondS.y += second.y;
+        }
+        if (pat < a.nPat) newt_finish(a, pat, DIM, nCat, likeS.x, firstS.x, secondS.x, tL, tF, tS);
+        if (pat + 1 < a.nPat) newt_finish(a, pat + 1, DIM, nCat, likeS.y, firstS.y, secondS.y, tL, tF, tS);
+    }
+    tL = warpSum(tL);
+    tF = warpSum(tF);
+    tS = warpSum(tS);
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (ln == 0) { sRed[0][w] = tL; sRed[1][w] = tF; sRed[2][w] = tS; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = 0; i < 4; i++) { v[0] += sRed[0][i]; v[1] += sRed[1][i]; v[2] += sRed[2][i]; }
+        a.partials[3 * blockIdx.x] = v[0];
+        a.partials[3 * blockIdx.x + 1] = v[1];
+        a.partials[3 * blockIdx.x + 2] = v[2];
+        __threadfence();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        sLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLast) {
+        __threadfence();
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            v[0] += __ldcg(a.partials + 3 * i);
+            v[1] += __ldcg(a.partials + 3 * i + 1);
+            v[2] += __ldcg(a.partials + 3 * i + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = warpSum(v[k]);
+            if (ln == 0) sRed[k][w] = v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double s2 = 0.0;
+            for (int i = 0; i < 4; i++) s2 += sRed[threadIdx.x][i];
             result[threadIdx.x] = s2;
         }
     }

@@ -2190,6 +2190,22 @@ static int newtDerivs(Tree *t, Node *n, double out[3])
             CUDA_TRY(cudaFuncSetAttribute(newt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attrSet = true;
         }
+        if (L.dim == 20 && a.useSmem) {
+            // two patterns per thread, the last CTA folds: deck launch + this one
+            static int residentAA = 0;
+            if (!residentAA) {
+                CUDA_TRY(cudaFuncSetAttribute(newt_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&residentAA, newt_aa_kernel, 128, smBytes));
+                if (residentAA < 1) residentAA = 1;
+                if (residentAA > 8) residentAA = 8;
+            }
+            int grid = (L.ps / 2 + 127) / 128;
+            if (grid > G.numSMs * residentAA) grid = G.numSMs * residentAA;
+            newt_aa_kernel<<<grid, 128, smBytes, G.stream>>>(a, S->ticket, S->result + 3 * p);
+            CUDA_TRY(cudaGetLastError());
+            G.launches++;
+            continue;
+        }
         if (L.dim == 20) newt_kernel<20><<<blocks, 128, smBytes, G.stream>>>(a);
         else newt_kernel<0><<<blocks, 128, smBytes, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
