@@ -71,3 +71,33 @@ def test_dirty_path_equals_full_recompute(pkg, big):
         a = big.recalcAfterBranchChange()
         b = big.calcLogLike()
         assert rel(a, b) <= 1e-12
+
+
+def test_newton_step_at_full_size(pkg, big):
+    """The Newton-Raphson quantities at 1 M patterns, by properties: the likelihood seen THROUGH any branch (cl2 on
+    one side, the node's CL or tip on the other) is the tree's likelihood; the analytic first derivative agrees with a
+    central difference of the full-tree evaluation; one Newton round over all 397 branches does not lower lnL and
+    leaves a consistent tree."""
+    pf = pkg.pf
+    base = big.calcLogLike()
+    pf.p4_newtSetup(big.cTree)
+    nodes = list(big.iterNodesNoRoot())
+    for n in (nodes[0], nodes[len(nodes) // 2], nodes[-1]):
+        l0, d1, d2 = pf.newtDerivs(n.cNode)
+        assert rel(l0, base) <= 1e-11
+        v = n.br.len
+        h = max(1e-3 * v, min(1e-5, 0.1 * v))
+        n.br.len = v + h
+        lp = big.calcLogLike()
+        n.br.len = v - h
+        lm = big.calcLogLike()
+        n.br.len = v
+        assert abs((lp - lm) / (2 * h) - d1) <= 1e-4 * max(1.0, abs(d1))
+        assert d2 == d2
+    assert rel(big.calcLogLike(), base) <= 1e-13
+    after = pf.newtAround(big.cTree, 1.0, 1.0e9)        # likeDelta so large that exactly one round runs
+    assert after >= base - 1e-6
+    lens = pf.p4_getBrLens(big.cTree)
+    for n in nodes:
+        n.br.len = lens[n.nodeNum]
+    assert rel(big.calcLogLike(), after) <= 1e-12
