@@ -31,45 +31,47 @@ struct NewtDeckJob {
     double r2[16];         // factor of the second derivative per category, squared by the kernel (:505-534)
 };
 
+// grid.x = rate category: the CTA of category c forms that category's slices of the three decks and tables.
 __global__ void __launch_bounds__(256)
 newt_deck_kernel(const NewtDeckJob job)
 {
-    extern __shared__ double sExp[];   // [nCat][dim] for P, then [nCat][dim] for the derivatives
-    const int dim = job.dim, nCat = job.nCat;
-    double *sExpD = sExp + nCat * dim;
+    extern __shared__ double sExp[];   // [dim] for P, then [dim] for the derivatives
+    const int dim = job.dim, nCat = job.nCat, c = blockIdx.x;
+    double *sExpD = sExp + dim;
     const double *V = job.eig;
     const double *Vi = V + dim * dim;
     const double *lam = Vi + dim * dim;
-    for (int i = threadIdx.x; i < nCat * dim; i += blockDim.x) {
-        sExp[i] = exp(lam[i % dim] * job.t0[i / dim]);
-        sExpD[i] = exp(lam[i % dim] * job.t1[i / dim]);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        sExp[i] = exp(lam[i] * job.t0[c]);
+        sExpD[i] = exp(lam[i] * job.t1[c]);
     }
     __syncthreads();
-    const int n = nCat * dim * dim;
+    const int n = nCat * dim * dim, nc = dim * dim;
     double *D0 = job.decks, *D1 = D0 + n, *D2 = D1 + n;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int c = idx / (dim * dim), ij = idx - c * dim * dim, i = ij / dim, j = ij - i * dim;
-        const double r1 = job.r1[c], r2 = job.r2[c];
+    const double r1 = job.r1[c], r2 = job.r2[c];
+    for (int ij = threadIdx.x; ij < nc; ij += blockDim.x) {
+        const int i = ij / dim, j = ij - i * dim;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int k = 0; k < dim; k++) {
             // the reference's association: V[i][k] * Vinv[k][j] * lambda * rate * exp(lambda t)
             const double vv = __dmul_rn(V[i * dim + k], Vi[k * dim + j]);
-            const double e = sExpD[c * dim + k], l = lam[k];
-            s0 = fma(vv, sExp[c * dim + k], s0);                   // identical to pmatrix_kernel
+            const double e = sExpD[k], l = lam[k];
+            s0 = fma(vv, sExp[k], s0);                             // identical to pmatrix_kernel
             s1 += __dmul_rn(__dmul_rn(__dmul_rn(vv, l), r1), e);
             s2 += __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(vv, l), l), r2), r2), e);
         }
-        D0[idx] = s0;
-        D1[idx] = s1;
-        D2[idx] = s2;
+        D0[c * nc + ij] = s0;
+        D1[c * nc + ij] = s1;
+        D2[c * nc + ij] = s2;
     }
     if (job.tblW > 0) {
         __syncthreads();   // the block's own global writes are visible after the barrier
         const int W = job.tblW;
-        const int nT = nCat * dim * W;
+        const int nT = nCat * dim * W, ncT = dim * W;
         double *T = D2 + n;
-        for (int idx = threadIdx.x; idx < 3 * nT; idx += blockDim.x) {
-            const int d = idx / nT, r = idx - d * nT, k = r / W, w = r - k * W;   // k = cat*dim + from
+        for (int idx = threadIdx.x; idx < 3 * ncT; idx += blockDim.x) {
+            const int d = idx / ncT, r = idx - d * ncT, f = r / W, w = r - f * W;
+            const int k = c * dim + f;                             // row of the table: cat*dim + from
             const double *D = job.decks + (size_t)d * n + (size_t)k * dim;
             double v = 0.0;
             if (w < dim) v = D[w];
@@ -84,7 +86,7 @@ newt_deck_kernel(const NewtDeckJob job)
                 for (int x = 0; x < dim; x++)
                     if ((m >> x) & 1ull) v += D[x];
             }
-            T[idx] = v;
+            T[(size_t)d * nT + (size_t)k * W + w] = v;
         }
     }
 }

@@ -2125,7 +2125,7 @@ static int newtDerivs(Tree *t, Node *n, double out[3])
         }
         const bool dna = L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
         if (!dna) {
-            newt_deck_kernel<<<1, 256, 2 * L.nCat * L.dim * sizeof(double), G.stream>>>(j);
+            newt_deck_kernel<<<L.nCat, 256, 2 * L.dim * sizeof(double), G.stream>>>(j);
             CUDA_TRY(cudaGetLastError());
             G.launches++;
         }
