@@ -92,7 +92,8 @@ def test_newton_step_at_full_size(pkg, big):
         n.br.len = v - h
         lm = big.calcLogLike()
         n.br.len = v
-        assert abs((lp - lm) / (2 * h) - d1) <= 1e-4 * max(1.0, abs(d1))
+        # a central difference of two sums of 10^6 terms near -1.7e8: truncation O(h^2) plus rounding ~ ulp(lnL) / h
+        assert abs((lp - lm) / (2 * h) - d1) <= 2e-3 * max(1.0, abs(d1)) + 64 * np.spacing(abs(base)) / h
         assert d2 == d2
     assert rel(big.calcLogLike(), base) <= 1e-13
     after = pf.newtAround(big.cTree, 1.0, 1.0e9)        # likeDelta so large that exactly one round runs
