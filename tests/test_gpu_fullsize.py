@@ -92,6 +92,7 @@ def test_newton_step_at_full_size(pkg, big):
         n.br.len = v - h
         lm = big.calcLogLike()
         n.br.len = v
+        assert rel(big.calcLogLike(), base) <= 1e-13      # the engine is back at the base lengths for the next node
         # a central difference of two sums of 10^6 terms near -1.7e8: truncation O(h^2) plus rounding ~ ulp(lnL) / h
         assert abs((lp - lm) / (2 * h) - d1) <= 2e-3 * max(1.0, abs(d1)) + 64 * np.spacing(abs(base)) / h
         assert d2 == d2
