@@ -230,3 +230,41 @@ def test_newt_setup_rejects_a_leaf_root(pkg):
     tree.calcLogLike()
     with pytest.raises(SystemExit):
         pf.p4_newtSetup(tree.cTree)
+
+
+def test_newt_around_61_states(pkg, ref_pf):
+    """61-symbol data (the any-dim derivative kernel with its decks read from global memory: 3 x 2 x 61 x 61 doubles
+    do not fit the shared-memory budget), two rate categories, gaps at the tips."""
+    P, H = pkg, pkg.host
+    pf = P.pf
+    rng = np.random.Generator(np.random.PCG64(61))
+    symbols = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ012345678"
+    tree = P.synth.random_tree(pf, 7, rng)
+    lut = np.frombuffer(symbols.encode(), dtype=np.uint8)
+    base = rng.integers(61, size=150)
+    seqs = []
+    for _ in range(7):
+        s = base.copy()
+        m = rng.random(150) < 0.4
+        s[m] = rng.integers(61, size=int(m.sum()))
+        chars = lut[s].copy()
+        chars[rng.random(150) < 0.03] = ord("-")
+        seqs.append(chars.tobytes())
+    aln = H.Alignment(pf, seqs, symbols, {})
+    mp = H.ModelPart(0, 61, 2)
+    mp.comps.append(H.Comp(P.synth.normalise_comp(rng.dirichlet(20.0 * np.ones(61)))))
+    mp.rMatrices.append(H.RMatrix("ones"))
+    mp.gdasrvs.append(H.Gdasrv(2, 0.8))
+    tree.attach(H.Data(pf, [aln]), H.Model(pf, [mp]))
+    twin = H.clone_tree(tree, ref_pf)
+    _perturb((tree, twin), seed=61, sd=0.5)
+    assert rel(tree.calcLogLike(), twin.calcLogLike()) <= 1e-9
+    pf.p4_newtSetup(tree.cTree)
+    ref_pf.p4_newtSetup(twin.cTree)
+    got = pf.newtAround(tree.cTree, 1.0e-5, 1.0e-7)
+    ref_peek.newt_lib().p4_newtAround(twin.cTree, 1.0e-5, 1.0e-7)
+    assert rel(got, ref_pf.p4_treeLogLike(twin.cTree, 0)) <= 1e-9
+    mineLens = pf.p4_getBrLens(tree.cTree)
+    for a, b in zip(tree.iterNodesNoRoot(), twin.iterNodesNoRoot()):
+        wantLen = ref_peek.node_brlen(b.cNode)
+        assert abs(mineLens[a.nodeNum] - wantLen) <= 1e-6 * max(wantLen, 1e-3), (a.nodeNum, mineLens[a.nodeNum], wantLen)
