@@ -26,7 +26,8 @@ p4_newGdasrv gdasrvCalcRates gdasrvCalcRates_np p4_setRMatrixBigR p4_setKappa p4
 p4_resetBQET p4_getRelRate p4_newTree p4_freeTree p4_newNode p4_freeNode p4_setNodeRelation p4_setTreeRoot p4_setBrLen
 p4_getTreeLen p4_setCompNum p4_setRMatrixNum p4_setGdasrvNum p4_setPrams p4_calculateBigPDecks
 p4_calculateAllBigPDecksAllParts p4_setConditionalLikelihoodsOfInternalNodePart p4_partLogLike p4_treeLogLike
-p4_copyCondLikes p4_copyBigPDecks p4_copyModelPrams p4_verifyIdentityOfTwoTrees""".split()
+p4_copyCondLikes p4_copyBigPDecks p4_copyModelPrams p4_verifyIdentityOfTwoTrees
+p4_newtSetup p4_newtAndBrentPowellOpt p4_newtAndBOBYQAOpt p4_getBrLens p4_getFreePrams""".split()
 MAKES_HANDLE = {"newData", "newPart", "p4_newModel", "p4_newTree", "p4_newNode", "p4_newGdasrv"}
 
 

@@ -235,8 +235,46 @@ def mcmc_ndch2(nChains, nGens, seed, name):
     print(out, os.path.getsize(out), "bytes;", sum(counts.values()), "calls;", props)
 
 
+def opt_newt(seed, name):
+    """The reference's real Tree.optLogLike(method="newtAndBrentPowell") and (method="newtAndBOBYQA") (p4/tree.py:9417-9499)
+    with every model parameter fixed: both drivers are then the four-call p4_newtAround schedule (Pf/p4_treeOpt.c:755-775,
+    1214-1226), a deterministic function of the tree -- F81+I+G4 on L_mcmc/d.nex from a random tree with default branch lengths,
+    then a second optimisation from doubled branch lengths."""
+    _begin(seed)
+    read(os.path.join(EX, "d.nex"))
+    d = Data()
+    t = func.randomTree(taxNames=d.taxNames)
+    t.data = d
+    t.newComp(free=0, spec="empirical")
+    t.newRMatrix(free=0, spec="ones")
+    t.setNGammaCat(nGammaCat=4)
+    t.newGdasrv(free=0, val=0.5)
+    t.setPInvar(free=0, val=0.2)
+    t.calcLogLike(verbose=0)
+    start = t.logLike
+    t.optLogLike(verbose=0, method="newtAndBrentPowell")
+    first = t.logLike
+    for n in t.iterNodesNoRoot():
+        n.br.len *= 2.0
+    t.optLogLike(verbose=0, method="newtAndBOBYQA")
+    rec.recording = False
+    counts = {}
+    for ev in rec.events:
+        if ev[0] == "call":
+            counts[ev[1]] = counts.get(ev[1], 0) + 1
+    meta = {"what": "reference p4 Tree.optLogLike(newtAndBrentPowell) then (newtAndBOBYQA), no free model parameter, F81+I+G4 on L_mcmc/d.nex",
+            "seed": seed, "calls": counts, "lnL": [float(start), float(first), float(t.logLike)],
+            "brLens": [float(n.br.len) for n in t.iterNodesNoRoot()]}
+    out = os.path.join(HERE, name)
+    rec.save(out, meta)
+    print(out, os.path.getsize(out), "bytes;", sum(counts.values()), "calls;", meta["lnL"])
+
+
 if __name__ == "__main__":
     os.chdir(tempfile.mkdtemp())
+    if len(sys.argv) > 1 and sys.argv[1] == "opt":      # only the optimisation trace
+        opt_newt(18, "trace_opt_newt.json.gz")
+        sys.exit(0)
     mcmc_simple(2, 120, 11, "trace_mcmc_gtr_i_g4.json.gz")
     mcmc_ndch2(2, 100, 12, "trace_mcmc_ndch2.json.gz")
     mcmc_two_parts(2, 100, 13, "trace_mcmc_two_parts_relrate.json.gz")
@@ -244,3 +282,4 @@ if __name__ == "__main__":
     mcmc_grouped_aa(2, 80, 15, "trace_mcmc_grouped_aa.json.gz")
     mcmc_protein(2, 80, 16, "trace_mcmc_protein_lg_i_g4.json.gz", 4)
     mcmc_protein(1, 60, 17, "trace_mcmc_protein_lg_i.json.gz", 1)
+    opt_newt(18, "trace_opt_newt.json.gz")

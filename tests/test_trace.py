@@ -1,4 +1,5 @@
-"""pf-boundary traces of the reference's REAL Mcmc (tests/golden/make_trace.py, oracle/pf_trace.py).
+"""pf-boundary traces of the reference's REAL Mcmc and of its REAL Tree.optLogLike (Newton-Raphson drivers)
+(tests/golden/make_trace.py, oracle/pf_trace.py).
 
 CPU: the trace replays exactly on the reference's own engine (the harness is sound), and this repository's ``pf`` module
 offers every function the reference's callers used.  GPU: the trace replays on the B200 engine -- every log-likelihood
@@ -21,7 +22,8 @@ def test_trace_replays_on_the_reference_engine(ref_pf, path):
     trace = pf_trace.load(path)
     stats = pf_trace.replay(ref_pf, trace, tol=1e-14)
     assert stats["calls"] == sum(trace["meta"]["calls"].values())
-    assert stats["checked_values"] > 100 and stats["worst_rel_diff"] <= 1e-14
+    few = os.path.basename(path).startswith("trace_opt_")     # an optimisation trace returns two vectors of branch lengths
+    assert stats["checked_values"] > (20 if few else 100) and stats["worst_rel_diff"] <= 1e-14
 
 
 @pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[6:-8] for p in TRACES])
@@ -42,7 +44,9 @@ def test_trace_replays_on_the_gpu_engine(pkg, path, mode):
         pf.setSharedCondLikes(0)
         pf.setMemoize(0)
     try:
-        stats = pf_trace.replay(pf, trace, tol=1e-9)
+        # optimisation traces return branch lengths -- fixed points of Newton iterations, compared at 1e-7 (observed <= 1e-11);
+        # every log-likelihood and engine-written float of the MCMC traces at 1e-9
+        stats = pf_trace.replay(pf, trace, tol=1e-7 if os.path.basename(path).startswith("trace_opt_") else 1e-9)
     finally:
         pf.setDeferredNodeCalls(1)
         pf.setSharedCondLikes(1)
