@@ -282,6 +282,21 @@ int p4b_partLogLikeBegin(p4b_tree t, int pNum);
  * pInvar share included), averaged over the rate categories; out[seqNum][state] for every leaf.
  * pf.p4_expectedCompositionCounts(tree, partNum) :2384 -> :859-949: the same times the number of
  * non-gap, non-'?' sites of the sequence.  P decks must be current (p4_setPrams). */
+/* pf.gsl_rng_get() :674, pf.gsl_rng_free :691, pf.gsl_rng_set(g, seed) :708, pf.gsl_rng_uniform(g) :739: the random
+ * stream p4 hands to its simulations (var.gsl_rng).  GSL's default generator mt19937 with GSL's seeding
+ * (seed 0 = 4357; uniform = 32-bit output / 2^32), so that a simulation is the same function of the seed. */
+void *p4b_rngNew(void);
+void p4b_rngFree(void *rng);
+void p4b_rngSet(void *rng, unsigned long seed);
+unsigned long p4b_rngGet(void *rng);
+double p4b_rngUniform(void *rng);
+/* pf.p4_simulate(tree, refTree|0, gsl_rng) :2333 -> p4_simulate Pf/p4_treeSim.c:14-420 (refTree must be 0):
+ * new sequences for every leaf, drawn down the tree from the root's composition through every branch's P decks
+ * (rate category and invariant-or-not per site, pInvar), consuming the stream in the reference's order -- the
+ * same seed gives the reference's sequences.  Writes part->sequences and globalInvarSitesVec, sets nPatterns
+ * to 0: the caller re-compresses with pf.makePatterns / pf.setGlobalInvarSitesVec (p4/tree.py:9617-9626); the
+ * tree lays its device state out again at its next use. */
+int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng);
 int p4b_expectedComposition(p4b_tree t, int pNum, double *outNTaxTimesDim);
 int p4b_expectedCompositionCounts(p4b_tree t, int pNum, double *outNTaxTimesDim);
 

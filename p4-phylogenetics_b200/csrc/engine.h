@@ -9,6 +9,7 @@
 // only when they change.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -192,6 +193,9 @@ void setFusedAAEnabled(int on);
 void setMemoizeEnabled(int on);
 int treesPartLogLike(Tree **trees, int n, int p, double *out);
 int treePartLogLikeBegin(Tree *t, int p);
+// simulate: device part (tree.cu).  `fill(dst, n)` must write the next n uniforms of the caller's stream.
+int treeSimulateDevice(Tree *t, int p, const uint8_t *cats, const uint8_t *rootStates, const uint8_t *invar, const int *rank,
+                       int nVar, const std::function<void(double *, size_t)> &fill);
 int treeNewtSetup(Tree *t);
 double treeNewtAround(Tree *t, double epsilon, double likeDelta);
 int nodeNewtDerivs(Node *n, double out[3]);

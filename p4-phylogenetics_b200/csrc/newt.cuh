@@ -641,4 +641,65 @@ newt_final_kernel(const double *__restrict__ partials, int n, double *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------
+// Simulation down the tree (p4_simulate, Pf/p4_treeSim.c:14-420): integer / byte work, one thread per SITE.
+//   picker_kernel    picker[cat][from][to] = running sum of the P deck's row, last entry 1.0
+//                    (p4_calculatePickerDecks, Pf/p4_node.c)
+//   simulate_kernel  a chunk of nodes in preOrder: a site's state at a node is its parent's state at an
+//                    invariant site, else the first `to` with u < picker[cat][parentState][to], u being the
+//                    site's own uniform of that node in the reference's stream order (:330-360).
+// States live as one byte per (node, site); a thread reads back only bytes it wrote itself.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+picker_kernel(const double *__restrict__ Pdeck, double *__restrict__ picker, long long pNodeDoubles, int pOff, int dim, int nCat, int nNodes)
+{
+    // one thread per (node, cat, from) row
+    const int rows = nNodes * nCat * dim;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        const int node = r / (nCat * dim), k = r - node * nCat * dim;
+        const double *src = Pdeck + (size_t)pNodeDoubles * node + pOff + (size_t)k * dim;
+        double *dst = picker + ((size_t)node * nCat * dim + k) * dim;
+        double run = src[0];
+        dst[0] = run;
+        for (int l = 1; l < dim - 1; l++) {
+            run = run + src[l];
+            dst[l] = run;
+        }
+        dst[dim - 1] = 1.0;
+    }
+}
+
+constexpr int kSimChunk = 64;
+struct SimArgs {
+    uint8_t *states;            // [nNodes][nChar]
+    const uint8_t *cats;        // [nChar]
+    const uint8_t *invar;       // [nChar]
+    const int *rank;            // [nChar]: index of the site among the variable sites
+    const double *picker;       // [nNodes][nCat][dim][dim]
+    const double *U;            // [nChunkNodes][nVar] uniforms of this chunk
+    int nChar, nVar, dim, nCat, n;
+    int node[kSimChunk], parent[kSimChunk];
+};
+
+__global__ void __launch_bounds__(256)
+simulate_kernel(const SimArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.nChar) return;
+    const bool inv = a.invar[k] != 0;
+    const int cat = a.cats[k], rk = a.rank[k], dim = a.dim;
+    for (int j = 0; j < a.n; j++) {
+        const int parentState = a.states[(size_t)a.parent[j] * a.nChar + k];
+        int st = parentState;
+        if (!inv) {
+            const double u = a.U[(size_t)j * a.nVar + rk];
+            const double *row = a.picker + (((size_t)a.node[j] * a.nCat + cat) * dim + parentState) * dim;
+            st = dim - 1;
+            for (int l = 0; l < dim; l++)
+                if (u < __ldg(row + l)) { st = l; break; }
+        }
+        a.states[(size_t)a.node[j] * a.nChar + k] = (uint8_t)st;
+    }
+}
+
 }  // namespace p4b

@@ -1,4 +1,5 @@
-// sim.cpp -- consumers of the P decks beside the likelihood.
+// sim.cpp -- consumers of the P decks beside the likelihood: expected tip
+// compositions, and simulation of data down the tree (p4_simulate) on the caller's random stream.
 //
 // p4_expectedComposition / p4_expectedCompositionCounts (Pf/p4_treeSim.c:859-1045) push the root's
 // composition down the tree through every branch's transition matrices (p4_calculateExpectedComp,
@@ -7,6 +8,8 @@
 // (p4/tree.py:8192, 8544, 9071-9180).  The P decks are the ones resident on the device; the
 // recursion itself is dim-sized per node and runs on the host in the reference's order of operations.
 #include <cmath>
+#include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "../../include/p4b200.h"
@@ -93,12 +96,139 @@ int treeExpectedComposition(Tree *t, int p, int counts, double *out)
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Random stream.  p4 hands its simulations a GSL generator (var.gsl_rng = pf.gsl_rng_get(), the library default
+// mt19937; Pf/pfmodule.c:674-749) and the reference consumes one gsl_rng_uniform per decision in a fixed order
+// (Pf/p4_treeSim.c:235-340).  Drawing the same stream here makes a simulation a pure function of (tree, model,
+// seed) that can be compared with the reference's site by site.  MT19937 (Matsumoto & Nishimura 1998) with GSL's
+// seeding: seed 0 means 4357; uniform = 32-bit output / 2^32.
+// ---------------------------------------------------------------------------
+struct Rng {
+    uint32_t mt[624];
+    int mti = 625;
+    void set(unsigned long seed)
+    {
+        if (seed == 0) seed = 4357;
+        mt[0] = (uint32_t)(seed & 0xffffffffUL);
+        for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        mti = 624;
+    }
+    uint32_t get()
+    {
+        if (mti >= 624) {
+            if (mti == 625) set(0);
+            static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
+            int kk = 0;
+            for (; kk < 624 - 397; kk++) {
+                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            for (; kk < 623; kk++) {
+                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+            mti = 0;
+        }
+        uint32_t y = mt[mti++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double uniform() { return get() / 4294967296.0; }
+};
+
+// p4_simulate(t, NULL, g), Pf/p4_treeSim.c:14-420.  Host: the per-site draws that need no tree (rate category,
+// root state, invariant or not -- :235-300, in the reference's order over parts) and the stream of uniforms of the
+// mutation phase, which the reference consumes node by node in preOrder and, within a node, site by site over the
+// VARIABLE sites only (:330-360).  Device (tree.cu): picker decks (running row sums of the P decks,
+// Pf/p4_node.c p4_calculatePickerDecks) and one thread per site walking the nodes.
+int treeSimulate(Tree *t, Rng *g)
+{
+    if (!t->dev) { setError("tree has no device state"); return 1; }
+    if (!t->root) { setError("p4_simulate: the tree has no root"); return 1; }
+    Data *d = t->data;
+    const int nParts = d->nParts;
+    std::vector<std::vector<uint8_t>> cats(nParts), rootSt(nParts), inv(nParts);
+    for (int p = 0; p < nParts; p++) d->parts[p]->nPatterns = 0;                       // :60-62
+    for (int p = 0; p < nParts; p++) {                                                 // rate categories, :235-246
+        Part *dp = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        if (mp->dim > 255 || mp->nCat > 255) { setError("p4_simulate: dim or nCat too large"); return 1; }
+        cats[p].assign(dp->nChar, 0);
+        if (mp->nCat > 1)
+            for (int i = 0; i < dp->nChar; i++) cats[p][i] = (uint8_t)(int)floor(((double)mp->nCat) * g->uniform());
+    }
+    for (int p = 0; p < nParts; p++) {                                                 // root states, :256-277
+        Part *dp = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        const int rc = t->root->compNums[p];
+        if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+        const double *pi = mp->comps[rc].val;
+        std::vector<double> picker(mp->dim);
+        picker[0] = pi[0];
+        for (int j = 1; j < mp->dim - 1; j++) picker[j] = picker[j - 1] + pi[j];
+        picker[mp->dim - 1] = 1.0;
+        rootSt[p].assign(dp->nChar, 0);
+        for (int j = 0; j < dp->nChar; j++) {
+            const double u = g->uniform();
+            for (int k = 0; k < mp->dim; k++)
+                if (u < picker[k]) { rootSt[p][j] = (uint8_t)k; break; }
+        }
+    }
+    for (int p = 0; p < nParts; p++) {                                                 // invariant sites, :284-300
+        Part *dp = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        inv[p].assign(dp->nChar, 0);
+        dp->globalInvarSitesVec.assign(dp->nChar, 0);
+        if (mp->pInvar > 0.0)
+            for (int i = 0; i < dp->nChar; i++) {
+                const double u = g->uniform();
+                inv[p][i] = u < mp->pInvar ? 1 : 0;
+                dp->globalInvarSitesVec[i] = inv[p][i];
+            }
+    }
+    if (treeCalculateAllBigPDecks(t)) return 1;                                        // :315-321
+    for (int p = 0; p < nParts; p++) {                                                 // mutation, :330-360
+        Part *dp = d->parts[p];
+        std::vector<int> rank(dp->nChar, 0);
+        int nVar = 0;
+        for (int k = 0; k < dp->nChar; k++) {
+            rank[k] = nVar;
+            if (!inv[p][k]) nVar++;
+        }
+        auto fill = [&](double *dst, size_t n) {
+            for (size_t i = 0; i < n; i++) dst[i] = g->uniform();
+        };
+        if (treeSimulateDevice(t, p, cats[p].data(), rootSt[p].data(), inv[p].data(), rank.data(), nVar, fill)) return 1;
+        dp->version++;
+    }
+    return 0;
+}
+
 }  // namespace p4b
 
 using namespace p4b;
 
 extern "C" {
 
+void *p4b_rngNew(void) { return new Rng(); }
+void p4b_rngFree(void *g) { delete (Rng *)g; }
+void p4b_rngSet(void *g, unsigned long seed)
+{
+    if (g) ((Rng *)g)->set(seed);
+}
+unsigned long p4b_rngGet(void *g) { return g ? ((Rng *)g)->get() : 0ul; }
+double p4b_rngUniform(void *g) { return g ? ((Rng *)g)->uniform() : 0.0; }
+int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng)
+{
+    if (!t || !rng) { setError("p4b_simulate: NULL argument"); return 1; }
+    if (refTree) { setError("p4_simulate with a refTree (ancestral states drawn from another tree's conditional likelihoods, Pf/p4_treeSim.c:200-232) is not available on this engine"); return 1; }
+    return treeSimulate((Tree *)t, (Rng *)rng);
+}
 int p4b_expectedComposition(p4b_tree t, int pNum, double *out)
 {
     if (!t || !out) { setError("p4b_expectedComposition: NULL argument"); return 1; }

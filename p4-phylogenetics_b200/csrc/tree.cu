@@ -14,7 +14,9 @@
 // p4b_treeLogLike are the synchronisation points.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <functional>
 #include <cstddef>
 #include <cstdlib>
 #include <cstdio>
@@ -268,6 +270,7 @@ struct PartLayout {
 
 struct TreeDevice {
     std::vector<PartLayout> parts;
+    std::vector<uint64_t> dataVersion;   // per part: Part::version this device state was laid out for
     // Node-level CL calls on parts the whole-tree kernel serves are not launched one by one: they queue
     // here (per part, in call order) and run as ONE step-list launch when something needs their result --
     // normally p4_partLogLike, which then also gets the root reduction fused in.
@@ -313,6 +316,7 @@ int treeDeviceCreate(Tree *t)
         if (!dp || !mp) { setError("p4_newTree: part %d missing in data or model", p); return 1; }
         if (dp->dim != mp->dim) { setError("p4_newTree: part %d dim mismatch data %d model %d", p, dp->dim, mp->dim); return 1; }
         if (partDeviceEnsure(dp)) return 1;
+        d->dataVersion.push_back(dp->version);
         PartLayout &L = d->parts[p];
         L.dim = mp->dim;
         L.nCat = mp->nCat;
@@ -498,6 +502,32 @@ int nodeDeviceCreate(Node *n)
     return 0;
 }
 
+// The data parts can change under a living tree: p4 simulates new sequences into them and re-compresses
+// (Tree.simulate -> pf.p4_simulate, pf.makePatterns; p4/tree.py:9617-9626).  The reference's arrays are sized by
+// nChar and survive that; here the pattern shard, its stride and the CL arenas depend on the pattern count, so
+// the tree's device state is laid out again the next time it is used (and every P deck recomputed).
+int treeCalculateAllBigPDecks(Tree *t);
+static int ensureFresh(Tree *t, bool needPatterns)
+{
+    TreeDevice *d = t->dev;
+    if (!d) return 0;
+    bool stale = false;
+    for (int p = 0; p < t->nParts; p++)
+        if (t->data->parts[p]->version != d->dataVersion[p]) stale = true;
+    if (!stale) return 0;
+    for (int p = 0; p < t->nParts; p++)
+        if (t->data->parts[p]->nPatterns <= 0) {
+            if (!needPatterns) return 0;      // nothing that needs patterns is being asked for yet
+            setError("part %d has no patterns (pf.makePatterns not called after the sequences changed?)", p);
+            return 1;
+        }
+    treeDeviceDestroy(t);
+    if (treeDeviceCreate(t)) return 1;
+    for (Node *n : t->nodes)
+        if (n && nodeDeviceCreate(n)) return 1;
+    return treeCalculateAllBigPDecks(t);
+}
+
 static inline double *nodeCL(Node *n, int p)
 {
     PartLayout &L = n->tree->dev->parts[p];
@@ -679,6 +709,7 @@ static int treeFlushAllPending(Tree *t);
 int treeSetPrams(Tree *t, int pNum)
 {
     if (!t->dev) { setError("tree has no device state"); return 1; }
+    if (ensureFresh(t, false)) return 1;
     if (pNum < -1 || pNum >= t->nParts) { setError("p4_setPrams: bad part %d", pNum); return 1; }
     if (treeFlushAllPending(t)) return 1;   // queued CLs were issued against the old P decks
     for (int p = 0; p < t->nParts; p++) {
@@ -808,6 +839,7 @@ int nodeSetCL(Node *n, int p) { return nodeSetCLImpl(n, p, true); }
 static int nodeSetCLImpl(Node *n, int p, bool memo)
 {
     Tree *t = n->tree;
+    if (ensureFresh(t, true)) return 1;
     TreeDevice *d = t->dev;
     if (p < 0 || p >= t->nParts) { setError("p4_setConditionalLikelihoodsOfInternalNodePart: bad part %d", p); return 1; }
     if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return 1; }
@@ -1397,6 +1429,7 @@ static int collectBegun(Tree *t, int p, double *lnL)
 double treePartLogLike(Tree *t, Part *dpArg, int p, int getSiteLikes)
 {
     if (!t->dev) { setError("tree has no device state"); return NAN; }
+    if (ensureFresh(t, true)) return NAN;
     if (p < 0 || p >= t->nParts) { setError("p4_partLogLike: bad part %d", p); return NAN; }
     (void)dpArg;   // the reference passes the part explicitly; it is data->parts[pNum]
     if (t->dev->likeBegun[p] && !getSiteLikes && t->dev->pending[p].empty()) {
@@ -1421,6 +1454,7 @@ double treePartLogLike(Tree *t, Part *dpArg, int p, int getSiteLikes)
 int treePartLogLikeBegin(Tree *t, int p)
 {
     if (!t->dev) { setError("tree has no device state"); return 1; }
+    if (ensureFresh(t, true)) return 1;
     if (p < 0 || p >= t->nParts) { setError("p4b_partLogLikeBegin: bad part %d", p); return 1; }
     TreeDevice *d = t->dev;
     if (launchPartLike(t, p, 0)) return 1;
@@ -1436,6 +1470,7 @@ int treePartLogLikeBegin(Tree *t, int p)
 double treeLogLike(Tree *t, int getSiteLikes)
 {
     if (!t->dev) { setError("tree has no device state"); return NAN; }
+    if (ensureFresh(t, true)) return NAN;
     TreeDevice *d = t->dev;
     if (treeFlushAllPending(t)) return NAN;
     d->lastCLLaunches = 0;
@@ -1487,6 +1522,8 @@ double treeLogLike(Tree *t, int getSiteLikes)
 int treesPartLogLike(Tree **trees, int n, int p, double *out)
 {
     if (n <= 0) return 0;
+    for (int i = 0; i < n; i++)
+        if (trees[i] && trees[i]->dev && ensureFresh(trees[i], true)) return 1;
     {   // evaluations already started by p4b_partLogLikeBegin: their results are on the way, wait for each
         bool allBegun = n <= kMaxBatchTrees;
         for (int i = 0; i < n && allBegun; i++) {
@@ -2329,6 +2366,108 @@ int nodeGetCL2(Node *n, int p, double *out)
 }
 
 long long treeNewtIterations(Tree *t) { return (t->dev && t->dev->newt) ? t->dev->newt->iters : 0; }
+
+
+// ---------------------------------------------------------------------------
+// p4_simulate, device part (Pf/p4_treeSim.c:315-360): picker decks from the current P decks, then the nodes in
+// preOrder, a chunk at a time; the uniforms of a chunk are produced by `fill` in the reference's stream order
+// and shipped through one pinned buffer.  Leaf states come back into part->sequences.
+// ---------------------------------------------------------------------------
+int treeSimulateDevice(Tree *t, int p, const uint8_t *cats, const uint8_t *rootStates, const uint8_t *invar, const int *rank,
+                       int nVar, const std::function<void(double *, size_t)> &fill)
+{
+    if (G.world > 1) { setError("p4_simulate is not available when patterns are sharded over several processes"); return 1; }
+    TreeDevice *d = t->dev;
+    PartLayout &L = d->parts[p];
+    Part *dp = t->data->parts[p];
+    const int nChar = dp->nChar, dim = L.dim, nCat = L.nCat;
+    if (flushPJobs()) return 1;
+    uint8_t *dStates = nullptr, *dCats = nullptr, *dInv = nullptr;
+    int *dRank = nullptr;
+    double *dPicker = nullptr, *dU = nullptr, *hU = nullptr;
+    std::vector<Node *> order;
+    for (int j = 0; j < t->nNodes; j++) {
+        const int i = t->preOrder[j];
+        if (i == P4B_NO_ORDER) continue;
+        Node *n = t->nodes[i];
+        if (n && n != t->root) order.push_back(n);
+    }
+    // chunk size: at most kSimChunk nodes and about 64 MB of uniforms
+    size_t perNode = (size_t)(nVar > 0 ? nVar : 1);
+    int chunk = (int)((64u << 20) / (perNode * sizeof(double)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > kSimChunk) chunk = kSimChunk;
+    int rc = 1;
+    do {
+        if (cudaMalloc(&dStates, (size_t)t->nNodes * nChar) != cudaSuccess) break;
+        if (cudaMalloc(&dCats, nChar) != cudaSuccess || cudaMalloc(&dInv, nChar) != cudaSuccess) break;
+        if (cudaMalloc(&dRank, sizeof(int) * (size_t)nChar) != cudaSuccess) break;
+        if (cudaMalloc(&dPicker, sizeof(double) * (size_t)t->nNodes * nCat * dim * dim) != cudaSuccess) break;
+        if (cudaMalloc(&dU, sizeof(double) * perNode * chunk) != cudaSuccess) break;
+        if (cudaMallocHost(&hU, sizeof(double) * perNode * chunk) != cudaSuccess) break;
+        if (cudaMemcpyAsync(dCats, cats, nChar, cudaMemcpyHostToDevice, G.stream) != cudaSuccess) break;
+        if (cudaMemcpyAsync(dInv, invar, nChar, cudaMemcpyHostToDevice, G.stream) != cudaSuccess) break;
+        if (cudaMemcpyAsync(dRank, rank, sizeof(int) * (size_t)nChar, cudaMemcpyHostToDevice, G.stream) != cudaSuccess) break;
+        if (cudaMemcpyAsync(dStates + (size_t)t->root->nodeNum * nChar, rootStates, nChar, cudaMemcpyHostToDevice, G.stream) != cudaSuccess) break;
+        picker_kernel<<<G.numSMs * 2, 256, 0, G.stream>>>(d->P, dPicker, (long long)d->pNodeDoubles, (int)L.pOff, dim, nCat, t->nNodes);
+        if (cudaGetLastError() != cudaSuccess) break;
+        G.launches++;
+        bool ok = true;
+        for (size_t j0 = 0; j0 < order.size() && ok; j0 += chunk) {
+            const int n = (int)std::min((size_t)chunk, order.size() - j0);
+            if (cudaStreamSynchronize(G.stream) != cudaSuccess) { ok = false; break; }   // the pinned buffer is free again
+            fill(hU, (size_t)n * nVar);
+            SimArgs a;
+            memset(&a, 0, sizeof(a));
+            a.states = dStates;
+            a.cats = dCats;
+            a.invar = dInv;
+            a.rank = dRank;
+            a.picker = dPicker;
+            a.U = dU;
+            a.nChar = nChar;
+            a.nVar = nVar;
+            a.dim = dim;
+            a.nCat = nCat;
+            a.n = n;
+            for (int j = 0; j < n; j++) {
+                a.node[j] = order[j0 + j]->nodeNum;
+                a.parent[j] = order[j0 + j]->parent ? order[j0 + j]->parent->nodeNum : t->root->nodeNum;
+            }
+            if (nVar > 0 && cudaMemcpyAsync(dU, hU, sizeof(double) * (size_t)n * nVar, cudaMemcpyHostToDevice, G.stream) != cudaSuccess) { ok = false; break; }
+            simulate_kernel<<<(nChar + 255) / 256, 256, 0, G.stream>>>(a);
+            if (cudaGetLastError() != cudaSuccess) { ok = false; break; }
+            G.launches++;
+        }
+        if (!ok) break;
+        std::vector<uint8_t> row(nChar);
+        for (Node *n : t->nodes) {
+            if (!n || !n->isLeaf) continue;
+            if (n->seqNum < 0 || n->seqNum >= dp->nTax) { ok = false; break; }
+            if (cudaMemcpyAsync(row.data(), dStates + (size_t)n->nodeNum * nChar, nChar, cudaMemcpyDeviceToHost, G.stream) != cudaSuccess) { ok = false; break; }
+            if (cudaStreamSynchronize(G.stream) != cudaSuccess) { ok = false; break; }
+            int *seq = &dp->sequences[(size_t)n->seqNum * nChar];
+            for (int k = 0; k < nChar; k++) seq[k] = row[k];
+        }
+        if (!ok) break;
+        rc = 0;
+    } while (0);
+    if (rc) {
+        cudaError_t e = cudaGetLastError();
+        setError("p4_simulate: device step failed (%s)", e == cudaSuccess ? "allocation, copy, or a leaf without a sequence" : cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(G.stream);
+    if (dStates) cudaFree(dStates);
+    if (dCats) cudaFree(dCats);
+    if (dInv) cudaFree(dInv);
+    if (dRank) cudaFree(dRank);
+    if (dPicker) cudaFree(dPicker);
+    if (dU) cudaFree(dU);
+    if (hU) cudaFreeHost(hU);
+    G.stageDirtySinceSync = false;
+    G.stageHead = 0;
+    return rc;
+}
 
 void *engineStream() { return (void *)G.stream; }
 int engineInitPublic() { return engineInit(); }

@@ -473,6 +473,24 @@ class Tree:
             print("optLogLike = %f" % self.logLike)
         return self.logLike
 
+    def simulate(self, seed=None, calculatePatterns=True):
+        """Tree.simulate() (p4/tree.py:9527-9637, refTree=None): new data down this tree with its model, into its own
+        data parts.  ``seed`` (an addition) re-seeds the stream kept on the tree, p4 keeps it in var.gsl_rng."""
+        pf = self.pf
+        if getattr(self, "gsl_rng", None) is None:
+            self.gsl_rng = pf.gsl_rng_get()
+            if seed is None:
+                import time
+                pf.gsl_rng_set(self.gsl_rng, int(time.time()))
+        if seed is not None:
+            pf.gsl_rng_set(self.gsl_rng, int(seed))
+        self._commonCStuff()
+        pf.p4_simulate(self.cTree, 0, self.gsl_rng)
+        if calculatePatterns:
+            for p in self.data.parts:
+                pf.makePatterns(p.cPart)
+                pf.setGlobalInvarSitesVec(p.cPart)
+
     def getSiteLikes(self):
         self._commonCStuff()
         self.logLike = self.pf.p4_treeLogLike(self.cTree, 1)

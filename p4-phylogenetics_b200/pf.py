@@ -144,6 +144,12 @@ _sig("p4b_logLikeForParameters", _d, _vp, _i, _vp)
 _sig("p4b_getBrLens", _i, _vp, _vp)
 _sig("p4b_optimizeBrLens", _d, _vp, _i, _d, C.POINTER(C.c_long))
 _sig("p4b_treePassLimit", _i, _vp)
+_sig("p4b_rngNew", _vp)
+_sig("p4b_rngFree", None, _vp)
+_sig("p4b_rngSet", None, _vp, C.c_ulong)
+_sig("p4b_rngGet", C.c_ulong, _vp)
+_sig("p4b_rngUniform", _d, _vp)
+_sig("p4b_simulate", _i, _vp, _vp, _vp)
 _sig("p4b_expectedComposition", _i, _vp, _i, _vp)
 _sig("p4b_expectedCompositionCounts", _i, _vp, _i, _vp)
 _sig("p4b_newtSetup", _i, _vp)
@@ -709,6 +715,31 @@ def _expected(cTree, pNum, fn):
     out = np.zeros((nTax, dim), dtype=np.float64)
     _ok(fn(cTree, int(pNum), out.ctypes.data))
     return tuple(tuple(float(v) for v in row) for row in out)
+
+
+def gsl_rng_get():
+    """pf.gsl_rng_get() -> handle of a new mt19937 stream (Pf/pfmodule.c:674; GSL's default generator and seeding)."""
+    return _lib.p4b_rngNew()
+
+
+def gsl_rng_free(g):
+    _lib.p4b_rngFree(g)
+
+
+def gsl_rng_set(g, seed):
+    """pf.gsl_rng_set(g, seed) (Pf/pfmodule.c:708)."""
+    _lib.p4b_rngSet(g, int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def gsl_rng_uniform(g):
+    """pf.gsl_rng_uniform(g) -> float in [0, 1) (Pf/pfmodule.c:739)."""
+    return _lib.p4b_rngUniform(g)
+
+
+def p4_simulate(cTree, cRefTree, g):
+    """pf.p4_simulate(cTree, cRefTree|0, gsl_rng) (Pf/pfmodule.c:2333, Pf/p4_treeSim.c:14-420): simulate new
+    sequences down the tree on the device; the same seed gives the reference's sequences."""
+    _ok(_lib.p4b_simulate(cTree, cRefTree if cRefTree else None, g))
 
 
 def p4_expectedComposition(cTree):

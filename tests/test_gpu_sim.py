@@ -59,3 +59,40 @@ def test_expected_composition_follows_the_model(pkg, ref_pf):
     after = np.array(pkg.pf.p4_expectedComposition(mine.cTree)[0])
     assert np.max(np.abs(after - before)) > 1e-5
     del rng
+
+
+# ---- p4_simulate -------------------------------------------------------------------------------------------------
+import ref_peek  # noqa: E402
+
+
+def _sequences(pf, tree, ref=False):
+    out = []
+    for p in tree.data.parts:
+        A = ref_peek.part_arrays(p.cPart) if ref else pf.partArrays(p.cPart)
+        out.append((np.array(A["sequences"]), int(A["nPatterns"]), np.array(A["patternCounts"]), np.array(A["globalInvarSitesVec"])))
+    return out
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (1, dict(nTax=12, nPatterns=500)),          # DNA GTR+I+G4: categories, invariant sites (no draw at those)
+    (2, dict(nTax=24, nPatterns=3000)),         # DNA GTR+G4
+    (3, dict(nTax=10, nPatterns=400)),          # protein LG+G4
+    (4, dict(nTax=8, nPatterns=200)),           # NDCH2, 4 parts: a composition per node, the stream runs over the parts
+])
+def test_simulate_gives_the_reference_sequences_for_the_same_seed(pkg, ref_pf, cfg, kw):
+    """pf.p4_simulate on the device consumes the caller's mt19937 stream in the reference's order (Pf/p4_treeSim.c:235-360):
+    with the same seed every simulated site of every taxon is the reference's, and so are the patterns made from them."""
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
+    for seed in (1, 20240):
+        mine.simulate(seed=seed)
+        twin.simulate(seed=seed)
+        for (s1, n1, c1, v1), (s0, n0, c0, v0) in zip(_sequences(pf, mine), _sequences(ref_pf, twin, ref=True)):
+            assert s1.shape == s0.shape
+            assert np.array_equal(s1, s0)
+            assert n1 == n0 and np.array_equal(c1[:n1], c0[:n0])
+            assert np.array_equal(v1[:n1], v0[:n0])
+        # the tree re-lays its device state for the new patterns: the likelihood of the simulated data agrees too
+        got, want = mine.calcLogLike(), twin.calcLogLike()
+        assert abs(got - want) <= 1e-9 * abs(want)
+    assert len(np.unique(_sequences(pf, mine)[0][0])) > 1
