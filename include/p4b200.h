@@ -290,13 +290,20 @@ void p4b_rngFree(void *rng);
 void p4b_rngSet(void *rng, unsigned long seed);
 unsigned long p4b_rngGet(void *rng);
 double p4b_rngUniform(void *rng);
-/* pf.p4_simulate(tree, refTree|0, gsl_rng) :2333 -> p4_simulate Pf/p4_treeSim.c:14-420 (refTree must be 0):
+/* pf.p4_simulate(tree, refTree|0, gsl_rng) :2333 -> p4_simulate Pf/p4_treeSim.c:14-420:
  * new sequences for every leaf, drawn down the tree from the root's composition through every branch's P decks
  * (rate category and invariant-or-not per site, pInvar), consuming the stream in the reference's order -- the
  * same seed gives the reference's sequences.  Writes part->sequences and globalInvarSitesVec, sets nPatterns
  * to 0: the caller re-compresses with pf.makePatterns / pf.setGlobalInvarSitesVec (p4/tree.py:9617-9626); the
  * tree lays its device state out again at its next use. */
 int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng);
+/* With a refTree (same tree and model on its own data, likelihood calculated): root state, rate category and
+ * invariant-or-not of every site are drawn from the posterior at refTree's root instead (Pf/p4_treeSim.c:200-232).
+ * pf.p4_drawAncState(tree, partNum, seqPos, draw) :2353 -> p4_drawAncStateP Pf/p4_treeSim.c:591-857: that draw for
+ * one site, draw = {chStNum, catNum, isInvar, invarChNum}; like the reference it draws from the C library's random(),
+ * which pf.reseedCRandomizer(seed) :472 seeds (srandom).  The root's conditional likelihoods must be current. */
+int p4b_drawAncState(p4b_tree t, int pNum, int seqPos, int *draw4);
+void p4b_reseedCRandomizer(int seed);
 int p4b_expectedComposition(p4b_tree t, int pNum, double *outNTaxTimesDim);
 int p4b_expectedCompositionCounts(p4b_tree t, int pNum, double *outNTaxTimesDim);
 

@@ -196,6 +196,7 @@ int treePartLogLikeBegin(Tree *t, int p);
 // simulate: device part (tree.cu).  `fill(dst, n)` must write the next n uniforms of the caller's stream.
 int treeSimulateDevice(Tree *t, int p, const uint8_t *cats, const uint8_t *rootStates, const uint8_t *invar, const int *rank,
                        int nVar, const std::function<void(double *, size_t)> &fill);
+const double *treeRootCLHost(Tree *t, int p, int *psOut);
 int treeNewtSetup(Tree *t);
 double treeNewtAround(Tree *t, double epsilon, double likeDelta);
 int nodeNewtDerivs(Node *n, double out[3]);

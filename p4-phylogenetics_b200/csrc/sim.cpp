@@ -9,6 +9,7 @@
 // recursion itself is dim-sized per node and runs on the host in the reference's order of operations.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <functional>
 #include <vector>
 
@@ -141,19 +142,110 @@ struct Rng {
     double uniform() { return get() / 4294967296.0; }
 };
 
-// p4_simulate(t, NULL, g), Pf/p4_treeSim.c:14-420.  Host: the per-site draws that need no tree (rate category,
+// p4_drawAncState (Pf/p4_treeSim.c:591-845): one draw of (root state, rate category | invariant) for one site from
+// the posterior the root's conditional likelihoods imply.  The reference draws from the C library's random()
+// (seeded through pf.reseedCRandomizer -> srandom), not from the GSL stream; so does this.
+// draw = {chStNum, catNum, isInvar, invarChNum} as p4_drawAncStateP returns them (:847-857).
+int treeDrawAncState(Tree *t, int p, int seqPos, int draw[4])
+{
+    int ps = 0;
+    const double *cl = treeRootCLHost(t, p, &ps);
+    if (!cl) return 1;
+    Part *dp = t->data->parts[p];
+    ModelPart *mp = t->model->parts[p];
+    if (seqPos < 0 || seqPos >= dp->nChar) { setError("p4_drawAncState: bad site %d", seqPos); return 1; }
+    const int dim = mp->dim, nCat = mp->nCat;
+    const int patNum = dp->sequencePositionPatternIndex[seqPos];
+    const int rc = t->root->compNums[p];
+    if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+    const double *pi = mp->comps[rc].val;
+    std::vector<double> picker((size_t)dim * (nCat + 1), 0.0);
+    const double fr = (1.0 - mp->pInvar) / (double)nCat;     // freqsTimesOneMinusPInvar, Pf/p4_tree.c:992-996
+    double sLike = 0.0;
+    int i = 0;
+    for (int c = 0; c < nCat; c++)
+        for (int s = 0; s < dim; s++) {
+            double sLikeC = pi[s] * cl[((size_t)c * dim + s) * ps + patNum];
+            sLikeC *= fr;
+            sLike += sLikeC;
+            picker[i++] = sLike;
+        }
+    if (mp->pInvar != 0.0) {
+        if (dp->globalInvarSitesArray.empty()) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+        for (int s = 0; s < dim; s++) {
+            if (dp->globalInvarSitesArray[(size_t)s * dp->nChar + patNum]) {
+                sLike += pi[s] * mp->pInvar;
+                picker[i] = sLike;
+            }
+            i++;
+        }
+    }
+    double u = (double)random() / ((double)(RAND_MAX) + 1.0);
+    u *= sLike;
+    bool gotIt = false;
+    int k = 0, c = 0, s = 0;
+    for (c = 0; c < nCat; c++) {
+        for (s = 0; s < dim; s++) {
+            if (u < picker[k]) gotIt = true;
+            k++;
+            if (gotIt) break;
+        }
+        if (gotIt) break;
+    }
+    bool isInvar = false;
+    if (!gotIt && mp->pInvarFree) {                          // :780-792: only a FREE pInvar is looked at here
+        for (s = 0; s < dim; s++) {
+            if (dp->globalInvarSitesArray[(size_t)s * dp->nChar + patNum])
+                if (u < picker[k]) { isInvar = true; gotIt = true; }
+            k++;
+            if (gotIt) break;
+        }
+    }
+    if (!gotIt) { setError("Something is wrong with the ancestral state picker. gotIt is zero."); return 1; }
+    if (!isInvar) { draw[0] = s; draw[1] = c; draw[2] = 0; draw[3] = -1; }
+    else { draw[0] = -1; draw[1] = -1; draw[2] = 1; draw[3] = s; }
+    return 0;
+}
+
+// p4_simulate(t, refTree, g), Pf/p4_treeSim.c:14-420.  Host: the per-site draws that need no tree (rate category,
 // root state, invariant or not -- :235-300, in the reference's order over parts) and the stream of uniforms of the
 // mutation phase, which the reference consumes node by node in preOrder and, within a node, site by site over the
 // VARIABLE sites only (:330-360).  Device (tree.cu): picker decks (running row sums of the P decks,
 // Pf/p4_node.c p4_calculatePickerDecks) and one thread per site walking the nodes.
-int treeSimulate(Tree *t, Rng *g)
+int treeSimulate(Tree *t, Tree *refTree, Rng *g)
 {
     if (!t->dev) { setError("tree has no device state"); return 1; }
     if (!t->root) { setError("p4_simulate: the tree has no root"); return 1; }
     Data *d = t->data;
     const int nParts = d->nParts;
     std::vector<std::vector<uint8_t>> cats(nParts), rootSt(nParts), inv(nParts);
+    if (refTree) {
+        // :200-232: root state, rate category and invariant-or-not of every site drawn from the posterior at the
+        // root of refTree (p4_drawAncState, the C library's random()), before this tree's data are touched
+        if (refTree->data == d) { setError("p4_simulate: refTree must have its own data"); return 1; }
+        if (refTree->data->nParts != nParts) { setError("p4_simulate: refTree has %d parts, the tree %d", refTree->data->nParts, nParts); return 1; }
+        for (int p = 0; p < nParts; p++) {
+            Part *dp = d->parts[p], *rp = refTree->data->parts[p];
+            if (rp->nChar != dp->nChar) { setError("p4_simulate: part %d of refTree has %d sites, the tree's %d", p, rp->nChar, dp->nChar); return 1; }
+            cats[p].assign(dp->nChar, 0);
+            rootSt[p].assign(dp->nChar, 0);
+            inv[p].assign(dp->nChar, 0);
+            for (int k = 0; k < rp->nChar; k++) {
+                int draw[4];
+                if (treeDrawAncState(refTree, p, k, draw)) return 1;
+                if (draw[2]) { rootSt[p][k] = (uint8_t)draw[3]; inv[p][k] = 1; }
+                else { cats[p][k] = (uint8_t)draw[1]; rootSt[p][k] = (uint8_t)draw[0]; }
+            }
+        }
+    }
     for (int p = 0; p < nParts; p++) d->parts[p]->nPatterns = 0;                       // :60-62
+    if (refTree) {
+        for (int p = 0; p < nParts; p++) {
+            Part *dp = d->parts[p];
+            dp->globalInvarSitesVec.assign(dp->nChar, 0);
+            for (int k = 0; k < dp->nChar; k++) dp->globalInvarSitesVec[k] = inv[p][k];
+        }
+    } else {
     for (int p = 0; p < nParts; p++) {                                                 // rate categories, :235-246
         Part *dp = d->parts[p];
         ModelPart *mp = t->model->parts[p];
@@ -191,6 +283,7 @@ int treeSimulate(Tree *t, Rng *g)
                 dp->globalInvarSitesVec[i] = inv[p][i];
             }
     }
+    }
     if (treeCalculateAllBigPDecks(t)) return 1;                                        // :315-321
     for (int p = 0; p < nParts; p++) {                                                 // mutation, :330-360
         Part *dp = d->parts[p];
@@ -226,9 +319,14 @@ double p4b_rngUniform(void *g) { return g ? ((Rng *)g)->uniform() : 0.0; }
 int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng)
 {
     if (!t || !rng) { setError("p4b_simulate: NULL argument"); return 1; }
-    if (refTree) { setError("p4_simulate with a refTree (ancestral states drawn from another tree's conditional likelihoods, Pf/p4_treeSim.c:200-232) is not available on this engine"); return 1; }
-    return treeSimulate((Tree *)t, (Rng *)rng);
+    return treeSimulate((Tree *)t, (Tree *)refTree, (Rng *)rng);
 }
+int p4b_drawAncState(p4b_tree t, int pNum, int seqPos, int *draw4)
+{
+    if (!t || !draw4) { setError("p4b_drawAncState: NULL argument"); return 1; }
+    return treeDrawAncState((Tree *)t, pNum, seqPos, draw4);
+}
+void p4b_reseedCRandomizer(int seed) { srandom((unsigned)seed); }
 int p4b_expectedComposition(p4b_tree t, int pNum, double *out)
 {
     if (!t || !out) { setError("p4b_expectedComposition: NULL argument"); return 1; }

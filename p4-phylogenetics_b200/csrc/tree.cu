@@ -271,6 +271,8 @@ struct PartLayout {
 struct TreeDevice {
     std::vector<PartLayout> parts;
     std::vector<uint64_t> dataVersion;   // per part: Part::version this device state was laid out for
+    std::vector<std::vector<double>> rootCLHost;   // per part: host copy of the root's CL (p4_drawAncState), [K][ps]
+    std::vector<uint64_t> rootCLStamp;             // ... and the computation id it is a copy of
     // Node-level CL calls on parts the whole-tree kernel serves are not launched one by one: they queue
     // here (per part, in call order) and run as ONE step-list launch when something needs their result --
     // normally p4_partLogLike, which then also gets the root reduction fused in.
@@ -2467,6 +2469,37 @@ int treeSimulateDevice(Tree *t, int p, const uint8_t *cats, const uint8_t *rootS
     G.stageDirtySinceSync = false;
     G.stageHead = 0;
     return rc;
+}
+
+
+// Host copy of the root's CL of part p, refreshed when the root's CL was recomputed since (p4_drawAncState reads one
+// column per call; p4 calls it once per site).  Returns NULL on error.
+const double *treeRootCLHost(Tree *t, int p, int *psOut)
+{
+    if (!t->dev) { setError("tree has no device state"); return nullptr; }
+    if (p < 0 || p >= t->nParts) { setError("bad part %d", p); return nullptr; }
+    if (G.world > 1) { setError("p4_drawAncState is not available when patterns are sharded over several processes"); return nullptr; }
+    if (ensureFresh(t, true)) return nullptr;
+    TreeDevice *d = t->dev;
+    Node *root = t->root;
+    if (!root || root->clSlot[p] < 0) { setError("the root has no conditional likelihoods (calculate the likelihood first)"); return nullptr; }
+    if (treeEnsureResident(t, p)) return nullptr;
+    PartLayout &L = d->parts[p];
+    if (d->rootCLHost.size() != (size_t)t->nParts) {
+        d->rootCLHost.assign(t->nParts, std::vector<double>());
+        d->rootCLStamp.assign(t->nParts, 0);
+    }
+    if (d->rootCLStamp[p] != root->clStamp[p] || root->clStamp[p] == 0 || d->rootCLHost[p].size() != L.clNodeDoubles) {
+        d->rootCLHost[p].resize(L.clNodeDoubles);
+        if (cudaMemcpyAsync(d->rootCLHost[p].data(), nodeCL(root, p), L.clNodeDoubles * sizeof(double), cudaMemcpyDeviceToHost, G.stream) != cudaSuccess ||
+            streamSync()) {
+            setError("p4_drawAncState: cannot read the root's conditional likelihoods");
+            return nullptr;
+        }
+        d->rootCLStamp[p] = root->clStamp[p];
+    }
+    *psOut = L.ps;
+    return d->rootCLHost[p].data();
 }
 
 void *engineStream() { return (void *)G.stream; }

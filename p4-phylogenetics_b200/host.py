@@ -473,9 +473,10 @@ class Tree:
             print("optLogLike = %f" % self.logLike)
         return self.logLike
 
-    def simulate(self, seed=None, calculatePatterns=True):
-        """Tree.simulate() (p4/tree.py:9527-9637, refTree=None): new data down this tree with its model, into its own
-        data parts.  ``seed`` (an addition) re-seeds the stream kept on the tree, p4 keeps it in var.gsl_rng."""
+    def simulate(self, seed=None, calculatePatterns=True, refTree=None):
+        """Tree.simulate() (p4/tree.py:9527-9637): new data down this tree with its model, into its own data parts; with a
+        refTree (same tree and model, its own data, likelihood calculated) the root states come from its posterior.
+        ``seed`` (an addition) re-seeds the stream kept on the tree, p4 keeps it in var.gsl_rng."""
         pf = self.pf
         if getattr(self, "gsl_rng", None) is None:
             self.gsl_rng = pf.gsl_rng_get()
@@ -485,11 +486,33 @@ class Tree:
         if seed is not None:
             pf.gsl_rng_set(self.gsl_rng, int(seed))
         self._commonCStuff()
-        pf.p4_simulate(self.cTree, 0, self.gsl_rng)
+        if refTree is not None:
+            if not refTree.cTree:
+                refTree.calcLogLike()
+            assert refTree.data.cData != self.data.cData
+        pf.p4_simulate(self.cTree, refTree.cTree if refTree is not None else 0, self.gsl_rng)
         if calculatePatterns:
             for p in self.data.parts:
                 pf.makePatterns(p.cPart)
                 pf.setGlobalInvarSitesVec(p.cPart)
+
+    def ancestralStateDraw(self):
+        """Tree.ancestralStateDraw() (p4/tree.py:9640-9677): one draw of the root's state at every site, as a string."""
+        pf = self.pf
+        self._commonCStuff()
+        self.logLike = pf.p4_treeLogLike(self.cTree, 0)
+        draw = np.empty(4, dtype=np.int32)
+        out = []
+        for pNum, dp in enumerate(self.data.parts):
+            for seqPos in range(dp.nChar):
+                pf.p4_drawAncState(self.cTree, pNum, seqPos, draw)
+                if draw[1] >= 0:
+                    out.append(dp.symbols[draw[0]])
+                elif draw[2]:
+                    out.append(dp.symbols[draw[3]])
+                else:
+                    raise RuntimeError("Tree.ancestralStateDraw(). Problem with returned draw.  Got %s" % draw)
+        return "".join(out)
 
     def getSiteLikes(self):
         self._commonCStuff()

@@ -150,6 +150,8 @@ _sig("p4b_rngSet", None, _vp, C.c_ulong)
 _sig("p4b_rngGet", C.c_ulong, _vp)
 _sig("p4b_rngUniform", _d, _vp)
 _sig("p4b_simulate", _i, _vp, _vp, _vp)
+_sig("p4b_drawAncState", _i, _vp, _i, _i, _vp)
+_sig("p4b_reseedCRandomizer", None, _i)
 _sig("p4b_expectedComposition", _i, _vp, _i, _vp)
 _sig("p4b_expectedCompositionCounts", _i, _vp, _i, _vp)
 _sig("p4b_newtSetup", _i, _vp)
@@ -740,6 +742,17 @@ def p4_simulate(cTree, cRefTree, g):
     """pf.p4_simulate(cTree, cRefTree|0, gsl_rng) (Pf/pfmodule.c:2333, Pf/p4_treeSim.c:14-420): simulate new
     sequences down the tree on the device; the same seed gives the reference's sequences."""
     _ok(_lib.p4b_simulate(cTree, cRefTree if cRefTree else None, g))
+
+
+def p4_drawAncState(cTree, partNum, seqPos, draw):
+    """pf.p4_drawAncState(cTree, partNum, seqPos, draw) (Pf/pfmodule.c:2353): fills the int32 array ``draw`` with
+    {chStNum, catNum, isInvar, invarChNum} for one draw from the root's posterior at that site."""
+    _ok(_lib.p4b_drawAncState(cTree, int(partNum), int(seqPos), _arr(draw, np.int32, "draw")))
+
+
+def reseedCRandomizer(seed):
+    """pf.reseedCRandomizer(seed) (Pf/pfmodule.c:472): srandom(seed)."""
+    _lib.p4b_reseedCRandomizer(int(seed))
 
 
 def p4_expectedComposition(cTree):

@@ -96,3 +96,56 @@ def test_simulate_gives_the_reference_sequences_for_the_same_seed(pkg, ref_pf, c
         got, want = mine.calcLogLike(), twin.calcLogLike()
         assert abs(got - want) <= 1e-9 * abs(want)
     assert len(np.unique(_sequences(pf, mine)[0][0])) > 1
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (1, dict(nTax=12, nPatterns=300)),          # pInvar: the reference looks at the invariant share only when pInvar is FREE
+    (3, dict(nTax=8, nPatterns=150)),           # protein, no pInvar
+])
+@pytest.mark.parametrize("pInvarFree", [0, 1])
+def test_draw_anc_state_matches_reference(pkg, ref_pf, cfg, kw, pInvarFree):
+    """pf.p4_drawAncState: one draw per site from the root's posterior, from the C library's random() like the reference
+    (pf.reseedCRandomizer seeds it): the same seed gives the same draws, site by site."""
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
+    for t in (mine, twin):
+        t.model.parts[0].pInvar.free = pInvarFree
+    pf.reseedCRandomizer(77)
+    got = mine.ancestralStateDraw()
+    ref_pf.reseedCRandomizer(77)
+    want = twin.ancestralStateDraw()
+    assert len(got) == len(want) == mine.data.parts[0].nChar
+    assert got == want
+    d1, d0 = np.empty(4, np.int32), np.empty(4, np.int32)
+    pf.reseedCRandomizer(5)
+    a = []
+    for k in range(50):
+        pf.p4_drawAncState(mine.cTree, 0, k, d1)
+        a.append(d1.tolist())
+    ref_pf.reseedCRandomizer(5)
+    b = []
+    for k in range(50):
+        ref_pf.p4_drawAncState(twin.cTree, 0, k, d0)
+        b.append(d0.tolist())
+    assert a == b
+
+
+def test_simulate_with_a_ref_tree(pkg, ref_pf):
+    """Tree.simulate(refTree=...): root states, categories and invariant flags from the posterior at refTree's root
+    (C library stream), the walk down the tree on the mt19937 stream; same seeds, same sequences as the reference."""
+    pf = pkg.pf
+    mine, twin = build_pair(pkg, ref_pf, 1, nTax=10, nPatterns=300)
+    refMine, refTwin = build_pair(pkg, ref_pf, 1, nTax=10, nPatterns=300)      # same tree + model on its own data objects
+    for t in (mine, twin, refMine, refTwin):
+        t.model.parts[0].pInvar.free = 1
+    refMine.calcLogLike()
+    refTwin.calcLogLike()
+    pf.reseedCRandomizer(9)
+    mine.simulate(seed=31, refTree=refMine)
+    ref_pf.reseedCRandomizer(9)
+    twin.simulate(seed=31, refTree=refTwin)
+    (s1, n1, c1, v1), (s0, n0, c0, v0) = _sequences(pf, mine)[0], _sequences(ref_pf, twin, ref=True)[0]
+    assert np.array_equal(s1, s0)
+    assert n1 == n0 and np.array_equal(c1[:n1], c0[:n0])
+    got, want = mine.calcLogLike(), twin.calcLogLike()
+    assert abs(got - want) <= 1e-9 * abs(want)
