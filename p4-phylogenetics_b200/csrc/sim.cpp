@@ -246,43 +246,43 @@ int treeSimulate(Tree *t, Tree *refTree, Rng *g)
             for (int k = 0; k < dp->nChar; k++) dp->globalInvarSitesVec[k] = inv[p][k];
         }
     } else {
-    for (int p = 0; p < nParts; p++) {                                                 // rate categories, :235-246
-        Part *dp = d->parts[p];
-        ModelPart *mp = t->model->parts[p];
-        if (mp->dim > 255 || mp->nCat > 255) { setError("p4_simulate: dim or nCat too large"); return 1; }
-        cats[p].assign(dp->nChar, 0);
-        if (mp->nCat > 1)
-            for (int i = 0; i < dp->nChar; i++) cats[p][i] = (uint8_t)(int)floor(((double)mp->nCat) * g->uniform());
-    }
-    for (int p = 0; p < nParts; p++) {                                                 // root states, :256-277
-        Part *dp = d->parts[p];
-        ModelPart *mp = t->model->parts[p];
-        const int rc = t->root->compNums[p];
-        if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
-        const double *pi = mp->comps[rc].val;
-        std::vector<double> picker(mp->dim);
-        picker[0] = pi[0];
-        for (int j = 1; j < mp->dim - 1; j++) picker[j] = picker[j - 1] + pi[j];
-        picker[mp->dim - 1] = 1.0;
-        rootSt[p].assign(dp->nChar, 0);
-        for (int j = 0; j < dp->nChar; j++) {
-            const double u = g->uniform();
-            for (int k = 0; k < mp->dim; k++)
-                if (u < picker[k]) { rootSt[p][j] = (uint8_t)k; break; }
+        for (int p = 0; p < nParts; p++) {                                                 // rate categories, :235-246
+            Part *dp = d->parts[p];
+            ModelPart *mp = t->model->parts[p];
+            if (mp->dim > 255 || mp->nCat > 255) { setError("p4_simulate: dim or nCat too large"); return 1; }
+            cats[p].assign(dp->nChar, 0);
+            if (mp->nCat > 1)
+                for (int i = 0; i < dp->nChar; i++) cats[p][i] = (uint8_t)(int)floor(((double)mp->nCat) * g->uniform());
         }
-    }
-    for (int p = 0; p < nParts; p++) {                                                 // invariant sites, :284-300
-        Part *dp = d->parts[p];
-        ModelPart *mp = t->model->parts[p];
-        inv[p].assign(dp->nChar, 0);
-        dp->globalInvarSitesVec.assign(dp->nChar, 0);
-        if (mp->pInvar > 0.0)
-            for (int i = 0; i < dp->nChar; i++) {
+        for (int p = 0; p < nParts; p++) {                                                 // root states, :256-277
+            Part *dp = d->parts[p];
+            ModelPart *mp = t->model->parts[p];
+            const int rc = t->root->compNums[p];
+            if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+            const double *pi = mp->comps[rc].val;
+            std::vector<double> picker(mp->dim);
+            picker[0] = pi[0];
+            for (int j = 1; j < mp->dim - 1; j++) picker[j] = picker[j - 1] + pi[j];
+            picker[mp->dim - 1] = 1.0;
+            rootSt[p].assign(dp->nChar, 0);
+            for (int j = 0; j < dp->nChar; j++) {
                 const double u = g->uniform();
-                inv[p][i] = u < mp->pInvar ? 1 : 0;
-                dp->globalInvarSitesVec[i] = inv[p][i];
+                for (int k = 0; k < mp->dim; k++)
+                    if (u < picker[k]) { rootSt[p][j] = (uint8_t)k; break; }
             }
-    }
+        }
+        for (int p = 0; p < nParts; p++) {                                                 // invariant sites, :284-300
+            Part *dp = d->parts[p];
+            ModelPart *mp = t->model->parts[p];
+            inv[p].assign(dp->nChar, 0);
+            dp->globalInvarSitesVec.assign(dp->nChar, 0);
+            if (mp->pInvar > 0.0)
+                for (int i = 0; i < dp->nChar; i++) {
+                    const double u = g->uniform();
+                    inv[p][i] = u < mp->pInvar ? 1 : 0;
+                    dp->globalInvarSitesVec[i] = inv[p][i];
+                }
+        }
     }
     if (treeCalculateAllBigPDecks(t)) return 1;                                        // :315-321
     for (int p = 0; p < nParts; p++) {                                                 // mutation, :330-360
