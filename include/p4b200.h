@@ -133,6 +133,18 @@ int p4b_partPatternCount(p4b_part p);                                    /* pf.p
  * p4/data.py:223-258, p4/tree.py:8182).  Needs patterns; any gap, '?' or ambiguity is an error.
  * Returns non-zero and leaves *out untouched on error. */
 int p4b_getUnconstrainedLogLike(p4b_part p, double *out);
+/* The part's own statistics and views (host; csrc/partstats.cpp), each equal to the reference's:
+ * pf.singleSequenceBaseCounts :219 -> Pf/part.c:556; pf.symbolSequences :233 -> :604 (out: nTax*nChar + 1 chars);
+ * pf.partSequenceSitesCount :363 -> :1068; pf.pokePartTaxListAtIndex :326; pf.partComposition :350 -> :850-1066;
+ * pf.partMeanNCharsPerSite :261 -> :1419; pf.partSimpleConstantSitesCount :275 -> :1459; pf.partBigXSquared :296 -> :1490. */
+int p4b_singleSequenceBaseCounts(p4b_part p, int seqNum, int *outDim);
+int p4b_symbolSequences(p4b_part p, char *outNTaxTimesNCharPlus1);
+int p4b_partSequenceSitesCount(p4b_part p, int seqNum);
+int p4b_pokePartTaxListAtIndex(p4b_part p, int val, int index);
+int p4b_partComposition(p4b_part p, double *outDim);
+double p4b_partMeanNCharsPerSite(p4b_part p);
+int p4b_partSimpleConstantSitesCount(p4b_part p);
+double p4b_partBigXSquared(p4b_part p);
 /* pf.getSiteLikes :378 -- copies part->siteLikes (nChar doubles) filled by the
  * last p4b_partLogLike(..., getSiteLikes=1).  Returns nChar, or -1 if none. */
 int p4b_getSiteLikes(p4b_part p, double *out, int nOut);

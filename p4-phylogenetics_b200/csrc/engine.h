@@ -43,6 +43,7 @@ struct Part {
     std::vector<int> globalInvarSitesVec;   // [nChar], empty until set (:45)
     std::vector<int> globalInvarSitesArray; // [dim][nChar] (:46)
     std::vector<double> siteLikes;          // [nChar], empty until asked for (:47)
+    std::vector<int> taxList;               // [nTax] which sequences partComposition looks at (:49); empty until poked
     uint64_t version = 1;         // bumped whenever patterns / invar arrays change
     // Leaf lookup tables have one column per tip code index:
     //   0..dim-1 the states, dim = "matches everything" (gap, '?', N-like

@@ -69,6 +69,23 @@ class Part:
 class Alignment:
     """Sequences of one datatype; ``_initParts`` builds the C part (one part per alignment)."""
 
+    def resetSequencesFromParts(self):
+        """Alignment.resetSequencesFromParts() (p4/alignment.py:5930-5970, one part per alignment here): bring the part's
+        sequences -- e.g. freshly simulated ones -- back as strings."""
+        p = self.parts[0]
+        allSeq = self.pf.symbolSequences(p.cPart)
+        asBytes = isinstance(self.sequences[0], (bytes, bytearray))
+        self.sequences = [(allSeq[i * p.nChar:(i + 1) * p.nChar].encode("latin-1") if asBytes else allSeq[i * p.nChar:(i + 1) * p.nChar])
+                          for i in range(p.nTax)]
+
+    def composition(self, sequenceNumberList=None):
+        """Part.composition() (p4/part.py:41-70): composition over the chosen sequences (all by default), ambiguities shared out."""
+        p = self.parts[0]
+        chosen = set(range(p.nTax)) if sequenceNumberList is None else set(sequenceNumberList)
+        for i in range(p.nTax):
+            self.pf.pokePartTaxListAtIndex(p.cPart, 1 if i in chosen else 0, i)
+        return self.pf.partComposition(p.cPart)
+
     def __init__(self, pf, sequences, symbols, equates):
         self.pf = pf
         self.sequences = sequences       # list of str or bytes, all the same length
@@ -473,7 +490,7 @@ class Tree:
             print("optLogLike = %f" % self.logLike)
         return self.logLike
 
-    def simulate(self, seed=None, calculatePatterns=True, refTree=None):
+    def simulate(self, seed=None, calculatePatterns=True, refTree=None, resetSequences=True):
         """Tree.simulate() (p4/tree.py:9527-9637): new data down this tree with its model, into its own data parts; with a
         refTree (same tree and model, its own data, likelihood calculated) the root states come from its posterior.
         ``seed`` (an addition) re-seeds the stream kept on the tree, p4 keeps it in var.gsl_rng."""
@@ -495,6 +512,9 @@ class Tree:
             for p in self.data.parts:
                 pf.makePatterns(p.cPart)
                 pf.setGlobalInvarSitesVec(p.cPart)
+        if resetSequences:                       # Data.resetSequencesFromParts, p4/tree.py:9627-9628
+            for a in self.data.alignments:
+                a.resetSequencesFromParts()
 
     def ancestralStateDraw(self):
         """Tree.ancestralStateDraw() (p4/tree.py:9640-9677): one draw of the root's state at every site, as a string."""

@@ -94,6 +94,14 @@ _sig("p4b_makePatterns", _i, _vp)
 _sig("p4b_setGlobalInvarSitesVec", _i, _vp)
 _sig("p4b_partPatternCount", _i, _vp)
 _sig("p4b_getUnconstrainedLogLike", _i, _vp, _dp)
+_sig("p4b_singleSequenceBaseCounts", _i, _vp, _i, _vp)
+_sig("p4b_symbolSequences", _i, _vp, _vp)
+_sig("p4b_partSequenceSitesCount", _i, _vp, _i)
+_sig("p4b_pokePartTaxListAtIndex", _i, _vp, _i, _i)
+_sig("p4b_partComposition", _i, _vp, _vp)
+_sig("p4b_partMeanNCharsPerSite", _d, _vp)
+_sig("p4b_partSimpleConstantSitesCount", _i, _vp)
+_sig("p4b_partBigXSquared", _d, _vp)
 _sig("p4b_getSiteLikes", _i, _vp, _vp, _i)
 for _n in ("Sequences", "Patterns", "PatternCounts", "SequencePositionPatternIndex", "GlobalInvarSitesVec",
            "GlobalInvarSitesArray", "Equates"):
@@ -342,6 +350,56 @@ def setGlobalInvarSitesVec(cPart):
 
 def partPatternCount(cPart):
     return _lib.p4b_partPatternCount(cPart)
+
+
+def singleSequenceBaseCounts(cPart, seqNum):
+    """pf.singleSequenceBaseCounts(cPart, seqNum) -> list of ints (Pf/pfmodule.c:219, Pf/part.c:556-602)."""
+    out = np.zeros(_lib.p4b_partDim(cPart), dtype=np.int32)
+    _ok(_lib.p4b_singleSequenceBaseCounts(cPart, int(seqNum), out.ctypes.data))
+    return [int(v) for v in out]
+
+
+def symbolSequences(cPart):
+    """pf.symbolSequences(cPart) -> all sequences as one string of nTax*nChar symbols (Pf/pfmodule.c:233, Pf/part.c:604-680)."""
+    n = _lib.p4b_partNTax(cPart) * _lib.p4b_partNChar(cPart)
+    buf = C.create_string_buffer(n + 1)
+    _ok(_lib.p4b_symbolSequences(cPart, C.cast(buf, C.c_void_p)))
+    return buf.raw[:n].decode("latin-1")
+
+
+def partSequenceSitesCount(cPart, seqNum):
+    """pf.partSequenceSitesCount(cPart, seqNum): sites that are neither gap nor '?' (Pf/pfmodule.c:363, Pf/part.c:1068)."""
+    v = _lib.p4b_partSequenceSitesCount(cPart, int(seqNum))
+    if v < 0:
+        _fatal()
+    return v
+
+
+def pokePartTaxListAtIndex(cPart, val, index):
+    """pf.pokePartTaxListAtIndex(cPart, val, index) (Pf/pfmodule.c:326): select the sequences partComposition looks at."""
+    _ok(_lib.p4b_pokePartTaxListAtIndex(cPart, int(val), int(index)))
+
+
+def partComposition(cPart):
+    """pf.partComposition(cPart) -> list of floats (Pf/pfmodule.c:350, Pf/part.c:850-1066)."""
+    out = np.zeros(_lib.p4b_partDim(cPart), dtype=np.float64)
+    _ok(_lib.p4b_partComposition(cPart, out.ctypes.data))
+    return [float(v) for v in out]
+
+
+def partMeanNCharsPerSite(cPart):
+    """pf.partMeanNCharsPerSite(cPart) (Pf/pfmodule.c:261, Pf/part.c:1419)."""
+    return _lib.p4b_partMeanNCharsPerSite(cPart)
+
+
+def partSimpleConstantSitesCount(cPart):
+    """pf.partSimpleConstantSitesCount(cPart) (Pf/pfmodule.c:275, Pf/part.c:1459)."""
+    return _lib.p4b_partSimpleConstantSitesCount(cPart)
+
+
+def partBigXSquared(cPart):
+    """pf.partBigXSquared(cPart) (Pf/pfmodule.c:296, Pf/part.c:1490); -2.0 when the data hold gaps or ambiguities."""
+    return _lib.p4b_partBigXSquared(cPart)
 
 
 def getUnconstrainedLogLike(cPart):

@@ -116,6 +116,33 @@ def test_rng_stream_is_mt19937_with_gsl_seeding(pkg, ref_pf):
     pf.gsl_rng_free(g)
 
 
+@pytest.mark.parametrize("kind,gaps", [("dna", 0.05), ("dna", 0.0), ("protein", 0.04)])
+def test_part_statistics_equal_the_reference(pkg, ref_pf, kind, gaps):
+    """The data part's own statistics and views (csrc/partstats.cpp vs Pf/part.c): equal values, not close ones."""
+    P = pkg
+    rng = np.random.Generator(np.random.PCG64(31))
+    t = P.synth.random_tree(P.pf, 9, rng)
+    mp = P.synth.dna_model_part(0, rng, 4) if kind == "dna" else P.synth.protein_model_part(0, rng)
+    aln = P.synth.make_alignment(P.pf, t, mp, 300, rng, kind, gap_frac=gaps, ambig_frac=gaps)
+    mine = aln._initParts()
+    theirs = P.host.Alignment(ref_pf, aln.sequences, aln.symbols, aln.equates)._initParts()
+    a, b, pf = mine.cPart, theirs.cPart, P.pf
+    assert pf.symbolSequences(a) == ref_pf.symbolSequences(b)
+    for k in range(9):
+        assert pf.singleSequenceBaseCounts(a, k) == list(ref_pf.singleSequenceBaseCounts(b, k))
+        assert pf.partSequenceSitesCount(a, k) == ref_pf.partSequenceSitesCount(b, k)
+    for sel in ([1] * 9, [1, 0, 1, 0, 0, 1, 1, 0, 1], [0] * 8 + [1]):
+        for i, v in enumerate(sel):
+            pf.pokePartTaxListAtIndex(a, v, i)
+            ref_pf.pokePartTaxListAtIndex(b, v, i)
+        assert pf.partComposition(a) == list(ref_pf.partComposition(b))
+    assert pf.partMeanNCharsPerSite(a) == ref_pf.partMeanNCharsPerSite(b)
+    assert pf.partSimpleConstantSitesCount(a) == ref_pf.partSimpleConstantSitesCount(b)
+    assert pf.partBigXSquared(a) == ref_pf.partBigXSquared(b)
+    P.pf.freePart(a)
+    ref_pf.freePart(b)
+
+
 def test_gamma_rates_bit_identical_to_reference(pkg, ref_pf):
     for alpha in (0.1, 0.2, 0.5, 0.73, 1.0, 2.7, 10.0, 100.0, 299.0):
         for K in (2, 3, 4, 5, 8, 16):

@@ -38,10 +38,10 @@ def main():
     a = ap.parse_args()
     pf = P.pf
     tree = build(pf, a.taxa, a.sites)
-    tree.simulate(seed=3, calculatePatterns=False)         # warm-up: allocations
+    tree.simulate(seed=3, calculatePatterns=False, resetSequences=False)         # warm-up: allocations
     k0 = pf.kernelLaunchCount()
     t0 = time.perf_counter()
-    tree.simulate(seed=4, calculatePatterns=False)
+    tree.simulate(seed=4, calculatePatterns=False, resetSequences=False)
     sim_s = time.perf_counter() - t0
     launches = pf.kernelLaunchCount() - k0
     t0 = time.perf_counter()
@@ -61,9 +61,9 @@ def main():
         if ref_loader.have_ref_pf():
             rpf = ref_loader.load_ref_pf()
             small = build(rpf, a.taxa, a.cpu_sites)
-            small.simulate(seed=3, calculatePatterns=False)
+            small.simulate(seed=3, calculatePatterns=False, resetSequences=False)
             t0 = time.perf_counter()
-            small.simulate(seed=4, calculatePatterns=False)
+            small.simulate(seed=4, calculatePatterns=False, resetSequences=False)
             t = time.perf_counter() - t0
             out["reference_1core"] = {"sites": a.cpu_sites, "simulate_s": t, "scaled_to_workload_s": t * a.sites / a.cpu_sites}
             out["speedup_vs_reference_1core"] = (t * a.sites / a.cpu_sites) / sim_s
