@@ -315,6 +315,9 @@ int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng);
  * one site, draw = {chStNum, catNum, isInvar, invarChNum}; like the reference it draws from the C library's random(),
  * which pf.reseedCRandomizer(seed) :472 seeds (srandom).  The root's conditional likelihoods must be current. */
 int p4b_drawAncState(p4b_tree t, int pNum, int seqPos, int *draw4);
+/* pf.bootstrapData(referenceData, toFillData, gsl_rng) :90 -> bootstrapData Pf/data.c:107-139: resample the sites of every part
+ * with replacement on the caller's stream (gsl_rng_uniform_int), then pf.makePatterns on the filled parts. */
+int p4b_bootstrapData(p4b_data reference, p4b_data toFill, void *rng);
 void p4b_reseedCRandomizer(int seed);
 int p4b_expectedComposition(p4b_tree t, int pNum, double *outNTaxTimesDim);
 int p4b_expectedCompositionCounts(p4b_tree t, int pNum, double *outNTaxTimesDim);

@@ -140,6 +140,16 @@ struct Rng {
         return y;
     }
     double uniform() { return get() / 4294967296.0; }
+    // gsl_rng_uniform_int for a generator with min 0 and max 2^32 - 1: equal-width bins, draws beyond the last bin rejected
+    unsigned long uniformInt(unsigned long n)
+    {
+        const unsigned long range = 0xffffffffUL;
+        if (n == 0 || n > range) return 0;
+        const unsigned long scale = range / n;
+        unsigned long k;
+        do { k = get() / scale; } while (k >= n);
+        return k;
+    }
 };
 
 // p4_drawAncState (Pf/p4_treeSim.c:591-845): one draw of (root state, rate category | invariant) for one site from
@@ -320,6 +330,26 @@ int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng)
 {
     if (!t || !rng) { setError("p4b_simulate: NULL argument"); return 1; }
     return treeSimulate((Tree *)t, (Tree *)refTree, (Rng *)rng);
+}
+/* pf.bootstrapData(referenceData, toFillData, gsl_rng) Pf/pfmodule.c:90 -> bootstrapData Pf/data.c:107-139: every site of every
+ * part of toFill becomes a site of the reference part drawn with gsl_rng_uniform_int on the caller's stream, then makePatterns. */
+int p4b_bootstrapData(p4b_data reference, p4b_data toFill, void *rng)
+{
+    Data *ref = (Data *)reference, *out = (Data *)toFill;
+    Rng *g = (Rng *)rng;
+    if (!ref || !out || !g) { setError("bootstrapData: NULL argument"); return 1; }
+    if (ref->nParts < out->nParts) { setError("bootstrapData: the reference has %d parts, the data to fill %d", ref->nParts, out->nParts); return 1; }
+    for (int p = 0; p < out->nParts; p++) {
+        Part *rp = ref->parts[p], *fp = out->parts[p];
+        if (!rp || !fp) { setError("bootstrapData: part %d missing", p); return 1; }
+        if (rp->nTax != fp->nTax || rp->nChar < fp->nChar) { setError("bootstrapData: part %d of the two data objects differ in shape", p); return 1; }
+        for (int pos = 0; pos < fp->nChar; pos++) {
+            const int ran = (int)g->uniformInt((unsigned long)fp->nChar);
+            for (int t = 0; t < fp->nTax; t++) fp->sequences[(size_t)t * fp->nChar + pos] = rp->sequences[(size_t)t * rp->nChar + ran];
+        }
+        if (makePatterns(fp)) return 1;
+    }
+    return 0;
 }
 int p4b_drawAncState(p4b_tree t, int pNum, int seqPos, int *draw4)
 {

@@ -159,6 +159,7 @@ _sig("p4b_rngGet", C.c_ulong, _vp)
 _sig("p4b_rngUniform", _d, _vp)
 _sig("p4b_simulate", _i, _vp, _vp, _vp)
 _sig("p4b_drawAncState", _i, _vp, _i, _i, _vp)
+_sig("p4b_bootstrapData", _i, _vp, _vp, _vp)
 _sig("p4b_reseedCRandomizer", None, _i)
 _sig("p4b_expectedComposition", _i, _vp, _i, _vp)
 _sig("p4b_expectedCompositionCounts", _i, _vp, _i, _vp)
@@ -806,6 +807,11 @@ def p4_drawAncState(cTree, partNum, seqPos, draw):
     """pf.p4_drawAncState(cTree, partNum, seqPos, draw) (Pf/pfmodule.c:2353): fills the int32 array ``draw`` with
     {chStNum, catNum, isInvar, invarChNum} for one draw from the root's posterior at that site."""
     _ok(_lib.p4b_drawAncState(cTree, int(partNum), int(seqPos), _arr(draw, np.int32, "draw")))
+
+
+def bootstrapData(cDataReference, cDataToFill, g):
+    """pf.bootstrapData(referenceData, toFillData, gsl_rng) (Pf/pfmodule.c:90, Pf/data.c:107-139)."""
+    _ok(_lib.p4b_bootstrapData(cDataReference, cDataToFill, g))
 
 
 def reseedCRandomizer(seed):

@@ -143,6 +143,30 @@ def test_part_statistics_equal_the_reference(pkg, ref_pf, kind, gaps):
     ref_pf.freePart(b)
 
 
+def test_bootstrap_equals_the_reference_for_the_same_seed(pkg, ref_pf):
+    """pf.bootstrapData: the same mt19937 seed resamples the same columns (gsl_rng_uniform_int), patterns re-made."""
+    P, H = pkg, pkg.host
+    rng = np.random.Generator(np.random.PCG64(12))
+    t = P.synth.random_tree(P.pf, 7, rng)
+    mp = P.synth.dna_model_part(0, rng, 4)
+    alns = [P.synth.make_alignment(P.pf, t, mp, n, rng, "dna", gap_frac=0.03, ambig_frac=0.02) for n in (150, 90)]
+    out = []
+    for pf in (P.pf, ref_pf):
+        src = H.Data(pf, [H.Alignment(pf, a.sequences, a.symbols, a.equates) for a in alns])
+        dst = H.Data(pf, [H.Alignment(pf, a.sequences, a.symbols, a.equates) for a in alns])
+        src._setCStuff()
+        dst._setCStuff()
+        g = pf.gsl_rng_get()
+        pf.gsl_rng_set(g, 99)
+        pf.bootstrapData(src.cData, dst.cData, g)
+        out.append([(pf.symbolSequences(p.cPart), pf.partPatternCount(p.cPart)) for p in dst.parts])
+        assert out[-1][0][0] != pf.symbolSequences(src.parts[0].cPart)
+        pf.gsl_rng_free(g)
+        src.free()
+        dst.free()
+    assert out[0] == out[1]
+
+
 def test_gamma_rates_bit_identical_to_reference(pkg, ref_pf):
     for alpha in (0.1, 0.2, 0.5, 0.73, 1.0, 2.7, 10.0, 100.0, 299.0):
         for K in (2, 3, 4, 5, 8, 16):
