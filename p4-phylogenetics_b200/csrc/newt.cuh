@@ -1,15 +1,22 @@
-// newt.cuh -- sm_100a FP64 kernels of the Newton-Raphson branch-length step.
+// newt.cuh -- sm_100a kernels of the Newton-Raphson branch-length step and of the
+// simulation down the tree (8f rank 4).
 //
 //   newt_deck_kernel   P(t), dP/dv, d2P/dv2 of ONE branch at a trial length, plus the three leaf lookup
-//                      tables when the node is a leaf   (Pf/eig.c:163-191, 294-318, 346-371;
+//                      tables when the node is a leaf; one CTA per rate category
+//                                                       (Pf/eig.c:163-191, 294-318, 346-371;
 //                                                        Pf/p4_node.c:296-346, 442-540)
 //   transpose_deck_kernel   P^T of a node's deck: the "up" term of a child's cl2 is a CL-kernel child
 //                      whose matrix is the parent's P transposed (Pf/p4_node.c:883-928 p4_setCL2Up)
-//   newt_kernel        per pattern: like, d like, d2 like through the branch from cl2 (everything on the
+//   newt_dna_kernel    4 states, ONE launch per derivative evaluation: decks in the prologue, two patterns
+//                      per thread with the next category's rows in flight, the last CTA folds
+//   newt_aa_kernel     20 states: two patterns per thread, 16-byte shared-memory operand reads, last CTA folds
+//   newt_kernel<DIM>   any dim (decks in shared memory when they fit, else read through L1) + newt_final_kernel
+//                      per pattern: like, d like, d2 like through the branch from cl2 (everything on the
 //                      far side of the branch) and the node's own CL or tip; folds
 //                      sum count*log(like), sum count*(f/l), sum count*((s*l - f*f)/(l*l))
 //                                                       (Pf/p4_treeNewt.c:210-533 p4_newtNode)
-//   newt_final_kernel  fixed-order fold of the per-block partials
+//   picker_kernel, simulate_kernel   p4_simulate: running row sums of the P decks, one thread per site walking
+//                      the nodes in preOrder on the caller's stream of uniforms (Pf/p4_treeSim.c:315-360)
 //
 // cl2 arrays have the layout of CL arrays ([cat*dim + state][pattern], row stride ps) and are computed by
 // the per-node CL kernels of kernels.cuh: cl2(n) = up(parent) * prod over siblings (P_s x cl_s), where
