@@ -302,6 +302,7 @@ void p4b_rngFree(void *rng);
 void p4b_rngSet(void *rng, unsigned long seed);
 unsigned long p4b_rngGet(void *rng);
 double p4b_rngUniform(void *rng);
+void p4b_rngFillUniform(void *rng, double *out, long n);   /* the next n uniforms of the stream, in order */
 /* pf.p4_simulate(tree, refTree|0, gsl_rng) :2333 -> p4_simulate Pf/p4_treeSim.c:14-420:
  * new sequences for every leaf, drawn down the tree from the root's composition through every branch's P decks
  * (rate category and invariant-or-not per site, pInvar), consuming the stream in the reference's order -- the

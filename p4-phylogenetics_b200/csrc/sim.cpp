@@ -116,22 +116,7 @@ struct Rng {
     }
     uint32_t get()
     {
-        if (mti >= 624) {
-            if (mti == 625) set(0);
-            static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
-            int kk = 0;
-            for (; kk < 624 - 397; kk++) {
-                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
-            }
-            for (; kk < 623; kk++) {
-                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
-            }
-            const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
-            mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
-            mti = 0;
-        }
+        if (mti >= 624) reload();
         uint32_t y = mt[mti++];
         y ^= (y >> 11);
         y ^= (y << 7) & 0x9d2c5680u;
@@ -140,6 +125,46 @@ struct Rng {
         return y;
     }
     double uniform() { return get() / 4294967296.0; }
+    void reload()
+    {
+        if (mti == 625) set(0);
+        static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
+        int kk = 0;
+        for (; kk < 624 - 397; kk++) {
+            const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+        }
+        for (; kk < 623; kk++) {
+            const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+        }
+        const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+        mti = 0;
+    }
+    // The next n uniforms of the stream, a state block at a time: the tempering of a block is a straight loop over
+    // the state words (no call, no branch per draw), which is what the simulation's 4e8 draws spend their time in.
+    void fillUniform(double *dst, size_t n)
+    {
+        size_t done = 0;
+        while (done < n) {
+            if (mti >= 624) reload();
+            size_t take = (size_t)(624 - mti);
+            if (take > n - done) take = n - done;
+            const uint32_t *src = mt + mti;
+            double *out = dst + done;
+            for (size_t i = 0; i < take; i++) {
+                uint32_t y = src[i];
+                y ^= (y >> 11);
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= (y >> 18);
+                out[i] = y / 4294967296.0;
+            }
+            mti += (int)take;
+            done += take;
+        }
+    }
     // gsl_rng_uniform_int for a generator with min 0 and max 2^32 - 1: equal-width bins, draws beyond the last bin rejected
     unsigned long uniformInt(unsigned long n)
     {
@@ -303,9 +328,7 @@ int treeSimulate(Tree *t, Tree *refTree, Rng *g)
             rank[k] = nVar;
             if (!inv[p][k]) nVar++;
         }
-        auto fill = [&](double *dst, size_t n) {
-            for (size_t i = 0; i < n; i++) dst[i] = g->uniform();
-        };
+        auto fill = [&](double *dst, size_t n) { g->fillUniform(dst, n); };
         if (treeSimulateDevice(t, p, cats[p].data(), rootSt[p].data(), inv[p].data(), rank.data(), nVar, fill)) return 1;
         dp->version++;
     }
@@ -326,6 +349,10 @@ void p4b_rngSet(void *g, unsigned long seed)
 }
 unsigned long p4b_rngGet(void *g) { return g ? ((Rng *)g)->get() : 0ul; }
 double p4b_rngUniform(void *g) { return g ? ((Rng *)g)->uniform() : 0.0; }
+void p4b_rngFillUniform(void *g, double *out, long n)
+{
+    if (g && out && n > 0) ((Rng *)g)->fillUniform(out, (size_t)n);
+}
 int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng)
 {
     if (!t || !rng) { setError("p4b_simulate: NULL argument"); return 1; }

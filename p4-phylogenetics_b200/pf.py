@@ -157,6 +157,7 @@ _sig("p4b_rngFree", None, _vp)
 _sig("p4b_rngSet", None, _vp, C.c_ulong)
 _sig("p4b_rngGet", C.c_ulong, _vp)
 _sig("p4b_rngUniform", _d, _vp)
+_sig("p4b_rngFillUniform", None, _vp, _vp, C.c_long)
 _sig("p4b_simulate", _i, _vp, _vp, _vp)
 _sig("p4b_drawAncState", _i, _vp, _i, _i, _vp)
 _sig("p4b_bootstrapData", _i, _vp, _vp, _vp)
@@ -795,6 +796,13 @@ def gsl_rng_set(g, seed):
 def gsl_rng_uniform(g):
     """pf.gsl_rng_uniform(g) -> float in [0, 1) (Pf/pfmodule.c:739)."""
     return _lib.p4b_rngUniform(g)
+
+
+def gsl_rng_uniform_array(g, n):
+    """The next n uniforms of the stream as a numpy array (an addition: what pf.p4_simulate draws from, in bulk)."""
+    out = np.empty(int(n), dtype=np.float64)
+    _lib.p4b_rngFillUniform(g, out.ctypes.data, int(n))
+    return out
 
 
 def p4_simulate(cTree, cRefTree, g):

@@ -113,6 +113,12 @@ def test_rng_stream_is_mt19937_with_gsl_seeding(pkg, ref_pf):
         pf.gsl_rng_set(g, seed)
         ref_pf.gsl_rng_set(r, seed)
         assert [pf.gsl_rng_uniform(g) for _ in range(1500)] == [ref_pf.gsl_rng_uniform(r) for _ in range(1500)]
+    # the bulk path the simulation draws from: same stream, whatever the block boundaries (624 words per state block)
+    for n0, n1 in ((0, 5000), (1, 623), (623, 2), (624, 624), (100, 1248)):
+        pf.gsl_rng_set(g, 7)
+        ref_pf.gsl_rng_set(r, 7)
+        got = [pf.gsl_rng_uniform(g) for _ in range(n0)] + list(pf.gsl_rng_uniform_array(g, n1)) + [pf.gsl_rng_uniform(g) for _ in range(3)]
+        assert got == [ref_pf.gsl_rng_uniform(r) for _ in range(n0 + n1 + 3)]
     pf.gsl_rng_free(g)
 
 
