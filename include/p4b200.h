@@ -320,6 +320,8 @@ int p4b_drawAncState(p4b_tree t, int pNum, int seqPos, int *draw4);
  * with replacement on the caller's stream (gsl_rng_uniform_int), then pf.makePatterns on the filled parts. */
 int p4b_bootstrapData(p4b_data reference, p4b_data toFill, void *rng);
 void p4b_reseedCRandomizer(int seed);
+/* Test hook: p4b_drawAncState's draw for a root CL given by the caller ([cat][state][pattern], nPatterns columns). */
+int p4b_drawAncStateFromCL(p4b_part part, int seqPos, int nCat, double pInvar, int pInvarFree, const double *pi, const double *rootCL, int *draw4);
 int p4b_expectedComposition(p4b_tree t, int pNum, double *outNTaxTimesDim);
 int p4b_expectedCompositionCounts(p4b_tree t, int pNum, double *outNTaxTimesDim);
 

@@ -5,6 +5,7 @@
 // partBigXSquared, partSimpleConstantSitesCount, partMeanNCharsPerSite; p4/tree.py:8119-9052, p4/data.py:339-766).
 // Host code on the part's integer arrays; every result is checked for equality with the reference's on the CPU
 // (tests/test_host.py).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -92,53 +93,54 @@ int p4b_partComposition(p4b_part part, double *outDim)
     if (!p || !outDim) { setError("partComposition: NULL argument"); return 1; }
     const int dim = p->dim, nEq = p->nEquates;
     if ((int)p->taxList.size() != p->nTax) p->taxList.assign(p->nTax, 0);
-    std::vector<double> symbolFreq(dim, 0.0), comp(dim, 0.0), symbSum(dim, 0.0), results(dim, 0.0), equateFreq(nEq, 0.0);
-    const double epsilon = 1.0e-12;
-    const int maxIterations = 1000;
-    bool hasEquates = false;                       // sticky over the sequences, as in the reference
-    int grandNSites = 0;
-    for (int seqNum = 0; seqNum < p->nTax; seqNum++) {
-        if (!p->taxList[seqNum]) continue;
-        int nGapsMissings = 0;
-        for (int k = 0; k < dim; k++) symbolFreq[k] = comp[k] = symbSum[k] = 0.0;
-        for (int k = 0; k < nEq; k++) equateFreq[k] = 0.0;
-        const int *row = &p->sequences[(size_t)seqNum * p->nChar];
+    // the states each ambiguity code stands for, ascending (the order the reference's loops visit them in)
+    std::vector<std::vector<int>> statesOf(nEq);
+    for (int e = 0; e < nEq; e++)
+        for (int k = 0; k < dim; k++)
+            if (p->equates[(size_t)e * dim + k]) statesOf[e].push_back(k);
+    std::vector<double> plain(dim), ambig(nEq), freq(dim), share(dim), weighted(dim, 0.0);
+    long totalSites = 0;
+    for (int seq = 0; seq < p->nTax; seq++) {
+        if (!p->taxList[seq]) continue;
+        // counts of this sequence: plain states, ambiguity codes, and the sites that carry neither
+        std::fill(plain.begin(), plain.end(), 0.0);
+        std::fill(ambig.begin(), ambig.end(), 0.0);
+        int blanks = 0;
+        const int *row = &p->sequences[(size_t)seq * p->nChar];
         for (int j = 0; j < p->nChar; j++) {
-            if (row[j] >= 0) symbolFreq[row[j]] = symbolFreq[row[j]] + 1.0;
-            else if (row[j] == P4B_QMARK_CODE || row[j] == P4B_GAP_CODE) nGapsMissings += 1;
-            else equateFreq[row[j] - P4B_EQUATES_BASE] += 1.0;
+            const int c = row[j];
+            if (c >= 0) plain[c] = plain[c] + 1.0;
+            else if (c == P4B_QMARK_CODE || c == P4B_GAP_CODE) blanks += 1;
+            else ambig[c - P4B_EQUATES_BASE] += 1.0;
         }
-        const int nSites = p->nChar - nGapsMissings;
-        grandNSites += nSites;
-        for (int i = 0; i < nEq; i++)
-            if (equateFreq[i] > 0.0) { hasEquates = true; break; }
+        const int nSites = p->nChar - blanks;
+        totalSites += nSites;
         if (!nSites) continue;
-        double x = 1.0 / ((float)dim);
-        for (int i = 0; i < dim; i++) comp[i] = x;
-        for (int it = 0; it < maxIterations; it++) {
-            for (int j = 0; j < dim; j++) symbSum[j] = symbolFreq[j];
-            if (hasEquates)
-                for (int j = 0; j < nEq; j++) {
-                    if (!(equateFreq[j] > 0.0)) continue;
-                    x = 0.0;
-                    for (int k = 0; k < dim; k++)
-                        if (p->equates[(size_t)j * dim + k]) x = x + comp[k];
-                    for (int k = 0; k < dim; k++)
-                        if (p->equates[(size_t)j * dim + k]) symbSum[k] = symbSum[k] + (equateFreq[j] * (comp[k] / x));
-                }
-            x = 0.0;
-            for (int j = 0; j < dim; j++) x = x + symbSum[j];
-            double diff = 0.0;
-            for (int j = 0; j < dim; j++) {
-                const double oldComp = comp[j];
-                comp[j] = symbSum[j] / x;
-                diff = diff + fabs(comp[j] - oldComp);
+        // fixed point of: share every ambiguity's count among its states in proportion to the current composition
+        // (start uniform -- the reference divides by a float dim --, stop when the composition moves by < 1e-12, 1000 rounds at most)
+        const double start = 1.0 / ((float)dim);
+        for (int k = 0; k < dim; k++) freq[k] = start;
+        for (int round = 0; round < 1000; round++) {
+            for (int k = 0; k < dim; k++) share[k] = plain[k];
+            for (int e = 0; e < nEq; e++) {
+                if (!(ambig[e] > 0.0)) continue;
+                double mass = 0.0;
+                for (int k : statesOf[e]) mass = mass + freq[k];
+                for (int k : statesOf[e]) share[k] = share[k] + (ambig[e] * (freq[k] / mass));
             }
-            if (diff < epsilon) break;
+            double total = 0.0;
+            for (int k = 0; k < dim; k++) total = total + share[k];
+            double moved = 0.0;
+            for (int k = 0; k < dim; k++) {
+                const double before = freq[k];
+                freq[k] = share[k] / total;
+                moved = moved + fabs(freq[k] - before);
+            }
+            if (moved < 1.0e-12) break;
         }
-        for (int j = 0; j < dim; j++) results[j] = results[j] + (comp[j] * (double)nSites);
+        for (int k = 0; k < dim; k++) weighted[k] = weighted[k] + (freq[k] * (double)nSites);   // sequences weigh by their sites
     }
-    for (int i = 0; i < dim; i++) outDim[i] = grandNSites ? results[i] / (double)grandNSites : 0.0;
+    for (int k = 0; k < dim; k++) outDim[k] = totalSites ? weighted[k] / (double)totalSites : 0.0;
     return 0;
 }
 

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <functional>
+#include <utility>
 #include <vector>
 
 #include "../../include/p4b200.h"
@@ -181,65 +182,66 @@ struct Rng {
 // the posterior the root's conditional likelihoods imply.  The reference draws from the C library's random()
 // (seeded through pf.reseedCRandomizer -> srandom), not from the GSL stream; so does this.
 // draw = {chStNum, catNum, isInvar, invarChNum} as p4_drawAncStateP returns them (:847-857).
+// The draw itself, given the root's CL as [cat*dim + state][pattern] with row stride `stride`.
+static int drawFromRootCL(const double *cl, size_t stride, Part *dp, int p, int seqPos, int dim, int nCat, double pInvar, int pInvarFree,
+                          const double *pi, int draw[4])
+{
+    if (seqPos < 0 || seqPos >= dp->nChar) { setError("p4_drawAncState: bad site %d", seqPos); return 1; }
+    const int patNum = dp->sequencePositionPatternIndex[seqPos];
+    const size_t ps = stride;
+    // running total of the site's likelihood, term by term in the reference's order: first every (category, state) of
+    // the variable-site mixture, then -- pInvar set -- the invariant share of every state the site could be constant for
+    const double fr = (1.0 - pInvar) / (double)nCat;     // freqsTimesOneMinusPInvar, Pf/p4_tree.c:992-996
+    std::vector<double> upTo((size_t)nCat * dim);
+    std::vector<std::pair<int, double>> invUpTo;
+    double total = 0.0;
+    for (int c = 0; c < nCat; c++)
+        for (int s = 0; s < dim; s++) {
+            double term = pi[s] * cl[((size_t)c * dim + s) * ps + patNum];
+            term *= fr;
+            total += term;
+            upTo[(size_t)c * dim + s] = total;
+        }
+    if (pInvar != 0.0) {
+        if (dp->globalInvarSitesArray.empty()) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+        for (int s = 0; s < dim; s++)
+            if (dp->globalInvarSitesArray[(size_t)s * dp->nChar + patNum]) {
+                total += pi[s] * pInvar;
+                invUpTo.emplace_back(s, total);
+            }
+    }
+    double u = (double)random() / ((double)(RAND_MAX) + 1.0);
+    u *= total;
+    for (size_t i = 0; i < upTo.size(); i++)
+        if (u < upTo[i]) {
+            draw[0] = (int)(i % dim);
+            draw[1] = (int)(i / dim);
+            draw[2] = 0;
+            draw[3] = -1;
+            return 0;
+        }
+    if (pInvarFree)                                      // :780-792: only a FREE pInvar's share is looked at
+        for (const auto &sv : invUpTo)
+            if (u < sv.second) {
+                draw[0] = -1;
+                draw[1] = -1;
+                draw[2] = 1;
+                draw[3] = sv.first;
+                return 0;
+            }
+    setError("Something is wrong with the ancestral state picker. gotIt is zero.");   // the reference's message (:794-797)
+    return 1;
+}
+
 int treeDrawAncState(Tree *t, int p, int seqPos, int draw[4])
 {
     int ps = 0;
     const double *cl = treeRootCLHost(t, p, &ps);
     if (!cl) return 1;
-    Part *dp = t->data->parts[p];
     ModelPart *mp = t->model->parts[p];
-    if (seqPos < 0 || seqPos >= dp->nChar) { setError("p4_drawAncState: bad site %d", seqPos); return 1; }
-    const int dim = mp->dim, nCat = mp->nCat;
-    const int patNum = dp->sequencePositionPatternIndex[seqPos];
     const int rc = t->root->compNums[p];
     if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
-    const double *pi = mp->comps[rc].val;
-    std::vector<double> picker((size_t)dim * (nCat + 1), 0.0);
-    const double fr = (1.0 - mp->pInvar) / (double)nCat;     // freqsTimesOneMinusPInvar, Pf/p4_tree.c:992-996
-    double sLike = 0.0;
-    int i = 0;
-    for (int c = 0; c < nCat; c++)
-        for (int s = 0; s < dim; s++) {
-            double sLikeC = pi[s] * cl[((size_t)c * dim + s) * ps + patNum];
-            sLikeC *= fr;
-            sLike += sLikeC;
-            picker[i++] = sLike;
-        }
-    if (mp->pInvar != 0.0) {
-        if (dp->globalInvarSitesArray.empty()) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
-        for (int s = 0; s < dim; s++) {
-            if (dp->globalInvarSitesArray[(size_t)s * dp->nChar + patNum]) {
-                sLike += pi[s] * mp->pInvar;
-                picker[i] = sLike;
-            }
-            i++;
-        }
-    }
-    double u = (double)random() / ((double)(RAND_MAX) + 1.0);
-    u *= sLike;
-    bool gotIt = false;
-    int k = 0, c = 0, s = 0;
-    for (c = 0; c < nCat; c++) {
-        for (s = 0; s < dim; s++) {
-            if (u < picker[k]) gotIt = true;
-            k++;
-            if (gotIt) break;
-        }
-        if (gotIt) break;
-    }
-    bool isInvar = false;
-    if (!gotIt && mp->pInvarFree) {                          // :780-792: only a FREE pInvar is looked at here
-        for (s = 0; s < dim; s++) {
-            if (dp->globalInvarSitesArray[(size_t)s * dp->nChar + patNum])
-                if (u < picker[k]) { isInvar = true; gotIt = true; }
-            k++;
-            if (gotIt) break;
-        }
-    }
-    if (!gotIt) { setError("Something is wrong with the ancestral state picker. gotIt is zero."); return 1; }
-    if (!isInvar) { draw[0] = s; draw[1] = c; draw[2] = 0; draw[3] = -1; }
-    else { draw[0] = -1; draw[1] = -1; draw[2] = 1; draw[3] = s; }
-    return 0;
+    return drawFromRootCL(cl, (size_t)ps, t->data->parts[p], p, seqPos, mp->dim, mp->nCat, mp->pInvar, mp->pInvarFree, mp->comps[rc].val, draw);
 }
 
 // p4_simulate(t, refTree, g), Pf/p4_treeSim.c:14-420.  Host: the per-site draws that need no tree (rate category,
@@ -377,6 +379,14 @@ int p4b_bootstrapData(p4b_data reference, p4b_data toFill, void *rng)
         if (makePatterns(fp)) return 1;
     }
     return 0;
+}
+/* Test hook: the draw of p4b_drawAncState for a root CL handed in by the caller ([cat][state][pattern], nPatterns columns),
+ * so that the host logic can be checked against the reference without a device. */
+int p4b_drawAncStateFromCL(p4b_part part, int seqPos, int nCat, double pInvar, int pInvarFree, const double *pi, const double *rootCL, int *draw4)
+{
+    Part *dp = (Part *)part;
+    if (!dp || !pi || !rootCL || !draw4) { setError("p4b_drawAncStateFromCL: NULL argument"); return 1; }
+    return drawFromRootCL(rootCL, (size_t)dp->nPatterns, dp, 0, seqPos, dp->dim, nCat, pInvar, pInvarFree, pi, draw4);
 }
 int p4b_drawAncState(p4b_tree t, int pNum, int seqPos, int *draw4)
 {

@@ -162,6 +162,7 @@ _sig("p4b_simulate", _i, _vp, _vp, _vp)
 _sig("p4b_drawAncState", _i, _vp, _i, _i, _vp)
 _sig("p4b_bootstrapData", _i, _vp, _vp, _vp)
 _sig("p4b_reseedCRandomizer", None, _i)
+_sig("p4b_drawAncStateFromCL", _i, _vp, _i, _i, _d, _i, _vp, _vp, _vp)
 _sig("p4b_expectedComposition", _i, _vp, _i, _vp)
 _sig("p4b_expectedCompositionCounts", _i, _vp, _i, _vp)
 _sig("p4b_newtSetup", _i, _vp)
@@ -820,6 +821,15 @@ def p4_drawAncState(cTree, partNum, seqPos, draw):
 def bootstrapData(cDataReference, cDataToFill, g):
     """pf.bootstrapData(referenceData, toFillData, gsl_rng) (Pf/pfmodule.c:90, Pf/data.c:107-139)."""
     _ok(_lib.p4b_bootstrapData(cDataReference, cDataToFill, g))
+
+
+def drawAncStateFromCL(cPart, seqPos, nCat, pInvar, pInvarFree, pi, rootCL):
+    """Test hook (include/p4b200.h p4b_drawAncStateFromCL): p4_drawAncState's draw for a given root CL [cat][state][pattern]."""
+    pi = np.ascontiguousarray(pi, dtype=np.float64)
+    cl = np.ascontiguousarray(rootCL, dtype=np.float64)
+    d = np.empty(4, dtype=np.int32)
+    _ok(_lib.p4b_drawAncStateFromCL(cPart, int(seqPos), int(nCat), float(pInvar), int(pInvarFree), pi.ctypes.data, cl.ctypes.data, d.ctypes.data))
+    return [int(v) for v in d]
 
 
 def reseedCRandomizer(seed):

@@ -173,6 +173,35 @@ def test_bootstrap_equals_the_reference_for_the_same_seed(pkg, ref_pf):
     assert out[0] == out[1]
 
 
+@pytest.mark.parametrize("cfg,kw,pInvarFree", [(1, dict(nTax=10, nPatterns=250), 1), (3, dict(nTax=7, nPatterns=120), 0)])
+def test_draw_anc_state_logic_vs_reference(pkg, ref_pf, cfg, kw, pInvarFree):
+    """The host logic of pf.p4_drawAncState (csrc/sim.cpp drawFromRootCL) fed with the REFERENCE's root CL: the same
+    srandom seed gives the reference's draws at every site (the device only supplies the root CL; GPU parity in tests/test_gpu_sim.py)."""
+    P = pkg
+    twin = P.synth.build_config(ref_pf, cfg, **kw)
+    mp = twin.model.parts[0]
+    mp.pInvar.free = pInvarFree
+    twin.calcLogLike()
+    rp = ref_peek.part_arrays(twin.data.parts[0].cPart)
+    cl = ref_peek.node_cl(twin.root.cNode, 0, mp.nGammaCat, mp.dim, rp["nChar"], rp["nPatterns"])
+    aln = twin.data.alignments[0]
+    mine = P.host.Alignment(P.pf, aln.sequences, aln.symbols, aln.equates)._initParts()
+    pi = np.array(mp.comps[twin.root.parts[0].compNum].val, dtype=np.float64)
+    pInvar = float(mp.pInvar.val)
+    n = rp["nChar"]
+    P.pf.reseedCRandomizer(123)
+    got = [P.pf.drawAncStateFromCL(mine.cPart, k, mp.nGammaCat, pInvar, pInvarFree, pi, cl) for k in range(n)]
+    ref_pf.reseedCRandomizer(123)
+    d = np.empty(4, dtype=np.int32)
+    want = []
+    for k in range(n):
+        ref_pf.p4_drawAncState(twin.cTree, 0, k, d)
+        want.append(d.tolist())
+    assert got == want
+    assert any(w[2] for w in want) == (cfg == 1)          # invariant draws do occur in the pInvar case
+    P.pf.freePart(mine.cPart)
+
+
 def test_gamma_rates_bit_identical_to_reference(pkg, ref_pf):
     for alpha in (0.1, 0.2, 0.5, 0.73, 1.0, 2.7, 10.0, 100.0, 299.0):
         for K in (2, 3, 4, 5, 8, 16):
