@@ -331,3 +331,161 @@ static void matrix_exp(const double *V, const double *Vi, const double *lam, int
 #undef REAL
 #undef FN
 #undef LOGF
+
+
+/* ---- Newton-Raphson on one branch length: Pf/p4_treeNewt.c, Pf/p4_node.c:860-1018 -------------------------
+ * out = { sum n log l,  sum n l'/l,  sum n (l'' l - l'^2)/l^2 }  in the length of `node`'s branch, the three sums
+ * p4_newtNode forms per iteration (:508-517).  cl2 (everything on the far side of a branch) is built top-down along
+ * the path from the root's child to `node` (p4_setNodeCL2 :603-624: p4_initializeCL2ToRootComp or p4_setCL2Up for
+ * the parent's side, p4_setCL2Down for every sibling); the derivative decks follow
+ * first/secondDerivativeOfMatrixExpTimesBranchLength (Pf/eig.c:294-371) with the rate factors of
+ * p4_calculateBigPDecks_1stD / _2ndD (Pf/p4_node.c:442-540, including the second derivative's extra relRate in the
+ * gamma, no-pInvar branch). */
+static double leaf_term(const pfport_part *D, int dim, int code, const double *row /* deck row [dim] */, int plainIsOne)
+{
+    if (code >= 0) return row[code];
+    if (code == GAP_CODE || code == QMARK_CODE) {
+        if (plainIsOne) return 1.0;
+        double s = 0.0;
+        for (int x = 0; x < dim; x++) s += row[x];
+        return s;
+    }
+    const int *eq = D->equates + (code - EQUATES_BASE) * dim;
+    double s = 0.0;
+    for (int x = 0; x < dim; x++)
+        if (eq[x]) s += row[x];
+    return s;
+}
+
+int pfport_branch_derivs(const pfport_tree *T, const pfport_part *D, const pfport_model *M, int node, double out[3])
+{
+    const int dim = M->dim, nCat = M->nCat, nPat = D->nPatterns, nN = T->nNodes;
+    const long clSize = (long)nCat * dim * nPat, pSize = (long)nCat * dim * dim;
+    if (node < 0 || node >= nN || node == T->root || T->parent[node] < 0) return 1;
+    double *cl = malloc(sizeof(double) * clSize * nN), *P = malloc(sizeof(double) * pSize * nN);
+    pfport_part_loglike(T, D, M, cl, P, NULL);
+    /* the path root's child ... node */
+    int *path = malloc(sizeof(int) * nN), nPath = 0;
+    for (int q = node; T->parent[q] >= 0; q = T->parent[q]) path[nPath++] = q;
+    double *cl2 = malloc(sizeof(double) * clSize * nPath);
+    const double *piRoot = M->comps + (long)T->compNum[T->root] * dim;
+    for (int k = nPath - 1; k >= 0; k--) {
+        const int q = path[k], par = T->parent[q];
+        double *mine = cl2 + (long)k * clSize;
+        const double *up = (par == T->root) ? NULL : cl2 + (long)(k + 1) * clSize;
+        for (int pat = 0; pat < nPat; pat++)
+            for (int cat = 0; cat < nCat; cat++)
+                for (int s = 0; s < dim; s++) {
+                    double v;
+                    if (!up) v = piRoot[s];                                          /* p4_initializeCL2ToRootComp */
+                    else {                                                           /* p4_setCL2Up */
+                        const double *Pp = P + (long)par * pSize + (long)cat * dim * dim;
+                        v = 0.0;
+                        for (int f = 0; f < dim; f++) v += Pp[f * dim + s] * up[((long)cat * dim + f) * nPat + pat];
+                    }
+                    for (int sib = T->leftChild[par]; sib >= 0; sib = T->sibling[sib]) {   /* p4_setCL2Down */
+                        if (sib == q) continue;
+                        const double *Pc = P + (long)sib * pSize + (long)cat * dim * dim + (long)s * dim;
+                        double f;
+                        if (T->isLeaf[sib]) {
+                            const int code = D->patterns[(long)T->seqNum[sib] * D->stride + pat];
+                            int isN = 0;
+                            if (code <= EQUATES_BASE + D->nEquates - 1 && code >= EQUATES_BASE) {
+                                const int *eq = D->equates + (code - EQUATES_BASE) * dim;
+                                isN = 1;
+                                for (int x = 0; x < dim; x++)
+                                    if (!eq[x]) { isN = 0; break; }
+                            }
+                            f = isN ? 1.0 : leaf_term(D, dim, code, Pc, 1);
+                        } else {
+                            const double *cc = cl + (long)sib * clSize + (long)cat * dim * nPat + pat;
+                            f = 0.0;
+                            for (int x = 0; x < dim; x++) f += Pc[x] * cc[(long)x * nPat];
+                        }
+                        v *= f;
+                    }
+                    mine[((long)cat * dim + s) * nPat + pat] = v;
+                }
+    }
+    /* decks of the branch: P (already in P), first and second derivative */
+    double *V = malloc(sizeof(double) * dim * dim), *Vi = malloc(sizeof(double) * dim * dim), *lam = malloc(sizeof(double) * dim),
+           *Q = malloc(sizeof(double) * dim * dim), *D1 = malloc(sizeof(double) * pSize), *D2 = malloc(sizeof(double) * pSize);
+    pfport_big_q(M->bigR + (long)T->rMatrixNum[node] * dim * dim, M->comps + (long)T->compNum[node] * dim, dim, Q);
+    eigen_reversible(Q, M->comps + (long)T->compNum[node] * dim, dim, V, Vi, lam);
+    const double *rates = M->nGdasrvs ? M->rates + (long)T->gdasrvNum[node] * nCat : NULL;
+    for (int cat = 0; cat < nCat; cat++) {
+        double t, r1, r2;
+        if (M->pInvar == 0.0) {
+            if (rates) { const double temp = rates[cat] * M->relRate; t = T->brLen[node] * temp; r1 = temp; r2 = temp * M->relRate; }
+            else { t = T->brLen[node] * M->relRate; r1 = r2 = M->relRate; }
+        } else {
+            if (rates) { const double temp = rates[cat] * M->relRate; t = (T->brLen[node] * temp) / (1.0 - M->pInvar); r1 = r2 = temp / (1.0 - M->pInvar); }
+            else { t = (T->brLen[node] * M->relRate) / (1.0 - M->pInvar); r1 = r2 = M->relRate / (1.0 - M->pInvar); }
+        }
+        for (int i = 0; i < dim; i++)
+            for (int j = 0; j < dim; j++) {
+                double a = 0.0, b = 0.0;
+                for (int k = 0; k < dim; k++) {
+                    a = a + (V[i * dim + k] * Vi[k * dim + j] * lam[k] * r1 * exp(lam[k] * t));
+                    b = b + (V[i * dim + k] * Vi[k * dim + j] * lam[k] * lam[k] * r2 * r2 * exp(lam[k] * t));
+                }
+                D1[(long)cat * dim * dim + i * dim + j] = a;
+                D2[(long)cat * dim * dim + i * dim + j] = b;
+            }
+    }
+    /* the sums of p4_newtNode, :258-517 */
+    const double *z = cl2, *x = cl + (long)node * clSize, *P0 = P + (long)node * pSize;
+    double lnL = 0.0, firstD = 0.0, secondD = 0.0;
+    for (int pat = 0; pat < nPat; pat++) {
+        double likeS = 0.0, firstS = 0.0, secondS = 0.0;
+        for (int cat = 0; cat < nCat; cat++) {
+            double like = 0.0, first = 0.0, second = 0.0;
+            for (int f = 0; f < dim; f++) {
+                const double zz = z[((long)cat * dim + f) * nPat + pat];
+                const double *r0 = P0 + (long)cat * dim * dim + (long)f * dim, *r1 = D1 + (long)cat * dim * dim + (long)f * dim,
+                             *r2 = D2 + (long)cat * dim * dim + (long)f * dim;
+                if (T->isLeaf[node]) {
+                    const int code = D->patterns[(long)T->seqNum[node] * D->stride + pat];
+                    like += zz * leaf_term(D, dim, code, r0, code == GAP_CODE || code == QMARK_CODE);
+                    first += zz * leaf_term(D, dim, code, r1, 0);
+                    second += zz * leaf_term(D, dim, code, r2, 0);
+                } else {
+                    for (int t = 0; t < dim; t++) {
+                        const double temp2 = zz * x[((long)cat * dim + t) * nPat + pat];
+                        like += temp2 * r0[t];
+                        first += temp2 * r1[t];
+                        second += temp2 * r2[t];
+                    }
+                }
+            }
+            likeS += like;
+            firstS += first;
+            secondS += second;
+        }
+        if (M->pInvar != 0.0) {
+            const double f0 = (1.0 - M->pInvar) / (double)nCat;
+            likeS *= f0;
+            firstS *= f0;
+            secondS *= f0;
+            if (D->invarVec[pat] > 0)
+                for (int s = 0; s < dim; s++)
+                    if (D->invarArray[(long)s * D->stride + pat]) likeS += piRoot[s] * M->pInvar;
+        } else if (nCat > 1) {
+            likeS /= (double)nCat;
+            firstS /= (double)nCat;
+            secondS /= (double)nCat;
+        }
+        const double cnt = D->patternCounts[pat];
+        if (likeS < 1.0e-300) { lnL += cnt * -100000; firstD += cnt * 1000000; secondD += cnt * 10000000; }
+        else {
+            lnL += cnt * log(likeS);
+            firstD += cnt * (firstS / likeS);
+            secondD += cnt * ((secondS * likeS - firstS * firstS) / (likeS * likeS));
+        }
+    }
+    out[0] = lnL;
+    out[1] = firstD;
+    out[2] = secondD;
+    free(cl); free(P); free(path); free(cl2); free(V); free(Vi); free(lam); free(Q); free(D1); free(D2);
+    return 0;
+}

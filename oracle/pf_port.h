@@ -42,4 +42,6 @@ double pfport_part_loglike(const pfport_tree *T, const pfport_part *D, const pfp
 /* Same, with the CL recursion carried in long double (no underflow for thousands of taxa). */
 double pfport_part_loglike_ld(const pfport_tree *T, const pfport_part *D, const pfport_model *M, double *clOut, double *pOut,
                               double *patLikes);
+/* The three sums of one Newton-Raphson iteration on the branch of `node` (Pf/p4_treeNewt.c:238-520): lnL, d lnL/dv, d2 lnL/dv2. */
+int pfport_branch_derivs(const pfport_tree *T, const pfport_part *D, const pfport_model *M, int node, double out[3]);
 #endif

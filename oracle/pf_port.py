@@ -139,6 +139,105 @@ def protein_big_r(spec):
     return _protein_cache[spec]
 
 
+def _structs(tree):
+    """Per part: the C structs of pf_port.h for a ``host.Tree`` (data and model attached), and the arrays they point into."""
+    nodes = tree.nodes
+    nN = len(nodes)
+    num = lambda x: x.nodeNum if x is not None else -1
+    parent = np.array([num(n.parent) for n in nodes], dtype=np.int32)
+    left = np.array([num(n.leftChild) for n in nodes], dtype=np.int32)
+    sib = np.array([num(n.sibling) for n in nodes], dtype=np.int32)
+    isLeaf = np.array([int(n.isLeaf) for n in nodes], dtype=np.int32)
+    seqNum = np.array([int(n.seqNum) for n in nodes], dtype=np.int32)
+    brLen = np.array([float(n.br.len) for n in nodes], dtype=np.float64)
+    if not tree.preAndPostOrderAreValid:
+        tree.setPreAndPostOrder()
+    post = np.ascontiguousarray(tree.postOrder, dtype=np.int32)
+    out = []
+    for pNum, (aln, mp) in enumerate(zip(tree.data.alignments, tree.model.parts)):
+        comp = compress(aln.sequences, aln.symbols, aln.equates)
+        dim, nCat = mp.dim, mp.nGammaCat
+        compNum = np.array([n.parts[pNum].compNum for n in nodes], dtype=np.int32)
+        rNum = np.array([n.br.parts[pNum].rMatrixNum for n in nodes], dtype=np.int32)
+        gNum = np.array([n.br.parts[pNum].gdasrvNum for n in nodes], dtype=np.int32)
+        comps = np.ascontiguousarray(np.stack([c.val for c in mp.comps]), dtype=np.float64)
+        bigR = np.ascontiguousarray(np.stack([_big_r(r, dim) for r in mp.rMatrices]), dtype=np.float64)
+        rates = np.ones((max(len(mp.gdasrvs), 1), nCat))
+        for gi, g in enumerate(mp.gdasrvs):
+            rates[gi] = discrete_gamma(float(g.val[0]), nCat)[1]
+        T = _Tree(nN, tree.root.nodeNum, len(post), _i(parent), _i(left), _i(sib), _i(isLeaf), _i(seqNum), _d(brLen), _i(post),
+                  _i(compNum), _i(rNum), _i(gNum))
+        D = _Part(comp["nTax"], comp["nPatterns"], comp["nChar"], _i(comp["patterns"]), _i(comp["patternCounts"]),
+                  comp["nEquates"], _i(comp["equates"]), _i(comp["globalInvarSitesVec"]), _i(comp["globalInvarSitesArray"]))
+        M = _Model(dim, nCat, len(mp.comps), len(mp.rMatrices), len(mp.gdasrvs), _d(comps), _d(bigR), _d(rates),
+                   float(mp.pInvar.val), float(mp.relRate))
+        keep = (parent, left, sib, isLeaf, seqNum, brLen, post, compNum, rNum, gNum, comps, bigR, rates, comp)
+        out.append((T, D, M, comp, rates, keep))
+    return out
+
+
+def branch_derivs(tree):
+    """{nodeNum: (lnL, d lnL/dv, d2 lnL/dv2)} in every branch length v, summed over the parts: the three sums of one
+    iteration of p4_newtNode (Pf/p4_treeNewt.c:238-520), by the oracle port alone (pfport_branch_derivs)."""
+    L = lib()
+    L.pfport_branch_derivs.restype = C.c_int
+    parts = _structs(tree)
+    res = {}
+    for n in tree.nodes:
+        if n is tree.root or n.parent is None:
+            continue
+        tot = np.zeros(3)
+        for (T, D, M, comp, rates, keep) in parts:
+            o = np.zeros(3)
+            if L.pfport_branch_derivs(C.byref(T), C.byref(D), C.byref(M), int(n.nodeNum), _d(o)):
+                raise ValueError("pfport_branch_derivs: bad node %d" % n.nodeNum)
+            tot += o
+        res[n.nodeNum] = (float(tot[0]), float(tot[1]), float(tot[2]))
+    return res
+
+
+def newt_node(tree, node, epsilon, brLenMin=1.0e-8, brLenMax=3.0):
+    """p4_newtNode (Pf/p4_treeNewt.c:210-600) for one node of a ``host.Tree``: Newton-Raphson on its branch length with the
+    reference's guards, the derivatives from the oracle port.  Sets and returns node.br.len."""
+    old = cur = float(node.br.len)
+    it = 0
+    while True:
+        node.br.len = cur
+        _, first, second = branch_derivs_of(tree, node)
+        nxt = cur - (first / second) if second != 0.0 else float("inf")
+        if second >= 0.0:
+            nxt = cur / 5.0
+        if nxt < brLenMin:
+            cur = brLenMin
+            break
+        if nxt >= 5.0 * old:
+            cur = 5.0 * old
+            break
+        if nxt > brLenMax:
+            cur = brLenMax
+            break
+        if it > 20:
+            break
+        it += 1
+        if abs(first) < epsilon:
+            break
+        cur = nxt
+    node.br.len = cur
+    return cur
+
+
+def branch_derivs_of(tree, node):
+    L = lib()
+    L.pfport_branch_derivs.restype = C.c_int
+    tot = np.zeros(3)
+    for (T, D, M, comp, rates, keep) in _structs(tree):
+        o = np.zeros(3)
+        if L.pfport_branch_derivs(C.byref(T), C.byref(D), C.byref(M), int(node.nodeNum), _d(o)):
+            raise ValueError("pfport_branch_derivs: bad node %d" % node.nodeNum)
+        tot += o
+    return float(tot[0]), float(tot[1]), float(tot[2])
+
+
 def tree_loglike(tree, want_arrays=False, long_double=False):
     """lnL of a ``host.Tree`` (data and model attached) computed by the oracle port alone.
 

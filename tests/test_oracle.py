@@ -81,3 +81,50 @@ def test_long_double_port_agrees_with_double_port(pkg):
     a = pf_port.tree_loglike(tree)
     b = pf_port.tree_loglike(tree, long_double=True)
     assert rel(a, b) <= 1e-13
+
+
+@pytest.mark.parametrize("cfg,kw", [(1, dict(nTax=9, nPatterns=200)), (3, dict(nTax=6, nPatterns=80))])
+def test_port_newton_step_matches_reference_engine(pkg, ref_pf, cfg, kw):
+    """The port's restatement of the Newton-Raphson sums (pfport_branch_derivs): lnL through every branch equals the tree's
+    lnL, the first derivative agrees with a central difference of the port's own lnL, and p4_newtNode driven by the port's
+    derivatives lands on the branch length the reference's own p4_newtNode lands on (leaf and internal branches)."""
+    import ref_peek
+    P = pkg
+    twin = P.synth.build_config(ref_pf, cfg, **kw)
+    rng = np.random.default_rng(cfg)
+    for n in twin.iterNodesNoRoot():
+        n.br.len = float(min(max(n.br.len * np.exp(rng.normal(0.0, 0.6)), 1e-4), 1.0))
+    base = twin.calcLogLike()
+    d = pf_port.branch_derivs(twin)
+    for k, (l0, d1, d2) in d.items():
+        assert rel(l0, base) <= 1e-10
+    n0 = [n for n in twin.iterNodesNoRoot() if not n.isLeaf][0]
+    v = n0.br.len
+    h = 1e-4 * v
+    n0.br.len = v + h
+    lp = pf_port.tree_loglike(twin)
+    n0.br.len = v - h
+    lm = pf_port.tree_loglike(twin)
+    n0.br.len = v
+    assert abs((lp - lm) / (2 * h) - d[n0.nodeNum][1]) <= 1e-4 * max(1.0, abs(d[n0.nodeNum][1]))
+    # the reference's p4_newtNode on the same branches: cl2 down the whole tree first, then one node at a time from the same state
+    ref_pf.p4_newtSetup(twin.cTree)
+    lib = ref_peek.newt_lib()
+    stack, order = [twin.root], []
+    while stack:
+        n = stack.pop()
+        if n is not twin.root:
+            order.append(n)
+        stack.extend(reversed(list(n.iterChildren())))
+    picks = [n for n in order if n.isLeaf][:2] + [n for n in order if not n.isLeaf][:2]
+    for n in picks:
+        start = n.br.len
+        twin.calcLogLike()                                   # CLs and P decks for the current lengths
+        for q in order:
+            lib.p4_setNodeCL2(twin.cTree, q.cNode)
+        lib.p4_newtNode(n.cNode, 1.0e-5, 1.0e-8, 3.0)
+        want = ref_peek.node_brlen(n.cNode)
+        n.br.len = start
+        got = pf_port.newt_node(twin, n, 1.0e-5)
+        assert abs(got - want) <= 1e-7 * max(want, 1e-3), (n.nodeNum, start, got, want)
+        n.br.len = start
