@@ -27,8 +27,9 @@ p4_resetBQET p4_getRelRate p4_newTree p4_freeTree p4_newNode p4_freeNode p4_setN
 p4_getTreeLen p4_setCompNum p4_setRMatrixNum p4_setGdasrvNum p4_setPrams p4_calculateBigPDecks
 p4_calculateAllBigPDecksAllParts p4_setConditionalLikelihoodsOfInternalNodePart p4_partLogLike p4_treeLogLike
 p4_copyCondLikes p4_copyBigPDecks p4_copyModelPrams p4_verifyIdentityOfTwoTrees
-p4_newtSetup p4_newtAndBrentPowellOpt p4_newtAndBOBYQAOpt p4_getBrLens p4_getFreePrams""".split()
-MAKES_HANDLE = {"newData", "newPart", "p4_newModel", "p4_newTree", "p4_newNode", "p4_newGdasrv"}
+p4_newtSetup p4_newtAndBrentPowellOpt p4_newtAndBOBYQAOpt p4_getBrLens p4_getFreePrams
+gsl_rng_get gsl_rng_set p4_simulate symbolSequences""".split()
+MAKES_HANDLE = {"newData", "newPart", "p4_newModel", "p4_newTree", "p4_newNode", "p4_newGdasrv", "gsl_rng_get"}
 
 
 class Recorder:
@@ -59,6 +60,8 @@ class Recorder:
                 self._nHandles += 1
                 self._handles[int(ret)] = hid
                 r = {"h": hid}
+            elif isinstance(ret, str):
+                r = {"str": ret}
             elif isinstance(ret, (list, tuple)):
                 r = [float(v) for v in ret]
             elif isinstance(ret, (int, float, np.integer, np.floating)):
@@ -151,7 +154,10 @@ def replay(pf, trace, tol=1e-9):
                     args.append(x)
             got = getattr(pf, name)(*args)
             nCalls += 1
-            if isinstance(want, dict):
+            if isinstance(want, dict) and "str" in want:
+                assert got == want["str"], "event %d: %s returned a different string" % (k, name)
+                nChecked += 1
+            elif isinstance(want, dict):
                 handles[want["h"]] = got
             elif isinstance(want, list):
                 assert len(got) == len(want), "event %d: %s returned %d values, recorded %d" % (k, name, len(got), len(want))

@@ -270,10 +270,56 @@ def opt_newt(seed, name):
     print(out, os.path.getsize(out), "bytes;", sum(counts.values()), "calls;", meta["lnL"])
 
 
+def sim_tree(seed, name):
+    """The reference's real Tree.simulate() (p4/tree.py:9527-9637): p4 makes its mt19937 stream (pf.gsl_rng_get / gsl_rng_set),
+    simulates into the tree's own data (pf.p4_simulate), re-compresses (pf.makePatterns, pf.setGlobalInvarSitesVec), brings the
+    sequences back (pf.symbolSequences) -- then evaluates the new data on the same tree.  GTR+I+G4 on L_mcmc/d.nex, twice."""
+    _begin(seed)
+    var.gsl_rng = None
+    read(os.path.join(EX, "d.nex"))
+    d = Data()
+    t = func.randomTree(taxNames=d.taxNames)
+    t.data = d
+    t.newComp(free=0, spec="empirical")
+    t.newRMatrix(free=0, spec="specified", val=[1.2, 3.1, 0.8, 0.9, 3.5, 1.0])
+    t.setNGammaCat(nGammaCat=4)
+    t.newGdasrv(free=0, val=0.6)
+    t.setPInvar(free=0, val=0.15)
+    lnLs = []
+    t.calcLogLike(verbose=0)
+    lnLs.append(float(t.logLike))
+    var.gsl_rng = pf_trace_rng_seed(4242)
+    for _ in range(2):
+        t.simulate()
+        t.calcLogLike(verbose=0)
+        lnLs.append(float(t.logLike))
+    rec.recording = False
+    var.gsl_rng = None
+    counts = {}
+    for ev in rec.events:
+        if ev[0] == "call":
+            counts[ev[1]] = counts.get(ev[1], 0) + 1
+    meta = {"what": "reference p4 Tree.calcLogLike(), then twice Tree.simulate() + Tree.calcLogLike() on the simulated data; GTR+I+G4, L_mcmc/d.nex",
+            "seed": seed, "calls": counts, "lnL": lnLs}
+    out = os.path.join(HERE, name)
+    rec.save(out, meta)
+    print(out, os.path.getsize(out), "bytes;", sum(counts.values()), "calls;", lnLs)
+
+
+def pf_trace_rng_seed(seed):
+    """What Tree.simulate does when var.gsl_rng is unset (p4/tree.py:9596-9598), with a fixed seed instead of the clock."""
+    g = rec.gsl_rng_get()
+    rec.gsl_rng_set(g, seed)
+    return g
+
+
 if __name__ == "__main__":
     os.chdir(tempfile.mkdtemp())
     if len(sys.argv) > 1 and sys.argv[1] == "opt":      # only the optimisation trace
         opt_newt(18, "trace_opt_newt.json.gz")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sim":      # only the simulation trace
+        sim_tree(19, "trace_sim_gtr_i_g4.json.gz")
         sys.exit(0)
     mcmc_simple(2, 120, 11, "trace_mcmc_gtr_i_g4.json.gz")
     mcmc_ndch2(2, 100, 12, "trace_mcmc_ndch2.json.gz")
@@ -283,3 +329,4 @@ if __name__ == "__main__":
     mcmc_protein(2, 80, 16, "trace_mcmc_protein_lg_i_g4.json.gz", 4)
     mcmc_protein(1, 60, 17, "trace_mcmc_protein_lg_i.json.gz", 1)
     opt_newt(18, "trace_opt_newt.json.gz")
+    sim_tree(19, "trace_sim_gtr_i_g4.json.gz")

@@ -1,5 +1,5 @@
-"""pf-boundary traces of the reference's REAL Mcmc and of its REAL Tree.optLogLike (Newton-Raphson drivers)
-(tests/golden/make_trace.py, oracle/pf_trace.py).
+"""pf-boundary traces of the reference's REAL Mcmc, of its REAL Tree.optLogLike (Newton-Raphson drivers) and of its REAL
+Tree.simulate (tests/golden/make_trace.py, oracle/pf_trace.py).
 
 CPU: the trace replays exactly on the reference's own engine (the harness is sound), and this repository's ``pf`` module
 offers every function the reference's callers used.  GPU: the trace replays on the B200 engine -- every log-likelihood
@@ -22,8 +22,10 @@ def test_trace_replays_on_the_reference_engine(ref_pf, path):
     trace = pf_trace.load(path)
     stats = pf_trace.replay(ref_pf, trace, tol=1e-14)
     assert stats["calls"] == sum(trace["meta"]["calls"].values())
-    few = os.path.basename(path).startswith("trace_opt_")     # an optimisation trace returns two vectors of branch lengths
-    assert stats["checked_values"] > (20 if few else 100) and stats["worst_rel_diff"] <= 1e-14
+    base = os.path.basename(path)
+    # an optimisation trace returns two vectors of branch lengths, a simulation trace three log-likelihoods and two sets of sequences
+    floor = 20 if base.startswith("trace_opt_") else (4 if base.startswith("trace_sim_") else 100)
+    assert stats["checked_values"] > floor and stats["worst_rel_diff"] <= 1e-14
 
 
 @pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[6:-8] for p in TRACES])
