@@ -40,4 +40,22 @@ pfm.gsl_rng_set(var.gsl_rng, 5)
 b = d.bootstrap()
 out["boot"] = [s.sequence for s in b.alignments[0].sequences]
 out["boot_nPat"] = [pfm.partPatternCount(p.cPart) for p in b.parts]
+# two character partitions of the same alignment (share/Examples/H_calcLike/C_3_data_partitions pattern), and a recoded datatype
+a = var.alignments[0]
+half = a.length // 2
+read("#nexus\nbegin sets;\n charset c1 = 1-%d;\n charset c2 = %d-.;\n charpartition cp1 = c1:c1, c2:c2;\nend;\n" % (half, half + 1))
+a.setCharPartition("cp1")
+d2 = Data()
+out["two_parts_nPatterns"] = [pfm.partPatternCount(p.cPart) for p in d2.parts]
+out["two_parts_comp"] = [list(p.composition()) for p in d2.parts]
+out["two_parts_sites_seq0"] = [pfm.partSequenceSitesCount(p.cPart, 0) for p in d2.parts]
+out["two_parts_counts_seq1"] = [list(pfm.singleSequenceBaseCounts(p.cPart, 1)) for p in d2.parts]
+var.alignments = []
+read(os.path.join(EX, "B_grouped_aa", "protein.nex"))
+pa = var.alignments[0]
+pa.recodeDayhoff()
+d3 = Data()
+out["dayhoff_nPatterns"] = [pfm.partPatternCount(p.cPart) for p in d3.parts]
+out["dayhoff_comp"] = list(d3.parts[0].composition())
+out["dayhoff_symbols"] = pfm.symbolSequences(d3.parts[0].cPart)[:200]
 print("RESULT" + json.dumps(out))
