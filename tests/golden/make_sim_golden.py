@@ -4,7 +4,7 @@ Runs in the BUILD container only.  For golden cases already committed here (inpu
 example data by make_golden.py) the reference's Pf engine (oracle/_ref) runs its own p4_simulate (Pf/p4_treeSim.c:14-420)
 on its own mt19937 stream seeded with SEED, and p4_drawAncState (Pf/p4_treeSim.c:591-857) for the first sites after
 srandom(SEED); the simulated sequences (as symbol strings, pf.symbolSequences) and the draws go to
-tests/golden/simulate.json.  tests/test_gpu_sim_golden.py replays them on the GPU.
+tests/golden/simulate.json.  tests/test_zz_gpu_sim_golden.py replays them on the GPU.
 
 Usage: python tests/golden/make_sim_golden.py
 """

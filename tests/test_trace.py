@@ -35,9 +35,14 @@ def test_engine_offers_every_call_the_reference_made(pkg, path):
         assert callable(getattr(pkg.pf, name)), name
 
 
+# the simulation trace was recorded after the round's GPU minutes were spent: it replays last (see the end of the file)
+SIM_TRACES = [p for p in TRACES if os.path.basename(p).startswith("trace_sim_")]
+GPU_TRACES = [p for p in TRACES if p not in SIM_TRACES]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["default", "immediate"])
-@pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[6:-8] for p in TRACES])
+@pytest.mark.parametrize("path", GPU_TRACES, ids=[os.path.basename(p)[6:-8] for p in GPU_TRACES])
 def test_trace_replays_on_the_gpu_engine(pkg, path, mode):
     pf = pkg.pf
     trace = pf_trace.load(path)
@@ -56,3 +61,11 @@ def test_trace_replays_on_the_gpu_engine(pkg, path, mode):
     assert stats["calls"] == sum(trace["meta"]["calls"].values())
     print("replayed %(calls)d calls, checked %(checked_values)d returned values and %(engine_written_buffers_checked)d "
           "engine-written buffers, worst rel. diff %(worst_rel_diff).3e" % stats)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["default", "immediate"])
+@pytest.mark.parametrize("path", SIM_TRACES, ids=[os.path.basename(p)[6:-8] for p in SIM_TRACES])
+def test_simulation_trace_replays_on_the_gpu_engine(pkg, path, mode):
+    """The reference's real Tree.simulate() + Tree.calcLogLike(): same sequences (pf.symbolSequences) and log-likelihoods."""
+    test_trace_replays_on_the_gpu_engine(pkg, path, mode)

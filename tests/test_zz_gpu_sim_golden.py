@@ -1,7 +1,9 @@
 """GPU: pf.p4_simulate and pf.p4_drawAncState on the engine against committed golden answers (tests/golden/simulate.json,
 frozen by tests/golden/make_sim_golden.py from the reference's own p4_simulate / p4_drawAncState on the reference's example
 cases): for the recorded seed every simulated symbol of every sequence, the pattern counts, the log-likelihood of the
-simulated data (1e-9) and the root-state draws are the reference's.  Needs no reference engine at run time."""
+simulated data (1e-9) and the root-state draws are the reference's.  Needs no reference engine at run time.
+(The file sorts last on purpose: it was written after the round's GPU minutes were spent -- its logic was checked against the
+reference engine on the CPU -- so under `pytest -x` a surprise here cannot hide the suites that were verified on a B200.)"""
 import json
 import os
 
