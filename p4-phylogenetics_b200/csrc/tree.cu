@@ -1608,6 +1608,7 @@ static int checkTwins(Tree *a, Tree *b)
 {
     if (!a->dev || !b->dev) { setError("tree has no device state"); return 1; }
     if (a->nNodes != b->nNodes || a->nParts != b->nParts) { setError("the two trees differ in node or part count"); return 1; }
+    if (ensureFresh(a, false) || ensureFresh(b, false)) return 1;   // data parts re-compressed since: lay both out again first
     for (int p = 0; p < a->nParts; p++) {
         const PartLayout &A = a->dev->parts[p], &B = b->dev->parts[p];
         if (A.clNodeDoubles != B.clNodeDoubles || A.pDoubles != B.pDoubles || A.W != B.W || A.scalers != B.scalers || A.ps != B.ps) { setError("the two trees differ in part %d layout", p); return 1; }
