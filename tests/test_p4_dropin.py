@@ -14,8 +14,8 @@ import ref_loader
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(which):
-    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin", "p4_data_side.py"), which], capture_output=True, text=True, timeout=300)
+def _run(which, script="p4_data_side.py"):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin", script), which], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1]
     return json.loads(line[len("RESULT"):])
@@ -29,3 +29,13 @@ def test_real_p4_data_side_runs_on_this_pf_module(pkg):
     for k in want:
         assert got[k] == want[k], k
     assert got["nPatterns"][0] > 10 and len(got["boot"]) >= 4
+
+
+def test_real_p4_model_side_runs_on_this_pf_module(pkg):
+    """p4's own Tree model API and Model.allocCStuff / setCStuff on this pf module: empirical composition, gamma rates and the
+    normalised rate matrix the engine then holds are the reference engine's, bit for bit."""
+    if not ref_loader.have_ref_p4():
+        pytest.skip("the reference's p4 package is not present (it never is on the GPU box)")
+    want, got = _run("ref", "p4_model_side.py"), _run("mine", "p4_model_side.py")
+    assert got == want
+    assert len(got["Q"]) == 16 and got["nFreePrams"] == 3 + 5 + 1 + 1
