@@ -75,6 +75,11 @@ int p4b_commDestroy(void);
  * default; 0 selects the one-launch-per-node kernels instead (same results;
  * kept for comparison and profiling). */
 void p4b_setFusedTreeKernel(int on);
+/* Launch shape of the 4-state whole-tree kernel.  -1 (default): chosen from the shard size -- 128 threads x 3
+ * CTAs/SM for three waves or more, 64 x 5 or 32 x 7 for smaller shards (what a 4- or 8-GPU run of BASELINE
+ * configs[1] uses).  0, 1, 2 force one of those three; 3..8 are comparison shapes.  Results are bit-identical
+ * across shapes; the setter exists so that the parity tests can run every shape at every shard size. */
+int p4b_setFusedVariant(int v);
 /* 20-state parts with 4 rate categories have a whole-tree kernel of their own (FP64 tensor cores, the
  * running CL stays in the accumulator registers from one node to the next); 0 keeps the one-launch-
  * per-node kernels for them. */

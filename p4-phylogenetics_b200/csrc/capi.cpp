@@ -37,6 +37,7 @@ int p4b_commInitRank(const char id128[128], int rank, int world) { return commIn
 int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
+int p4b_setFusedVariant(int v) { return setFusedVariant(v); }
 void p4b_setFusedTreeKernel20(int on) { setFusedAAEnabled(on); }
 void p4b_setDeferredNodeCalls(int on) { setDeferEnabled(on); }
 void p4b_setSharedCondLikes(int on) { setShareEnabled(on); }
@@ -383,8 +384,13 @@ p4b_node p4b_newNode(int nodeNum, p4b_tree t, int seqNum, int isLeaf, int inTree
     n->rMatrixNums.assign(T->nParts, 0);
     n->gdasrvNums.assign(T->nParts, 0);
     n->clNeedsUpdating = (!isLeaf && inTree) ? 1 : 0;   // Pf/p4_node.c:114-122
-    if (nodeDeviceCreate(n)) { delete n; return nullptr; }
-    delete T->nodes[nodeNum];
+    if (Node *old = T->nodes[nodeNum]) {   // a replaced node gives its CL slots back before the new one asks for its own
+        if (treeHasPending(T)) treeFlushPending(T);
+        nodeDeviceRelease(old);
+        T->nodes[nodeNum] = nullptr;
+        delete old;
+    }
+    if (nodeDeviceCreate(n)) { nodeDeviceRelease(n); delete n; return nullptr; }
     T->nodes[nodeNum] = n;
     return n;
 }

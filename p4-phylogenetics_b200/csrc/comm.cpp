@@ -81,12 +81,15 @@ int commInitRank(const char id128[128], int rank, int world)
     if (load()) return 1;
     if (N.comm) { setError("communicator already initialised"); return 1; }
     if (engineInitPublic()) return 1;
-    if (setShard(rank, world)) return 1;
+    if (world < 1 || rank < 0 || rank >= world) { setError("p4b_commInitRank: bad rank %d of %d", rank, world); return 1; }
     UniqueId id;
     memcpy(id.internal, id128, 128);
-    if (check(N.commInitRank(&N.comm, world, id, rank), "ncclCommInitRank")) return 1;
+    if (check(N.commInitRank(&N.comm, world, id, rank), "ncclCommInitRank")) { N.comm = nullptr; return 1; }
     N.world = world;
-    return 0;
+    // the process owns its pattern range only once the communicator exists: a failed init must not
+    // leave a shard behind whose partial lnL nobody sums (part mirrors and trees laid out for another
+    // range are rebuilt at their next use, csrc/tree.cu partDeviceEnsure / ensureFresh)
+    return setShard(rank, world);
 }
 
 int commDestroy()
@@ -94,6 +97,8 @@ int commDestroy()
     if (N.comm) {
         N.commDestroy(N.comm);
         N.comm = nullptr;
+        N.world = 1;
+        setShard(0, 1);   // without a communicator every process evaluates the whole alignment again
     }
     return 0;
 }

@@ -30,6 +30,7 @@ struct PartDevice {
     uint64_t *equateMask = nullptr; // [nRealEquates] bit s set <=> state s allowed
     uint64_t dataVersion = 0;  // Part::version this mirror was built from
     int device = -1;
+    int rank = 0, world = 1;   // the shard (p4b_setShard) lo/hi were cut for
 };
 
 struct Part {
@@ -183,6 +184,7 @@ int treeFlushL2(Tree *t);
 int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
 void setFusedEnabled(int on);
+int setFusedVariant(int v);
 void setDmmaEnabled(int on);
 void setScalersEnabled(int on);
 int treeEnsureResident(Tree *t, int p);

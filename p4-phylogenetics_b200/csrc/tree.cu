@@ -173,7 +173,8 @@ void partDeviceFree(Part *p)
 static int partDeviceEnsure(Part *p)
 {
     PartDevice &d = p->dev;
-    if (d.tips && d.dataVersion == p->version && d.device == G.device) return 0;
+    if (d.tips && d.dataVersion == p->version && d.device == G.device && d.rank == G.rank && d.world == G.world) return 0;
+    if (d.tips && (d.rank != G.rank || d.world != G.world)) p->version++;   // the shard moved: trees laid out on the old range are stale too
     partDeviceFree(p);
     if (p->nPatterns <= 0) { setError("part has no patterns (pf.makePatterns not called?)"); return 1; }
     shardRange(p->nPatterns, &d.lo, &d.hi);
@@ -226,6 +227,8 @@ static int partDeviceEnsure(Part *p)
     CUDA_TRY(cudaMemcpy(d.equateMask, em.data(), em.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
     d.dataVersion = p->version;
     d.device = G.device;
+    d.rank = G.rank;
+    d.world = G.world;
     return 0;
 }
 
@@ -514,8 +517,12 @@ static int ensureFresh(Tree *t, bool needPatterns)
     TreeDevice *d = t->dev;
     if (!d) return 0;
     bool stale = false;
-    for (int p = 0; p < t->nParts; p++)
-        if (t->data->parts[p]->version != d->dataVersion[p]) stale = true;
+    for (int p = 0; p < t->nParts; p++) {
+        Part *dp = t->data->parts[p];
+        // a mirror built before p4b_setShard / p4b_commInitRank moved this process to another pattern range
+        if (dp->dev.tips && (dp->dev.rank != G.rank || dp->dev.world != G.world)) dp->version++;
+        if (dp->version != d->dataVersion[p]) stale = true;
+    }
     if (!stale) return 0;
     for (int p = 0; p < t->nParts; p++)
         if (t->data->parts[p]->nPatterns <= 0) {
@@ -524,9 +531,11 @@ static int ensureFresh(Tree *t, bool needPatterns)
             return 1;
         }
     treeDeviceDestroy(t);
-    if (treeDeviceCreate(t)) return 1;
+    // on any failure leave NO device state behind: later calls then report "tree has no device state"
+    // instead of walking a half-built layout
+    if (treeDeviceCreate(t)) { treeDeviceDestroy(t); return 1; }
     for (Node *n : t->nodes)
-        if (n && nodeDeviceCreate(n)) return 1;
+        if (n && nodeDeviceCreate(n)) { treeDeviceDestroy(t); return 1; }
     return treeCalculateAllBigPDecks(t);
 }
 
@@ -943,6 +952,13 @@ struct FusedJob {
 // 2.70 / 2.82 / 3.21, 250 k 1.56 / 1.42 / 1.65, 125 k 0.99 / 0.90 / 0.86.  What decides is how many waves
 // of 128-thread CTAs the launch makes: the last, partial wave leaves SMs idle unless the CTAs are small.
 // P4B_FUSED_VARIANT overrides the choice (tuning).
+static int g_fusedVariant = -1;   // p4b_setFusedVariant: -1 = by shard size
+int setFusedVariant(int v)
+{
+    if (v < -1 || v > 8) { setError("p4b_setFusedVariant: launch shape %d does not exist (-1 .. 8)", v); return 1; }
+    g_fusedVariant = v;
+    return 0;
+}
 static int fusedVariant(int ps, int nTrees)
 {
     static int forced = -2;
@@ -951,6 +967,7 @@ static int fusedVariant(int ps, int nTrees)
         forced = e ? atoi(e) : -1;
         if (forced < -1 || forced > 8) forced = -1;
     }
+    if (g_fusedVariant >= 0) return g_fusedVariant;
     if (forced >= 0) return forced;
     const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
     return waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
@@ -1555,6 +1572,7 @@ int treesPartLogLike(Tree **trees, int n, int p, double *out)
         }
         return 0;
     }
+    const int stepKids = trees[0]->dev->parts[p].dim == 20 ? kAAKids : kMaxChildren;
     int i0 = 0;
     while (i0 < n) {
         // greedy group: at most kMaxBatchTrees trees and kMaxSteps steps
@@ -1564,7 +1582,7 @@ int treesPartLogLike(Tree **trees, int n, int p, double *out)
             for (Node *nd : trees[i1]->dev->pending[p]) {
                 int kids = 0;
                 for (Node *c = nd->leftChild; c; c = c->sibling) kids++;
-                need += (kids + kMaxChildren - 1) / kMaxChildren;
+                need += (kids + stepKids - 1) / stepKids;     // the kernel's own step width: an upper bound on what buildSteps writes
             }
             if (i1 > i0 && steps + need > kMaxSteps) break;
             steps += need;
@@ -1585,7 +1603,21 @@ int treesPartLogLike(Tree **trees, int n, int p, double *out)
             orders[k].swap(t->dev->pending[p]);
             jobs[k] = FusedJob{t, &orders[k], true, false, true, true};
         }
-        if (launchFusedBatch(jobs.data(), m, p, G.dBatch)) return 1;
+        if (launchFusedBatch(jobs.data(), m, p, G.dBatch)) {
+            // nothing was launched: the calls go back into their queues, and no node of them may pass for
+            // computed (buildSteps stamps nodes as it writes their steps)
+            for (int k = 0; k < m; k++) {
+                Tree *t = trees[i0 + k];
+                for (Node *nd : orders[k]) {
+                    nd->clStamp[p] = ++G.stamp;
+                    nd->clKey[p].clear();
+                    nd->clNeedsUpdating = 1;
+                }
+                std::vector<Node *> &q = t->dev->pending[p];
+                q.insert(q.begin(), orders[k].begin(), orders[k].end());
+            }
+            return 1;
+        }
         if (commActive())
             if (commAllReduceSum(G.dBatch, 2 * m, (void *)G.stream)) return 1;
         CUDA_TRY(cudaMemcpyAsync(G.hBatch, G.dBatch, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
@@ -1962,6 +1994,10 @@ static void newtStateFree(TreeDevice *d)
 int treeNewtSetup(Tree *t)
 {
     if (!t->dev) { setError("tree has no device state"); return 1; }
+    // the data parts may have been re-compressed since the tree was laid out: cl2 must be sized for the
+    // layout the evaluation will use, not for one that is about to be discarded
+    if (ensureFresh(t, true)) return 1;
+    if (!t->dev) { setError("tree has no device state"); return 1; }
     TreeDevice *d = t->dev;
     if (d->newt) return 0;
     if (!t->root) { setError("p4_newtSetup: the tree has no root"); return 1; }
@@ -2296,10 +2332,17 @@ double treeNewtAround(Tree *t, double epsilon, double likeDelta)
 {
     if (!t->dev) { setError("tree has no device state"); return NAN; }
     if (!t->dev->newt) { setError("p4_newtAround: call p4_newtSetup first"); return NAN; }
-    NewtState *S = t->dev->newt;
+    // A data-version change (pf.makePatterns, setGlobalInvarSitesVec, p4_simulate) lays the tree out again
+    // and drops the Newton work arrays with the old layout: do that NOW and set them up again for the new
+    // one, so that no pointer into the old state is held across it.
+    if (ensureFresh(t, true)) return NAN;
+    if (!t->dev) { setError("tree has no device state"); return NAN; }
+    if (!t->dev->newt && treeNewtSetup(t)) return NAN;
     if (t->root && t->root->isLeaf) { setError("p4_newtAround: the root is a leaf"); return NAN; }
     double previous = treeLogLike(t, 0);
     if (previous != previous) return NAN;
+    NewtState *S = t->dev ? t->dev->newt : nullptr;
+    if (!S) { setError("p4_newtAround: the Newton state was lost during the evaluation"); return NAN; }
     for (Node *n : t->nodes)
         if (n) n->clNeedsUpdating = 0;
     std::vector<Node *> order;
@@ -2344,6 +2387,9 @@ int nodeNewtDerivs(Node *n, double out[3])
 {
     Tree *t = n->tree;
     if (!t->dev || !t->dev->newt) { setError("p4b_newtDerivs: call p4_newtSetup first"); return 1; }
+    if (ensureFresh(t, true)) return 1;
+    if (!t->dev) { setError("tree has no device state"); return 1; }
+    if (!t->dev->newt && treeNewtSetup(t)) return 1;
     if (n == t->root || !n->parent) { setError("p4b_newtDerivs: the root has no branch"); return 1; }
     if (treeFlushAllPending(t)) return 1;
     if (newtUploadRootTables(t)) return 1;

@@ -75,6 +75,7 @@ _sig("p4b_commInitRank", _i, C.c_char_p, _i, _i)
 _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
+_sig("p4b_setFusedVariant", _i, _i)
 _sig("p4b_setTensorCoreKernel", None, _i)
 _sig("p4b_setFusedTreeKernel20", None, _i)
 _sig("p4b_setDeferredNodeCalls", None, _i)
@@ -262,6 +263,11 @@ def commDestroy():
 
 def setFusedTreeKernel(on):
     _lib.p4b_setFusedTreeKernel(int(on))
+
+
+def setFusedVariant(v):
+    """Launch shape of the 4-state whole-tree kernel: -1 by shard size (default), 0/1/2 forced (include/p4b200.h)."""
+    _ok(_lib.p4b_setFusedVariant(int(v)))
 
 
 def setDeferredNodeCalls(on):
