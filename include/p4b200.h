@@ -254,6 +254,18 @@ double p4b_logLikeForParameters(p4b_tree t, int doBrLens, const double *x);   /*
  * parent to the root.  maxPasses passes over all branches or until a pass gains less than tol.  Returns
  * the final log-likelihood (NaN on error); *nEvals receives the number of likelihood evaluations. */
 double p4b_optimizeBrLens(p4b_tree t, int maxPasses, double tol, long *nEvals);
+/* The reference's four optimiser entry points, native (csrc/opt.cpp, csrc/praxis.cpp): the reference's schedules of
+ * calls with every objective evaluation (p4_setPrams + p4_treeLogLike) on the GPU.  Each returns the number of
+ * objective evaluations, -1 on error. */
+long p4b_allBrentPowellOptimize(p4b_tree t);               /* pf.p4_allBrentPowellOptimize, Pf/pfmodule.c:2247 -> Pf/p4_treeOpt.c:996-1180: Brent's praxis over model parameters and branch lengths */
+long p4b_allBOBYQAOptimize(p4b_tree t, int doBrLens);      /* pf.p4_allBOBYQAOptimize :2212 -> Pf/p4_treeOpt.c:617-753: the box of p4_windUpParameters; a bounded Powell method stands where the reference calls nlopt */
+long p4b_newtAndBrentPowellOpt(p4b_tree t);                /* pf.p4_newtAndBrentPowellOpt :2262 -> Pf/p4_treeOpt.c:1182-1330 (needs no p4_newtSetup call: it is made) */
+long p4b_newtAndBOBYQAOpt(p4b_tree t);                     /* pf.p4_newtAndBOBYQAOpt :2230 -> Pf/p4_treeOpt.c:755-945 */
+/* The two minimisers on a caller's objective fn(x, ctx) (host code; used by the entry points above and by the CPU tests):
+ * Brent's principal-axis method as Pf/brent.c runs it (tol, h as there), and Powell's method confined to the box [lo, hi]. */
+double p4b_praxisMinimize(int n, double *x, double tol, double h, double (*fn)(const double *, void *), void *ctx);
+double p4b_boundedMinimize(int n, double *x, const double *lo, const double *hi, double xtol, double ftol, long maxEvals,
+                           double (*fn)(const double *, void *), void *ctx, long *nEvals);
 /* ---- Newton-Raphson on the branch lengths --- Pf/p4_treeNewt.c -- */
 /* pf.p4_newtSetup(tree) Pf/pfmodule.c:2298 -> p4_newtSetup Pf/p4_treeNewt.c:11-75: allocates cl2 (per node,
  * the conditional likelihoods of everything on the far side of the node's branch) and the work space of the

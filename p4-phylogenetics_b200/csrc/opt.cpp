@@ -5,19 +5,23 @@
 // rebuilds the model and evaluates the tree (p4_logLikeForNLOpt :579-615:
 // p4_unWindParameters -> p4_setPrams -> p4_treeLogLike).  This file provides the same packing,
 // unpacking and objective on the B200 engine, so that any bounded optimiser can drive the GPU
-// with the reference's own parameterisation.  The optimiser itself is not here: nlopt's BOBYQA
-// is a third-party library the reference links (absent from this image); pf.py drives this
-// objective with a bounded derivative-free method instead.
+// with the reference's own parameterisation, and the reference's four optimiser entry points on top of it
+// (p4_allBrentPowellOptimize :947-1180, p4_newtAndBrentPowellOpt :1182-1330, p4_allBOBYQAOptimize :617-753,
+// p4_newtAndBOBYQAOpt :755-945): the same schedules of calls, with Brent's praxis restated in csrc/praxis.cpp
+// and a bounded Powell method where the reference calls nlopt's BOBYQA (a third-party library this engine does
+// not link).  Every objective evaluation is p4_setPrams + p4_treeLogLike on the GPU.
 //
 // Unpacking follows p4_unWindParameters (:186-565) with one simplification: where the reference
 // nudges an out-of-bounds rate by a random amount (RATE_MIN * ranDoubleUpToOne(), :356, :373) the
-// value is clamped, so the objective is a deterministic function of the vector.
+// value is clamped, so the objective is a deterministic function of the vector.  Like the reference
+// (:568-571) a vector that hit a limit is wound up again from the clamped model, in place.
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "../../include/p4b200.h"
 #include "engine.h"
+#include "optim.h"
 
 namespace p4b {
 
@@ -79,10 +83,19 @@ int windUpParameters(Tree *t, int doBrLens, double *x, double *lb, double *ub)
     return pos;
 }
 
+static bool g_hitLimit = false;   // set by unWindParameters when a value had to be clamped
+static inline double clampHit(double v, double lo, double hi)
+{
+    if (v < lo) { g_hitLimit = true; return lo; }
+    if (v > hi) { g_hitLimit = true; return hi; }
+    return v;
+}
+
 int unWindParameters(Tree *t, int doBrLens, const double *x)
 {
     Model *m = t->model;
     int pos = 0;
+    g_hitLimit = false;
     for (int p = 0; p < m->nParts; p++) {
         ModelPart *mp = m->parts[p];
         const int dim = mp->dim;
@@ -92,7 +105,7 @@ int unWindParameters(Tree *t, int doBrLens, const double *x)
                 double sum = 0.0;
                 for (int i = 0; i < dim - 1; i++) {
                     double par = x[pos++];
-                    par = par <= pmin ? 0.0 : par - pmin;
+                    if (par <= pmin) { g_hitLimit = true; par = 0.0; } else par = par - pmin;
                     c.val[i] = par;
                     sum += par;
                 }
@@ -106,17 +119,17 @@ int unWindParameters(Tree *t, int doBrLens, const double *x)
         for (auto &r : mp->rMatrices)
             if (r.isFree) {
                 if (r.spec == 5) {
-                    r.kappa = clampd(x[pos++], m->KAPPA_MIN[0], m->KAPPA_MAX[0]);
+                    r.kappa = clampHit(x[pos++], m->KAPPA_MIN[0], m->KAPPA_MAX[0]);
                     setKappaBigR(r);
                 } else if (m->rMatrixNormalizeTo1 && m->rMatrixNormalizeTo1[0]) {   // :343-404
                     double sum = 0.0;
                     for (int i = 0; i < dim - 2; i++)
                         for (int j = i + 1; j < dim; j++) {
-                            const double par = clampd(x[pos++], m->RATE_MIN[0], 0.999);
+                            const double par = clampHit(x[pos++], m->RATE_MIN[0], 0.999);
                             r.bigR[i * dim + j] = par;
                             sum += par;
                         }
-                    double last = sum < 1.0 ? clampd(1.0 - sum, m->RATE_MIN[0], 0.999) : m->RATE_MIN[0] * sum;
+                    double last = sum < 1.0 ? clampHit(1.0 - sum, m->RATE_MIN[0], 0.999) : m->RATE_MIN[0] * sum;
                     sum += last;
                     r.bigR[(dim - 2) * dim + (dim - 1)] = last;
                     for (int i = 0; i < dim - 1; i++)
@@ -127,17 +140,17 @@ int unWindParameters(Tree *t, int doBrLens, const double *x)
                 } else {
                     for (int i = 0; i < dim - 2; i++)
                         for (int j = i + 1; j < dim; j++) {
-                            const double par = clampd(x[pos++], m->RATE_MIN[0], m->RATE_MAX[0]);
+                            const double par = clampHit(x[pos++], m->RATE_MIN[0], m->RATE_MAX[0]);
                             r.bigR[i * dim + j] = r.bigR[j * dim + i] = par;
                         }
                 }
             }
         for (Gdasrv *g : mp->gdasrvs)
-            if (g && g->isFree) g->val[0] = clampd(x[pos++], m->GAMMA_SHAPE_MIN[0], m->GAMMA_SHAPE_MAX[0]);
-        if (mp->pInvarFree) mp->pInvar = clampd(x[pos++], m->PINVAR_MIN[0], m->PINVAR_MAX[0]);
+            if (g && g->isFree) g->val[0] = clampHit(x[pos++], m->GAMMA_SHAPE_MIN[0], m->GAMMA_SHAPE_MAX[0]);
+        if (mp->pInvarFree) mp->pInvar = clampHit(x[pos++], m->PINVAR_MIN[0], m->PINVAR_MAX[0]);
     }
     if (m->relRatesAreFree) {   // :521-545: the last part's rate keeps the site-weighted mean at 1
-        for (int p = 0; p < m->nParts - 1; p++) m->parts[p]->relRate = clampd(x[pos++], m->RELRATE_MIN[0], m->RELRATE_MAX[0]);
+        for (int p = 0; p < m->nParts - 1; p++) m->parts[p]->relRate = clampHit(x[pos++], m->RELRATE_MIN[0], m->RELRATE_MAX[0]);
         long totLen = 0;
         for (int p = 0; p < m->nParts; p++) totLen += t->data->parts[p]->nChar;
         double sum = 0.0;
@@ -146,7 +159,7 @@ int unWindParameters(Tree *t, int doBrLens, const double *x)
     }
     if (doBrLens)
         for (Node *nd : t->nodes)
-            if (nd && nd != t->root) nd->brLen = clampd(x[pos++], m->BRLEN_MIN[0], m->BRLEN_MAX[0]);
+            if (nd && nd != t->root) nd->brLen = clampHit(x[pos++], m->BRLEN_MIN[0], m->BRLEN_MAX[0]);
     return pos;
 }
 
@@ -264,6 +277,190 @@ double optimizeBrLens(Tree *t, int maxPasses, double tol, long *nEvals)
     return cur;
 }
 
+
+// ---------------------------------------------------------------------------
+// The reference's optimiser entry points
+// ---------------------------------------------------------------------------
+namespace {
+struct OptRun {
+    Tree *t;
+    int doBrLens;
+    long evals = 0;
+    bool failed = false;
+    // minus the log-likelihood at x: p4_minusLogLikeForBrent (Pf/p4_treeOpt.c:947-985)
+    double minusLogLike(double *x)
+    {
+        if (failed) return 1.0e99;
+        unWindParameters(t, doBrLens, x);
+        if (g_hitLimit) windUpParameters(t, doBrLens, x, nullptr, nullptr);
+        if (treeSetPrams(t, -1)) { failed = true; return 1.0e99; }
+        const double v = treeLogLike(t, 0);
+        evals++;
+        if (v != v) { failed = true; return 1.0e99; }
+        return -v;
+    }
+    // make the model and the tree those of x (the last point evaluated need not be the best one)
+    int settle(double *x)
+    {
+        unWindParameters(t, doBrLens, x);
+        return treeSetPrams(t, -1);
+    }
+};
+
+// evaluations that never read a CL back run in lnL-only mode (Tree::storeCL = 0); restored on the way out
+struct LnLOnly {
+    Tree *t;
+    int saved;
+    explicit LnLOnly(Tree *tr) : t(tr), saved(tr->storeCL) { t->storeCL = 0; }
+    ~LnLOnly() { t->storeCL = saved; }
+};
+
+inline bool isBad(double v) { return v != v; }
+const double kNewtFull[4][2] = {{1.0, 10.0}, {1.0e-1, 1.0}, {1.0e-2, 0.1}, {1.0e-5, 1.0e-7}};
+}  // namespace
+
+// p4_allBrentPowellOptimize (Pf/p4_treeOpt.c:996-1180): praxis(1e-4, 0.1) over all parameters and branch lengths
+// until a call gains less than 1e-6, then the same again with h = 0.05.  Returns the number of evaluations, -1 on error.
+long allBrentPowellOptimize(Tree *t)
+{
+    const int n = countParameters(t, 1);
+    if (n <= 0) return 0;
+    OptRun run{t, 1};
+    std::vector<double> x(n);
+    windUpParameters(t, 1, x.data(), nullptr, nullptr);
+    Praxis px(n);
+    double previous = treeLogLike(t, 0);
+    if (previous != previous) return -1;
+    run.evals = 1;
+    Objective f = [&](double *p) { return run.minusLogLike(p); };
+    {
+        LnLOnly guard(t);
+        double diff = previous;
+        while (fabs(diff) > 1.0e-6) {
+            const double lnL = -px.minimize(1.0e-4, 0.1, x.data(), f);
+            if (run.failed || run.settle(x.data())) return -1;
+            diff = lnL - previous;
+            previous = lnL;
+        }
+    }
+    if (isBad(treeLogLike(t, 0))) return -1;     // (the reference evaluates the tree here, :1113)
+    windUpParameters(t, 1, x.data(), nullptr, nullptr);
+    {
+        LnLOnly guard(t);
+        double diff = 1.0;
+        while (fabs(diff) > 1.0e-6) {
+            const double lnL = -px.minimize(1.0e-4, 0.05, x.data(), f);
+            if (run.failed || run.settle(x.data())) return -1;
+            diff = previous - lnL;
+            previous = lnL;
+        }
+    }
+    const double last = treeLogLike(t, 0);
+    if (last != last) return -1;
+    return run.evals + 3;
+}
+
+// p4_allBOBYQAOptimize (Pf/p4_treeOpt.c:617-753): two bounded derivative-free maximisations of the objective,
+// the second from the re-wound result of the first with the tighter stopping rule (ftol_abs 1e-6, then 1e-8).
+long allBoundedOptimize(Tree *t, int doBrLens)
+{
+    const int n = countParameters(t, doBrLens);
+    if (n <= 0) return 0;
+    OptRun run{t, doBrLens};
+    std::vector<double> x(n), lo(n), hi(n);
+    windUpParameters(t, doBrLens, x.data(), lo.data(), hi.data());
+    Objective f = [&](double *p) { return run.minusLogLike(p); };
+    long evals = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        {
+            LnLOnly guard(t);
+            const double fAbs = pass == 0 ? 1.0e-6 : 1.0e-8;
+            double scale = fabs(treeLogLike(t, 0));
+            if (!(scale > 1.0)) scale = 1.0;
+            boundedPowell(n, x.data(), lo.data(), hi.data(), f, 1.0e-7, fAbs / scale, 400L * n + 4000, &evals);
+            if (run.failed || run.settle(x.data())) return -1;
+        }
+        const double v = treeLogLike(t, 0);
+        if (v != v) return -1;
+        windUpParameters(t, doBrLens, x.data(), lo.data(), hi.data());
+    }
+    return evals + run.evals;
+}
+
+static int newtSchedule(Tree *t, int from, int to)
+{
+    for (int i = from; i < to; i++) {
+        const double v = treeNewtAround(t, kNewtFull[i][0], kNewtFull[i][1]);
+        if (v != v) return 1;
+    }
+    return 0;
+}
+
+// p4_newtAndBrentPowellOpt (Pf/p4_treeOpt.c:1182-1330) and p4_newtAndBOBYQAOpt (:755-945): branch lengths by
+// Newton-Raphson (p4_newtAround), the free model parameters by praxis (bounded = 0) or the bounded method
+// (bounded = 1), alternating until a round gains less than 1e-6 or the pass limit is reached.
+long newtAndModelOpt(Tree *t, int bounded)
+{
+    if (treeNewtSetup(t)) return -1;
+    const int n = countParameters(t, 0);
+    if (n == 0) return newtSchedule(t, 0, 4) ? -1 : 0;          // :1214-1226
+    OptRun run{t, 0};
+    std::vector<double> x(n), lo(n), hi(n);
+    windUpParameters(t, 0, x.data(), lo.data(), hi.data());
+    Objective f = [&](double *p) { return run.minusLogLike(p); };
+    long evals = 0;
+    if (n == 1 && !bounded) {
+        // p4_newtAnd1DBrent (:1395-1436): Newton rounds, then the one parameter by Brent's one-dimensional
+        // minimiser, alternating.  The reference brackets the minimum first and then runs LocalMin; here the
+        // parameter's own bounds are the bracket.
+        if (newtSchedule(t, 0, 3)) return -1;
+        double before = 0.0;
+        for (int iter = 0; iter <= 21; iter++) {
+            if (iter > 0 && isBad(treeNewtAround(t, 1.0e-5, 1.0e-7))) return -1;
+            windUpParameters(t, 0, x.data(), lo.data(), hi.data());
+            double lnL;
+            {
+                LnLOnly guard(t);
+                lnL = -boundedPowell(1, x.data(), lo.data(), hi.data(), f, 1.0e-7, 1.0e-14, 400, &evals);
+                if (run.failed || run.settle(x.data())) return -1;
+            }
+            if (iter > 0 && fabs(lnL - before) < 1.0e-6) break;
+            before = lnL;
+        }
+        return isBad(treeLogLike(t, 0)) ? -1 : evals + run.evals;
+    }
+    if (isBad(treeNewtAround(t, 1.0, 10.0))) return -1;       // :1242-1244 / :800-802
+    {
+        const double a = treeNewtAround(t, 1.0e-1, 1.0), b = treeNewtAround(t, 1.0e-5, 1.0e-7);
+        if (a != a || b != b) return -1;
+    }
+    Praxis px(n);
+    double previous = treeLogLike(t, 0);
+    if (previous != previous) return -1;
+    const int limit = bounded ? 50 : ((t->passLimit && t->passLimit[0] > 0) ? t->passLimit[0] : 50);
+    for (int pass = 0;; ) {
+        if (isBad(treeNewtAround(t, 1.0e-5, 1.0e-7))) return -1;
+        double lnL;
+        {
+            LnLOnly guard(t);
+            if (bounded) {
+                double scale = fabs(previous) > 1.0 ? fabs(previous) : 1.0;
+                lnL = -boundedPowell(n, x.data(), lo.data(), hi.data(), f, 1.0e-7, 1.0e-8 / scale, 400L * n + 4000, &evals);
+            } else {
+                lnL = -px.minimize(1.0e-4, 1.0, x.data(), f);
+            }
+            if (run.failed || run.settle(x.data())) return -1;
+        }
+        const double diff = lnL - previous;
+        previous = lnL;
+        if (fabs(diff) < 1.0e-6) break;
+        if (++pass > limit) break;       // the reference prints "Pass limit exceeded without convergence" and stops too
+    }
+    const double last = treeLogLike(t, 0);
+    if (last != last) return -1;
+    return evals + run.evals;
+}
+
 }  // namespace p4b
 
 using namespace p4b;
@@ -298,6 +495,42 @@ double p4b_optimizeBrLens(p4b_tree t, int maxPasses, double tol, long *nEvals)
     if (!t) { setError("p4b_optimizeBrLens: NULL handle"); return NAN; }
     if (nEvals) *nEvals = 0;
     return optimizeBrLens((Tree *)t, maxPasses < 1 ? 1 : maxPasses, tol, nEvals);
+}
+long p4b_allBrentPowellOptimize(p4b_tree t)
+{
+    if (!t) { setError("p4_allBrentPowellOptimize: NULL handle"); return -1; }
+    return allBrentPowellOptimize((Tree *)t);
+}
+long p4b_allBOBYQAOptimize(p4b_tree t, int doBrLens)
+{
+    if (!t) { setError("p4_allBOBYQAOptimize: NULL handle"); return -1; }
+    return allBoundedOptimize((Tree *)t, doBrLens);
+}
+long p4b_newtAndBrentPowellOpt(p4b_tree t)
+{
+    if (!t) { setError("p4_newtAndBrentPowellOpt: NULL handle"); return -1; }
+    return newtAndModelOpt((Tree *)t, 0);
+}
+long p4b_newtAndBOBYQAOpt(p4b_tree t)
+{
+    if (!t) { setError("p4_newtAndBOBYQAOpt: NULL handle"); return -1; }
+    return newtAndModelOpt((Tree *)t, 1);
+}
+// The minimisers themselves, on a caller's objective (tests drive them with analytic functions on the CPU).
+double p4b_praxisMinimize(int n, double *x, double tol, double h, double (*fn)(const double *, void *), void *ctx)
+{
+    if (n < 1 || !x || !fn) { setError("p4b_praxisMinimize: bad argument"); return NAN; }
+    Praxis px(n);
+    return px.minimize(tol, h, x, [&](double *p) { return fn(p, ctx); });
+}
+double p4b_boundedMinimize(int n, double *x, const double *lo, const double *hi, double xtol, double ftol, long maxEvals,
+                           double (*fn)(const double *, void *), void *ctx, long *nEvals)
+{
+    if (n < 1 || !x || !lo || !hi || !fn) { setError("p4b_boundedMinimize: bad argument"); return NAN; }
+    long e = 0;
+    const double v = boundedPowell(n, x, lo, hi, [&](double *p) { return fn(p, ctx); }, xtol, ftol, maxEvals, &e);
+    if (nEvals) *nEvals = e;
+    return v;
 }
 int p4b_newtSetup(p4b_tree t)
 {

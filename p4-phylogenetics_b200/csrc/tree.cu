@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <functional>
 #include <cstddef>
@@ -28,6 +29,7 @@
 #include "../../include/p4b200.h"
 #include "engine.h"
 #include "kernels.cuh"
+#include "tree_dna.cuh"
 #include "newt.cuh"
 
 namespace p4b {
@@ -65,6 +67,16 @@ struct Engine {
     std::vector<double> pT;
     // results of a batched evaluation of several trees: [2*kMaxBatchTrees] device + pinned host
     double *dBatch = nullptr, *hBatch = nullptr;
+    unsigned *batchTickets = nullptr;          // [kMaxBatchTrees] last-CTA tickets of a batched launch
+    // step lists of the second-generation whole-tree kernel: one device buffer; uploads go through rotating pinned
+    // slabs; a list identical to the one already on the device (a repeated full-tree evaluation) is not sent again
+    Step2 *stepDev = nullptr;
+    size_t stepDevCap = 0;
+    Step2 *stepSlab[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stepSlabCap[4] = {0, 0, 0, 0};
+    cudaEvent_t stepEv[4] = {nullptr, nullptr, nullptr, nullptr};
+    int stepSlabNext = 0;
+    std::vector<Step2> stepShadow;             // what stepDev holds (once the stream reaches the last upload)
 };
 static Engine G;
 static int flushPJobs();
@@ -125,6 +137,8 @@ static int engineInit()
     G.numSMs = prop.multiProcessorCount;
     CUDA_TRY(cudaMalloc(&G.dBatch, 2 * sizeof(double) * kMaxBatchTrees));
     CUDA_TRY(cudaMallocHost(&G.hBatch, 2 * sizeof(double) * kMaxBatchTrees));
+    CUDA_TRY(cudaMalloc(&G.batchTickets, sizeof(unsigned) * kMaxBatchTrees));
+    CUDA_TRY(cudaMemset(G.batchTickets, 0, sizeof(unsigned) * kMaxBatchTrees));
     G.ready = true;
     return 0;
 }
@@ -289,6 +303,7 @@ struct TreeDevice {
     double *result = nullptr;     // [2*nParts] device
     double *hResult = nullptr;    // pinned
     double *partials = nullptr;   // [2*maxBlocks]
+    unsigned *tickets = nullptr;  // [nParts] last-CTA tickets of the fused root reduction
     int maxLikeBlocks = 0;
     double *patLikes = nullptr;
     int patLikesCap = 0;
@@ -331,10 +346,10 @@ int treeDeviceCreate(Tree *t)
         L.clNodeDoubles = (size_t)L.nCat * L.dim * L.ps;
         L.pOff = d->pNodeDoubles;
         L.pDoubles = (size_t)L.nCat * L.dim * L.dim;
-        d->pNodeDoubles += L.pDoubles;
+        d->pNodeDoubles += (L.pDoubles + 1) & ~(size_t)1;      // every part's deck starts 16-byte aligned (bulk copies)
         L.tblOff = d->tblNodeDoubles;
         L.tblDoubles = (size_t)L.nCat * L.dim * L.W;
-        d->tblNodeDoubles += L.tblDoubles;
+        d->tblNodeDoubles += (L.tblDoubles + 1) & ~(size_t)1;
         if (L.dim == 20 && L.nCat == 4) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
             L.auxOff = d->auxNodeDoubles;
             L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * L.dim * L.W;
@@ -389,6 +404,8 @@ int treeDeviceCreate(Tree *t)
     CUDA_TRY(cudaMallocHost(&d->hResult, 2 * sizeof(double) * t->nParts));
     CUDA_TRY(cudaMalloc(&d->partials, 2 * sizeof(double) * (size_t)d->maxLikeBlocks * 8 * t->nParts));
     CUDA_TRY(cudaMalloc(&d->flag, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->tickets, sizeof(unsigned) * t->nParts));
+    CUDA_TRY(cudaMemsetAsync(d->tickets, 0, sizeof(unsigned) * t->nParts, G.stream));
     CUDA_TRY(cudaEventCreate(&d->evA));
     CUDA_TRY(cudaEventCreate(&d->evB));
     CUDA_TRY(cudaEventCreate(&d->evCLa));
@@ -420,6 +437,7 @@ void treeDeviceDestroy(Tree *t)
     if (d->partials) cudaFree(d->partials);
     if (d->patLikes) cudaFree(d->patLikes);
     if (d->flag) cudaFree(d->flag);
+    if (d->tickets) cudaFree(d->tickets);
     if (d->evA) cudaEventDestroy(d->evA);
     if (d->evB) cudaEventDestroy(d->evB);
     if (d->evCLa) cudaEventDestroy(d->evCLa);
@@ -955,7 +973,7 @@ struct FusedJob {
 static int g_fusedVariant = -1;   // p4b_setFusedVariant: -1 = by shard size
 int setFusedVariant(int v)
 {
-    if (v < -1 || v > 8) { setError("p4b_setFusedVariant: launch shape %d does not exist (-1 .. 8)", v); return 1; }
+    if (v < -1 || (v > 8 && v < 10) || v > 16) { setError("p4b_setFusedVariant: launch shape %d does not exist (-1, 0..8, 10..16)", v); return 1; }
     g_fusedVariant = v;
     return 0;
 }
@@ -967,7 +985,7 @@ static int fusedVariant(int ps, int nTrees)
         forced = e ? atoi(e) : -1;
         if (forced < -1 || forced > 8) forced = -1;
     }
-    if (g_fusedVariant >= 0) return g_fusedVariant;
+    if (g_fusedVariant >= 0 && g_fusedVariant <= 8) return g_fusedVariant;
     if (forced >= 0) return forced;
     const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
     return waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
@@ -1062,12 +1080,359 @@ static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int 
     return ns;
 }
 
+// ---------------------------------------------------------------------------
+// Second-generation whole-tree kernel for 4-state parts (tree_dna.cuh): step planning and launch
+// ---------------------------------------------------------------------------
+static bool g_fused2 = true;           // P4B_FUSED2=0 / p4b_setFusedVariant(0..8) select the first-generation kernel
+static bool g_heavyFirst = true;       // P4B_HEAVY_FIRST=0 keeps the caller's post-order
+static bool g_pushBuf = true;          // P4B_PUSH=0: siblings always travel through global memory (prefetched)
+
+// Any order in which children precede parents computes the same numbers.  The caller's post-order leaves a node's
+// FIRST-visited internal child waiting in memory while the other child's whole subtree is computed; visiting the
+// heavier subtree first makes that wait as short as possible, so the re-read (or the push buffer) finds it close:
+// in L2, or in shared memory.  Only the order of the launch's steps changes, never the order of a node's children.
+static void reorderHeavyFirst(std::vector<Node *> &order)
+{
+    const size_t n = order.size();
+    if (n < 3) return;
+    std::unordered_map<Node *, int> w;
+    w.reserve(n * 2);
+    for (Node *x : order) w[x] = 0;
+    for (Node *x : order) {           // children precede parents in a valid order
+        int sum = 1;
+        for (Node *c = x->leftChild; c; c = c->sibling) {
+            auto it = w.find(c);
+            if (it != w.end()) sum += it->second;
+        }
+        w[x] = sum;
+    }
+    std::vector<Node *> out;
+    out.reserve(n);
+    struct Frame { Node *n; std::vector<Node *> kids; size_t next; };
+    std::vector<Frame> stack;
+    auto open = [&](Node *x) {
+        Frame f{x, {}, 0};
+        for (Node *c = x->leftChild; c; c = c->sibling)
+            if (w.count(c)) f.kids.push_back(c);
+        std::stable_sort(f.kids.begin(), f.kids.end(), [&](Node *a, Node *b) { return w[a] > w[b]; });
+        stack.push_back(std::move(f));
+    };
+    for (Node *r : order) {
+        if (r->parent && w.count(r->parent)) continue;      // not a root of the set
+        open(r);
+        while (!stack.empty()) {
+            Frame &f = stack.back();
+            if (f.next < f.kids.size()) { Node *c = f.kids[f.next++]; open(c); }
+            else { out.push_back(f.n); stack.pop_back(); }
+        }
+    }
+    if (out.size() == n) order.swap(out);
+}
+
+// Steps of one job, appended to `steps`; fills the job's header fields that depend on them.  Returns the number of
+// steps, or -1 on error.
+static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &job, int p)
+{
+    Tree *t = job.t;
+    Part *dp = t->data->parts[p];
+    std::vector<Node *> order = *job.order;
+    if (g_heavyFirst) reorderHeavyFirst(order);
+    const size_t base = steps.size();
+    std::unordered_map<Node *, int> doneAt;          // node -> step (relative) that finishes it in this launch
+    std::vector<std::array<unsigned, 2>> tipRows;    // per step: tip rows of its leaf children
+    std::vector<std::array<Node *, 2>> kidsOf;       // per step: the children themselves
+    std::vector<Node *> nodeOf;
+    Node *prev = nullptr;
+    for (size_t oi = 0; oi < order.size(); oi++) {
+        Node *n = order[oi];
+        if (!n->leftChild) { setError("node %d has no children; cannot set its conditional likelihoods", n->nodeNum); return -1; }
+        std::vector<uint64_t> key;
+        makeClKey(n, p, key);
+        // never skip the node the fused root reduction reads from registers
+        if (job.memo && !(job.withLike && n == order.back()) && clIsCurrent(n, p, key)) { n->clNeedsUpdating = 0; continue; }
+        if (nodeMakeWritable(n, p)) return -1;   // a buffer shared with the twin tree is left to the twin
+        int k = 0;
+        bool firstChunk = true, prevUsed = false;
+        Step2 st;
+        auto begin = [&]() {
+            memset(&st, 0, sizeof(st));
+            st.out = nodeSlotCode(n, p);
+            st.c0 = st.c1 = 0;
+            st.nt0 = st.nt1 = st.pf = kNone;
+            tipRows.push_back({kNone, kNone});
+            kidsOf.push_back({nullptr, nullptr});
+            nodeOf.push_back(n);
+        };
+        auto finish = [&](bool last) {
+            st.flags |= (unsigned)k | (firstChunk ? kStepFirst : 0u) | (last ? kStepStore : 0u);
+            steps.push_back(st);
+        };
+        begin();
+        for (Node *c = n->leftChild; c; c = c->sibling) {
+            unsigned kind;
+            if (c->isLeaf) {
+                if (c->seqNum < 0 || c->seqNum >= dp->nTax) { setError("leaf node %d has seqNum %d", c->nodeNum, c->seqNum); return -1; }
+                kind = 2u;
+                tipRows.back()[k] = (unsigned)c->seqNum;
+            } else {
+                if (c->clSlot[p] < 0) { setError("internal node %d has no conditional likelihoods", c->nodeNum); return -1; }
+                kind = (c == prev && !prevUsed && firstChunk) ? 1u : 0u;
+                if (kind == 1u) prevUsed = true;
+                (k == 0 ? st.c0 : st.c1) = nodeSlotCode(c, p);
+            }
+            (k == 0 ? st.n0 : st.n1) = (unsigned)c->nodeNum;
+            st.flags |= kind << (4 + 2 * k);
+            kidsOf.back()[k] = c;
+            k++;
+            if (k == 2 && c->sibling) {          // node wider than one step: continue in the next
+                finish(false);
+                firstChunk = false;
+                k = 0;
+                begin();
+            }
+        }
+        finish(true);
+        doneAt[n] = (int)(steps.size() - base) - 1;
+        prev = n;
+        n->clStamp[p] = ++G.stamp;
+        n->clKey[p].swap(key);
+        n->clResident[p] = 1;
+        n->clNeedsUpdating = 0;
+    }
+    const int ns = (int)(steps.size() - base);
+    Step2 *S = steps.data() + base;
+    // tip codes travel one step ahead
+    h.t0 = h.t1 = h.pf0 = kNone;
+    if (ns > 0) { h.t0 = tipRows[0][0]; h.t1 = tipRows[0][1]; }
+    for (int j = 1; j < ns; j++) { S[j - 1].nt0 = tipRows[j][0]; S[j - 1].nt1 = tipRows[j][1]; }
+    // The per-thread shared-memory buffer: in consumption order, give each step's first in-memory child the buffer if it
+    // is free -- pushed by the step that produces it when nothing else needs the buffer in between (no global re-read),
+    // else prefetched from global memory up to three steps ahead; a child that gets neither is loaded when it is needed.
+    std::unordered_set<Node *> needsMemory;
+    int lastUse = -1;                    // step whose computation last reads the buffer
+    for (int j = 0; j < ns; j++) {
+        bool taken = false;
+        for (int i = 0; i < (int)(S[j].flags & 3u); i++) {
+            const unsigned kind = (S[j].flags >> (4 + 2 * i)) & 3u;
+            if (kind != 0u) continue;
+            Node *x = kidsOf[j][i];
+            auto it = doneAt.find(x);
+            const int s = it == doneAt.end() ? -1 : it->second;
+            const unsigned code = i == 0 ? S[j].c0 : S[j].c1;
+            bool viaBuffer = false;
+            if (!taken) {
+                if (g_pushBuf && s >= 0 && lastUse <= s) {
+                    S[s].flags |= kStepPush;
+                    viaBuffer = true;
+                } else if (j == 0) {
+                    h.pf0 = code;
+                    needsMemory.insert(x);
+                    viaBuffer = true;
+                } else {
+                    int e = s + 1;
+                    if (e < lastUse) e = lastUse;
+                    if (e < j - 3) e = j - 3;
+                    if (e < 0) e = 0;
+                    if (e <= j - 1 && S[e].pf == kNone) {
+                        S[e].pf = code;
+                        if (e == lastUse) S[e].flags |= kStepPfLate;     // step e reads the buffer itself: refill it afterwards
+                        needsMemory.insert(x);
+                        viaBuffer = true;
+                    }
+                }
+            }
+            if (viaBuffer) {
+                S[j].flags = (S[j].flags & ~(3u << (4 + 2 * i))) | (3u << (4 + 2 * i));
+                taken = true;
+                lastUse = j;
+            } else {
+                needsMemory.insert(x);
+            }
+        }
+    }
+    if (!job.storeAll) {
+        // lnL-only evaluation: a node is written to its buffer only if a later step of this launch reads it from there
+        for (int j = 0; j < ns; j++) S[j].flags &= ~kStepStore;
+        for (auto &kv : doneAt) {
+            if (needsMemory.count(kv.first)) { S[kv.second].flags |= kStepStore; kv.first->clResident[p] = 1; }
+            else kv.first->clResident[p] = 0;
+        }
+    }
+    h.nSteps = ns;
+    return ns;
+}
+
+// Launch shapes of the second-generation kernel: {categories per thread, warps per CTA, CTAs per SM}.
+struct Shape2 { int ct, cw, minb; };
+static const Shape2 kShapes2[] = {
+    {4, 4, 3},    // 10: 128 threads x 3
+    {4, 2, 6},    // 11:  64 threads x 6
+    {4, 1, 12},   // 12:  32 threads x 12
+    {2, 4, 5},    // 13: categories split over 2 warps, 128 threads x 5
+    {2, 2, 10},   // 14:  64 threads x 10
+    {1, 4, 6},    // 15: one category per warp, 128 threads x 6
+    {2, 8, 2},    // 16: 256 threads x 2
+};
+constexpr int kNumShapes2 = (int)(sizeof(kShapes2) / sizeof(kShapes2[0]));
+typedef void (*Kernel2Fn)(const TreeArgs2);
+static Kernel2Fn kernel2For(int nCat, int shape)
+{
+    static const Kernel2Fn k4[kNumShapes2] = {cl_tree_dna2_kernel<4, 4, 4, 3>, cl_tree_dna2_kernel<4, 4, 2, 6>, cl_tree_dna2_kernel<4, 4, 1, 12>,
+                                              cl_tree_dna2_kernel<4, 2, 4, 5>, cl_tree_dna2_kernel<4, 2, 2, 10>, cl_tree_dna2_kernel<4, 1, 4, 6>,
+                                              cl_tree_dna2_kernel<4, 2, 8, 2>};
+    static const Kernel2Fn k1[3] = {cl_tree_dna2_kernel<1, 1, 4, 4>, cl_tree_dna2_kernel<1, 1, 2, 8>, cl_tree_dna2_kernel<1, 1, 1, 16>};
+    if (nCat == 4) return k4[shape];
+    return k1[shape < 3 ? shape : 0];
+}
+
+static int fused2Shape(int ps, int nTrees)
+{
+    if (g_fusedVariant >= 10 && g_fusedVariant < 10 + kNumShapes2) return g_fusedVariant - 10;
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("P4B_FUSED2_SHAPE");
+        forced = e ? atoi(e) : -1;
+        if (forced < -1 || forced >= kNumShapes2) forced = -1;
+    }
+    if (forced >= 0) return forced;
+    const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
+    return waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
+}
+
+// Make `steps` the content of the device step buffer (skipped when it already is).
+static int uploadSteps2(const std::vector<Step2> &steps)
+{
+    const size_t n = steps.size(), bytes = n * sizeof(Step2);
+    if (n == 0) return 0;
+    if (G.stepShadow.size() == n && memcmp(G.stepShadow.data(), steps.data(), bytes) == 0) return 0;
+    if (G.stepDevCap < n) {
+        if (G.stepDev) { CUDA_TRY(cudaStreamSynchronize(G.stream)); cudaFree(G.stepDev); G.stepDev = nullptr; }
+        size_t cap = n < 1024 ? 1024 : n * 2;
+        CUDA_TRY(cudaMalloc(&G.stepDev, cap * sizeof(Step2)));
+        G.stepDevCap = cap;
+    }
+    const int k = G.stepSlabNext;
+    G.stepSlabNext = (k + 1) & 3;
+    if (!G.stepEv[k]) CUDA_TRY(cudaEventCreateWithFlags(&G.stepEv[k], cudaEventDisableTiming));
+    else CUDA_TRY(cudaEventSynchronize(G.stepEv[k]));       // the slab's previous upload has left the host
+    if (G.stepSlabCap[k] < n) {
+        if (G.stepSlab[k]) cudaFreeHost(G.stepSlab[k]);
+        size_t cap = n < 1024 ? 1024 : n * 2;
+        CUDA_TRY(cudaMallocHost(&G.stepSlab[k], cap * sizeof(Step2)));
+        G.stepSlabCap[k] = cap;
+    }
+    memcpy(G.stepSlab[k], steps.data(), bytes);
+    CUDA_TRY(cudaMemcpyAsync(G.stepDev, G.stepSlab[k], bytes, cudaMemcpyHostToDevice, G.stream));
+    CUDA_TRY(cudaEventRecord(G.stepEv[k], G.stream));
+    G.stepShadow = steps;
+    return 0;
+}
+
+static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
+{
+    if (flushPJobs()) return 1;
+    Tree *t0 = jobs[0].t;
+    TreeDevice *d0 = t0->dev;
+    PartLayout &L = d0->parts[p];
+    Part *dp = t0->data->parts[p];
+    static TreeArgs2 a;
+    memset(&a, 0, sizeof(a));
+    a.ps = L.ps;
+    a.nPat = L.nPat;
+    a.tblW = L.W;
+    a.nTrees = nJobs;
+    a.tileLog = 0;
+    a.pNodeDoubles = (long long)d0->pNodeDoubles;
+    a.tblNodeDoubles = (long long)d0->tblNodeDoubles;
+    a.tips = dp->dev.tips;
+    a.counts = dp->dev.counts;
+    a.invarMask = dp->dev.invarMask;
+    a.eqMask = dp->dev.equateMask;
+    const int shape = fused2Shape(L.ps, nJobs);
+    const Shape2 sh = L.nCat == 4 ? kShapes2[shape] : Shape2{1, shape == 0 ? 4 : (shape == 1 ? 2 : 1), shape == 0 ? 4 : (shape == 1 ? 8 : 16)};
+    const int csplit = L.nCat / sh.ct;
+    const int patsPerCta = (sh.cw / csplit) * 64;
+    const int blocks = (L.ps + patsPerCta - 1) / patsPerCta;
+    static std::vector<Step2> steps;
+    steps.clear();
+    int maxSteps = 1;
+    for (int i = 0; i < nJobs; i++) {
+        Tree *t = jobs[i].t;
+        TreeDevice *d = t->dev;
+        PartLayout &Li = d->parts[p];
+        ModelPart *mp = t->model->parts[p];
+        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != L.dim || Li.W != L.W || d->pNodeDoubles != d0->pNodeDoubles ||
+            d->tblNodeDoubles != d0->tblNodeDoubles || Li.scalers != L.scalers) {
+            setError("batched evaluation: the trees do not share the data part and model shape");
+            return 1;
+        }
+        TreeHdr2 &h = a.hdr[i];
+        h.arena = arenaBase(Li);
+        h.Pdeck = d->P + Li.pOff;
+        h.tbl = d->tbl + Li.tblOff;
+        h.result = resultDev + 2 * i;
+        h.ticket = nJobs == 1 ? d->tickets + p : G.batchTickets + i;
+        h.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
+        if (blocks > d->maxLikeBlocks * 8) { setError("internal: partial buffer too small"); return 1; }
+        if (jobs[i].withLike) {
+            Node *root = t->root;
+            if (!root || jobs[i].order->empty() || jobs[i].order->back() != root) { setError("fused evaluation: the last node must be the root"); return 1; }
+            const int rc = root->compNums[p];
+            if (rc < 0 || rc >= mp->nComps || !mp->comps[rc].val) { setError("root uses comp %d which does not exist", rc); return 1; }
+            h.rootTips = root->isLeaf ? dp->dev.tips + (size_t)root->seqNum * L.ps : nullptr;
+            h.pInvar = mp->pInvar;
+            if (h.pInvar != 0.0 && !a.invarMask) { setError("pInvar is set but pf.setGlobalInvarSitesVec was not called on part %d", p); return 1; }
+            for (int s = 0; s < 4; s++) h.pi[s] = mp->comps[rc].val[s];
+            if (jobs[i].wantPatLikes) {
+                if (d->patLikesCap < L.ps) {
+                    if (d->patLikes) cudaFree(d->patLikes);
+                    CUDA_TRY(cudaMalloc(&d->patLikes, sizeof(double) * L.ps));
+                    d->patLikesCap = L.ps;
+                }
+                h.patLikes = d->patLikes;
+            }
+            h.doLike = 1;
+        }
+        h.stepBase = (int)steps.size();
+        const int ns = buildSteps2(steps, h, jobs[i], p);
+        if (ns < 0) return 1;
+        if (ns > maxSteps) maxSteps = ns;
+    }
+    bool anything = false;
+    for (int i = 0; i < nJobs; i++)
+        if (a.hdr[i].nSteps > 0 || a.hdr[i].doLike) anything = true;
+    if (!anything) return 0;
+    a.maxSteps = maxSteps;
+    const size_t smem = treeDna2SmemBytes(L.nCat, L.W, sh.ct, sh.cw, maxSteps);
+    if (smem > 200 * 1024) { setError("internal: step list of %d steps does not fit the whole-tree kernel's shared memory", maxSteps); return 1; }
+    if (uploadSteps2(steps)) return 1;
+    a.steps = G.stepDev;
+    Kernel2Fn fn = kernel2For(L.nCat, shape);
+    static std::unordered_set<void *> attrSet;
+    if (!attrSet.count((void *)fn)) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attrSet.insert((void *)fn);
+    }
+    fn<<<dim3(blocks, nJobs), sh.cw * 32, smem, G.stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    G.launches++;
+    for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
+    return 0;
+}
+
 // Whole-tree kernel over one or several trees that share data part p (same shard, same model shape).
 // With withLike jobs the per-tree results land in resultDev[2*i] (sum of count*log like) and
 // resultDev[2*i+1] (count of non-positive likelihoods) for job i.
 static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
 {
     if (nJobs < 1 || nJobs > kMaxBatchTrees) { setError("internal: bad batch size %d", nJobs); return 1; }
+    {
+        const PartLayout &L0 = jobs[0].t->dev->parts[p];
+        static int env2 = -1;
+        if (env2 < 0) { const char *e = getenv("P4B_FUSED2"); env2 = e ? atoi(e) != 0 : 1; }
+        const bool oldForced = g_fusedVariant >= 0 && g_fusedVariant < 10;
+        if (L0.dim == 4 && !L0.scalers && g_fused2 && env2 && !oldForced) return launchFused2Batch(jobs, nJobs, p, resultDev);
+    }
     if (flushPJobs()) return 1;
     Tree *t0 = jobs[0].t;
     TreeDevice *d0 = t0->dev;

@@ -1,0 +1,360 @@
+// tree_dna.cuh -- whole-tree CL recursion for 4-state parts, second generation (sm_100a, FP64).
+//
+// Computes what Pf/p4_node.c:636-857 (p4_setConditionalLikelihoodsOfInternalNodePart) computes for every node
+// of a step list, and -- when the list ends at the root -- what Pf/p4_tree.c:1029-1378 (p4_partLogLikeLoop /
+// ...RootLeaf) computes from the root's CL, in ONE launch.
+//
+// A thread owns two adjacent patterns (16-byte accesses) and CT of the part's rate categories; it walks the
+// step list by itself, the CL of the node it has just computed staying in registers.  What the first
+// generation (cl_tree_dna_kernel, kernels.cuh) paid per step and per warp -- decoding the step from
+// runtime-indexed constant memory, staging the children's P decks / leaf tables with per-thread cp.async, a
+// CTA-wide barrier -- is taken off the path:
+//   * the tree's whole step list, pre-decoded by the host (48 bytes per step), is copied into shared memory
+//     once, in the prologue: a step's descriptor is two 16-byte shared-memory loads;
+//   * the operands of a step's (at most two) children -- P decks, leaf tables -- arrive in a ring of kRing
+//     slots by bulk copies (TMA, cp.async.bulk) that complete on the slot's mbarrier.  Nobody is a dedicated
+//     producer: the LAST warp to finish step s (a shared-memory counter per slot) issues the copies of step
+//     s + kRing into the slot it has just freed.  Warps wait on the slot's mbarrier only (try_wait, normally
+//     already satisfied) and drift up to kRing - 1 steps apart: no CTA barrier inside the step loop.
+// The one internal child of a step that is not in registers comes from a per-thread shared-memory buffer that
+// the host's step planner fills in one of two ways: the producing step PUSHES its result there (no global
+// re-read at all; short-lived siblings), or the thread PREFETCHES it from its own earlier global store with
+// cp.async one or more steps ahead.  Tip codes of a step's leaf children are fetched during the previous step.
+// Rate categories can be split over CSPLIT = NCAT / CT warps (more warps per SM at fewer registers each).
+// After the last step the root CL (in registers) is folded into site likelihoods and the CTA's partial lnL;
+// the LAST CTA to finish (atomic ticket) folds the partials in a fixed order: no second launch.
+#pragma once
+#include "kernels.cuh"
+
+namespace p4b {
+
+constexpr unsigned kNone = 0xffffffffu;
+constexpr int kRing = 6;          // steps the producer may run ahead
+
+// flags of a step
+constexpr unsigned kStepFirst = 4u, kStepStore = 8u, kStepPush = 256u, kStepPfLate = 512u;
+
+struct Step2 {            // 48 bytes in global memory; the first 32 travel into the ring slot
+    unsigned out;         // the node's CL buffer: (address - hdr.arena) / 256 bytes
+    unsigned flags;       // bits 0-1 children (1..2) | kStepFirst | kStepStore | kind of child 0 << 4 | kind of child 1 << 6 | kStepPush | kStepPfLate
+                          //   kind 0 internal child, loaded from its buffer now; 1 internal child in registers (previous step);
+                          //   2 leaf child; 3 internal child in the thread's shared-memory buffer (pushed or prefetched)
+    unsigned c0, c1;      // kind 0: the child's CL buffer (256-byte units)
+    unsigned nt0, nt1;    // tip rows to fetch during this step for the NEXT step's children 0 / 1 (kNone: none)
+    unsigned pf;          // CL buffer to prefetch into the shared-memory buffer during this step (kNone: none)
+    unsigned pad;
+    unsigned n0, n1;      // node numbers of the children: they address the P deck / leaf table
+    unsigned pad2[2];
+};
+static_assert(sizeof(Step2) == 48, "Step2 layout");
+
+struct TreeHdr2 {
+    double *arena;            // base address the tree's CL buffers are addressed from
+    const double *Pdeck;      // tree's P decks, already offset to this part
+    const double *tbl;        // tree's leaf tables, already offset to this part
+    double *patLikes;         // optional [ps]
+    double *partials;         // [2*gridDim.x]
+    double *result;           // [2]: sum of count*log(like), count of like <= 0 -- written by the last CTA
+    unsigned *ticket;
+    const uint8_t *rootTips;  // non-NULL when the root is a leaf
+    double pInvar;
+    double pi[4];
+    int stepBase, nSteps;
+    unsigned t0, t1, pf0;     // prologue: tip rows of step 0's children, buffer to prefetch for step 0
+    int doLike;
+};
+
+struct TreeArgs2 {
+    int ps, nPat, tblW, nTrees;
+    int tileLog, maxSteps;    // maxSteps: most steps any tree of the launch has (sizes the shared-memory step list)
+                              // CL layout: 0 = rows [k][ps]; else tiles of 2^tileLog patterns, [tile][k][2^tileLog]
+    long long pNodeDoubles;   // stride between nodes in a P deck
+    long long tblNodeDoubles;
+    const uint8_t *tips;      // part's tip rows [nTax][ps]
+    const int *counts;
+    const uint64_t *invarMask;
+    const uint64_t *eqMask;
+    const Step2 *steps;
+    TreeHdr2 hdr[kMaxBatchTrees];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+
+// Shared memory of one CTA: the step list [nSteps] x 48 B, ring slots [operands of child 0 | operands of child 1],
+// the mbarriers full[kRing], the slot counters, the per-thread buffers [KT][CW*32] double2, the root reduction's scratch.
+__host__ __device__ inline size_t treeDna2OpsDoubles(int K, int W) { return (size_t)K * (W > 4 ? W : 4); }
+__host__ inline size_t treeDna2SmemBytes(int nCat, int W, int CT, int CW, int maxSteps)
+{
+    const int K = nCat * 4;
+    return (size_t)maxSteps * sizeof(Step2) + kRing * 2 * treeDna2OpsDoubles(K, W) * 8 + kRing * 8 + kRing * 4 + 8 /* align */ +
+           (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 + (2 * CW + 2) * 8;
+}
+
+template <int NCAT, int CT, int CW, int MINB>
+__global__ void __launch_bounds__(CW * 32, MINB)
+cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
+{
+    constexpr int K = NCAT * 4;            // rows of a CL buffer
+    constexpr int KT = CT * 4;             // rows this thread owns
+    constexpr int CSPLIT = NCAT / CT;      // warps sharing a block of 64 patterns
+    constexpr int CTH = CW * 32;           // threads
+    constexpr int PB = CW / CSPLIT;        // pattern blocks (64 patterns each) per CTA
+    static_assert(NCAT % CT == 0 && CW % CSPLIT == 0, "shape");
+    const TreeHdr2 &hd = a.hdr[blockIdx.y];
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int W = a.tblW;
+    const int nSteps = hd.nSteps;
+    const size_t opsD = treeDna2OpsDoubles(K, W);
+    const size_t slotB = 2 * opsD * 8;
+    const uint4 *sSteps = reinterpret_cast<const uint4 *>(smraw);                  // [nSteps][3]
+    unsigned char *ring = smraw + (size_t)a.maxSteps * sizeof(Step2);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kRing * slotB);
+    unsigned *cnt = reinterpret_cast<unsigned *>(full + kRing);
+    double2 *bufAll = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(cnt + kRing) + 15) & ~(uintptr_t)15);
+    double2 *sA = bufAll + (size_t)KT * CTH;           // hand-over of the category sum between the warps of a pattern block
+    double *sRed = reinterpret_cast<double *>(sA + CTH);   // [2][CW] + flag
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // one lane: the bulk copies of step j's operands into its ring slot, completing on the slot's mbarrier
+    auto produce = [&](int j) {
+        const int slot = j % kRing;
+        const uint4 dA = sSteps[3 * j], dC = sSteps[3 * j + 2];
+        const unsigned pBytes = K * 4 * 8, tBytes = (unsigned)(K * W * 8);
+        const unsigned nc = dA.y & 3u, k0 = (dA.y >> 4) & 3u, k1 = (dA.y >> 6) & 3u;
+        const unsigned b0 = k0 == 2u ? tBytes : pBytes, b1 = nc == 2u ? (k1 == 2u ? tBytes : pBytes) : 0u;
+        unsigned char *sl = ring + slot * slotB;
+        mbar_expect_tx(full + slot, b0 + b1);
+        bulk_g2s(sl, k0 == 2u ? hd.tbl + a.tblNodeDoubles * dC.x : hd.Pdeck + a.pNodeDoubles * dC.x, b0, full + slot);
+        if (nc == 2u)
+            bulk_g2s(sl + opsD * 8, k1 == 2u ? hd.tbl + a.tblNodeDoubles * dC.y : hd.Pdeck + a.pNodeDoubles * dC.y, b1, full + slot);
+    };
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + hd.stepBase);
+        uint4 *dst = reinterpret_cast<uint4 *>(smraw);
+        for (int i = threadIdx.x; i < 3 * nSteps; i += CTH) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < kRing; i++) { mbar_init(full + i, 1); cnt[i] = 0u; }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int j = 0; j < kRing && j < nSteps; j++) produce(j);
+
+    const int cg = warp % CSPLIT, pb = warp / CSPLIT;       // category group, pattern block of this warp
+    const int pat = ((blockIdx.x * PB + pb) * 32 + lane) * 2;
+    const bool active = pat < a.ps;
+    const unsigned ps = (unsigned)a.ps;
+    // this thread's two patterns inside a CL buffer: element offset of row 0, and the row stride
+    size_t off;
+    unsigned rs;
+    if (a.tileLog == 0) { off = (size_t)pat; rs = ps; }
+    else {
+        const unsigned T = 1u << a.tileLog;
+        off = (size_t)(pat >> a.tileLog) * ((size_t)K << a.tileLog) + (pat & (T - 1u));
+        rs = T;
+    }
+    off += (size_t)(cg * KT) * rs;                           // first row of this thread's categories
+    double2 *buf = bufAll + threadIdx.x;                     // [KT][CTH]: row stride CTH double2
+    const int opOff = cg * CT;                               // first category of this thread inside a P deck / leaf table
+
+    double2 cur[KT];
+#pragma unroll
+    for (int k = 0; k < KT; k++) cur[k] = make_double2(1.0, 1.0);
+
+    auto prefetch = [&](unsigned code) {
+        const double *cl = hd.arena + (size_t)code * 32 + off;
+#pragma unroll
+        for (int k = 0; k < KT; k++) cp_async16(buf + k * CTH, cl + (size_t)k * rs);
+        cp_async_commit();
+    };
+    auto tipLoad = [&](unsigned row) -> unsigned {
+        return *reinterpret_cast<const unsigned short *>(a.tips + (size_t)row * ps + pat);
+    };
+
+    unsigned next0 = 0u, next1 = 0u;
+    if (active) {
+        if (hd.t0 != kNone) next0 = tipLoad(hd.t0);
+        if (hd.t1 != kNone) next1 = tipLoad(hd.t1);
+        if (hd.pf0 != kNone) prefetch(hd.pf0);
+    }
+
+    for (int si = 0; si < nSteps; si++) {
+        const int slot = si % kRing;
+        mbar_wait(full + slot, (unsigned)(si / kRing) & 1u);
+        const unsigned char *sl = ring + slot * slotB;
+        const uint4 dA = sSteps[3 * si], dB = sSteps[3 * si + 1];
+        const unsigned flags = dA.y;
+        const unsigned nc = flags & 3u, k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
+        const unsigned code0 = next0, code1 = next1;
+        if (active) {
+            next0 = dB.x != kNone ? tipLoad(dB.x) : 0u;      // in flight while this step computes
+            next1 = dB.y != kNone ? tipLoad(dB.y) : 0u;
+            if (k0 == 3u || k1 == 3u) cp_async_wait_all();   // a prefetched child has landed (a pushed one is already there)
+            if (dB.z != kNone && !(flags & kStepPfLate)) prefetch(dB.z);
+            const double *s0 = reinterpret_cast<const double *>(sl);
+            const double *s1 = s0 + opsD;
+            double *outp = hd.arena + (size_t)dA.x * 32 + off;
+            const double *m0 = hd.arena + (size_t)dA.z * 32 + off, *m1 = hd.arena + (size_t)dA.w * 32 + off;
+            const bool first = (flags & kStepFirst) != 0u, store = (flags & kStepStore) != 0u, push = (flags & kStepPush) != 0u;
+            const unsigned c0x = code0 & 0xffu, c0y = (code0 >> 8) & 0xffu, c1x = code1 & 0xffu, c1y = (code1 >> 8) & 0xffu;
+#pragma unroll
+            for (int c = 0; c < CT; c++) {
+                const int cat = opOff + c;
+                // factor of one child for the 4 states of this category (same association as kernels.cuh child_factor)
+                auto child = [&](unsigned kind, const double *__restrict__ s, unsigned cx, unsigned cy, const double *__restrict__ mem, double2 f[4]) {
+                    if (kind == 2u) {
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const int k = cat * 4 + s4;
+                            f[s4].x = s[k * W + cx];
+                            f[s4].y = s[k * W + cy];
+                        }
+                    } else {
+                        double2 v0 = cur[c * 4 + 0], v1 = cur[c * 4 + 1], v2 = cur[c * 4 + 2], v3 = cur[c * 4 + 3];
+                        if (kind == 3u) {
+                            v0 = buf[(c * 4 + 0) * CTH]; v1 = buf[(c * 4 + 1) * CTH]; v2 = buf[(c * 4 + 2) * CTH]; v3 = buf[(c * 4 + 3) * CTH];
+                        } else if (kind == 0u) {
+                            v0 = ld2(mem + (size_t)(c * 4 + 0) * rs); v1 = ld2(mem + (size_t)(c * 4 + 1) * rs);
+                            v2 = ld2(mem + (size_t)(c * 4 + 2) * rs); v3 = ld2(mem + (size_t)(c * 4 + 3) * rs);
+                        }
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const double2 p01 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4);
+                            const double2 p23 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4 + 2);
+                            double2 sum;
+                            sum.x = p01.x * v0.x;
+                            sum.y = p01.x * v0.y;
+                            sum.x = fma(p01.y, v1.x, sum.x);
+                            sum.y = fma(p01.y, v1.y, sum.y);
+                            sum.x = fma(p23.x, v2.x, sum.x);
+                            sum.y = fma(p23.x, v2.y, sum.y);
+                            sum.x = fma(p23.y, v3.x, sum.x);
+                            sum.y = fma(p23.y, v3.y, sum.y);
+                            f[s4] = sum;
+                        }
+                    }
+                };
+                double2 f[4];
+                child(k0, s0, c0x, c0y, m0, f);
+                if (!first) {      // continuation of a node with more than two children: the running product is in cur
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) { f[s4].x = cur[c * 4 + s4].x * f[s4].x; f[s4].y = cur[c * 4 + s4].y * f[s4].y; }
+                }
+                if (nc == 2u) {
+                    double2 g[4];
+                    child(k1, s1, c1x, c1y, m1, g);
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) { f[s4].x *= g[s4].x; f[s4].y *= g[s4].y; }   // (left child) * (sibling), the reference's order
+                }
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) {
+                    cur[c * 4 + s4] = f[s4];
+                    if (store) st2(outp + (size_t)(c * 4 + s4) * rs, f[s4]);
+                    if (push) buf[(c * 4 + s4) * CTH] = f[s4];
+                }
+            }
+            if (dB.z != kNone && (flags & kStepPfLate)) prefetch(dB.z);   // the buffer was in use by this step: refill it now
+        }
+        // release the slot; the last warp to do so refills it with the operands of step si + kRing
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(cnt + slot, 1u) == (unsigned)(CW - 1)) {
+                cnt[slot] = 0u;
+                if (si + kRing < nSteps) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warps' reads of the slot precede the bulk copy's writes
+                    produce(si + kRing);
+                }
+            }
+        }
+    }
+
+    if (!hd.doLike) return;
+    // ---- root reduction from registers (Pf/p4_tree.c:1029-1378) -------------------------------------------------
+    // The sum over categories runs in category order as ONE fma chain, handed from warp to warp of the pattern
+    // block when the categories are split: the result does not depend on CSPLIT.
+    double2 A = make_double2(0.0, 0.0);
+    uint64_t mask0 = ~0ull, mask1 = ~0ull;
+    if (active && hd.rootTips) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (pat + h < a.nPat) {
+                const int w = hd.rootTips[pat + h];
+                uint64_t m = ~0ull;
+                if (w < 4) m = 1ull << w;
+                else if (w > 4) m = a.eqMask[w - 5];
+                if (h) mask1 = m; else mask0 = m;
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < CSPLIT; g++) {
+        if (cg == g) {
+            if (g > 0) A = sA[pb * 32 * CSPLIT + lane];
+#pragma unroll
+            for (int k = 0; k < KT; k++) {
+                if ((mask0 >> (k & 3)) & 1ull) A.x = fma(hd.pi[k & 3], cur[k].x, A.x);
+                if ((mask1 >> (k & 3)) & 1ull) A.y = fma(hd.pi[k & 3], cur[k].y, A.y);
+            }
+            if (g < CSPLIT - 1) sA[pb * 32 * CSPLIT + lane] = A;
+        }
+        if (g < CSPLIT - 1) named_barrier(1, CTH);
+    }
+    double term = 0.0, bad = 0.0;
+    if (cg == CSPLIT - 1 && active) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p1 = pat + h;
+            if (p1 < a.nPat) {
+                const uint64_t im = (hd.pInvar != 0.0 && a.invarMask) ? a.invarMask[p1] : 0ull;
+                double t1 = 0.0, like = 0.0;
+                if (like_term(h ? A.y : A.x, 0, hd.pInvar, NCAT, im, hd.pi, 4, a.counts[p1], &t1, &like)) term += t1;
+                else bad += 1.0;
+                if (hd.patLikes) hd.patLikes[p1] = like;
+            }
+        }
+    }
+    term = warpSum(term);
+    bad = warpSum(bad);
+    if (lane == 0) { sRed[warp] = term; sRed[CW + warp] = bad; }
+    named_barrier(1, CTH);
+    int *sLast = reinterpret_cast<int *>(sRed + 2 * CW);
+    if (threadIdx.x == 0) {
+        double t = 0.0, b = 0.0;
+        for (int i = 0; i < CW; i++) { t += sRed[i]; b += sRed[CW + i]; }
+        hd.partials[2 * blockIdx.x] = t;
+        hd.partials[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        const unsigned tk = atomicInc(hd.ticket, gridDim.x - 1);   // wraps to 0 with the last CTA: ready for the next launch
+        *sLast = (tk == gridDim.x - 1) ? 1 : 0;
+    }
+    named_barrier(1, CTH);
+    if (*sLast) {
+        // the last CTA folds every CTA's partial in a fixed order (deterministic for a given launch shape)
+        __threadfence();
+        double t = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += CTH) {
+            t += __ldcg(hd.partials + 2 * i);
+            b += __ldcg(hd.partials + 2 * i + 1);
+        }
+        t = warpSum(t);
+        b = warpSum(b);
+        named_barrier(1, CTH);          // sRed is read above by thread 0 only, before the previous barrier
+        if (lane == 0) { sRed[warp] = t; sRed[CW + warp] = b; }
+        named_barrier(1, CTH);
+        if (threadIdx.x == 0) {
+            double tt = 0.0, bb = 0.0;
+            for (int i = 0; i < CW; i++) { tt += sRed[i]; bb += sRed[CW + i]; }
+            hd.result[0] = tt;
+            hd.result[1] = bb;
+        }
+    }
+}
+
+}  // namespace p4b

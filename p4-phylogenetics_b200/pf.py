@@ -76,6 +76,13 @@ _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setFusedVariant", _i, _i)
+_OBJ = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
+_sig("p4b_allBrentPowellOptimize", C.c_long, _vp)
+_sig("p4b_allBOBYQAOptimize", C.c_long, _vp, _i)
+_sig("p4b_newtAndBrentPowellOpt", C.c_long, _vp)
+_sig("p4b_newtAndBOBYQAOpt", C.c_long, _vp)
+_sig("p4b_praxisMinimize", C.c_double, _i, _vp, C.c_double, C.c_double, _OBJ, _vp)
+_sig("p4b_boundedMinimize", C.c_double, _i, _vp, _vp, _vp, C.c_double, C.c_double, C.c_long, _OBJ, _vp, _vp)
 _sig("p4b_setTensorCoreKernel", None, _i)
 _sig("p4b_setFusedTreeKernel20", None, _i)
 _sig("p4b_setDeferredNodeCalls", None, _i)
@@ -656,39 +663,34 @@ def p4_getFreePrams(cTree):
     return [float(v) for v in windUpParameters(cTree, 0)[0]]
 
 
-def p4_allBOBYQAOptimize(cTree, doBrLens=1, verbose=0, maxEvals=None, ftol=1e-8):
-    """pf.p4_allBOBYQAOptimize(cTree, doBrLens): maximise lnL over the free model parameters and,
-    with doBrLens, all branch lengths (Pf/p4_treeOpt.c:617-753).
+def _optResult(n):
+    if n < 0:
+        _fatal()
+    return int(n)
 
-    The reference hands its objective to nlopt's BOBYQA.  nlopt is a third-party dependency that this
-    engine does not link; the same objective -- evaluated on the GPU in lnL-only mode -- is driven here
-    by SciPy's bounded Powell method, also derivative-free.  The contract is the optimum, not the
-    trajectory.  Returns the number of likelihood evaluations."""
-    from scipy.optimize import minimize
-    x0, lo, hi = windUpParameters(cTree, doBrLens)
-    if len(x0) == 0:
-        return 0
-    _ok(_lib.p4b_setTreeStoresCL(cTree, 0))
-    nEvals = [0]
 
-    def neg(x):
-        nEvals[0] += 1
-        v = logLikeForParameters(cTree, doBrLens, x)
-        return 1.0e99 if v <= -1.0e98 else -v
+def p4_allBOBYQAOptimize(cTree, doBrLens=1, verbose=0):
+    """pf.p4_allBOBYQAOptimize(cTree, doBrLens) (Pf/pfmodule.c:2212 -> Pf/p4_treeOpt.c:617-753): maximise lnL over the
+    free model parameters and, with doBrLens, all branch lengths, inside the reference's box of bounds.
 
-    try:
-        x0 = np.clip(x0, lo, hi)
-        res = minimize(neg, x0, method="Powell", bounds=list(zip(lo, hi)),
-                       options={"xtol": 1e-6, "ftol": ftol, "maxfev": maxEvals or 200 * len(x0) + 2000})
-        logLikeForParameters(cTree, doBrLens, res.x)
-    finally:
-        _ok(_lib.p4b_setTreeStoresCL(cTree, 1))
+    Native (csrc/opt.cpp p4b_allBOBYQAOptimize): the reference's two-pass schedule on the reference's objective
+    (p4_unWindParameters -> p4_setPrams -> p4_treeLogLike, evaluated on the GPU).  Where the reference calls nlopt's
+    BOBYQA -- a third-party library this engine does not link -- a bounded Powell method runs (csrc/praxis.cpp): the
+    contract kept is the box and the optimum, not BOBYQA's trajectory.  Returns the number of likelihood evaluations."""
+    n = _optResult(_lib.p4b_allBOBYQAOptimize(cTree, int(doBrLens)))
     if verbose:
-        print("p4_allBOBYQAOptimize (Powell on the B200 objective): %d evaluations, lnL %.6f" % (nEvals[0], -res.fun))
-    return nEvals[0]
+        print("p4_allBOBYQAOptimize: %d likelihood evaluations, lnL %.6f" % (n, p4_treeLogLike(cTree, 0)))
+    return n
 
 
-p4_allBrentPowellOptimize = p4_allBOBYQAOptimize
+def p4_allBrentPowellOptimize(cTree, verbose=0):
+    """pf.p4_allBrentPowellOptimize(cTree) (Pf/pfmodule.c:2244 -> Pf/p4_treeOpt.c:996-1180): Brent's praxis over model
+    parameters and branch lengths, the reference's schedule (tol 1e-4, h 0.1 until a call gains < 1e-6, then h 0.05).
+    Native: csrc/praxis.cpp restates Brent's published algorithm with the reference's settings."""
+    n = _optResult(_lib.p4b_allBrentPowellOptimize(cTree))
+    if verbose:
+        print("p4_allBrentPowellOptimize: %d likelihood evaluations, lnL %.6f" % (n, p4_treeLogLike(cTree, 0)))
+    return n
 
 
 def optimizeBrLens(cTree, maxPasses=1, tol=1e-6):
@@ -738,42 +740,45 @@ def newtIterations(cTree):
     return int(_lib.p4b_newtIterations(cTree))
 
 
-def _newtSchedule(cTree, steps):
-    for eps, delta in steps:
-        lnL = newtAround(cTree, eps, delta)
-    return lnL
-
-
 def p4_newtAndBrentPowellOpt(cTree, verbose=0):
-    """pf.p4_newtAndBrentPowellOpt(cTree) (Pf/p4_treeOpt.c:1182-1330): branch lengths by Newton-Raphson
-    (p4_newtAround on the device, the reference's schedule of tolerances), free model parameters by a
-    derivative-free method on the reference's parameter vector (the reference: Brent-Powell praxis; here
-    SciPy's bounded Powell on the GPU objective), alternating until a round gains less than 1e-6 or
-    var.newtAndBrentPowellOptPassLimit rounds have run.  With no free parameter it is exactly the reference's
-    four p4_newtAround calls (:1214-1226).  Returns the number of objective evaluations of the model step."""
-    p4_newtSetup(cTree)
-    nPrams = len(windUpParameters(cTree, 0)[0])
-    if nPrams == 0:
-        _newtSchedule(cTree, ((1.0, 10.0), (1.0e-1, 1.0), (1.0e-2, 0.1), (1.0e-5, 1.0e-7)))
-        return 0
-    limit = max(1, _lib.p4b_treePassLimit(cTree))
-    _newtSchedule(cTree, ((1.0, 10.0), (1.0e-1, 1.0), (1.0e-5, 1.0e-7)))      # :1242-1244
-    previous = p4_treeLogLike(cTree, 0)
-    nEvals = 0
-    for rnd in range(limit + 1):
-        newtAround(cTree, 1.0e-5, 1.0e-7)                                      # :1266
-        nEvals += p4_allBOBYQAOptimize(cTree, 0, ftol=1e-9)
-        lnL = p4_treeLogLike(cTree, 0)
-        if verbose:
-            print("p4_newtAndBrentPowellOpt round %d: lnL %.6f (%d evaluations so far)" % (rnd, lnL, nEvals))
-        diff = lnL - previous
-        previous = lnL
-        if abs(diff) < 1.0e-6:
-            break
-    return nEvals
+    """pf.p4_newtAndBrentPowellOpt(cTree) (Pf/pfmodule.c:2259 -> Pf/p4_treeOpt.c:1182-1330): branch lengths by
+    Newton-Raphson (p4_newtAround on the device, the reference's schedule of tolerances), free model parameters by
+    Brent's praxis on the reference's parameter vector, alternating until a round gains less than 1e-6 or
+    var.newtAndBrentPowellOptPassLimit rounds have run.  With no free parameter it is exactly the reference's four
+    p4_newtAround calls (:1214-1226); with one, Newton + a one-dimensional Brent search (:1395-1436).  Native
+    (csrc/opt.cpp).  Returns the number of objective evaluations of the model step."""
+    n = _optResult(_lib.p4b_newtAndBrentPowellOpt(cTree))
+    if verbose:
+        print("p4_newtAndBrentPowellOpt: %d likelihood evaluations, lnL %.6f" % (n, p4_treeLogLike(cTree, 0)))
+    return n
 
 
-p4_newtAndBOBYQAOpt = p4_newtAndBrentPowellOpt
+def p4_newtAndBOBYQAOpt(cTree, verbose=0):
+    """pf.p4_newtAndBOBYQAOpt(cTree) (Pf/pfmodule.c:2227 -> Pf/p4_treeOpt.c:755-945): as above with the bounded method
+    for the model step (pass limit 50).  Native (csrc/opt.cpp)."""
+    n = _optResult(_lib.p4b_newtAndBOBYQAOpt(cTree))
+    if verbose:
+        print("p4_newtAndBOBYQAOpt: %d likelihood evaluations, lnL %.6f" % (n, p4_treeLogLike(cTree, 0)))
+    return n
+
+
+def praxisMinimize(fn, x0, tol=1.0e-4, h=1.0):
+    """Brent's principal-axis minimiser (csrc/praxis.cpp) on a Python objective: (minimum, x).  For tests."""
+    x = np.array(x0, dtype=np.float64)
+    cb = _OBJ(lambda p, ctx: float(fn(np.ctypeslib.as_array(p, shape=(len(x),)))))
+    v = _lib.p4b_praxisMinimize(len(x), x.ctypes.data, float(tol), float(h), cb, None)
+    return v, x
+
+
+def boundedMinimize(fn, x0, lo, hi, xtol=1.0e-7, ftol=1.0e-12, maxEvals=100000):
+    """Powell's method inside the box (csrc/praxis.cpp) on a Python objective: (minimum, x, evaluations).  For tests."""
+    x = np.array(x0, dtype=np.float64)
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    cb = _OBJ(lambda p, ctx: float(fn(np.ctypeslib.as_array(p, shape=(len(x),)))))
+    n = C.c_long(0)
+    v = _lib.p4b_boundedMinimize(len(x), x.ctypes.data, lo.ctypes.data, hi.ctypes.data, float(xtol), float(ftol), int(maxEvals), cb, None, C.byref(n))
+    return v, x, n.value
 
 
 # ---- consumers of the P decks beside the likelihood -----------------------------------------
