@@ -320,6 +320,18 @@ void p4b_rngSet(void *rng, unsigned long seed);
 unsigned long p4b_rngGet(void *rng);
 double p4b_rngUniform(void *rng);
 void p4b_rngFillUniform(void *rng, double *out, long n);   /* the next n uniforms of the stream, in order */
+/* The random draws and special functions Chain's proposals take from GSL through pf between likelihood evaluations
+ * (p4/chain.py:2274-2565).  GSL is a third-party dependency of the reference; these are the algorithms GSL documents
+ * (gamma: Marsaglia & Tsang 2000; Dirichlet: normalised gammas) on the mt19937 stream above, densities through libm. */
+long p4b_rngSize(void *rng);                                                     /* pf.gsl_rng_size, Pf/pfmodule.c:724 */
+void p4b_rngGetState(void *rng, void *buf);                                      /* pf.gsl_rng_getstate :752 (Mcmc checkpoints) */
+void p4b_rngSetState(void *rng, const void *buf);                                /* pf.gsl_rng_setstate :779 */
+double p4b_ranGamma(void *rng, double a, double b);                              /* pf.gsl_ran_gamma :827 */
+void p4b_ranDirichlet(void *rng, int k, const double *alpha, double *theta);     /* pf.gsl_ran_dirichlet :940 */
+double p4b_ranDirichletLnPdf(int k, const double *alpha, const double *theta);   /* pf.gsl_ran_dirichlet_lnpdf :989 */
+double p4b_sfLnGamma(double x);                                                  /* pf.gsl_sf_lngamma :887 */
+double p4b_ranGammaPdf(double x, double a, double b);                            /* pf.gsl_ran_gamma_pdf :848 */
+void p4b_meanVariance(const double *seq, int n, double *mean, double *variance); /* pf.gsl_meanVariance :1025 */
 /* pf.p4_simulate(tree, refTree|0, gsl_rng) :2333 -> p4_simulate Pf/p4_treeSim.c:14-420:
  * new sequences for every leaf, drawn down the tree from the root's composition through every branch's P decks
  * (rate category and invariant-or-not per site, pInvar), consuming the stream in the reference's order -- the

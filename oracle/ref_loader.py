@@ -2,8 +2,9 @@
 
 Loads the reference's own Pf engine (``oracle/_ref/pf*.so``, built by
 ``oracle/Makefile`` from the unmodified sources under /root/reference/Pf) as a
-Python module, and -- only in the build container, where /root/reference
-exists -- the reference's pure-Python ``p4`` package on top of it.
+Python module, and the reference's pure-Python ``p4`` package on top of it
+(from /root/reference in the build container, from the copy staged under
+oracle/_ref/p4 on the GPU box).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the cpu_baseline / ``--impl
 reference`` legs of ``bench.py`` may import this file.  The product package
@@ -45,8 +46,18 @@ def load_ref_pf(as_name="pf_ref"):
     return mod
 
 
+def ref_p4_parent():
+    """Directory that holds the reference's ``p4`` package: /root/reference in the build container, else the copy
+    ``make -C oracle`` staged under oracle/_ref/ (git-ignored; it travels to the GPU box with the snapshot)."""
+    if os.path.isdir(os.path.join(REF_ROOT, "p4")):
+        return REF_ROOT
+    if os.path.isfile(os.path.join(_HERE, "_ref", "p4", "__init__.py")):
+        return os.path.join(_HERE, "_ref")
+    return None
+
+
 def have_ref_p4():
-    return os.path.isdir(os.path.join(REF_ROOT, "p4")) and have_ref_pf()
+    return ref_p4_parent() is not None and have_ref_pf()
 
 
 def load_ref_p4(pf_module=None):
@@ -58,8 +69,9 @@ def load_ref_p4(pf_module=None):
     """
     if "p4" in sys.modules:
         return sys.modules["p4"]
-    if not os.path.isdir(os.path.join(REF_ROOT, "p4")):
-        raise ImportError("%s/p4 not present (it never is on the GPU box)" % REF_ROOT)
+    parent = ref_p4_parent()
+    if parent is None:
+        raise ImportError("the reference's p4 package is neither at %s/p4 nor staged under oracle/_ref/p4" % REF_ROOT)
     if pf_module is None:
         pf_module = load_ref_pf()
     sys.modules["p4.pf"] = pf_module
@@ -68,11 +80,11 @@ def load_ref_p4(pf_module=None):
         stub = types.ModuleType("bitarray")
         stub.bitarray = type("bitarray", (), {})
         sys.modules["bitarray"] = stub
-    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, parent)
     try:
         import p4  # noqa: F401
     finally:
-        sys.path.remove(REF_ROOT)
+        sys.path.remove(parent)
     p4 = sys.modules["p4"]
     p4.pf = pf_module
     return p4

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <utility>
 #include <vector>
@@ -355,6 +356,86 @@ void p4b_rngFillUniform(void *g, double *out, long n)
 {
     if (g && out && n > 0) ((Rng *)g)->fillUniform(out, (size_t)n);
 }
+// ---- the random draws and special functions p4's MCMC proposals take from GSL through pf (Pf/pfmodule.c:724-1057) ----
+// GSL is a third-party dependency of the reference (absent here).  The draws below are the published algorithms GSL
+// documents for them -- gamma by Marsaglia & Tsang (2000) on a polar-method normal deviate, Dirichlet as normalised
+// gammas -- on this file's mt19937 stream; densities and lnGamma through libm.  They are host code beside the path:
+// Chain's proposals call them between likelihood evaluations (p4/chain.py:2274-2565).
+static double rngUniformPos(Rng *r)
+{
+    double x;
+    do { x = r->uniform(); } while (x == 0.0);
+    return x;
+}
+static double rngGaussian(Rng *r)
+{
+    double x, y, r2;
+    do {
+        x = -1 + 2 * rngUniformPos(r);
+        y = -1 + 2 * rngUniformPos(r);
+        r2 = x * x + y * y;
+    } while (r2 > 1.0 || r2 == 0);
+    return y * sqrt(-2.0 * log(r2) / r2);
+}
+static double rngGamma(Rng *r, double a, double b)
+{
+    if (a < 1) {
+        const double u = rngUniformPos(r);
+        return rngGamma(r, 1.0 + a, b) * pow(u, 1.0 / a);
+    }
+    const double d = a - 1.0 / 3.0, c = (1.0 / 3.0) / sqrt(d);
+    double x, v, u;
+    for (;;) {
+        do { x = rngGaussian(r); v = 1.0 + c * x; } while (v <= 0);
+        v = v * v * v;
+        u = rngUniformPos(r);
+        if (u < 1 - 0.0331 * x * x * x * x) break;
+        if (log(u) < 0.5 * x * x + d * (1 - v + log(v))) break;
+    }
+    return b * d * v;
+}
+long p4b_rngSize(void *g) { (void)g; return (long)sizeof(Rng); }                       /* pf.gsl_rng_size :724 */
+void p4b_rngGetState(void *g, void *buf) { if (g && buf) memcpy(buf, g, sizeof(Rng)); }   /* pf.gsl_rng_getstate :752 */
+void p4b_rngSetState(void *g, const void *buf) { if (g && buf) memcpy(g, buf, sizeof(Rng)); }   /* pf.gsl_rng_setstate :779 */
+double p4b_ranGamma(void *g, double a, double b) { return g ? rngGamma((Rng *)g, a, b) : NAN; }   /* pf.gsl_ran_gamma :827 */
+void p4b_ranDirichlet(void *g, int k, const double *alpha, double *theta)              /* pf.gsl_ran_dirichlet :940 */
+{
+    if (!g || !alpha || !theta) return;
+    double norm = 0.0;
+    for (int i = 0; i < k; i++) theta[i] = rngGamma((Rng *)g, alpha[i], 1.0);
+    for (int i = 0; i < k; i++) norm += theta[i];
+    for (int i = 0; i < k; i++) theta[i] /= norm;
+}
+double p4b_ranDirichletLnPdf(int k, const double *alpha, const double *theta)          /* pf.gsl_ran_dirichlet_lnpdf :989 */
+{
+    double logP = 0.0, sumAlpha = 0.0;
+    for (int i = 0; i < k; i++) logP += (alpha[i] - 1.0) * log(theta[i]);
+    for (int i = 0; i < k; i++) sumAlpha += alpha[i];
+    logP += lgamma(sumAlpha);
+    for (int i = 0; i < k; i++) logP -= lgamma(alpha[i]);
+    return logP;
+}
+double p4b_sfLnGamma(double x) { return lgamma(x); }                                   /* pf.gsl_sf_lngamma :887 */
+double p4b_ranGammaPdf(double x, double a, double b)                                   /* pf.gsl_ran_gamma_pdf :848 */
+{
+    if (x < 0) return 0;
+    if (x == 0) return (a == 1) ? 1 / b : 0;
+    if (a == 1) return exp(-x / b) / b;
+    return exp((a - 1) * log(x / b) - x / b - lgamma(a)) / b;
+}
+void p4b_meanVariance(const double *seq, int n, double *mean, double *variance)        /* pf.gsl_meanVariance :1025 */
+{
+    long double m = 0;
+    for (int i = 0; i < n; i++) m += (seq[i] - m) / (i + 1);
+    long double v = 0;
+    for (int i = 0; i < n; i++) {
+        const long double delta = seq[i] - (double)m;
+        v += (delta * delta - v) / (i + 1);
+    }
+    *mean = (double)m;
+    *variance = (double)(v * ((double)n / (double)(n - 1)));
+}
+
 int p4b_simulate(p4b_tree t, p4b_tree refTree, void *rng)
 {
     if (!t || !rng) { setError("p4b_simulate: NULL argument"); return 1; }

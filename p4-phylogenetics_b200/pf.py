@@ -76,6 +76,15 @@ _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setFusedVariant", _i, _i)
+_sig("p4b_rngSize", C.c_long, _vp)
+_sig("p4b_rngGetState", None, _vp, _vp)
+_sig("p4b_rngSetState", None, _vp, _vp)
+_sig("p4b_ranGamma", C.c_double, _vp, C.c_double, C.c_double)
+_sig("p4b_ranDirichlet", None, _vp, _i, _vp, _vp)
+_sig("p4b_ranDirichletLnPdf", C.c_double, _i, _vp, _vp)
+_sig("p4b_sfLnGamma", C.c_double, C.c_double)
+_sig("p4b_ranGammaPdf", C.c_double, C.c_double, C.c_double, C.c_double)
+_sig("p4b_meanVariance", None, _vp, _i, _vp, _vp)
 _OBJ = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
 _sig("p4b_allBrentPowellOptimize", C.c_long, _vp)
 _sig("p4b_allBOBYQAOptimize", C.c_long, _vp, _i)
@@ -815,6 +824,76 @@ def gsl_rng_uniform_array(g, n):
     out = np.empty(int(n), dtype=np.float64)
     _lib.p4b_rngFillUniform(g, out.ctypes.data, int(n))
     return out
+
+
+def gsl_rng_size(g):
+    """pf.gsl_rng_size(g) (Pf/pfmodule.c:724): bytes of generator state (what Mcmc checkpoints pickle)."""
+    return int(_lib.p4b_rngSize(g))
+
+
+def gsl_rng_getstate(g, byteArray):
+    """pf.gsl_rng_getstate(g, numpy byte array) (Pf/pfmodule.c:752)."""
+    a = np.asarray(byteArray)
+    if a.nbytes < gsl_rng_size(g):
+        raise ValueError("gsl_rng_getstate: the array is smaller than the generator state")
+    _lib.p4b_rngGetState(g, a.ctypes.data)
+
+
+def gsl_rng_setstate(g, byteArray):
+    """pf.gsl_rng_setstate(g, numpy byte array) (Pf/pfmodule.c:779)."""
+    a = np.ascontiguousarray(byteArray)
+    if a.nbytes < gsl_rng_size(g):
+        raise ValueError("gsl_rng_setstate: the array is smaller than the generator state")
+    _lib.p4b_rngSetState(g, a.ctypes.data)
+
+
+def gsl_ran_gamma(g, a, b):
+    """pf.gsl_ran_gamma(g, a, b) -> a draw from the gamma distribution (Pf/pfmodule.c:827)."""
+    return _lib.p4b_ranGamma(g, float(a), float(b))
+
+
+def gsl_ran_dirichlet(g, k, alpha, theta):
+    """pf.gsl_ran_dirichlet(g, k, alpha, theta): theta is overwritten with the draw (Pf/pfmodule.c:940)."""
+    _lib.p4b_ranDirichlet(g, int(k), _arr(alpha, np.float64, "alpha"), _arr(theta, np.float64, "theta"))
+
+
+def gsl_ran_dirichlet_lnpdf(k, alpha, theta):
+    """pf.gsl_ran_dirichlet_lnpdf(k, alpha, theta) -> float (Pf/pfmodule.c:989)."""
+    return _lib.p4b_ranDirichletLnPdf(int(k), _arr(alpha, np.float64, "alpha"), _arr(theta, np.float64, "theta"))
+
+
+def gsl_ran_dirichlet_pdf(k, alpha, theta):
+    return float(np.exp(gsl_ran_dirichlet_lnpdf(k, alpha, theta)))
+
+
+def gsl_sf_lngamma(a):
+    """pf.gsl_sf_lngamma(a) (Pf/pfmodule.c:887)."""
+    return _lib.p4b_sfLnGamma(float(a))
+
+
+def gsl_ran_gamma_pdf(x, a, b):
+    """pf.gsl_ran_gamma_pdf(x, a, b) (Pf/pfmodule.c:848)."""
+    return _lib.p4b_ranGammaPdf(float(x), float(a), float(b))
+
+
+def gsl_meanVariance(seq, seqLen, mean, variance):
+    """pf.gsl_meanVariance(seq, N, mean, variance): the two 1-element arrays are filled (Pf/pfmodule.c:1025)."""
+    _lib.p4b_meanVariance(_arr(seq, np.float64, "seq"), int(seqLen), _arr(mean, np.float64, "mean"), _arr(variance, np.float64, "variance"))
+
+
+_mcmcTreeCallbacks = {}
+
+
+def setMcmcTreeCallback(cTree, fn):
+    """pf.setMcmcTreeCallback(cTree, callable) (Pf/pfmodule.c:2727): the reference stores the callable on the tree and
+    only ever calls it from code that is compiled out (Pf/p4_node.c:420-438); it is kept here for the same lifetime."""
+    if not callable(fn):
+        raise TypeError("pf_setMcmcTreeCallback(): parameter must be callable")
+    _mcmcTreeCallbacks[cTree] = fn
+
+
+def unsetMcmcTreeCallback(cTree):
+    _mcmcTreeCallbacks.pop(cTree, None)
 
 
 def p4_simulate(cTree, cRefTree, g):
