@@ -14,7 +14,14 @@ the partial lnL.
   e2e       evals/s of ``Tree.calcLogLike()`` through the pf mirror: Python glue,
             host Q/eigen/gamma, host->device parameter blocks, P(t) kernel, CL
             recursion, reduction, device->host result
-  roofline  the CL kernels: algorithmic bytes / CUDA-event time
+  roofline  the whole-tree CL kernel: compulsory bytes of the fused design (every internal CL stored once, tips and
+            counts read once) / its CUDA-event time, against the measured HBM peak; measured DRAM traffic of the same
+            kernel at the same shard size from this round's ncu capture (profiles/r2_traffic.json); SURVEY.md 8(d)'s
+            per-node byte model under its own name
+  sustained the same step back to back for >= 1.5 s (clocks under the power cap), beside the K-step burst
+  configs   at N = 1: BASELINE configs 1, 3, 4 (full evaluation + dirty path) and 5 (generations/s, through the
+            call-protocol mirror and through the reference's REAL p4 Mcmc), each device-timed, with roofline,
+            single-core reference on a column sample and site likelihoods checked against the reference
   cpu_baseline / --impl reference
             the reference's own Pf engine (oracle/_ref, built from its unmodified
             sources) on the host cores, on a bounded sample of the same alignment,
@@ -57,6 +64,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16384, help="patterns in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-node", action="store_true", help="one CL launch per node instead of the whole-tree kernel")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (1, 3, 4, 5) that follow the headline at N=1")
+    ap.add_argument("--no-real-p4", action="store_true", help="skip the run of the reference's real p4 Mcmc on this engine (config 5)")
+    ap.add_argument("--sustained-s", type=float, default=1.5, help="length of the sustained sub-measurement")
     return ap.parse_args()
 
 
@@ -188,7 +198,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------
 def _ref_worker(args):
     """One process: the reference Pf engine on a slice of the sample alignment."""
-    taxa, sample, lo, hi, reps = args
+    taxa, sample, lo, hi, reps, warm = args
     import numpy as np
     import ref_loader
     import p4_phylogenetics_b200 as P
@@ -196,7 +206,8 @@ def _ref_worker(args):
     tree = build_tree(P, rpf, taxa, sample, site_slice=(lo, hi), repeat=False)
     tree._commonCStuff()
     nPat = rpf.partPatternCount(tree.data.parts[0].cPart)
-    lnL = rpf.p4_treeLogLike(tree.cTree, 0)   # warm-up
+    for _ in range(max(1, warm)):
+        lnL = rpf.p4_treeLogLike(tree.cTree, 0)   # warm-up
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -232,7 +243,7 @@ def build_tree(P, pf, taxa, patterns, site_slice=None, repeat=True):
     return tree
 
 
-def time_reference(taxa, full_patterns, sample, nproc, reps):
+def time_reference(taxa, full_patterns, sample, nproc, reps, warm=1):
     """Reference Pf evals/s extrapolated to ``full_patterns``: the sample alignment
     is cut into ``nproc`` column ranges, one process each (Pf itself is
     single-threaded); a whole-sample evaluation takes as long as
@@ -247,7 +258,7 @@ def time_reference(taxa, full_patterns, sample, nproc, reps):
     aln = P.synth.make_alignment(None, tree, mpart, sample, rng, "dna", repeat=False)
     nSites = aln.length
     cuts = [(nSites * i) // nproc for i in range(nproc + 1)]
-    jobs = [(taxa, sample, cuts[i], cuts[i + 1], reps) for i in range(nproc)]
+    jobs = [(taxa, sample, cuts[i], cuts[i + 1], reps, warm) for i in range(nproc)]
     if nproc == 1:
         res = [_ref_worker(jobs[0])]
     else:
@@ -256,7 +267,7 @@ def time_reference(taxa, full_patterns, sample, nproc, reps):
             res = pool.map(_ref_worker, jobs)
     nPat = sum(r[0] for r in res)                      # patterns actually evaluated (slices compress separately)
     per_rep = [max(r[1][k] for r in res) for k in range(reps)]
-    t = min(per_rep)
+    t = sum(per_rep) / len(per_rep)                    # the mean over the timed steps, like the GPU arm
     evals_per_s_sample = 1.0 / t
     return evals_per_s_sample * (nPat / float(full_patterns)), nPat, t
 
@@ -273,14 +284,14 @@ def run_reference(a):
     nproc = max(1, min(nproc, 64))
     sample = a.cpu_sample * nproc
     sample = min(sample, a.patterns)
-    reps = max(1, min(a.steps, 3))
+    reps = max(1, min(a.steps, 200))                   # exactly --steps timed steps (each ~0.3 s of CPU work), after --warmup untimed ones
     t0 = time.perf_counter()
-    value, nPat, t = time_reference(a.taxa, a.patterns, sample, nproc, reps)
+    value, nPat, t = time_reference(a.taxa, a.patterns, sample, nproc, reps, max(1, a.warmup))
     wall = time.perf_counter() - t0
     sample_desc = ("%d patterns of the %d (%d column ranges, one process each); %.3f s per evaluation of the sample; "
                    "scaled by patterns" % (nPat, a.patterns, nproc, t))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": reps, "warmup": 1,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": reps, "warmup": max(1, a.warmup),
         "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "engine": "reference Pf (Pf/*.c, gcc -O2) on host cores", "wall_s": round(wall, 1)},
@@ -289,6 +300,233 @@ def run_reference(a):
     }
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------
+# byte / flop models, the reference on a column sample, the other BASELINE configs
+# ------------------------------------------------------------------------------
+def work_model(pf, tree, shard_of=None):
+    """Per full-tree evaluation on this rank.
+      compulsory  what the fused whole-tree design MUST move through HBM: every internal node's CL written once (the state
+                  p4_treeLogLike leaves behind, as the reference does), every tip code and every pattern count read once.
+                  Child CLs are not in it: a node's running CL stays in registers / shared memory / L2 between steps.
+      algorithmic SURVEY.md 8(d): the same plus one read of every non-root internal CL (what a per-node design moves).
+      flops       2*dim^2*nCat per internal-child edge and pattern."""
+    comp = alg = flops = 0
+    for pNum, mp in enumerate(tree.model.parts):
+        if shard_of is not None:
+            lo, hi = shard_of(pNum)
+            nPat = hi - lo
+        else:
+            nPat = pf.partPatternCount(tree.data.parts[pNum].cPart)
+        unit = 8 * mp.dim * mp.nGammaCat
+        nLeaves = sum(1 for n in tree.nodes if n.isLeaf)
+        for n in tree.iterInternalsPostOrder():
+            kids = list(n.iterChildren())
+            k_int = sum(1 for c in kids if not c.isLeaf)
+            comp += unit * nPat
+            alg += (unit * (1 + k_int) + (len(kids) - k_int)) * nPat
+            flops += 2 * mp.dim * mp.dim * mp.nGammaCat * k_int * nPat
+        comp += (nLeaves + 4) * nPat
+    return float(comp), float(alg), float(flops)
+
+
+def load_peaks():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP64_DMMA_TFLOPS = 37.0   # FP64 mma.sync m8n8k4, measured on this pool with tools/microbench/membw.cu (profiles/r2_membw.txt); FMA pipe 34.7
+
+
+def measured_traffic(kernel_key, taxa, patterns_per_gpu):
+    """DRAM bytes per launch of the shipped kernel at this exact shard size, from this round's ncu --set full captures
+    (profiles/r2_traffic.json); None when no capture of this kernel at this size exists."""
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(tpath):
+        return None, None
+    for e in json.load(open(tpath)).get("entries", []):
+        if e.get("kernel") == kernel_key and e.get("taxa") == taxa and e.get("patterns_per_gpu") == patterns_per_gpu:
+            return e["dram_bytes_read"] + e["dram_bytes_write"], e.get("source")
+    return None, None
+
+
+def sample_twin(P, rpf, tree, nCols, seed):
+    """The reference engine on nCols sampled columns of every alignment of `tree` (site likelihoods do not depend on the
+    other columns, so the reference only has to evaluate the sample)."""
+    import numpy as np
+    H = P.host
+    rng = np.random.default_rng(seed)
+    alns, colsPer = [], []
+    for aln in tree.data.alignments:
+        cols = np.sort(rng.choice(aln.length, size=min(nCols, aln.length), replace=False))
+        seqs = [np.frombuffer(x if isinstance(x, (bytes, bytearray)) else x.encode(), dtype=np.uint8)[cols].tobytes() for x in aln.sequences]
+        alns.append(H.Alignment(rpf, seqs, aln.symbols, aln.equates))
+        colsPer.append(cols)
+    twin = tree.dupe()
+    twin.pf = rpf
+    twin.data = H.Data(rpf, alns)
+    twin.model = H.clone_model(tree.model, rpf)
+    return twin, colsPer
+
+
+def reference_on_sample(P, pf, tree, nCols, seed=3, reps=3):
+    """(max relative difference of the site likelihoods on the sample, reference evals/s of ONE core scaled to the full
+    pattern count, description) -- the reference's own Pf engine (oracle/_ref)."""
+    import numpy as np
+    import ref_loader
+    if not ref_loader.have_ref_pf():
+        return None, None, "oracle/_ref not built"
+    rpf = ref_loader.load_ref_pf()
+    site = np.array(tree.getSiteLikes())
+    twin, colsPer = sample_twin(P, rpf, tree, nCols, seed)
+    want = np.array(twin.getSiteLikes())
+    off = woff = 0
+    worst = 0.0
+    for aln, cols in zip(tree.data.alignments, colsPer):
+        got = site[off + cols]
+        w = want[woff:woff + len(cols)]
+        worst = max(worst, float(np.max(np.abs(got - w) / w)))
+        off += aln.length
+        woff += len(cols)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rpf.p4_treeLogLike(twin.cTree, 0)
+        ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    nSample = sum(rpf.partPatternCount(p.cPart) for p in twin.data.parts)
+    nFull = sum(pf.partPatternCount(p.cPart) for p in tree.data.parts)
+    value = 1.0 / (t * nFull / float(nSample))
+    desc = "%d patterns of the %d (a column sample per part); %.3f s per evaluation of the sample; scaled by patterns" % (nSample, nFull, t)
+    twin.deleteCStuff()
+    twin.model.free()
+    twin.data.free()
+    return worst, value, desc
+
+
+def free_tree(tree):
+    tree.deleteCStuff()
+    tree.model.free()
+    tree.data.free()
+
+
+CFG_NAMES = {
+    1: "cfg1: 32-taxon synthetic DNA, 10k patterns, GTR+I+G4, Tree.calcLogLike",
+    3: "cfg3: 100-taxon synthetic protein, 200k patterns, LG+G4 (20-state FP64 DMMA contraction)",
+    4: "cfg4: 60-taxon protein NDCH2 (a composition per node), 4 parts x 50k patterns, full evaluation + dirty path",
+    5: "cfg5: Mcmc.run, 8 Metropolis-coupled chains, 100-taxon DNA, 500k patterns, GTR+G4, generations/s",
+}
+CFG_SAMPLE = {1: 10000, 3: 1500, 4: 300, 5: 4096}
+
+
+def config_block(P, pf, cfg, peak, steps, real_p4=True):
+    """One BASELINE config that is not the headline: device-timed evaluations, roofline, single-core reference on a
+    sample, site likelihoods checked against the reference.  Returns a dict for the bench line's `configs` block."""
+    import numpy as np
+    t0 = time.perf_counter()
+    tree = P.synth.build_config(pf, cfg)
+    setup = time.perf_counter() - t0
+    lnL = tree.calcLogLike()
+    for _ in range(3):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    pf.treeTimerBegin(tree.cTree)
+    for _ in range(steps):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    ms = pf.treeTimerEnd(tree.cTree) / steps
+    e0 = time.perf_counter()
+    for _ in range(steps):
+        tree.calcLogLike()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
+    comp, alg, flops = work_model(pf, tree)
+    dim = tree.model.parts[0].dim
+    out = {"workload": CFG_NAMES[cfg], "taxa": sum(1 for n in tree.nodes if n.isLeaf), "parts": tree.model.nParts,
+           "patterns": [pf.partPatternCount(p.cPart) for p in tree.data.parts], "lnL": lnL, "setup_s": round(setup, 1),
+           "ms_per_eval": ms, "evals_per_s": 1000.0 / ms, "e2e_calcLogLike_evals_per_s": 1000.0 / e2e_ms,
+           "roofline": {"bound": "hbm", "achieved": comp / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": comp / ms / 1e6 / peak,
+                        "basis": "compulsory bytes: every internal CL stored once + tips + counts", "compulsory_GB": comp / 1e9,
+                        "algorithmic_8d_GB": alg / 1e9, "algorithmic_8d_GBps": alg / ms / 1e6}}
+    if dim == 20:
+        out["roofline"]["tensor"] = {"GFLOP_per_eval": flops / 1e9, "TFLOPs": flops / ms / 1e9, "peak_TFLOPs": FP64_DMMA_TFLOPS,
+                                     "frac": flops / ms / 1e9 / FP64_DMMA_TFLOPS, "peak_source": "FP64 mma.sync m8n8k4 microbenchmark (profiles/r2_membw.txt)"}
+    worst, cpu_value, desc = reference_on_sample(P, pf, tree, CFG_SAMPLE[cfg])
+    out["reference_check"] = {"site_likelihoods_max_rel_diff": worst, "tolerance": 1e-9, "ok": (worst is not None and worst <= 1e-9)}
+    out["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": desc}
+    if cfg == 4:
+        # the dirty path: ONE composition changed, p4's whole-part protocol (p4/chain.py:305-380: p4_setPrams(pNum), every
+        # internal node, p4_partLogLike); the engine finds by content what the change reaches (memoisation, its default)
+        rng = np.random.default_rng(0)
+        pf.setMemoize(1)
+        tree.calcLogLike()
+        leaves = [n for n in tree.nodes if n.isLeaf]
+        internals = [n for n in tree.nodes if not n.isLeaf and n is not tree.root]
+        res = {}
+        for name, pool in (("one_leaf_composition", leaves), ("one_internal_composition", internals)):
+            ts = []
+            for k in range(steps):
+                pNum = k % tree.model.nParts
+                c = tree.model.parts[pNum].comps[pool[k % len(pool)].parts[pNum].compNum]
+                c.val[:] = P.synth.normalise_comp(c.val * np.exp(rng.normal(0.0, 0.05, size=c.val.shape)))
+                t1 = time.perf_counter()
+                pf.p4_setPrams(tree.cTree, pNum)
+                for n in tree.iterInternalsPostOrder():
+                    pf.p4_setConditionalLikelihoodsOfInternalNodePart(n.cNode, pNum)
+                v = pf.p4_partLogLike(tree.cTree, tree.data.parts[pNum].cPart, pNum, 0)
+                ts.append((time.perf_counter() - t1) * 1e3)
+            res[name + "_ms"] = sum(ts) / len(ts)
+        dirty = sum(tree.partLikes)
+        full = tree.calcLogLike()
+        res["dirty_equals_full_rel_diff"] = abs(dirty - full) / abs(full)
+        pf.setMemoize(0)
+        out["dirty_path"] = res
+    if cfg == 5:
+        free_tree(tree)
+        tree = P.synth.build_config(pf, 5)
+        tree.bulkSetCStuff = True
+        m = P.mcmc.Mcmc(tree, nChains=8, seed=1)
+        pf.setMemoize(1)
+        m.run(10, batched="pipelined")
+        gens = 100
+        n0 = pf.kernelLaunchCount()
+        t1 = time.perf_counter()
+        m.run(gens, batched="pipelined")
+        pf.treeSync(m.chains[0].curTree.cTree)
+        dt = time.perf_counter() - t1
+        pf.setMemoize(0)
+        out["mcmc_mirror"] = {"gens_per_s": gens / dt, "ms_per_gen": 1e3 * dt / gens, "chains": 8, "gens": gens,
+                              "launches_per_gen": (pf.kernelLaunchCount() - n0) / gens,
+                              "driver": "p4-phylogenetics_b200/mcmc.py (the call protocol of Chain.proposeSp / gen with nine proposals; pipelined chains)"}
+        for c in m.chains:
+            for t in (c.curTree, c.propTree):
+                if t is not tree:
+                    t.deleteCStuff()
+                    t.model.free()
+    free_tree(tree)
+    if cfg == 5 and real_p4:
+        out["mcmc_real_p4"] = real_p4_mcmc()
+    return out
+
+
+def real_p4_mcmc(taxa=100, patterns=500000, chains=8, gens=40):
+    """Config 5 through the reference's REAL p4 package (its own Mcmc.run / Chain code, staged under oracle/_ref/p4) with
+    this repository's pf module as p4.pf -- a process of its own (tests/dropin/p4_like_side.py)."""
+    import ref_loader
+    if not ref_loader.have_ref_p4():
+        return {"unavailable": "oracle/_ref/p4 not staged"}
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "dropin", "p4_like_side.py"), "mine", "--taxa", str(taxa), "--patterns", str(patterns),
+           "--gens", str(gens), "--chains", str(chains), "--skip-opt"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "timed out"}
+    lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
+    if r.returncode != 0 or not lines:
+        return {"unavailable": "failed: " + (r.stderr or r.stdout)[-300:]}
+    d = json.loads(lines[-1][len("RESULT"):])
+    return {"gens_per_s": d["gens_per_s"], "gens": gens, "chains": chains, "lnL0": d["lnL0"], "calcLogLike_s": d["calc_again_s"],
+            "driver": "p4.Mcmc(t, nChains=8).run(n) -- p4/mcmc.py:2496, p4/chain.py proposals, unmodified -- on this pf module"}
 
 
 # ------------------------------------------------------------------------------
@@ -379,6 +617,23 @@ def run_b200(a):
         dist.all_reduce(tl, op=dist.ReduceOp.MAX)
     lean_value = 1000.0 * a.steps / float(tl.item())
 
+    # ---- sustained: the same step back to back for >= a.sustained_s seconds (clocks settle under the power cap) -----
+    n_sus = max(a.steps, int(a.sustained_s * 1000.0 / ms_per_step) + 1)
+    sampler2 = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler2.start()
+    pf.treeTimerBegin(tree.cTree)
+    for _ in range(n_sus):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    sus_ms = pf.treeTimerEnd(tree.cTree)
+    barrier()
+    clocks_sus = sampler2.stop() if rank == 0 else None
+    ts = torch.tensor([sus_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sustained = {"value": 1000.0 * n_sus / float(ts.item()), "unit": UNIT, "steps": n_sus, "seconds": float(ts.item()) / 1e3, "clocks": clocks_sus}
+
     # ---- e2e: Tree.calcLogLike() through the pf mirror ----------------------------
     rng = np.random.default_rng(1)
     for _ in range(2):
@@ -417,36 +672,28 @@ def run_b200(a):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the CL kernels ------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # ---- roofline of the CL kernel --------------------------------------------------
+    # achieved = COMPULSORY bytes of the fused design / the kernel's CUDA-event time: every internal CL written once (the
+    # state p4_treeLogLike leaves behind), tips and counts read once.  SURVEY.md 8(d)'s per-node figure, which also counts a
+    # re-read of every internal child, is reported beside it under its own name: a whole-tree kernel keeps children in
+    # registers / shared memory / L2, so that figure divided by the time would exceed the HBM peak without meaning anything.
+    peak, peak_src = load_peaks()
     shard = hi - lo
-    cl_bytes = float(bpp) * shard                         # algorithmic bytes of one evaluation on this rank
+    comp_bytes, alg_bytes, flops = work_model(pf, tree, shard_of=lambda pNum: pf.treeShardRange(tree.cTree, pNum))
     cl_ms_avg = sum(cl_ms) / len(cl_ms)
-    achieved = cl_bytes / (cl_ms_avg * 1e-3) / 1e9
-    ps_pad = (shard + 31) // 32 * 32
-    waves = (ps_pad / 2) / (128.0 * 3.0 * 148)      # the engine's launch-shape rule (csrc/tree.cu fusedVariant)
-    shape = "128 threads x 3 CTAs/SM" if waves >= 3.0 else ("64 x 5" if waves >= 1.6 else "32 x 7")
-    kernel = "cl_tree_dna_kernel<4>, %s (whole-tree CL recursion + site likelihoods, one launch)" % shape if cl_launches == 1 \
-        else "cl_dna_kernel<4> (all %d CL launches of one evaluation)" % cl_launches
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and cl_launches == 1:
-        for e in json.load(open(tpath))["entries"]:
-            if e["taxa"] == a.taxa and e["patterns_per_gpu"] == shard:
-                traffic = e["dram_bytes_read"] + e["dram_bytes_write"]
-                traffic_src = e["source"]
-    roofline = {"bound": "hbm", "kernel": kernel,
+    achieved = comp_bytes / (cl_ms_avg * 1e-3) / 1e9
+    kernel = pf.lastCLKernelName() if cl_launches == 1 else "cl_dna_kernel<4> (all %d CL launches of one evaluation)" % cl_launches
+    traffic, traffic_src = measured_traffic(kernel, a.taxa, shard)
+    roofline = {"bound": "hbm", "kernel": kernel + " (whole-tree CL recursion + site likelihoods + lnL fold, one launch)" if cl_launches == 1 else kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "basis": "compulsory bytes per launch: 8*dim*nCat bytes stored per internal node and pattern + tips + counts",
+                "compulsory_bytes_per_pattern": comp_bytes / shard,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_GBps": (traffic / (cl_ms_avg * 1e-3) / 1e9) if traffic else None,
-                "note": "achieved counts ALGORITHMIC bytes (SURVEY.md 8d); the kernel keeps a third of the child reads in registers "
-                        "and most of the rest in L2, so DRAM traffic is about 0.55x the algorithmic bytes and frac exceeds 1",
-                "algorithmic_bytes_per_pattern": bpp, "launches_per_eval": cl_launches,
-                "avg_launch_us": 1e3 * cl_ms_avg / max(cl_launches, 1), "cl_ms_per_eval": cl_ms_avg}
+                "traffic_frac_of_peak": (traffic / (cl_ms_avg * 1e-3) / 1e9 / peak) if traffic else None,
+                "algorithmic_8d": {"bytes_per_pattern": bpp, "GBps": float(bpp) * shard / (cl_ms_avg * 1e-3) / 1e9,
+                                   "note": "SURVEY.md 8(d) per-node byte model (every child CL re-read from HBM); kept for comparison, not a roofline fraction"},
+                "launches_per_eval": cl_launches, "avg_launch_us": 1e3 * cl_ms_avg / max(cl_launches, 1), "cl_ms_per_eval": cl_ms_avg}
 
     cpu = None
     if not a.no_cpu_baseline:
@@ -477,7 +724,23 @@ def run_b200(a):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "sustained": sustained,
+        "host": "torch is imported for the rendezvous (torch.distributed), the timing barrier and the max over ranks only; the engine is libp4b200.so (nvcc, no torch)",
     }
+    # ---- the other BASELINE configs (N = 1 only; parity-test cases, reported beside the headline) --------------------
+    if world == 1 and not a.no_configs and a.patterns == N_PATTERNS and a.taxa == N_TAX:
+        free_tree(tree)
+        tree = None
+        configs = {}
+        for cfg in (1, 3, 4, 5):
+            try:
+                configs["cfg%d" % cfg] = config_block(P, pf, cfg, peak, 10, real_p4=not a.no_real_p4)
+            except SystemExit as e:
+                configs["cfg%d" % cfg] = {"failed": "engine error: %s" % (e,)}
+            except Exception as e:      # the headline line must still be printed
+                configs["cfg%d" % cfg] = {"failed": "%s: %s" % (type(e).__name__, e)}
+            log("cfg%d: %s" % (cfg, json.dumps(configs["cfg%d" % cfg])[:400]))
+        line["configs"] = configs
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -80,6 +80,8 @@ void p4b_setFusedTreeKernel(int on);
  * configs[1] uses).  0, 1, 2 force one of those three; 3..8 are comparison shapes.  Results are bit-identical
  * across shapes; the setter exists so that the parity tests can run every shape at every shard size. */
 int p4b_setFusedVariant(int v);
+/* Name and launch shape of the CL kernel launched last (bench.py reports it beside its roofline). */
+const char *p4b_lastCLKernelName(void);
 /* 20-state parts with 4 rate categories have a whole-tree kernel of their own (FP64 tensor cores, the
  * running CL stays in the accumulator registers from one node to the next); 0 keeps the one-launch-
  * per-node kernels for them. */

@@ -38,6 +38,7 @@ int p4b_commDestroy(void) { return commDestroy(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
 int p4b_setFusedVariant(int v) { return setFusedVariant(v); }
+const char *p4b_lastCLKernelName(void) { return lastCLKernelName(); }
 void p4b_setFusedTreeKernel20(int on) { setFusedAAEnabled(on); }
 void p4b_setDeferredNodeCalls(int on) { setDeferEnabled(on); }
 void p4b_setSharedCondLikes(int on) { setShareEnabled(on); }

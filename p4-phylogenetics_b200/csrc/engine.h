@@ -185,6 +185,7 @@ int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
 void setFusedEnabled(int on);
 int setFusedVariant(int v);
+const char *lastCLKernelName();
 void setDmmaEnabled(int on);
 void setScalersEnabled(int on);
 int treeEnsureResident(Tree *t, int p);

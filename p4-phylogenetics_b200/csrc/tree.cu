@@ -79,6 +79,8 @@ struct Engine {
     std::vector<Step2> stepShadow;             // what stepDev holds (once the stream reaches the last upload)
 };
 static Engine G;
+static char g_lastKernel[128] = "";   // p4b_lastCLKernelName: the CL kernel launched last (bench.py names it in its roofline)
+const char *lastCLKernelName() { return g_lastKernel; }
 static int flushPJobs();
 void nodeDeviceRelease(Node *n);
 static bool g_useScalers = false;
@@ -841,6 +843,7 @@ static int launchCL(const CLArgs &a)
         cl_generic_kernel<<<grid, 128, 0, G.stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
+    snprintf(g_lastKernel, sizeof(g_lastKernel), "per-node CL kernels (dim %d, nCat %d)", a.dim, a.nCat);
     G.launches++;
     return 0;
 }
@@ -1415,6 +1418,7 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     }
     fn<<<dim3(blocks, nJobs), sh.cw * 32, smem, G.stream>>>(a);
     CUDA_TRY(cudaGetLastError());
+    snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_dna2_kernel<%d,%d,%d,%d>", L.nCat, sh.ct, sh.cw, sh.minb);
     G.launches++;
     for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
     return 0;
@@ -1585,6 +1589,8 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         }
         fn<<<dim3(blocks, nTrees), THREADS, smemNow, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
+        if (aa) snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa_kernel<%d,%d,%d,%d>", L.nCat, aaGroups, aaMinB, aaMT);
+        else snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_dna_kernel<%d,%d> shape %d", L.nCat, THREADS, variant);
         G.launches++;
         for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
         return 0;

@@ -76,6 +76,7 @@ _sig("p4b_commDestroy", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setFusedVariant", _i, _i)
+_sig("p4b_lastCLKernelName", _cp)
 _sig("p4b_rngSize", C.c_long, _vp)
 _sig("p4b_rngGetState", None, _vp, _vp)
 _sig("p4b_rngSetState", None, _vp, _vp)
@@ -284,6 +285,10 @@ def setFusedTreeKernel(on):
 def setFusedVariant(v):
     """Launch shape of the 4-state whole-tree kernel: -1 by shard size (default), 0/1/2 forced (include/p4b200.h)."""
     _ok(_lib.p4b_setFusedVariant(int(v)))
+
+
+def lastCLKernelName():
+    return (_lib.p4b_lastCLKernelName() or b"").decode()
 
 
 def setDeferredNodeCalls(on):
