@@ -51,7 +51,13 @@ struct Part {
     //   equates), dim+1+j = the j-th equate that is not N-like.
     std::vector<int> realEquateOfEquate; // [nEquates] -> j or -1 if N-like
     int nRealEquates = 0;
-    int tableWidth() const { return dim + 1 + nRealEquates; }
+    // ... of which only those that OCCUR in the patterns get a column (recounted whenever the device mirror is
+    // rebuilt): with the eleven IUPAC ambiguity codes defined but two of them present a DNA table is 7 wide, not 15
+    std::vector<int> usedEquateOfEquate; // [nEquates] -> column j or -1 (N-like, or absent from the data)
+    int nUsedEquates = -1;               // -1: not counted yet (then every real equate has a column)
+    int equateColumn(int e) const { return nUsedEquates < 0 ? realEquateOfEquate[e] : usedEquateOfEquate[e]; }
+    int nEquateColumns() const { return nUsedEquates < 0 ? nRealEquates : nUsedEquates; }
+    int tableWidth() const { return dim + 1 + nEquateColumns(); }
     PartDevice dev;
 };
 

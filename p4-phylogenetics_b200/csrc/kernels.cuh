@@ -30,6 +30,7 @@ struct PJob {
     const uint64_t *eq;    // masks of the part's non-N-like equates
     double *aux;           // 20-state parts served by the whole-tree kernel: P^T in fragment order + transposed leaf table
     int dim, nCat, tblW, nRealEq;
+    int auxDP, pad;        // aux layout: 0 = the 20-state kernel's; else the padded state count of cl_tree_dmma_kernel
     long long tOff;        // into the staged doubles: t[cat] effective branch lengths
 };
 
@@ -173,7 +174,30 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
             T[idx] = v;
         }
     }
-    if (job.aux) {
+    if (job.aux && job.auxDP > 0) {
+        // Operand decks of cl_tree_dmma_kernel (tree_dmma.cuh), padded state count DP:
+        //   aux[0 .. nCat*F), F = (DP/4)*(DP/8)*32   P^T in mma fragment order [cat][kk][nt][lane]: lane (g,q) holds
+        //                                            P[cat][8nt+g][x], x = 8*(kk>>1) + 2q + (kk&1); zero beyond dim
+        //   aux[nCat*F .. +nCat*W*DP)                leaf table transposed and padded, [cat][w][DP]; zero beyond dim
+        __syncthreads();
+        const int DP = job.auxDP, NT = DP / 8, KS = DP / 4, F = KS * NT * 32;
+        double *A = job.aux;
+        for (int i = threadIdx.x; i < nCat * F; i += blockDim.x) {
+            const int l = i & 31, nt = (i >> 5) % NT, kk = (i / (32 * NT)) % KS, ct = i / F;
+            const int s = 8 * nt + (l >> 2), x = 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1);
+            A[i] = (s < dim && x < dim) ? P[(ct * dim + s) * dim + x] : 0.0;
+        }
+        if (job.tblW > 0) {
+            const int W = job.tblW;
+            const double *T = job.tbl;
+            double *TT = A + (size_t)nCat * F;
+            const int nT = nCat * W * DP;
+            for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+                const int st = i % DP, w = (i / DP) % W, ct = i / (DP * W);
+                TT[i] = st < dim ? T[(ct * dim + st) * W + w] : 0.0;
+            }
+        }
+    } else if (job.aux) {
         // Operand decks of cl_tree_aa_kernel, so that its per-step staging is a straight copy:
         //   aux[0 .. nCat*480)            P^T in mma fragment order [cat][kk][nt][lane]: lane (g,q) holds P[cat][8nt+g][x],
         //                                 x = 8t+2q+i for kk = 2t+i < 4, x = 16+q for kk = 4; zero where the parent state is >= 20

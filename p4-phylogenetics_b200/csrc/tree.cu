@@ -30,6 +30,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "tree_dna.cuh"
+#include "tree_dmma.cuh"
 #include "newt.cuh"
 
 namespace p4b {
@@ -194,6 +195,23 @@ static int partDeviceEnsure(Part *p)
     partDeviceFree(p);
     if (p->nPatterns <= 0) { setError("part has no patterns (pf.makePatterns not called?)"); return 1; }
     shardRange(p->nPatterns, &d.lo, &d.hi);
+    {   // which ambiguity codes occur at all (over ALL patterns, so that every rank lays its tables out alike)
+        std::vector<char> used(p->nEquates > 0 ? p->nEquates : 1, 0);
+        for (int t = 0; t < p->nTax; t++) {
+            const int *row = p->patterns.data() + (size_t)t * p->nChar;
+            for (int k = 0; k < p->nPatterns; k++) {
+                const int c = row[k];
+                if (c < 0 && c != P4B_GAP_CODE && c != P4B_QMARK_CODE && c != -3) {
+                    const int e = c - P4B_EQUATES_BASE;
+                    if (e >= 0 && e < p->nEquates) used[e] = 1;
+                }
+            }
+        }
+        p->usedEquateOfEquate.assign(p->nEquates, -1);
+        p->nUsedEquates = 0;
+        for (int e = 0; e < p->nEquates; e++)
+            if (p->realEquateOfEquate[e] >= 0 && used[e]) p->usedEquateOfEquate[e] = p->nUsedEquates++;
+    }
     const int n = d.hi - d.lo;
     d.ps = ((n > 0 ? n : 1) + 31) & ~31;
     const size_t ps = (size_t)d.ps;
@@ -210,7 +228,7 @@ static int partDeviceEnsure(Part *p)
             else {
                 const int e = c - P4B_EQUATES_BASE;
                 if (e < 0 || e >= p->nEquates) { setError("bad character code %d in patterns", c); return 1; }
-                const int j = p->realEquateOfEquate[e];
+                const int j = p->equateColumn(e);
                 w = j < 0 ? dim : dim + 1 + j;
             }
             out[k] = (uint8_t)w;
@@ -234,7 +252,7 @@ static int partDeviceEnsure(Part *p)
     }
     std::vector<uint64_t> em(p->nRealEquates > 0 ? p->nRealEquates : 1, 0);
     for (int e = 0; e < p->nEquates; e++) {
-        const int j = p->realEquateOfEquate[e];
+        const int j = p->equateColumn(e);
         if (j < 0) continue;
         for (int s = 0; s < dim; s++)
             if (p->equates[(size_t)e * dim + s]) em[j] |= 1ull << s;
@@ -277,7 +295,8 @@ struct PartLayout {
     size_t clNodeDoubles = 0;    // nCat*dim*ps
     size_t pOff = 0, pDoubles = 0;       // within a node's P deck
     size_t tblOff = 0, tblDoubles = 0;   // within a node's leaf tables
-    size_t auxOff = 0, auxDoubles = 0;   // within a node's operand decks of the 20-state whole-tree kernel (0: none)
+    size_t auxOff = 0, auxDoubles = 0;   // within a node's operand decks of the tensor-core whole-tree kernels (0: none)
+    int auxDP = 0;                       // 0: the 20-state kernel's deck layout; else the padded state count of cl_tree_dmma_kernel
     size_t eigOff = 0, eigStride = 0;    // within the eig mirror; stride per (comp,rMatrix)
     size_t eqOff = 0;                    // within the equate mask mirror
     int nPairs = 0;                      // nComps*nRMatrices
@@ -355,6 +374,11 @@ int treeDeviceCreate(Tree *t)
         if (L.dim == 20 && L.nCat == 4) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
             L.auxOff = d->auxNodeDoubles;
             L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * L.dim * L.W;
+            d->auxNodeDoubles += L.auxDoubles;
+        } else if (L.dim > 20 && L.dim <= 64 && !g_useScalers) {   // 21..64 states: the generic tensor-core kernel's decks (tree_dmma.cuh)
+            L.auxDP = dmmaPaddedDim(L.dim);
+            L.auxOff = d->auxNodeDoubles;
+            L.auxDoubles = dmmaAuxDoubles(L.auxDP, L.nCat, L.W);
             d->auxNodeDoubles += L.auxDoubles;
         }
         L.nPairs = mp->nComps * mp->nRMatrices;
@@ -691,6 +715,8 @@ static int buildPJob(Node *n, int p, bool allowSkip)
     j.aux = L.auxDoubles ? d->aux + d->auxNodeDoubles * (size_t)n->nodeNum + L.auxOff : nullptr;
     j.dim = L.dim;
     j.nCat = L.nCat;
+    j.auxDP = L.auxDP;
+    j.pad = 0;
     j.tblW = n->isLeaf ? L.W : 0;
     j.nRealEq = L.W - L.dim - 1;
     j.tOff = (long long)tvals.size();
@@ -796,6 +822,9 @@ static bool fusedEligible(const PartLayout &L)
     if (!g_fusedEnabled) return false;
     if (L.dim == 4) return L.nCat == 4 || L.nCat == 1;
     if (L.dim == 20) return g_fusedAAEnabled && g_dmmaEnabled && L.nCat == 4 && !L.scalers && L.W <= 64;
+    if (L.dim > 20 && L.dim <= 64)    // two children x two buffers of max(P^T fragments, transposed leaf table) must fit shared memory
+        return g_fusedAAEnabled && g_dmmaEnabled && !L.scalers && L.auxDP > 0 && L.nCat <= 64 &&
+               4 * sizeof(double) * std::max(dmmaFragDoubles(L.auxDP), (size_t)L.W * L.auxDP) + 64 <= 200 * 1024;
     return false;
 }
 
@@ -1351,6 +1380,7 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     a.counts = dp->dev.counts;
     a.invarMask = dp->dev.invarMask;
     a.eqMask = dp->dev.equateMask;
+    if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
     const int shape = fused2Shape(L.ps, nJobs);
     const Shape2 sh = L.nCat == 4 ? kShapes2[shape] : Shape2{1, shape == 0 ? 4 : (shape == 1 ? 2 : 1), shape == 0 ? 4 : (shape == 1 ? 8 : 16)};
     const int csplit = L.nCat / sh.ct;
@@ -1424,6 +1454,103 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// 21..64 states: the generic tensor-core whole-tree kernel (tree_dmma.cuh)
+// ---------------------------------------------------------------------------
+static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int p, bool *overflowOk, size_t *resumeAt, int maxKids);
+static int launchFusedDmmaBatch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
+{
+    if (flushPJobs()) return 1;
+    Tree *t0 = jobs[0].t;
+    TreeDevice *d0 = t0->dev;
+    PartLayout &L = d0->parts[p];
+    Part *dp = t0->data->parts[p];
+    static TreeArgs a;
+    memset(&a, 0, offsetof(TreeArgs, steps));
+    a.ps = L.ps;
+    a.nPat = L.nPat;
+    a.tblW = L.W;
+    a.pNodeDoubles = (long long)d0->pNodeDoubles;
+    a.tblNodeDoubles = (long long)d0->tblNodeDoubles;
+    a.auxNodeDoubles = (long long)d0->auxNodeDoubles;
+    a.tips = dp->dev.tips;
+    a.counts = dp->dev.counts;
+    a.invarMask = dp->dev.invarMask;
+    a.eqMask = dp->dev.equateMask;
+    if (!d0->aux || !L.auxDP) { setError("internal: generic tensor-core kernel without operand decks"); return 1; }
+    static int mt = -1, warps = 8;
+    if (mt < 0) {
+        const char *e = getenv("P4B_DMMA_MT");
+        mt = e ? atoi(e) : 2;
+        if (mt != 1 && mt != 2) mt = 2;
+        warps = mt == 1 ? 16 : 8;
+    }
+    const int DP = L.auxDP;
+    const int patsPerCta = warps * 8 * mt;
+    const int blocks = (L.ps + patsPerCta - 1) / patsPerCta;
+    for (int i = 0; i < nJobs; i++) {
+        Tree *t = jobs[i].t;
+        TreeDevice *d = t->dev;
+        PartLayout &Li = d->parts[p];
+        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != L.dim || Li.W != L.W || d->auxNodeDoubles != d0->auxNodeDoubles || Li.auxDP != L.auxDP) {
+            setError("batched evaluation: the trees do not share the data part and model shape");
+            return 1;
+        }
+        TreeHdr &h = a.hdr[i];
+        h.arena = arenaBase(Li);
+        h.Pdeck = d->P + Li.pOff;
+        h.tbl = d->tbl + Li.tblOff;
+        h.aux = d->aux + Li.auxOff;
+        if (jobs[i].withLike && (!t->root || jobs[i].order->empty() || jobs[i].order->back() != t->root)) { setError("fused evaluation: the last node must be the root"); return 1; }
+    }
+    const size_t slot = std::max(dmmaFragDoubles(DP), (size_t)L.W * DP);
+    const size_t smem = 2 * kAAKids * slot * sizeof(double) + 64;
+    typedef void (*Fn)(const TreeArgs, const int, const int);
+    Fn fn = DP == 32 ? (mt == 1 ? (Fn)cl_tree_dmma_kernel<32, 1, 16> : (Fn)cl_tree_dmma_kernel<32, 2, 8>)
+                     : (mt == 1 ? (Fn)cl_tree_dmma_kernel<64, 1, 16> : (Fn)cl_tree_dmma_kernel<64, 2, 8>);
+    static std::unordered_set<void *> attrSet;
+    if (!attrSet.count((void *)fn)) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attrSet.insert((void *)fn);
+    }
+    auto launch = [&](int nTrees) -> int {
+        a.nTrees = nTrees;
+        fn<<<dim3(blocks, nTrees, L.nCat), warps * 32, smem, G.stream>>>(a, L.dim, L.nCat);
+        CUDA_TRY(cudaGetLastError());
+        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_dmma_kernel<%d,%d,%d>", DP, mt, warps);
+        G.launches++;
+        for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
+        return 0;
+    };
+    if (nJobs == 1) {
+        size_t at = 0;
+        for (;;) {
+            bool more = true;
+            const int ns = buildSteps(a, 0, kMaxSteps, jobs[0], p, &more, &at, kAAKids);
+            if (ns < 0) return 1;
+            a.hdr[0].stepBase = 0;
+            a.hdr[0].nSteps = ns;
+            if (ns > 0 && launch(1)) return 1;
+            if (!more) break;
+        }
+    } else {
+        int base = 0;
+        for (int i = 0; i < nJobs; i++) {
+            const int ns = buildSteps(a, base, kMaxSteps - base, jobs[i], p, nullptr, nullptr, kAAKids);
+            if (ns == -2) { setError("batched evaluation: the step lists of the trees do not fit one launch"); return 1; }
+            if (ns < 0) return 1;
+            a.hdr[i].stepBase = base;
+            a.hdr[i].nSteps = ns;
+            base += ns;
+        }
+        if (launch(nJobs)) return 1;
+    }
+    for (int i = 0; i < nJobs; i++)
+        if (jobs[i].withLike)
+            if (enqueueRootLike(jobs[i].t, p, jobs[i].wantPatLikes, resultDev + 2 * i)) return 1;
+    return 0;
+}
+
 // Whole-tree kernel over one or several trees that share data part p (same shard, same model shape).
 // With withLike jobs the per-tree results land in resultDev[2*i] (sum of count*log like) and
 // resultDev[2*i+1] (count of non-positive likelihoods) for job i.
@@ -1436,6 +1563,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         if (env2 < 0) { const char *e = getenv("P4B_FUSED2"); env2 = e ? atoi(e) != 0 : 1; }
         const bool oldForced = g_fusedVariant >= 0 && g_fusedVariant < 10;
         if (L0.dim == 4 && !L0.scalers && g_fused2 && env2 && !oldForced) return launchFused2Batch(jobs, nJobs, p, resultDev);
+        if (L0.dim > 20) return launchFusedDmmaBatch(jobs, nJobs, p, resultDev);
     }
     if (flushPJobs()) return 1;
     Tree *t0 = jobs[0].t;
@@ -1943,7 +2071,7 @@ int treesPartLogLike(Tree **trees, int n, int p, double *out)
         }
         return 0;
     }
-    const int stepKids = trees[0]->dev->parts[p].dim == 20 ? kAAKids : kMaxChildren;
+    const int stepKids = trees[0]->dev->parts[p].dim != 4 ? kAAKids : 2;     // every whole-tree kernel takes at most two children per step
     int i0 = 0;
     while (i0 < n) {
         // greedy group: at most kMaxBatchTrees trees and kMaxSteps steps
@@ -2220,7 +2348,7 @@ int nodeSetBigP(Node *n, int p, const double *in)
     const int dim = L.dim, W = L.W;
     std::vector<uint64_t> em(dp->nRealEquates > 0 ? dp->nRealEquates : 1, 0);
     for (int e = 0; e < dp->nEquates; e++) {
-        const int j = dp->realEquateOfEquate[e];
+        const int j = dp->equateColumn(e);
         if (j < 0) continue;
         for (int s = 0; s < dim; s++)
             if (dp->equates[(size_t)e * dim + s]) em[j] |= 1ull << s;
@@ -2239,7 +2367,20 @@ int nodeSetBigP(Node *n, int p, const double *in)
         }
     CUDA_TRY(cudaMemcpyAsync(nodeTbl(n, p), T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
     std::vector<double> A(L.auxDoubles);
-    if (L.auxDoubles) {   // the same two decks pmatrix_kernel derives from P
+    if (L.auxDoubles && L.auxDP > 0) {   // the generic tensor-core kernel's decks, as pmatrix_kernel derives them from P
+        const int DP = L.auxDP, NT = DP / 8, KS = DP / 4, F = KS * NT * 32;
+        for (int i = 0; i < L.nCat * F; i++) {
+            const int l = i & 31, nt = (i >> 5) % NT, kk = (i / (32 * NT)) % KS, ct = i / F;
+            const int s = 8 * nt + (l >> 2), x = 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1);
+            A[i] = (s < dim && x < dim) ? in[((size_t)ct * dim + s) * dim + x] : 0.0;
+        }
+        const size_t nF = (size_t)L.nCat * F;
+        for (int i = 0; i < L.nCat * W * DP; i++) {
+            const int st = i % DP, w = (i / DP) % W, ct = i / (DP * W);
+            A[nF + i] = st < dim ? T[((size_t)ct * dim + st) * W + w] : 0.0;
+        }
+        CUDA_TRY(cudaMemcpyAsync(nodeAux(n, p), A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    } else if (L.auxDoubles) {   // the same two decks pmatrix_kernel derives from P
         const int nF = L.nCat * kAAFrag;
         for (int i = 0; i < nF; i++) {
             const int l = i & 31, nt = (i >> 5) % 3, kk = (i / 96) % 5, ct = i / kAAFrag;

@@ -29,12 +29,12 @@
 namespace p4b {
 
 constexpr unsigned kNone = 0xffffffffu;
-constexpr int kRing = 6;          // steps the producer may run ahead
+constexpr int kRing = 4;          // operand ring: steps whose P decks / leaf tables can be in flight ahead of a warp
 
 // flags of a step
 constexpr unsigned kStepFirst = 4u, kStepStore = 8u, kStepPush = 256u, kStepPfLate = 512u;
 
-struct Step2 {            // 48 bytes in global memory; the first 32 travel into the ring slot
+struct Step2 {            // 48 bytes in global memory, written by the host's step planner
     unsigned out;         // the node's CL buffer: (address - hdr.arena) / 256 bytes
     unsigned flags;       // bits 0-1 children (1..2) | kStepFirst | kStepStore | kind of child 0 << 4 | kind of child 1 << 6 | kStepPush | kStepPfLate
                           //   kind 0 internal child, loaded from its buffer now; 1 internal child in registers (previous step);
@@ -78,20 +78,82 @@ struct TreeArgs2 {
     TreeHdr2 hdr[kMaxBatchTrees];
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
-
-// Shared memory of one CTA: the step list [nSteps] x 48 B, ring slots [operands of child 0 | operands of child 1],
-// the mbarriers full[kRing], the slot counters, the per-thread buffers [KT][CW*32] double2, the root reduction's scratch.
+// Shared memory of one CTA (all offsets multiples of 16 bytes):
+//   step digests [maxSteps] x 16 B | operand ring [kRing][2 children][ops] | per-thread buffers [KT][CW*32] double2 |
+//   category hand-over [CW*32] double2 | mbarriers full[kRing] | slot counters [kRing] | reduction scratch
+// A digest is what a warp needs of a step on its fast path: {out, pf, flags | nt0 << 16, nt1}; the rest of the record
+// (children loaded directly from global memory, node numbers for the operand copies) is read from global memory.
 __host__ __device__ inline size_t treeDna2OpsDoubles(int K, int W) { return (size_t)K * (W > 4 ? W : 4); }
+__host__ __device__ inline size_t treeDna2StepBytes(int maxSteps) { return ((size_t)maxSteps * 16 + 15) & ~(size_t)15; }
 __host__ inline size_t treeDna2SmemBytes(int nCat, int W, int CT, int CW, int maxSteps)
 {
     const int K = nCat * 4;
-    return (size_t)maxSteps * sizeof(Step2) + kRing * 2 * treeDna2OpsDoubles(K, W) * 8 + kRing * 8 + kRing * 4 + 8 /* align */ +
-           (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 + (2 * CW + 2) * 8;
+    return treeDna2StepBytes(maxSteps) + kRing * 2 * treeDna2OpsDoubles(K, W) * 8 + (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 +
+           kRing * 8 + kRing * 4 + 16 + (2 * CW + 2) * 8;
+}
+
+__device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+
+// Factor contributed by one child to the 4 states of category `cat` (same association as kernels.cuh child_factor).
+//   KIND 1: the child's CL is in `cur` (rows c*4..c*4+3)      KIND 3: in the thread's shared-memory buffer
+//   KIND 2: leaf, table lookup with the two tip codes          KIND 0: in global memory at `mem` (row stride rs)
+template <int KIND, int CTH>
+__device__ __forceinline__ void child2(int c, int cat, const double *__restrict__ s, int W, unsigned cx, unsigned cy, const double2 *cur,
+                                       const double2 *buf, const double *__restrict__ mem, unsigned rs, double2 f[4])
+{
+    if (KIND == 2) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const int k = cat * 4 + s4;
+            f[s4].x = s[k * W + cx];
+            f[s4].y = s[k * W + cy];
+        }
+    } else {
+        double2 v0, v1, v2, v3;
+        if (KIND == 1) { v0 = cur[c * 4 + 0]; v1 = cur[c * 4 + 1]; v2 = cur[c * 4 + 2]; v3 = cur[c * 4 + 3]; }
+        else if (KIND == 3) { v0 = buf[(c * 4 + 0) * CTH]; v1 = buf[(c * 4 + 1) * CTH]; v2 = buf[(c * 4 + 2) * CTH]; v3 = buf[(c * 4 + 3) * CTH]; }
+        else {
+            v0 = ld2(mem + (size_t)(c * 4 + 0) * rs); v1 = ld2(mem + (size_t)(c * 4 + 1) * rs);
+            v2 = ld2(mem + (size_t)(c * 4 + 2) * rs); v3 = ld2(mem + (size_t)(c * 4 + 3) * rs);
+        }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const double2 p01 = lds2(s + cat * 16 + s4 * 4), p23 = lds2(s + cat * 16 + s4 * 4 + 2);
+            double2 sum;
+            sum.x = p01.x * v0.x;
+            sum.y = p01.x * v0.y;
+            sum.x = fma(p01.y, v1.x, sum.x);
+            sum.y = fma(p01.y, v1.y, sum.y);
+            sum.x = fma(p23.x, v2.x, sum.x);
+            sum.y = fma(p23.x, v2.y, sum.y);
+            sum.x = fma(p23.y, v3.x, sum.x);
+            sum.y = fma(p23.y, v3.y, sum.y);
+            f[s4] = sum;
+        }
+    }
+}
+
+// A first step with exactly two children -- nearly every step of a binary tree -- as straight-line code for one
+// combination of child kinds.
+template <int CT, int CTH, int K0, int K1>
+__device__ __forceinline__ void step2(bool store, double2 *cur, const double2 *buf, int opOff, const double *__restrict__ s0,
+                                      const double *__restrict__ s1, int W, unsigned code0, unsigned code1, unsigned rs, double *__restrict__ outp)
+{
+    const unsigned c0x = code0 & 0xffu, c0y = (code0 >> 8) & 0xffu, c1x = code1 & 0xffu, c1y = (code1 >> 8) & 0xffu;
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+        double2 f[4], g[4];
+        child2<K0, CTH>(c, opOff + c, s0, W, c0x, c0y, cur, buf, nullptr, rs, f);
+        child2<K1, CTH>(c, opOff + c, s1, W, c1x, c1y, cur, buf, nullptr, rs, g);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            double2 r;
+            r.x = f[s4].x * g[s4].x;      // (left child) * (sibling), the reference's order
+            r.y = f[s4].y * g[s4].y;
+            cur[c * 4 + s4] = r;
+            if (store) st2(outp + (size_t)(c * 4 + s4) * rs, r);
+        }
+    }
 }
 
 template <int NCAT, int CT, int CW, int MINB>
@@ -108,35 +170,37 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     extern __shared__ __align__(16) unsigned char smraw[];
     const int W = a.tblW;
     const int nSteps = hd.nSteps;
-    const size_t opsD = treeDna2OpsDoubles(K, W);
-    const size_t slotB = 2 * opsD * 8;
-    const uint4 *sSteps = reinterpret_cast<const uint4 *>(smraw);                  // [nSteps][3]
-    unsigned char *ring = smraw + (size_t)a.maxSteps * sizeof(Step2);
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kRing * slotB);
+    const unsigned opsD = (unsigned)treeDna2OpsDoubles(K, W);
+    const unsigned slotD = 2 * opsD;                                  // doubles per ring slot
+    uint4 *sSteps = reinterpret_cast<uint4 *>(smraw);                 // [nSteps] digests
+    double *ring = reinterpret_cast<double *>(smraw + treeDna2StepBytes(a.maxSteps));
+    double2 *bufAll = reinterpret_cast<double2 *>(ring + kRing * slotD);   // [KT][CTH]
+    double2 *sA = bufAll + KT * CTH;                                  // hand-over of the category sum between the warps of a pattern block
+    uint64_t *full = reinterpret_cast<uint64_t *>(sA + CTH);
     unsigned *cnt = reinterpret_cast<unsigned *>(full + kRing);
-    double2 *bufAll = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(cnt + kRing) + 15) & ~(uintptr_t)15);
-    double2 *sA = bufAll + (size_t)KT * CTH;           // hand-over of the category sum between the warps of a pattern block
-    double *sRed = reinterpret_cast<double *>(sA + CTH);   // [2][CW] + flag
+    double *sRed = reinterpret_cast<double *>(cnt + kRing + (kRing & 1) + 2);   // [2][CW] + flag, 8-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Step2 *gSteps = a.steps + hd.stepBase;
 
-    // one lane: the bulk copies of step j's operands into its ring slot, completing on the slot's mbarrier
+    // one lane: the bulk copies (TMA) of step j's operands into its ring slot, completing on the slot's mbarrier
     auto produce = [&](int j) {
-        const int slot = j % kRing;
-        const uint4 dA = sSteps[3 * j], dC = sSteps[3 * j + 2];
+        const int slot = j & (kRing - 1);
+        const unsigned flags = __ldg(&gSteps[j].flags), n0 = __ldg(&gSteps[j].n0), n1 = __ldg(&gSteps[j].n1);
         const unsigned pBytes = K * 4 * 8, tBytes = (unsigned)(K * W * 8);
-        const unsigned nc = dA.y & 3u, k0 = (dA.y >> 4) & 3u, k1 = (dA.y >> 6) & 3u;
+        const unsigned nc = flags & 3u, k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
         const unsigned b0 = k0 == 2u ? tBytes : pBytes, b1 = nc == 2u ? (k1 == 2u ? tBytes : pBytes) : 0u;
-        unsigned char *sl = ring + slot * slotB;
+        double *sl = ring + slot * slotD;
         mbar_expect_tx(full + slot, b0 + b1);
-        bulk_g2s(sl, k0 == 2u ? hd.tbl + a.tblNodeDoubles * dC.x : hd.Pdeck + a.pNodeDoubles * dC.x, b0, full + slot);
-        if (nc == 2u)
-            bulk_g2s(sl + opsD * 8, k1 == 2u ? hd.tbl + a.tblNodeDoubles * dC.y : hd.Pdeck + a.pNodeDoubles * dC.y, b1, full + slot);
+        bulk_g2s(sl, k0 == 2u ? hd.tbl + a.tblNodeDoubles * n0 : hd.Pdeck + a.pNodeDoubles * n0, b0, full + slot);
+        if (nc == 2u) bulk_g2s(sl + opsD, k1 == 2u ? hd.tbl + a.tblNodeDoubles * n1 : hd.Pdeck + a.pNodeDoubles * n1, b1, full + slot);
     };
 
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + hd.stepBase);
-        uint4 *dst = reinterpret_cast<uint4 *>(smraw);
-        for (int i = threadIdx.x; i < 3 * nSteps; i += CTH) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < nSteps; i += CTH) {
+            const uint4 dA = __ldg(reinterpret_cast<const uint4 *>(gSteps + i)), dB = __ldg(reinterpret_cast<const uint4 *>(gSteps + i) + 1);
+            // {out, pf, flags | tip row of the next step's child 0 << 16 (0xffff: none), ... child 1}
+            sSteps[i] = make_uint4(dA.x, dB.z, (dA.y & 0xffffu) | ((dB.x == kNone ? 0xffffu : dB.x) << 16), dB.y == kNone ? 0xffffu : dB.y);
+        }
         if (threadIdx.x == 0) {
             for (int i = 0; i < kRing; i++) { mbar_init(full + i, 1); cnt[i] = 0u; }
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -150,16 +214,15 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     const int pat = ((blockIdx.x * PB + pb) * 32 + lane) * 2;
     const bool active = pat < a.ps;
     const unsigned ps = (unsigned)a.ps;
-    // this thread's two patterns inside a CL buffer: element offset of row 0, and the row stride
-    size_t off;
-    unsigned rs;
-    if (a.tileLog == 0) { off = (size_t)pat; rs = ps; }
+    // this thread's two patterns inside a CL buffer: element offset of its first row, and the row stride (both < 2^31)
+    unsigned off, rs;
+    if (a.tileLog == 0) { off = (unsigned)pat; rs = ps; }
     else {
         const unsigned T = 1u << a.tileLog;
-        off = (size_t)(pat >> a.tileLog) * ((size_t)K << a.tileLog) + (pat & (T - 1u));
+        off = (unsigned)(pat >> a.tileLog) * ((unsigned)K << a.tileLog) + ((unsigned)pat & (T - 1u));
         rs = T;
     }
-    off += (size_t)(cg * KT) * rs;                           // first row of this thread's categories
+    off += (unsigned)(cg * KT) * rs;
     double2 *buf = bufAll + threadIdx.x;                     // [KT][CTH]: row stride CTH double2
     const int opOff = cg * CT;                               // first category of this thread inside a P deck / leaf table
 
@@ -173,9 +236,8 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         for (int k = 0; k < KT; k++) cp_async16(buf + k * CTH, cl + (size_t)k * rs);
         cp_async_commit();
     };
-    auto tipLoad = [&](unsigned row) -> unsigned {
-        return *reinterpret_cast<const unsigned short *>(a.tips + (size_t)row * ps + pat);
-    };
+    const uint8_t *tipBase = a.tips + pat;
+    auto tipLoad = [&](unsigned row) -> unsigned { return *reinterpret_cast<const unsigned short *>(tipBase + (size_t)row * ps); };
 
     unsigned next0 = 0u, next1 = 0u;
     if (active) {
@@ -184,82 +246,75 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         if (hd.pf0 != kNone) prefetch(hd.pf0);
     }
 
+    uint4 d = nSteps > 0 ? sSteps[0] : make_uint4(0u, 0u, 0u, 0u);
     for (int si = 0; si < nSteps; si++) {
-        const int slot = si % kRing;
-        mbar_wait(full + slot, (unsigned)(si / kRing) & 1u);
-        const unsigned char *sl = ring + slot * slotB;
-        const uint4 dA = sSteps[3 * si], dB = sSteps[3 * si + 1];
-        const unsigned flags = dA.y;
-        const unsigned nc = flags & 3u, k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
+        const int slot = si & (kRing - 1);
+        const unsigned flags = d.z & 0xffffu, pf = d.y;
         const unsigned code0 = next0, code1 = next1;
+        const unsigned k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
         if (active) {
-            next0 = dB.x != kNone ? tipLoad(dB.x) : 0u;      // in flight while this step computes
-            next1 = dB.y != kNone ? tipLoad(dB.y) : 0u;
+            const unsigned t0 = d.z >> 16, t1 = d.w;
+            next0 = t0 != 0xffffu ? tipLoad(t0) : 0u;        // in flight while this step computes
+            next1 = t1 != 0xffffu ? tipLoad(t1) : 0u;
+        }
+        double *outp = hd.arena + (size_t)d.x * 32 + off;
+        if (si + 1 < nSteps) d = sSteps[si + 1];             // the next step's digest, ahead of its use
+        mbar_wait(full + slot, (unsigned)(si / kRing) & 1u);
+        if (active) {
             if (k0 == 3u || k1 == 3u) cp_async_wait_all();   // a prefetched child has landed (a pushed one is already there)
-            if (dB.z != kNone && !(flags & kStepPfLate)) prefetch(dB.z);
-            const double *s0 = reinterpret_cast<const double *>(sl);
-            const double *s1 = s0 + opsD;
-            double *outp = hd.arena + (size_t)dA.x * 32 + off;
-            const double *m0 = hd.arena + (size_t)dA.z * 32 + off, *m1 = hd.arena + (size_t)dA.w * 32 + off;
-            const bool first = (flags & kStepFirst) != 0u, store = (flags & kStepStore) != 0u, push = (flags & kStepPush) != 0u;
-            const unsigned c0x = code0 & 0xffu, c0y = (code0 >> 8) & 0xffu, c1x = code1 & 0xffu, c1y = (code1 >> 8) & 0xffu;
+            if (pf != kNone && !(flags & kStepPfLate)) prefetch(pf);
+            const double *s0 = ring + slot * slotD, *s1 = s0 + opsD;
+            const bool store = (flags & kStepStore) != 0u, push = (flags & kStepPush) != 0u;
+            if ((flags & (3u | kStepFirst)) == (2u | kStepFirst) && k0 != 0u && k1 != 0u) {
+                switch (k0 * 4 + k1) {     // uniform across the warp
+                case 1 * 4 + 2: step2<CT, CTH, 1, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                case 2 * 4 + 1: step2<CT, CTH, 2, 1>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                case 1 * 4 + 3: step2<CT, CTH, 1, 3>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                case 3 * 4 + 1: step2<CT, CTH, 3, 1>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                case 2 * 4 + 3: step2<CT, CTH, 2, 3>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                case 3 * 4 + 2: step2<CT, CTH, 3, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                default: step2<CT, CTH, 2, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
+                }
+            } else {
+                // any other shape: one child, a continuation of a node with more than two children, children loaded
+                // straight from global memory -- kinds decided at run time
+                const unsigned nc = flags & 3u;
+                const bool first = (flags & kStepFirst) != 0u;
+                const double *m0 = hd.arena + (size_t)__ldg(&gSteps[si].c0) * 32 + off, *m1 = hd.arena + (size_t)__ldg(&gSteps[si].c1) * 32 + off;
+                const unsigned c0x = code0 & 0xffu, c0y = (code0 >> 8) & 0xffu, c1x = code1 & 0xffu, c1y = (code1 >> 8) & 0xffu;
 #pragma unroll
-            for (int c = 0; c < CT; c++) {
-                const int cat = opOff + c;
-                // factor of one child for the 4 states of this category (same association as kernels.cuh child_factor)
-                auto child = [&](unsigned kind, const double *__restrict__ s, unsigned cx, unsigned cy, const double *__restrict__ mem, double2 f[4]) {
-                    if (kind == 2u) {
+                for (int c = 0; c < CT; c++) {
+                    const int cat = opOff + c;
+                    double2 f[4];
+                    if (k0 == 2u) child2<2, CTH>(c, cat, s0, W, c0x, c0y, cur, buf, m0, rs, f);
+                    else if (k0 == 1u) child2<1, CTH>(c, cat, s0, W, c0x, c0y, cur, buf, m0, rs, f);
+                    else if (k0 == 3u) child2<3, CTH>(c, cat, s0, W, c0x, c0y, cur, buf, m0, rs, f);
+                    else child2<0, CTH>(c, cat, s0, W, c0x, c0y, cur, buf, m0, rs, f);
+                    if (!first) {
 #pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const int k = cat * 4 + s4;
-                            f[s4].x = s[k * W + cx];
-                            f[s4].y = s[k * W + cy];
-                        }
-                    } else {
-                        double2 v0 = cur[c * 4 + 0], v1 = cur[c * 4 + 1], v2 = cur[c * 4 + 2], v3 = cur[c * 4 + 3];
-                        if (kind == 3u) {
-                            v0 = buf[(c * 4 + 0) * CTH]; v1 = buf[(c * 4 + 1) * CTH]; v2 = buf[(c * 4 + 2) * CTH]; v3 = buf[(c * 4 + 3) * CTH];
-                        } else if (kind == 0u) {
-                            v0 = ld2(mem + (size_t)(c * 4 + 0) * rs); v1 = ld2(mem + (size_t)(c * 4 + 1) * rs);
-                            v2 = ld2(mem + (size_t)(c * 4 + 2) * rs); v3 = ld2(mem + (size_t)(c * 4 + 3) * rs);
-                        }
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const double2 p01 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4);
-                            const double2 p23 = *reinterpret_cast<const double2 *>(s + cat * 16 + s4 * 4 + 2);
-                            double2 sum;
-                            sum.x = p01.x * v0.x;
-                            sum.y = p01.x * v0.y;
-                            sum.x = fma(p01.y, v1.x, sum.x);
-                            sum.y = fma(p01.y, v1.y, sum.y);
-                            sum.x = fma(p23.x, v2.x, sum.x);
-                            sum.y = fma(p23.x, v2.y, sum.y);
-                            sum.x = fma(p23.y, v3.x, sum.x);
-                            sum.y = fma(p23.y, v3.y, sum.y);
-                            f[s4] = sum;
-                        }
+                        for (int s4 = 0; s4 < 4; s4++) { f[s4].x = cur[c * 4 + s4].x * f[s4].x; f[s4].y = cur[c * 4 + s4].y * f[s4].y; }
                     }
-                };
-                double2 f[4];
-                child(k0, s0, c0x, c0y, m0, f);
-                if (!first) {      // continuation of a node with more than two children: the running product is in cur
+                    if (nc == 2u) {
+                        double2 g[4];
+                        if (k1 == 2u) child2<2, CTH>(c, cat, s1, W, c1x, c1y, cur, buf, m1, rs, g);
+                        else if (k1 == 1u) child2<1, CTH>(c, cat, s1, W, c1x, c1y, cur, buf, m1, rs, g);
+                        else if (k1 == 3u) child2<3, CTH>(c, cat, s1, W, c1x, c1y, cur, buf, m1, rs, g);
+                        else child2<0, CTH>(c, cat, s1, W, c1x, c1y, cur, buf, m1, rs, g);
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) { f[s4].x = cur[c * 4 + s4].x * f[s4].x; f[s4].y = cur[c * 4 + s4].y * f[s4].y; }
-                }
-                if (nc == 2u) {
-                    double2 g[4];
-                    child(k1, s1, c1x, c1y, m1, g);
+                        for (int s4 = 0; s4 < 4; s4++) { f[s4].x *= g[s4].x; f[s4].y *= g[s4].y; }
+                    }
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) { f[s4].x *= g[s4].x; f[s4].y *= g[s4].y; }   // (left child) * (sibling), the reference's order
-                }
-#pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) {
-                    cur[c * 4 + s4] = f[s4];
-                    if (store) st2(outp + (size_t)(c * 4 + s4) * rs, f[s4]);
-                    if (push) buf[(c * 4 + s4) * CTH] = f[s4];
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        cur[c * 4 + s4] = f[s4];
+                        if (store) st2(outp + (size_t)(c * 4 + s4) * rs, f[s4]);
+                    }
                 }
             }
-            if (dB.z != kNone && (flags & kStepPfLate)) prefetch(dB.z);   // the buffer was in use by this step: refill it now
+            if (push) {      // a later step takes this node from the thread's shared-memory buffer
+#pragma unroll
+                for (int k = 0; k < KT; k++) buf[k * CTH] = cur[k];
+            }
+            if (pf != kNone && (flags & kStepPfLate)) prefetch(pf);   // the buffer was in use by this step: refill it now
         }
         // release the slot; the last warp to do so refills it with the operands of step si + kRing
         __syncwarp();
@@ -296,13 +351,13 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
 #pragma unroll
     for (int g = 0; g < CSPLIT; g++) {
         if (cg == g) {
-            if (g > 0) A = sA[pb * 32 * CSPLIT + lane];
+            if (g > 0) A = sA[pb * 32 + lane];
 #pragma unroll
             for (int k = 0; k < KT; k++) {
                 if ((mask0 >> (k & 3)) & 1ull) A.x = fma(hd.pi[k & 3], cur[k].x, A.x);
                 if ((mask1 >> (k & 3)) & 1ull) A.y = fma(hd.pi[k & 3], cur[k].y, A.y);
             }
-            if (g < CSPLIT - 1) sA[pb * 32 * CSPLIT + lane] = A;
+            if (g < CSPLIT - 1) sA[pb * 32 + lane] = A;
         }
         if (g < CSPLIT - 1) named_barrier(1, CTH);
     }
@@ -345,7 +400,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         }
         t = warpSum(t);
         b = warpSum(b);
-        named_barrier(1, CTH);          // sRed is read above by thread 0 only, before the previous barrier
+        named_barrier(1, CTH);          // sRed was read by thread 0 before the previous barrier
         if (lane == 0) { sRed[warp] = t; sRed[CW + warp] = b; }
         named_barrier(1, CTH);
         if (threadIdx.x == 0) {

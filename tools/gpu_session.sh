@@ -18,14 +18,14 @@ run_one() {
       timeout 900 python bench.py "$@" > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; tail -c 2500 gpurun_out/bench_$TAG.json ;;
     sizes)
       for n in 1000000 250000 125000; do
-        timeout 300 python bench.py --patterns $n --steps 100 --warmup 5 --no-cpu-baseline "$@" 2>/dev/null | tail -1 > gpurun_out/bench_${TAG}_$n.json
+        timeout 300 python bench.py --patterns $n --steps 100 --warmup 5 --no-cpu-baseline --no-configs "$@" 2>/dev/null | tail -1 > gpurun_out/bench_${TAG}_$n.json
         python -c "
 import json,sys
 d=json.load(open('gpurun_out/bench_${TAG}_$n.json'))
 print($n, 'evals/s %.1f ms %.4f cl_ms %.4f e2e %.1f' % (d['value'], d['ms_per_step'], d['roofline'].get('cl_ms_per_eval', 0), d['e2e']['value']), d.get('clocks'))"
       done ;;
     launches)
-      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline "$@" > /dev/null 2>&1; echo "launches rc=$?" ;;
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-configs "$@" > /dev/null 2>&1; echo "launches rc=$?" ;;
     prof)
       regex=$1; skip=$2; tag=$3; shift 3
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip $skip -c 1 -o gpurun_out/prof_$tag "$@" > gpurun_out/prof_$tag.log 2>&1; echo "prof $tag rc=$?" ;;
