@@ -816,11 +816,20 @@ void setDeferEnabled(int on) { g_deferCL = on != 0; }
 static bool g_fusedAAEnabled = true;
 void setFusedAAEnabled(int on) { g_fusedAAEnabled = on != 0; }
 
-// Parts the whole-tree kernels serve: 4 states (FMA kernel), 20 states with 4 categories (tensor-core kernel).
+// second-generation 4-state kernel in use?  (P4B_FUSED2=0 or a forced first-generation launch shape switch it off)
+static int g_fusedVariant = -1;   // p4b_setFusedVariant: -1 = by shard size
+static bool g_fused2On()
+{
+    static int env2 = -1;
+    if (env2 < 0) { const char *e = getenv("P4B_FUSED2"); env2 = e ? atoi(e) != 0 : 1; }
+    return env2 && !(g_fusedVariant >= 0 && g_fusedVariant < 10);
+}
+
+// Parts the whole-tree kernels serve: 4 states (FMA kernels), 20 states with 4 categories and 21..64 states (tensor-core kernels).
 static bool fusedEligible(const PartLayout &L)
 {
     if (!g_fusedEnabled) return false;
-    if (L.dim == 4) return L.nCat == 4 || L.nCat == 1;
+    if (L.dim == 4) return L.nCat == 4 || L.nCat == 1 || (!L.scalers && L.nCat >= 2 && L.nCat <= 8 && g_fused2On());
     if (L.dim == 20) return g_fusedAAEnabled && g_dmmaEnabled && L.nCat == 4 && !L.scalers && L.W <= 64;
     if (L.dim > 20 && L.dim <= 64)    // two children x two buffers of max(P^T fragments, transposed leaf table) must fit shared memory
         return g_fusedAAEnabled && g_dmmaEnabled && !L.scalers && L.auxDP > 0 && L.nCat <= 64 &&
@@ -841,13 +850,21 @@ static int launchCL(const CLArgs &a)
 {
     if (flushPJobs()) return 1;
     const int maxPer = a.dim * (a.tblW > a.dim ? a.tblW : a.dim);
-    if (a.dim == 4 && (a.nCat == 4 || a.nCat == 1)) {
+    if (a.dim == 4 && a.nCat >= 1 && a.nCat <= 8) {
         const int K = a.nCat * 4;
         const size_t sm = (size_t)a.nChildren * K * (a.tblW > 4 ? a.tblW : 4) * sizeof(double);
         const int pairs = a.ps / 2;
         const dim3 grid((pairs + 255) / 256);
-        if (a.nCat == 4) cl_dna_kernel<4><<<grid, 256, sm, G.stream>>>(a);
-        else cl_dna_kernel<1><<<grid, 256, sm, G.stream>>>(a);
+        switch (a.nCat) {
+        case 1: cl_dna_kernel<1><<<grid, 256, sm, G.stream>>>(a); break;
+        case 2: cl_dna_kernel<2><<<grid, 256, sm, G.stream>>>(a); break;
+        case 3: cl_dna_kernel<3><<<grid, 256, sm, G.stream>>>(a); break;
+        case 4: cl_dna_kernel<4><<<grid, 256, sm, G.stream>>>(a); break;
+        case 5: cl_dna_kernel<5><<<grid, 256, sm, G.stream>>>(a); break;
+        case 6: cl_dna_kernel<6><<<grid, 256, sm, G.stream>>>(a); break;
+        case 7: cl_dna_kernel<7><<<grid, 256, sm, G.stream>>>(a); break;
+        default: cl_dna_kernel<8><<<grid, 256, sm, G.stream>>>(a); break;
+        }
     } else if (a.dim == 20 && g_dmmaEnabled && dmmaSmemBytes(a) <= 200 * 1024) {
         static bool attrSet = false;
         if (!attrSet) {
@@ -1002,7 +1019,6 @@ struct FusedJob {
 // 2.70 / 2.82 / 3.21, 250 k 1.56 / 1.42 / 1.65, 125 k 0.99 / 0.90 / 0.86.  What decides is how many waves
 // of 128-thread CTAs the launch makes: the last, partial wave leaves SMs idle unless the CTAs are small.
 // P4B_FUSED_VARIANT overrides the choice (tuning).
-static int g_fusedVariant = -1;   // p4b_setFusedVariant: -1 = by shard size
 int setFusedVariant(int v)
 {
     if (v < -1 || (v > 8 && v < 10) || v > 16) { setError("p4b_setFusedVariant: launch shape %d does not exist (-1, 0..8, 10..16)", v); return 1; }
@@ -1300,21 +1316,44 @@ static const Shape2 kShapes2[] = {
     {4, 4, 3},    // 10: 128 threads x 3
     {4, 2, 6},    // 11:  64 threads x 6
     {4, 1, 12},   // 12:  32 threads x 12
-    {2, 4, 5},    // 13: categories split over 2 warps, 128 threads x 5
-    {2, 2, 10},   // 14:  64 threads x 10
+    {2, 4, 4},    // 13: categories split over 2 warps, 128 threads x 4
+    {2, 2, 8},    // 14:  64 threads x 8
     {1, 4, 6},    // 15: one category per warp, 128 threads x 6
     {2, 8, 2},    // 16: 256 threads x 2
 };
 constexpr int kNumShapes2 = (int)(sizeof(kShapes2) / sizeof(kShapes2[0]));
 typedef void (*Kernel2Fn)(const TreeArgs2);
+// Rate-category counts other than 1 and 4 (the reference is generic in nCat, Pf/p4_node.c:652-654): one shape each,
+// with the categories split over warps where that keeps a thread at four categories or fewer.
+static bool shapeForNCat(int nCat, Shape2 *sh)
+{
+    switch (nCat) {
+    case 2: *sh = {2, 4, 4}; return true;
+    case 3: *sh = {3, 4, 3}; return true;
+    case 5: *sh = {1, 5, 4}; return true;
+    case 6: *sh = {3, 4, 3}; return true;
+    case 7: *sh = {1, 7, 3}; return true;
+    case 8: *sh = {4, 4, 3}; return true;
+    default: return false;
+    }
+}
 static Kernel2Fn kernel2For(int nCat, int shape)
 {
     static const Kernel2Fn k4[kNumShapes2] = {cl_tree_dna2_kernel<4, 4, 4, 3>, cl_tree_dna2_kernel<4, 4, 2, 6>, cl_tree_dna2_kernel<4, 4, 1, 12>,
-                                              cl_tree_dna2_kernel<4, 2, 4, 5>, cl_tree_dna2_kernel<4, 2, 2, 10>, cl_tree_dna2_kernel<4, 1, 4, 6>,
+                                              cl_tree_dna2_kernel<4, 2, 4, 4>, cl_tree_dna2_kernel<4, 2, 2, 8>, cl_tree_dna2_kernel<4, 1, 4, 6>,
                                               cl_tree_dna2_kernel<4, 2, 8, 2>};
     static const Kernel2Fn k1[3] = {cl_tree_dna2_kernel<1, 1, 4, 4>, cl_tree_dna2_kernel<1, 1, 2, 8>, cl_tree_dna2_kernel<1, 1, 1, 16>};
-    if (nCat == 4) return k4[shape];
-    return k1[shape < 3 ? shape : 0];
+    switch (nCat) {
+    case 4: return k4[shape];
+    case 1: return k1[shape < 3 ? shape : 0];
+    case 2: return cl_tree_dna2_kernel<2, 2, 4, 4>;
+    case 3: return cl_tree_dna2_kernel<3, 3, 4, 3>;
+    case 5: return cl_tree_dna2_kernel<5, 1, 5, 4>;
+    case 6: return cl_tree_dna2_kernel<6, 3, 4, 3>;
+    case 7: return cl_tree_dna2_kernel<7, 1, 7, 3>;
+    case 8: return cl_tree_dna2_kernel<8, 4, 4, 3>;
+    default: return nullptr;
+    }
 }
 
 static int fused2Shape(int ps, int nTrees)
@@ -1382,7 +1421,8 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     a.eqMask = dp->dev.equateMask;
     if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
     const int shape = fused2Shape(L.ps, nJobs);
-    const Shape2 sh = L.nCat == 4 ? kShapes2[shape] : Shape2{1, shape == 0 ? 4 : (shape == 1 ? 2 : 1), shape == 0 ? 4 : (shape == 1 ? 8 : 16)};
+    Shape2 sh = L.nCat == 4 ? kShapes2[shape] : Shape2{1, shape == 0 ? 4 : (shape == 1 ? 2 : 1), shape == 0 ? 4 : (shape == 1 ? 8 : 16)};
+    if (L.nCat != 4 && L.nCat != 1 && !shapeForNCat(L.nCat, &sh)) { setError("internal: no whole-tree kernel for %d rate categories", L.nCat); return 1; }
     const int csplit = L.nCat / sh.ct;
     const int patsPerCta = (sh.cw / csplit) * 64;
     const int blocks = (L.ps + patsPerCta - 1) / patsPerCta;
@@ -1559,10 +1599,8 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     if (nJobs < 1 || nJobs > kMaxBatchTrees) { setError("internal: bad batch size %d", nJobs); return 1; }
     {
         const PartLayout &L0 = jobs[0].t->dev->parts[p];
-        static int env2 = -1;
-        if (env2 < 0) { const char *e = getenv("P4B_FUSED2"); env2 = e ? atoi(e) != 0 : 1; }
-        const bool oldForced = g_fusedVariant >= 0 && g_fusedVariant < 10;
-        if (L0.dim == 4 && !L0.scalers && g_fused2 && env2 && !oldForced) return launchFused2Batch(jobs, nJobs, p, resultDev);
+        if (L0.dim == 4 && !L0.scalers && g_fused2 && g_fused2On()) return launchFused2Batch(jobs, nJobs, p, resultDev);
+        if (L0.dim == 4 && L0.nCat != 4 && L0.nCat != 1) { setError("internal: the first-generation whole-tree kernel serves 1 or 4 rate categories"); return 1; }
         if (L0.dim > 20) return launchFusedDmmaBatch(jobs, nJobs, p, resultDev);
     }
     if (flushPJobs()) return 1;

@@ -12,10 +12,10 @@
 //   * the tree's whole step list, pre-decoded by the host (48 bytes per step), is copied into shared memory
 //     once, in the prologue: a step's descriptor is two 16-byte shared-memory loads;
 //   * the operands of a step's (at most two) children -- P decks, leaf tables -- arrive in a ring of kRing
-//     slots by bulk copies (TMA, cp.async.bulk) that complete on the slot's mbarrier.  Nobody is a dedicated
-//     producer: the LAST warp to finish step s (a shared-memory counter per slot) issues the copies of step
-//     s + kRing into the slot it has just freed.  Warps wait on the slot's mbarrier only (try_wait, normally
-//     already satisfied) and drift up to kRing - 1 steps apart: no CTA barrier inside the step loop.
+//     slots PER WARP by bulk copies (TMA, cp.async.bulk) that complete on the slot's mbarrier: a warp that has
+//     finished step s issues the copies of step s + kRing into the slot it has just freed and waits on its own
+//     mbarriers only (try_wait, normally already satisfied).  No barrier, no atomic, no other warp inside the
+//     step loop: the warps of a CTA drift freely.
 // The one internal child of a step that is not in registers comes from a per-thread shared-memory buffer that
 // the host's step planner fills in one of two ways: the producing step PUSHES its result there (no global
 // re-read at all; short-lived siblings), or the thread PREFETCHES it from its own earlier global store with
@@ -29,7 +29,7 @@
 namespace p4b {
 
 constexpr unsigned kNone = 0xffffffffu;
-constexpr int kRing = 4;          // operand ring: steps whose P decks / leaf tables can be in flight ahead of a warp
+constexpr int kRing = 3;          // operand ring of a warp: the current step's P decks / leaf tables and those of the next two
 
 // flags of a step
 constexpr unsigned kStepFirst = 4u, kStepStore = 8u, kStepPush = 256u, kStepPfLate = 512u;
@@ -79,17 +79,19 @@ struct TreeArgs2 {
 };
 
 // Shared memory of one CTA (all offsets multiples of 16 bytes):
-//   step digests [maxSteps] x 16 B | operand ring [kRing][2 children][ops] | per-thread buffers [KT][CW*32] double2 |
-//   category hand-over [CW*32] double2 | mbarriers full[kRing] | slot counters [kRing] | reduction scratch
+//   step digests [maxSteps] x 16 B, node numbers of the children [maxSteps] x 8 B | per warp: operand ring [kRing][2 children][ops] | per-thread buffers [KT][CW*32] double2 |
+//   category hand-over [CW*32] double2 | per warp: mbarriers full[kRing] | reduction scratch
 // A digest is what a warp needs of a step on its fast path: {out, pf, flags | nt0 << 16, nt1}; the rest of the record
 // (children loaded directly from global memory, node numbers for the operand copies) is read from global memory.
+// Every warp has a ring of its OWN: it issues the bulk copies of step s + kRing into the slot it has just finished
+// with, and waits on its own mbarriers only -- the warps of a CTA never wait for one another inside the step loop.
 __host__ __device__ inline size_t treeDna2OpsDoubles(int K, int W) { return (size_t)K * (W > 4 ? W : 4); }
-__host__ __device__ inline size_t treeDna2StepBytes(int maxSteps) { return ((size_t)maxSteps * 16 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t treeDna2StepBytes(int maxSteps) { return ((size_t)maxSteps * 24 + 15) & ~(size_t)15; }   // 16-byte digest + the two node numbers
 __host__ inline size_t treeDna2SmemBytes(int nCat, int W, int CT, int CW, int maxSteps)
 {
     const int K = nCat * 4;
-    return treeDna2StepBytes(maxSteps) + kRing * 2 * treeDna2OpsDoubles(K, W) * 8 + (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 +
-           kRing * 8 + kRing * 4 + 16 + (2 * CW + 2) * 8;
+    return treeDna2StepBytes(maxSteps) + (size_t)CW * kRing * 2 * treeDna2OpsDoubles(K, W) * 8 + (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 +
+           (size_t)CW * kRing * 8 + 16 + (2 * CW + 2) * 8;
 }
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
@@ -172,20 +174,22 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     const int nSteps = hd.nSteps;
     const unsigned opsD = (unsigned)treeDna2OpsDoubles(K, W);
     const unsigned slotD = 2 * opsD;                                  // doubles per ring slot
-    uint4 *sSteps = reinterpret_cast<uint4 *>(smraw);                 // [nSteps] digests
-    double *ring = reinterpret_cast<double *>(smraw + treeDna2StepBytes(a.maxSteps));
-    double2 *bufAll = reinterpret_cast<double2 *>(ring + kRing * slotD);   // [KT][CTH]
+    uint4 *sSteps = reinterpret_cast<uint4 *>(smraw);                 // [maxSteps] digests
+    uint2 *sNodes = reinterpret_cast<uint2 *>(sSteps + a.maxSteps);   // [maxSteps] node numbers of the children (operand addresses)
+    double *ringAll = reinterpret_cast<double *>(smraw + treeDna2StepBytes(a.maxSteps));
+    double2 *bufAll = reinterpret_cast<double2 *>(ringAll + (size_t)CW * kRing * slotD);   // [KT][CTH]
     double2 *sA = bufAll + KT * CTH;                                  // hand-over of the category sum between the warps of a pattern block
-    uint64_t *full = reinterpret_cast<uint64_t *>(sA + CTH);
-    unsigned *cnt = reinterpret_cast<unsigned *>(full + kRing);
-    double *sRed = reinterpret_cast<double *>(cnt + kRing + (kRing & 1) + 2);   // [2][CW] + flag, 8-byte aligned
+    uint64_t *fullAll = reinterpret_cast<uint64_t *>(sA + CTH);
+    double *sRed = reinterpret_cast<double *>(fullAll + CW * kRing + 2);   // [2][CW] + flag
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Step2 *gSteps = a.steps + hd.stepBase;
+    double *ring = ringAll + (size_t)warp * kRing * slotD;            // this warp's operand ring
+    uint64_t *full = fullAll + warp * kRing;                          // ... and its mbarriers
 
-    // one lane: the bulk copies (TMA) of step j's operands into its ring slot, completing on the slot's mbarrier
-    auto produce = [&](int j) {
-        const int slot = j & (kRing - 1);
-        const unsigned flags = __ldg(&gSteps[j].flags), n0 = __ldg(&gSteps[j].n0), n1 = __ldg(&gSteps[j].n1);
+    // one lane: the bulk copies (TMA) of step j's operands into the warp's ring slot `slot`, completing on that slot's mbarrier
+    auto produce = [&](int j, int slot) {
+        const unsigned flags = sSteps[j].z;
+        const uint2 nn = sNodes[j];
+        const unsigned n0 = nn.x, n1 = nn.y;
         const unsigned pBytes = K * 4 * 8, tBytes = (unsigned)(K * W * 8);
         const unsigned nc = flags & 3u, k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
         const unsigned b0 = k0 == 2u ? tBytes : pBytes, b1 = nc == 2u ? (k1 == 2u ? tBytes : pBytes) : 0u;
@@ -196,19 +200,21 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     };
 
     {
+        const Step2 *gSteps = a.steps + hd.stepBase;
         for (int i = threadIdx.x; i < nSteps; i += CTH) {
             const uint4 dA = __ldg(reinterpret_cast<const uint4 *>(gSteps + i)), dB = __ldg(reinterpret_cast<const uint4 *>(gSteps + i) + 1);
             // {out, pf, flags | tip row of the next step's child 0 << 16 (0xffff: none), ... child 1}
             sSteps[i] = make_uint4(dA.x, dB.z, (dA.y & 0xffffu) | ((dB.x == kNone ? 0xffffu : dB.x) << 16), dB.y == kNone ? 0xffffu : dB.y);
+            sNodes[i] = make_uint2(__ldg(&gSteps[i].n0), __ldg(&gSteps[i].n1));
         }
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < kRing; i++) { mbar_init(full + i, 1); cnt[i] = 0u; }
+        if (lane == 0) {
+            for (int i = 0; i < kRing; i++) mbar_init(full + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (int j = 0; j < kRing && j < nSteps; j++) produce(j);
+    if (lane == 0)
+        for (int j = 0; j < kRing && j < nSteps; j++) produce(j, j);
 
     const int cg = warp % CSPLIT, pb = warp / CSPLIT;       // category group, pattern block of this warp
     const int pat = ((blockIdx.x * PB + pb) * 32 + lane) * 2;
@@ -236,8 +242,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         for (int k = 0; k < KT; k++) cp_async16(buf + k * CTH, cl + (size_t)k * rs);
         cp_async_commit();
     };
-    const uint8_t *tipBase = a.tips + pat;
-    auto tipLoad = [&](unsigned row) -> unsigned { return *reinterpret_cast<const unsigned short *>(tipBase + (size_t)row * ps); };
+    auto tipLoad = [&](unsigned row) -> unsigned { return *reinterpret_cast<const unsigned short *>(a.tips + ((size_t)row * ps + (unsigned)pat)); };
 
     unsigned next0 = 0u, next1 = 0u;
     if (active) {
@@ -247,8 +252,9 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     }
 
     uint4 d = nSteps > 0 ? sSteps[0] : make_uint4(0u, 0u, 0u, 0u);
+    int slot = 0;
+    unsigned parity = 0u;
     for (int si = 0; si < nSteps; si++) {
-        const int slot = si & (kRing - 1);
         const unsigned flags = d.z & 0xffffu, pf = d.y;
         const unsigned code0 = next0, code1 = next1;
         const unsigned k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
@@ -257,10 +263,11 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             next0 = t0 != 0xffffu ? tipLoad(t0) : 0u;        // in flight while this step computes
             next1 = t1 != 0xffffu ? tipLoad(t1) : 0u;
         }
-        double *outp = hd.arena + (size_t)d.x * 32 + off;
+        const unsigned outCode = d.x;
         if (si + 1 < nSteps) d = sSteps[si + 1];             // the next step's digest, ahead of its use
-        mbar_wait(full + slot, (unsigned)(si / kRing) & 1u);
+        mbar_wait(full + slot, parity);
         if (active) {
+            double *outp = hd.arena + (size_t)outCode * 32 + off;
             if (k0 == 3u || k1 == 3u) cp_async_wait_all();   // a prefetched child has landed (a pushed one is already there)
             if (pf != kNone && !(flags & kStepPfLate)) prefetch(pf);
             const double *s0 = ring + slot * slotD, *s1 = s0 + opsD;
@@ -280,7 +287,8 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
                 // straight from global memory -- kinds decided at run time
                 const unsigned nc = flags & 3u;
                 const bool first = (flags & kStepFirst) != 0u;
-                const double *m0 = hd.arena + (size_t)__ldg(&gSteps[si].c0) * 32 + off, *m1 = hd.arena + (size_t)__ldg(&gSteps[si].c1) * 32 + off;
+                const Step2 *gs = a.steps + hd.stepBase + si;
+                const double *m0 = hd.arena + (size_t)__ldg(&gs->c0) * 32 + off, *m1 = hd.arena + (size_t)__ldg(&gs->c1) * 32 + off;
                 const unsigned c0x = code0 & 0xffu, c0y = (code0 >> 8) & 0xffu, c1x = code1 & 0xffu, c1y = (code1 >> 8) & 0xffu;
 #pragma unroll
                 for (int c = 0; c < CT; c++) {
@@ -316,18 +324,13 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             }
             if (pf != kNone && (flags & kStepPfLate)) prefetch(pf);   // the buffer was in use by this step: refill it now
         }
-        // release the slot; the last warp to do so refills it with the operands of step si + kRing
+        // the warp is done with the slot: refill it with the operands of step si + kRing
         __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            if (atomicAdd(cnt + slot, 1u) == (unsigned)(CW - 1)) {
-                cnt[slot] = 0u;
-                if (si + kRing < nSteps) {
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warps' reads of the slot precede the bulk copy's writes
-                    produce(si + kRing);
-                }
-            }
+        if (lane == 0 && si + kRing < nSteps) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warp's reads of the slot precede the bulk copy's writes
+            produce(si + kRing, slot);
         }
+        if (++slot == kRing) { slot = 0; parity ^= 1u; }
     }
 
     if (!hd.doLike) return;

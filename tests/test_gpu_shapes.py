@@ -215,3 +215,43 @@ def test_cfg5_shape_batched_eight_trees(pkg, ref_pf):
         base.deleteCStuff()
         base.model.free()
         base.data.free()
+
+
+# ---- any number of rate categories (the reference is generic in nCat, Pf/p4_node.c:652-654) -----------------------
+@pytest.mark.parametrize("nCat", [2, 3, 5, 6, 7, 8])
+def test_dna_whole_tree_kernel_any_ncat(pkg, ref_pf, nCat):
+    P, H, pf = pkg, pkg.host, pkg.pf
+    rng = np.random.Generator(np.random.PCG64(800 + nCat))
+    tree = P.synth.random_tree(pf, 14, rng)
+    mp = P.synth.dna_model_part(0, rng, nCat, pInvar=0.1 if nCat % 2 else 0.0)
+    aln = P.synth.make_alignment(pf, tree, mp, 1500, rng, "dna", gap_frac=0.02, ambig_frac=0.02)
+    tree.attach(H.Data(pf, [aln]), H.Model(pf, [mp]))
+    twin = H.clone_tree(tree, ref_pf)
+    want = twin.calcLogLike()
+    got = tree.calcLogLike()
+    assert pf.lastCLKernelName().startswith("cl_tree_dna2_kernel<%d," % nCat), pf.lastCLKernelName()
+    assert rel(got, want) <= 1e-9
+    rp = ref_peek.part_arrays(twin.data.parts[0].cPart)
+    for a, b in zip(tree.nodes, twin.nodes):
+        if a.isLeaf:
+            continue
+        c1 = pf.getNodeCL(tree.cTree, a.cNode, 0, nCat, 4)
+        c0 = ref_peek.node_cl(b.cNode, 0, nCat, 4, rp["nChar"], rp["nPatterns"])
+        scale = np.max(np.abs(c0), axis=(0, 1), keepdims=True)
+        assert np.max(np.abs(c1 - c0) / scale) <= 1e-9
+    # the per-node kernels (cl_dna_kernel<nCat>) leave the same CLs, bit for bit
+    whole = [pf.getNodeCL(tree.cTree, a.cNode, 0, nCat, 4) for a in tree.nodes if not a.isLeaf]
+    pf.setFusedTreeKernel(0)
+    try:
+        perNode = tree.calcLogLike()
+        for a, w in zip([a for a in tree.nodes if not a.isLeaf], whole):
+            assert np.array_equal(pf.getNodeCL(tree.cTree, a.cNode, 0, nCat, 4), w)
+    finally:
+        pf.setFusedTreeKernel(1)
+    assert rel(perNode, got) <= 1e-13
+    # a dirty path through the queue
+    for t in (tree, twin):
+        n = [x for x in t.iterNodesNoRoot()][5]
+        n.br.len *= 1.7
+        n.br.lenChanged = True
+    assert rel(tree.recalcAfterBranchChange(), twin.recalcAfterBranchChange()) <= 1e-9
