@@ -5,10 +5,12 @@
 // without it (and shares the copy PyTorch has already loaded when the host
 // program uses torch.distributed for its rendezvous).  The reference has no
 // counterpart: it is a single process.
+#include <cuda_runtime.h>
 #include <dlfcn.h>
 
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "engine.h"
 
@@ -20,6 +22,7 @@ typedef void *Comm;
 typedef int (*GetUniqueIdFn)(UniqueId *);
 typedef int (*CommInitRankFn)(Comm *, int, UniqueId, int);
 typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, Comm, void *);
+typedef int (*AllGatherFn)(const void *, void *, size_t, int, Comm, void *);
 typedef int (*CommDestroyFn)(Comm);
 typedef const char *(*GetErrorStringFn)(int);
 
@@ -28,6 +31,7 @@ struct Nccl {
     GetUniqueIdFn getUniqueId = nullptr;
     CommInitRankFn commInitRank = nullptr;
     AllReduceFn allReduce = nullptr;
+    AllGatherFn allGather = nullptr;
     CommDestroyFn commDestroy = nullptr;
     GetErrorStringFn errorString = nullptr;
     Comm comm = nullptr;
@@ -35,7 +39,9 @@ struct Nccl {
 } N;
 
 const int kNcclDouble = 8;   // ncclFloat64
+const int kNcclChar = 0;     // ncclInt8
 const int kNcclSum = 0;
+const int kNcclMin = 3;
 
 int load()
 {
@@ -50,6 +56,7 @@ int load()
     N.getUniqueId = (GetUniqueIdFn)dlsym(N.lib, "ncclGetUniqueId");
     N.commInitRank = (CommInitRankFn)dlsym(N.lib, "ncclCommInitRank");
     N.allReduce = (AllReduceFn)dlsym(N.lib, "ncclAllReduce");
+    N.allGather = (AllGatherFn)dlsym(N.lib, "ncclAllGather");
     N.commDestroy = (CommDestroyFn)dlsym(N.lib, "ncclCommDestroy");
     N.errorString = (GetErrorStringFn)dlsym(N.lib, "ncclGetErrorString");
     if (!N.getUniqueId || !N.commInitRank || !N.allReduce || !N.commDestroy) {
@@ -104,6 +111,49 @@ int commDestroy()
 }
 
 bool commActive() { return N.comm != nullptr && N.world > 1; }
+int commWorld() { return N.comm ? N.world : 1; }
+
+// Peer mailboxes for the in-kernel all-reduce of the partial log-likelihoods (csrc/tree.cu): every rank's mailbox is
+// opened on every other rank through CUDA IPC, the 64-byte handles travelling by one ncclAllGather.  peers[r] receives
+// the address of rank r's mailbox as this process sees it (its own for r == rank).  Returns 0 when EVERY rank succeeded
+// (agreed by an all-reduce of the outcome), 1 otherwise -- then nobody uses the mailboxes and NCCL stays in charge.
+int commOpenPeerMailboxes(void *mine, int rank, void **peers, void *cudaStream)
+{
+    if (!N.comm || !N.allGather) return 1;
+    const int world = N.world;
+    cudaStream_t st = (cudaStream_t)cudaStream;
+    int ok = 1;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (cudaIpcGetMemHandle(&h, mine) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    char *dBuf = nullptr;
+    if (cudaMalloc(&dBuf, sizeof(h) * (size_t)(world + 1) + sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 1; }
+    std::vector<cudaIpcMemHandle_t> all(world);
+    // every rank takes part in both collectives whatever its own outcome so far, so that nobody is left waiting
+    cudaMemcpyAsync(dBuf, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+    if (N.allGather(dBuf, dBuf + sizeof(h), sizeof(h), kNcclChar, N.comm, st) != 0) ok = 0;
+    cudaMemcpyAsync(all.data(), dBuf + sizeof(h), sizeof(h) * world, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok)
+        for (int r = 0; r < world; r++) {
+            if (r == rank) { peers[r] = mine; continue; }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            peers[r] = p;
+        }
+    double flag = ok ? 1.0 : 0.0, *dFlag = reinterpret_cast<double *>(dBuf + sizeof(h) * (size_t)(world + 1));
+    cudaMemcpyAsync(dFlag, &flag, sizeof(double), cudaMemcpyHostToDevice, st);
+    if (N.allReduce(dFlag, dFlag, 1, kNcclDouble, kNcclMin, N.comm, st) != 0) flag = 0.0;
+    else cudaMemcpyAsync(&flag, dFlag, sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); flag = 0.0; }
+    cudaFree(dBuf);
+    return flag > 0.5 ? 0 : 1;
+}
+void commClosePeerMailboxes(int rank, void **peers)
+{
+    for (int r = 0; r < N.world; r++)
+        if (r != rank && peers[r]) { cudaIpcCloseMemHandle(peers[r]); peers[r] = nullptr; }
+}
 
 int commAllReduceSum(double *devBuf, int count, void *cudaStream)
 {

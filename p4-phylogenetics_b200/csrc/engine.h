@@ -189,6 +189,7 @@ long long treeDeviceBytes(Tree *t);
 int treeFlushL2(Tree *t);
 int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
+void engineMailShutdown();
 void setFusedEnabled(int on);
 int setFusedVariant(int v);
 const char *lastCLKernelName();
@@ -218,6 +219,9 @@ int commGetUniqueId(char id128[128]);
 int commInitRank(const char id128[128], int rank, int world);
 int commDestroy();
 bool commActive();
+int commWorld();
+int commOpenPeerMailboxes(void *mine, int rank, void **peers, void *cudaStream);
+void commClosePeerMailboxes(int rank, void **peers);
 int commAllReduceSum(double *devBuf, int count, void *cudaStream);
 
 }  // namespace p4b

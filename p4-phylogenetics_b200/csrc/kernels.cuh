@@ -234,6 +234,49 @@ __device__ __forceinline__ double warpSum(double v)
     return v;
 }
 
+// ---------------------------------------------------------------------------
+// In-kernel all-reduce of (partial lnL, count of non-positive likelihoods) across the pattern shards of a multi-GPU run
+// (the path's one exchange step).  Every rank owns a small mailbox in its HBM that every other rank has
+// mapped through CUDA IPC (csrc/comm.cpp commOpenPeerMailboxes).  The thread that has folded its rank's partials writes
+// them straight into every peer's mailbox over NVLink (plain stores to peer memory, a system-scope fence, then the
+// sequence number as the "ready" flag), waits until the entries of all ranks carry this evaluation's sequence number
+// in its own mailbox, and sums them in rank order -- the same order on every rank, so all ranks return the same bits.
+// No NCCL launch, no extra kernel: the exchange rides in the epilogue of the kernel that produced the partials.
+// Entry = {sum, bad, seq, -}; index ((seq % 4) * kMaxBatchTrees + tree) * world + source rank.
+// ---------------------------------------------------------------------------
+constexpr int kMailSlots = 4, kMailTrees = 16, kMailMaxWorld = 8;
+struct MailArgs {
+    double *mine;
+    double *peer[kMailMaxWorld];
+    unsigned long long seq;
+    int rank, world;      // world <= 1: no exchange
+};
+__device__ __noinline__ void mail_allreduce(const MailArgs &m, int tree, double &sum, double &bad)   // ONE thread calls this
+{
+    const size_t base = ((size_t)(m.seq & (kMailSlots - 1)) * kMailTrees + tree) * m.world;
+    for (int r = 0; r < m.world; r++) {
+        volatile double *dst = m.peer[r] + (base + m.rank) * 4;
+        dst[0] = sum;
+        dst[1] = bad;
+    }
+    __threadfence_system();
+    for (int r = 0; r < m.world; r++)
+        *(reinterpret_cast<volatile unsigned long long *>(m.peer[r] + (base + m.rank) * 4) + 2) = m.seq;
+    double s = 0.0, b = 0.0;
+    for (int r = 0; r < m.world; r++) {
+        volatile double *src = m.mine + (base + r) * 4;
+        volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(m.mine + (base + r) * 4) + 2;
+        long spins = 0;
+        while (*flag != m.seq)
+            if (++spins > (1L << 28)) __trap();      // a rank that never evaluates must be an error, not a hang
+        __threadfence_system();
+        s += src[0];
+        b += src[1];
+    }
+    sum = s;
+    bad = b;
+}
+
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
@@ -1240,7 +1283,7 @@ like_kernel(const LikeArgs a)
 
 // One block folds the per-block partials in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
-like_final_kernel(const double *__restrict__ partials, int n, double *__restrict__ result)
+like_final_kernel(const double *__restrict__ partials, int n, double *__restrict__ result, const MailArgs mail)
 {
     __shared__ double sSum[8], sBad[8];
     double term = 0.0, bad = 0.0;
@@ -1258,7 +1301,11 @@ like_final_kernel(const double *__restrict__ partials, int n, double *__restrict
         bad = (l < 8) ? sBad[l] : 0.0;
         term = warpSum(term);
         bad = warpSum(bad);
-        if (l == 0) { result[0] = term; result[1] = bad; }
+        if (l == 0) {
+            if (mail.world > 1) mail_allreduce(mail, 0, term, bad);
+            result[0] = term;
+            result[1] = bad;
+        }
     }
 }
 
@@ -1267,6 +1314,7 @@ struct FinalBatchArgs {
     const double *partials[kMaxBatchTrees];
     double *result;     // [2*nTrees]
     int nBlocks;
+    MailArgs mail;
 };
 __global__ void __launch_bounds__(256)
 like_final_batch_kernel(const FinalBatchArgs a)
@@ -1288,7 +1336,11 @@ like_final_batch_kernel(const FinalBatchArgs a)
         bad = (l < 8) ? sBad[l] : 0.0;
         term = warpSum(term);
         bad = warpSum(bad);
-        if (l == 0) { a.result[2 * blockIdx.x] = term; a.result[2 * blockIdx.x + 1] = bad; }
+        if (l == 0) {
+            if (a.mail.world > 1) mail_allreduce(a.mail, blockIdx.x, term, bad);
+            a.result[2 * blockIdx.x] = term;
+            a.result[2 * blockIdx.x + 1] = bad;
+        }
     }
 }
 

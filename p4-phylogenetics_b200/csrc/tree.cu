@@ -78,6 +78,11 @@ struct Engine {
     cudaEvent_t stepEv[4] = {nullptr, nullptr, nullptr, nullptr};
     int stepSlabNext = 0;
     std::vector<Step2> stepShadow;             // what stepDev holds (once the stream reaches the last upload)
+    // peer mailboxes of the in-kernel all-reduce (kernels.cuh mail_allreduce); mailState 0 untried, 1 on, -1 unavailable
+    int mailState = 0;
+    double *mailMine = nullptr;
+    void *mailPeers[kMailMaxWorld] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long mailSeq = 0;
 };
 static Engine G;
 static char g_lastKernel[128] = "";   // p4b_lastCLKernelName: the CL kernel launched last (bench.py names it in its roofline)
@@ -117,6 +122,60 @@ void shardRange(int nPatterns, int *lo, int *hi)
 }
 
 long long kernelLaunchCount() { return G.launches; }
+
+// The exchange step of a sharded evaluation.  With a communicator present the ranks' partial sums are combined inside
+// the kernel that folds them (peer mailboxes over NVLink); NCCL's all-reduce remains the fallback when the mailboxes
+// cannot be mapped (no peer access, P4B_PEER_REDUCE=0).  Returns the kernel argument for the NEXT reducing launch.
+static bool mailOn()
+{
+    if (!commActive()) return false;
+    if (G.mailState == 0) {
+        G.mailState = -1;
+        const char *e = getenv("P4B_PEER_REDUCE");
+        const int world = commWorld();
+        // every rank goes through the hand-shake (it contains collectives) unless the switch is off everywhere
+        if (!(e && atoi(e) == 0) && world <= kMailMaxWorld) {
+            const size_t bytes = (size_t)kMailSlots * kMailTrees * kMailMaxWorld * 4 * sizeof(double);
+            bool ok = cudaMalloc(&G.mailMine, bytes) == cudaSuccess && cudaMemset(G.mailMine, 0, bytes) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); if (G.mailMine) { cudaFree(G.mailMine); G.mailMine = nullptr; } }
+            void *dummy = nullptr;
+            if (!ok) cudaMalloc(&dummy, 256);      // the hand-shake needs SOME allocation to name; its outcome will be "failed"
+            if (commOpenPeerMailboxes(ok ? (void *)G.mailMine : dummy, G.rank, G.mailPeers, (void *)G.stream) == 0 && ok) G.mailState = 1;
+            if (dummy) cudaFree(dummy);
+        }
+    }
+    return G.mailState == 1;
+}
+void engineMailShutdown()     // p4b_commDestroy: the mailboxes go with the communicator
+{
+    if (G.mailState == 1) {
+        if (G.stream) cudaStreamSynchronize(G.stream);
+        commClosePeerMailboxes(G.rank, G.mailPeers);
+    }
+    if (G.mailMine) { cudaFree(G.mailMine); G.mailMine = nullptr; }
+    G.mailState = 0;
+    G.mailSeq = 0;
+}
+static MailArgs nextMail()
+{
+    MailArgs m;
+    memset(&m, 0, sizeof(m));
+    m.world = 1;
+    if (mailOn()) {
+        m.mine = G.mailMine;
+        m.world = commWorld();
+        m.rank = G.rank;
+        for (int r = 0; r < m.world; r++) m.peer[r] = (double *)G.mailPeers[r];
+        m.seq = ++G.mailSeq;
+    }
+    return m;
+}
+// what callers do after a reducing launch: NCCL only when the kernel did not exchange the sums itself
+static int allReduceIfNeeded(double *devBuf, int count)
+{
+    if (!commActive() || mailOn()) return 0;
+    return commAllReduceSum(devBuf, count, (void *)G.stream);
+}
 
 static int engineInit()
 {
@@ -234,7 +293,7 @@ static int partDeviceEnsure(Part *p)
             out[k] = (uint8_t)w;
         }
     }
-    CUDA_TRY(cudaMalloc(&d.tips, tips.size()));
+    CUDA_TRY(cudaMalloc(&d.tips, tips.size() + 1024));      // + slack: the whole-tree kernel copies a CTA's 64..256 tip codes of a row at once, the last CTA past ps
     CUDA_TRY(cudaMemcpy(d.tips, tips.data(), tips.size(), cudaMemcpyHostToDevice));
     std::vector<int> counts(ps, 0);
     for (int k = 0; k < n; k++) counts[k] = p->patternCounts[d.lo + k];
@@ -1249,10 +1308,8 @@ static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &j
     }
     const int ns = (int)(steps.size() - base);
     Step2 *S = steps.data() + base;
-    // tip codes travel one step ahead
     h.t0 = h.t1 = h.pf0 = kNone;
-    if (ns > 0) { h.t0 = tipRows[0][0]; h.t1 = tipRows[0][1]; }
-    for (int j = 1; j < ns; j++) { S[j - 1].nt0 = tipRows[j][0]; S[j - 1].nt1 = tipRows[j][1]; }
+    for (int j = 0; j < ns; j++) { S[j].nt0 = tipRows[j][0]; S[j].nt1 = tipRows[j][1]; }   // a leaf child's tip codes travel with its lookup table
     // The per-thread shared-memory buffer: in consumption order, give each step's first in-memory child the buffer if it
     // is free -- pushed by the step that produces it when nothing else needs the buffer in between (no global re-read),
     // else prefetched from global memory up to three steps ahead; a child that gets neither is loaded when it is needed.
@@ -1480,6 +1537,10 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     if (smem > 200 * 1024) { setError("internal: step list of %d steps does not fit the whole-tree kernel's shared memory", maxSteps); return 1; }
     if (uploadSteps2(steps)) return 1;
     a.steps = G.stepDev;
+    bool anyLike2 = false;
+    for (int i = 0; i < nJobs; i++) anyLike2 = anyLike2 || a.hdr[i].doLike;
+    if (anyLike2) a.mail = nextMail();
+    else a.mail.world = 1;
     Kernel2Fn fn = kernel2For(L.nCat, shape);
     static std::unordered_set<void *> attrSet;
     if (!attrSet.count((void *)fn)) {
@@ -1792,10 +1853,11 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     }
     if (anyLike) {
         if (nJobs == 1) {
-            like_final_kernel<<<1, 256, 0, G.stream>>>(a.hdr[0].partials, blocks, resultDev);
+            like_final_kernel<<<1, 256, 0, G.stream>>>(a.hdr[0].partials, blocks, resultDev, nextMail());
         } else {
             FinalBatchArgs f;
             memset(&f, 0, sizeof(f));
+            f.mail = nextMail();
             for (int i = 0; i < nJobs; i++) f.partials[i] = jobs[i].withLike ? a.hdr[i].partials : a.hdr[0].partials;
             f.result = resultDev;
             f.nBlocks = blocks;
@@ -1914,7 +1976,7 @@ static int enqueueRootLike(Tree *t, int p, bool wantPatLikes, double *resultDev)
     a.partials = d->partials + (size_t)2 * d->maxLikeBlocks * 8 * p;
     like_kernel<<<blocks, 256, 0, G.stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, resultDev);
+    like_final_kernel<<<1, 256, 0, G.stream>>>(a.partials, blocks, resultDev, nextMail());
     CUDA_TRY(cudaGetLastError());
     G.launches += 2;
     return 0;
@@ -1932,8 +1994,7 @@ static int fetchResults(Tree *t, int p0, int p1)
 {
     TreeDevice *d = t->dev;
     const int n = 2 * (p1 - p0);
-    if (commActive())
-        if (commAllReduceSum(d->result + 2 * p0, n, (void *)G.stream)) return 1;
+    if (allReduceIfNeeded(d->result + 2 * p0, n)) return 1;
     CUDA_TRY(cudaMemcpyAsync(d->hResult + 2 * p0, d->result + 2 * p0, n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
     return streamSync();
 }
@@ -2014,8 +2075,7 @@ int treePartLogLikeBegin(Tree *t, int p)
     if (p < 0 || p >= t->nParts) { setError("p4b_partLogLikeBegin: bad part %d", p); return 1; }
     TreeDevice *d = t->dev;
     if (launchPartLike(t, p, 0)) return 1;
-    if (commActive())
-        if (commAllReduceSum(d->result + 2 * p, 2, (void *)G.stream)) return 1;
+    if (allReduceIfNeeded(d->result + 2 * p, 2)) return 1;
     CUDA_TRY(cudaMemcpyAsync(d->hResult + 2 * p, d->result + 2 * p, 2 * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
     if (!d->evLike[p]) CUDA_TRY(cudaEventCreateWithFlags(&d->evLike[p], cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(d->evLike[p], G.stream));
@@ -2155,8 +2215,7 @@ int treesPartLogLike(Tree **trees, int n, int p, double *out)
             }
             return 1;
         }
-        if (commActive())
-            if (commAllReduceSum(G.dBatch, 2 * m, (void *)G.stream)) return 1;
+        if (allReduceIfNeeded(G.dBatch, 2 * m)) return 1;
         CUDA_TRY(cudaMemcpyAsync(G.hBatch, G.dBatch, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
         if (streamSync()) return 1;
         for (int k = 0; k < m; k++) {

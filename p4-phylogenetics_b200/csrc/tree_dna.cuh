@@ -11,15 +11,16 @@
 // CTA-wide barrier -- is taken off the path:
 //   * the tree's whole step list, pre-decoded by the host (48 bytes per step), is copied into shared memory
 //     once, in the prologue: a step's descriptor is two 16-byte shared-memory loads;
-//   * the operands of a step's (at most two) children -- P decks, leaf tables -- arrive in a ring of kRing
-//     slots PER WARP by bulk copies (TMA, cp.async.bulk) that complete on the slot's mbarrier: a warp that has
-//     finished step s issues the copies of step s + kRing into the slot it has just freed and waits on its own
-//     mbarriers only (try_wait, normally already satisfied).  No barrier, no atomic, no other warp inside the
-//     step loop: the warps of a CTA drift freely.
+//   * the operands of a step's (at most two) children -- P decks, leaf tables, and the CTA's tip codes of a leaf
+//     child -- arrive in a ring of slots by bulk copies (TMA, cp.async.bulk) that complete on the slot's
+//     mbarrier.  Nobody is a dedicated producer: the LAST warp to finish step s (a shared-memory counter per
+//     slot) issues the copies of step s + RING into the slot it has just freed.  Warps wait on the slot's
+//     mbarrier only (try_wait, normally already satisfied) and drift up to RING - 1 steps apart: no CTA barrier
+//     inside the step loop, no per-thread global load on the step's path.
 // The one internal child of a step that is not in registers comes from a per-thread shared-memory buffer that
 // the host's step planner fills in one of two ways: the producing step PUSHES its result there (no global
 // re-read at all; short-lived siblings), or the thread PREFETCHES it from its own earlier global store with
-// cp.async one or more steps ahead.  Tip codes of a step's leaf children are fetched during the previous step.
+// cp.async one or more steps ahead.
 // Rate categories can be split over CSPLIT = NCAT / CT warps (more warps per SM at fewer registers each).
 // After the last step the root CL (in registers) is folded into site likelihoods and the CTA's partial lnL;
 // the LAST CTA to finish (atomic ticket) folds the partials in a fixed order: no second launch.
@@ -29,7 +30,6 @@
 namespace p4b {
 
 constexpr unsigned kNone = 0xffffffffu;
-constexpr int kRing = 3;          // operand ring of a warp: the current step's P decks / leaf tables and those of the next two
 
 // flags of a step
 constexpr unsigned kStepFirst = 4u, kStepStore = 8u, kStepPush = 256u, kStepPfLate = 512u;
@@ -40,7 +40,7 @@ struct Step2 {            // 48 bytes in global memory, written by the host's st
                           //   kind 0 internal child, loaded from its buffer now; 1 internal child in registers (previous step);
                           //   2 leaf child; 3 internal child in the thread's shared-memory buffer (pushed or prefetched)
     unsigned c0, c1;      // kind 0: the child's CL buffer (256-byte units)
-    unsigned nt0, nt1;    // tip rows to fetch during this step for the NEXT step's children 0 / 1 (kNone: none)
+    unsigned nt0, nt1;    // tip rows (sequence numbers) of this step's leaf children 0 / 1 (kNone: not a leaf)
     unsigned pf;          // CL buffer to prefetch into the shared-memory buffer during this step (kNone: none)
     unsigned pad;
     unsigned n0, n1;      // node numbers of the children: they address the P deck / leaf table
@@ -60,7 +60,7 @@ struct TreeHdr2 {
     double pInvar;
     double pi[4];
     int stepBase, nSteps;
-    unsigned t0, t1, pf0;     // prologue: tip rows of step 0's children, buffer to prefetch for step 0
+    unsigned t0, t1, pf0;     // pf0: buffer to prefetch for step 0 in the prologue (t0, t1 unused)
     int doLike;
 };
 
@@ -75,23 +75,25 @@ struct TreeArgs2 {
     const uint64_t *invarMask;
     const uint64_t *eqMask;
     const Step2 *steps;
+    MailArgs mail;            // world > 1: the last CTA exchanges the folded sums with the other pattern shards (kernels.cuh)
     TreeHdr2 hdr[kMaxBatchTrees];
 };
 
 // Shared memory of one CTA (all offsets multiples of 16 bytes):
-//   step digests [maxSteps] x 16 B, node numbers of the children [maxSteps] x 8 B | per warp: operand ring [kRing][2 children][ops] | per-thread buffers [KT][CW*32] double2 |
-//   category hand-over [CW*32] double2 | per warp: mbarriers full[kRing] | reduction scratch
-// A digest is what a warp needs of a step on its fast path: {out, pf, flags | nt0 << 16, nt1}; the rest of the record
-// (children loaded directly from global memory, node numbers for the operand copies) is read from global memory.
-// Every warp has a ring of its OWN: it issues the bulk copies of step s + kRing into the slot it has just finished
-// with, and waits on its own mbarriers only -- the warps of a CTA never wait for one another inside the step loop.
+//   step digests [maxSteps] x 16 B, node numbers of the children [maxSteps] x 8 B |
+//   operand ring [RING][ops child 0 | ops child 1 | tips child 0 | tips child 1] | per-thread buffers [KT][CW*32] double2 |
+//   category hand-over [CW*32] double2 | mbarriers full[RING] | slot counters [RING] | reduction scratch
+// A digest is what a warp needs of a step on its fast path: {out, pf, flags, -}; the node numbers address the operand
+// copies; children loaded directly from global memory (rare) are looked up in the global record.
+__host__ __device__ inline int treeDna2Ring(int CW) { return CW >= 4 ? 8 : 4; }
 __host__ __device__ inline size_t treeDna2OpsDoubles(int K, int W) { return (size_t)K * (W > 4 ? W : 4); }
-__host__ __device__ inline size_t treeDna2StepBytes(int maxSteps) { return ((size_t)maxSteps * 24 + 15) & ~(size_t)15; }   // 16-byte digest + the two node numbers
+__host__ __device__ inline size_t treeDna2StepBytes(int maxSteps) { return ((size_t)maxSteps * 24 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t treeDna2SlotBytes(int K, int W, int PB) { return 2 * treeDna2OpsDoubles(K, W) * 8 + 2 * (size_t)PB * 64; }
 __host__ inline size_t treeDna2SmemBytes(int nCat, int W, int CT, int CW, int maxSteps)
 {
-    const int K = nCat * 4;
-    return treeDna2StepBytes(maxSteps) + (size_t)CW * kRing * 2 * treeDna2OpsDoubles(K, W) * 8 + (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 +
-           (size_t)CW * kRing * 8 + 16 + (2 * CW + 2) * 8;
+    const int K = nCat * 4, PB = CW / (nCat / CT), RING = treeDna2Ring(CW);
+    return treeDna2StepBytes(maxSteps) + RING * treeDna2SlotBytes(K, W, PB) + (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 +
+           RING * 8 + RING * 4 + 16 + (2 * CW + 2) * 8;
 }
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
@@ -168,61 +170,68 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     constexpr int CTH = CW * 32;           // threads
     constexpr int PB = CW / CSPLIT;        // pattern blocks (64 patterns each) per CTA
     static_assert(NCAT % CT == 0 && CW % CSPLIT == 0, "shape");
+    constexpr int RING = CW >= 4 ? 8 : 4;
     const TreeHdr2 &hd = a.hdr[blockIdx.y];
     extern __shared__ __align__(16) unsigned char smraw[];
     const int W = a.tblW;
     const int nSteps = hd.nSteps;
     const unsigned opsD = (unsigned)treeDna2OpsDoubles(K, W);
-    const unsigned slotD = 2 * opsD;                                  // doubles per ring slot
+    const unsigned slotB = (unsigned)treeDna2SlotBytes(K, W, PB);     // bytes per ring slot
     uint4 *sSteps = reinterpret_cast<uint4 *>(smraw);                 // [maxSteps] digests
     uint2 *sNodes = reinterpret_cast<uint2 *>(sSteps + a.maxSteps);   // [maxSteps] node numbers of the children (operand addresses)
-    double *ringAll = reinterpret_cast<double *>(smraw + treeDna2StepBytes(a.maxSteps));
-    double2 *bufAll = reinterpret_cast<double2 *>(ringAll + (size_t)CW * kRing * slotD);   // [KT][CTH]
+    unsigned char *ring = smraw + treeDna2StepBytes(a.maxSteps);
+    double2 *bufAll = reinterpret_cast<double2 *>(ring + RING * slotB);   // [KT][CTH]
     double2 *sA = bufAll + KT * CTH;                                  // hand-over of the category sum between the warps of a pattern block
-    uint64_t *fullAll = reinterpret_cast<uint64_t *>(sA + CTH);
-    double *sRed = reinterpret_cast<double *>(fullAll + CW * kRing + 2);   // [2][CW] + flag
+    uint64_t *full = reinterpret_cast<uint64_t *>(sA + CTH);
+    unsigned *cnt = reinterpret_cast<unsigned *>(full + RING);
+    double *sRed = reinterpret_cast<double *>(cnt + RING + 2);        // [2][CW] + flag, 8-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *ring = ringAll + (size_t)warp * kRing * slotD;            // this warp's operand ring
-    uint64_t *full = fullAll + warp * kRing;                          // ... and its mbarriers
+    const size_t ps = (size_t)a.ps;
+    const uint8_t *ctaTips = a.tips + (size_t)blockIdx.x * (PB * 64);     // the CTA's PB*64 patterns of tip row 0
 
-    // one lane: the bulk copies (TMA) of step j's operands into the warp's ring slot `slot`, completing on that slot's mbarrier
-    auto produce = [&](int j, int slot) {
-        const unsigned flags = sSteps[j].z;
+    // one lane: the bulk copies (TMA) of step j's operands into its ring slot, completing on the slot's mbarrier.
+    // A leaf child's copy is its lookup table plus the CTA's tip codes of its sequence; `tipRow` = its sequence number.
+    auto produce = [&](int j) {
+        const int slot = j & (RING - 1);
+        const uint4 dg = sSteps[j];
         const uint2 nn = sNodes[j];
-        const unsigned n0 = nn.x, n1 = nn.y;
-        const unsigned pBytes = K * 4 * 8, tBytes = (unsigned)(K * W * 8);
+        const unsigned flags = dg.z;
+        const unsigned pBytes = K * 4 * 8, tBytes = (unsigned)(K * W * 8), tipBytes = PB * 64;
         const unsigned nc = flags & 3u, k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
-        const unsigned b0 = k0 == 2u ? tBytes : pBytes, b1 = nc == 2u ? (k1 == 2u ? tBytes : pBytes) : 0u;
-        double *sl = ring + slot * slotD;
-        mbar_expect_tx(full + slot, b0 + b1);
-        bulk_g2s(sl, k0 == 2u ? hd.tbl + a.tblNodeDoubles * n0 : hd.Pdeck + a.pNodeDoubles * n0, b0, full + slot);
-        if (nc == 2u) bulk_g2s(sl + opsD, k1 == 2u ? hd.tbl + a.tblNodeDoubles * n1 : hd.Pdeck + a.pNodeDoubles * n1, b1, full + slot);
+        const bool l0 = k0 == 2u, l1 = nc == 2u && k1 == 2u;
+        unsigned char *sl = ring + slot * slotB;
+        mbar_expect_tx(full + slot, (l0 ? tBytes + tipBytes : pBytes) + (nc == 2u ? (l1 ? tBytes + tipBytes : pBytes) : 0u));
+        bulk_g2s(sl, l0 ? hd.tbl + a.tblNodeDoubles * nn.x : hd.Pdeck + a.pNodeDoubles * nn.x, l0 ? tBytes : pBytes, full + slot);
+        if (l0) bulk_g2s(sl + 2 * opsD * 8, ctaTips + (size_t)(dg.w & 0xffffu) * ps, tipBytes, full + slot);
+        if (nc == 2u) {
+            bulk_g2s(sl + opsD * 8, l1 ? hd.tbl + a.tblNodeDoubles * nn.y : hd.Pdeck + a.pNodeDoubles * nn.y, l1 ? tBytes : pBytes, full + slot);
+            if (l1) bulk_g2s(sl + 2 * opsD * 8 + tipBytes, ctaTips + (size_t)(dg.w >> 16) * ps, tipBytes, full + slot);
+        }
     };
 
     {
         const Step2 *gSteps = a.steps + hd.stepBase;
         for (int i = threadIdx.x; i < nSteps; i += CTH) {
             const uint4 dA = __ldg(reinterpret_cast<const uint4 *>(gSteps + i)), dB = __ldg(reinterpret_cast<const uint4 *>(gSteps + i) + 1);
-            // {out, pf, flags | tip row of the next step's child 0 << 16 (0xffff: none), ... child 1}
-            sSteps[i] = make_uint4(dA.x, dB.z, (dA.y & 0xffffu) | ((dB.x == kNone ? 0xffffu : dB.x) << 16), dB.y == kNone ? 0xffffu : dB.y);
+            // {out, pf, flags, tip row (sequence number) of a leaf child 0 | of a leaf child 1 << 16}
+            sSteps[i] = make_uint4(dA.x, dB.z, dA.y, (dB.x & 0xffffu) | (dB.y << 16));
             sNodes[i] = make_uint2(__ldg(&gSteps[i].n0), __ldg(&gSteps[i].n1));
         }
-        if (lane == 0) {
-            for (int i = 0; i < kRing; i++) mbar_init(full + i, 1);
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < RING; i++) { mbar_init(full + i, 1); cnt[i] = 0u; }
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
     }
     __syncthreads();
-    if (lane == 0)
-        for (int j = 0; j < kRing && j < nSteps; j++) produce(j, j);
+    if (threadIdx.x == 0)
+        for (int j = 0; j < RING && j < nSteps; j++) produce(j);
 
     const int cg = warp % CSPLIT, pb = warp / CSPLIT;       // category group, pattern block of this warp
     const int pat = ((blockIdx.x * PB + pb) * 32 + lane) * 2;
     const bool active = pat < a.ps;
-    const unsigned ps = (unsigned)a.ps;
     // this thread's two patterns inside a CL buffer: element offset of its first row, and the row stride (both < 2^31)
     unsigned off, rs;
-    if (a.tileLog == 0) { off = (unsigned)pat; rs = ps; }
+    if (a.tileLog == 0) { off = (unsigned)pat; rs = (unsigned)a.ps; }
     else {
         const unsigned T = 1u << a.tileLog;
         off = (unsigned)(pat >> a.tileLog) * ((unsigned)K << a.tileLog) + ((unsigned)pat & (T - 1u));
@@ -231,6 +240,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     off += (unsigned)(cg * KT) * rs;
     double2 *buf = bufAll + threadIdx.x;                     // [KT][CTH]: row stride CTH double2
     const int opOff = cg * CT;                               // first category of this thread inside a P deck / leaf table
+    const unsigned tipOff = 2 * opsD * 8 + (unsigned)(pb * 64 + lane * 2);   // this thread's two tip codes of child 0 inside a slot
 
     double2 cur[KT];
 #pragma unroll
@@ -242,35 +252,22 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         for (int k = 0; k < KT; k++) cp_async16(buf + k * CTH, cl + (size_t)k * rs);
         cp_async_commit();
     };
-    auto tipLoad = [&](unsigned row) -> unsigned { return *reinterpret_cast<const unsigned short *>(a.tips + ((size_t)row * ps + (unsigned)pat)); };
+    if (active && hd.pf0 != kNone) prefetch(hd.pf0);
 
-    unsigned next0 = 0u, next1 = 0u;
-    if (active) {
-        if (hd.t0 != kNone) next0 = tipLoad(hd.t0);
-        if (hd.t1 != kNone) next1 = tipLoad(hd.t1);
-        if (hd.pf0 != kNone) prefetch(hd.pf0);
-    }
-
-    uint4 d = nSteps > 0 ? sSteps[0] : make_uint4(0u, 0u, 0u, 0u);
-    int slot = 0;
-    unsigned parity = 0u;
     for (int si = 0; si < nSteps; si++) {
-        const unsigned flags = d.z & 0xffffu, pf = d.y;
-        const unsigned code0 = next0, code1 = next1;
-        const unsigned k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
+        const int slot = si & (RING - 1);
+        mbar_wait(full + slot, (unsigned)(si / RING) & 1u);
         if (active) {
-            const unsigned t0 = d.z >> 16, t1 = d.w;
-            next0 = t0 != 0xffffu ? tipLoad(t0) : 0u;        // in flight while this step computes
-            next1 = t1 != 0xffffu ? tipLoad(t1) : 0u;
-        }
-        const unsigned outCode = d.x;
-        if (si + 1 < nSteps) d = sSteps[si + 1];             // the next step's digest, ahead of its use
-        mbar_wait(full + slot, parity);
-        if (active) {
-            double *outp = hd.arena + (size_t)outCode * 32 + off;
+            const uint4 d = sSteps[si];
+            const unsigned flags = d.z, pf = d.y;
+            const unsigned k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
+            const unsigned char *sl = ring + slot * slotB;
+            const unsigned code0 = *reinterpret_cast<const unsigned short *>(sl + tipOff);              // meaningful for a leaf child only
+            const unsigned code1 = *reinterpret_cast<const unsigned short *>(sl + tipOff + PB * 64);
             if (k0 == 3u || k1 == 3u) cp_async_wait_all();   // a prefetched child has landed (a pushed one is already there)
             if (pf != kNone && !(flags & kStepPfLate)) prefetch(pf);
-            const double *s0 = ring + slot * slotD, *s1 = s0 + opsD;
+            const double *s0 = reinterpret_cast<const double *>(sl), *s1 = s0 + opsD;
+            double *outp = hd.arena + (size_t)d.x * 32 + off;
             const bool store = (flags & kStepStore) != 0u, push = (flags & kStepPush) != 0u;
             if ((flags & (3u | kStepFirst)) == (2u | kStepFirst) && k0 != 0u && k1 != 0u) {
                 switch (k0 * 4 + k1) {     // uniform across the warp
@@ -324,13 +321,18 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             }
             if (pf != kNone && (flags & kStepPfLate)) prefetch(pf);   // the buffer was in use by this step: refill it now
         }
-        // the warp is done with the slot: refill it with the operands of step si + kRing
+        // release the slot; the last warp to do so refills it with the operands of step si + RING
         __syncwarp();
-        if (lane == 0 && si + kRing < nSteps) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warp's reads of the slot precede the bulk copy's writes
-            produce(si + kRing, slot);
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(cnt + slot, 1u) == (unsigned)(CW - 1)) {
+                cnt[slot] = 0u;
+                if (si + RING < nSteps) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warps' reads of the slot precede the bulk copy's writes
+                    produce(si + RING);
+                }
+            }
         }
-        if (++slot == kRing) { slot = 0; parity ^= 1u; }
     }
 
     if (!hd.doLike) return;
@@ -409,6 +411,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         if (threadIdx.x == 0) {
             double tt = 0.0, bb = 0.0;
             for (int i = 0; i < CW; i++) { tt += sRed[i]; bb += sRed[CW + i]; }
+            if (a.mail.world > 1) mail_allreduce(a.mail, blockIdx.y, tt, bb);   // the other shards' sums, over NVLink
             hd.result[0] = tt;
             hd.result[1] = bb;
         }
