@@ -71,6 +71,11 @@ int p4b_shardRangeFor(int nPatterns, int rank, int world, int *lo, int *hi);
 int p4b_commGetUniqueId(char id128[128]);
 int p4b_commInitRank(const char id128[128], int rank, int world);
 int p4b_commDestroy(void);
+/* How the shard sums of a log-likelihood are combined when a communicator is present: 1 = inside the kernel that folds them,
+ * through peer mailboxes over NVLink (every rank's mailbox mapped on every other rank with CUDA IPC; the default where peer
+ * access exists), -1 = NCCL all-reduce after the kernel (fallback, or P4B_PEER_REDUCE=0), 0 = not decided yet (no sharded
+ * evaluation has run). */
+int p4b_peerReduceState(void);
 /* p4b_treeLogLike evaluates 4-state parts with ONE whole-tree kernel launch by
  * default; 0 selects the one-launch-per-node kernels instead (same results;
  * kept for comparison and profiling). */

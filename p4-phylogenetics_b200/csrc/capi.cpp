@@ -35,6 +35,7 @@ int p4b_shardRangeFor(int nPatterns, int rank, int world, int *lo, int *hi)
 int p4b_commGetUniqueId(char id128[128]) { return commGetUniqueId(id128); }
 int p4b_commInitRank(const char id128[128], int rank, int world) { return commInitRank(id128, rank, world); }
 int p4b_commDestroy(void) { engineMailShutdown(); return commDestroy(); }
+int p4b_peerReduceState(void) { return peerReduceState(); }
 long long p4b_kernelLaunchCount(void) { return kernelLaunchCount(); }
 void p4b_setFusedTreeKernel(int on) { setFusedEnabled(on); }
 int p4b_setFusedVariant(int v) { return setFusedVariant(v); }

@@ -190,6 +190,7 @@ int treeFlushL2(Tree *t);
 int treeShardRangeOf(Tree *t, int p, int *lo, int *hi);
 int engineInitPublic();
 void engineMailShutdown();
+int peerReduceState();
 void setFusedEnabled(int on);
 int setFusedVariant(int v);
 const char *lastCLKernelName();

@@ -146,6 +146,7 @@ static bool mailOn()
     }
     return G.mailState == 1;
 }
+int peerReduceState() { return G.mailState; }
 void engineMailShutdown()     // p4b_commDestroy: the mailboxes go with the communicator
 {
     if (G.mailState == 1) {
@@ -272,7 +273,7 @@ static int partDeviceEnsure(Part *p)
             if (p->realEquateOfEquate[e] >= 0 && used[e]) p->usedEquateOfEquate[e] = p->nUsedEquates++;
     }
     const int n = d.hi - d.lo;
-    d.ps = ((n > 0 ? n : 1) + 31) & ~31;
+    d.ps = ((n > 0 ? n : 1) + 255) & ~255;      // a multiple of every whole-tree kernel's CTA tile: no thread is ever out of range
     const size_t ps = (size_t)d.ps;
     const int dim = p->dim;
     std::vector<uint8_t> tips((size_t)p->nTax * ps, (uint8_t)dim);   // padding behaves like a gap
@@ -1308,6 +1309,18 @@ static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &j
     }
     const int ns = (int)(steps.size() - base);
     Step2 *S = steps.data() + base;
+    // operand addresses as 32-bit offsets (doubles) into the tree's leaf tables / P decks
+    {
+        TreeDevice *d = t->dev;
+        for (int j = 0; j < ns; j++) {
+            const unsigned k0 = (S[j].flags >> 4) & 3u, k1 = (S[j].flags >> 6) & 3u;
+            const unsigned long long o0 = (unsigned long long)(k0 == 2u ? d->tblNodeDoubles : d->pNodeDoubles) * S[j].n0;
+            const unsigned long long o1 = (unsigned long long)(k1 == 2u ? d->tblNodeDoubles : d->pNodeDoubles) * S[j].n1;
+            if (o0 >> 32 || o1 >> 32) { setError("internal: operand decks larger than 32 GB"); return -1; }
+            S[j].n0 = (unsigned)o0;
+            S[j].n1 = (unsigned)o1;
+        }
+    }
     h.t0 = h.t1 = h.pf0 = kNone;
     for (int j = 0; j < ns; j++) { S[j].nt0 = tipRows[j][0]; S[j].nt1 = tipRows[j][1]; }   // a leaf child's tip codes travel with its lookup table
     // The per-thread shared-memory buffer: in consumption order, give each step's first in-memory child the buffer if it
@@ -1353,6 +1366,20 @@ static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &j
             } else {
                 needsMemory.insert(x);
             }
+        }
+    }
+    // Canonical child order for the kernel's straight-line bodies.  The product of the two children's factors is
+    // commutative bit for bit, so the children of a two-children first step can be handed over in either order: the
+    // one in registers first, else the one in the buffer, leaves last -- four combinations instead of seven.
+    for (int j = 0; j < ns; j++) {
+        if ((S[j].flags & (3u | kStepFirst)) != (2u | kStepFirst)) continue;
+        const unsigned k0 = (S[j].flags >> 4) & 3u, k1 = (S[j].flags >> 6) & 3u;
+        auto rank = [](unsigned k) { return k == 1u ? 0 : (k == 3u ? 1 : (k == 2u ? 2 : 3)); };
+        if (rank(k1) < rank(k0)) {
+            std::swap(S[j].c0, S[j].c1);
+            std::swap(S[j].nt0, S[j].nt1);
+            std::swap(S[j].n0, S[j].n1);
+            S[j].flags = (S[j].flags & ~0xf0u) | (k1 << 4) | (k0 << 6);
         }
     }
     if (!job.storeAll) {

@@ -43,7 +43,7 @@ struct Step2 {            // 48 bytes in global memory, written by the host's st
     unsigned nt0, nt1;    // tip rows (sequence numbers) of this step's leaf children 0 / 1 (kNone: not a leaf)
     unsigned pf;          // CL buffer to prefetch into the shared-memory buffer during this step (kNone: none)
     unsigned pad;
-    unsigned n0, n1;      // node numbers of the children: they address the P deck / leaf table
+    unsigned n0, n1;      // where the children's operands lie: offset (doubles) of the leaf table from hdr.tbl / of the P deck from hdr.Pdeck
     unsigned pad2[2];
 };
 static_assert(sizeof(Step2) == 48, "Step2 layout");
@@ -97,6 +97,15 @@ __host__ inline size_t treeDna2SmemBytes(int nCat, int W, int CT, int CW, int ma
 }
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)      // one try_wait: has the phase completed?
+{
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+    return done != 0u;
+}
 
 // Factor contributed by one child to the 4 states of category `cat` (same association as kernels.cuh child_factor).
 //   KIND 1: the child's CL is in `cur` (rows c*4..c*4+3)      KIND 3: in the thread's shared-memory buffer
@@ -178,7 +187,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     const unsigned opsD = (unsigned)treeDna2OpsDoubles(K, W);
     const unsigned slotB = (unsigned)treeDna2SlotBytes(K, W, PB);     // bytes per ring slot
     uint4 *sSteps = reinterpret_cast<uint4 *>(smraw);                 // [maxSteps] digests
-    uint2 *sNodes = reinterpret_cast<uint2 *>(sSteps + a.maxSteps);   // [maxSteps] node numbers of the children (operand addresses)
+    uint2 *sNodes = reinterpret_cast<uint2 *>(sSteps + a.maxSteps);   // [maxSteps] where the children's operands lie (offsets into the decks)
     unsigned char *ring = smraw + treeDna2StepBytes(a.maxSteps);
     double2 *bufAll = reinterpret_cast<double2 *>(ring + RING * slotB);   // [KT][CTH]
     double2 *sA = bufAll + KT * CTH;                                  // hand-over of the category sum between the warps of a pattern block
@@ -201,10 +210,10 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         const bool l0 = k0 == 2u, l1 = nc == 2u && k1 == 2u;
         unsigned char *sl = ring + slot * slotB;
         mbar_expect_tx(full + slot, (l0 ? tBytes + tipBytes : pBytes) + (nc == 2u ? (l1 ? tBytes + tipBytes : pBytes) : 0u));
-        bulk_g2s(sl, l0 ? hd.tbl + a.tblNodeDoubles * nn.x : hd.Pdeck + a.pNodeDoubles * nn.x, l0 ? tBytes : pBytes, full + slot);
+        bulk_g2s(sl, (l0 ? hd.tbl : hd.Pdeck) + nn.x, l0 ? tBytes : pBytes, full + slot);
         if (l0) bulk_g2s(sl + 2 * opsD * 8, ctaTips + (size_t)(dg.w & 0xffffu) * ps, tipBytes, full + slot);
         if (nc == 2u) {
-            bulk_g2s(sl + opsD * 8, l1 ? hd.tbl + a.tblNodeDoubles * nn.y : hd.Pdeck + a.pNodeDoubles * nn.y, l1 ? tBytes : pBytes, full + slot);
+            bulk_g2s(sl + opsD * 8, (l1 ? hd.tbl : hd.Pdeck) + nn.y, l1 ? tBytes : pBytes, full + slot);
             if (l1) bulk_g2s(sl + 2 * opsD * 8 + tipBytes, ctaTips + (size_t)(dg.w >> 16) * ps, tipBytes, full + slot);
         }
     };
@@ -228,7 +237,6 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
 
     const int cg = warp % CSPLIT, pb = warp / CSPLIT;       // category group, pattern block of this warp
     const int pat = ((blockIdx.x * PB + pb) * 32 + lane) * 2;
-    const bool active = pat < a.ps;
     // this thread's two patterns inside a CL buffer: element offset of its first row, and the row stride (both < 2^31)
     unsigned off, rs;
     if (a.tileLog == 0) { off = (unsigned)pat; rs = (unsigned)a.ps; }
@@ -252,12 +260,34 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         for (int k = 0; k < KT; k++) cp_async16(buf + k * CTH, cl + (size_t)k * rs);
         cp_async_commit();
     };
-    if (active && hd.pf0 != kNone) prefetch(hd.pf0);
+    if (hd.pf0 != kNone) prefetch(hd.pf0);
+
+    // Refilling the ring is shared out: warp w refills the slots of the steps w, w + CW, w + 2 CW, ... -- each as soon as
+    // all CW warps have left that step (the slot's counter) -- so no warp carries the producer's work alone and falls
+    // behind the others.  `done` = the last step this warp has finished.
+    int myNext = warp;
+    auto service = [&](int done) {      // lane 0 only
+        while (myNext <= done && myNext + RING < nSteps) {
+            volatile unsigned *c = cnt + (myNext & (RING - 1));
+            if (*c != (unsigned)CW) break;              // somebody is still working from that slot
+            *c = 0u;
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warps' reads of the slot precede the bulk copy's writes
+            produce(myNext + RING);
+            myNext += CW;
+        }
+    };
 
     for (int si = 0; si < nSteps; si++) {
         const int slot = si & (RING - 1);
-        mbar_wait(full + slot, (unsigned)(si / RING) & 1u);
-        if (active) {
+        {   // this step's operands; while they are not there, lane 0 keeps up with its refills (nobody can be starved)
+            const unsigned parity = (unsigned)(si / RING) & 1u;
+            int spins = 0;
+            while (!mbar_test(full + slot, parity)) {
+                if (lane == 0) service(si - 1);
+                if (++spins > (1 << 22)) __trap();       // a lost copy must be an error, never a hang
+            }
+        }
+        {
             const uint4 d = sSteps[si];
             const unsigned flags = d.z, pf = d.y;
             const unsigned k0 = (flags >> 4) & 3u, k1 = (flags >> 6) & 3u;
@@ -269,16 +299,13 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             const double *s0 = reinterpret_cast<const double *>(sl), *s1 = s0 + opsD;
             double *outp = hd.arena + (size_t)d.x * 32 + off;
             const bool store = (flags & kStepStore) != 0u, push = (flags & kStepPush) != 0u;
-            if ((flags & (3u | kStepFirst)) == (2u | kStepFirst) && k0 != 0u && k1 != 0u) {
-                switch (k0 * 4 + k1) {     // uniform across the warp
-                case 1 * 4 + 2: step2<CT, CTH, 1, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                case 2 * 4 + 1: step2<CT, CTH, 2, 1>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                case 1 * 4 + 3: step2<CT, CTH, 1, 3>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                case 3 * 4 + 1: step2<CT, CTH, 3, 1>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                case 2 * 4 + 3: step2<CT, CTH, 2, 3>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                case 3 * 4 + 2: step2<CT, CTH, 3, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                default: step2<CT, CTH, 2, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp); break;
-                }
+            if ((flags & (3u | kStepFirst)) == (2u | kStepFirst) && ((k0 == 1u && k1 >= 2u) || (k0 >= 2u && k1 == 2u))) {
+                // the planner hands the children over in canonical order: registers, buffer, leaf
+                if (k0 == 1u) {
+                    if (k1 == 2u) step2<CT, CTH, 1, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp);
+                    else step2<CT, CTH, 1, 3>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp);
+                } else if (k0 == 3u) step2<CT, CTH, 3, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp);
+                else step2<CT, CTH, 2, 2>(store, cur, buf, opOff, s0, s1, W, code0, code1, rs, outp);
             } else {
                 // any other shape: one child, a continuation of a node with more than two children, children loaded
                 // straight from global memory -- kinds decided at run time
@@ -321,17 +348,12 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             }
             if (pf != kNone && (flags & kStepPfLate)) prefetch(pf);   // the buffer was in use by this step: refill it now
         }
-        // release the slot; the last warp to do so refills it with the operands of step si + RING
+        // this warp has left the slot
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
-            if (atomicAdd(cnt + slot, 1u) == (unsigned)(CW - 1)) {
-                cnt[slot] = 0u;
-                if (si + RING < nSteps) {
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warps' reads of the slot precede the bulk copy's writes
-                    produce(si + RING);
-                }
-            }
+            atomicAdd(cnt + slot, 1u);
+            service(si);
         }
     }
 
@@ -341,7 +363,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     // block when the categories are split: the result does not depend on CSPLIT.
     double2 A = make_double2(0.0, 0.0);
     uint64_t mask0 = ~0ull, mask1 = ~0ull;
-    if (active && hd.rootTips) {
+    if (hd.rootTips) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             if (pat + h < a.nPat) {
@@ -367,7 +389,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         if (g < CSPLIT - 1) named_barrier(1, CTH);
     }
     double term = 0.0, bad = 0.0;
-    if (cg == CSPLIT - 1 && active) {
+    if (cg == CSPLIT - 1) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int p1 = pat + h;

@@ -73,6 +73,7 @@ _sig("p4b_shardRangeFor", _i, _i, _i, _i, _ip, _ip)
 _sig("p4b_commGetUniqueId", _i, C.c_char_p)
 _sig("p4b_commInitRank", _i, C.c_char_p, _i, _i)
 _sig("p4b_commDestroy", _i)
+_sig("p4b_peerReduceState", _i)
 _sig("p4b_kernelLaunchCount", C.c_longlong)
 _sig("p4b_setFusedTreeKernel", None, _i)
 _sig("p4b_setFusedVariant", _i, _i)
@@ -276,6 +277,11 @@ def commInitRank(uid, rank, world):
 
 def commDestroy():
     _ok(_lib.p4b_commDestroy())
+
+
+def peerReduceState():
+    """1: shard sums are combined inside the kernel over NVLink peer mailboxes; -1: NCCL all-reduce; 0: undecided."""
+    return int(_lib.p4b_peerReduceState())
 
 
 def setFusedTreeKernel(on):

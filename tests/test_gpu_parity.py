@@ -202,7 +202,7 @@ def test_fused_tree_kernel_equals_per_node_kernels(pkg, cfg, kw):
         cl_b = {n.nodeNum: pf.getNodeCL(tree.cTree, n.cNode, 0, mp.nGammaCat, mp.dim) for n in tree.nodes if not n.isLeaf}
     finally:
         pf.setFusedTreeKernel(1)
-    assert lb == 2      # whole-tree CL + site likelihoods, final fold (no P(t) job: every deck already has these inputs)
+    assert lb == 1      # whole-tree CL + site likelihoods + the last CTA's fold: ONE launch (no P(t) job: every deck already has these inputs)
     assert rel(b, a) <= 1e-13
     for k in cl_a:
         assert np.array_equal(cl_a[k], cl_b[k]), "CL of node %d" % k
