@@ -1450,8 +1450,13 @@ static int fused2Shape(int ps, int nTrees)
         if (forced < -1 || forced >= kNumShapes2) forced = -1;
     }
     if (forced >= 0) return forced;
-    const double waves = (double)nTrees * (double)(ps / 2) / (128.0 * 3.0 * G.numSMs);
-    return waves >= 3.0 ? 0 : (waves >= 1.6 ? 1 : 2);
+    // Measured on B200 (tools/sweep_dna.py, 200 taxa; profiles/r2_sweep_dna.txt): shape 16 -- two rate categories per
+    // thread, the four categories of a pattern block split over two warps, 256 threads x 2 CTAs/SM = 16 warps/SM at 128
+    // registers -- is the fastest at every shard size: 1 M patterns 4.61 ms (10: 5.08, 13: 4.73), 250 k 1.21 (13: 1.25),
+    // 125 k 0.67 (13: 0.70, 14: 0.71); the first-generation kernel 4.98 / 1.35 / 0.82.
+    (void)ps;
+    (void)nTrees;
+    return 6;
 }
 
 // Make `steps` the content of the device step buffer (skipped when it already is).
