@@ -201,7 +201,7 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
         // Operand decks of cl_tree_aa_kernel, so that its per-step staging is a straight copy:
         //   aux[0 .. nCat*480)            P^T in mma fragment order [cat][kk][nt][lane]: lane (g,q) holds P[cat][8nt+g][x],
         //                                 x = 8t+2q+i for kk = 2t+i < 4, x = 16+q for kk = 4; zero where the parent state is >= 20
-        //   aux[nCat*480 .. +nCat*W*20)   leaf table transposed, [cat][w][state]
+        //   aux[nCat*480 .. +nCat*W*24)   leaf table transposed and padded with zeros, [cat][w][24]
         __syncthreads();
         double *A = job.aux;
         const int nF = nCat * 480;
@@ -214,10 +214,10 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
             const int W = job.tblW;
             const double *T = job.tbl;
             double *TT = A + nF;
-            const int nT = nCat * W * dim;
+            const int nT = nCat * W * 24;
             for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-                const int st = i % dim, w = (i / dim) % W, ct = i / (dim * W);
-                TT[i] = T[(ct * dim + st) * W + w];
+                const int st = i % 24, w = (i / 24) % W, ct = i / (24 * W);
+                TT[i] = st < dim ? T[(ct * dim + st) * W + w] : 0.0;
             }
         }
     }
@@ -938,7 +938,7 @@ cl_dmma20_kernel(const __grid_constant__ CLArgs a)
 }
 
 // ---------------------------------------------------------------------------
-// Whole-tree CL recursion, 20 states, FP64 tensor cores, ONE launch.
+// Whole-tree CL recursion, 20 states, FP64 tensor cores, ONE launch: the scheme (the kernel itself is cl_tree_aa2_kernel, tree_aa.cuh).
 //
 // The per-node kernel above computes out = P x cl_child with P as the A operand, so its result
 // comes out of the tensor core in the C layout and would have to be transposed (shared memory or
@@ -1000,206 +1000,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
                      : "memory");
         if (!done && ++spins > (1 << 22)) __trap();   // a lost copy must be an error, never a hang
     } while (!done);
-}
-
-template <int NCAT, int GROUPS, int MINB, int MT>
-__global__ void __launch_bounds__(NCAT * GROUPS * 32, MINB)
-cl_tree_aa_kernel(const __grid_constant__ TreeArgs a)
-{
-    constexpr int DIM = 20, GT = GROUPS * 32;   // threads of one category group
-    constexpr int WP = 8 * MT;                  // patterns per warp: MT m-tiles of 8; a lane owns MT consecutive patterns of a row
-    const int treeIdx = blockIdx.y;
-    const TreeHdr &hd = a.hdr[treeIdx];
-    extern __shared__ double sm[];              // [cat][2 buffers][kAAKids][slot], then [cat][2] mbarriers
-    const int W = a.tblW;
-    const int tblSize = DIM * W;                // per category
-    const int slot = kAAFrag > tblSize ? kAAFrag : tblSize;
-    const int bufSize = kAAKids * slot;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    // The warps of one rate category (one per pattern group) form a group of their own: one of its threads
-    // stages that category's operands (bulk copies signalling an mbarrier) and the group synchronises on a
-    // named barrier, so the categories of a CTA drift apart and one category's tensor-core phase overlaps
-    // another's loads and stores.  Consecutive warps belong to one category, so every SM sub-partition
-    // (warp % 4) hosts warps of different groups.
-    const int cat = warp / GROUPS, grp = warp % GROUPS;
-    const int gtid = grp * 32 + lane;
-    double *smc = sm + (size_t)cat * 2 * bufSize;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + (size_t)NCAT * 2 * bufSize) + cat * 2;
-    const int pat0 = (blockIdx.x * GROUPS + grp) * WP;
-    const bool active = pat0 < a.ps;
-    const size_t ps = (size_t)a.ps;
-    const size_t rowBase = (size_t)cat * DIM * ps + pat0 + MT * g;   // + state * ps: this lane's MT patterns of a row
-    const size_t auxLeafOff = (size_t)NCAT * kAAFrag + (size_t)cat * tblSize;
-    const int nSteps = hd.nSteps, stepBase = hd.stepBase;
-    // Lanes q >= 2 hold, in n-tile 2, the padding states 16+2q+i >= 20: computed as zeros (zero columns of P^T),
-    // kept at zero through leaf lookups, never stored.
-    const bool tail = q >= 2;
-
-    auto stage = [&](int stepIdx, int b) {      // one thread per category
-        const StepC &st = a.steps[stepBase + stepIdx];
-        const int nc = st.nChildren;
-        unsigned total = 0;
-        for (int c = 0; c < nc; c++) total += (((unsigned)st.ch[c].a >> 30) == 2u ? tblSize : kAAFrag) * 8;
-        mbar_expect_tx(bars + b, total);
-        for (int c = 0; c < nc; c++) {
-            const bool leaf = ((unsigned)st.ch[c].a >> 30) == 2u;
-            const double *src = hd.aux + a.auxNodeDoubles * st.ch[c].b + (leaf ? auxLeafOff : (size_t)cat * kAAFrag);
-            bulk_g2s(smc + b * bufSize + c * slot, src, (leaf ? tblSize : kAAFrag) * 8, bars + b);
-        }
-    };
-    // tip codes (MT patterns, one byte each) of child c of a step, if it is a leaf; fetched one step ahead
-    auto tipCode = [&](int stepIdx, int c) -> unsigned {
-        if (!active || stepIdx >= nSteps) return 0u;
-        const StepC &st = a.steps[stepBase + stepIdx];
-        const unsigned av = (unsigned)st.ch[c].a;
-        if (c >= st.nChildren || (av >> 30) != 2u) return 0u;
-        const uint8_t *tp = a.tips + (size_t)(av & 0x3fffffffu) * ps + pat0 + MT * g;
-        return MT == 4 ? *reinterpret_cast<const unsigned *>(tp) : (unsigned)*reinterpret_cast<const unsigned short *>(tp);
-    };
-
-    // out (=|*=) A x B for one child: A in registers (C layout of the child for the states 0..15, a4 = the fifth
-    // k-step's operand: state 16 + q), B fragments of this category.  The three n-tiles advance together:
-    // 3*MT independent accumulator chains keep the tensor pipe fed.
-    auto contract = [&](const double (&A)[MT][3][2], const double (&a4)[MT], const double *__restrict__ Bc, double (&out)[MT][3][2], bool assign) {
-        double acc[MT][3][2];
-#pragma unroll
-        for (int j = 0; j < MT; j++)
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) acc[j][nt][0] = acc[j][nt][1] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 5; kk++) {
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
-                const double b = Bc[(kk * 3 + nt) * 32];
-#pragma unroll
-                for (int j = 0; j < MT; j++) dmma884(acc[j][nt][0], acc[j][nt][1], kk < 4 ? A[j][kk >> 1][kk & 1] : a4[j], b);
-            }
-        }
-        if (assign) {
-#pragma unroll
-            for (int j = 0; j < MT; j++)
-#pragma unroll
-                for (int nt = 0; nt < 3; nt++) { out[j][nt][0] = acc[j][nt][0]; out[j][nt][1] = acc[j][nt][1]; }
-        } else {
-#pragma unroll
-            for (int j = 0; j < MT; j++)
-#pragma unroll
-                for (int nt = 0; nt < 3; nt++) { out[j][nt][0] *= acc[j][nt][0]; out[j][nt][1] *= acc[j][nt][1]; }
-        }
-    };
-    const int quadSrc = (lane & ~3) | (q >> 1);   // the lane of this quad that holds state 16 + q (as its element q & 1 of n-tile 2)
-
-    unsigned next0 = 0u, next1 = 0u;   // tip codes of the next step's children
-
-    // One step: `in` holds the CL of the node computed by the previous step, `out` receives this node's.
-    // The caller alternates two register arrays, so no step ends with a copy.
-    auto step = [&](int si, const double (&in)[MT][3][2], double (&out)[MT][3][2]) {
-        named_barrier(1 + cat, GT);   // every warp of the category is done with step si-1: its buffer is free
-        if (gtid == 0 && si + 1 < nSteps) stage(si + 1, (si + 1) & 1);
-        const unsigned code0 = next0, code1 = next1;
-        next0 = tipCode(si + 1, 0);          // in flight while this step computes
-        next1 = tipCode(si + 1, 1);
-        mbar_wait(bars + (si & 1), (unsigned)(si >> 1) & 1u);   // this step's operands have landed
-        if (!active) return;
-        const double *buf = smc + (si & 1) * bufSize;
-        const StepC &st = a.steps[stepBase + si];
-        const int nc = st.nChildren;
-        int regChild = -1;
-        for (int c = 0; c < nc; c++)
-            if (((unsigned)st.ch[c].a >> 30) == 1u) regChild = c;
-        if (regChild >= 0) {                 // the child computed by the previous step: straight from registers
-            double a4[MT];
-#pragma unroll
-            for (int j = 0; j < MT; j++) {
-                const double v0 = __shfl_sync(0xffffffffu, in[j][2][0], quadSrc), v1 = __shfl_sync(0xffffffffu, in[j][2][1], quadSrc);
-                a4[j] = (q & 1) ? v1 : v0;
-            }
-            contract(in, a4, buf + regChild * slot + lane, out, true);
-        } else if (!st.first) {              // continuation of a node with more than two children
-#pragma unroll
-            for (int j = 0; j < MT; j++)
-#pragma unroll
-                for (int t = 0; t < 3; t++) { out[j][t][0] = in[j][t][0]; out[j][t][1] = in[j][t][1]; }
-        } else {
-#pragma unroll
-            for (int j = 0; j < MT; j++)
-#pragma unroll
-                for (int t = 0; t < 3; t++) out[j][t][0] = out[j][t][1] = 1.0;
-        }
-        for (int c = 0; c < nc; c++) {
-            if (c == regChild) continue;
-            const unsigned av = (unsigned)st.ch[c].a, kind = av >> 30;
-            if (kind == 2u) {
-                // leaf: out *= T[state][code]; the table is [code][state], so the lane's states 8t+2q, 8t+2q+1 are one 16-byte load
-                const unsigned cw = c == 0 ? code0 : code1;
-                const double *T = buf + c * slot + 2 * q;
-#pragma unroll
-                for (int j = 0; j < MT; j++) {
-                    const double *Tj = T + ((cw >> (8 * j)) & 0xffu) * DIM;
-                    const double2 v0 = *reinterpret_cast<const double2 *>(Tj);
-                    const double2 v1 = *reinterpret_cast<const double2 *>(Tj + 8);
-                    const double2 v2 = *reinterpret_cast<const double2 *>(Tj + (tail ? 8 : 16));
-                    out[j][0][0] *= v0.x; out[j][0][1] *= v0.y;
-                    out[j][1][0] *= v1.x; out[j][1][1] *= v1.y;
-                    out[j][2][0] *= tail ? 0.0 : v2.x;    // padding entries must stay finite: keep them at zero
-                    out[j][2][1] *= tail ? 0.0 : v2.y;
-                }
-            } else {                         // internal child in memory (written earlier by this same lane)
-                const double *cl = hd.arena + (size_t)(av & 0x3fffffffu) * 32 + rowBase;
-                double sib[MT][3][2], a4[MT];
-#pragma unroll
-                for (int r = 0; r < 4; r++) {            // states 8t + 2q + i, t = r >> 1, i = r & 1
-                    const double *row = cl + (size_t)(8 * (r >> 1) + 2 * q + (r & 1)) * ps;
-#pragma unroll
-                    for (int h = 0; h < MT / 2; h++) {
-                        const double2 v = ld2(row + 2 * h);
-                        sib[2 * h][r >> 1][r & 1] = v.x;
-                        sib[2 * h + 1][r >> 1][r & 1] = v.y;
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < MT / 2; h++) {       // state 16 + q: the fifth k-step's operand, straight from its row
-                    const double2 v = ld2(cl + (size_t)(16 + q) * ps + 2 * h);
-                    a4[2 * h] = v.x;
-                    a4[2 * h + 1] = v.y;
-                }
-#pragma unroll
-                for (int j = 0; j < MT; j++) sib[j][2][0] = sib[j][2][1] = 0.0;   // not read
-                contract(sib, a4, buf + c * slot + lane, out, false);
-            }
-        }
-        if (st.store) {
-            double *o = hd.arena + (size_t)(unsigned)st.outSlot * 32 + rowBase + (size_t)(2 * q) * ps;
-#pragma unroll
-            for (int r = 0; r < 6; r++) {
-                if (r < 4 || !tail) {
-                    double *orow = o + (size_t)(8 * (r >> 1) + (r & 1)) * ps;
-#pragma unroll
-                    for (int h = 0; h < MT / 2; h++) st2(orow + 2 * h, make_double2(out[2 * h][r >> 1][r & 1], out[2 * h + 1][r >> 1][r & 1]));
-                }
-            }
-        }
-    };
-
-    double cA[MT][3][2], cB[MT][3][2];
-#pragma unroll
-    for (int j = 0; j < MT; j++)
-#pragma unroll
-        for (int t = 0; t < 3; t++) cA[j][t][0] = cA[j][t][1] = cB[j][t][0] = cB[j][t][1] = 0.0;
-
-    if (gtid == 0) {
-        mbar_init(bars, 1);
-        mbar_init(bars + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    named_barrier(1 + cat, GT);
-    if (gtid == 0 && nSteps > 0) stage(0, 0);
-    next0 = tipCode(0, 0);
-    next1 = tipCode(0, 1);
-    for (int si = 0; si < nSteps; si += 2) {
-        step(si, cA, cB);
-        if (si + 1 < nSteps) step(si + 1, cB, cA);
-    }
 }
 
 // ---------------------------------------------------------------------------

@@ -31,6 +31,7 @@
 #include "kernels.cuh"
 #include "tree_dna.cuh"
 #include "tree_dmma.cuh"
+#include "tree_aa.cuh"
 #include "newt.cuh"
 
 namespace p4b {
@@ -433,7 +434,7 @@ int treeDeviceCreate(Tree *t)
         d->tblNodeDoubles += (L.tblDoubles + 1) & ~(size_t)1;
         if (L.dim == 20 && L.nCat == 4) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
             L.auxOff = d->auxNodeDoubles;
-            L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * L.dim * L.W;
+            L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * kAA2TblStates * L.W;
             d->auxNodeDoubles += L.auxDoubles;
         } else if (L.dim > 20 && L.dim <= 64 && !g_useScalers) {   // 21..64 states: the generic tensor-core kernel's decks (tree_dmma.cuh)
             L.auxDP = dmmaPaddedDim(L.dim);
@@ -1239,7 +1240,8 @@ static void reorderHeavyFirst(std::vector<Node *> &order)
 
 // Steps of one job, appended to `steps`; fills the job's header fields that depend on them.  Returns the number of
 // steps, or -1 on error.
-static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &job, int p)
+// mode 0: 4-state kernel (P decks / leaf tables, shared-memory buffer); mode 1: 20-state kernel (operand decks, no buffer).
+static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &job, int p, int mode = 0)
 {
     Tree *t = job.t;
     Part *dp = t->data->parts[p];
@@ -1314,8 +1316,16 @@ static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &j
         TreeDevice *d = t->dev;
         for (int j = 0; j < ns; j++) {
             const unsigned k0 = (S[j].flags >> 4) & 3u, k1 = (S[j].flags >> 6) & 3u;
-            const unsigned long long o0 = (unsigned long long)(k0 == 2u ? d->tblNodeDoubles : d->pNodeDoubles) * S[j].n0;
-            const unsigned long long o1 = (unsigned long long)(k1 == 2u ? d->tblNodeDoubles : d->pNodeDoubles) * S[j].n1;
+            unsigned long long o0, o1;
+            if (mode == 1) {       // operand deck of the node; a leaf's transposed tables lie behind the P^T fragments
+                const PartLayout &L = d->parts[p];
+                const unsigned long long leafOff = (unsigned long long)L.nCat * kAAFrag;
+                o0 = (unsigned long long)d->auxNodeDoubles * S[j].n0 + (k0 == 2u ? leafOff : 0ull);
+                o1 = (unsigned long long)d->auxNodeDoubles * S[j].n1 + (k1 == 2u ? leafOff : 0ull);
+            } else {
+                o0 = (unsigned long long)(k0 == 2u ? d->tblNodeDoubles : d->pNodeDoubles) * S[j].n0;
+                o1 = (unsigned long long)(k1 == 2u ? d->tblNodeDoubles : d->pNodeDoubles) * S[j].n1;
+            }
             if (o0 >> 32 || o1 >> 32) { setError("internal: operand decks larger than 32 GB"); return -1; }
             S[j].n0 = (unsigned)o0;
             S[j].n1 = (unsigned)o1;
@@ -1329,7 +1339,7 @@ static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &j
     std::unordered_set<Node *> needsMemory;
     int lastUse = -1;                    // step whose computation last reads the buffer
     for (int j = 0; j < ns; j++) {
-        bool taken = false;
+        bool taken = mode == 1;          // the 20-state kernel has no buffer: in-memory children are loaded when they are needed
         for (int i = 0; i < (int)(S[j].flags & 3u); i++) {
             const unsigned kind = (S[j].flags >> (4 + 2 * i)) & 3u;
             if (kind != 0u) continue;
@@ -1374,7 +1384,7 @@ static int buildSteps2(std::vector<Step2> &steps, TreeHdr2 &h, const FusedJob &j
     for (int j = 0; j < ns; j++) {
         if ((S[j].flags & (3u | kStepFirst)) != (2u | kStepFirst)) continue;
         const unsigned k0 = (S[j].flags >> 4) & 3u, k1 = (S[j].flags >> 6) & 3u;
-        auto rank = [](unsigned k) { return k == 1u ? 0 : (k == 3u ? 1 : (k == 2u ? 2 : 3)); };
+        auto rank = [mode](unsigned k) { return mode == 1 ? (k == 1u ? 0 : (k == 0u ? 1 : 2)) : (k == 1u ? 0 : (k == 3u ? 1 : (k == 2u ? 2 : 3))); };
         if (rank(k1) < rank(k0)) {
             std::swap(S[j].c0, S[j].c1);
             std::swap(S[j].nt0, S[j].nt1);
@@ -1588,6 +1598,90 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
 }
 
 // ---------------------------------------------------------------------------
+// 20 states: the second-generation tensor-core whole-tree kernel (tree_aa.cuh)
+// ---------------------------------------------------------------------------
+static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
+{
+    if (flushPJobs()) return 1;
+    Tree *t0 = jobs[0].t;
+    TreeDevice *d0 = t0->dev;
+    PartLayout &L = d0->parts[p];
+    Part *dp = t0->data->parts[p];
+    if (!d0->aux || L.auxDP != 0 || !L.auxDoubles) { setError("internal: 20-state whole-tree kernel without operand decks"); return 1; }
+    if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
+    static TreeArgsAA2 a;
+    memset(&a, 0, sizeof(a));
+    a.ps = L.ps;
+    a.nPat = L.nPat;
+    a.tblW = L.W;
+    a.nTrees = nJobs;
+    a.tips = dp->dev.tips;
+    static int groups = -1, ringSel = 4;
+    if (groups < 0) {
+        const char *e = getenv("P4B_AA2_GROUPS");
+        groups = e ? atoi(e) : 4;
+        if (groups != 1 && groups != 2 && groups != 4) groups = 4;
+        e = getenv("P4B_AA2_RING");
+        ringSel = e ? atoi(e) : (groups == 4 ? 4 : 2);
+        if (ringSel != 2 && ringSel != 4) ringSel = 2;
+    }
+    static std::vector<Step2> steps;
+    steps.clear();
+    int maxSteps = 1;
+    for (int i = 0; i < nJobs; i++) {
+        Tree *t = jobs[i].t;
+        TreeDevice *d = t->dev;
+        PartLayout &Li = d->parts[p];
+        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != L.dim || Li.W != L.W || d->auxNodeDoubles != d0->auxNodeDoubles) {
+            setError("batched evaluation: the trees do not share the data part and model shape");
+            return 1;
+        }
+        if (jobs[i].withLike && (!t->root || jobs[i].order->empty() || jobs[i].order->back() != t->root)) { setError("fused evaluation: the last node must be the root"); return 1; }
+        a.hdr[i].arena = arenaBase(Li);
+        a.hdr[i].aux = d->aux + Li.auxOff;
+        a.hdr[i].stepBase = (int)steps.size();
+        TreeHdr2 h;
+        memset(&h, 0, sizeof(h));
+        FusedJob job = jobs[i];
+        job.storeAll = true;          // (no lnL-only mode here: the root reduction reads the root's CL from memory)
+        const int ns = buildSteps2(steps, h, job, p, 1);
+        if (ns < 0) return 1;
+        a.hdr[i].nSteps = ns;
+        if (ns > maxSteps) maxSteps = ns;
+    }
+    bool anything = false;
+    for (int i = 0; i < nJobs; i++)
+        if (a.hdr[i].nSteps > 0) anything = true;
+    if (anything) {
+        a.maxSteps = maxSteps;
+        size_t smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps);
+        if (smem > 220 * 1024 && ringSel == 4) { ringSel = 2; smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps); }
+        if (smem > 220 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
+        if (uploadSteps2(steps)) return 1;
+        a.steps = G.stepDev;
+        typedef void (*Fn)(const TreeArgsAA2);
+        Fn fn = groups == 4 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 4, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 4, 2, 1>)
+              : groups == 2 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 2, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 2, 2, 2>)
+                            : (Fn)cl_tree_aa2_kernel<4, 1, 2, 3>;
+        static std::unordered_set<void *> attrSet;
+        if (!attrSet.count((void *)fn)) {
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attrSet.insert((void *)fn);
+        }
+        const int blocks = L.ps / (groups * 16);
+        fn<<<dim3(blocks, nJobs), L.nCat * groups * 32, smem, G.stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa2_kernel<%d,%d,%d>", L.nCat, groups, ringSel);
+        G.launches++;
+        for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
+    }
+    for (int i = 0; i < nJobs; i++)
+        if (jobs[i].withLike)
+            if (enqueueRootLike(jobs[i].t, p, jobs[i].wantPatLikes, resultDev + 2 * i)) return 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // 21..64 states: the generic tensor-core whole-tree kernel (tree_dmma.cuh)
 // ---------------------------------------------------------------------------
 static int buildSteps(TreeArgs &a, int base, int room, const FusedJob &job, int p, bool *overflowOk, size_t *resumeAt, int maxKids);
@@ -1695,6 +1789,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         if (L0.dim == 4 && !L0.scalers && g_fused2 && g_fused2On()) return launchFused2Batch(jobs, nJobs, p, resultDev);
         if (L0.dim == 4 && L0.nCat != 4 && L0.nCat != 1) { setError("internal: the first-generation whole-tree kernel serves 1 or 4 rate categories"); return 1; }
         if (L0.dim > 20) return launchFusedDmmaBatch(jobs, nJobs, p, resultDev);
+        if (L0.dim == 20) return launchFusedAA2Batch(jobs, nJobs, p, resultDev);
     }
     if (flushPJobs()) return 1;
     Tree *t0 = jobs[0].t;
@@ -1713,23 +1808,10 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.counts = dp->dev.counts;
     a.invarMask = dp->dev.invarMask;
     a.eqMask = dp->dev.equateMask;
-    const bool aa = L.dim == 20;      // tensor-core kernel: root reduction is a separate kernel
-    const int variant = aa ? 0 : fusedVariant(L.ps, nJobs);
+    const bool aa = false;            // (20-state parts have their own launch path: launchFusedAA2Batch)
+    const int variant = fusedVariant(L.ps, nJobs);
     static const int kThreads[9] = {128, 64, 32, 128, 256, 64, 32, 64, 32};
-    static int aaGroups = -1, aaMinB = 1, aaMT = 2;   // 20-state kernel: pattern groups per CTA, CTAs per SM, m-tiles per warp
-    if (aaGroups < 0) {
-        const char *e = getenv("P4B_AA_GROUPS");
-        // measured on B200, cfg 3 (100 taxa x 200 k patterns): groups x CTAs/SM = 2x2 5.63 ms, 1x3 5.76, 3x1 5.98,
-        // 4x1 6.32 (all with 2 m-tiles per warp); 2x1 with 4 m-tiles 6.02; the per-node kernels 7.70
-        aaGroups = e ? atoi(e) : 2;
-        if (aaGroups < 1 || aaGroups > 4) aaGroups = 2;
-        e = getenv("P4B_AA_MINB");
-        aaMinB = e ? atoi(e) : (aaGroups == 2 ? 2 : 1);
-        if (aaMinB < 1 || aaMinB > 3 || aaMinB * aaGroups > 4) aaMinB = 1;
-        e = getenv("P4B_AA_MT");
-        aaMT = e ? atoi(e) : 2;
-        if (aaMT != 2 && aaMT != 4) aaMT = 2;
-    }
+    const int aaGroups = 1, aaMinB = 1, aaMT = 2;
     const int THREADS = aa ? 128 * aaGroups : kThreads[variant];
     const int blocks = aa ? (L.ps / (8 * aaMT) + aaGroups - 1) / aaGroups : (L.ps / 2 + THREADS - 1) / THREADS;
     const int maxKids = aa ? kAAKids : kMaxChildren;
@@ -1782,15 +1864,6 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     }
     if (smem > (aa ? 200 : 100) * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
     typedef void (*KernelFn)(const TreeArgs);
-    static const KernelFn kFnAA[2][4][3] = {
-        {{cl_tree_aa_kernel<4, 1, 1, 2>, cl_tree_aa_kernel<4, 1, 2, 2>, cl_tree_aa_kernel<4, 1, 3, 2>},
-         {cl_tree_aa_kernel<4, 2, 1, 2>, cl_tree_aa_kernel<4, 2, 2, 2>, nullptr},
-         {cl_tree_aa_kernel<4, 3, 1, 2>, nullptr, nullptr},
-         {cl_tree_aa_kernel<4, 4, 1, 2>, nullptr, nullptr}},
-        {{cl_tree_aa_kernel<4, 1, 1, 4>, cl_tree_aa_kernel<4, 1, 2, 4>, cl_tree_aa_kernel<4, 1, 3, 4>},
-         {cl_tree_aa_kernel<4, 2, 1, 4>, cl_tree_aa_kernel<4, 2, 2, 4>, nullptr},
-         {cl_tree_aa_kernel<4, 3, 1, 4>, nullptr, nullptr},
-         {cl_tree_aa_kernel<4, 4, 1, 4>, nullptr, nullptr}}};
     static const KernelFn kFn4[9] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
                                      cl_tree_dna_kernel<4, 32, 12, false>, cl_tree_dna_kernel<4, 128, 4, false>,
                                      cl_tree_dna_kernel<4, 256, 2, false>, cl_tree_dna_kernel<4, 64, 8, false>,
@@ -1810,13 +1883,8 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         if (variant > 2) { setError("scalers need one of the default launch shapes"); return 1; }
         fn = L.nCat == 4 ? kFn4s[variant] : kFn1s[variant];
     }
-    if (aa) fn = kFnAA[aaMT / 2 - 1][aaGroups - 1][aaMinB - 1];
     static bool attrSet = false;
     if (!attrSet) {
-        for (int t = 0; t < 2; t++)
-            for (int v = 0; v < 4; v++)
-                for (int m = 0; m < 3; m++)
-                    if (kFnAA[t][v][m]) CUDA_TRY(cudaFuncSetAttribute(kFnAA[t][v][m], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         for (int v = 0; v < 9; v++) {
             CUDA_TRY(cudaFuncSetAttribute(kFn4[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(kFn1[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -2516,9 +2584,9 @@ int nodeSetBigP(Node *n, int p, const double *in)
             const int s = 8 * nt + (l >> 2), x = kk < 4 ? 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1) : 16 + (l & 3);
             A[i] = (s < dim && x < dim) ? in[((size_t)ct * dim + s) * dim + x] : 0.0;
         }
-        for (int i = 0; i < L.nCat * W * dim; i++) {
-            const int st = i % dim, w = (i / dim) % W, ct = i / (dim * W);
-            A[nF + i] = T[((size_t)ct * dim + st) * W + w];
+        for (int i = 0; i < L.nCat * W * kAA2TblStates; i++) {
+            const int st = i % kAA2TblStates, w = (i / kAA2TblStates) % W, ct = i / (kAA2TblStates * W);
+            A[nF + i] = st < dim ? T[((size_t)ct * dim + st) * W + w] : 0.0;
         }
         CUDA_TRY(cudaMemcpyAsync(nodeAux(n, p), A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
     }

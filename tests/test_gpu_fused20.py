@@ -1,4 +1,4 @@
-"""The whole-tree 20-state kernel (cl_tree_aa_kernel: FP64 tensor cores, running CL in accumulator
+"""The whole-tree 20-state kernel (cl_tree_aa2_kernel, tree_aa.cuh: FP64 tensor cores, running CL in accumulator
 registers) against the one-launch-per-node kernels and the reference engine."""
 import numpy as np
 import pytest
