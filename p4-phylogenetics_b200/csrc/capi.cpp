@@ -394,6 +394,7 @@ p4b_node p4b_newNode(int nodeNum, p4b_tree t, int seqNum, int isLeaf, int inTree
     }
     if (nodeDeviceCreate(n)) { nodeDeviceRelease(n); delete n; return nullptr; }
     T->nodes[nodeNum] = n;
+    T->topoStamp++;
     return n;
 }
 
@@ -403,6 +404,7 @@ void p4b_freeNode(p4b_node n)
     if (!N) return;
     if (N->tree && treeHasPending(N->tree)) treeFlushPending(N->tree);   // queued CL calls may name this node
     nodeDeviceRelease(N);
+    if (N->tree) N->tree->topoStamp++;
     if (N->tree && N->nodeNum >= 0 && N->nodeNum < (int)N->tree->nodes.size() && N->tree->nodes[N->nodeNum] == N) N->tree->nodes[N->nodeNum] = nullptr;
     delete N;
 }
@@ -418,16 +420,16 @@ int p4b_setNodeRelation(p4b_node n, int relation, int relNum)
         if (relNum >= N->tree->nNodes || !N->tree->nodes[relNum]) { setError("p4_setNodeRelation: node %d does not exist", relNum); return 1; }
         rel = N->tree->nodes[relNum];
     }
-    if (relation == 0) N->parent = rel;
-    else if (relation == 1) N->leftChild = rel;
-    else if (relation == 2) N->sibling = rel;
-    else { setError("Error in p4_setNodeRelation: \"relation\" is out of range"); return 1; }
+    Node **slot = relation == 0 ? &N->parent : (relation == 1 ? &N->leftChild : (relation == 2 ? &N->sibling : nullptr));
+    if (!slot) { setError("Error in p4_setNodeRelation: \"relation\" is out of range"); return 1; }
+    if (*slot != rel) { *slot = rel; N->tree->topoStamp++; }     // p4 re-sends the whole topology with every Tree.setCStuff: only a CHANGE invalidates cached launch plans
     return 0;
 }
 int p4b_setTreeRoot(p4b_tree t, p4b_node n)
 {
     CHECK_PTR(t, "p4_setTreeRoot", 1);
-    ((Tree *)t)->root = (Node *)n;
+    Tree *T = (Tree *)t;
+    if (T->root != (Node *)n) { T->root = (Node *)n; T->topoStamp++; }
     return 0;
 }
 int p4b_setBrLen(p4b_node n, double brLen)
@@ -454,10 +456,12 @@ int p4b_setTreeCStuff(p4b_tree t, int nNodes, const int *parent, const int *left
     for (int i = 0; i < nNodes; i++) {
         Node *n = T->nodes[i];
         if (!n) continue;
-        if (at(parent[i], &n->parent) || at(leftChild[i], &n->leftChild) || at(sibling[i], &n->sibling)) return 1;
+        Node *par = nullptr, *lc = nullptr, *sib = nullptr;
+        if (at(parent[i], &par) || at(leftChild[i], &lc) || at(sibling[i], &sib)) return 1;
+        if (par != n->parent || lc != n->leftChild || sib != n->sibling) { n->parent = par; n->leftChild = lc; n->sibling = sib; T->topoStamp++; }
         if (i != rootNum) n->brLen = brLen[i];
     }
-    T->root = T->nodes[rootNum];
+    if (T->root != T->nodes[rootNum]) { T->root = T->nodes[rootNum]; T->topoStamp++; }
     return 0;
 }
 static int setNum(p4b_node n, int pNum, int val, int which)

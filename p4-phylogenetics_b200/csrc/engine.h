@@ -153,6 +153,7 @@ struct Tree {
     // 0: a whole-tree evaluation writes only the CLs it must re-read itself; the others are
     // recomputed (one storing pass) the first time anything asks for them.
     int storeCL = 1;
+    uint64_t topoStamp = 1;       // bumped whenever a node relation, the root or a node itself changes (plans of whole-tree launches are cached per topology)
     TreeDevice *dev = nullptr;
 };
 

@@ -367,6 +367,20 @@ struct PartLayout {
     std::vector<uint64_t> eigUploaded;   // version of each (comp,rMatrix) mirrored on the device
 };
 
+// The step list of a whole-tree launch depends on the topology, on which CL buffer every node uses and on what was
+// asked; planning it (ordering, buffer allocation, operand offsets) costs tens of microseconds on the host, which at
+// 8 GPUs is several percent of an evaluation.  A repeated evaluation of an unchanged tree reuses the plan.
+struct PlanCache {
+    bool valid = false;
+    uint64_t topo = 0, slot = 0;
+    bool withLike = false, storeAll = true;
+    std::vector<Node *> order;          // the job it was made for
+    std::vector<Node *> nodes;          // nodes that have steps, in step order (one entry per node)
+    std::vector<char> resident;         // their clResident after the launch
+    std::vector<Step2> steps;
+    unsigned pf0 = 0xffffffffu;
+};
+
 struct TreeDevice {
     std::vector<PartLayout> parts;
     std::vector<uint64_t> dataVersion;   // per part: Part::version this device state was laid out for
@@ -386,6 +400,8 @@ struct TreeDevice {
     double *hResult = nullptr;    // pinned
     double *partials = nullptr;   // [2*maxBlocks]
     unsigned *tickets = nullptr;  // [nParts] last-CTA tickets of the fused root reduction
+    uint64_t slotStamp = 1;       // bumped whenever a node's CL buffer assignment (or the arena pairing) changes
+    std::vector<struct PlanCache> plan;   // per part: the last whole-tree launch plan of the 4-state kernel (reused while nothing it depends on changed)
     int maxLikeBlocks = 0;
     double *patLikes = nullptr;
     int patLikesCap = 0;
@@ -408,6 +424,7 @@ int treeDeviceCreate(Tree *t)
     d->scalers = g_useScalers;
     d->parts.resize(t->nParts);
     d->pending.resize(t->nParts);
+    d->plan.resize(t->nParts);
     d->likeBegun.assign(t->nParts, 0);
     d->evLike.assign(t->nParts, nullptr);
     size_t eigTotal = 0, eqTotal = 0;
@@ -566,6 +583,7 @@ static int nodeEnsureCLSlot(Node *n, int p)
     if (slotAcquire(n->tree, p, &sel, &slot, n->nodeNum)) return 1;
     n->clSel[p] = (char)sel;
     n->clSlot[p] = slot;
+    n->tree->dev->slotStamp++;
     return 0;
 }
 
@@ -582,6 +600,7 @@ static int nodeMakeWritable(Node *n, int p)
     A->refs[n->clSlot[p]]--;
     n->clSel[p] = (char)sel;
     n->clSlot[p] = slot;
+    n->tree->dev->slotStamp++;
     return 0;
 }
 
@@ -593,6 +612,7 @@ void nodeDeviceRelease(Node *n)
         if (n->clSlot[p] < 0) continue;
         slotRelease(t->dev->parts[p].arena(n->clSel[p]), n->clSlot[p]);
         n->clSlot[p] = -1;
+        t->dev->slotStamp++;
     }
 }
 
@@ -1520,7 +1540,8 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     a.eqMask = dp->dev.equateMask;
     if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
     const int shape = fused2Shape(L.ps, nJobs);
-    Shape2 sh = L.nCat == 4 ? kShapes2[shape] : Shape2{1, shape == 0 ? 4 : (shape == 1 ? 2 : 1), shape == 0 ? 4 : (shape == 1 ? 8 : 16)};
+    const int shape1 = shape == 1 ? 1 : (shape == 2 ? 2 : 0);      // one rate category: 128 threads unless a small-CTA shape is forced
+    Shape2 sh = L.nCat == 4 ? kShapes2[shape] : Shape2{1, shape1 == 0 ? 4 : (shape1 == 1 ? 2 : 1), shape1 == 0 ? 4 : (shape1 == 1 ? 8 : 16)};
     if (L.nCat != 4 && L.nCat != 1 && !shapeForNCat(L.nCat, &sh)) { setError("internal: no whole-tree kernel for %d rate categories", L.nCat); return 1; }
     const int csplit = L.nCat / sh.ct;
     const int patsPerCta = (sh.cw / csplit) * 64;
@@ -1566,8 +1587,48 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
             h.doLike = 1;
         }
         h.stepBase = (int)steps.size();
-        const int ns = buildSteps2(steps, h, jobs[i], p);
-        if (ns < 0) return 1;
+        int ns = -1;
+        PlanCache *pc = (nJobs == 1 && !jobs[i].memo) ? &d->plan[p] : nullptr;
+        if (pc && pc->valid && pc->topo == t->topoStamp && pc->withLike == jobs[i].withLike && pc->storeAll == jobs[i].storeAll && pc->order == *jobs[i].order) {
+            // the plan of the last launch may still hold: every node must keep the buffer it had
+            bool ok = true;
+            for (Node *n : pc->nodes)
+                if (nodeMakeWritable(n, p)) return 1;
+            ok = pc->slot == d->slotStamp;
+            if (ok) {
+                steps.insert(steps.end(), pc->steps.begin(), pc->steps.end());
+                for (size_t k = 0; k < pc->nodes.size(); k++) {
+                    Node *n = pc->nodes[k];
+                    n->clStamp[p] = ++G.stamp;
+                    n->clKey[p].clear();          // (no input record: a later node-level call on it recomputes rather than skips)
+                    n->clResident[p] = pc->resident[k];
+                    n->clNeedsUpdating = 0;
+                }
+                h.pf0 = pc->pf0;
+                h.t0 = h.t1 = kNone;
+                h.nSteps = ns = (int)pc->steps.size();
+            }
+        }
+        if (ns < 0) {
+            ns = buildSteps2(steps, h, jobs[i], p);
+            if (ns < 0) return 1;
+            if (pc) {
+                pc->valid = true;
+                pc->topo = t->topoStamp;
+                pc->slot = d->slotStamp;
+                pc->withLike = jobs[i].withLike;
+                pc->storeAll = jobs[i].storeAll;
+                pc->order = *jobs[i].order;
+                pc->steps.assign(steps.begin() + h.stepBase, steps.end());
+                pc->pf0 = h.pf0;
+                pc->nodes.clear();
+                pc->resident.clear();
+                for (Node *n : *jobs[i].order) {       // every node of a non-memoised job has steps
+                    pc->nodes.push_back(n);
+                    pc->resident.push_back(n->clResident[p]);
+                }
+            }
+        }
         if (ns > maxSteps) maxSteps = ns;
     }
     bool anything = false;
@@ -1583,12 +1644,13 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
     for (int i = 0; i < nJobs; i++) anyLike2 = anyLike2 || a.hdr[i].doLike;
     if (anyLike2) a.mail = nextMail();
     else a.mail.world = 1;
-    Kernel2Fn fn = kernel2For(L.nCat, shape);
+    Kernel2Fn fn = kernel2For(L.nCat, L.nCat == 1 ? shape1 : shape);
     static std::unordered_set<void *> attrSet;
     if (!attrSet.count((void *)fn)) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attrSet.insert((void *)fn);
     }
+    if (blocks * patsPerCta != L.ps) { setError("internal: pattern stride %d is not a multiple of the CTA tile", L.ps); return 1; }
     fn<<<dim3(blocks, nJobs), sh.cw * 32, smem, G.stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_dna2_kernel<%d,%d,%d,%d>", L.nCat, sh.ct, sh.cw, sh.minb);
@@ -2366,6 +2428,8 @@ static bool canShare(Tree *a, Tree *b, int p)
         B->partner = A;
         LA.twin = LB.own;
         LB.twin = LA.own;
+        a->dev->slotStamp++;
+        b->dev->slotStamp++;
     }
     return LA.twin.get() == B && LB.twin.get() == A;
 }
@@ -2397,6 +2461,7 @@ int treeCopyCondLikes(Tree *a, Tree *b, int doAll)
                 src->refs[slot]++;
                 nB->clSel[p] = (char)(src == LB.own.get() ? 0 : 1);
                 nB->clSlot[p] = slot;
+                b->dev->slotStamp++;
             } else {
                 if (nodeMakeWritable(nB, p)) return 1;
                 CUDA_TRY(cudaMemcpyAsync(nodeCL(nB, p), nodeCL(nA, p), a->dev->parts[p].own->slotDoubles * sizeof(double),

@@ -130,6 +130,21 @@ cl_tree_aa2_kernel(const __grid_constant__ TreeArgsAA2 a)
     };
     const int quadSrc = (lane & ~3) | (q >> 1);   // the lane of this quad that holds state 16 + q (as its element q & 1 of n-tile 2)
 
+    // an internal child's CL from global memory (written earlier by this same lane), in the operand layout
+    auto loadSib = [&](unsigned slotCode, double (&sib)[MT][3][2], double (&a4)[MT]) {
+        const double *cl = hd.arena + (size_t)slotCode * 32 + rowBase;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {            // states 8t + 2q + i, t = r >> 1, i = r & 1
+            const double2 v = ld2(cl + (size_t)(8 * (r >> 1) + 2 * q + (r & 1)) * ps);
+            sib[0][r >> 1][r & 1] = v.x;
+            sib[1][r >> 1][r & 1] = v.y;
+        }
+        const double2 v = ld2(cl + (size_t)(16 + q) * ps);    // state 16 + q: the fifth k-step's operand, straight from its row
+        a4[0] = v.x;
+        a4[1] = v.y;
+#pragma unroll
+        for (int j = 0; j < MT; j++) sib[j][2][0] = sib[j][2][1] = 0.0;   // not read
+    };
     // the factor of one child folded into `out`; KIND 1: the child is `in` (registers), 0: its CL is in global memory, 2: leaf
     auto child = [&](auto kindTag, bool assign, const double (&in)[MT][3][2], double (&out)[MT][3][2], const unsigned char *opsB, unsigned code, unsigned slotCode) {
         constexpr int KIND = decltype(kindTag)::value;
@@ -156,21 +171,8 @@ cl_tree_aa2_kernel(const __grid_constant__ TreeArgsAA2 a)
             }
             contract(in, a4, ops + lane, out, assign);
         } else {
-            const double *cl = hd.arena + (size_t)slotCode * 32 + rowBase;
             double sib[MT][3][2], a4[MT];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {            // states 8t + 2q + i, t = r >> 1, i = r & 1
-                const double2 v = ld2(cl + (size_t)(8 * (r >> 1) + 2 * q + (r & 1)) * ps);
-                sib[0][r >> 1][r & 1] = v.x;
-                sib[1][r >> 1][r & 1] = v.y;
-            }
-            {
-                const double2 v = ld2(cl + (size_t)(16 + q) * ps);    // state 16 + q: the fifth k-step's operand, straight from its row
-                a4[0] = v.x;
-                a4[1] = v.y;
-            }
-#pragma unroll
-            for (int j = 0; j < MT; j++) sib[j][2][0] = sib[j][2][1] = 0.0;   // not read
+            loadSib(slotCode, sib, a4);
             contract(sib, a4, ops + lane, out, assign);
         }
     };
@@ -218,7 +220,12 @@ cl_tree_aa2_kernel(const __grid_constant__ TreeArgsAA2 a)
             // two children in canonical order (registers, memory, leaf): straight-line code per combination
             if (k0 == 1u) {
                 if (k1 == 2u) { child(REG, true, in, out, sl, 0u, 0u); child(LEAF, false, in, out, sl + childB, code1, 0u); }
-                else { child(REG, true, in, out, sl, 0u, 0u); child(MEM, false, in, out, sl + childB, 0u, d.y); }
+                else {       // the sibling's rows are requested before the contraction of the child in registers: their latency hides behind it
+                    double sib[MT][3][2], a4[MT];
+                    loadSib(d.y, sib, a4);
+                    child(REG, true, in, out, sl, 0u, 0u);
+                    contract(sib, a4, reinterpret_cast<const double *>(sl + childB) + (size_t)cat * kAAFrag + lane, out, false);
+                }
             } else if (k0 == 0u) {
                 if (k1 == 2u) { child(MEM, true, in, out, sl, 0u, d.y); child(LEAF, false, in, out, sl + childB, code1, 0u); }
                 else { child(MEM, true, in, out, sl, 0u, d.y); child(MEM, false, in, out, sl + childB, 0u, __ldg(&(a.steps + hd.stepBase + si)->c1)); }
