@@ -509,6 +509,35 @@ def config_block(P, pf, cfg, peak, steps, real_p4=True):
     return out
 
 
+def codon61_block(P, pf, peak, nTax=32, nSites=60000, nCat=4):
+    """north_star's "61-state codon" case (not a BASELINE config; the reference has no codon model: a 61-symbol 'standard'
+    datatype through its generic-dim loop): the generic tensor-core whole-tree kernel (csrc/tree_dmma.cuh), device-timed,
+    with its FP64 tensor throughput and the site likelihoods checked against the reference on a column sample."""
+    t0 = time.perf_counter()
+    tree = P.synth.build_generic(pf, P.synth.SYMBOLS_61, nTax, nSites, nCat, 6161, equates={"!": "abcd"})
+    setup = time.perf_counter() - t0
+    lnL = tree.calcLogLike()
+    for _ in range(3):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    steps = 10
+    pf.treeTimerBegin(tree.cTree)
+    for _ in range(steps):
+        pf.p4_treeLogLike(tree.cTree, 0)
+    ms = pf.treeTimerEnd(tree.cTree) / steps
+    comp, alg, flops = work_model(pf, tree)
+    out = {"workload": "61-state 'standard' data (codon-like), %d taxa, %d patterns, %d rate categories, full-tree lnL" %
+                       (nTax, pf.partPatternCount(tree.data.parts[0].cPart), nCat),
+           "kernel": pf.lastCLKernelName(), "lnL": lnL, "setup_s": round(setup, 1), "ms_per_eval": ms, "evals_per_s": 1000.0 / ms,
+           "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": FP64_DMMA_TFLOPS, "unit": "TFLOP/s", "frac": flops / ms / 1e9 / FP64_DMMA_TFLOPS,
+                        "GFLOP_per_eval": flops / 1e9, "peak_source": "FP64 mma.sync m8n8k4 microbenchmark (profiles/r2_membw.txt)",
+                        "hbm_compulsory_GBps": comp / ms / 1e6, "hbm_frac": comp / ms / 1e6 / peak}}
+    worst, cpu_value, desc = reference_on_sample(P, pf, tree, 400)
+    out["reference_check"] = {"site_likelihoods_max_rel_diff": worst, "tolerance": 1e-9, "ok": (worst is not None and worst <= 1e-9)}
+    out["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": desc}
+    free_tree(tree)
+    return out
+
+
 def real_p4_mcmc(taxa=100, patterns=500000, chains=8, gens=40):
     """Config 5 through the reference's REAL p4 package (its own Mcmc.run / Chain code, staged under oracle/_ref/p4) with
     this repository's pf module as p4.pf -- a process of its own (tests/dropin/p4_like_side.py)."""
@@ -740,6 +769,13 @@ def run_b200(a):
             except Exception as e:      # the headline line must still be printed
                 configs["cfg%d" % cfg] = {"failed": "%s: %s" % (type(e).__name__, e)}
             log("cfg%d: %s" % (cfg, json.dumps(configs["cfg%d" % cfg])[:400]))
+        try:
+            configs["codon61"] = codon61_block(P, pf, peak)
+        except SystemExit as e:
+            configs["codon61"] = {"failed": "engine error: %s" % (e,)}
+        except Exception as e:
+            configs["codon61"] = {"failed": "%s: %s" % (type(e).__name__, e)}
+        log("codon61: %s" % json.dumps(configs["codon61"])[:400])
         line["configs"] = configs
     print(json.dumps(line))
     if dist is not None:

@@ -321,3 +321,54 @@ def build_config(pf, cfg, nTax=None, nPatterns=None, seed=None):
             for p in range(4):
                 n.parts[p].compNum = n.nodeNum
     return tree
+
+
+# ------------------------------------------------------------------------------
+# any state count (61-state codon-like data: a 'standard' datatype with 61 symbols, SURVEY.md section 2 note)
+# ------------------------------------------------------------------------------
+SYMBOLS_61 = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ012345678"
+
+
+def evolve_states(rng, tree, dim, nSites, mut=0.35):
+    """Leaf state rows with phylogenetic signal: states copied down the tree, changed with a per-branch probability."""
+    tree.setPreAndPostOrder()
+    states = {tree.root.nodeNum: rng.integers(dim, size=nSites)}
+    out = {}
+    for i in tree.preOrder:
+        if i < 0 or i == tree.root.nodeNum:
+            continue
+        n = tree.nodes[i]
+        s = states[n.parent.nodeNum].copy()
+        m = rng.random(nSites) < min(0.9, mut * (0.3 + 5.0 * n.br.len))
+        s[m] = rng.integers(dim, size=int(m.sum()))
+        states[i] = s
+        if n.isLeaf:
+            out[n.seqNum] = s
+    return [out[k] for k in sorted(out)]
+
+
+def build_generic(pf, symbols, nTax, nSites, nCat, seed, equates=None, pInvar=0.0, tree=None):
+    """Tree + data + model for a datatype with len(symbols) states: random composition and exchangeabilities, gamma rates."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    dim = len(symbols)
+    if tree is None:
+        tree = random_tree(pf, nTax, rng)
+    lut = np.frombuffer(symbols.encode(), dtype=np.uint8)
+    seqs = []
+    eqChars = sorted((equates or {}).keys())
+    for s in evolve_states(rng, tree, dim, nSites):
+        chars = lut[s].copy()
+        chars[rng.random(nSites) < 0.02] = ord("-")
+        for e in eqChars:
+            chars[rng.random(nSites) < 0.01] = ord(e)
+        seqs.append(chars.tobytes())
+    aln = host.Alignment(pf, seqs, symbols, equates or {})
+    mp = host.ModelPart(0, dim, nCat)
+    mp.comps.append(host.Comp(normalise_comp(rng.dirichlet(20.0 * np.ones(dim)))))
+    r = rng.dirichlet(3.0 * np.ones(dim * (dim - 1) // 2))
+    mp.rMatrices.append(host.RMatrix("specified", r / r.sum()))
+    if nCat > 1:
+        mp.gdasrvs.append(host.Gdasrv(nCat, 0.7))
+    mp.pInvar = host.PInvar(pInvar)
+    tree.attach(host.Data(pf, [aln]), host.Model(pf, [mp]))
+    return tree

@@ -16,35 +16,16 @@ from util import rel
 
 pytestmark = pytest.mark.gpu
 
-SYM61 = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ012345678"
+SYM61 = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ012345678"      # = synth.SYMBOLS_61
 SYM24 = "abcdefghijklmnopqrstuvwx"
-
-
-def _evolve(rng, tree, dim, nSites, mut=0.35):
-    """Sequences with phylogenetic signal: states copied down the tree with per-branch change probability."""
-    states = {}
-    root = tree.root
-    states[root.nodeNum] = rng.integers(dim, size=nSites)
-    out = {}
-    for i in tree.preOrder:
-        if i < 0 or i == root.nodeNum:
-            continue
-        n = tree.nodes[i]
-        s = states[n.parent.nodeNum].copy()
-        m = rng.random(nSites) < min(0.9, mut * (0.3 + 5.0 * n.br.len))
-        s[m] = rng.integers(dim, size=int(m.sum()))
-        states[i] = s
-        if n.isLeaf:
-            out[n.seqNum] = s
-    return [out[k] for k in sorted(out)]
 
 
 def _build(pkg, symbols, nTax, nSites, nCat, seed, equates=None, pInvar=0.0, polytomy=False):
     P, H = pkg, pkg.host
-    rng = np.random.Generator(np.random.PCG64(seed))
-    dim = len(symbols)
-    tree = P.synth.random_tree(P.pf, nTax, rng)
+    tree = None
     if polytomy:        # collapse internal branches below the root until the root has 5 children
+        rng = np.random.Generator(np.random.PCG64(seed + 1000))
+        tree = P.synth.random_tree(P.pf, nTax, rng)
         while sum(1 for _ in tree.root.iterChildren()) < 5:
             c = next(k for k in tree.root.iterChildren() if not k.isLeaf)
             kids = list(c.iterChildren())
@@ -59,27 +40,7 @@ def _build(pkg, symbols, nTax, nSites, nCat, seed, equates=None, pInvar=0.0, pol
             for k, n in enumerate(tree.nodes):
                 n.nodeNum = k
         tree = H.Tree(P.pf, tree.nodes, tree.root)
-        tree.setPreAndPostOrder()
-    lut = np.frombuffer(symbols.encode(), dtype=np.uint8)
-    rows = _evolve(rng, tree, dim, nSites)
-    seqs = []
-    eqChars = sorted((equates or {}).keys())
-    for s in rows:
-        chars = lut[s].copy()
-        chars[rng.random(nSites) < 0.02] = ord("-")
-        for e in eqChars:
-            chars[rng.random(nSites) < 0.01] = ord(e)
-        seqs.append(chars.tobytes())
-    aln = H.Alignment(P.pf, seqs, symbols, equates or {})
-    mp = H.ModelPart(0, dim, nCat)
-    mp.comps.append(H.Comp(P.synth.normalise_comp(rng.dirichlet(20.0 * np.ones(dim)))))
-    r = rng.dirichlet(3.0 * np.ones(dim * (dim - 1) // 2))
-    mp.rMatrices.append(H.RMatrix("specified", r / r.sum()))
-    if nCat > 1:
-        mp.gdasrvs.append(H.Gdasrv(nCat, 0.7))
-    mp.pInvar = H.PInvar(pInvar)
-    tree.attach(H.Data(P.pf, [aln]), H.Model(P.pf, [mp]))
-    return tree
+    return P.synth.build_generic(P.pf, symbols, nTax, nSites, nCat, seed, equates=equates, pInvar=pInvar, tree=tree)
 
 
 def _compare(pkg, ref_pf, tree, clTol=1e-9):
