@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp4b200.so")
 SOURCES = ["capi.cpp", "data.cpp", "model.cpp", "comm.cpp", "opt.cpp", "praxis.cpp", "sim.cpp", "partstats.cpp", "tree.cu"]
-HEADERS = ["engine.h", "optim.h", "kernels.cuh", "tree_dna.cuh", "newt.cuh", "protein_rmatrices.inc", os.path.join("..", "..", "include", "p4b200.h")]
+HEADERS = ["engine.h", "optim.h", "kernels.cuh", "tree_dna.cuh", "tree_aa.cuh", "tree_dmma.cuh", "newt.cuh", "protein_rmatrices.inc", os.path.join("..", "..", "include", "p4b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

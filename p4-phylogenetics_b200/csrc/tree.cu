@@ -449,7 +449,7 @@ int treeDeviceCreate(Tree *t)
         L.tblOff = d->tblNodeDoubles;
         L.tblDoubles = (size_t)L.nCat * L.dim * L.W;
         d->tblNodeDoubles += (L.tblDoubles + 1) & ~(size_t)1;
-        if (L.dim == 20 && L.nCat == 4) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
+        if (L.dim == 20 && L.nCat <= 16) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
             L.auxOff = d->auxNodeDoubles;
             L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * kAA2TblStates * L.W;
             d->auxNodeDoubles += L.auxDoubles;
@@ -911,7 +911,7 @@ static bool fusedEligible(const PartLayout &L)
 {
     if (!g_fusedEnabled) return false;
     if (L.dim == 4) return L.nCat == 4 || L.nCat == 1 || (!L.scalers && L.nCat >= 2 && L.nCat <= 8 && g_fused2On());
-    if (L.dim == 20) return g_fusedAAEnabled && g_dmmaEnabled && L.nCat == 4 && !L.scalers && L.W <= 64;
+    if (L.dim == 20) return g_fusedAAEnabled && g_dmmaEnabled && L.nCat <= 16 && !L.scalers && L.W <= 64;
     if (L.dim > 20 && L.dim <= 64)    // two children x two buffers of max(P^T fragments, transposed leaf table) must fit shared memory
         return g_fusedAAEnabled && g_dmmaEnabled && !L.scalers && L.auxDP > 0 && L.nCat <= 64 &&
                4 * sizeof(double) * std::max(dmmaFragDoubles(L.auxDP), (size_t)L.W * L.auxDP) + 64 <= 200 * 1024;
@@ -1678,15 +1678,28 @@ static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *r
     a.tblW = L.W;
     a.nTrees = nJobs;
     a.tips = dp->dev.tips;
-    static int groups = -1, ringSel = 4;
-    if (groups < 0) {
-        const char *e = getenv("P4B_AA2_GROUPS");
+    // launch shape: generation 3 (one category per CTA, deep ring, asynchronous stores) with 16 warps x ring 8 by default;
+    // P4B_AA_GEN=2 selects the second generation (4 categories per CTA; nCat == 4 only), P4B_AA2_GROUPS / P4B_AA2_RING its shape,
+    // P4B_AA3_SHAPE the third generation's
+    static int gen = -1, groups = 4, ringSel = 4, dbgNoStore = 0, groups3 = 8, ring3 = 8, minb3 = 2, pm3 = 0;
+    if (gen < 0) {
+        const char *e = getenv("P4B_AA_GEN");
+        gen = e ? atoi(e) : 3;
+        if (gen != 2) gen = 3;
+        e = getenv("P4B_AA2_GROUPS");
         groups = e ? atoi(e) : 4;
         if (groups != 1 && groups != 2 && groups != 4) groups = 4;
         e = getenv("P4B_AA2_RING");
         ringSel = e ? atoi(e) : (groups == 4 ? 4 : 2);
         if (ringSel != 2 && ringSel != 4) ringSel = 2;
+        e = getenv("P4B_AA3_SHAPE");        // "warps,ring,CTAs per SM,pattern mapping"
+        if (e && sscanf(e, "%d,%d,%d,%d", &groups3, &ring3, &minb3, &pm3) != 4) { groups3 = 8; ring3 = 8; minb3 = 2; pm3 = 0; }
+        e = getenv("P4B_AA2_NOSTORE");      // measurement only: the CLs of an earlier evaluation stay in the arena
+        dbgNoStore = e ? atoi(e) : 0;
     }
+    a.pad0 = dbgNoStore;
+    a.nCat = L.nCat;
+    const int useGen = L.nCat == 4 ? gen : 3;
     static std::vector<Step2> steps;
     steps.clear();
     int maxSteps = 1;
@@ -1716,24 +1729,50 @@ static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *r
         if (a.hdr[i].nSteps > 0) anything = true;
     if (anything) {
         a.maxSteps = maxSteps;
-        size_t smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps);
-        if (smem > 220 * 1024 && ringSel == 4) { ringSel = 2; smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps); }
-        if (smem > 220 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
         if (uploadSteps2(steps)) return 1;
         a.steps = G.stepDev;
         typedef void (*Fn)(const TreeArgsAA2);
-        Fn fn = groups == 4 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 4, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 4, 2, 1>)
-              : groups == 2 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 2, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 2, 2, 2>)
-                            : (Fn)cl_tree_aa2_kernel<4, 1, 2, 3>;
         static std::unordered_set<void *> attrSet;
-        if (!attrSet.count((void *)fn)) {
+        auto prepare = [&](Fn fn) {
+            if (attrSet.count((void *)fn)) return 0;
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attrSet.insert((void *)fn);
+            return 0;
+        };
+        if (useGen == 3) {
+            // shapes: warps per CTA, ring depth, CTAs per SM the register budget is set for
+            struct Shape { int g, r, b, pm; Fn fn; };
+            static const Shape shapes[] = {
+                {16, 8, 1, 0, (Fn)cl_tree_aa3_kernel<16, 8, 1, 0>}, {8, 4, 2, 0, (Fn)cl_tree_aa3_kernel<8, 4, 2, 0>}, {8, 8, 2, 0, (Fn)cl_tree_aa3_kernel<8, 8, 2, 0>},
+                {4, 4, 4, 0, (Fn)cl_tree_aa3_kernel<4, 4, 4, 0>},   {4, 8, 4, 0, (Fn)cl_tree_aa3_kernel<4, 8, 4, 0>},
+                {16, 8, 1, 1, (Fn)cl_tree_aa3_kernel<16, 8, 1, 1>}, {8, 4, 2, 1, (Fn)cl_tree_aa3_kernel<8, 4, 2, 1>}, {8, 8, 2, 1, (Fn)cl_tree_aa3_kernel<8, 8, 2, 1>},
+                {4, 4, 4, 1, (Fn)cl_tree_aa3_kernel<4, 4, 4, 1>},   {4, 8, 4, 1, (Fn)cl_tree_aa3_kernel<4, 8, 4, 1>},
+                {4, 4, 5, 1, (Fn)cl_tree_aa3_kernel<4, 4, 5, 1>},   {8, 4, 3, 1, (Fn)cl_tree_aa3_kernel<8, 4, 3, 1>},
+            };
+            const Shape *sh = nullptr;
+            for (const Shape &c : shapes)
+                if (c.g == groups3 && c.r == ring3 && c.b == minb3 && c.pm == pm3) sh = &c;
+            if (!sh) { setError("P4B_AA3_SHAPE: no such launch shape of the 20-state whole-tree kernel"); return 1; }
+            const size_t smem = aa3SmemBytes(L.W, sh->g, sh->r, maxSteps);
+            if ((smem + 1024) * sh->b > 227 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
+            if (prepare(sh->fn)) return 1;
+            const int blocks = L.ps / (sh->g * 16);
+            sh->fn<<<dim3(blocks, nJobs, L.nCat), sh->g * 32, smem, G.stream>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa3_kernel<%d,%d,%d,%d> x %d categories", sh->g, sh->r, sh->b, sh->pm, L.nCat);
+        } else {
+            size_t smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps);
+            if (smem > 220 * 1024 && ringSel == 4) { ringSel = 2; smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps); }
+            if (smem > 220 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
+            Fn fn = groups == 4 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 4, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 4, 2, 1>)
+                  : groups == 2 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 2, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 2, 2, 2>)
+                                : (Fn)cl_tree_aa2_kernel<4, 1, 2, 3>;
+            if (prepare(fn)) return 1;
+            const int blocks = L.ps / (groups * 16);
+            fn<<<dim3(blocks, nJobs), L.nCat * groups * 32, smem, G.stream>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa2_kernel<%d,%d,%d>", L.nCat, groups, ringSel);
         }
-        const int blocks = L.ps / (groups * 16);
-        fn<<<dim3(blocks, nJobs), L.nCat * groups * 32, smem, G.stream>>>(a);
-        CUDA_TRY(cudaGetLastError());
-        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa2_kernel<%d,%d,%d>", L.nCat, groups, ringSel);
         G.launches++;
         for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
     }

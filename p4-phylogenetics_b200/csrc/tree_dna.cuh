@@ -93,7 +93,7 @@ __host__ inline size_t treeDna2SmemBytes(int nCat, int W, int CT, int CW, int ma
 {
     const int K = nCat * 4, PB = CW / (nCat / CT), RING = treeDna2Ring(CW);
     return treeDna2StepBytes(maxSteps) + RING * treeDna2SlotBytes(K, W, PB) + (size_t)CT * 4 * CW * 32 * 16 + (size_t)CW * 32 * 16 +
-           RING * 8 + RING * 4 + 16 + (2 * CW + 2) * 8;
+           RING * 8 + RING * 8 + 16 + (2 * CW + 2) * 8;
 }
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
@@ -101,6 +101,24 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)      /
 {
     unsigned done;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+    return done != 0u;
+}
+
+// Leaving a ring slot: a plain arrival on the slot's "empty" mbarrier.  (A shared-memory counter needs a fence in front of its
+// atomicAdd to order the warp's reads of the slot before it -- MEMBAR.SC.CTA, which also waits for every global STORE the
+// lane has in flight: the full latency of a store to L2 on every warp's path, once per step.  An mbarrier arrival carries
+// that ordering for shared memory by itself: one SYNCS.ARRIVE, no MEMBAR.)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_poll(uint64_t *bar, unsigned parity)      // non-blocking test: has the phase completed?
+{
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(done)
                  : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
                  : "memory");
@@ -192,8 +210,8 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     double2 *bufAll = reinterpret_cast<double2 *>(ring + RING * slotB);   // [KT][CTH]
     double2 *sA = bufAll + KT * CTH;                                  // hand-over of the category sum between the warps of a pattern block
     uint64_t *full = reinterpret_cast<uint64_t *>(sA + CTH);
-    unsigned *cnt = reinterpret_cast<unsigned *>(full + RING);
-    double *sRed = reinterpret_cast<double *>(cnt + RING + 2);        // [2][CW] + flag, 8-byte aligned
+    uint64_t *empty = full + RING;                                    // arrivals of the CW warps that have left the slot
+    double *sRed = reinterpret_cast<double *>(empty + RING + 1);      // [2][CW] + flag, 8-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t ps = (size_t)a.ps;
     const uint8_t *ctaTips = a.tips + (size_t)blockIdx.x * (PB * 64);     // the CTA's PB*64 patterns of tip row 0
@@ -227,7 +245,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             sNodes[i] = make_uint2(__ldg(&gSteps[i].n0), __ldg(&gSteps[i].n1));
         }
         if (threadIdx.x == 0) {
-            for (int i = 0; i < RING; i++) { mbar_init(full + i, 1); cnt[i] = 0u; }
+            for (int i = 0; i < RING; i++) { mbar_init(full + i, 1); mbar_init(empty + i, CW); }
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
     }
@@ -268,9 +286,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     int myNext = warp;
     auto service = [&](int done) {      // lane 0 only
         while (myNext <= done && myNext + RING < nSteps) {
-            volatile unsigned *c = cnt + (myNext & (RING - 1));
-            if (*c != (unsigned)CW) break;              // somebody is still working from that slot
-            *c = 0u;
+            if (!mbar_poll(empty + (myNext & (RING - 1)), (unsigned)(myNext / RING) & 1u)) break;   // somebody is still working from that slot
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the warps' reads of the slot precede the bulk copy's writes
             produce(myNext + RING);
             myNext += CW;
@@ -351,8 +367,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
         // this warp has left the slot
         __syncwarp();
         if (lane == 0) {
-            __threadfence_block();
-            atomicAdd(cnt + slot, 1u);
+            mbar_arrive(empty + slot);
             service(si);
         }
     }
