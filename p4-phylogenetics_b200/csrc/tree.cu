@@ -451,7 +451,7 @@ int treeDeviceCreate(Tree *t)
         d->tblNodeDoubles += (L.tblDoubles + 1) & ~(size_t)1;
         if (L.dim == 20 && L.nCat <= 16) {   // P^T in fragment order + transposed leaf table (kernels.cuh, pmatrix_kernel)
             L.auxOff = d->auxNodeDoubles;
-            L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * kAA2TblStates * L.W;
+            L.auxDoubles = (size_t)L.nCat * kAAFrag + (size_t)L.nCat * kAATblStates * L.W;
             d->auxNodeDoubles += L.auxDoubles;
         } else if (L.dim > 20 && L.dim <= 64 && !g_useScalers) {   // 21..64 states: the generic tensor-core kernel's decks (tree_dmma.cuh)
             L.auxDP = dmmaPaddedDim(L.dim);
@@ -1660,9 +1660,9 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
 }
 
 // ---------------------------------------------------------------------------
-// 20 states: the second-generation tensor-core whole-tree kernel (tree_aa.cuh)
+// 20 states: the tensor-core whole-tree kernel (tree_aa.cuh)
 // ---------------------------------------------------------------------------
-static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
+static int launchFusedAABatch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
 {
     if (flushPJobs()) return 1;
     Tree *t0 = jobs[0].t;
@@ -1671,35 +1671,24 @@ static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *r
     Part *dp = t0->data->parts[p];
     if (!d0->aux || L.auxDP != 0 || !L.auxDoubles) { setError("internal: 20-state whole-tree kernel without operand decks"); return 1; }
     if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
-    static TreeArgsAA2 a;
+    static TreeArgsAA a;
     memset(&a, 0, sizeof(a));
     a.ps = L.ps;
     a.nPat = L.nPat;
     a.tblW = L.W;
     a.nTrees = nJobs;
     a.tips = dp->dev.tips;
-    // launch shape: generation 3 (one category per CTA, deep ring, asynchronous stores) with 16 warps x ring 8 by default;
-    // P4B_AA_GEN=2 selects the second generation (4 categories per CTA; nCat == 4 only), P4B_AA2_GROUPS / P4B_AA2_RING its shape,
-    // P4B_AA3_SHAPE the third generation's
-    static int gen = -1, groups = 4, ringSel = 4, dbgNoStore = 0, groups3 = 8, ring3 = 8, minb3 = 2, pm3 = 0;
-    if (gen < 0) {
-        const char *e = getenv("P4B_AA_GEN");
-        gen = e ? atoi(e) : 3;
-        if (gen != 2) gen = 3;
-        e = getenv("P4B_AA2_GROUPS");
-        groups = e ? atoi(e) : 4;
-        if (groups != 1 && groups != 2 && groups != 4) groups = 4;
-        e = getenv("P4B_AA2_RING");
-        ringSel = e ? atoi(e) : (groups == 4 ? 4 : 2);
-        if (ringSel != 2 && ringSel != 4) ringSel = 2;
-        e = getenv("P4B_AA3_SHAPE");        // "warps,ring,CTAs per SM,pattern mapping"
-        if (e && sscanf(e, "%d,%d,%d,%d", &groups3, &ring3, &minb3, &pm3) != 4) { groups3 = 8; ring3 = 8; minb3 = 2; pm3 = 0; }
-        e = getenv("P4B_AA2_NOSTORE");      // measurement only: the CLs of an earlier evaluation stay in the arena
+    // launch shape "warps per CTA,ring depth,CTAs per SM": 8,8,2 unless P4B_AA_SHAPE says otherwise
+    static int shapeRead = 0, dbgNoStore = 0, groups3 = 8, ring3 = 8, minb3 = 2;
+    if (!shapeRead) {
+        shapeRead = 1;
+        const char *e = getenv("P4B_AA_SHAPE");
+        if (e && sscanf(e, "%d,%d,%d", &groups3, &ring3, &minb3) != 3) { groups3 = 8; ring3 = 8; minb3 = 2; }
+        e = getenv("P4B_AA_NOSTORE");      // measurement only: the CLs of an earlier evaluation stay in the arena
         dbgNoStore = e ? atoi(e) : 0;
     }
     a.pad0 = dbgNoStore;
     a.nCat = L.nCat;
-    const int useGen = L.nCat == 4 ? gen : 3;
     static std::vector<Step2> steps;
     steps.clear();
     int maxSteps = 1;
@@ -1731,7 +1720,7 @@ static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *r
         a.maxSteps = maxSteps;
         if (uploadSteps2(steps)) return 1;
         a.steps = G.stepDev;
-        typedef void (*Fn)(const TreeArgsAA2);
+        typedef void (*Fn)(const TreeArgsAA);
         static std::unordered_set<void *> attrSet;
         auto prepare = [&](Fn fn) {
             if (attrSet.count((void *)fn)) return 0;
@@ -1739,40 +1728,25 @@ static int launchFusedAA2Batch(const FusedJob *jobs, int nJobs, int p, double *r
             attrSet.insert((void *)fn);
             return 0;
         };
-        if (useGen == 3) {
-            // shapes: warps per CTA, ring depth, CTAs per SM the register budget is set for
-            struct Shape { int g, r, b, pm; Fn fn; };
-            static const Shape shapes[] = {
-                {16, 8, 1, 0, (Fn)cl_tree_aa3_kernel<16, 8, 1, 0>}, {8, 4, 2, 0, (Fn)cl_tree_aa3_kernel<8, 4, 2, 0>}, {8, 8, 2, 0, (Fn)cl_tree_aa3_kernel<8, 8, 2, 0>},
-                {4, 4, 4, 0, (Fn)cl_tree_aa3_kernel<4, 4, 4, 0>},   {4, 8, 4, 0, (Fn)cl_tree_aa3_kernel<4, 8, 4, 0>},
-                {16, 8, 1, 1, (Fn)cl_tree_aa3_kernel<16, 8, 1, 1>}, {8, 4, 2, 1, (Fn)cl_tree_aa3_kernel<8, 4, 2, 1>}, {8, 8, 2, 1, (Fn)cl_tree_aa3_kernel<8, 8, 2, 1>},
-                {4, 4, 4, 1, (Fn)cl_tree_aa3_kernel<4, 4, 4, 1>},   {4, 8, 4, 1, (Fn)cl_tree_aa3_kernel<4, 8, 4, 1>},
-                {4, 4, 5, 1, (Fn)cl_tree_aa3_kernel<4, 4, 5, 1>},   {8, 4, 3, 1, (Fn)cl_tree_aa3_kernel<8, 4, 3, 1>},
-            };
-            const Shape *sh = nullptr;
-            for (const Shape &c : shapes)
-                if (c.g == groups3 && c.r == ring3 && c.b == minb3 && c.pm == pm3) sh = &c;
-            if (!sh) { setError("P4B_AA3_SHAPE: no such launch shape of the 20-state whole-tree kernel"); return 1; }
-            const size_t smem = aa3SmemBytes(L.W, sh->g, sh->r, maxSteps);
-            if ((smem + 1024) * sh->b > 227 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
-            if (prepare(sh->fn)) return 1;
-            const int blocks = L.ps / (sh->g * 16);
-            sh->fn<<<dim3(blocks, nJobs, L.nCat), sh->g * 32, smem, G.stream>>>(a);
-            CUDA_TRY(cudaGetLastError());
-            snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa3_kernel<%d,%d,%d,%d> x %d categories", sh->g, sh->r, sh->b, sh->pm, L.nCat);
-        } else {
-            size_t smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps);
-            if (smem > 220 * 1024 && ringSel == 4) { ringSel = 2; smem = aa2SmemBytes(L.nCat, L.W, groups, ringSel, maxSteps); }
-            if (smem > 220 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
-            Fn fn = groups == 4 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 4, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 4, 2, 1>)
-                  : groups == 2 ? (ringSel == 4 ? (Fn)cl_tree_aa2_kernel<4, 2, 4, 1> : (Fn)cl_tree_aa2_kernel<4, 2, 2, 2>)
-                                : (Fn)cl_tree_aa2_kernel<4, 1, 2, 3>;
-            if (prepare(fn)) return 1;
-            const int blocks = L.ps / (groups * 16);
-            fn<<<dim3(blocks, nJobs), L.nCat * groups * 32, smem, G.stream>>>(a);
-            CUDA_TRY(cudaGetLastError());
-            snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa2_kernel<%d,%d,%d>", L.nCat, groups, ringSel);
+        struct Shape { int g, r, b; Fn fn; };
+        static const Shape shapes[] = {
+            {8, 8, 2, (Fn)cl_tree_aa_kernel<8, 8, 2>}, {8, 4, 2, (Fn)cl_tree_aa_kernel<8, 4, 2>}, {4, 4, 4, (Fn)cl_tree_aa_kernel<4, 4, 4>}, {16, 8, 1, (Fn)cl_tree_aa_kernel<16, 8, 1>},
+        };
+        const Shape *sh = nullptr;
+        for (const Shape &c : shapes)
+            if (c.g == groups3 && c.r == ring3 && c.b == minb3) sh = &c;
+        if (!sh) { setError("P4B_AA_SHAPE: no such launch shape of the 20-state whole-tree kernel"); return 1; }
+        size_t smem = aaSmemBytes(L.W, sh->g, sh->r, maxSteps);
+        if ((smem + 1024) * sh->b > 227 * 1024 && sh->g == 8 && sh->r == 8) {      // wide leaf tables or a long step list: the shallower ring
+            sh = &shapes[1];
+            smem = aaSmemBytes(L.W, sh->g, sh->r, maxSteps);
         }
+        if (smem > 220 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
+        if (prepare(sh->fn)) return 1;
+        const int blocks = L.ps / (sh->g * 16);
+        sh->fn<<<dim3(blocks, nJobs, L.nCat), sh->g * 32, smem, G.stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa_kernel<%d,%d,%d> x %d categories", sh->g, sh->r, sh->b, L.nCat);
         G.launches++;
         for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
     }
@@ -1890,7 +1864,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         if (L0.dim == 4 && !L0.scalers && g_fused2 && g_fused2On()) return launchFused2Batch(jobs, nJobs, p, resultDev);
         if (L0.dim == 4 && L0.nCat != 4 && L0.nCat != 1) { setError("internal: the first-generation whole-tree kernel serves 1 or 4 rate categories"); return 1; }
         if (L0.dim > 20) return launchFusedDmmaBatch(jobs, nJobs, p, resultDev);
-        if (L0.dim == 20) return launchFusedAA2Batch(jobs, nJobs, p, resultDev);
+        if (L0.dim == 20) return launchFusedAABatch(jobs, nJobs, p, resultDev);
     }
     if (flushPJobs()) return 1;
     Tree *t0 = jobs[0].t;
@@ -1909,7 +1883,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.counts = dp->dev.counts;
     a.invarMask = dp->dev.invarMask;
     a.eqMask = dp->dev.equateMask;
-    const bool aa = false;            // (20-state parts have their own launch path: launchFusedAA2Batch)
+    const bool aa = false;            // (20-state parts have their own launch path: launchFusedAABatch)
     const int variant = fusedVariant(L.ps, nJobs);
     static const int kThreads[9] = {128, 64, 32, 128, 256, 64, 32, 64, 32};
     const int aaGroups = 1, aaMinB = 1, aaMT = 2;
@@ -2688,8 +2662,8 @@ int nodeSetBigP(Node *n, int p, const double *in)
             const int s = 8 * nt + (l >> 2), x = kk < 4 ? 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1) : 16 + (l & 3);
             A[i] = (s < dim && x < dim) ? in[((size_t)ct * dim + s) * dim + x] : 0.0;
         }
-        for (int i = 0; i < L.nCat * W * kAA2TblStates; i++) {
-            const int st = i % kAA2TblStates, w = (i / kAA2TblStates) % W, ct = i / (kAA2TblStates * W);
+        for (int i = 0; i < L.nCat * W * kAATblStates; i++) {
+            const int st = i % kAATblStates, w = (i / kAATblStates) % W, ct = i / (kAATblStates * W);
             A[nF + i] = st < dim ? T[((size_t)ct * dim + st) * W + w] : 0.0;
         }
         CUDA_TRY(cudaMemcpyAsync(nodeAux(n, p), A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));

@@ -1,5 +1,5 @@
-"""The whole-tree 20-state kernel (cl_tree_aa2_kernel, tree_aa.cuh: FP64 tensor cores, running CL in accumulator
-registers) against the one-launch-per-node kernels and the reference engine."""
+"""The whole-tree 20-state kernel (cl_tree_aa_kernel, tree_aa.cuh: FP64 tensor cores, running CL in accumulator
+registers, one rate category per CTA) against the one-launch-per-node kernels and the reference engine."""
 import numpy as np
 import pytest
 
@@ -43,6 +43,30 @@ def test_whole_tree_kernel_equals_per_node_kernels(pkg, ref_pf, cfg, kw):
         for k in x:
             scale = np.max(np.abs(y[k]), axis=(0, 1), keepdims=True)
             assert np.max(np.abs(x[k] - y[k]) / scale) < 1e-13, "CL of node %d" % k
+
+
+@pytest.mark.parametrize("nCat", [1, 2, 3, 6, 8])
+def test_any_number_of_rate_categories(pkg, ref_pf, nCat):
+    """The reference is generic in nCat (Pf/p4_node.c:652-654); the whole-tree kernel takes a category per CTA, so any
+    number is served: lnL and EVERY node's CL array against the reference engine, gaps and ambiguity codes included."""
+    P, pf = pkg, pkg.pf
+    rng = np.random.Generator(np.random.PCG64(40 + nCat))
+    tree = P.synth.random_tree(pf, 13, rng)
+    mp = P.synth.protein_model_part(0, rng, "lg", nCat)
+    aln = P.synth.make_alignment(pf, tree, mp, 700, rng, "protein", gap_frac=0.03, ambig_frac=0.03)
+    tree.attach(P.host.Data(pf, [aln]), P.host.Model(pf, [mp]))
+    twin = P.host.clone_tree(tree, ref_pf)
+    got, want = tree.calcLogLike(), twin.calcLogLike()
+    assert pf.lastCLKernelName().startswith("cl_tree_aa_kernel"), pf.lastCLKernelName()
+    assert rel(got, want) <= LNL_TOL
+    rp = ref_peek.part_arrays(twin.data.parts[0].cPart)
+    for a, b in zip(tree.nodes, twin.nodes):
+        if a.isLeaf:
+            continue
+        c1 = pf.getNodeCL(tree.cTree, a.cNode, 0, nCat, 20)
+        c0 = ref_peek.node_cl(b.cNode, 0, nCat, 20, rp["nChar"], rp["nPatterns"])
+        scale = np.max(np.abs(c0), axis=(0, 1), keepdims=True)
+        assert np.max(np.abs(c1 - c0) / scale) < 1e-9, "CL of node %d" % a.nodeNum
 
 
 def test_cl_arrays_match_reference(pkg, ref_pf):

@@ -1,7 +1,7 @@
 """tools/sweep_aa.py -- one device-timed line for the 20-state whole-tree kernel on BASELINE config 3 (or 4).
 
-The launch shape is chosen by environment variables read once per process (P4B_AA2_GROUPS, P4B_AA2_RING, P4B_AA2_KERNEL,
-P4B_AA2_NOSTORE), so a sweep is one process per shape:  for g in 4 2 1; do P4B_AA2_GROUPS=$g python tools/sweep_aa.py; done
+The launch shape is chosen by environment variables read once per process (P4B_AA_SHAPE = "warps per CTA,ring depth,CTAs per SM",
+P4B_AA_NOSTORE), so a sweep is one process per shape:  for s in 8,8,2 8,4,2 4,4,4 16,8,1; do P4B_AA_SHAPE=$s python tools/sweep_aa.py; done
 """
 import argparse
 import json
@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--taxa", type=int, default=None)
     ap.add_argument("--patterns", type=int, default=None)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--sustain", type=float, default=0.0, help="seconds of back-to-back evaluations with SM clock / power sampling")
     ap.add_argument("--want", type=float, default=None, help="lnL expected (printed with the relative difference)")
     a = ap.parse_args()
     pf = P.pf
@@ -31,8 +32,37 @@ def main():
     for _ in range(a.steps):
         lnL = pf.p4_treeLogLike(tree.cTree, 0)
     ms = pf.treeTimerEnd(tree.cTree) / a.steps
-    env = {k: v for k, v in os.environ.items() if k.startswith("P4B_AA2")}
+    clocks = None
+    if a.sustain > 0:      # the same call back to back for a while, SM clock and power sampled through NVML every 5 ms
+        import threading
+        import time
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        sm, pw, stop = [], [], []
+
+        def loop():
+            while not stop:
+                sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                pw.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                time.sleep(0.005)
+        th = threading.Thread(target=loop)
+        n = max(1, int(a.sustain * 1000.0 / ms))
+        th.start()
+        pf.treeTimerBegin(tree.cTree)
+        for _ in range(n):
+            pf.p4_treeLogLike(tree.cTree, 0)
+        ms2 = pf.treeTimerEnd(tree.cTree) / n
+        stop.append(1)
+        th.join()
+        sm.sort()
+        pw.sort()
+        clocks = {"sustained_ms": ms2, "steps": n, "sm_mhz_median": sm[len(sm) // 2], "sm_mhz_min": sm[0], "power_w_median": pw[len(pw) // 2], "power_w_max": pw[-1],
+                  "sm_max_mhz": pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), "power_limit_w": pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0}
+    env = {k: v for k, v in os.environ.items() if k.startswith("P4B_AA")}
     rec = {"cfg": a.cfg, "env": env, "kernel": pf.lastCLKernelName(), "ms": ms, "cl_ms": pf.treeLastCLTiming(tree.cTree)[0], "lnL": lnL}
+    if clocks:
+        rec["clocks"] = clocks
     if a.want is not None:
         rec["rel"] = abs(lnL - a.want) / abs(a.want)
     print("SWEEPAA" + json.dumps(rec), flush=True)
