@@ -1706,10 +1706,12 @@ static int launchFusedAABatch(const FusedJob *jobs, int nJobs, int p, double *re
         a.hdr[i].stepBase = (int)steps.size();
         TreeHdr2 h;
         memset(&h, 0, sizeof(h));
-        FusedJob job = jobs[i];
-        job.storeAll = true;          // (no lnL-only mode here: the root reduction reads the root's CL from memory)
-        const int ns = buildSteps2(steps, h, job, p, 1);
+        const int ns = buildSteps2(steps, h, jobs[i], p, 1);
         if (ns < 0) return 1;
+        if (!jobs[i].storeAll && jobs[i].withLike && ns > 0) {      // lnL-only: the root reduction reads the root's CL from memory
+            steps.back().flags |= kStepStore;
+            t->root->clResident[p] = 1;
+        }
         a.hdr[i].nSteps = ns;
         if (ns > maxSteps) maxSteps = ns;
     }
@@ -2279,7 +2281,7 @@ double treeLogLike(Tree *t, int getSiteLikes)
     std::vector<char> likeDone(t->nParts, 0);
     for (int p = 0; p < t->nParts; p++) {
         if (fusedEligible(d->parts[p])) {
-            const bool storeAll = t->storeCL != 0 || d->parts[p].dim != 4 || order.size() + 8 > (size_t)kMaxSteps;
+            const bool storeAll = t->storeCL != 0 || (d->parts[p].dim != 4 && d->parts[p].dim != 20) || order.size() + 8 > (size_t)kMaxSteps;
             if (launchFusedTree(t, p, order, true, getSiteLikes != 0, storeAll)) return NAN;
             likeDone[p] = 1;
             if (getSiteLikes && fillSiteLikes(t, p)) return NAN;

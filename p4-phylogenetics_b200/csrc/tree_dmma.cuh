@@ -113,7 +113,17 @@ cl_tree_dmma_kernel(const __grid_constant__ TreeArgs a, const int dim, const int
         int regChild = -1;
         for (int c = 0; c < nc; c++)
             if (((unsigned)st.ch[c].a >> 30) == 1u) regChild = c;
-        if (regChild >= 0) {
+        // The two warps that share a scheduler (w and w + 4) take a step's children in opposite orders: while one runs the
+        // DMMAs of the child in registers the other is in its table lookups, instead of both queueing for the tensor pipe and
+        // then both leaving it idle (the steps are in lock step: one CTA barrier each).  A product of factors is the same
+        // number in either order.
+        const bool regLast = regChild >= 0 && nc > 1 && st.first && ((warp >> 2) & 1);
+        if (regLast) {
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int t = 0; t < NT; t++) out[j][t][0] = out[j][t][1] = 1.0;
+        } else if (regChild >= 0) {
             contract(in, buf + regChild * slot + lane, out, true);
         } else if (!st.first) {
 #pragma unroll
@@ -170,6 +180,7 @@ cl_tree_dmma_kernel(const __grid_constant__ TreeArgs a, const int dim, const int
                 contract(sib, buf + c * slot + lane, out, false);
             }
         }
+        if (regLast) contract(in, buf + regChild * slot + lane, out, false);
         if (st.store) {
             double *o = hd.arena + (size_t)(unsigned)st.outSlot * 32 + rowBase;
 #pragma unroll

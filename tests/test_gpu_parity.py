@@ -262,11 +262,12 @@ def test_tensor_core_kernel_equals_fma_kernel(pkg, ref_pf, cfg, kw):
         assert max_rel_err(cl_b[k], cl_a[k]) < 1e-12, k
 
 
-def test_lnl_only_mode_is_transparent(pkg, ref_pf):
+@pytest.mark.parametrize("cfg,kw", [(2, dict(nTax=30, nPatterns=2500)), (3, dict(nTax=21, nPatterns=900))])
+def test_lnl_only_mode_is_transparent(pkg, ref_pf, cfg, kw):
     """p4b_setTreeStoresCL(0): whole-tree evaluations keep only the CLs they re-read; anything that
-    later needs a CL gets it recomputed.  lnL, CLs and the dirty path must be unaffected."""
+    later needs a CL gets it recomputed.  lnL, CLs and the dirty path must be unaffected (4 and 20 states)."""
     pf = pkg.pf
-    mine, twin = build_pair(pkg, ref_pf, 2, nTax=30, nPatterns=2500)
+    mine, twin = build_pair(pkg, ref_pf, cfg, **kw)
     want = twin.calcLogLike()
     full = mine.calcLogLike()
     mp = mine.model.parts[0]

@@ -20,12 +20,18 @@ def main():
     ap.add_argument("--patterns", type=int, default=None)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--sustain", type=float, default=0.0, help="seconds of back-to-back evaluations with SM clock / power sampling")
+    ap.add_argument("--lean", action="store_true", help="lnL-only evaluations (p4b_setTreeStoresCL(0))")
     ap.add_argument("--want", type=float, default=None, help="lnL expected (printed with the relative difference)")
     a = ap.parse_args()
     pf = P.pf
     pf.setMemoize(0)
-    tree = P.synth.build_config(pf, a.cfg, nTax=a.taxa, nPatterns=a.patterns)
+    if a.cfg == 61:      # the 61-state case of bench.py's codon61 block (generic tensor-core kernel, tree_dmma.cuh)
+        tree = P.synth.build_generic(pf, P.synth.SYMBOLS_61, a.taxa or 32, a.patterns or 60000, 4, 6161, equates={"!": "abcd"})
+    else:
+        tree = P.synth.build_config(pf, a.cfg, nTax=a.taxa, nPatterns=a.patterns)
     lnL = tree.calcLogLike()
+    if a.lean:
+        pf.setTreeStoresCL(tree.cTree, 0)
     for _ in range(3):
         pf.p4_treeLogLike(tree.cTree, 0)
     pf.treeTimerBegin(tree.cTree)
