@@ -442,12 +442,30 @@ def config_block(P, pf, cfg, peak, steps, real_p4=True):
     e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
     comp, alg, flops = work_model(pf, tree)
     dim = tree.model.parts[0].dim
+    kernel = pf.lastCLKernelName()
+    nPat0 = pf.partPatternCount(tree.data.parts[0].cPart)
+    traffic, traffic_src = measured_traffic(kernel, sum(1 for n in tree.nodes if n.isLeaf), nPat0)
+    if traffic and tree.model.nParts > 1:      # one capture = one launch = one part; the parts are the same size to a pattern
+        traffic, traffic_src = traffic * tree.model.nParts, traffic_src + " x %d parts" % tree.model.nParts
+    lean_ms = None
+    if dim in (4, 20):      # lnL-only evaluations (p4b_setTreeStoresCL(0)): what the optimisers' objective runs
+        pf.setTreeStoresCL(tree.cTree, 0)
+        for _ in range(3):
+            pf.p4_treeLogLike(tree.cTree, 0)
+        pf.treeTimerBegin(tree.cTree)
+        for _ in range(steps):
+            pf.p4_treeLogLike(tree.cTree, 0)
+        lean_ms = pf.treeTimerEnd(tree.cTree) / steps
+        pf.setTreeStoresCL(tree.cTree, 1)
+        tree.calcLogLike()
     out = {"workload": CFG_NAMES[cfg], "taxa": sum(1 for n in tree.nodes if n.isLeaf), "parts": tree.model.nParts,
            "patterns": [pf.partPatternCount(p.cPart) for p in tree.data.parts], "lnL": lnL, "setup_s": round(setup, 1),
            "ms_per_eval": ms, "evals_per_s": 1000.0 / ms, "e2e_calcLogLike_evals_per_s": 1000.0 / e2e_ms,
            "roofline": {"bound": "hbm", "achieved": comp / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": comp / ms / 1e6 / peak,
                         "basis": "compulsory bytes: every internal CL stored once + tips + counts", "compulsory_GB": comp / 1e9,
-                        "algorithmic_8d_GB": alg / 1e9, "algorithmic_8d_GBps": alg / ms / 1e6}}
+                        "algorithmic_8d_GB": alg / 1e9, "algorithmic_8d_GBps": alg / ms / 1e6,
+                        "kernel": kernel, "traffic": traffic, "traffic_source": traffic_src},
+           "lnl_only_ms_per_eval": lean_ms}
     if dim == 20:
         out["roofline"]["tensor"] = {"GFLOP_per_eval": flops / 1e9, "TFLOPs": flops / ms / 1e9, "peak_TFLOPs": FP64_DMMA_TFLOPS,
                                      "frac": flops / ms / 1e9 / FP64_DMMA_TFLOPS, "peak_source": "FP64 mma.sync m8n8k4 microbenchmark (profiles/r2_membw.txt)"}
@@ -538,7 +556,7 @@ def codon61_block(P, pf, peak, nTax=32, nSites=60000, nCat=4):
     return out
 
 
-def real_p4_mcmc(taxa=100, patterns=500000, chains=8, gens=40):
+def real_p4_mcmc(taxa=100, patterns=500000, chains=8, gens=160):
     """Config 5 through the reference's REAL p4 package (its own Mcmc.run / Chain code, staged under oracle/_ref/p4) with
     this repository's pf module as p4.pf -- a process of its own (tests/dropin/p4_like_side.py)."""
     import ref_loader

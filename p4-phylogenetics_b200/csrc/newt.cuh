@@ -623,6 +623,185 @@ newt_aa_kernel(const NewtArgs a, unsigned *__restrict__ ticket, double *__restri
     }
 }
 
+// ---------------------------------------------------------------------------
+// 20 states, internal node, on the FP64 tensor cores.  The three sums of a pattern and category are
+//     like / first / second = SUM_f z[f] * (D_d x)[f],   D_0 = P(v), D_1 = dP/dv, D_2 = d2P/dv2 (20 x 20 each)
+// (Pf/p4_treeNewt.c:238-520): three matrix products with the node's CL -- the contraction of the whole-tree kernel
+// (tree_aa.cuh) with D_d in the place of P: Y^T = x^T D_d^T on mma.sync.m8n8k4, patterns as rows, the summation index
+// dealt to the k-steps so that k-step (t, i) covers the states {8t + 2q + i} and a fifth one the states 16 + q; 15 DMMAs
+// per deck and 8 patterns, 45 for the three decks, where the FMA kernel above spends 1260 FMAs and 15 shared-memory reads
+// per pattern.  A lane then holds Y[pattern g][f = 8nt + 2q + i]; it weights them with z[f] (read in the same layout),
+// adds up over its f's and over the categories, and the quad (q = 0..3) folds its four partial sums: the order of the
+// additions differs from the reference's f-then-category order by rounding only.
+// A warp owns 16 patterns (two m-tiles; a lane's two patterns are one 16-byte access) and takes tiles round-robin
+// (persistent CTAs); the CTA's prologue lays the three decks out in shared memory in fragment order
+// [deck][cat][k-step][n-tile][lane] (zero rows for the padding states 20..23).  The last CTA folds the partials.
+// ---------------------------------------------------------------------------
+template <int WARPS, int MINB, int NCAT>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+newt_aa_dmma_kernel(const NewtArgs a, unsigned *__restrict__ ticket, double *__restrict__ result)
+{
+    constexpr int DIM = 20, FRAG = 15 * 32, MT = 2;
+    extern __shared__ double sF[];            // [3][nCat][FRAG]
+    __shared__ double sRed[3][WARPS];
+    __shared__ bool sLast;
+    const int nCat = NCAT ? NCAT : a.nCat;
+    {
+        const int per = nCat * DIM * DIM, total = 3 * nCat * FRAG;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int r = i % FRAG, ct = (i / FRAG) % nCat, d = i / (FRAG * nCat);
+            const int l = r & 31, nt = (r >> 5) % 3, kk = r / 96;
+            const int f = 8 * nt + (l >> 2), x = kk < 4 ? 8 * (kk >> 1) + 2 * (l & 3) + (kk & 1) : 16 + (l & 3);
+            sF[i] = f < DIM ? a.decks[(size_t)d * per + (size_t)ct * DIM * DIM + f * DIM + x] : 0.0;
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const size_t ps = (size_t)a.ps;
+    const int nTiles = a.ps >> 4, tileStride = gridDim.x * WARPS;
+    double tL = 0.0, tF = 0.0, tS = 0.0;
+
+    struct Ops { double A[5][MT], Z[3][2][MT]; };
+    // the lane's operands of one (tile, category): x in the A layout (states 8t + 2q + i and 16 + q), z in the C layout
+    auto load = [&](int tile, int c, Ops &o) {
+        const size_t base = (size_t)c * DIM * ps + (size_t)tile * 16 + MT * g;
+        const double *x = a.cl + base, *z = a.cl2 + base;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {            // states 8t + 2q + i, t = r >> 1, i = r & 1
+            const size_t row = (size_t)(8 * (r >> 1) + 2 * q + (r & 1)) * ps;
+            const double2 xv = ld2(x + row), zv = ld2(z + row);
+            o.A[r][0] = xv.x;
+            o.A[r][1] = xv.y;
+            o.Z[r >> 1][r & 1][0] = zv.x;
+            o.Z[r >> 1][r & 1][1] = zv.y;
+        }
+        {
+            const double2 xv = ld2(x + (size_t)(16 + q) * ps);     // the fifth k-step's operand: state 16 + q
+            o.A[4][0] = xv.x;
+            o.A[4][1] = xv.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {            // states 16 + 2q + i exist for q < 2; the padding states weigh nothing
+            double2 zv = make_double2(0.0, 0.0);
+            if (q < 2) zv = ld2(z + (size_t)(16 + 2 * q + i) * ps);
+            o.Z[2][i][0] = zv.x;
+            o.Z[2][i][1] = zv.y;
+        }
+    };
+    auto compute = [&](int c, const Ops &o, double (&sum)[3][MT]) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double *Bc = sF + ((size_t)d * nCat + c) * FRAG + lane;
+            double acc[MT][3][2];
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) acc[j][nt][0] = acc[j][nt][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 5; kk++) {
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) {
+                    const double b = Bc[(kk * 3 + nt) * 32];
+#pragma unroll
+                    for (int j = 0; j < MT; j++) dmma884(acc[j][nt][0], acc[j][nt][1], o.A[kk][j], b);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) {
+                    sum[d][j] = fma(o.Z[nt][0][j], acc[j][nt][0], sum[d][j]);
+                    sum[d][j] = fma(o.Z[nt][1][j], acc[j][nt][1], sum[d][j]);
+                }
+        }
+    };
+    auto finish = [&](int tile, double (&sum)[3][MT]) {
+        // the quad's four lanes hold the sums over their own f's: fold them (every lane ends with the total)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+            for (int j = 0; j < MT; j++) {
+                double v = sum[d][j];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                sum[d][j] = v;
+            }
+        // lane q = 0 finishes the quad's first pattern, lane q = 1 the second
+        if (q < MT) {
+            const int pp = tile * 16 + MT * g + q;
+            if (pp < a.nPat) newt_finish(a, pp, DIM, nCat, q ? sum[0][1] : sum[0][0], q ? sum[1][1] : sum[1][0], q ? sum[2][1] : sum[2][0], tL, tF, tS);
+        }
+    };
+
+    if (NCAT > 0 && (NCAT & 1) == 0) {
+        // an even number of categories known at compile time: the operands of the next (tile, category) are requested
+        // before the DMMAs of the current one, in two operand sets that swap roles (the unrolled loop indexes them statically)
+        Ops o[2];
+        int tile = blockIdx.x * WARPS + warp;
+        if (tile < nTiles) load(tile, 0, o[0]);
+        for (; tile < nTiles; tile += tileStride) {
+            double sum[3][MT];
+#pragma unroll
+            for (int d = 0; d < 3; d++) sum[d][0] = sum[d][1] = 0.0;
+#pragma unroll
+            for (int c = 0; c < (NCAT ? NCAT : 1); c++) {
+                if (c + 1 < NCAT) load(tile, c + 1, o[(c + 1) & 1]);
+                else if (tile + tileStride < nTiles) load(tile + tileStride, 0, o[(c + 1) & 1]);
+                compute(c, o[c & 1], sum);
+            }
+            finish(tile, sum);
+        }
+    } else {
+        for (int tile = blockIdx.x * WARPS + warp; tile < nTiles; tile += tileStride) {
+            double sum[3][MT];
+#pragma unroll
+            for (int d = 0; d < 3; d++) sum[d][0] = sum[d][1] = 0.0;
+            for (int c = 0; c < nCat; c++) {
+                Ops o;
+                load(tile, c, o);
+                compute(c, o, sum);
+            }
+            finish(tile, sum);
+        }
+    }
+    tL = warpSum(tL);
+    tF = warpSum(tF);
+    tS = warpSum(tS);
+    if (lane == 0) { sRed[0][warp] = tL; sRed[1][warp] = tF; sRed[2][warp] = tS; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = 0; i < WARPS; i++) { v[0] += sRed[0][i]; v[1] += sRed[1][i]; v[2] += sRed[2][i]; }
+        a.partials[3 * blockIdx.x] = v[0];
+        a.partials[3 * blockIdx.x + 1] = v[1];
+        a.partials[3 * blockIdx.x + 2] = v[2];
+        __threadfence();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);   // wraps to 0 with the last CTA: ready for the next launch
+        sLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLast) {
+        __threadfence();
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            v[0] += __ldcg(a.partials + 3 * i);
+            v[1] += __ldcg(a.partials + 3 * i + 1);
+            v[2] += __ldcg(a.partials + 3 * i + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = warpSum(v[k]);
+            if (lane == 0) sRed[k][warp] = v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double s2 = 0.0;
+            for (int i = 0; i < WARPS; i++) s2 += sRed[threadIdx.x][i];
+            result[threadIdx.x] = s2;
+        }
+    }
+}
+
 // One block folds the per-block partials in a fixed order (deterministic): result[0..2].
 __global__ void __launch_bounds__(256)
 newt_final_kernel(const double *__restrict__ partials, int n, double *__restrict__ result)

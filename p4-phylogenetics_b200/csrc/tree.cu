@@ -888,6 +888,7 @@ int treeCalculateAllBigPDecks(Tree *t)   // Pf/p4_tree.c p4_calculateAllBigPDeck
 // Conditional likelihoods
 // ---------------------------------------------------------------------------
 static bool g_dmmaEnabled = true;
+static const bool g_newtDmma = [] { const char *e = getenv("P4B_NEWT_DMMA"); return e ? atoi(e) != 0 : true; }();   // 0: the FMA derivative kernel for 20-state internal nodes too
 void setDmmaEnabled(int on) { g_dmmaEnabled = on != 0; }
 static bool g_fusedEnabled = true;
 static bool g_deferCL = true;
@@ -3054,6 +3055,29 @@ static int newtDerivs(Tree *t, Node *n, double out[3])
             CUDA_TRY(cudaFuncSetAttribute(newt_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(newt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attrSet = true;
+        }
+        if (L.dim == 20 && !n->isLeaf && g_dmmaEnabled && g_newtDmma && (size_t)3 * L.nCat * 480 * sizeof(double) <= 200 * 1024 && S->maxBlocks >= 3 * G.numSMs) {
+            // an internal node on the FP64 tensor cores: persistent CTAs, 16 patterns per warp and tile
+            const size_t fragBytes = (size_t)3 * L.nCat * 480 * sizeof(double);
+            typedef void (*NFn)(const NewtArgs, unsigned *, double *);
+            static int shape = -1;          // 0: 4 warps x 3 CTAs per SM (168 registers); 1: 8 warps x 2 (128 registers)
+            static const NFn fns[2][2] = {{(NFn)newt_aa_dmma_kernel<4, 3, 4>, (NFn)newt_aa_dmma_kernel<4, 3, 0>},
+                                          {(NFn)newt_aa_dmma_kernel<8, 2, 4>, (NFn)newt_aa_dmma_kernel<8, 2, 0>}};
+            if (shape < 0) {
+                const char *e = getenv("P4B_NEWT_DMMA_SHAPE");
+                shape = e ? (atoi(e) != 0) : 0;
+                for (int i = 0; i < 4; i++) CUDA_TRY(cudaFuncSetAttribute(fns[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            }
+            const int warps = shape == 0 ? 4 : 8, want = shape == 0 ? 3 : 2;
+            int perSM = (int)((227 * 1024) / (fragBytes + 2048));
+            if (perSM > want) perSM = want;
+            if (perSM < 1) perSM = 1;
+            int grid = (L.ps / 16 + warps - 1) / warps;
+            if (grid > G.numSMs * perSM) grid = G.numSMs * perSM;
+            fns[shape][L.nCat == 4 ? 0 : 1]<<<grid, warps * 32, fragBytes, G.stream>>>(a, S->ticket, S->result + 3 * p);
+            CUDA_TRY(cudaGetLastError());
+            G.launches++;
+            continue;
         }
         if (L.dim == 20 && a.useSmem) {
             // two patterns per thread, the last CTA folds: deck launch + this one
