@@ -38,22 +38,25 @@ struct NewtDeckJob {
     double r2[16];         // factor of the second derivative per category, squared by the kernel (:505-534)
 };
 
-// grid.x = rate category: the CTA of category c forms that category's slices of the three decks and tables.
+// grid.x = rate category: the CTA of category c forms that category's slices of the three decks and tables.  The
+// eigensystem is staged in shared memory first (every entry of a deck reads a row of V and a column of V^-1), and the
+// category's deck slices stay there for the table pass: nothing on the 20-term sums' path comes from global memory.
+// Shared memory: V | V^-1 | lambda | exp(lambda t0) | exp(lambda t1) | the three deck slices = (5 dim^2 + 3 dim) doubles.
 __global__ void __launch_bounds__(256)
 newt_deck_kernel(const NewtDeckJob job)
 {
-    extern __shared__ double sExp[];   // [dim] for P, then [dim] for the derivatives
+    extern __shared__ double sDk[];
     const int dim = job.dim, nCat = job.nCat, c = blockIdx.x;
-    double *sExpD = sExp + dim;
-    const double *V = job.eig;
-    const double *Vi = V + dim * dim;
-    const double *lam = Vi + dim * dim;
+    const int nc = dim * dim;
+    double *V = sDk, *Vi = V + nc, *lam = Vi + nc, *sExp = lam + dim, *sExpD = sExp + dim, *sDeck = sExpD + dim;   // sDeck: [3][dim*dim]
+    for (int i = threadIdx.x; i < 2 * nc + dim; i += blockDim.x) sDk[i] = job.eig[i];
+    __syncthreads();
     for (int i = threadIdx.x; i < dim; i += blockDim.x) {
         sExp[i] = exp(lam[i] * job.t0[c]);
         sExpD[i] = exp(lam[i] * job.t1[c]);
     }
     __syncthreads();
-    const int n = nCat * dim * dim, nc = dim * dim;
+    const int n = nCat * nc;
     double *D0 = job.decks, *D1 = D0 + n, *D2 = D1 + n;
     const double r1 = job.r1[c], r2 = job.r2[c];
     for (int ij = threadIdx.x; ij < nc; ij += blockDim.x) {
@@ -67,19 +70,19 @@ newt_deck_kernel(const NewtDeckJob job)
             s1 += __dmul_rn(__dmul_rn(__dmul_rn(vv, l), r1), e);
             s2 += __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(vv, l), l), r2), r2), e);
         }
-        D0[c * nc + ij] = s0;
-        D1[c * nc + ij] = s1;
-        D2[c * nc + ij] = s2;
+        D0[c * nc + ij] = sDeck[ij] = s0;
+        D1[c * nc + ij] = sDeck[nc + ij] = s1;
+        D2[c * nc + ij] = sDeck[2 * nc + ij] = s2;
     }
     if (job.tblW > 0) {
-        __syncthreads();   // the block's own global writes are visible after the barrier
+        __syncthreads();
         const int W = job.tblW;
         const int nT = nCat * dim * W, ncT = dim * W;
         double *T = D2 + n;
         for (int idx = threadIdx.x; idx < 3 * ncT; idx += blockDim.x) {
             const int d = idx / ncT, r = idx - d * ncT, f = r / W, w = r - f * W;
             const int k = c * dim + f;                             // row of the table: cat*dim + from
-            const double *D = job.decks + (size_t)d * n + (size_t)k * dim;
+            const double *D = sDeck + (size_t)d * nc + (size_t)f * dim;
             double v = 0.0;
             if (w < dim) v = D[w];
             else if (w == dim) {
@@ -528,9 +531,12 @@ newt_aa_kernel(const NewtArgs a, unsigned *__restrict__ ticket, double *__restri
             double2 like = make_double2(0.0, 0.0), first = like, second = like;
             if (leaf) {
                 const double *T0 = sD + (size_t)c * DIM * W, *T1 = T0 + per, *T2 = T1 + per;
-#pragma unroll 4
+                double2 zr[DIM];          // all twenty rows requested before the first is used: the loads in flight are what
+#pragma unroll                            // bounds a leaf evaluation (128 MB read, 120 FMAs per pattern pair and category)
+                for (int f = 0; f < DIM; f++) zr[f] = ld2(z + (size_t)f * ps);
+#pragma unroll
                 for (int f = 0; f < DIM; f++) {
-                    const double2 zz = ld2(z + (size_t)f * ps);
+                    const double2 zz = zr[f];
                     like.x = fma(zz.x, T0[f * W + code.x], like.x);
                     like.y = fma(zz.y, T0[f * W + code.y], like.y);
                     first.x = fma(zz.x, T1[f * W + code.x], first.x);

@@ -2991,7 +2991,13 @@ static int newtDerivs(Tree *t, Node *n, double out[3])
         }
         const bool dna = L.dim == 4 && (L.nCat == 4 || L.nCat == 1);
         if (!dna) {
-            newt_deck_kernel<<<L.nCat, 256, 2 * L.dim * sizeof(double), G.stream>>>(j);
+            const size_t deckSm = ((size_t)5 * L.dim * L.dim + 3 * L.dim) * sizeof(double);      // 161 KB at 64 states
+            static bool deckAttr = false;
+            if (!deckAttr) {
+                CUDA_TRY(cudaFuncSetAttribute(newt_deck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                deckAttr = true;
+            }
+            newt_deck_kernel<<<L.nCat, 256, deckSm, G.stream>>>(j);
             CUDA_TRY(cudaGetLastError());
             G.launches++;
         }
