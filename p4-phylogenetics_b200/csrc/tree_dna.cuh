@@ -210,7 +210,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
     double2 *bufAll = reinterpret_cast<double2 *>(ring + RING * slotB);   // [KT][CTH]
     double2 *sA = bufAll + KT * CTH;                                  // hand-over of the category sum between the warps of a pattern block
     uint64_t *full = reinterpret_cast<uint64_t *>(sA + CTH);
-    uint64_t *empty = full + RING;                                    // arrivals of the CW warps that have left the slot
+    uint64_t *empty = full + RING;                                    // arrivals of the CW x 32 lanes that have left the slot
     double *sRed = reinterpret_cast<double *>(empty + RING + 1);      // [2][CW] + flag, 8-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t ps = (size_t)a.ps;
@@ -245,7 +245,7 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             sNodes[i] = make_uint2(__ldg(&gSteps[i].n0), __ldg(&gSteps[i].n1));
         }
         if (threadIdx.x == 0) {
-            for (int i = 0; i < RING; i++) { mbar_init(full + i, 1); mbar_init(empty + i, CW); }
+            for (int i = 0; i < RING; i++) { mbar_init(full + i, 1); mbar_init(empty + i, CW * 32); }
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
     }
@@ -364,12 +364,10 @@ cl_tree_dna2_kernel(const __grid_constant__ TreeArgs2 a)
             }
             if (pf != kNone && (flags & kStepPfLate)) prefetch(pf);   // the buffer was in use by this step: refill it now
         }
-        // this warp has left the slot
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(empty + slot);
-            service(si);
-        }
+        // this warp has left the slot: every lane arrives for itself (CW x 32 arrivals per phase), so each lane's reads of
+        // the slot are ordered before the refill by its own arrival
+        mbar_arrive(empty + slot);
+        if (lane == 0) service(si);
     }
 
     if (!hd.doLike) return;
