@@ -1663,22 +1663,15 @@ static int launchFused2Batch(const FusedJob *jobs, int nJobs, int p, double *res
 // ---------------------------------------------------------------------------
 // 20 states: the tensor-core whole-tree kernel (tree_aa.cuh)
 // ---------------------------------------------------------------------------
-static int launchFusedAABatch(const FusedJob *jobs, int nJobs, int p, double *resultDev)
+// jobs[i] is (tree, part partOf[i]) -- or part p for all of them when partOf is NULL (the batched trees of one part); the root
+// reduction of job i writes resultOf[i] (NULL: resultDev + 2 i).
+static int launchFusedAABatch(const FusedJob *jobs, int nJobs, int p, double *resultDev, const int *partOf = nullptr, double *const *resultOf = nullptr)
 {
     if (flushPJobs()) return 1;
-    Tree *t0 = jobs[0].t;
-    TreeDevice *d0 = t0->dev;
-    PartLayout &L = d0->parts[p];
-    Part *dp = t0->data->parts[p];
-    if (!d0->aux || L.auxDP != 0 || !L.auxDoubles) { setError("internal: 20-state whole-tree kernel without operand decks"); return 1; }
-    if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
+    if (nJobs > kMaxBatchTrees) { setError("internal: more than %d (tree, part) pairs in one launch", kMaxBatchTrees); return 1; }
     static TreeArgsAA a;
     memset(&a, 0, sizeof(a));
-    a.ps = L.ps;
-    a.nPat = L.nPat;
-    a.tblW = L.W;
     a.nTrees = nJobs;
-    a.tips = dp->dev.tips;
     // launch shape "warps per CTA,ring depth,CTAs per SM": 8,8,2 unless P4B_AA_SHAPE says otherwise
     static int shapeRead = 0, dbgNoStore = 0, groups3 = 8, ring3 = 8, minb3 = 2;
     if (!shapeRead) {
@@ -1689,37 +1682,43 @@ static int launchFusedAABatch(const FusedJob *jobs, int nJobs, int p, double *re
         dbgNoStore = e ? atoi(e) : 0;
     }
     a.pad0 = dbgNoStore;
-    a.nCat = L.nCat;
     static std::vector<Step2> steps;
     steps.clear();
-    int maxSteps = 1;
+    int maxSteps = 1, maxW = 1, maxPs = 0, maxCat = 1;
     for (int i = 0; i < nJobs; i++) {
         Tree *t = jobs[i].t;
         TreeDevice *d = t->dev;
-        PartLayout &Li = d->parts[p];
-        if (t->data->parts[p] != dp || Li.ps != L.ps || Li.nCat != L.nCat || Li.dim != L.dim || Li.W != L.W || d->auxNodeDoubles != d0->auxNodeDoubles) {
-            setError("batched evaluation: the trees do not share the data part and model shape");
-            return 1;
-        }
+        const int pi = partOf ? partOf[i] : p;
+        PartLayout &Li = d->parts[pi];
+        Part *dp = t->data->parts[pi];
+        if (Li.dim != 20 || !d->aux || Li.auxDP != 0 || !Li.auxDoubles) { setError("internal: 20-state whole-tree kernel without operand decks"); return 1; }
+        if (dp->nTax >= 65535) { setError("internal: more than 65534 sequences"); return 1; }
         if (jobs[i].withLike && (!t->root || jobs[i].order->empty() || jobs[i].order->back() != t->root)) { setError("fused evaluation: the last node must be the root"); return 1; }
-        a.hdr[i].arena = arenaBase(Li);
-        a.hdr[i].aux = d->aux + Li.auxOff;
-        a.hdr[i].stepBase = (int)steps.size();
+        TreeArgsAA::Hdr &hd = a.hdr[i];
+        hd.arena = arenaBase(Li);
+        hd.aux = d->aux + Li.auxOff;
+        hd.tips = dp->dev.tips;
+        hd.ps = Li.ps;
+        hd.tblW = Li.W;
+        hd.nCat = Li.nCat;
+        hd.stepBase = (int)steps.size();
         TreeHdr2 h;
         memset(&h, 0, sizeof(h));
-        const int ns = buildSteps2(steps, h, jobs[i], p, 1);
+        const int ns = buildSteps2(steps, h, jobs[i], pi, 1);
         if (ns < 0) return 1;
         if (!jobs[i].storeAll && jobs[i].withLike && ns > 0) {      // lnL-only: the root reduction reads the root's CL from memory
             steps.back().flags |= kStepStore;
-            t->root->clResident[p] = 1;
+            t->root->clResident[pi] = 1;
         }
-        a.hdr[i].nSteps = ns;
+        hd.nSteps = ns;
         if (ns > maxSteps) maxSteps = ns;
+        if (ns > 0) {
+            if (Li.W > maxW) maxW = Li.W;
+            if (Li.ps > maxPs) maxPs = Li.ps;
+            if (Li.nCat > maxCat) maxCat = Li.nCat;
+        }
     }
-    bool anything = false;
-    for (int i = 0; i < nJobs; i++)
-        if (a.hdr[i].nSteps > 0) anything = true;
-    if (anything) {
+    if (maxPs > 0) {
         a.maxSteps = maxSteps;
         if (uploadSteps2(steps)) return 1;
         a.steps = G.stepDev;
@@ -1739,23 +1738,25 @@ static int launchFusedAABatch(const FusedJob *jobs, int nJobs, int p, double *re
         for (const Shape &c : shapes)
             if (c.g == groups3 && c.r == ring3 && c.b == minb3) sh = &c;
         if (!sh) { setError("P4B_AA_SHAPE: no such launch shape of the 20-state whole-tree kernel"); return 1; }
-        size_t smem = aaSmemBytes(L.W, sh->g, sh->r, maxSteps);
+        size_t smem = aaSmemBytes(maxW, sh->g, sh->r, maxSteps);
         if ((smem + 1024) * sh->b > 227 * 1024 && sh->g == 8 && sh->r == 8) {      // wide leaf tables or a long step list: the shallower ring
             sh = &shapes[1];
-            smem = aaSmemBytes(L.W, sh->g, sh->r, maxSteps);
+            smem = aaSmemBytes(maxW, sh->g, sh->r, maxSteps);
         }
         if (smem > 220 * 1024) { setError("internal: leaf tables or step list too large for the 20-state whole-tree kernel's shared memory"); return 1; }
         if (prepare(sh->fn)) return 1;
-        const int blocks = L.ps / (sh->g * 16);
-        sh->fn<<<dim3(blocks, nJobs, L.nCat), sh->g * 32, smem, G.stream>>>(a);
+        for (int i = 0; i < nJobs; i++) a.hdr[i].nBlocks = a.hdr[i].nSteps > 0 ? a.hdr[i].ps / (sh->g * 16) : 0;
+        const int blocks = maxPs / (sh->g * 16);
+        sh->fn<<<dim3(blocks, nJobs, maxCat), sh->g * 32, smem, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
-        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa_kernel<%d,%d,%d> x %d categories", sh->g, sh->r, sh->b, L.nCat);
+        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa_kernel<%d,%d,%d> x %d categories", sh->g, sh->r, sh->b, maxCat);
         G.launches++;
-        for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
+        for (int i = 0; i < nJobs; i++)
+            if (i == 0 || jobs[i].t != jobs[i - 1].t) jobs[i].t->dev->lastCLLaunches++;
     }
     for (int i = 0; i < nJobs; i++)
         if (jobs[i].withLike)
-            if (enqueueRootLike(jobs[i].t, p, jobs[i].wantPatLikes, resultDev + 2 * i)) return 1;
+            if (enqueueRootLike(jobs[i].t, partOf ? partOf[i] : p, jobs[i].wantPatLikes, resultOf ? resultOf[i] : resultDev + 2 * i)) return 1;
     return 0;
 }
 
@@ -2280,7 +2281,22 @@ double treeLogLike(Tree *t, int getSiteLikes)
     if (order.empty() || order.back() != t->root) { setError("p4_treeLogLike: postOrder does not end at the root"); return NAN; }
     cudaEventRecord(d->evCLa, G.stream);
     std::vector<char> likeDone(t->nParts, 0);
+    {   // the 20-state parts of a partitioned alignment go through ONE launch of the whole-tree kernel: no launch gaps, and one
+        // last, partly filled wave of CTAs instead of one per part
+        std::vector<int> aaParts;
+        for (int p = 0; p < t->nParts; p++)
+            if (d->parts[p].dim == 20 && fusedEligible(d->parts[p])) aaParts.push_back(p);
+        if (!getSiteLikes && aaParts.size() >= 2 && aaParts.size() <= (size_t)kMaxBatchTrees && order.size() + 8 <= (size_t)kMaxSteps) {      // (site likelihoods: one part at a time, they share a buffer)
+            const bool storeAll = t->storeCL != 0;
+            std::vector<FusedJob> jobs(aaParts.size(), FusedJob{t, &order, true, false, storeAll, false});
+            std::vector<double *> res;
+            for (int p : aaParts) res.push_back(d->result + 2 * p);
+            if (launchFusedAABatch(jobs.data(), (int)jobs.size(), aaParts[0], nullptr, aaParts.data(), res.data())) return NAN;
+            for (int p : aaParts) likeDone[p] = 1;
+        }
+    }
     for (int p = 0; p < t->nParts; p++) {
+        if (likeDone[p]) continue;
         if (fusedEligible(d->parts[p])) {
             const bool storeAll = t->storeCL != 0 || (d->parts[p].dim != 4 && d->parts[p].dim != 20) || order.size() + 8 > (size_t)kMaxSteps;
             if (launchFusedTree(t, p, order, true, getSiteLikes != 0, storeAll)) return NAN;

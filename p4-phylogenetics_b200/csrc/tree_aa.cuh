@@ -33,16 +33,20 @@ constexpr int kAATblStates = 24;      // states per code in the transposed leaf 
 __host__ __device__ inline size_t aaCatDoubles(int W) { return (size_t)W * kAATblStates > (size_t)kAAFrag ? (size_t)W * kAATblStates : (size_t)kAAFrag; }
 // ring slot: [child 0: catDoubles][child 1: catDoubles][tips child 0: GROUPS*16 B][tips child 1]
 
+// One launch serves up to kMaxBatchTrees (tree, part) pairs (blockIdx.y): the trees of a batched MCMC evaluation of one part, or
+// the 20-state parts of one tree -- each with its own data part, pattern count, leaf-table width and number of categories; the grid
+// is sized for the largest, CTAs beyond a pair's own extent leave at once.
 struct TreeArgsAA {
-    int ps, nPat, tblW, nTrees;
-    int maxSteps, pad0;       // pad0: measurement switch (no stores)
-    int nCat, pad1;
-    const uint8_t *tips;      // part's tip rows [nTax][ps]
+    int nTrees, maxSteps;
+    int pad0, pad1;           // pad0: measurement switch (no stores)
     const Step2 *steps;       // n0 / n1: offset (doubles) of the child's operands from hdr.aux -- P^T fragments or transposed leaf tables of category 0
     struct Hdr {
         double *arena;
         const double *aux;    // tree's operand decks, already offset to this part
+        const uint8_t *tips;  // part's tip rows [nTax][ps]
         int stepBase, nSteps;
+        int ps, tblW;         // pattern stride of the part's shard; width of its leaf tables
+        int nCat, nBlocks;    // rate categories; CTAs along x that have patterns (ps / (GROUPS * 16))
     } hdr[kMaxBatchTrees];
 };
 
@@ -61,7 +65,8 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgsAA a)
     constexpr int DIM = 20, MT = 2, NW = GROUPS;
     const TreeArgsAA::Hdr &hd = a.hdr[blockIdx.y];
     extern __shared__ __align__(16) unsigned char smraw[];
-    const int W = a.tblW, nSteps = hd.nSteps;
+    if ((int)blockIdx.x >= hd.nBlocks || (int)blockIdx.z >= hd.nCat) return;
+    const int W = hd.tblW, nSteps = hd.nSteps;
     const int cat = blockIdx.z;
     const unsigned catD = (unsigned)aaCatDoubles(W);
     const unsigned childB = catD * 8;                               // bytes of one child's operands (this category) in a slot
@@ -76,10 +81,10 @@ cl_tree_aa_kernel(const __grid_constant__ TreeArgsAA a)
     // 25-cycle scoreboard wait) wherever the step loop needs the lane under register pressure
     const unsigned tidx = __shfl_sync(0xffffffffu, threadIdx.x, threadIdx.x & 31u);
     const int lane = tidx & 31, warp = tidx >> 5, g = lane >> 2, q = lane & 3;
-    const size_t ps = (size_t)a.ps;
+    const size_t ps = (size_t)hd.ps;
     const int pat0 = (blockIdx.x * GROUPS + warp) * (8 * MT);
     const size_t rowBase = (size_t)cat * DIM * ps + pat0 + MT * g;       // + state * ps: this lane's two patterns of a row
-    const uint8_t *ctaTips = a.tips + (size_t)blockIdx.x * (GROUPS * 16);
+    const uint8_t *ctaTips = hd.tips + (size_t)blockIdx.x * (GROUPS * 16);
 
     auto produce = [&](int j) {
         const int slot = j % RING;
