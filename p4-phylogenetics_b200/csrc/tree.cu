@@ -1887,13 +1887,12 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     a.counts = dp->dev.counts;
     a.invarMask = dp->dev.invarMask;
     a.eqMask = dp->dev.equateMask;
-    const bool aa = false;            // (20-state parts have their own launch path: launchFusedAABatch)
+    // (20-state parts have their own launch path: launchFusedAABatch)
     const int variant = fusedVariant(L.ps, nJobs);
     static const int kThreads[9] = {128, 64, 32, 128, 256, 64, 32, 64, 32};
-    const int aaGroups = 1, aaMinB = 1, aaMT = 2;
-    const int THREADS = aa ? 128 * aaGroups : kThreads[variant];
-    const int blocks = aa ? (L.ps / (8 * aaMT) + aaGroups - 1) / aaGroups : (L.ps / 2 + THREADS - 1) / THREADS;
-    const int maxKids = aa ? kAAKids : kMaxChildren;
+    const int THREADS = kThreads[variant];
+    const int blocks = (L.ps / 2 + THREADS - 1) / THREADS;
+    const int maxKids = kMaxChildren;
     bool anyLike = false;
     for (int i = 0; i < nJobs; i++) {
         Tree *t = jobs[i].t;
@@ -1910,9 +1909,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         h.Pdeck = d->P + Li.pOff;
         h.tbl = d->tbl + Li.tblOff;
         h.aux = d->aux ? d->aux + Li.auxOff : nullptr;
-        if (jobs[i].withLike && aa) {
-            if (!t->root || jobs[i].order->empty() || jobs[i].order->back() != t->root) { setError("fused evaluation: the last node must be the root"); return 1; }
-        } else if (jobs[i].withLike) {
+        if (jobs[i].withLike) {
             anyLike = true;
             Node *root = t->root;
             if (!root || jobs[i].order->empty() || jobs[i].order->back() != root) { setError("fused evaluation: the last node must be the root"); return 1; }
@@ -1936,12 +1933,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     }
     const int K = L.nCat * 4;
     size_t smem = (size_t)2 * kMaxChildren * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
-    if (aa) {
-        const size_t frag = kAAFrag, tblSize = (size_t)20 * L.W;   // per category
-        smem = (size_t)L.nCat * 2 * kAAKids * (frag > tblSize ? frag : tblSize) * sizeof(double) + 64;   // + the mbarriers
-        if (!d0->aux) { setError("internal: 20-state whole-tree kernel without operand decks"); return 1; }
-    }
-    if (smem > (aa ? 200 : 100) * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
+    if (smem > 100 * 1024) { setError("leaf tables too wide for the fused kernel"); return 1; }
     typedef void (*KernelFn)(const TreeArgs);
     static const KernelFn kFn4[9] = {cl_tree_dna_kernel<4, 128, 3, false>, cl_tree_dna_kernel<4, 64, 6, false>,
                                      cl_tree_dna_kernel<4, 32, 12, false>, cl_tree_dna_kernel<4, 128, 4, false>,
@@ -1977,26 +1969,24 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
     auto launch = [&](int nTrees) -> int {
         a.nTrees = nTrees;
         size_t smemNow = smem;
-        if (!aa) {   // staging buffers sized by the widest step actually present (2 or 3 in a binary tree), not by kMaxChildren
-            int mk = 1;
-            for (int i = 0; i < nTrees; i++)
-                for (int k = 0; k < a.hdr[i].nSteps; k++) mk = a.steps[a.hdr[i].stepBase + k].nChildren > mk ? a.steps[a.hdr[i].stepBase + k].nChildren : mk;
-            a.maxKids = mk;
-            smemNow = (size_t)2 * mk * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
-            // Residency of the small-CTA shapes is set on purpose, through the shared-memory request: 5 CTAs of 64
-            // threads, 7 of 32.  A step costs a fixed latency whatever the occupancy, so what matters for a shard of
-            // one to three waves is that the LAST wave is nearly full: 125 k patterns are 1.9 waves of 7 x 32 threads
-            // per SM (0.86 ms) but 1.2 waves of 11 x 32 (0.93 ms); 250 k: 64 x 5 1.39 ms, 64 x 6 1.49 ms.
-            static const int kResident[3] = {0, 5, 7};
-            if (variant >= 1 && variant <= 2 && !getenv("P4B_FUSED_NOCAP")) {
-                const size_t need = (size_t)233472 / (kResident[variant] + 1) - 1024 + 256;
-                if (smemNow < need) smemNow = need;
-            }
+        // staging buffers sized by the widest step actually present (2 or 3 in a binary tree), not by kMaxChildren
+        int mk = 1;
+        for (int i = 0; i < nTrees; i++)
+            for (int k = 0; k < a.hdr[i].nSteps; k++) mk = a.steps[a.hdr[i].stepBase + k].nChildren > mk ? a.steps[a.hdr[i].stepBase + k].nChildren : mk;
+        a.maxKids = mk;
+        smemNow = (size_t)2 * mk * K * (L.W > 4 ? L.W : 4) * sizeof(double) + (size_t)K * THREADS * sizeof(double) * 2;
+        // Residency of the small-CTA shapes is set on purpose, through the shared-memory request: 5 CTAs of 64
+        // threads, 7 of 32.  A step costs a fixed latency whatever the occupancy, so what matters for a shard of
+        // one to three waves is that the LAST wave is nearly full: 125 k patterns are 1.9 waves of 7 x 32 threads
+        // per SM (0.86 ms) but 1.2 waves of 11 x 32 (0.93 ms); 250 k: 64 x 5 1.39 ms, 64 x 6 1.49 ms.
+        static const int kResident[3] = {0, 5, 7};
+        if (variant >= 1 && variant <= 2 && !getenv("P4B_FUSED_NOCAP")) {
+            const size_t need = (size_t)233472 / (kResident[variant] + 1) - 1024 + 256;
+            if (smemNow < need) smemNow = need;
         }
         fn<<<dim3(blocks, nTrees), THREADS, smemNow, G.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
-        if (aa) snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_aa_kernel<%d,%d,%d,%d>", L.nCat, aaGroups, aaMinB, aaMT);
-        else snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_dna_kernel<%d,%d> shape %d", L.nCat, THREADS, variant);
+        snprintf(g_lastKernel, sizeof(g_lastKernel), "cl_tree_dna_kernel<%d,%d> shape %d", L.nCat, THREADS, variant);
         G.launches++;
         for (int i = 0; i < nJobs; i++) jobs[i].t->dev->lastCLLaunches++;
         return 0;
@@ -2012,7 +2002,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
             if (ns < 0) return 1;
             a.hdr[0].stepBase = 0;
             a.hdr[0].nSteps = ns;
-            a.hdr[0].doLike = (jobs[0].withLike && !more && !aa) ? 1 : 0;
+            a.hdr[0].doLike = (jobs[0].withLike && !more) ? 1 : 0;
             if (ns > 0 || a.hdr[0].doLike)
                 if (launch(1)) return 1;
             if (!more) break;
@@ -2025,7 +2015,7 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
             if (ns < 0) return 1;
             a.hdr[i].stepBase = base;
             a.hdr[i].nSteps = ns;
-            a.hdr[i].doLike = (jobs[i].withLike && !aa) ? 1 : 0;
+            a.hdr[i].doLike = jobs[i].withLike ? 1 : 0;
             base += ns;
         }
         if (launch(nJobs)) return 1;
@@ -2045,10 +2035,6 @@ static int launchFusedBatch(const FusedJob *jobs, int nJobs, int p, double *resu
         CUDA_TRY(cudaGetLastError());
         G.launches++;
     }
-    if (aa)
-        for (int i = 0; i < nJobs; i++)
-            if (jobs[i].withLike)
-                if (enqueueRootLike(jobs[i].t, p, jobs[i].wantPatLikes, resultDev + 2 * i)) return 1;
     return 0;
 }
 

@@ -69,6 +69,50 @@ def test_any_number_of_rate_categories(pkg, ref_pf, nCat):
         assert np.max(np.abs(c1 - c0) / scale) < 1e-9, "CL of node %d" % a.nodeNum
 
 
+def test_unequal_protein_parts_in_one_launch(pkg, ref_pf):
+    """p4_treeLogLike sends all 20-state parts of a tree through ONE launch; the parts may differ in pattern count, leaf-table
+    width (ambiguity codes present) and number of rate categories, and a DNA part may sit between them."""
+    P, pf = pkg, pkg.pf
+    rng = np.random.Generator(np.random.PCG64(77))
+    tree = P.synth.random_tree(pf, 14, rng)
+    mps = [P.synth.protein_model_part(0, rng, "lg", 4), P.synth.dna_model_part(1, rng, 4, pInvar=0.1),
+           P.synth.protein_model_part(2, rng, "lg", 2), P.synth.protein_model_part(3, rng, "lg", 1)]
+    alns = [P.synth.make_alignment(pf, tree, mps[0], 300, rng, "protein", gap_frac=0.02, ambig_frac=0.02),
+            P.synth.make_alignment(pf, tree, mps[1], 500, rng, "dna"),
+            P.synth.make_alignment(pf, tree, mps[2], 1000, rng, "protein", gap_frac=0.0, ambig_frac=0.0),
+            P.synth.make_alignment(pf, tree, mps[3], 150, rng, "protein", gap_frac=0.05, ambig_frac=0.0)]
+    tree.attach(P.host.Data(pf, alns), P.host.Model(pf, mps))
+    twin = P.host.clone_tree(tree, ref_pf)
+    n0 = pf.kernelLaunchCount()
+    got, want = tree.calcLogLike(), twin.calcLogLike()
+    merged = pf.kernelLaunchCount() - n0
+    assert rel(got, want) <= LNL_TOL
+    for a, b in zip(tree.partLikes, twin.partLikes):
+        assert rel(a, b) <= LNL_TOL
+    rp = [ref_peek.part_arrays(p.cPart) for p in twin.data.parts]
+    for pNum in (0, 2, 3):
+        nCat = mps[pNum].nGammaCat
+        for a, b in zip(tree.nodes, twin.nodes):
+            if a.isLeaf:
+                continue
+            c1 = pf.getNodeCL(tree.cTree, a.cNode, pNum, nCat, 20)
+            c0 = ref_peek.node_cl(b.cNode, pNum, nCat, 20, rp[pNum]["nChar"], rp[pNum]["nPatterns"])
+            scale = np.max(np.abs(c0), axis=(0, 1), keepdims=True)
+            assert np.max(np.abs(c1 - c0) / scale) < 1e-9, "part %d, CL of node %d" % (pNum, a.nodeNum)
+    pf.setFusedTreeKernel20(0)
+    try:
+        n0 = pf.kernelLaunchCount()
+        assert rel(tree.calcLogLike(), got) <= 1e-12
+        assert merged < pf.kernelLaunchCount() - n0
+    finally:
+        pf.setFusedTreeKernel20(1)
+    # lnL-only evaluations take the same route
+    pf.setTreeStoresCL(tree.cTree, 0)
+    assert rel(pf.p4_treeLogLike(tree.cTree, 0), want) <= LNL_TOL
+    pf.setTreeStoresCL(tree.cTree, 1)
+    assert rel(tree.calcLogLike(), want) <= LNL_TOL
+
+
 def test_cl_arrays_match_reference(pkg, ref_pf):
     pf = pkg.pf
     mine, twin = build_pair(pkg, ref_pf, 3, nTax=11, nPatterns=400)
