@@ -133,31 +133,47 @@ rescale_kernel(const RescaleArgs a)
 // ---------------------------------------------------------------------------
 // P(t)
 // ---------------------------------------------------------------------------
+// Doubles of shared memory a job wants so that nothing on its paths comes from global memory: exp(lambda t) per category, the
+// eigensystem, the P deck and the leaf table (the table and operand-deck passes read P and the table back).
+__host__ __device__ inline size_t pmatrixStageDoubles(int dim, int nCat, int W) { return (size_t)nCat * dim + 2 * (size_t)dim * dim + dim + (size_t)nCat * dim * dim + (size_t)nCat * dim * W; }
+
 __global__ void __launch_bounds__(128)
-pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
+pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged, const int smCap)
 {
-    extern __shared__ double sExp[];   // [nCat][dim] exp(lambda_k * t_cat)
+    extern __shared__ double sExp[];   // [nCat][dim] exp(lambda_k * t_cat) | (staged jobs) V | Vinv | lambda | P | table
     const PJob job = jobs[blockIdx.x];
     const int dim = job.dim, nCat = job.nCat;
-    const double *V = job.eig;
+    // a job that fits the launch's shared memory (every 4- and 20-state part does) keeps its eigensystem, its P deck and its
+    // leaf table there: a lone 20-state job -- one changed branch of an MCMC proposal, one Newton step -- took 35 us with
+    // every pass going through global memory
+    const bool st = pmatrixStageDoubles(dim, nCat, job.tblW) <= (size_t)smCap;
+    double *sEig = sExp + nCat * dim, *sP = sEig + 2 * dim * dim + dim, *sT = sP + nCat * dim * dim;
+    if (st) {
+        for (int i = threadIdx.x; i < 2 * dim * dim + dim; i += blockDim.x) sEig[i] = job.eig[i];
+        __syncthreads();
+    }
+    const double *V = st ? sEig : job.eig;
     const double *Vi = V + dim * dim;
     const double *lam = Vi + dim * dim;
     const double *t = staged + job.tOff;
     for (int i = threadIdx.x; i < nCat * dim; i += blockDim.x) sExp[i] = exp(lam[i % dim] * t[i / dim]);
     __syncthreads();
-    double *P = job.P;
+    double *Pg = job.P;
     const int n = nCat * dim * dim;
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const int c = idx / (dim * dim), ij = idx - c * dim * dim, i = ij / dim, j = ij - i * dim;
         double sum = 0.0;
         // same association as the reference: sum += (V[i][k] * Vinv[k][j]) * exp(.)
         for (int k = 0; k < dim; k++) sum = fma(__dmul_rn(V[i * dim + k], Vi[k * dim + j]), sExp[c * dim + k], sum);
-        P[idx] = sum;
+        Pg[idx] = sum;
+        if (st) sP[idx] = sum;
     }
+    const double *P = st ? sP : Pg;        // what the later passes read
+    const double *T = st ? sT : job.tbl;
     if (job.tblW > 0) {
-        __syncthreads();   // the block's own global writes of P are visible after the barrier
+        __syncthreads();   // the block's own writes of P are visible after the barrier
         const int W = job.tblW;
-        double *T = job.tbl;
+        double *Tg = job.tbl;
         const uint64_t *em = job.eq;
         const int nT = nCat * dim * W;
         for (int idx = threadIdx.x; idx < nT; idx += blockDim.x) {
@@ -171,7 +187,8 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
                 for (int x = 0; x < dim; x++)
                     if ((m >> x) & 1ull) v += P[k * dim + x];
             }
-            T[idx] = v;
+            Tg[idx] = v;
+            if (st) sT[idx] = v;
         }
     }
     if (job.aux && job.auxDP > 0) {
@@ -189,7 +206,6 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
         }
         if (job.tblW > 0) {
             const int W = job.tblW;
-            const double *T = job.tbl;
             double *TT = A + (size_t)nCat * F;
             const int nT = nCat * W * DP;
             for (int i = threadIdx.x; i < nT; i += blockDim.x) {
@@ -212,7 +228,6 @@ pmatrix_kernel(const PJob *__restrict__ jobs, const double *__restrict__ staged)
         }
         if (job.tblW > 0) {
             const int W = job.tblW;
-            const double *T = job.tbl;
             double *TT = A + nF;
             const int nT = nCat * W * 24;
             for (int i = threadIdx.x; i < nT; i += blockDim.x) {

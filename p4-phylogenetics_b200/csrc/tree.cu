@@ -828,15 +828,27 @@ static int flushPJobs()
     std::vector<char> blk(tBytes + jobs.size() * sizeof(PJob));
     memcpy(blk.data(), tvals.data(), tvals.size() * sizeof(double));
     memcpy(blk.data() + tBytes, jobs.data(), jobs.size() * sizeof(PJob));
-    int maxSm = 0;
-    for (auto &j : jobs) maxSm = j.nCat * j.dim > maxSm ? j.nCat * j.dim : maxSm;
+    // shared memory: exp(lambda t) per category for every job, and for the jobs that fit 64 KB (every 4- and 20-state part)
+    // the eigensystem, the P deck and the leaf table as well (kernels.cuh, pmatrixStageDoubles)
+    size_t maxSm = 0;
+    static const bool stageP = [] { const char *e = getenv("P4B_PMATRIX_STAGE"); return e ? atoi(e) != 0 : true; }();
+    for (auto &j : jobs) {
+        size_t need = pmatrixStageDoubles(j.dim, j.nCat, j.tblW);
+        if (!stageP || need * sizeof(double) > 64 * 1024) need = (size_t)j.nCat * j.dim;
+        if (need > maxSm) maxSm = need;
+    }
+    static bool pAttr = false;
+    if (!pAttr) {
+        CUDA_TRY(cudaFuncSetAttribute(pmatrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        pAttr = true;
+    }
     const unsigned nJobs = (unsigned)jobs.size();
     jobs.clear();
     tvals.clear();
     void *dblk = nullptr;
     if (stage(blk.data(), blk.size(), &dblk)) return 1;
     pmatrix_kernel<<<nJobs, 128, maxSm * sizeof(double), G.stream>>>(
-        reinterpret_cast<const PJob *>((char *)dblk + tBytes), reinterpret_cast<const double *>(dblk));
+        reinterpret_cast<const PJob *>((char *)dblk + tBytes), reinterpret_cast<const double *>(dblk), (int)maxSm);
     CUDA_TRY(cudaGetLastError());
     G.launches++;
     return 0;
