@@ -152,6 +152,33 @@ def test_newt_around_matches_reference(pkg, ref_pf, cfg, kw):
     assert rel(mine.calcLogLike(), got) <= 1e-10
 
 
+@pytest.mark.parametrize("nCat", [1, 3])
+def test_newt_around_protein_other_category_counts(pkg, ref_pf, nCat):
+    """The tensor-core derivative kernel for 20-state internal nodes (newt_aa_dmma_kernel) has a compile-time path for four
+    categories and a run-time one for any other number; pInvar exercises the constant-site term of the finishing step."""
+    P, pf = pkg, pkg.pf
+    rng = np.random.Generator(np.random.PCG64(300 + nCat))
+    tree = P.synth.random_tree(pf, 9, rng)
+    mp = P.synth.protein_model_part(0, rng, "lg", nCat)
+    mp.pInvar = P.host.PInvar(0.15)
+    aln = P.synth.make_alignment(pf, tree, mp, 350, rng, "protein", gap_frac=0.02, ambig_frac=0.02)
+    tree.attach(P.host.Data(pf, [aln]), P.host.Model(pf, [mp]))
+    twin = P.host.clone_tree(tree, ref_pf)
+    _perturb((tree, twin), seed=nCat)
+    start = tree.calcLogLike()
+    assert rel(start, twin.calcLogLike()) <= 1e-9
+    pf.p4_newtSetup(tree.cTree)
+    ref_pf.p4_newtSetup(twin.cTree)
+    got = pf.newtAround(tree.cTree, 1.0e-5, 1.0e-7)
+    ref_peek.newt_lib().p4_newtAround(twin.cTree, 1.0e-5, 1.0e-7)
+    want = ref_pf.p4_treeLogLike(twin.cTree, 0)
+    assert got > start and rel(got, want) <= 1e-9, (got, want)
+    lens = pf.p4_getBrLens(tree.cTree)
+    for a, b in zip(tree.iterNodesNoRoot(), twin.iterNodesNoRoot()):
+        wantLen = ref_peek.node_brlen(b.cNode)
+        assert abs(lens[a.nodeNum] - wantLen) <= 1e-6 * max(wantLen, 1e-3), (a.nodeNum, lens[a.nodeNum], wantLen)
+
+
 def test_newt_around_two_parts_relrates_pinvar_hetero(pkg, ref_pf):
     """Two parts with relRates 0.7 / 1.4 (the reference's second-derivative factor carries an extra relRate in the
     gamma, no-pInvar branch, Pf/p4_node.c:510-514 -- step sizes depend on it), pInvar in one part, a model that
