@@ -1,0 +1,38 @@
+"""The bench line's evidence files (CPU): bench.py looks `roofline.traffic` up in profiles/r2_traffic.json by the kernel name the
+engine reports, the taxon count and the patterns per GPU -- a renamed kernel or a stale capture would silently turn it into null."""
+import importlib.util
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_traffic_captures_cover_every_shard_size_of_the_bench():
+    bench = _load("bench_under_test", os.path.join(ROOT, "bench.py"))
+    for pats in (1000000, 500000, 250000, 125000):          # 1, 2, 4, 8 GPUs of BASELINE configs[1]
+        traffic, src = bench.measured_traffic("cl_tree_dna2_kernel<4,2,8,2>", 200, pats)
+        assert traffic and src, pats
+        # a whole-tree evaluation writes every internal CL once: 198 nodes x 16 rows x 8 bytes per pattern, and little more
+        assert 0.99 * 198 * 128 * pats <= traffic <= 1.08 * 198 * 128 * pats, (pats, traffic)
+    for taxa, pats, nodes in ((100, 199999, 98), (60, 50000, 58)):      # configs 3 and 4 (one part): 80 rows
+        traffic, src = bench.measured_traffic("cl_tree_aa_kernel<8,8,2> x 4 categories", taxa, pats)
+        assert traffic and src, (taxa, pats)
+        assert 0.99 * nodes * 640 * pats <= traffic <= 1.08 * nodes * 640 * pats, (taxa, traffic)
+
+
+def test_kernel_names_of_the_generator_match_the_engine():
+    gen = _load("make_traffic_json", os.path.join(ROOT, "tools", "make_traffic_json.py"))
+    assert gen.short_name("void p4b::cl_tree_dna2_kernel<(int)4, (int)2, (int)8, (int)2>(p4b::TreeArgs2)") == "cl_tree_dna2_kernel<4,2,8,2>"
+    assert gen.short_name("void p4b::cl_tree_aa_kernel<(int)8, (int)8, (int)2>(p4b::TreeArgsAA)") == "cl_tree_aa_kernel<8,8,2>"
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    for e in d["entries"]:
+        assert os.path.exists(os.path.join(ROOT, e["source"].split(" ")[0])), e["source"]
