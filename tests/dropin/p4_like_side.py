@@ -39,6 +39,8 @@ ap.add_argument("--chains", type=int, default=4)
 ap.add_argument("--skip-opt", action="store_true")
 ap.add_argument("--opt-method", default="newtAndBrentPowell")
 ap.add_argument("--seed", type=int, default=7)
+ap.add_argument("--continue-gens", type=int, default=0,
+                help="after the run, time a second Mcmc.run(N) of the same object: generations/s without chain construction")
 args = ap.parse_args()
 
 import p4_phylogenetics_b200 as P          # the synthetic-input generator lives in the package (numpy only)
@@ -128,5 +130,14 @@ if args.gens > 0:
     out["mcmc_likes"] = likes
     out["final_likes"] = [float(c.curTree.logLike) for c in m.chains]
     out["accepted"] = [[p.name, int(sum(p.nAcceptances)), int(sum(p.nProposals))] for p in m.props.proposals]
+    if args.continue_gens > 0:
+        # Mcmc.run builds its chains (two trees each: device state) on the first call; a second call continues the run
+        try:
+            t0 = time.perf_counter()
+            m.run(args.continue_gens, verbose=False)
+            out["mcmc_continued_s"] = time.perf_counter() - t0
+            out["gens_per_s_continued"] = args.continue_gens / out["mcmc_continued_s"]
+        except Exception as e:     # the first run's numbers above stand on their own
+            out["mcmc_continued_error"] = repr(e)[:200]
 os.chdir(cwd)
 print("RESULT" + json.dumps(out))
