@@ -77,6 +77,13 @@ def workload_name(a):
 # ------------------------------------------------------------------------------
 # algorithmic bytes
 # ------------------------------------------------------------------------------
+def bench_config(a):
+    """The ``config`` object of the JSON line: the workload only, the same in both arms (what differs by arm is under ``run``)."""
+    return {"workload": workload_name(a), "taxa": a.taxa, "patterns": a.patterns, "model": "GTR+G4", "parts": 1,
+            "l2": "inputs larger than L2: an evaluation streams the whole CL working set (8*4*4 bytes per internal node and pattern; "
+                  "25.5 GB over all GPUs at the full size), no flush between steps"}
+
+
 def algorithmic_bytes_per_pattern(tree):
     """Per pattern and per full-tree evaluation: for every internal node,
     8*dim*nCat*(1 + k_internal_children) + k_leaf_children bytes."""
@@ -294,7 +301,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": reps, "warmup": max(1, a.warmup),
         "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "engine": "reference Pf (Pf/*.c, gcc -O2) on host cores", "wall_s": round(wall, 1)},
+        "config": bench_config(a),
+        "run": {"engine": "reference Pf (Pf/*.c, gcc -O2) on host cores", "wall_s": round(wall, 1)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -759,9 +767,10 @@ def run_b200(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "patterns_per_gpu": shard, "internal_nodes": n_internal, "setup_s": round(t_setup, 1),
-                   "l2": "inputs larger than L2 (CL working set %.1f GB per GPU)" % (pf.treeDeviceBytes(tree.cTree) / 1e9),
-                   "timing": "CUDA events on the engine stream, max over ranks"},
+        "config": bench_config(a),
+        "run": {"engine": "libp4b200.so on %d B200" % world, "patterns_per_gpu": shard, "internal_nodes": n_internal, "setup_s": round(t_setup, 1),
+                "cl_working_set_GB_per_gpu": round(pf.treeDeviceBytes(tree.cTree) / 1e9, 2),
+                "timing": "CUDA events on the engine stream, max over ranks"},
         "pattern_updates_per_s": value * n_internal * nPat,
         "lnL": lnL, "wall_ms_per_step": wall_ms_max / a.steps,
         "lnl_only": {"value": lean_value, "unit": UNIT, "lnL": lnL_lean,
