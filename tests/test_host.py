@@ -84,6 +84,41 @@ def test_pattern_compression_bit_exact_vs_reference(pkg, ref_pf, seed, nTax, nPa
     ref_pf.freePart(theirs.cPart)
 
 
+EDGE_ALIGNMENTS = {
+    "one column": ["a", "c", "g"],
+    "two taxa": ["acgtacgt", "acgtaagt"],
+    "every column the same": ["aaaaaaaa", "cccccccc", "gggggggg", "tttttttt"],
+    "every column distinct": ["acgtacgtacgtacgt", "aaaaccccggggtttt", "acgtcagtgtactgca"],
+    "all-gap, all-? and all-n columns between data": ["a-?na-c", "c-?nc-c", "g-?ng-t", "t-?nt-a"],
+    "ambiguity codes only": ["rynrynry", "yrnyrnyr", "nnnnnnnn"],
+    "gaps make equal columns unequal": ["aa-a", "cccc", "gg-g"],
+    "first occurrence order (later columns repeat earlier ones out of order)": ["gatcgatcctag", "gatcgatcctag", "ccccaaaagggg"],
+    "constant except for gaps and ambiguities": ["aaaaaa", "a-anra", "aa?ana", "aaaaya"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_ALIGNMENTS))
+def test_pattern_compression_edge_cases_vs_reference(pkg, ref_pf, name):
+    """Hand-made alignments at the edges of Pf/part.c:127-448 (makePatterns) and :716-848 (setGlobalInvarSitesVec): one column,
+    one pattern, no repeated pattern, columns of gaps / missing / fully ambiguous characters, columns that differ only by a gap."""
+    P = pkg
+    seqs = EDGE_ALIGNMENTS[name]
+    mine = P.host.Alignment(P.pf, seqs, P.host.DNA_SYMBOLS, P.host.DNA_EQUATES)._initParts()
+    theirs = P.host.Alignment(ref_pf, seqs, P.host.DNA_SYMBOLS, P.host.DNA_EQUATES)._initParts()
+    A, B = P.pf.partArrays(mine.cPart), ref_peek.part_arrays(theirs.cPart)
+    n = A["nPatterns"]
+    assert n == B["nPatterns"]
+    for k in ("sequences", "sequencePositionPatternIndex"):
+        assert np.array_equal(A[k], B[k]), k
+    assert np.array_equal(A["patternCounts"][:n], B["patternCounts"][:n])
+    assert np.array_equal(A["patterns"][:, :n], B["patterns"][:, :n])
+    assert np.array_equal(A["globalInvarSitesVec"][:n], B["globalInvarSitesVec"][:n])
+    assert np.array_equal(A["globalInvarSitesArray"][:, :n], B["globalInvarSitesArray"][:, :n])
+    assert int(A["patternCounts"][:n].sum()) == len(seqs[0])
+    P.pf.freePart(mine.cPart)
+    ref_pf.freePart(theirs.cPart)
+
+
 def test_unconstrained_loglike_vs_reference(pkg, ref_pf):
     """pf.getUnconstrainedLogLike (Pf/part.c:682-714): same number on clean data, fatal with any gap or ambiguity."""
     P = pkg
