@@ -36,3 +36,37 @@ def test_kernel_names_of_the_generator_match_the_engine():
     d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
     for e in d["entries"]:
         assert os.path.exists(os.path.join(ROOT, e["source"].split(" ")[0])), e["source"]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (rank 0 only; the reference's own Pf engine on the host cores) prints ONE JSON line with the
+    contract's keys, its `config` object equal to the one the B200 arm prints for the same arguments."""
+    import subprocess
+    import pytest
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    if not ref_loader.have_ref_pf():
+        pytest.skip("oracle/_ref not built")
+    args = ["--gpus", "1", "--steps", "2", "--warmup", "1", "--patterns", "4000", "--taxa", "12", "--cpu-sample", "256"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "reference"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    bench = _load("bench_under_test2", os.path.join(ROOT, "bench.py"))
+    sys.argv, keep = ["bench.py"] + args, sys.argv
+    try:
+        assert d["config"] == bench.bench_config(bench.parse())
+    finally:
+        sys.argv = keep
+    # under torchrun every other rank leaves without work and without a line
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"] + args, capture_output=True, text=True, timeout=60,
+                       env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and not r.stdout.strip()
