@@ -70,3 +70,31 @@ def test_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"] + args, capture_output=True, text=True, timeout=60,
                        env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and not r.stdout.strip()
+
+
+def test_clock_feed_cuts_samples_to_the_timed_region(monkeypatch):
+    """bench.py samples the SM clock and the throttle reasons from a process of its own and keeps the samples whose time stamps fall
+    inside a timed region; without NVML (here) the feed yields nothing and the in-process sampler's result stands."""
+    import time
+    bench = _load("bench_under_test3", os.path.join(ROOT, "bench.py"))
+    monkeypatch.setenv("P4B_BENCH_FAKE_CLOCKS", "1")
+    feed = bench.ClockFeed(0)
+    try:
+        time.sleep(0.4)
+        t0 = time.time()
+        time.sleep(0.25)
+        t1 = time.time()
+        w = feed.window(t0, t1)
+        assert w and 10 <= w["samples"] <= 60 and w["sm_mhz"] == 1800.0 and w["sm_max_mhz"] == 1965.0 and w["reasons"] == ["sw_power_cap"]
+        assert feed.window(t1 + 100, t1 + 200) is None
+        assert bench.better_clocks({"samples": 1, "sm_mhz": 1.0}, feed, t0, t1) == w
+        assert bench.better_clocks({"samples": 10 ** 6}, feed, t0, t1) == {"samples": 10 ** 6}
+    finally:
+        pid = feed.proc.pid
+        feed.close()
+    assert not os.path.exists("/proc/%d" % pid)
+    monkeypatch.delenv("P4B_BENCH_FAKE_CLOCKS")
+    dead = bench.ClockFeed(0)            # no NVML device here: the child exits at once
+    time.sleep(0.5)
+    assert dead.window(0, time.time() + 1) is None and bench.better_clocks({"samples": 1}, dead, 0, time.time()) == {"samples": 1}
+    dead.close()
