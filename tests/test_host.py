@@ -297,6 +297,35 @@ def test_q_and_eigensystem(pkg, name):
     tree.data.free()
 
 
+def test_every_empirical_protein_model_equals_the_reference(pkg, ref_pf):
+    """All eighteen empirical protein rate matrices (Pf/proteinModels.c through pf.getBigR, Pf/pfmodule.c:1270; p4/var.py:245-263) and
+    the normalised Q each of them gives with its own composition (Pf/p4_tree.c:340-450): bit-identical to the reference's."""
+    P, pf = pkg, pkg.pf
+    assert len(P.host.RMATRIX_PROTEIN_SPEC) == 18
+    for spec, code in sorted(P.host.RMATRIX_PROTEIN_SPEC.items(), key=lambda kv: kv[1]):
+        A, B = np.zeros((20, 20)), np.zeros((20, 20))
+        pf.getBigR(code, A)
+        ref_pf.getBigR(code, B)
+        assert np.array_equal(A, B) and np.array_equal(B, B.T) and B.max() > 0, spec
+        rng = np.random.Generator(np.random.PCG64(code))
+        tree = P.synth.random_tree(pf, 5, rng)
+        mp = P.synth.protein_model_part(0, rng, spec, 2)
+        aln = P.synth.make_alignment(pf, tree, mp, 20, rng, "protein")
+        tree.attach(P.host.Data(pf, [aln]), P.host.Model(pf, [mp]))
+        twin = P.host.clone_tree(tree, ref_pf)
+        twin.calcLogLike()                              # the reference builds its Q on the way (CPU)
+        tree.model.allocCStuff()
+        tree.model.setCStuff()
+        pf.p4_resetBQET(tree.model.cModel, 0, 0, 0)      # host side only: no device needed
+        pf.getBigQ(tree.model.cModel, 20, 0, 0, 0, A)
+        ref_pf.getBigQ(twin.model.cModel, 20, 0, 0, 0, B)
+        assert np.array_equal(A, B), spec
+        V, Vi, lam = pf.getEig(tree.model.cModel, 20, 0, 0, 0)
+        assert np.max(np.abs(V @ np.diag(lam) @ Vi - A)) < 5e-14 and np.max(np.abs(V @ Vi - np.eye(20))) < 5e-15, spec
+        tree.model.free()
+        tree.data.free()
+
+
 def test_fast_bindings_mirror_the_ctypes_wrappers(pkg):
     """csrc/pfhot.c: the METH_FASTCALL bindings of the per-node calls are installed over the ctypes wrappers and keep
     their contract: same names, arity checked, engine errors raise P4bFatal (no GPU needed: NULL handles)."""
