@@ -119,6 +119,33 @@ def test_pattern_compression_edge_cases_vs_reference(pkg, ref_pf, name):
     ref_pf.freePart(theirs.cPart)
 
 
+def test_pattern_compression_random_ragged_inputs_vs_reference(pkg, ref_pf):
+    """300 random alignments -- 1 to 8 taxa, 1 to 400 columns, DNA and protein, drawn from small random subsets of the symbols, gaps,
+    missing and every equate (so columns repeat heavily, in any order) -- compressed by this engine's hashed makePatterns and by the
+    reference's scan (Pf/part.c:127-448): every array identical."""
+    P = pkg
+    rng = np.random.default_rng(11)
+    for it in range(300):
+        sym, eq = (P.host.DNA_SYMBOLS, P.host.DNA_EQUATES) if it % 3 else (P.host.PROTEIN_SYMBOLS, P.host.PROTEIN_EQUATES)
+        alphabet = list(sym + "-?" + "".join(sorted(eq)))
+        nTax, nChar = int(rng.integers(1, 9)), int(rng.integers(1, 400))
+        letters = rng.choice(alphabet, size=int(rng.integers(1, len(alphabet) + 1)), replace=False)
+        seqs = ["".join(rng.choice(letters, size=nChar)) for _ in range(nTax)]
+        mine = P.host.Alignment(P.pf, seqs, sym, eq)._initParts()
+        theirs = P.host.Alignment(ref_pf, seqs, sym, eq)._initParts()
+        A, B = P.pf.partArrays(mine.cPart), ref_peek.part_arrays(theirs.cPart)
+        n = A["nPatterns"]
+        assert n == B["nPatterns"], (it, seqs)
+        for k in ("sequences", "sequencePositionPatternIndex"):
+            assert np.array_equal(A[k], B[k]), (it, k, seqs)
+        for k in ("patternCounts", "globalInvarSitesVec"):
+            assert np.array_equal(A[k][:n], B[k][:n]), (it, k, seqs)
+        for k in ("patterns", "globalInvarSitesArray"):
+            assert np.array_equal(A[k][:, :n], B[k][:, :n]), (it, k, seqs)
+        P.pf.freePart(mine.cPart)
+        ref_pf.freePart(theirs.cPart)
+
+
 def test_unconstrained_loglike_vs_reference(pkg, ref_pf):
     """pf.getUnconstrainedLogLike (Pf/part.c:682-714): same number on clean data, fatal with any gap or ambiguity."""
     P = pkg
@@ -244,6 +271,13 @@ def test_gamma_rates_bit_identical_to_reference(pkg, ref_pf):
             pkg.pf.gdasrvCalcRates_np(K, alpha, f1, r1)
             ref_pf.gdasrvCalcRates_np(K, alpha, f2, r2)
             assert np.array_equal(r1, r2) and np.array_equal(f1, f2), (alpha, K)
+    rng = np.random.default_rng(5)              # and 1000 random shapes between 0.001 and 300, 2 to 12 categories
+    for _ in range(1000):
+        alpha, K = float(np.exp(rng.uniform(np.log(1e-3), np.log(300.0)))), int(rng.integers(2, 13))
+        f1, r1, f2, r2 = np.zeros(K), np.zeros(K), np.zeros(K), np.zeros(K)
+        pkg.pf.gdasrvCalcRates_np(K, alpha, f1, r1)
+        ref_pf.gdasrvCalcRates_np(K, alpha, f2, r2)
+        assert np.array_equal(r1, r2) and np.array_equal(f1, f2), (alpha, K)
 
 
 def _expm_longdouble(Q, t):
