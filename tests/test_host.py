@@ -360,6 +360,43 @@ def test_every_empirical_protein_model_equals_the_reference(pkg, ref_pf):
         tree.data.free()
 
 
+def test_q_and_eigensystem_on_skewed_models_of_every_size(pkg, ref_pf):
+    """Sixty random models with 2 to 61 states, frequencies down to 1e-7 and exchangeabilities down to 1e-9: Q bit-identical to the
+    reference's, and P(t) = V exp(lambda t) V^-1 from this engine's eigensystem (symmetric Jacobi, csrc/model.cpp) never further from
+    exp(Qt) (80-bit Taylor) than 10x the error of the reference's own P decks (EISPACK general, Pf/eig.c:63-161)."""
+    P, pf = pkg, pkg.pf
+    syms = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"
+    rng = np.random.default_rng(3)
+    for it in range(60):
+        dim = int(rng.choice([2, 3, 4, 4, 5, 6, 11, 20, 21, 33, 61]))
+        tree = P.synth.build_generic(pf, syms[:dim], 4, 12, 1, 1000 + it)
+        mp = tree.model.parts[0]
+        v = np.maximum(rng.dirichlet(float(rng.choice([0.05, 0.3, 1.0])) * np.ones(dim)), 1e-7)
+        mp.comps[0].val[:] = P.synth.normalise_comp(v)
+        r = np.maximum(rng.dirichlet(float(rng.choice([0.1, 1.0, 5.0])) * np.ones(dim * (dim - 1) // 2)), 1e-9)
+        mp.rMatrices[0].val[:] = r / r.sum()
+        twin = P.host.clone_tree(tree, ref_pf)
+        twin.calcLogLike()
+        tree.model.allocCStuff()
+        tree.model.setCStuff()
+        pf.p4_resetBQET(tree.model.cModel, 0, 0, 0)
+        Q, Qref = np.zeros((dim, dim)), np.zeros((dim, dim))
+        pf.getBigQ(tree.model.cModel, dim, 0, 0, 0, Q)
+        ref_pf.getBigQ(twin.model.cModel, dim, 0, 0, 0, Qref)
+        assert np.array_equal(Q, Qref), (it, dim)
+        V, Vi, lam = pf.getEig(tree.model.cModel, dim, 0, 0, 0)
+        mine = theirs = 0.0
+        for a, b in zip(tree.nodes, twin.nodes):
+            if a is tree.root:
+                continue
+            truth = _expm_longdouble(Q, a.br.len)
+            mine = max(mine, float(np.max(np.abs((V * np.exp(lam * a.br.len)[None, :]) @ Vi - truth))))
+            theirs = max(theirs, float(np.max(np.abs(ref_peek.node_bigP(b.cNode, 0, 1, dim)[0] - truth))))
+        assert mine <= max(10.0 * theirs, 5e-14), (it, dim, mine, theirs)
+        tree.model.free()
+        tree.data.free()
+
+
 def test_fast_bindings_mirror_the_ctypes_wrappers(pkg):
     """csrc/pfhot.c: the METH_FASTCALL bindings of the per-node calls are installed over the ctypes wrappers and keep
     their contract: same names, arity checked, engine errors raise P4bFatal (no GPU needed: NULL handles)."""
